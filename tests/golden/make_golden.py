@@ -1,0 +1,453 @@
+"""Generate golden fixtures from the REFERENCE itself (jkomijani/normflow_).
+
+Run in the build container only (needs /root/reference, which does not exist on
+the GPU box):
+
+    python tests/golden/make_golden.py
+
+The reference is pure Python; it is imported from /root/reference/src through a
+temporary symlink named `normflow_ref`, with the `np.product` shim numpy>=2 needs
+(header table).  It runs on CPU in its default float64.  Inputs are
+drawn in float32 and widened, so the CUDA tests can feed bit-identical values.
+The outputs land in tests/golden/*.npz (committed).  Nothing at test/bench time
+reads /root/reference.
+"""
+
+import os
+import sys
+import tempfile
+import warnings
+
+import numpy as np
+
+warnings.filterwarnings("ignore")
+np.product = np.prod  # removed in numpy 2; the reference still calls it
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_tmp = tempfile.mkdtemp()
+os.symlink("/root/reference/src", os.path.join(_tmp, "normflow_ref"))
+sys.path.insert(0, _tmp)
+
+import torch  # noqa: E402
+import normflow_ref as nf  # noqa: E402  (sets default dtype float64)
+from normflow_ref.mask import EvenOddMask, AlongAxesEvenOddMask  # noqa: E402
+from normflow_ref.action import ScalarPhi4Action  # noqa: E402
+from normflow_ref.prior import NormalPrior  # noqa: E402
+from normflow_ref.nn import (ModuleList_, ConvAct, AffineCoupling_, ShiftCoupling_,  # noqa: E402
+                             RQSplineCoupling_, DistConvertor_)
+from normflow_ref.lib.spline import RQSpline  # noqa: E402
+from normflow_ref.mcmc.mcmc import Metropolis, MCMCSampler  # noqa: E402
+from normflow_ref import Model  # noqa: E402
+
+assert torch.get_default_dtype() == torch.float64
+
+ACTION = dict(kappa=0.67, m_sq=-4 * 0.67, lambd=0.5)
+
+
+def f32(t):
+    """Round to float32-representable values, keep float64 storage."""
+    return t.float().double()
+
+
+def randn32(*shape, seed):
+    g = torch.Generator('cpu').manual_seed(seed)
+    return torch.randn(*shape, generator=g, dtype=torch.float32).double()
+
+
+def npy(t):
+    if not torch.is_tensor(t):   # e.g. ShiftCoupling_ hands log0=0 through untouched
+        return np.asarray(t, dtype=np.float64)
+    return t.detach().cpu().numpy()
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print(f"wrote {path}  ({os.path.getsize(path) / 1024:.1f} KiB)")
+
+
+def round_params(module):
+    for p in module.parameters():
+        p.data = f32(p.data)
+
+
+# -----------------------------------------------------------------------------
+def gen_masks():
+    out = {}
+    cases = [((4, 4), 0, None), ((4, 4), 1, None), ((1,), 0, None), ((5,), 1, None),
+             ((3, 5), 0, None), ((4, 6), 0, 1), ((4, 4, 4), 1, None), ((2, 3, 4), 0, 0),
+             ((3, 2, 2, 3), 0, None), ((4, 4, 4, 4), 1, 3)]
+    for i, (shape, parity, mu) in enumerate(cases):
+        m = EvenOddMask(shape=shape, parity=parity, exclude_mu=mu)
+        out[f"eo_{i}_mask"] = npy(m._mask)
+        out[f"eo_{i}_cmask"] = npy(m._c_mask)
+        out[f"eo_{i}_meta"] = np.array([parity, -1 if mu is None else mu] + list(shape))
+    for i, (shape, parity, mu) in enumerate([((4, 6), 0, 0), ((4, 6), 1, 1), ((3, 4, 5), 0, 2)]):
+        m = AlongAxesEvenOddMask(shape=shape, parity=parity, mu=mu)
+        out[f"aa_{i}_mask"] = npy(m._mask)
+        out[f"aa_{i}_meta"] = np.array([parity, mu] + list(shape))
+    save("masks", **out)
+
+
+def gen_action():
+    out = {}
+    for i, shape in enumerate([(1,), (2,), (7,), (8, 8), (5, 6), (4, 4, 4), (3, 4, 5), (4, 4, 4, 4), (2, 3, 2, 3)]):
+        cfgs = randn32(6, *shape, seed=100 + i).requires_grad_(True)
+        act = ScalarPhi4Action(**ACTION)
+        S = act(cfgs)
+        w = randn32(6, seed=200 + i)
+        (g,) = torch.autograd.grad((S * w).sum(), cfgs)
+        out[f"a{i}_cfgs"] = npy(cfgs)
+        out[f"a{i}_S"] = npy(S)
+        out[f"a{i}_density"] = npy(act.action_density(cfgs))
+        out[f"a{i}_gS"] = npy(w)
+        out[f"a{i}_gcfgs"] = npy(g)
+    # zero-dim config-1 action (kappa=0)
+    cfgs = randn32(128, 1, seed=31)
+    out["zd_cfgs"] = npy(cfgs)
+    out["zd_S"] = npy(ScalarPhi4Action(kappa=0, m_sq=-1.2, lambd=0.5)(cfgs))
+    # a != 1
+    cfgs = randn32(3, 4, 4, seed=32)
+    out["lat_cfgs"] = npy(cfgs)
+    out["lat_S"] = npy(ScalarPhi4Action(kappa=0.5, m_sq=0.3, lambd=0.2, a=0.5)(cfgs))
+    save("action", **out)
+
+
+def gen_prior():
+    out = {}
+    x = randn32(5, 4, 6, seed=41)
+    prior = NormalPrior(shape=(4, 6))
+    out["std_x"], out["std_logr"] = npy(x), npy(prior.log_prob(x))
+    loc = f32(randn32(4, 6, seed=42) * 0.3)
+    scale = f32(torch.rand(4, 6, generator=torch.Generator('cpu').manual_seed(43)) + 0.5)
+    prior = NormalPrior(loc=loc, scale=scale)
+    out["gen_x"], out["gen_loc"], out["gen_scale"] = npy(x), npy(loc), npy(scale)
+    out["gen_logr"] = npy(prior.log_prob(x))
+    save("prior", **out)
+
+
+def gen_spline():
+    """RQSpline with explicit knots along axis 1, all extrapolation modes."""
+    out = {}
+    B, K, V = 3, 6, 40
+    g = torch.Generator('cpu').manual_seed(51)
+    wx = torch.rand(B, K - 1, V, generator=g) + 0.2
+    wy = torch.rand(B, K - 1, V, generator=g) + 0.2
+    kx = f32(torch.cat([torch.zeros(B, 1, V), torch.cumsum(wx / wx.sum(1, keepdim=True), 1)], 1) * 2 - 1)
+    ky = f32(torch.cat([torch.zeros(B, 1, V), torch.cumsum(wy / wy.sum(1, keepdim=True), 1)], 1) * 3 - 1.5)
+    kd = f32(torch.rand(B, K, V, generator=g) * 1.5 + 0.25)
+    x = f32((torch.rand(B, 1, V, generator=g) * 4 - 2))   # covers outside [-1, 1]
+    # put a few points exactly on knots (searchsorted right=False edge)
+    x[0, 0, :K] = kx[0, :, 0]
+    kx[0, :, :K] = kx[0, :, :1]
+    out.update(kx=npy(kx), ky=npy(ky), kd=npy(kd), x=npy(x))
+    modes = {"none": {}, "lin": dict(left='linear', right='linear'),
+             "linleft": dict(left='linear'), "linright": dict(right='linear'),
+             "antileft": dict(left='anti'), "antiright": dict(right='anti'),
+             "antilin": dict(left='anti', right='linear')}
+    for name, extrap in modes.items():
+        sp = RQSpline(knots_x=kx, knots_y=ky, knots_d=kd, knots_axis=1, extrap=extrap)
+        y, gr = sp(x, grad=True)
+        out[f"{name}_y"], out[f"{name}_g"] = npy(y), npy(gr)
+        out[f"{name}_nknots"] = np.array(sp.knots_x.shape[1])
+        # inverse evaluated on the forward image (in-range by construction)
+        xi, gi = sp.backward(y, grad=True)
+        out[f"{name}_xinv"], out[f"{name}_ginv"] = npy(xi), npy(gi)
+    # smooth derivatives, 1-D shared knots, anti-left (the DistConvertor_ smooth case)
+    k1x, k1y = kx[1, :, 3].contiguous(), ky[1, :, 3].contiguous()
+    sp = RQSpline(knots_x=k1x, knots_y=k1y, knots_d=None, extrap=dict(left='anti'))
+    xs = f32(torch.rand(200, generator=g) * 5 - 3.5)
+    ys, gs = sp(xs, grad=True)
+    out.update(s1_kx=npy(k1x), s1_ky=npy(k1y), s1_x=npy(xs), s1_y=npy(ys), s1_g=npy(gs),
+               s1_kd=npy(sp.knots_d), s1_kxaug=npy(sp.knots_x))
+    save("spline", **out)
+
+
+def conv_layers(net):
+    """Export ConvAct weights in standard (Co, Ci, *k) shape."""
+    ws = {}
+    i = 0
+    for m in net:
+        if hasattr(m, "weight") and not isinstance(m, (torch.nn.Tanh,)):
+            ws[f"w{i}"] = npy(m.weight)
+            if getattr(m, "bias", None) is not None:
+                ws[f"b{i}"] = npy(m.bias)
+            if hasattr(m, "_conv_lower_dim"):
+                ws[f"wlower{i}"] = npy(m._conv_lower_dim.weight)
+            i += 1
+    return ws
+
+
+def gen_coupling(name, shape, B, blocks, seed, hidden=(8, 8), bias=False, acts=None):
+    """blocks: list of ('affine'|'shift'|'rqs', n_steps).  Records every block's
+    output (ModuleList_.hack), the inverse, and reference-autograd gradients of
+    loss = mean(logr - logJ + S) w.r.t. x and every parameter."""
+    torch.manual_seed(seed)
+    nd = len(shape)
+    K = 10
+    if acts is None:
+        acts = (*['tanh'] * len(hidden), None)
+    mask = EvenOddMask(shape=shape)
+    nets_, meta = [], []
+    for kind, n_steps in blocks:
+        P = {'affine': 2, 'shift': 1, 'rqs': 3 * K - 2}[kind]
+        nets = [ConvAct(1, P, 3, conv_dim=nd, hidden_sizes=list(hidden), acts=acts, bias=bias)
+                for _ in range(n_steps)]
+        for n in nets:
+            round_params(n)
+        if kind == 'affine':
+            nets_.append(AffineCoupling_(nets, mask=mask))
+        elif kind == 'shift':
+            nets_.append(ShiftCoupling_(nets, mask=mask))
+        else:
+            nets_.append(RQSplineCoupling_(nets, mask=mask, xlim=(-5, 5), ylim=(-5, 5),
+                                           extrap=dict(left='linear', right='linear')))
+        meta.append((kind, n_steps))
+    net_ = ModuleList_(nets_)
+    x = randn32(B, *shape, seed=seed + 1)
+    if any(k == 'rqs' for k, _ in blocks):
+        x = x * 2.0   # push a few sites outside xlim so linear extrapolation is hit
+        x = f32(x)
+    x.requires_grad_(True)
+    prior = NormalPrior(shape=shape)
+    action = ScalarPhi4Action(**ACTION)
+    out = dict(x=npy(x), shape=np.array(shape), mask=npy(mask._mask))
+    stack = net_.hack(x, log0=0)
+    for i, (xi, li) in enumerate(stack[1:]):
+        out[f"blk{i}_y"], out[f"blk{i}_logJ"] = npy(xi), npy(li)
+    y, logJ = stack[-1]
+    if not torch.is_tensor(logJ):
+        logJ = torch.zeros(B) + logJ
+    logr = prior.log_prob(x)
+    S = action(y)
+    loss = (logr - logJ + S).mean()
+    params = list(net_.parameters())
+    grads = torch.autograd.grad(loss, [x] + params)
+    out.update(y=npy(y), logJ=npy(logJ), logr=npy(logr), S=npy(S), loss=npy(loss), gx=npy(grads[0]))
+    # weights + grads, addressed as blk{i}_step{k}_{w,b}{layer}
+    gi = 1
+    for bi, cpl in enumerate(net_):
+        for k, net in enumerate(cpl.nets):
+            for key, val in conv_layers(net).items():
+                out[f"blk{bi}_step{k}_{key}"] = val
+            for pname, p in net.named_parameters():
+                out[f"blk{bi}_step{k}_grad_{pname}"] = npy(grads[gi])
+                gi += 1
+    assert gi == len(grads)
+    # per-step conditioner outputs for the first block (kernel-only parity)
+    with torch.no_grad():
+        cpl = net_[0]
+        parts = list(cpl.mask.split(x))
+        for k, net in enumerate(cpl.nets):
+            p = k % 2
+            o = net(parts[1 - p].unsqueeze(1))
+            out[f"blk0_step{k}_out"] = npy(o)
+            out[f"blk0_step{k}_xactive"] = npy(parts[p])
+            parts[p], _ = cpl.atomic_forward(x_active=parts[p], x_frozen=parts[1 - p],
+                                             parity=p, net=net, log0=0)
+            out[f"blk0_step{k}_fx"] = npy(parts[p])
+        # inverse of the whole flow
+        xb, lb = net_.backward(y.detach(), log0=logJ.detach())
+        out["inv_x"], out["inv_log"] = npy(xb), npy(lb)
+    out["blocks"] = np.array([f"{k}:{n}" for k, n in meta])
+    out["hidden"] = np.array(hidden)
+    out["acts"] = np.array(['none' if a is None else a for a in acts])
+    save(name, **out)
+
+
+def gen_rqs_kernel_only():
+    """Kernel-only parity for one RQS atomic step: explicit conditioner output
+    `out = 0.5 randn`, forward values + reference-autograd gradients
+    w.r.t. x_active and out for random upstream weights; plus the inverse."""
+    res = {}
+    for tag, shape, B, extrap in [("lin", (8, 8), 3, dict(left='linear', right='linear')),
+                                  ("none", (6,), 4, {}),
+                                  ("mixed", (4, 4, 4), 2, dict(left='linear'))]:
+        K = 10
+        mask = EvenOddMask(shape=shape)
+        cpl = RQSplineCoupling_([torch.nn.Identity()], mask=mask, xlim=(-5, 5), ylim=(-4, 6),
+                                extrap=extrap)
+        x = f32(randn32(B, *shape, seed=61) * 2.5)
+        out_raw = f32(randn32(B, 3 * K - 2, *shape, seed=4321) * 0.5)
+        for parity in (0, 1):
+            xa = cpl.mask.purify(x, parity).clone().requires_grad_(True)
+            o = out_raw.clone().requires_grad_(True)
+            sp = cpl.make_spline(o)
+            fx, g = sp(xa.unsqueeze(1), grad=True)
+            fx, g = fx.squeeze(1), g.squeeze(1)
+            fx = cpl.mask.purify(fx, parity)
+            logJ = cpl.sum_density(cpl.mask.purify(torch.log(g), parity))
+            r = randn32(B, *shape, seed=62)
+            c = randn32(B, seed=63)
+            L = (fx * r).sum() + (logJ * c).sum()
+            gxa, go = torch.autograd.grad(L, [xa, o])
+            xi, gi = sp.backward(fx.detach().unsqueeze(1), grad=True)
+            res.update({f"{tag}_p{parity}_fx": npy(fx), f"{tag}_p{parity}_logJ": npy(logJ),
+                        f"{tag}_p{parity}_gx": npy(gxa), f"{tag}_p{parity}_gout": npy(go),
+                        f"{tag}_p{parity}_xinv": npy(cpl.mask.purify(xi.squeeze(1), parity)),
+                        f"{tag}_p{parity}_loginv": npy(cpl.sum_density(
+                            cpl.mask.purify(torch.log(gi.squeeze(1)), parity)))})
+        res.update({f"{tag}_x": npy(x), f"{tag}_out": npy(out_raw), f"{tag}_r": npy(r),
+                    f"{tag}_c": npy(c), f"{tag}_mask": npy(mask._mask)})
+    save("rqs_kernel", **res)
+
+
+def gen_affine_kernel_only():
+    res = {}
+    shape, B = (8, 8), 3
+    mask = EvenOddMask(shape=shape)
+    cpl = AffineCoupling_([torch.nn.Identity()], mask=mask)
+    x = randn32(B, *shape, seed=71)
+    out_raw = f32(randn32(B, 2, *shape, seed=72) * 0.7)
+    r, c = randn32(B, *shape, seed=73), randn32(B, seed=74)
+    for parity in (0, 1):
+        xa = cpl.mask.purify(x, parity).clone().requires_grad_(True)
+        o = out_raw.clone().requires_grad_(True)
+        fx, logJ = cpl.atomic_forward(x_active=xa, x_frozen=x, parity=parity,
+                                      net=lambda _: o, log0=0)
+        L = (fx * r).sum() + (logJ * c).sum()
+        gxa, go = torch.autograd.grad(L, [xa, o])
+        xi, li = cpl.atomic_backward(x_active=fx.detach(), x_frozen=x, parity=parity,
+                                     net=lambda _: o.detach(), log0=0)
+        res.update({f"p{parity}_fx": npy(fx), f"p{parity}_logJ": npy(logJ), f"p{parity}_gx": npy(gxa),
+                    f"p{parity}_gout": npy(go), f"p{parity}_xinv": npy(xi), f"p{parity}_loginv": npy(li)})
+    res.update(x=npy(x), out=npy(out_raw), r=npy(r), c=npy(c), mask=npy(mask._mask))
+    save("affine_kernel", **res)
+
+
+def gen_distconv():
+    res = {}
+    for tag, kw, shape, B in [("zd_sym", dict(symmetric=True), (1,), 128),
+                              ("lat_sym_smooth", dict(symmetric=True, smooth=True), (4, 4), 6),
+                              ("lat_asym", dict(symmetric=False), (6,), 9)]:
+        torch.manual_seed(81)
+        K = 10
+        net_ = DistConvertor_(K, **kw)
+        for p in net_.parameters():
+            p.data = f32(torch.randn_like(p) * 0.5)
+        x = randn32(B, *shape, seed=82)
+        if tag == "lat_asym":
+            x = f32(x * 3.0)   # reach the tails: |x| up to ~9
+        x.requires_grad_(True)
+        y, logJ = net_(x)
+        r, c = randn32(B, *shape, seed=83), randn32(B, seed=84)
+        L = (y * r).sum() + (logJ * c).sum()
+        params = list(net_.parameters())
+        grads = torch.autograd.grad(L, [x] + params)
+        with torch.no_grad():
+            xb, lb = net_.backward(y.detach(), log0=logJ.detach())
+        sp = net_.spline_layer_
+        res.update({f"{tag}_x": npy(x), f"{tag}_y": npy(y), f"{tag}_logJ": npy(logJ),
+                    f"{tag}_r": npy(r), f"{tag}_c": npy(c), f"{tag}_gx": npy(grads[0]),
+                    f"{tag}_inv_x": npy(xb), f"{tag}_inv_log": npy(lb),
+                    f"{tag}_wx": npy(sp.weights_x), f"{tag}_wy": npy(sp.weights_y)})
+        names = [n for n, _ in net_.named_parameters()]
+        for n, gval in zip(names, grads[1:]):
+            res[f"{tag}_grad_{n}"] = npy(gval)
+        if sp.weights_d is not None:
+            res[f"{tag}_wd"] = npy(sp.weights_d)
+        res[f"{tag}_param_names"] = np.array(names)
+    save("distconv", **res)
+
+
+def gen_mcmc():
+    res = {}
+    rng = np.random.RandomState(5)
+    logqp = rng.randn(64).astype(np.float32).astype(np.float64) * 0.8
+    np.random.seed(7)
+    res["u_first"] = np.random.rand(64)
+    np.random.seed(7)
+    st = Metropolis.calc_accept_status(logqp)
+    res.update(logqp=logqp, status_noref=st, ind_noref=Metropolis.calc_accept_indices(st))
+    np.random.seed(8)
+    res["u_second"] = np.random.rand(64)
+    np.random.seed(8)
+    st = Metropolis.calc_accept_status(logqp, logqp_ref=-0.3)
+    res.update(status_ref=st, ind_ref=Metropolis.calc_accept_indices(st), ref=np.array(-0.3))
+
+    # two consecutive MCMCSampler._accept_reject_step calls (chain state carried over)
+    class _M:  # minimal stand-in for Model: _accept_reject_step never touches it
+        pass
+    sampler = MCMCSampler(_M())
+    for call in range(2):
+        y = randn32(16, 4, 4, seed=90 + call)
+        logq = randn32(16, seed=92 + call)
+        logp = f32(logq + randn32(16, seed=94 + call) * 0.7)
+        np.random.seed(100 + call)
+        u = np.random.rand(16)
+        np.random.seed(100 + call)
+        yo, lqo, lpo = sampler._accept_reject_step(y.clone(), logq.clone(), logp.clone())
+        res.update({f"c{call}_y": npy(y), f"c{call}_logq": npy(logq), f"c{call}_logp": npy(logp),
+                    f"c{call}_u": u, f"c{call}_yo": npy(yo), f"c{call}_logqo": npy(lqo),
+                    f"c{call}_logpo": npy(lpo),
+                    f"c{call}_accept_rate": np.array(sampler.history.accept_rate[-1])})
+    save("mcmc", **res)
+
+
+def gen_conv():
+    """Circular ConvAct stacks alone, every supported dimension (conv parity),
+    including Conv4d in its stored (lower-dim) weight layout and a biased one."""
+    res = {}
+    for tag, shape, hidden, P, bias in [("d1", (9,), (4,), 3, True), ("d2", (6, 5), (8, 8), 28, False),
+                                        ("d3", (4, 3, 5), (4,), 2, True), ("d4", (3, 4, 3, 4), (3,), 2, True)]:
+        torch.manual_seed(111)
+        nd = len(shape)
+        net = ConvAct(1, P, 3, conv_dim=nd, hidden_sizes=list(hidden),
+                      acts=(*['tanh'] * len(hidden), None), bias=bias)
+        round_params(net)
+        x = randn32(2, 1, *shape, seed=112).requires_grad_(True)
+        o = net(x)
+        r = randn32(*o.shape, seed=113)
+        grads = torch.autograd.grad((o * r).sum(), [x] + list(net.parameters()))
+        res.update({f"{tag}_x": npy(x), f"{tag}_out": npy(o), f"{tag}_r": npy(r), f"{tag}_gx": npy(grads[0])})
+        for key, val in conv_layers(net).items():
+            res[f"{tag}_{key}"] = val
+        for (pname, _), gval in zip(net.named_parameters(), grads[1:]):
+            res[f"{tag}_grad_{pname}"] = npy(gval)
+        res[f"{tag}_hidden"] = np.array(hidden)
+    save("conv", **res)
+
+
+def gen_model_zero_dim():
+    """Config 1 end to end: posterior.sample__ with the prior draw pinned, and
+    one Fitter-style loss + gradient."""
+    torch.manual_seed(121)
+    net_ = DistConvertor_(10, symmetric=True)
+    for p in net_.parameters():
+        p.data = f32(torch.randn_like(p) * 0.3)
+    prior = NormalPrior(shape=1)
+    action = ScalarPhi4Action(kappa=0, m_sq=-1.2, lambd=0.5)
+    model = Model(net_=net_, prior=prior, action=action)
+    x = randn32(128, 1, seed=122)
+    logr = prior.log_prob(x)
+    y, logJ = net_(x)
+    logq = logr - logJ
+    logp = -action(y)
+    loss = model.fit.calc_kl_mean(logq, logp)
+    grads = torch.autograd.grad(loss, list(net_.parameters()))
+    res = dict(x=npy(x), y=npy(y), logq=npy(logq), logp=npy(logp), loss=npy(loss))
+    for (n, p), gval in zip(net_.named_parameters(), grads):
+        res[f"w_{n}"] = npy(p)
+        res[f"g_{n}"] = npy(gval)
+    save("model_zero_dim", **res)
+
+
+if __name__ == "__main__":
+    gen_masks()
+    gen_action()
+    gen_prior()
+    gen_spline()
+    gen_rqs_kernel_only()
+    gen_affine_kernel_only()
+    gen_distconv()
+    gen_mcmc()
+    gen_conv()
+    gen_model_zero_dim()
+    # whole coupling stacks: config-2 style (affine), config-3 style (rqs), 1-D shift,
+    # 3-D mixed (config-4 style), 4-D with Conv4d (config-5 style)
+    gen_coupling("cpl_affine_2d", (8, 8), 4, [("affine", 4)], seed=10)
+    gen_coupling("cpl_rqs_2d", (8, 8), 3, [("rqs", 4)], seed=20)
+    gen_coupling("cpl_shift_1d", (10,), 4, [("shift", 2)], seed=30, hidden=(4,), bias=True)
+    gen_coupling("cpl_mixed_3d", (4, 4, 4), 2, [("affine", 2), ("rqs", 2)], seed=40, hidden=(4, 4))
+    gen_coupling("cpl_mixed_4d", (4, 4, 4, 4), 2, [("affine", 2), ("rqs", 2)], seed=50, hidden=(4,),
+                 bias=True)
