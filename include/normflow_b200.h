@@ -1,0 +1,222 @@
+/*
+ * normflow_b200.h -- C ABI of libnormflow_b200.so
+ *
+ * Hand-written sm_100a CUDA kernels for the data-parallel hot path of
+ * jkomijani/normflow_ (Model.fit / posterior.sample / mcmc.sample inner loop).
+ *
+ * The reference is 100 % Python on PyTorch ops and defines NO FFI / plugin
+ * interface; the drop-in boundary is its duck-typed Python
+ * protocol, which normflow__b200/ mirrors.  This header is the native layer under
+ * that mirror: every entry point cites the reference call site (file:line under
+ * /root/reference/src) whose ATen operator sequence it replaces.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types.
+ *   - All data pointers are DEVICE pointers to contiguous arrays, float32 unless
+ *     stated (uint8 masks, int64 indices, float64 Metropolis inputs).
+ *   - `stream` is a cudaStream_t passed as void*; kernels are enqueued on it and
+ *     the call returns immediately (no host sync, no allocation; CUDA-graph
+ *     capturable).  The caller owns every buffer.
+ *   - Return value: 0 on success, a negative NFK_E* code otherwise
+ *     (nfk_strerror).  Nothing throws.
+ *   - Field layout: x[B][V] with V = prod(lattice shape), row-major sites.
+ *     Conditioner output: out[B][P][V] (channel-major per sample, NCHW-like).
+ *   - mask: uint8[V]; mask[s] = 1 <=> site s belongs to partition 0
+ *     (Mask._mask, mask/mask.py:23).  A coupling step with `parity` p updates the
+ *     sites with mask[s] == (p == 0 ? 1 : 0)  (couplings_.py:56-64).
+ *   - frozen_mode: what the step writes at the frozen (non-updated) sites:
+ *       NFK_FROZEN_ZERO  (0)  y = 0      -- the reference's x_active -> fx_active
+ *                                           dataflow (atomic_forward)
+ *       NFK_FROZEN_COPY  (1)  y = x      -- full-field update (split/cat fused away)
+ *   - log_in may be NULL (treated as zeros); log_out[b] = log_in[b] + sum_sites(...).
+ */
+#ifndef NORMFLOW_B200_H
+#define NORMFLOW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NFK_OK            0
+#define NFK_EINVAL       -1   /* bad argument (null pointer, unsupported size)  */
+#define NFK_EUNSUPPORTED -2   /* combination not implemented                     */
+#define NFK_ECUDA        -3   /* CUDA runtime reported an error at launch        */
+
+#define NFK_FROZEN_ZERO 0
+#define NFK_FROZEN_COPY 1
+
+/* spline extrapolation modes (lib/spline/spline.py:415-432) */
+#define NFK_EXTRAP_NONE   0   /* first / last segment extended                   */
+#define NFK_EXTRAP_LINEAR 1   /* straight line with the end-knot derivative      */
+#define NFK_EXTRAP_ANTI   2   /* point mirror about the end knot                 */
+
+/* activations of the ConvAct conditioner (nn/scalar/modules.py:43-54) */
+#define NFK_ACT_NONE       0
+#define NFK_ACT_TANH       1
+#define NFK_ACT_RELU       2
+#define NFK_ACT_LEAKY_RELU 3
+#define NFK_ACT_SOFTPLUS   4
+#define NFK_ACT_ABS        5
+
+#define NFK_MAX_DIM   4
+#define NFK_MAX_KNOTS 64
+
+/* Lattice geometry: ndim in 1..4, shape[d] = extent (unused entries = 1). */
+typedef struct {
+    int32_t ndim;
+    int32_t shape[NFK_MAX_DIM];
+} nfk_lattice;
+
+/* Parameters of a rational-quadratic coupling spline
+ * (RQSplineCoupling_.__init__, nn/scalar/couplings_.py:159-176). */
+typedef struct {
+    int32_t n_knots;        /* K; conditioner emits P = 3K-2 channels            */
+    float   xlim0, xlim1;   /* xlim                                              */
+    float   ylim0, ylim1;   /* ylim                                              */
+    int32_t extrap_left;    /* NFK_EXTRAP_NONE | NFK_EXTRAP_LINEAR               */
+    int32_t extrap_right;
+} nfk_rqs_params;
+
+const char* nfk_strerror(int code);
+int nfk_version(void);
+/* number of kernel launches issued by this library since load (bench "gpu_launches") */
+uint64_t nfk_launch_count(void);
+
+/* ---------------------------------------------------------------- masks ----
+ * EvenOddMask.make_mask (mask/mask.py:53-61): mask[ind] = (1 - parity + sum(ind)
+ * [- ind[exclude_mu]]) mod 2; exclude_mu < 0 means none.
+ * AlongAxesEvenOddMask.make_mask (mask/mask.py:64-72): (1 - parity + ind[mu]) mod 2.
+ * Integer work; bit-exact with the reference.                                   */
+int nfk_mask_evenodd(uint8_t* mask, nfk_lattice lat, int parity, int exclude_mu, void* stream);
+int nfk_mask_alongaxis(uint8_t* mask, nfk_lattice lat, int parity, int mu, void* stream);
+/* Mask.split / purify (mask/mask.py:30-37): y[b][s] = mask[s]==keep ? x[b][s] : 0 */
+int nfk_mask_select(const float* x, const uint8_t* mask, int keep, float* y,
+                    int64_t B, int64_t V, void* stream);
+
+/* ---------------------------------------------------------------- prior ----
+ * NormalPrior.sample_ (prior/prior.py:26-28, 92-104): x = loc + scale * N(0,1)
+ * (Philox4x32-10 counter RNG + Box-Muller, stream (seed, offset)), and
+ * Prior.log_prob (prior/prior.py:30-36): logr[b] = sum_s( -(x-loc)^2/(2 scale^2)
+ * - log scale - log sqrt(2 pi) ).  loc / scale: float[V] or NULL (0 / 1).       */
+int nfk_prior_normal_sample(float* x, float* logr, int64_t B, int64_t V,
+                            const float* loc, const float* scale,
+                            uint64_t seed, uint64_t offset, void* stream);
+int nfk_prior_normal_logprob(const float* x, float* logr, int64_t B, int64_t V,
+                             const float* loc, const float* scale, void* stream);
+
+/* -------------------------------------------------------------- couplings --
+ * AffineCoupling_.atomic_forward / atomic_backward (couplings_.py:123-139):
+ *   out[B][2][V] -> t, s = |s| at active sites;
+ *   fwd: y = t + x e^{-s}, log_out = log_in - sum s ; inv: y = (x - t) e^{s}, + sum s.
+ * _bwd is the vector-Jacobian product of _fwd: given gy[B][V] and glog[B]
+ * (NULL = 0) it writes gx[B][V] and gout[B][2][V] (zeros at frozen sites).      */
+int nfk_affine_fwd(const float* x, const float* out, const uint8_t* mask, int parity,
+                   int frozen_mode, const float* log_in, float* y, float* log_out,
+                   int64_t B, int64_t V, void* stream);
+int nfk_affine_inv(const float* x, const float* out, const uint8_t* mask, int parity,
+                   int frozen_mode, const float* log_in, float* y, float* log_out,
+                   int64_t B, int64_t V, void* stream);
+int nfk_affine_bwd(const float* x, const float* out, const uint8_t* mask, int parity,
+                   int frozen_mode, const float* gy, const float* glog,
+                   float* gx, float* gout, int64_t B, int64_t V, void* stream);
+
+/* ShiftCoupling_.atomic_forward / atomic_backward (couplings_.py:110-116):
+ *   out[B][1][V]; y = x + sign * t at active sites (sign = +1 fwd, -1 inv).     */
+int nfk_shift_apply(const float* x, const float* out, const uint8_t* mask, int parity,
+                    int frozen_mode, float sign, float* y, int64_t B, int64_t V, void* stream);
+
+/* RQSplineCoupling_.atomic_forward / atomic_backward + make_spline
+ * (couplings_.py:178-262) + RQSpline (lib/spline/spline.py:39-123, 154-287,
+ * 458-486): out[B][3K-2][V] -> knots by softmax/cumsum/softplus(beta=ln2), bin
+ * search (searchsorted right=False + clamp), Pade[2,2] value and derivative,
+ * log|dy/dx| summed over active sites.  _inv uses the numerically stable root.
+ * _bwd: VJP of _fwd (gx[B][V], gout[B][3K-2][V]).                               */
+int nfk_rqs_fwd(const float* x, const float* out, const uint8_t* mask, int parity,
+                int frozen_mode, nfk_rqs_params prm, const float* log_in,
+                float* y, float* log_out, int64_t B, int64_t V, void* stream);
+int nfk_rqs_inv(const float* x, const float* out, const uint8_t* mask, int parity,
+                int frozen_mode, nfk_rqs_params prm, const float* log_in,
+                float* y, float* log_out, int64_t B, int64_t V, void* stream);
+int nfk_rqs_bwd(const float* x, const float* out, const uint8_t* mask, int parity,
+                int frozen_mode, nfk_rqs_params prm, const float* gy, const float* glog,
+                float* gx, float* gout, int64_t B, int64_t V, void* stream);
+
+/* ------------------------------------------------- pointwise spline chain --
+ * SplineNet_ / DistConvertor_ (nn/scalar/modules_.py:93-114, 277-302, 333-383):
+ * one shared 1-D spline with explicit knots kx, ky, kd (float[K], device) applied
+ * to every element; logistic != 0 wraps it as Expit_ -> spline -> Logit_ (the
+ * DistConvertor_ chain) evaluated in complement form so the tails keep fp32
+ * relative accuracy.  inverse != 0 evaluates ModuleList_.backward of the chain.
+ * _bwd: VJP of the forward direction: gx[B][V] and gkx, gky, gkd (float[K],
+ * ACCUMULATED with atomics: zero them first).                                   */
+int nfk_spline1d_fwd(const float* x, const float* kx, const float* ky, const float* kd,
+                     int K, int extrap_left, int extrap_right, int logistic, int inverse,
+                     const float* log_in, float* y, float* log_out,
+                     int64_t B, int64_t V, void* stream);
+int nfk_spline1d_bwd(const float* x, const float* kx, const float* ky, const float* kd,
+                     int K, int extrap_left, int extrap_right, int logistic,
+                     const float* gy, const float* glog,
+                     float* gx, float* gkx, float* gky, float* gkd,
+                     int64_t B, int64_t V, void* stream);
+/* Expit_ / Logit_ alone (modules_.py:93-114); which = 0 expit, 1 logit.         */
+int nfk_logistic_fwd(const float* x, int which, const float* log_in, float* y, float* log_out,
+                     int64_t B, int64_t V, void* stream);
+int nfk_logistic_bwd(const float* x, int which, const float* gy, const float* glog, float* gx,
+                     int64_t B, int64_t V, void* stream);
+
+/* --------------------------------------------------------------- action ----
+ * ScalarPhi4Action.action (action/scalar_action.py:38-46):
+ *   S[b] = sum_x (w2 phi^2 + w4 phi^4) - w0 sum_mu sum_x phi(x) phi(x - mu)  (periodic)
+ * _bwd: gphi = gS[b] (2 w2 phi + 4 w4 phi^3 - w0 sum_mu (phi(x+mu) + phi(x-mu))). */
+int nfk_phi4_action_fwd(const float* phi, nfk_lattice lat, float w0, float w2, float w4,
+                        float* S, int64_t B, void* stream);
+int nfk_phi4_action_bwd(const float* phi, nfk_lattice lat, float w0, float w2, float w4,
+                        const float* gS, float* gphi, int64_t B, void* stream);
+
+/* ------------------------------------------------------------ conditioner --
+ * One layer of ConvAct (nn/scalar/modules.py:131-145): Conv{1,2,3}d / Conv4d
+ * (convNd.py:84-127) with padding='same', padding_mode='circular', odd kernel
+ * size ksize in every direction, fused activation.
+ *   in[B][Ci][V], w[Co][Ci][ksize^ndim] (standard layout), bias[Co] or NULL,
+ *   out[B][Co][V] = act(bias + sum w * in(shifted, periodic)).
+ * in_mask != NULL: the input is read as (in_mask[s]==in_keep ? in : 0), i.e.
+ * Mask.split fused into the first layer (couplings_.py:88-89).
+ * dact_from != NULL (backward use): out is multiplied by act'(.) evaluated from
+ * the saved post-activation tensor dact_from[B][Co][V] with activation dact_kind. */
+int nfk_conv_circ_fwd(const float* in, const float* w, const float* bias,
+                      const uint8_t* in_mask, int in_keep,
+                      int act, const float* dact_from, int dact_kind,
+                      float* out, nfk_lattice lat, int ksize,
+                      int Ci, int Co, int64_t B, void* stream);
+/* gw[Co][Ci][ksize^ndim] += sum_{b,s} gpre[b][co][s] * in[b][ci][s + tap]  and
+ * gbias[Co] += sum gpre (gbias may be NULL).  ACCUMULATES with atomics.         */
+int nfk_conv_circ_bwd_weight(const float* in, const uint8_t* in_mask, int in_keep,
+                             const float* gpre, float* gw, float* gbias,
+                             nfk_lattice lat, int ksize, int Ci, int Co, int64_t B, void* stream);
+
+/* ----------------------------------------------------------------- mcmc ----
+ * Metropolis.calc_accept_status + calc_accept_indices (mcmc/mcmc.py:304-328),
+ * sequential independence-Metropolis scan on the device (one warp):
+ *   accept[i] = log_u[i] < ref - l[i];  on accept ref <- l[i]
+ * logq, logp float32[B] (l = logq - logp formed in float64); log_u float64[B] =
+ * np.log(np.random.rand(B)) drawn and logged on the HOST exactly as the reference
+ * does (mcmc.py:312), so decisions match it bit for bit given the same seed;
+ * ref_inout float64[2] = {ref, has_ref} is the chain state carried across calls
+ * (MCMCSampler._ref['logqp'], mcmc.py:21,77-81); accept uint8[B]; idx int64[B] =
+ * index of the last accepted proposal <= i, or -1 while none has been accepted
+ * yet (the caller substitutes the previous call's last sample, mcmc.py:67-68);
+ * n_accept int64[1] (may be NULL) = number of acceptances.                       */
+int nfk_metropolis_scan(const float* logq, const float* logp, const double* log_u,
+                        double* ref_inout, uint8_t* accept, int64_t* idx, int64_t* n_accept,
+                        int64_t B, void* stream);
+/* index_select(0, idx) (mcmc.py:73-75): dst[i][:] = idx[i] >= 0 ? src[idx[i]][:] :
+ * prev[:]  (prev may be NULL when no idx is negative).                          */
+int nfk_gather_rows(const float* src, const int64_t* idx, const float* prev, float* dst,
+                    int64_t B, int64_t row_elems, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NORMFLOW_B200_H */

@@ -1,0 +1,385 @@
+// nfk_kernels.cu -- C-ABI entry points for the pointwise / per-sample kernels:
+// masks, prior, affine / shift / RQ-spline couplings, shared 1-D spline chain
+// (DistConvertor_), phi^4 action, Metropolis scan, row gather.
+// Target: sm_100a (B200).  See include/normflow_b200.h for the contract.
+
+#include "nfk_common.cuh"
+
+namespace nfk {
+unsigned long long g_launches = 0;
+}
+using namespace nfk;
+
+#define NFK_STREAM(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" const char* nfk_strerror(int code) {
+    switch (code) {
+        case NFK_OK: return "ok";
+        case NFK_EINVAL: return "invalid argument";
+        case NFK_EUNSUPPORTED: return "unsupported configuration";
+        case NFK_ECUDA: return "CUDA launch error";
+        default: return "unknown error";
+    }
+}
+extern "C" int nfk_version(void) { return 100; }
+extern "C" uint64_t nfk_launch_count(void) { return g_launches; }
+
+// ============================================================== masks
+__global__ void mask_kernel(uint8_t* mask, Lat lat, int V, int parity, int mu, int along) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= V) return;
+    mask[s] = along ? alongaxis_bit(lat, s, parity, mu) : evenodd_bit(lat, s, parity, mu);
+}
+extern "C" int nfk_mask_evenodd(uint8_t* mask, nfk_lattice lat, int parity, int exclude_mu, void* stream) {
+    if (!mask || !lat_ok(lat) || exclude_mu >= lat.ndim) return NFK_EINVAL;
+    const int V = (int)lat_volume(lat);
+    mask_kernel<<<(V + 255) / 256, 256, 0, NFK_STREAM(stream)>>>(mask, to_lat(lat), V, parity,
+                                                                exclude_mu < 0 ? -1 : exclude_mu, 0);
+    return check_launch();
+}
+extern "C" int nfk_mask_alongaxis(uint8_t* mask, nfk_lattice lat, int parity, int mu, void* stream) {
+    if (!mask || !lat_ok(lat) || mu < 0 || mu >= lat.ndim) return NFK_EINVAL;
+    const int V = (int)lat_volume(lat);
+    mask_kernel<<<(V + 255) / 256, 256, 0, NFK_STREAM(stream)>>>(mask, to_lat(lat), V, parity, mu, 1);
+    return check_launch();
+}
+extern "C" int nfk_mask_select(const float* x, const uint8_t* mask, int keep, float* y,
+                               int64_t B, int64_t V, void* stream) {
+    if (!x || !mask || !y) return NFK_EINVAL;
+    return launch_sites(MaskSelectOp{x, mask, keep, y, V}, B, V, nullptr, nullptr, NFK_STREAM(stream));
+}
+
+// ============================================================== prior
+extern "C" int nfk_prior_normal_sample(float* x, float* logr, int64_t B, int64_t V,
+                                       const float* loc, const float* scale,
+                                       uint64_t seed, uint64_t offset, void* stream) {
+    if (!x) return NFK_EINVAL;
+    return launch_sites_vec<PriorSampleOp, 4>(PriorSampleOp{x, loc, scale, V, seed, offset}, B, V,
+                                              nullptr, logr, NFK_STREAM(stream));
+}
+extern "C" int nfk_prior_normal_logprob(const float* x, float* logr, int64_t B, int64_t V,
+                                        const float* loc, const float* scale, void* stream) {
+    if (!x || !logr) return NFK_EINVAL;
+    return launch_sites(PriorLogProbOp{x, loc, scale, V}, B, V, nullptr, logr, NFK_STREAM(stream));
+}
+
+// ============================================================== affine / shift
+extern "C" int nfk_affine_fwd(const float* x, const float* out, const uint8_t* mask, int parity,
+                              int frozen_mode, const float* log_in, float* y, float* log_out,
+                              int64_t B, int64_t V, void* stream) {
+    if (!x || !out || !mask || !y) return NFK_EINVAL;
+    return launch_sites(AffineOp<0>{x, out, mask, parity == 0 ? 1 : 0, frozen_mode, y, V}, B, V, log_in,
+                        log_out, NFK_STREAM(stream));
+}
+extern "C" int nfk_affine_inv(const float* x, const float* out, const uint8_t* mask, int parity,
+                              int frozen_mode, const float* log_in, float* y, float* log_out,
+                              int64_t B, int64_t V, void* stream) {
+    if (!x || !out || !mask || !y) return NFK_EINVAL;
+    return launch_sites(AffineOp<1>{x, out, mask, parity == 0 ? 1 : 0, frozen_mode, y, V}, B, V, log_in,
+                        log_out, NFK_STREAM(stream));
+}
+extern "C" int nfk_affine_bwd(const float* x, const float* out, const uint8_t* mask, int parity,
+                              int frozen_mode, const float* gy, const float* glog,
+                              float* gx, float* gout, int64_t B, int64_t V, void* stream) {
+    if (!x || !out || !mask || !gy || !gx || !gout) return NFK_EINVAL;
+    return launch_sites(AffineBwdOp{x, out, mask, parity == 0 ? 1 : 0, frozen_mode, gy, glog, gx, gout, V},
+                        B, V, nullptr, nullptr, NFK_STREAM(stream));
+}
+extern "C" int nfk_shift_apply(const float* x, const float* out, const uint8_t* mask, int parity,
+                               int frozen_mode, float sign, float* y, int64_t B, int64_t V, void* stream) {
+    if (!x || !out || !mask || !y) return NFK_EINVAL;
+    return launch_sites(ShiftOp{x, out, mask, parity == 0 ? 1 : 0, frozen_mode, sign, y, V}, B, V, nullptr,
+                        nullptr, NFK_STREAM(stream));
+}
+
+// ============================================================== RQ-spline coupling
+static bool rqs_cfg(const nfk_rqs_params& p, RqsCfg& c) {
+    if (p.n_knots < 2 || !(p.xlim1 > p.xlim0) || !(p.ylim1 > p.ylim0)) return false;
+    if (p.extrap_left != NFK_EXTRAP_NONE && p.extrap_left != NFK_EXTRAP_LINEAR) return false;
+    if (p.extrap_right != NFK_EXTRAP_NONE && p.extrap_right != NFK_EXTRAP_LINEAR) return false;
+    c.xlim0 = p.xlim0; c.xw = p.xlim1 - p.xlim0;
+    c.ylim0 = p.ylim0; c.yw = p.ylim1 - p.ylim0;
+    c.left = p.extrap_left; c.right = p.extrap_right;
+    return true;
+}
+
+// the knot count is a template parameter (per-site knot arrays live in registers)
+#define NFK_FOR_EACH_K(X) \
+    X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(14) X(16) X(20) X(24) X(32)
+
+template <int MODE>
+static int rqs_apply(const float* x, const float* out, const uint8_t* mask, int parity, int frozen_mode,
+                     nfk_rqs_params prm, const float* log_in, float* y, float* log_out,
+                     int64_t B, int64_t V, cudaStream_t st) {
+    RqsCfg cfg;
+    if (!x || !out || !mask || !y) return NFK_EINVAL;
+    if (!rqs_cfg(prm, cfg)) return NFK_EINVAL;
+    const int av = parity == 0 ? 1 : 0;
+    switch (prm.n_knots) {
+#define X(KK) case KK: return launch_sites(RqsOp<KK, MODE>{x, out, mask, av, frozen_mode, cfg, y, V}, B, V, log_in, log_out, st);
+        NFK_FOR_EACH_K(X)
+#undef X
+        default: return NFK_EUNSUPPORTED;
+    }
+}
+extern "C" int nfk_rqs_fwd(const float* x, const float* out, const uint8_t* mask, int parity,
+                           int frozen_mode, nfk_rqs_params prm, const float* log_in,
+                           float* y, float* log_out, int64_t B, int64_t V, void* stream) {
+    return rqs_apply<0>(x, out, mask, parity, frozen_mode, prm, log_in, y, log_out, B, V, NFK_STREAM(stream));
+}
+extern "C" int nfk_rqs_inv(const float* x, const float* out, const uint8_t* mask, int parity,
+                           int frozen_mode, nfk_rqs_params prm, const float* log_in,
+                           float* y, float* log_out, int64_t B, int64_t V, void* stream) {
+    return rqs_apply<1>(x, out, mask, parity, frozen_mode, prm, log_in, y, log_out, B, V, NFK_STREAM(stream));
+}
+extern "C" int nfk_rqs_bwd(const float* x, const float* out, const uint8_t* mask, int parity,
+                           int frozen_mode, nfk_rqs_params prm, const float* gy, const float* glog,
+                           float* gx, float* gout, int64_t B, int64_t V, void* stream) {
+    RqsCfg cfg;
+    if (!x || !out || !mask || !gy || !gx || !gout) return NFK_EINVAL;
+    if (!rqs_cfg(prm, cfg)) return NFK_EINVAL;
+    const int av = parity == 0 ? 1 : 0;
+    switch (prm.n_knots) {
+#define X(KK) case KK: return launch_sites(RqsBwdOp<KK>{x, out, mask, av, frozen_mode, cfg, gy, glog, gx, gout, V}, B, V, nullptr, nullptr, NFK_STREAM(stream));
+        NFK_FOR_EACH_K(X)
+#undef X
+        default: return NFK_EUNSUPPORTED;
+    }
+}
+
+// ============================================================== Expit_ / Logit_
+extern "C" int nfk_logistic_fwd(const float* x, int which, const float* log_in, float* y, float* log_out,
+                                int64_t B, int64_t V, void* stream) {
+    if (!x || !y || (which != 0 && which != 1)) return NFK_EINVAL;
+    return launch_sites(LogisticOp{x, which, y, V}, B, V, log_in, log_out, NFK_STREAM(stream));
+}
+extern "C" int nfk_logistic_bwd(const float* x, int which, const float* gy, const float* glog, float* gx,
+                                int64_t B, int64_t V, void* stream) {
+    if (!x || !gy || !gx || (which != 0 && which != 1)) return NFK_EINVAL;
+    return launch_sites(LogisticBwdOp{x, which, gy, glog, gx, V}, B, V, nullptr, nullptr, NFK_STREAM(stream));
+}
+
+// ============================================================== shared 1-D spline chain
+// The knots (3K floats) are staged in shared memory by every CTA; elements are
+// walked grid-stride over the flattened [B*V] array when V is tiny, else with the
+// per-sample plan so the log-Jacobian reduces without atomics.
+struct SplineArgs {
+    const float *x, *kx, *ky, *kd;
+    Spline1dCfg cfg;
+    int inverse;
+    const float *gy, *glog;
+    float *y, *gx, *gk;     // gk: global [3K] accumulation (backward)
+    const float* log_in;
+    float* log_out;
+    int64_t B, V;
+    int chunks;
+    int64_t chunk_len;
+};
+
+template <bool BWD, bool SMALL>
+__global__ void __launch_bounds__(256) spline1d_kernel(SplineArgs a) {
+    __shared__ float knots[3 * NFK_MAX_KNOTS];
+    __shared__ float gacc[3 * NFK_MAX_KNOTS];
+    const int K = a.cfg.K;
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+        knots[i] = a.kx[i];
+        knots[K + i] = a.ky[i];
+        knots[2 * K + i] = a.kd[i];
+    }
+    if (BWD)
+        for (int i = threadIdx.x; i < 3 * K; i += blockDim.x) gacc[i] = 0.f;
+    __syncthreads();
+    const float *kx = knots, *ky = knots + K, *kd = knots + 2 * K;
+
+    if (SMALL) {            // one thread per sample
+        const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (b < a.B) {
+            float acc = 0.f;
+            for (int64_t s = 0; s < a.V; ++s) {
+                if (BWD) Spline1dBwdOp{a.x, kx, ky, kd, a.cfg, a.gy, a.glog, a.gx, gacc, a.V}(b, s);
+                else acc += Spline1dOp{a.x, kx, ky, kd, a.cfg, a.inverse, a.y, a.V}(b, s);
+            }
+            if (!BWD && a.log_out) a.log_out[b] = (a.log_in ? a.log_in[b] : 0.f) + acc;
+        }
+    } else {
+        const int64_t b = blockIdx.x / a.chunks;
+        const int chunk = (int)(blockIdx.x % a.chunks);
+        const int64_t s0 = chunk * a.chunk_len;
+        const int64_t s1 = s0 + a.chunk_len < a.V ? s0 + a.chunk_len : a.V;
+        float acc = 0.f;
+        for (int64_t s = s0 + threadIdx.x; s < s1; s += blockDim.x) {
+            if (BWD) Spline1dBwdOp{a.x, kx, ky, kd, a.cfg, a.gy, a.glog, a.gx, gacc, a.V}(b, s);
+            else acc += Spline1dOp{a.x, kx, ky, kd, a.cfg, a.inverse, a.y, a.V}(b, s);
+        }
+        if (!BWD && a.log_out) {
+            acc = block_sum(acc);
+            if (threadIdx.x == 0) {
+                if (a.chunks == 1) a.log_out[b] = (a.log_in ? a.log_in[b] : 0.f) + acc;
+                else atomicAdd(a.log_out + b, acc);
+            }
+        }
+    }
+    if (BWD) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 3 * K; i += blockDim.x)
+            if (gacc[i] != 0.f) atomicAdd(a.gk + i, gacc[i]);
+    }
+}
+
+static bool spline_cfg(int K, int left, int right, int logistic, Spline1dCfg& c) {
+    if (K < 2 || K > NFK_MAX_KNOTS) return false;
+    if (left < 0 || left > 2 || right < 0 || right > 2) return false;
+    if (logistic && (right != NFK_EXTRAP_NONE || left == NFK_EXTRAP_LINEAR)) return false;
+    c.K = K; c.left = left; c.right = right; c.logistic = logistic;
+    return true;
+}
+
+template <bool BWD>
+static int spline1d_launch(SplineArgs a, cudaStream_t st) {
+    if (a.B <= 0 || a.V <= 0) return NFK_OK;
+    const Plan p = make_plan(a.V, 1);
+    a.chunks = p.chunks;
+    a.chunk_len = p.chunk_len;
+    if (p.small) {
+        spline1d_kernel<BWD, true><<<(unsigned)((a.B + 127) / 128), 128, 0, st>>>(a);
+        return check_launch();
+    }
+    if (!BWD && p.chunks > 1 && a.log_out) {
+        init_log_kernel<<<(unsigned)((a.B + 255) / 256), 256, 0, st>>>(a.log_in, a.log_out, a.B);
+        if (int e = check_launch()) return e;
+    }
+    spline1d_kernel<BWD, false><<<(unsigned)(a.B * p.chunks), p.threads, 0, st>>>(a);
+    return check_launch();
+}
+
+extern "C" int nfk_spline1d_fwd(const float* x, const float* kx, const float* ky, const float* kd,
+                                int K, int extrap_left, int extrap_right, int logistic, int inverse,
+                                const float* log_in, float* y, float* log_out,
+                                int64_t B, int64_t V, void* stream) {
+    SplineArgs a{};
+    if (!x || !kx || !ky || !kd || !y) return NFK_EINVAL;
+    if (!spline_cfg(K, extrap_left, extrap_right, logistic, a.cfg)) return NFK_EINVAL;
+    a.x = x; a.kx = kx; a.ky = ky; a.kd = kd; a.inverse = inverse;
+    a.y = y; a.log_in = log_in; a.log_out = log_out; a.B = B; a.V = V;
+    return spline1d_launch<false>(a, NFK_STREAM(stream));
+}
+extern "C" int nfk_spline1d_bwd(const float* x, const float* kx, const float* ky, const float* kd,
+                                int K, int extrap_left, int extrap_right, int logistic,
+                                const float* gy, const float* glog,
+                                float* gx, float* gkx, float* gky, float* gkd,
+                                int64_t B, int64_t V, void* stream) {
+    SplineArgs a{};
+    if (!x || !kx || !ky || !kd || !gy || !gx || !gkx) return NFK_EINVAL;
+    // the three knot gradients must be one contiguous [3K] buffer: gkx | gky | gkd
+    if (gky != gkx + K || gkd != gkx + 2 * K) return NFK_EINVAL;
+    if (!spline_cfg(K, extrap_left, extrap_right, logistic, a.cfg)) return NFK_EINVAL;
+    a.x = x; a.kx = kx; a.ky = ky; a.kd = kd; a.gy = gy; a.glog = glog;
+    a.gx = gx; a.gk = gkx; a.B = B; a.V = V;
+    return spline1d_launch<true>(a, NFK_STREAM(stream));
+}
+
+// ============================================================== phi^4 action
+extern "C" int nfk_phi4_action_fwd(const float* phi, nfk_lattice lat, float w0, float w2, float w4,
+                                   float* S, int64_t B, void* stream) {
+    if (!phi || !S || !lat_ok(lat)) return NFK_EINVAL;
+    const int64_t V = lat_volume(lat);
+    return launch_sites(Phi4Op{phi, to_lat(lat), w0, w2, w4, V}, B, V, nullptr, S, NFK_STREAM(stream));
+}
+extern "C" int nfk_phi4_action_bwd(const float* phi, nfk_lattice lat, float w0, float w2, float w4,
+                                   const float* gS, float* gphi, int64_t B, void* stream) {
+    if (!phi || !gS || !gphi || !lat_ok(lat)) return NFK_EINVAL;
+    const int64_t V = lat_volume(lat);
+    return launch_sites(Phi4BwdOp{phi, to_lat(lat), w0, w2, w4, gS, gphi, V}, B, V, nullptr, nullptr,
+                        NFK_STREAM(stream));
+}
+
+// ============================================================== Metropolis scan
+// One warp.  The chain is sequential, but its inputs are not: the lanes stream
+// l = logq - logp and log u into shared memory 32 at a time (double precision,
+// mcmc.py:64 hands float64 to numpy), lane 0 walks the 32 decisions, and the
+// lanes then publish accept flags / indices coalesced.
+__global__ void metropolis_kernel(const float* logq, const float* logp, const double* log_u,
+                                  double* ref_inout, uint8_t* accept, int64_t* idx, int64_t* n_accept,
+                                  int64_t B) {
+    __shared__ double sl[32], su[32];
+    __shared__ uint8_t sa[32];
+    __shared__ int64_t si[32];
+    const int lane = threadIdx.x;
+    double ref = ref_inout[0];
+    bool has_ref = ref_inout[1] != 0.0;
+    int64_t last = -1, count = 0;
+    for (int64_t base = 0; base < B; base += 32) {
+        const int64_t i = base + lane;
+        if (i < B) {
+            sl[lane] = (double)logq[i] - (double)logp[i];
+            su[lane] = log_u[i];
+        }
+        __syncwarp();
+        if (lane == 0) {
+            const int n = B - base < 32 ? (int)(B - base) : 32;
+            for (int k = 0; k < n; ++k) {
+                const double l = sl[k];
+                if (!has_ref) { ref = l; has_ref = true; }      // mcmc.py:308-309
+                const bool acc = su[k] < ref - l;               // mcmc.py:313
+                if (acc) { ref = l; last = base + k; ++count; }
+                sa[k] = acc;
+                si[k] = last;
+            }
+        }
+        __syncwarp();
+        if (i < B) {
+            accept[i] = sa[lane];
+            idx[i] = si[lane];
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        ref_inout[0] = ref;
+        ref_inout[1] = has_ref ? 1.0 : 0.0;
+        if (n_accept) *n_accept = count;
+    }
+}
+extern "C" int nfk_metropolis_scan(const float* logq, const float* logp, const double* log_u,
+                                   double* ref_inout, uint8_t* accept, int64_t* idx, int64_t* n_accept,
+                                   int64_t B, void* stream) {
+    if (!logq || !logp || !log_u || !ref_inout || !accept || !idx) return NFK_EINVAL;
+    if (B <= 0) return NFK_OK;
+    metropolis_kernel<<<1, 32, 0, NFK_STREAM(stream)>>>(logq, logp, log_u, ref_inout, accept, idx, n_accept, B);
+    return check_launch();
+}
+
+// ============================================================== row gather
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* src, const int64_t* idx, const float* prev,
+                                                          float* dst, int64_t row, int vec_ok) {
+    const int64_t i = blockIdx.x;
+    const int64_t j = idx[i];
+    const float* from = j >= 0 ? src + j * row : prev;
+    float* to = dst + i * row;
+    if (vec_ok) {
+        const float4* f4 = reinterpret_cast<const float4*>(from);
+        float4* t4 = reinterpret_cast<float4*>(to);
+        for (int64_t k = threadIdx.x; k < row / 4; k += blockDim.x) t4[k] = f4[k];
+    } else {
+        for (int64_t k = threadIdx.x; k < row; k += blockDim.x) to[k] = from[k];
+    }
+}
+__global__ void gather_scalar_kernel(const float* src, const int64_t* idx, const float* prev, float* dst, int64_t B) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const int64_t j = idx[i];
+    dst[i] = j >= 0 ? src[j] : prev[0];
+}
+extern "C" int nfk_gather_rows(const float* src, const int64_t* idx, const float* prev, float* dst,
+                               int64_t B, int64_t row_elems, void* stream) {
+    if (!src || !idx || !dst || row_elems < 1) return NFK_EINVAL;
+    if (B <= 0) return NFK_OK;
+    if (row_elems == 1) {
+        gather_scalar_kernel<<<(unsigned)((B + 255) / 256), 256, 0, NFK_STREAM(stream)>>>(src, idx, prev, dst, B);
+        return check_launch();
+    }
+    const bool aligned = ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0) &&
+                         (prev == nullptr || (uintptr_t)prev % 16 == 0) && row_elems % 4 == 0;
+    const int threads = row_elems >= 1024 ? 256 : (row_elems >= 256 ? 64 : 32);
+    gather_rows_kernel<<<(unsigned)B, threads, 0, NFK_STREAM(stream)>>>(src, idx, prev, dst, row_elems, aligned ? 1 : 0);
+    return check_launch();
+}

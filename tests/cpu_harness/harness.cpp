@@ -1,0 +1,196 @@
+// tests/cpu_harness/harness.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Compiles the very same per-site functors the CUDA kernels use
+// (normflow__b200/csrc/nfk_ops.cuh, nfk_math.cuh) with g++ and drives them with a
+// plain host loop, so the fp32 arithmetic and the indexing can be checked against
+// the oracle on a machine without a GPU.  It mirrors the C ABI with a `cpu_`
+// prefix.  The product never loads this library.
+
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../include/normflow_b200.h"
+#include "../../normflow__b200/csrc/nfk_ops.cuh"
+
+using namespace nfk;
+
+template <class Op>
+static void run_sites(const Op& op, int64_t B, int64_t V, const float* log_in, float* log_out) {
+    for (int64_t b = 0; b < B; ++b) {
+        float acc = 0.f;
+        for (int64_t s = 0; s < V; ++s) acc += op(b, s);
+        if (log_out) log_out[b] = (log_in ? log_in[b] : 0.f) + acc;
+    }
+}
+
+static RqsCfg to_cfg(const nfk_rqs_params& p) {
+    RqsCfg c;
+    c.xlim0 = p.xlim0; c.xw = p.xlim1 - p.xlim0;
+    c.ylim0 = p.ylim0; c.yw = p.ylim1 - p.ylim0;
+    c.left = p.extrap_left; c.right = p.extrap_right;
+    return c;
+}
+
+#define FOR_EACH_K(X) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(14) X(16) X(20) X(24) X(32)
+
+extern "C" {
+
+int cpu_mask_evenodd(uint8_t* mask, nfk_lattice lat, int parity, int exclude_mu) {
+    const Lat l = make_lat(lat.ndim, lat.shape);
+    int V = 1;
+    for (int d = 0; d < lat.ndim; ++d) V *= lat.shape[d];
+    for (int s = 0; s < V; ++s) mask[s] = evenodd_bit(l, s, parity, exclude_mu < 0 ? -1 : exclude_mu);
+    return 0;
+}
+int cpu_mask_alongaxis(uint8_t* mask, nfk_lattice lat, int parity, int mu) {
+    const Lat l = make_lat(lat.ndim, lat.shape);
+    int V = 1;
+    for (int d = 0; d < lat.ndim; ++d) V *= lat.shape[d];
+    for (int s = 0; s < V; ++s) mask[s] = alongaxis_bit(l, s, parity, mu);
+    return 0;
+}
+int cpu_mask_select(const float* x, const uint8_t* mask, int keep, float* y, int64_t B, int64_t V) {
+    run_sites(MaskSelectOp{x, mask, keep, y, V}, B, V, nullptr, nullptr);
+    return 0;
+}
+int cpu_prior_normal_sample(float* x, float* logr, int64_t B, int64_t V, const float* loc,
+                            const float* scale, uint64_t seed, uint64_t offset) {
+    const PriorSampleOp op{x, loc, scale, V, seed, offset};
+    for (int64_t b = 0; b < B; ++b) {
+        float acc = 0.f;
+        for (int64_t s = 0; s < V; s += 4) acc += op(b, s, V - s < 4 ? (int)(V - s) : 4);
+        if (logr) logr[b] = acc;
+    }
+    return 0;
+}
+int cpu_prior_normal_logprob(const float* x, float* logr, int64_t B, int64_t V, const float* loc,
+                             const float* scale) {
+    run_sites(PriorLogProbOp{x, loc, scale, V}, B, V, nullptr, logr);
+    return 0;
+}
+int cpu_affine_fwd(const float* x, const float* out, const uint8_t* mask, int parity, int frozen_mode,
+                   const float* log_in, float* y, float* log_out, int64_t B, int64_t V) {
+    run_sites(AffineOp<0>{x, out, mask, parity == 0 ? 1 : 0, frozen_mode, y, V}, B, V, log_in, log_out);
+    return 0;
+}
+int cpu_affine_inv(const float* x, const float* out, const uint8_t* mask, int parity, int frozen_mode,
+                   const float* log_in, float* y, float* log_out, int64_t B, int64_t V) {
+    run_sites(AffineOp<1>{x, out, mask, parity == 0 ? 1 : 0, frozen_mode, y, V}, B, V, log_in, log_out);
+    return 0;
+}
+int cpu_affine_bwd(const float* x, const float* out, const uint8_t* mask, int parity, int frozen_mode,
+                   const float* gy, const float* glog, float* gx, float* gout, int64_t B, int64_t V) {
+    run_sites(AffineBwdOp{x, out, mask, parity == 0 ? 1 : 0, frozen_mode, gy, glog, gx, gout, V}, B, V,
+              nullptr, nullptr);
+    return 0;
+}
+int cpu_shift_apply(const float* x, const float* out, const uint8_t* mask, int parity, int frozen_mode,
+                    float sign, float* y, int64_t B, int64_t V) {
+    run_sites(ShiftOp{x, out, mask, parity == 0 ? 1 : 0, frozen_mode, sign, y, V}, B, V, nullptr, nullptr);
+    return 0;
+}
+int cpu_rqs_fwd(const float* x, const float* out, const uint8_t* mask, int parity, int frozen_mode,
+                nfk_rqs_params prm, const float* log_in, float* y, float* log_out, int64_t B, int64_t V) {
+    const RqsCfg cfg = to_cfg(prm);
+    const int av = parity == 0 ? 1 : 0;
+    switch (prm.n_knots) {
+#define X(KK) case KK: run_sites(RqsOp<KK, 0>{x, out, mask, av, frozen_mode, cfg, y, V}, B, V, log_in, log_out); return 0;
+        FOR_EACH_K(X)
+#undef X
+    }
+    return NFK_EUNSUPPORTED;
+}
+int cpu_rqs_inv(const float* x, const float* out, const uint8_t* mask, int parity, int frozen_mode,
+                nfk_rqs_params prm, const float* log_in, float* y, float* log_out, int64_t B, int64_t V) {
+    const RqsCfg cfg = to_cfg(prm);
+    const int av = parity == 0 ? 1 : 0;
+    switch (prm.n_knots) {
+#define X(KK) case KK: run_sites(RqsOp<KK, 1>{x, out, mask, av, frozen_mode, cfg, y, V}, B, V, log_in, log_out); return 0;
+        FOR_EACH_K(X)
+#undef X
+    }
+    return NFK_EUNSUPPORTED;
+}
+int cpu_rqs_bwd(const float* x, const float* out, const uint8_t* mask, int parity, int frozen_mode,
+                nfk_rqs_params prm, const float* gy, const float* glog, float* gx, float* gout,
+                int64_t B, int64_t V) {
+    const RqsCfg cfg = to_cfg(prm);
+    const int av = parity == 0 ? 1 : 0;
+    switch (prm.n_knots) {
+#define X(KK) case KK: run_sites(RqsBwdOp<KK>{x, out, mask, av, frozen_mode, cfg, gy, glog, gx, gout, V}, B, V, nullptr, nullptr); return 0;
+        FOR_EACH_K(X)
+#undef X
+    }
+    return NFK_EUNSUPPORTED;
+}
+int cpu_logistic_fwd(const float* x, int which, const float* log_in, float* y, float* log_out,
+                     int64_t B, int64_t V) {
+    run_sites(LogisticOp{x, which, y, V}, B, V, log_in, log_out);
+    return 0;
+}
+int cpu_logistic_bwd(const float* x, int which, const float* gy, const float* glog, float* gx,
+                     int64_t B, int64_t V) {
+    run_sites(LogisticBwdOp{x, which, gy, glog, gx, V}, B, V, nullptr, nullptr);
+    return 0;
+}
+int cpu_spline1d_fwd(const float* x, const float* kx, const float* ky, const float* kd, int K,
+                     int extrap_left, int extrap_right, int logistic, int inverse, const float* log_in,
+                     float* y, float* log_out, int64_t B, int64_t V) {
+    const Spline1dCfg cfg{K, extrap_left, extrap_right, logistic};
+    run_sites(Spline1dOp{x, kx, ky, kd, cfg, inverse, y, V}, B, V, log_in, log_out);
+    return 0;
+}
+int cpu_spline1d_bwd(const float* x, const float* kx, const float* ky, const float* kd, int K,
+                     int extrap_left, int extrap_right, int logistic, const float* gy, const float* glog,
+                     float* gx, float* gk, int64_t B, int64_t V) {
+    const Spline1dCfg cfg{K, extrap_left, extrap_right, logistic};
+    run_sites(Spline1dBwdOp{x, kx, ky, kd, cfg, gy, glog, gx, gk, V}, B, V, nullptr, nullptr);
+    return 0;
+}
+int cpu_phi4_action_fwd(const float* phi, nfk_lattice lat, float w0, float w2, float w4, float* S, int64_t B) {
+    const Lat l = make_lat(lat.ndim, lat.shape);
+    int64_t V = 1;
+    for (int d = 0; d < lat.ndim; ++d) V *= lat.shape[d];
+    run_sites(Phi4Op{phi, l, w0, w2, w4, V}, B, V, nullptr, S);
+    return 0;
+}
+int cpu_phi4_action_bwd(const float* phi, nfk_lattice lat, float w0, float w2, float w4, const float* gS,
+                        float* gphi, int64_t B) {
+    const Lat l = make_lat(lat.ndim, lat.shape);
+    int64_t V = 1;
+    for (int d = 0; d < lat.ndim; ++d) V *= lat.shape[d];
+    run_sites(Phi4BwdOp{phi, l, w0, w2, w4, gS, gphi, V}, B, V, nullptr, nullptr);
+    return 0;
+}
+// same staging as conv_fwd_kernel<8>: weights re-laid as [Ci*T][8] per channel block
+int cpu_conv_circ_fwd(const float* in, const float* w, const float* bias, const uint8_t* in_mask, int in_keep,
+                      int act, const float* dact_from, int dact_kind, float* out, nfk_lattice lat, int ksize,
+                      int Ci, int Co, int64_t B) {
+    const Lat l = make_lat(lat.ndim, lat.shape);
+    int V = 1, T = 1;
+    for (int d = 0; d < lat.ndim; ++d) { V *= lat.shape[d]; T *= ksize; }
+    constexpr int CO = 8;
+    std::vector<float> wt((size_t)Ci * T * CO);
+    for (int co0 = 0; co0 < Co; co0 += CO) {
+        for (int i = 0; i < Ci * T * CO; ++i) {
+            const int co = i % CO, r = i / CO;
+            wt[i] = (co0 + co < Co) ? w[(int64_t)(co0 + co) * Ci * T + r] : 0.f;
+        }
+        for (int64_t b = 0; b < B; ++b)
+            for (int s = 0; s < V; ++s) {
+                float acc[CO];
+                for (int co = 0; co < CO; ++co) acc[co] = (bias && co0 + co < Co) ? bias[co0 + co] : 0.f;
+                conv_site<CO>(in + b * Ci * (int64_t)V, wt.data(), in_mask, in_keep, l, s, Ci, T, ksize, V, acc);
+                for (int co = 0; co < CO && co0 + co < Co; ++co) {
+                    const int64_t o = (b * Co + co0 + co) * (int64_t)V + s;
+                    float v = act_apply(act, acc[co]);
+                    if (dact_from) v *= act_grad_from_post(dact_kind, dact_from[o]);
+                    out[o] = v;
+                }
+            }
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,341 @@
+"""fp32 per-site arithmetic of the CUDA kernels, run on the host through
+tests/cpu_harness (the same nfk_ops.cuh functors, compiled with g++), against the
+golden fixtures made from the reference.  Catches arithmetic / indexing mistakes
+before any GPU time is spent; the `-m gpu` tests repeat these through the real
+C-ABI on the device.  Tolerance: |d| <= 1e-5 * max(|ref|, 1) (north_star)."""
+
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from cpu_harness import load, lattice, RqsParams
+
+H = load()
+F = ctypes.POINTER(ctypes.c_float)
+U8 = ctypes.POINTER(ctypes.c_uint8)
+I64 = ctypes.c_int64
+
+
+def fp(a):
+    return None if a is None else a.ctypes.data_as(F)
+
+
+def up(a):
+    return a.ctypes.data_as(U8)
+
+
+def f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def close(got, ref, tol=1e-5):
+    ref = np.asarray(ref, dtype=np.float64)
+    err = np.abs(np.asarray(got, dtype=np.float64) - ref)
+    bound = tol * np.maximum(np.abs(ref), 1.0)
+    assert np.all(err <= bound), f"max excess {np.max(err / bound):.3g} (abs err {err.max():.3g})"
+
+
+def close_grad(got, ref, tol=1e-5):
+    """Gradients: error measured against the scale of the whole gradient tensor (the
+    softmax chain sums terms of mixed sign, so single small components carry the rounding
+    of the large ones)."""
+    ref = np.asarray(ref, dtype=np.float64)
+    err = np.abs(np.asarray(got, dtype=np.float64) - ref).max()
+    assert err <= tol * max(np.abs(ref).max(), 1.0), f"abs err {err:.3g} vs scale {np.abs(ref).max():.3g}"
+
+
+def test_masks_bit_exact():
+    g = load_golden("masks")
+    for key in g.files:
+        if not key.endswith("_meta"):
+            continue
+        tag, meta = key[:-5], g[key]
+        parity, mu, shape = int(meta[0]), int(meta[1]), tuple(int(v) for v in meta[2:])
+        m = np.empty(shape, dtype=np.uint8)
+        if tag.startswith("eo_"):
+            H.cpu_mask_evenodd(up(m), lattice(shape), parity, mu)
+        else:
+            H.cpu_mask_alongaxis(up(m), lattice(shape), parity, mu)
+        assert np.array_equal(m, g[tag + "_mask"])
+
+
+def test_action():
+    g = load_golden("action")
+    for i in range(9):
+        cfgs = f32(g[f"a{i}_cfgs"])
+        B, shape = cfgs.shape[0], cfgs.shape[1:]
+        S = np.empty(B, dtype=np.float32)
+        w0, w2, w4 = 0.67, 0.5 * (-4 * 0.67 + 2 * 0.67 * len(shape)), 0.5
+        H.cpu_phi4_action_fwd(fp(cfgs), lattice(shape), ctypes.c_float(w0), ctypes.c_float(w2),
+                              ctypes.c_float(w4), fp(S), I64(B))
+        close(S, g[f"a{i}_S"])
+        gS, gphi = f32(g[f"a{i}_gS"]), np.empty_like(cfgs)
+        H.cpu_phi4_action_bwd(fp(cfgs), lattice(shape), ctypes.c_float(w0), ctypes.c_float(w2),
+                              ctypes.c_float(w4), fp(gS), fp(gphi), I64(B))
+        close(gphi, g[f"a{i}_gcfgs"])
+
+
+def test_prior_logprob_and_sampler_statistics():
+    g = load_golden("prior")
+    x = f32(g["gen_x"])
+    B, V = x.shape[0], x[0].size
+    logr = np.empty(B, dtype=np.float32)
+    H.cpu_prior_normal_logprob(fp(x), fp(logr), I64(B), I64(V), fp(f32(g["gen_loc"])), fp(f32(g["gen_scale"])))
+    close(logr, g["gen_logr"])
+    H.cpu_prior_normal_logprob(fp(f32(g["std_x"])), fp(logr), I64(B), I64(V), None, None)
+    close(logr, g["std_logr"])
+    # sampler: moments, reproducibility, stream separation, fused log-prob
+    B, V = 64, 1030
+    xs, lr = np.empty((B, V), dtype=np.float32), np.empty(B, dtype=np.float32)
+    H.cpu_prior_normal_sample(fp(xs), fp(lr), I64(B), I64(V), None, None, ctypes.c_uint64(1234), ctypes.c_uint64(0))
+    n = xs.size
+    assert abs(xs.mean()) < 4 / np.sqrt(n) and abs(xs.var() - 1) < 4 * np.sqrt(2 / n)
+    assert abs(np.mean(xs ** 3)) < 0.05 and abs(np.mean(xs ** 4) - 3) < 0.1
+    ref = (-0.5 * xs.astype(np.float64) ** 2 - 0.5 * np.log(2 * np.pi)).sum(1)
+    close(lr, ref)
+    xs2 = np.empty_like(xs)
+    H.cpu_prior_normal_sample(fp(xs2), None, I64(B), I64(V), None, None, ctypes.c_uint64(1234), ctypes.c_uint64(0))
+    assert np.array_equal(xs, xs2)
+    H.cpu_prior_normal_sample(fp(xs2), None, I64(B), I64(V), None, None, ctypes.c_uint64(1234), ctypes.c_uint64(1))
+    assert abs(np.corrcoef(xs.ravel(), xs2.ravel())[0, 1]) < 0.02
+    # no correlation between neighbouring samples / sites
+    assert abs(np.corrcoef(xs[:-1].ravel(), xs[1:].ravel())[0, 1]) < 0.02
+    assert abs(np.corrcoef(xs[:, :-1].ravel(), xs[:, 1:].ravel())[0, 1]) < 0.02
+
+
+def test_affine_kernel():
+    g = load_golden("affine_kernel")
+    mask = np.ascontiguousarray(g["mask"])
+    B, V = g["x"].shape[0], mask.size
+    out = f32(g["out"])
+    for parity in (0, 1):
+        xa = f32(g["x"] * (mask if parity == 0 else 1 - mask))
+        y, logJ = np.empty_like(xa), np.empty(B, dtype=np.float32)
+        H.cpu_affine_fwd(fp(xa), fp(out), up(mask), parity, 0, None, fp(y), fp(logJ), I64(B), I64(V))
+        close(y, g[f"p{parity}_fx"])
+        close(logJ, g[f"p{parity}_logJ"])
+        xi, li = np.empty_like(xa), np.empty(B, dtype=np.float32)
+        H.cpu_affine_inv(fp(y), fp(out), up(mask), parity, 0, None, fp(xi), fp(li), I64(B), I64(V))
+        close(xi, g[f"p{parity}_xinv"])
+        close(li, g[f"p{parity}_loginv"])
+        gx, gout = np.empty_like(xa), np.empty_like(out)
+        # the reference's  t + x_active * exp(-s)  has t = s = 0 at frozen sites, i.e. it hands
+        # x_active through there: its VJP is the FROZEN_COPY mode of the kernel
+        H.cpu_affine_bwd(fp(xa), fp(out), up(mask), parity, 1, fp(f32(g["r"])), fp(f32(g["c"])),
+                         fp(gx), fp(gout), I64(B), I64(V))
+        close(gx, g[f"p{parity}_gx"])
+        close(gout, g[f"p{parity}_gout"])
+        # full-field mode: frozen sites pass through
+        xfull = f32(g["x"])
+        H.cpu_affine_fwd(fp(xfull), fp(out), up(mask), parity, 1, None, fp(y), fp(logJ), I64(B), I64(V))
+        act = (mask if parity == 0 else 1 - mask).astype(bool)
+        assert np.array_equal(y[:, ~act], xfull[:, ~act])
+        close(y[:, act], g[f"p{parity}_fx"][:, act])
+
+
+@pytest.mark.parametrize("tag,left,right", [("lin", 1, 1), ("none", 0, 0), ("mixed", 1, 0)])
+def test_rqs_kernel(tag, left, right):
+    g = load_golden("rqs_kernel")
+    mask = np.ascontiguousarray(g[f"{tag}_mask"])
+    B, V = g[f"{tag}_x"].shape[0], mask.size
+    out = f32(g[f"{tag}_out"])
+    prm = RqsParams(10, -5.0, 5.0, -4.0, 6.0, left, right)
+    for parity in (0, 1):
+        m = (mask if parity == 0 else 1 - mask)
+        xa = f32(g[f"{tag}_x"] * m)
+        y, logJ = np.empty_like(xa), np.empty(B, dtype=np.float32)
+        assert H.cpu_rqs_fwd(fp(xa), fp(out), up(mask), parity, 0, prm, None, fp(y), fp(logJ), I64(B), I64(V)) == 0
+        close(y, g[f"{tag}_p{parity}_fx"])
+        close(logJ, g[f"{tag}_p{parity}_logJ"])
+        gx, gout = np.empty_like(xa), np.empty_like(out)
+        H.cpu_rqs_bwd(fp(xa), fp(out), up(mask), parity, 0, prm, fp(f32(g[f"{tag}_r"])), fp(f32(g[f"{tag}_c"])),
+                      fp(gx), fp(gout), I64(B), I64(V))
+        close_grad(gx, g[f"{tag}_p{parity}_gx"])
+        close_grad(gout, g[f"{tag}_p{parity}_gout"])
+        # inverse on the forward image: back to x (active sites), log-Jacobians cancel
+        xi, li = np.empty_like(xa), np.empty(B, dtype=np.float32)
+        H.cpu_rqs_inv(fp(f32(g[f"{tag}_p{parity}_fx"])), fp(out), up(mask), parity, 0, prm, None,
+                      fp(xi), fp(li), I64(B), I64(V))
+        if tag == "lin":    # monotone everywhere: exact inverse, log-Jacobians cancel
+            close(xi, xa.astype(np.float64), tol=3e-5)
+            close(li, -g[f"{tag}_p{parity}_logJ"], tol=3e-5)
+        else:               # an end segment extended without 'linear' is not monotone outside xlim
+            inside = (np.abs(xa) < 5.0) & m.astype(bool)
+            close(xi[inside], xa[inside].astype(np.float64), tol=3e-5)
+
+
+def _knots(wx, wy, wd, lim):
+    """Host-side knot construction as the python layer does it (fp32)."""
+    from oracle import nf_oracle as O
+    kx, ky, kd = O.splinenet_knots(wx, wy, wd, xlim=lim, ylim=lim)
+    if kd is None:
+        kd = O.smooth_derivatives(kx, ky, 0)
+    kx[-1] = ky[-1] = lim[1]
+    return f32(kx), f32(ky), f32(kd)
+
+
+@pytest.mark.parametrize("tag,symmetric", [("zd_sym", True), ("lat_sym_smooth", True), ("lat_asym", False)])
+def test_distconvertor(tag, symmetric):
+    g = load_golden("distconv")
+    wd = g[f"{tag}_wd"] if f"{tag}_wd" in g.files else None
+    lim = (0.5, 1.0) if symmetric else (0.0, 1.0)
+    kx, ky, kd = _knots(g[f"{tag}_wx"], g[f"{tag}_wy"], wd, lim)
+    K = len(kx)
+    x = f32(g[f"{tag}_x"])
+    B, V = x.shape[0], x[0].size
+    left = 2 if symmetric else 0
+    y, logJ = np.empty_like(x), np.empty(B, dtype=np.float32)
+    H.cpu_spline1d_fwd(fp(x), fp(kx), fp(ky), fp(kd), K, left, 0, 1, 0, None, fp(y), fp(logJ), I64(B), I64(V))
+    close(y, g[f"{tag}_y"])
+    close(logJ, g[f"{tag}_logJ"])
+    # inverse: ModuleList_.backward(y, log0=logJ) -> (x, ~0)
+    xb, lb = np.empty_like(x), np.empty(B, dtype=np.float32)
+    H.cpu_spline1d_fwd(fp(f32(g[f"{tag}_y"])), fp(kx), fp(ky), fp(kd), K, left, 0, 1, 1, fp(f32(g[f"{tag}_logJ"])),
+                       fp(xb), fp(lb), I64(B), I64(V))
+    close(xb, g[f"{tag}_x"], tol=2e-5)
+    close(lb, np.zeros(B), tol=3e-5)
+    # gradient w.r.t. x (knot gradients are checked through autograd in the gpu tests)
+    gx, gk = np.empty_like(x), np.zeros(3 * K, dtype=np.float32)
+    H.cpu_spline1d_bwd(fp(x), fp(kx), fp(ky), fp(kd), K, left, 0, 1, fp(f32(g[f"{tag}_r"])), fp(f32(g[f"{tag}_c"])),
+                       fp(gx), fp(gk), I64(B), I64(V))
+    close_grad(gx, g[f"{tag}_gx"])
+
+
+def test_distconvertor_tails_keep_relative_accuracy():
+    """|x| up to 15: a naive fp32 expit->spline->logit loses all digits there."""
+    from oracle import nf_oracle as O
+    rs = np.random.RandomState(0)
+    wx, wy, wd = rs.randn(9) * 0.5, rs.randn(9) * 0.5, rs.randn(10) * 0.5
+    for symmetric in (True, False):
+        lim = (0.5, 1.0) if symmetric else (0.0, 1.0)
+        kx, ky, kd = _knots(wx, wy, wd, lim)
+        x = f32(np.linspace(-15, 15, 601)[None, :])
+        yr, lr = O.distconvertor(x.astype(np.float64), 0.0, (f32(wx).astype(np.float64), f32(wy).astype(np.float64),
+                                                              f32(wd).astype(np.float64)), symmetric=symmetric)
+        y, lj = np.empty_like(x), np.empty(1, dtype=np.float32)
+        H.cpu_spline1d_fwd(fp(x), fp(kx), fp(ky), fp(kd), 10, 2 if symmetric else 0, 0, 1, 0, None,
+                           fp(y), fp(lj), I64(1), I64(x.size))
+        close(y, yr, tol=2e-5)
+        close(lj, lr, tol=2e-5)
+
+
+def test_spline1d_plain_modes():
+    """Non-logistic shared-knot spline, every extrapolation mode, vs spline golden."""
+    g = load_golden("spline")
+    kx, ky, kd = f32(g["s1_kx"]), f32(g["s1_ky"]), f32(g["s1_kd"][len(g["s1_kx"]) - 1:])
+    x = f32(g["s1_x"][None, :])
+    y, lj = np.empty_like(x), np.empty(1, dtype=np.float32)
+    H.cpu_spline1d_fwd(fp(x), fp(kx), fp(ky), fp(kd), len(kx), 2, 0, 0, 0, None, fp(y), fp(lj), I64(1), I64(x.size))
+    close(y[0], g["s1_y"], tol=2e-5)
+    close(lj, np.log(g["s1_g"]).sum(), tol=2e-5)
+    xi, li = np.empty_like(x), np.empty(1, dtype=np.float32)
+    H.cpu_spline1d_fwd(fp(f32(g["s1_y"][None, :])), fp(kx), fp(ky), fp(kd), len(kx), 2, 0, 0, 1, None,
+                       fp(xi), fp(li), I64(1), I64(x.size))
+    inside = g["s1_x"] > 2 * kx[0] - kx[-1]   # beyond the mirrored range the end segment is extended
+    close(xi[0][inside], g["s1_x"][inside], tol=5e-5)
+
+
+def test_logistic_ops():
+    x = f32(np.linspace(-12, 12, 97)[None, :])
+    y, lj = np.empty_like(x), np.empty(1, dtype=np.float32)
+    H.cpu_logistic_fwd(fp(x), 0, None, fp(y), fp(lj), I64(1), I64(x.size))
+    xd = x.astype(np.float64)
+    close(y, 1 / (1 + np.exp(-xd)))
+    close(lj, (-xd + 2 * np.log(1 / (1 + np.exp(-xd)))).sum())
+    p = f32(np.linspace(0.01, 0.99, 50)[None, :])
+    H_y, H_l = np.empty_like(p), np.empty(1, dtype=np.float32)
+    H.cpu_logistic_fwd(fp(p), 1, None, fp(H_y), fp(H_l), I64(1), I64(p.size))
+    pd = p.astype(np.float64)
+    close(H_y, np.log(pd / (1 - pd)))
+    close(H_l, -np.log(pd * (1 - pd)).sum())
+
+
+@pytest.mark.parametrize("tag", ["d1", "d2", "d3", "d4"])
+def test_conv_layers(tag):
+    g = load_golden("conv")
+    n = len(g[f"{tag}_hidden"]) + 1
+    h = f32(g[f"{tag}_x"])
+    B, shape = h.shape[0], h.shape[2:]
+    for i in range(n):
+        w = f32(g[f"{tag}_w{i}"])
+        b = f32(g[f"{tag}_b{i}"]) if f"{tag}_b{i}" in g.files else None
+        Co, Ci = w.shape[:2]
+        out = np.empty((B, Co) + shape, dtype=np.float32)
+        H.cpu_conv_circ_fwd(fp(h), fp(w), fp(b), None, 0, 1 if i < n - 1 else 0, None, 0, fp(out),
+                            lattice(shape), 3, Ci, Co, I64(B))
+        h = out
+    close(h, g[f"{tag}_out"])
+
+
+def test_whole_rqs_stack_through_harness():
+    """Config-3-style stack (8x8 here): conv -> rqs, four steps, full-field mode."""
+    g = load_golden("cpl_rqs_2d")
+    mask = np.ascontiguousarray(g["mask"])
+    x = f32(g["x"])
+    B, shape, V = x.shape[0], x.shape[1:], mask.size
+    log = np.zeros(B, dtype=np.float32)
+    prm = RqsParams(10, -5.0, 5.0, -5.0, 5.0, 1, 1)
+    for k in range(4):
+        p = k % 2
+        h = x.reshape((B, 1) + shape)
+        for i in range(3):
+            w = f32(g[f"blk0_step{k}_w{i}"])
+            Co, Ci = w.shape[:2]
+            out = np.empty((B, Co) + shape, dtype=np.float32)
+            # first layer reads the frozen partition only: mask.split fused in
+            H.cpu_conv_circ_fwd(fp(h), fp(w), None, up(mask) if i == 0 else None, 0 if p == 0 else 1,
+                                1 if i < 2 else 0, None, 0, fp(out), lattice(shape), 3, Ci, Co, I64(B))
+            h = out
+        if k < 4:
+            close(h, g[f"blk0_step{k}_out"], tol=2e-5) if k == 0 else None
+        y, lo = np.empty_like(x), np.empty(B, dtype=np.float32)
+        H.cpu_rqs_fwd(fp(x), fp(h), up(mask), p, 1, prm, fp(log), fp(y), fp(lo), I64(B), I64(V))
+        x, log = y, lo
+    close(x, g["y"])
+    close(log, g["logJ"])
+
+
+@pytest.mark.parametrize("logistic,left,right,lim", [(1, 2, 0, (0.5, 1.0)), (1, 0, 0, (0.0, 1.0)),
+                                                      (0, 1, 1, (-2.0, 3.0)), (0, 2, 0, (0.0, 2.0)),
+                                                      (0, 0, 2, (-1.0, 1.0))])
+def test_spline1d_knot_gradients(logistic, left, right, lim):
+    """VJP w.r.t. the explicit knots vs a complex-step derivative of the oracle."""
+    from oracle import nf_oracle as O
+    rs = np.random.RandomState(11)
+    K = 7
+    wx, wy, wd = rs.randn(K - 1) * 0.6, rs.randn(K - 1) * 0.6, rs.randn(K) * 0.5
+    kx, ky, kd = _knots(wx, wy, wd, lim)
+    B, V = 5, 9
+    x = f32(rs.randn(B, V) * (2.0 if logistic else 1.5) + (0 if logistic else 0.5 * (lim[0] + lim[1])))
+    r, c = f32(rs.randn(B, V)), f32(rs.randn(B))
+    names = {0: None, 1: 'linear', 2: 'anti'}
+    extrap = {k: v for k, v in (('left', names[left]), ('right', names[right])) if v}
+
+    def scalar(kx_, ky_, kd_):
+        xx, log0 = x.astype(np.float64), 0.0
+        if logistic:
+            xx, log0 = O.expit_forward(xx, log0)
+        xx, log0 = O.splinenet_forward(xx, log0, (kx_, ky_, kd_), extrap)
+        if logistic:
+            xx, log0 = O.logit_forward(xx, log0)
+        return (xx * r).sum() + (log0 * c).sum()
+
+    args = tuple(a.astype(np.float64) for a in (kx, ky, kd))
+    gx, gk = np.empty_like(x), np.zeros(3 * K, dtype=np.float32)
+    H.cpu_spline1d_bwd(fp(x), fp(kx), fp(ky), fp(kd), K, left, right, logistic, fp(r), fp(c),
+                       fp(gx), fp(gk), I64(B), I64(V))
+    ref = np.zeros(3 * K)
+    for j in range(3):
+        for i in range(K):
+            if logistic and i in (0, K - 1) and j < 2:
+                continue     # end knots are the constants xlim / ylim of DistConvertor_
+            v = [np.zeros(K) for _ in range(3)]
+            v[j][i] = 1.0
+            ref[j * K + i] = O.directional_derivative(scalar, args, v)
+    got = gk.astype(np.float64).copy()
+    if logistic:
+        for j in range(2):
+            got[j * K] = got[j * K + K - 1] = 0.0
+    close_grad(got, ref, tol=2e-5)
