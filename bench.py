@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- samples/sec of "flow forward + log|det J| + action" on the 64x64 phi^4
+workload of BASELINE.json (configs[2]: RQ-spline coupling x4, ConvAct(1->8->8->28)
+conditioner, K=10 knots, batch 16384 per GPU), on N GPUs of one node.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the CPU arm: the oracle port on the host cores
+
+One "step" = one pass of the hot path over one synthetic batch: NormalPrior draw with
+log-density -> four checkerboard RQ-spline coupling steps (conditioner + spline +
+log|det J|) -> phi^4 action, i.e. `model.posterior.sample__(B)`.  Ranks are independent
+(batch sharding, no data-path collective): weak scaling, `value` = all ranks' samples
+divided by the slowest rank's device time.
+
+The JSON line carries, besides the base contract:
+  roofline     : the dominant HBM-bound kernel (the RQ-spline apply), algorithmic bytes
+                 ((8 + 4 P) B per site and step = 120 B at P = 28) over its mean
+                 launch duration measured with CUDA events inside the timed steps, against
+                 the measured copy bandwidth of MEASURED_PEAKS.json
+  cpu_baseline : the numpy oracle port of the same path timed on a bounded sample
+  e2e          : the same metric through the public API with HOST buffers: the prior draw
+                 comes from pinned host memory (H2D inside the timed region) and log q,
+                 log p are read back (D2H)
+"""
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+LATTICE = (64, 64)
+KNOTS = 10
+HIDDEN = [8, 8]
+N_STEPS_FLOW = 4
+ACTION = dict(kappa=0.67, m_sq=-4 * 0.67, lambd=0.5)
+METRIC = "samples/sec (flow fwd+logJ+action) 64^2 phi^4"
+WORKLOAD = ("configs[2]: 2-D scalar phi^4 64x64, RQ-spline coupling x4 (K=10, xlim=ylim=(-5,5), linear "
+            "extrapolation), ConvAct(1->8->8->28, k=3, tanh, circular, no bias) conditioner")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=16384, help="samples per GPU and step")
+    ap.add_argument("--cpu-batch", type=int, default=16, help="samples per step of the CPU arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------- CPU arm
+def oracle_model(seed=0):
+    """The same workload for the numpy oracle (test infrastructure; here as the CPU
+    baseline only).  Weights: fan-in scaled normal, float64."""
+    from oracle import nf_oracle as O
+    rs = np.random.RandomState(seed)
+    mask = O.evenodd_mask(LATTICE)
+    sizes = [1] + HIDDEN + [3 * KNOTS - 2]
+    steps = []
+    for _ in range(N_STEPS_FLOW):
+        layers = [(rs.randn(sizes[i + 1], sizes[i], 3, 3) / np.sqrt(9 * sizes[i]), None) for i in range(3)]
+        steps.append(O.make_convact_step('rqs', layers, ['tanh', 'tanh', None], mask, xlim=(-5, 5), ylim=(-5, 5),
+                                         extrap=dict(left='linear', right='linear')))
+    flow = lambda x, log0: O.coupling_forward(x, log0, mask, steps)
+    return O, flow, rs
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def time_oracle(batch, steps, warmup):
+    O, flow, rs = oracle_model()
+    def one():
+        x = rs.randn(batch, *LATTICE)
+        return O.posterior_sample__(x, flow, ACTION)
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path.  The reference is pure Python on torch
+    and cannot travel to the GPU box, so this times the oracle port (numpy, float64) of the
+    same workload on the host cores; each step is a bounded sample of `--cpu-batch` samples."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, dt = time_oracle(args.cpu_batch, args.steps, args.warmup)
+    cores = blas_threads()
+    sample = f"{args.cpu_batch} samples/step x {args.steps} steps of the same workload (numpy float64 oracle port)"
+    line = {
+        "metric": METRIC, "value": value, "unit": "samples/s", "impl": "reference",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_step": args.cpu_batch, "lattice": list(LATTICE)},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU during the timed region."""
+
+    def __init__(self, index, period=0.1):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.sm, self.reasons, self.sm_max = [], set(), None
+        self._stop = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if bits & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def finish(self):
+        self._stop.set()
+        self.join(timeout=2)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons)}
+
+
+# --------------------------------------------------------------------------- GPU arm
+def build_model(torch):
+    from normflow__b200 import Model
+    from normflow__b200.action import ScalarPhi4Action
+    from normflow__b200.mask import EvenOddMask
+    from normflow__b200.nn import ModuleList_, ConvAct, RQSplineCoupling_
+    from normflow__b200.prior import NormalPrior
+    torch.manual_seed(0)
+    mask = EvenOddMask(shape=LATTICE)
+    nets = [ConvAct(1, 3 * KNOTS - 2, 3, conv_dim=2, hidden_sizes=HIDDEN, acts=('tanh', 'tanh', None), bias=False)
+            for _ in range(N_STEPS_FLOW)]
+    net_ = ModuleList_([RQSplineCoupling_(nets, mask=mask, xlim=(-5, 5), ylim=(-5, 5),
+                                          extrap=dict(left='linear', right='linear'))])
+    model = Model(prior=NormalPrior(shape=LATTICE), net_=net_, action=ScalarPhi4Action(**ACTION))
+    model.device_handler.to('cuda')
+    return model
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu summary."""
+    path = os.path.join(ROOT, "profiles", "dominant_kernel.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh).get("dram_bytes_per_launch")
+    return None
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (normflow__b200 has no CPU path); "
+                           "use --impl reference for the CPU arm")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from normflow__b200 import _C
+    model = build_model(torch)
+    B, V = args.batch, int(np.prod(LATTICE))
+    torch.manual_seed(1234 + rank)          # independent Philox key per rank
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        return model.posterior.sample__(B)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # ---- timed region: K steps, device time, max over ranks -------------------------
+    timer = _C.KernelTimer()
+    _C.kernel_timer = timer
+    clocks = ClockSampler(local)
+    clocks.start()
+    n0 = _C.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        y, logq, logp = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _C.launch_count() - n0
+    clock_info = clocks.finish()
+    _C.kernel_timer = None
+    kernels = timer.summary()
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- end to end with host buffers ---------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host_x = torch.randn(B, *LATTICE, dtype=torch.float32, device="cpu").pin_memory()
+        host_out = torch.empty(2, B, dtype=torch.float32, device="cpu").pin_memory()
+
+        def e2e_step():
+            with torch.no_grad():
+                x = host_x.to("cuda", non_blocking=True)
+                logr = model.prior.log_prob(x)
+                yy, logJ = model.net_(x)
+                res = torch.stack([logr - logJ, -model.action(yy)])
+                host_out.copy_(res, non_blocking=True)
+            torch.cuda.synchronize()
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = t.item()
+        e2e = {"value": world * B * args.steps / dt, "unit": "samples/s",
+               "h2d_bytes_per_step": int(B * V * 4), "d2h_bytes_per_step": int(2 * B * 4)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant HBM-bound kernel --------------------------------------
+    pk, pk_src = peaks()
+    P = 3 * KNOTS - 2
+    rq = kernels.get("rqs_fwd", None)
+    roofline = None
+    if rq:
+        bytes_per_launch = (8 + 4 * P) * V * B          # read x, read P params, write y
+        achieved = bytes_per_launch / (rq["avg_ms"] * 1e-3) / 1e9
+        roofline = {"kernel": "nfk_rqs_fwd (site_kernel<RqsOp<10,0>>)", "bound": "hbm", "achieved": achieved,
+                    "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
+                    "traffic": ncu_traffic(), "peak_source": pk_src,
+                    "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": rq["avg_ms"],
+                    "share_of_step": rq["total_ms"] / ms}
+    step_bytes = (4 + N_STEPS_FLOW * (8 + 4 * P) + 4) * V      # 488 V per sample
+    total_ms = sum(k["total_ms"] for k in kernels.values())
+    kernel_table = {name: {"launches": k["launches"], "avg_ms": round(k["avg_ms"], 4),
+                           "share": round(k["total_ms"] / max(total_ms, 1e-9), 4)} for name, k in kernels.items()}
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        cb = args.cpu_batch
+        v, dt = time_oracle(cb, steps=6, warmup=1)
+        cpu = {"value": v, "unit": "samples/s", "cores": blas_threads(), "kind": "port",
+               "sample": f"{cb} samples/step x 6 steps of the same workload, numpy float64 oracle port, {dt:.1f} s"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "lattice": list(LATTICE),
+                   "l2": "per-step working set (x 268 MB, conditioner output 7.5 GB) is far larger than the 126 MB L2",
+                   "model_bytes_per_sample": step_bytes,
+                   "hbm_model_frac_whole_step": step_bytes * value / world / 1e9 / pk["hbm_gbs"]},
+        "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "cpu_baseline": cpu, "kernels": kernel_table,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

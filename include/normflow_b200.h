@@ -184,8 +184,11 @@ int nfk_phi4_action_bwd(const float* phi, nfk_lattice lat, float w0, float w2, f
  * in_mask != NULL: the input is read as (in_mask[s]==in_keep ? in : 0), i.e.
  * Mask.split fused into the first layer (couplings_.py:88-89).
  * dact_from != NULL (backward use): out is multiplied by act'(.) evaluated from
- * the saved post-activation tensor dact_from[B][Co][V] with activation dact_kind. */
-int nfk_conv_circ_fwd(const float* in, const float* w, const float* bias,
+ * the saved post-activation tensor dact_from[B][Co][V] with activation dact_kind.
+ * w_transposed != 0 (backward use, data gradient): `w` is the FORWARD layer's
+ * weight w[Ci][Co][taps] and is read transposed with every tap flipped, so the
+ * same kernel computes d loss / d input from d loss / d pre-activation.          */
+int nfk_conv_circ_fwd(const float* in, const float* w, int w_transposed, const float* bias,
                       const uint8_t* in_mask, int in_keep,
                       int act, const float* dact_from, int dact_kind,
                       float* out, nfk_lattice lat, int ksize,

@@ -66,7 +66,7 @@ def build(force=False, verbose=False):
             raise RuntimeError(f"nvcc failed on {src}")
     with open(os.path.join(LIBDIR, "ptxas.log"), "w") as fh:
         fh.write("\n".join(log))
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-lcudart"]
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs]   # static cudart (nvcc default)
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)

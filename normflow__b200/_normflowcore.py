@@ -1,0 +1,299 @@
+"""Model, Posterior and Fitter: the drivers of the hot loop
+(reference src/_normflowcore.py).
+
+    model = Model(prior=..., net_=..., action=...)
+    model.fit(n_epochs=..., batch_size=...)          # training      (Fitter)
+    y = model.posterior.sample(batch_size)           # raw proposals (Posterior)
+    y = model.mcmc.sample(batch_size)                # with Metropolis accept/reject
+
+The classes only sequence the work: every pass over a batch of lattice fields (prior
+draw + log-density, coupling layers with log|det J|, action, accept/reject, and their
+gradients) is a kernel of libnormflow_b200.so reached through prior / net_ / action.
+"""
+
+import os
+import time
+
+import numpy as np
+import torch
+
+from .mcmc import MCMCSampler
+from .lib.combo import estimate_logz, fmt_val_err
+from .device import ModelDeviceHandler
+
+
+class Model:
+    """Bundle of a prior, an invertible network and an action
+    (reference Model, _normflowcore.py:33-67).
+
+    prior  : e.g. prior.NormalPrior(shape=lattice_shape)
+    net_   : nn.ModuleList_ (or any layer with forward/backward returning log-Jacobians)
+    action : e.g. action.ScalarPhi4Action(...)
+    """
+
+    def __init__(self, *, prior, net_, action, name=None):
+        self.name = name
+        self.net_ = net_
+        self.prior = prior
+        self.action = action
+
+        self.fit = Fitter(self)
+        self.posterior = Posterior(self)
+        self.raw_dist = self.posterior      # older alias kept by the reference
+        self.mcmc = MCMCSampler(self)
+        self.device_handler = ModelDeviceHandler(self)
+
+    def transform(self, x):
+        return self.net_(x)[0]
+
+
+class Posterior:
+    """Samples drawn straight from the flow, no accept/reject
+    (reference Posterior, _normflowcore.py:70-119)."""
+
+    def __init__(self, model):
+        self._model = model
+
+    @torch.no_grad()
+    def sample(self, batch_size=1, **kwargs):
+        return self.sample_(batch_size=batch_size, **kwargs)[0]
+
+    @torch.no_grad()
+    def sample_(self, batch_size=1, preprocess_func=None):
+        """(y, log q(y)); `preprocess_func(x, logr)` may edit the prior draw first."""
+        x, logr = self._model.prior.sample_(batch_size)
+        if preprocess_func is not None:
+            x, logr = preprocess_func(x, logr)
+        y, logJ = self._model.net_(x)
+        return y, logr - logJ
+
+    @torch.no_grad()
+    def sample__(self, batch_size=1, **kwargs):
+        """(y, log q(y), log p(y) + log z): the benchmark's "flow fwd + logJ + action"."""
+        y, logq = self.sample_(batch_size=batch_size, **kwargs)
+        return y, logq, -self._model.action(y)
+
+    @torch.no_grad()
+    def log_prob(self, y):
+        """log q(y) through the inverse flow."""
+        x, minus_logJ = self._model.net_.backward(y)
+        return self._model.prior.log_prob(x) + minus_logJ
+
+
+class Fitter:
+    """Trains the model by minimising a divergence between q and p
+    (reference Fitter, _normflowcore.py:122-428)."""
+
+    def __init__(self, model):
+        self._model = model
+        self.train_batch_size = 1
+        self.train_history = dict(loss=[], logqp=[], logz=[], ess=[], rho=[], accept_rate=[])
+        self.hyperparam = dict(lr=0.001, weight_decay=0.01)
+        self.checkpoint_dict = dict(display=False, print_stride=100, print_batch_size=1024,
+                                    print_extra_func=None, snapshot_path=None, epochs_run=0)
+
+    def __call__(self, n_epochs=1000, save_every=None, batch_size=64,
+                 optimizer_class=torch.optim.AdamW, scheduler=None, loss_fn=None,
+                 hyperparam={}, checkpoint_dict={}):
+        """Train for `n_epochs` steps of `batch_size` fresh samples each.
+
+        save_every      : snapshot period in epochs (default: only at the end)
+        optimizer_class : torch optimiser class (AdamW by default)
+        scheduler       : callable optimiser -> lr scheduler, or None
+        loss_fn         : f(logq, logp) -> scalar; default reverse KL (`calc_kl_mean`)
+        hyperparam      : optimiser keyword arguments (lr, weight_decay, ...)
+        checkpoint_dict : print_stride, print_batch_size, snapshot_path, ...
+        """
+        self.hyperparam.update(hyperparam)
+        self.checkpoint_dict.update(checkpoint_dict)
+        snapshot_path = self.checkpoint_dict['snapshot_path']
+        if save_every is None:
+            save_every = n_epochs
+
+        if snapshot_path is None:
+            print("Not saving model snapshots")
+        elif os.path.exists(snapshot_path):
+            print(f"Trying to load snapshot from {snapshot_path}")
+            self._load_snapshot()
+        else:
+            print("Starting training from scratch")
+
+        self.loss_fn = Fitter.calc_kl_mean if loss_fn is None else loss_fn
+
+        # (the reference's test for parameter groups, `'_groups' is net_.__dict__.keys()`,
+        # is never true, so it always optimises net_.parameters(); kept that way)
+        self.optimizer = optimizer_class(self._model.net_.parameters(), **self.hyperparam)
+        self.scheduler = None if scheduler is None else scheduler(self.optimizer)
+        return self.train(n_epochs, batch_size, save_every)
+
+    # ---- snapshots ({"MODEL_STATE", "EPOCHS_RUN"}, reference :221-247) -------------
+    def _load_snapshot(self):
+        path = self.checkpoint_dict['snapshot_path']
+        if torch.cuda.is_available():
+            loc = f"cuda:{self._model.device_handler.rank}"
+            print(f"GPU: Attempting to load saved model into {loc}")
+        else:
+            loc = None
+            print("CPU: Attempting to load saved model")
+        snapshot = torch.load(path, map_location=loc)
+        state = {k: (v.float() if torch.is_floating_point(v) else v)
+                 for k, v in snapshot["MODEL_STATE"].items()}     # reference snapshots are float64
+        self._model.net_.load_state_dict(state)
+        self.checkpoint_dict['epochs_run'] = snapshot['EPOCHS_RUN']
+        print(f"Snapshot found: {path}\nResuming training via Saved Snapshot at Epoch {snapshot['EPOCHS_RUN']}")
+
+    def _save_snapshot(self, epoch):
+        path = self.checkpoint_dict['snapshot_path']
+        epochs_run = epoch + self.checkpoint_dict['epochs_run']
+        new_path = path.rsplit('.', 2)[0] + ".E" + str(epochs_run) + ".tar"
+        torch.save({"MODEL_STATE": self._model.net_.state_dict(), "EPOCHS_RUN": epochs_run}, new_path)
+        print(f"Epoch {epochs_run} | Model Snapshot saved at {new_path}")
+
+    # ---- the loop -------------------------------------------------------------------
+    def train(self, n_epochs, batch_size, save_every):
+        """The epoch loop; call through `__call__` (which builds the optimiser) at least once."""
+        self.train_batch_size = batch_size
+        t_start = time.time()
+        loss = None
+        for epoch in range(1, n_epochs + 1):
+            loss, _ = self.step()
+            self.checkpoint(epoch, loss, save_every)
+            if self.scheduler is not None:
+                self.scheduler.step()
+        if n_epochs > 0 and self._model.device_handler.rank == 0:
+            print(f"({loss.device}) Time = {time.time() - t_start:.3g} sec.")
+
+    def step(self):
+        """One optimisation step on a fresh batch (reference Fitter.step, :275-294)."""
+        model, handler = self._model, self._model.device_handler
+        x, logr = model.prior.sample_(self.train_batch_size)
+        y, logJ = model.net_(x)
+        logq = logr - logJ
+        logp = -model.action(y)
+        loss = self.loss_fn(logq, logp)
+
+        handler.zero_grad(self.optimizer)
+        loss.backward()
+        handler.sync_gradients()          # one flat all-reduce when nranks > 1
+        if torch.isnan(loss):
+            print("OOPS: loss is divergent -> no *step* is taken.")
+        else:
+            self.optimizer.step()
+        return loss, logq - logp
+
+    def checkpoint(self, epoch, loss, save_every):
+        handler = self._model.device_handler
+        rank = handler.rank
+        print_stride = self.checkpoint_dict['print_stride']
+        print_batch_size = self.checkpoint_dict['print_batch_size'] // handler.nranks
+        snapshot_path = self.checkpoint_dict['snapshot_path']
+
+        if rank == 0:
+            self.train_history['loss'].append(loss.item())
+            if snapshot_path is not None and (epoch % save_every == 0):
+                self._save_snapshot(epoch)
+
+        if epoch == 1 or epoch == 10 or (epoch % print_stride == 0):
+            _, logq, logp = self._model.posterior.sample__(print_batch_size)
+            logq = handler.all_gather_into_tensor(logq)
+            logp = handler.all_gather_into_tensor(logp)
+            if rank == 0:
+                loss_ = self.loss_fn(logq, logp)
+                self._append_to_train_history(logq, logp)
+                self.print_fit_status(epoch, loss=loss_)
+
+    # ---- losses and diagnostics on [B] vectors (negligible bytes: tensor expressions) --
+    @staticmethod
+    def calc_kl_mean(logq, logp):
+        """Reverse KL up to log z, estimated with samples from q."""
+        return (logq - logp).mean()
+
+    @staticmethod
+    def calc_kl_var(logq, logp):
+        return (logq - logp).var()
+
+    @staticmethod
+    def calc_corrcoef(logq, logp):
+        return torch.corrcoef(torch.stack([logq, logp]))[0, 1]
+
+    @staticmethod
+    def calc_direct_kl_mean(logq, logp):
+        r"""sum(p/q (log(p/q) + log z)) / sum(p/q) with log z = log mean(p/q);
+        invariant under rescaling p or q."""
+        logpq = logp - logq
+        logpq = logpq - (torch.logsumexp(logpq, dim=0) - np.log(logp.shape[0]))
+        return (torch.exp(logpq) * logpq).mean()
+
+    @staticmethod
+    def calc_kl_mean_includelogz(logq, logp):
+        logqp = logq - logp
+        return logqp.mean() + torch.logsumexp(-logqp, dim=0) - np.log(logp.shape[0])
+
+    @staticmethod
+    def calc_least_squares(logq, logp):
+        logqp = logq - logp
+        logz = torch.logsumexp(-logqp, dim=0) - np.log(logp.shape[0])
+        return torch.mean((logqp + logz) ** 2)
+
+    @staticmethod
+    def calc_minus_logz(logq, logp):
+        return -(torch.logsumexp(logp - logq, dim=0) - np.log(logp.shape[0]))
+
+    @staticmethod
+    def calc_ess(logq, logp):
+        """Effective sample size, normalised to (0, 1]."""
+        logqp = logq - logp
+        log_ess = 2 * torch.logsumexp(-logqp, dim=0) - torch.logsumexp(-2 * logqp, dim=0)
+        return torch.exp(log_ess) / len(logqp)
+
+    def calc_minus_ess(self, logq, logp):
+        return -self.calc_ess(logq, logp)
+
+    @torch.no_grad()
+    def _append_to_train_history(self, logq, logp):
+        logqp = logq - logp
+        hist = self.train_history
+        hist['logz'].append(estimate_logz(logqp, method='jackknife'))
+        hist['accept_rate'].append(self._model.mcmc.estimate_accept_rate(logqp))
+        hist['ess'].append(self.calc_ess(logqp, 0))
+        hist['rho'].append(self.calc_corrcoef(logq, logp))
+        hist['logqp'].append((logqp.mean().item(), logqp.std().item()))
+
+    def print_fit_status(self, epoch, loss=None):
+        hist = self.train_history
+        if loss is None:
+            loss = hist['loss'][-1]
+        logqp_mean, logqp_std = hist['logqp'][-1]
+        logz_mean, logz_std = hist['logz'][-1]
+        rate_mean, rate_std = hist['accept_rate'][-1]
+        ess, rho = hist['ess'][-1], hist['rho'][-1]
+
+        if epoch == 1:
+            print(f"\n>>> Training progress ({ess.device}) <<<\n")
+            print("Note: log(q/p) is estimated with normalized p; "
+                  "mean & error are obtained from samples in a batch\n")
+
+        epoch += self.checkpoint_dict['epochs_run']
+        line = f"Epoch: {epoch} | loss: {loss:g} | ess: {ess:g} | rho: {rho:g}"
+        line += " | log(z): {0} | log(q/p): {1} | accept_rate: {2}".format(
+            fmt_val_err(logz_mean, logz_std, err_digits=2),
+            fmt_val_err(logqp_mean + logz_mean, logqp_std, err_digits=2),   # p normalised by the estimate
+            fmt_val_err(rate_mean, rate_std, err_digits=1))
+        if self.checkpoint_dict['print_extra_func'] is not None:
+            line += self.checkpoint_dict['print_extra_func'](epoch)
+        print(line)
+
+
+@torch.no_grad()
+def backward_sanitychecker(model, n_samples=5, net_=None, return_details=False):
+    """net_.backward(net_(x)) must give back x with a vanishing residual log-Jacobian
+    (reference _normflowcore.py:432-451).  Prints sum|x - x_hat| and sum|log0_hat|."""
+    if net_ is None:
+        net_ = model.net_
+    x = model.prior.sample(n_samples)
+    y, logJ = net_(x)
+    x_hat, log0_hat = net_.backward(y, log0=logJ)
+    print("Sanity check is OK if following numbers are zero up to round off:")
+    print(f"{torch.sum(torch.abs(x - x_hat)).item():g}", f"{torch.sum(torch.abs(log0_hat)).item():g}")
+    if return_details:
+        return (x, y, x_hat), (logJ, log0_hat)

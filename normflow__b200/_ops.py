@@ -1,0 +1,477 @@
+"""Thin torch.autograd wrappers over the C ABI (include/normflow_b200.h).
+
+Every function here enqueues hand-written sm_100a kernels on torch's current CUDA
+stream; tensors are only the memory they work on.  Nothing in this file computes on
+the host and nothing falls back to eager PyTorch: a CPU tensor raises.
+"""
+
+import numbers
+
+import numpy as np
+import torch
+
+from . import _C
+from ._C import dev, stream, check, lib
+
+
+def _f32c(t, name):
+    """Contiguous float32 view of a CUDA tensor (copying only when it has to)."""
+    if not torch.is_tensor(t):
+        raise TypeError(f"normflow_b200: {name} must be a tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"normflow_b200: {name} is on '{t.device}'; the hot path runs on CUDA only "
+                           "(no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise TypeError(f"normflow_b200: {name} must be float32 (got {t.dtype}); the kernels are fp32")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def as_log(log0, like):
+    """The reference threads `log0=0` (a python number) through the flow; the kernels
+    take NULL for zero.  Returns a float32 [B] tensor or None."""
+    if log0 is None:
+        return None
+    if isinstance(log0, numbers.Number):
+        if log0 == 0:
+            return None
+        return torch.full((like.shape[0],), float(log0), dtype=torch.float32, device=like.device)
+    return _f32c(log0, "log0")
+
+
+def _mask_u8(mask):
+    if mask.dtype != torch.uint8:
+        raise TypeError("normflow_b200: mask must be uint8 (Mask._mask)")
+    return mask if mask.is_contiguous() else mask.contiguous()
+
+
+def _no_grad_needed(*tensors):
+    if torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in tensors):
+        raise NotImplementedError(
+            "normflow_b200: the inverse direction is a sampling/evaluation path and has no "
+            "backward kernel; call it under torch.no_grad()")
+
+
+# ---------------------------------------------------------------------------- masks
+class _MaskSelect(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mask, keep):
+        x = _f32c(x, "x")
+        y = torch.empty_like(x)
+        B = x.shape[0]
+        check(lib().nfk_mask_select(dev(x), dev(mask, torch.uint8), keep, dev(y), B, x.numel() // max(B, 1),
+                                    stream()), "mask_select")
+        ctx.mask, ctx.keep = mask, keep
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        return _MaskSelect.apply(gy, ctx.mask, ctx.keep), None, None
+
+
+def mask_select(x, mask, keep):
+    """Mask.split / purify: x where mask == keep, 0 elsewhere (mask/mask.py:30-37)."""
+    return _MaskSelect.apply(x, _mask_u8(mask), int(keep))
+
+
+def make_evenodd_mask(shape, parity, exclude_mu, device):
+    m = torch.empty(tuple(shape), dtype=torch.uint8, device=device)
+    check(lib().nfk_mask_evenodd(dev(m, torch.uint8), _C.lattice(shape), int(parity),
+                                 -1 if exclude_mu is None else int(exclude_mu), stream()), "mask_evenodd")
+    return m
+
+
+def make_alongaxis_mask(shape, parity, mu, device):
+    m = torch.empty(tuple(shape), dtype=torch.uint8, device=device)
+    check(lib().nfk_mask_alongaxis(dev(m, torch.uint8), _C.lattice(shape), int(parity), int(mu), stream()),
+          "mask_alongaxis")
+    return m
+
+
+# ---------------------------------------------------------------------------- prior
+def prior_sample(batch_size, shape, loc, scale, seed, offset, device, with_logprob=True):
+    """x = loc + scale * N(0,1) and (optionally) its log-density summed per sample."""
+    shape = tuple(int(v) for v in shape)
+    V = int(np.prod(shape)) if len(shape) else 1
+    x = torch.empty((batch_size,) + shape, dtype=torch.float32, device=device)
+    logr = torch.empty((batch_size,), dtype=torch.float32, device=device) if with_logprob else None
+    with _C.timed("prior_normal_sample"):
+        check(lib().nfk_prior_normal_sample(dev(x), dev(logr), batch_size, V, dev(loc), dev(scale),
+                                            int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1), stream()),
+              "prior_normal_sample")
+    return x, logr
+
+
+def prior_logprob(x, loc, scale):
+    x = _f32c(x, "x")
+    B = x.shape[0]
+    logr = torch.empty((B,), dtype=torch.float32, device=x.device)
+    check(lib().nfk_prior_normal_logprob(dev(x), dev(logr), B, x.numel() // max(B, 1), dev(loc), dev(scale),
+                                         stream()), "prior_normal_logprob")
+    return logr
+
+
+# ---------------------------------------------------------------------------- couplings
+def _bv(x):
+    B = x.shape[0]
+    return B, x.numel() // max(B, 1)
+
+
+class _AffineFwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, out, log_in, mask, parity, frozen_mode):
+        x, out = _f32c(x, "x"), _f32c(out, "conditioner output")
+        B, V = _bv(x)
+        if out.numel() != 2 * B * V:
+            raise ValueError(f"affine coupling needs 2 conditioner channels, got shape {tuple(out.shape)}")
+        y = torch.empty_like(x)
+        log_out = torch.empty((B,), dtype=torch.float32, device=x.device)
+        check(lib().nfk_affine_fwd(dev(x), dev(out), dev(mask, torch.uint8), parity, frozen_mode, dev(log_in),
+                                   dev(y), dev(log_out), B, V, stream()), "affine_fwd")
+        ctx.save_for_backward(x, out, mask)
+        ctx.cfg = (parity, frozen_mode, log_in is not None)
+        return y, log_out
+
+    @staticmethod
+    def backward(ctx, gy, glog):
+        x, out, mask = ctx.saved_tensors
+        parity, frozen_mode, has_log = ctx.cfg
+        B, V = _bv(x)
+        gy, glog = _f32c(gy, "gy"), _f32c(glog, "glog")
+        gx, gout = torch.empty_like(x), torch.empty_like(out)
+        check(lib().nfk_affine_bwd(dev(x), dev(out), dev(mask, torch.uint8), parity, frozen_mode, dev(gy),
+                                   dev(glog), dev(gx), dev(gout), B, V, stream()), "affine_bwd")
+        return gx, gout, (glog if has_log else None), None, None, None
+
+
+def affine_apply(x, out, mask, parity, log0=0, frozen_mode=_C.FROZEN_COPY, inverse=False):
+    """AffineCoupling_.atomic_forward/backward (couplings_.py:123-139)."""
+    mask = _mask_u8(mask)
+    log_in = as_log(log0, x)
+    if not inverse:
+        return _AffineFwd.apply(x, out, log_in, mask, int(parity), int(frozen_mode))
+    _no_grad_needed(x, out, log_in)
+    x, out = _f32c(x, "x"), _f32c(out, "conditioner output")
+    B, V = _bv(x)
+    y = torch.empty_like(x)
+    log_out = torch.empty((B,), dtype=torch.float32, device=x.device)
+    check(lib().nfk_affine_inv(dev(x), dev(out), dev(mask, torch.uint8), int(parity), int(frozen_mode),
+                               dev(log_in), dev(y), dev(log_out), B, V, stream()), "affine_inv")
+    return y, log_out
+
+
+class _Shift(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, out, mask, parity, frozen_mode, sign):
+        x, out = _f32c(x, "x"), _f32c(out, "conditioner output")
+        B, V = _bv(x)
+        if out.numel() != B * V:
+            raise ValueError(f"shift coupling needs 1 conditioner channel, got shape {tuple(out.shape)}")
+        y = torch.empty_like(x)
+        check(lib().nfk_shift_apply(dev(x), dev(out), dev(mask, torch.uint8), parity, frozen_mode, sign, dev(y),
+                                    B, V, stream()), "shift_apply")
+        ctx.mask = mask
+        ctx.cfg = (parity, frozen_mode, sign, out.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        parity, frozen_mode, sign, oshape = ctx.cfg
+        gy = _f32c(gy, "gy")
+        active = 1 if parity == 0 else 0
+        g_act = mask_select(gy, ctx.mask, active)
+        gx = gy if frozen_mode == _C.FROZEN_COPY else g_act
+        return gx, (sign * g_act).reshape(oshape), None, None, None, None
+
+
+def shift_apply(x, out, mask, parity, frozen_mode=_C.FROZEN_COPY, inverse=False):
+    """ShiftCoupling_.atomic_forward/backward (couplings_.py:110-116)."""
+    return _Shift.apply(x, out, _mask_u8(mask), int(parity), int(frozen_mode), -1.0 if inverse else 1.0)
+
+
+def rqs_params(n_knots, xlim, ylim, extrap):
+    extrap = extrap or {}
+    for side in ('left', 'right'):
+        if extrap.get(side) not in (None, 'linear'):
+            raise NotImplementedError(
+                f"RQSplineCoupling_: extrap[{side!r}]={extrap.get(side)!r} is not available in the fused "
+                "coupling kernel (supported: None, 'linear')")
+    return _C.RqsParams(int(n_knots), float(xlim[0]), float(xlim[1]), float(ylim[0]), float(ylim[1]),
+                        _C.EXTRAP[extrap.get('left')], _C.EXTRAP[extrap.get('right')])
+
+
+class _RqsFwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, out, log_in, mask, parity, frozen_mode, prm):
+        x, out = _f32c(x, "x"), _f32c(out, "conditioner output")
+        B, V = _bv(x)
+        if out.numel() != (3 * prm.n_knots - 2) * B * V:
+            raise ValueError(f"RQ-spline coupling with {prm.n_knots} knots needs {3 * prm.n_knots - 2} "
+                             f"conditioner channels, got shape {tuple(out.shape)}")
+        y = torch.empty_like(x)
+        log_out = torch.empty((B,), dtype=torch.float32, device=x.device)
+        with _C.timed("rqs_fwd"):
+            check(lib().nfk_rqs_fwd(dev(x), dev(out), dev(mask, torch.uint8), parity, frozen_mode, prm,
+                                    dev(log_in), dev(y), dev(log_out), B, V, stream()), "rqs_fwd")
+        ctx.save_for_backward(x, out, mask)
+        ctx.cfg = (parity, frozen_mode, prm, log_in is not None)
+        return y, log_out
+
+    @staticmethod
+    def backward(ctx, gy, glog):
+        x, out, mask = ctx.saved_tensors
+        parity, frozen_mode, prm, has_log = ctx.cfg
+        B, V = _bv(x)
+        gy, glog = _f32c(gy, "gy"), _f32c(glog, "glog")
+        gx, gout = torch.empty_like(x), torch.empty_like(out)
+        with _C.timed("rqs_bwd"):
+            check(lib().nfk_rqs_bwd(dev(x), dev(out), dev(mask, torch.uint8), parity, frozen_mode, prm, dev(gy),
+                                    dev(glog), dev(gx), dev(gout), B, V, stream()), "rqs_bwd")
+        return gx, gout, (glog if has_log else None), None, None, None, None
+
+
+def rqs_apply(x, out, mask, parity, prm, log0=0, frozen_mode=_C.FROZEN_COPY, inverse=False):
+    """RQSplineCoupling_.atomic_forward/backward incl. make_spline (couplings_.py:178-262)."""
+    mask = _mask_u8(mask)
+    log_in = as_log(log0, x)
+    if not inverse:
+        return _RqsFwd.apply(x, out, log_in, mask, int(parity), int(frozen_mode), prm)
+    _no_grad_needed(x, out, log_in)
+    x, out = _f32c(x, "x"), _f32c(out, "conditioner output")
+    B, V = _bv(x)
+    y = torch.empty_like(x)
+    log_out = torch.empty((B,), dtype=torch.float32, device=x.device)
+    check(lib().nfk_rqs_inv(dev(x), dev(out), dev(mask, torch.uint8), int(parity), int(frozen_mode), prm,
+                            dev(log_in), dev(y), dev(log_out), B, V, stream()), "rqs_inv")
+    return y, log_out
+
+
+# ---------------------------------------------------------------------------- pointwise chains
+class _Logistic(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, log_in, which):
+        x = _f32c(x, "x")
+        B, V = _bv(x)
+        y = torch.empty_like(x)
+        log_out = torch.empty((B,), dtype=torch.float32, device=x.device)
+        check(lib().nfk_logistic_fwd(dev(x), which, dev(log_in), dev(y), dev(log_out), B, V, stream()),
+              "logistic_fwd")
+        ctx.save_for_backward(x)
+        ctx.cfg = (which, log_in is not None)
+        return y, log_out
+
+    @staticmethod
+    def backward(ctx, gy, glog):
+        (x,) = ctx.saved_tensors
+        which, has_log = ctx.cfg
+        B, V = _bv(x)
+        gy, glog = _f32c(gy, "gy"), _f32c(glog, "glog")
+        gx = torch.empty_like(x)
+        check(lib().nfk_logistic_bwd(dev(x), which, dev(gy), dev(glog), dev(gx), B, V, stream()), "logistic_bwd")
+        return gx, (glog if has_log else None), None
+
+
+def logistic(x, which, log0=0):
+    """Expit_ (which=0) / Logit_ (which=1) forward with log-Jacobian (modules_.py:93-114)."""
+    return _Logistic.apply(x, as_log(log0, x), int(which))
+
+
+class _Spline1d(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, kx, ky, kd, log_in, left, right, logistic_wrap):
+        x = _f32c(x, "x")
+        knots = torch.stack([_f32c(kx, "knots_x"), _f32c(ky, "knots_y"), _f32c(kd, "knots_d")]).contiguous()
+        K = knots.shape[1]
+        B, V = _bv(x)
+        y = torch.empty_like(x)
+        log_out = torch.empty((B,), dtype=torch.float32, device=x.device)
+        p = knots.data_ptr()
+        check(lib().nfk_spline1d_fwd(dev(x), p, p + 4 * K, p + 8 * K, K, left, right, logistic_wrap, 0,
+                                     dev(log_in), dev(y), dev(log_out), B, V, stream()), "spline1d_fwd")
+        ctx.save_for_backward(x, knots)
+        ctx.cfg = (left, right, logistic_wrap, log_in is not None)
+        return y, log_out
+
+    @staticmethod
+    def backward(ctx, gy, glog):
+        x, knots = ctx.saved_tensors
+        left, right, logistic_wrap, has_log = ctx.cfg
+        K = knots.shape[1]
+        B, V = _bv(x)
+        gy, glog = _f32c(gy, "gy"), _f32c(glog, "glog")
+        gx = torch.empty_like(x)
+        gk = torch.zeros_like(knots)
+        p, q = knots.data_ptr(), gk.data_ptr()
+        check(lib().nfk_spline1d_bwd(dev(x), p, p + 4 * K, p + 8 * K, K, left, right, logistic_wrap,
+                                     dev(gy), dev(glog), dev(gx), q, q + 4 * K, q + 8 * K, B, V, stream()),
+              "spline1d_bwd")
+        return gx, gk[0], gk[1], gk[2], (glog if has_log else None), None, None, None
+
+
+def spline1d(x, kx, ky, kd, log0=0, extrap=None, logistic_wrap=False, inverse=False):
+    """One shared 1-D RQ spline over every element (SplineNet_), optionally wrapped as
+    Expit_ -> spline -> Logit_ (DistConvertor_) in a single kernel."""
+    extrap = extrap or {}
+    left, right = _C.EXTRAP[extrap.get('left')], _C.EXTRAP[extrap.get('right')]
+    log_in = as_log(log0, x)
+    if not inverse:
+        return _Spline1d.apply(x, kx, ky, kd, log_in, left, right, int(bool(logistic_wrap)))
+    _no_grad_needed(x, kx, ky, kd, log_in)
+    x = _f32c(x, "x")
+    knots = torch.stack([_f32c(kx, "knots_x"), _f32c(ky, "knots_y"), _f32c(kd, "knots_d")]).contiguous()
+    K = knots.shape[1]
+    B, V = _bv(x)
+    y = torch.empty_like(x)
+    log_out = torch.empty((B,), dtype=torch.float32, device=x.device)
+    p = knots.data_ptr()
+    check(lib().nfk_spline1d_fwd(dev(x), p, p + 4 * K, p + 8 * K, K, left, right, int(bool(logistic_wrap)), 1,
+                                 dev(log_in), dev(y), dev(log_out), B, V, stream()), "spline1d_fwd(inverse)")
+    return y, log_out
+
+
+# ---------------------------------------------------------------------------- action
+class _Phi4(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, phi, w0, w2, w4):
+        phi = _f32c(phi, "cfgs")
+        B = phi.shape[0]
+        lat = _C.lattice(phi.shape[1:])
+        S = torch.empty((B,), dtype=torch.float32, device=phi.device)
+        with _C.timed("phi4_action_fwd"):
+            check(lib().nfk_phi4_action_fwd(dev(phi), lat, w0, w2, w4, dev(S), B, stream()), "phi4_action_fwd")
+        ctx.save_for_backward(phi)
+        ctx.cfg = (lat, w0, w2, w4)
+        return S
+
+    @staticmethod
+    def backward(ctx, gS):
+        (phi,) = ctx.saved_tensors
+        lat, w0, w2, w4 = ctx.cfg
+        gS = _f32c(gS, "gS")
+        gphi = torch.empty_like(phi)
+        check(lib().nfk_phi4_action_bwd(dev(phi), lat, w0, w2, w4, dev(gS), dev(gphi), phi.shape[0], stream()),
+              "phi4_action_bwd")
+        return gphi, None, None, None
+
+
+def phi4_action(cfgs, w0, w2, w4):
+    """ScalarPhi4Action.action (scalar_action.py:38-46)."""
+    if cfgs.ndim < 2:
+        raise ValueError("cfgs must have a batch axis and at least one lattice axis")
+    return _Phi4.apply(cfgs, float(w0), float(w2), float(w4))
+
+
+# ---------------------------------------------------------------------------- conditioner
+def _conv_call(inp, w, transposed, bias, in_mask, in_keep, act, dact_from, dact_kind, shape, ksize, Ci, Co):
+    B = inp.shape[0]
+    out = torch.empty((B, Co) + tuple(shape), dtype=torch.float32, device=inp.device)
+    with _C.timed(f"conv_circ_fwd[{Ci}->{Co}]"):
+        check(lib().nfk_conv_circ_fwd(dev(inp), dev(w), int(transposed), dev(bias), dev(in_mask, torch.uint8),
+                                      int(in_keep), int(act), dev(dact_from), int(dact_kind), dev(out),
+                                      _C.lattice(shape), int(ksize), int(Ci), int(Co), B, stream()),
+              "conv_circ_fwd")
+    return out
+
+
+def _conv_weight_grad(inp, in_mask, in_keep, gpre, w_shape, want_bias, shape, ksize):
+    Co, Ci = w_shape[0], w_shape[1]
+    gw = torch.zeros(w_shape, dtype=torch.float32, device=inp.device)
+    gb = torch.zeros((Co,), dtype=torch.float32, device=inp.device) if want_bias else None
+    with _C.timed(f"conv_circ_bwd_weight[{Ci}->{Co}]"):
+        check(lib().nfk_conv_circ_bwd_weight(dev(inp), dev(in_mask, torch.uint8), int(in_keep), dev(gpre),
+                                             dev(gw), dev(gb), _C.lattice(shape), int(ksize), int(Ci), int(Co),
+                                             inp.shape[0], stream()), "conv_circ_bwd_weight")
+    return gw, gb
+
+
+class _ConvStack(torch.autograd.Function):
+    """A whole ConvAct stack (conv -> act)* as ONE autograd node.
+
+    forward keeps each layer's post-activation output; backward walks the layers in
+    reverse, each step one weight-gradient kernel plus one data-gradient kernel (the
+    same circular conv on transposed/flipped weights with act' fused in its epilogue).
+    """
+
+    @staticmethod
+    def forward(ctx, inp, in_mask, in_keep, acts, ksize, n_layers, *params):
+        inp = _f32c(inp, "conditioner input")
+        weights, biases = params[:n_layers], params[n_layers:]
+        shape = tuple(inp.shape[2:])
+        hs = [inp]
+        for i in range(n_layers):
+            w = _f32c(weights[i], "conv weight")
+            b = None if biases[i] is None else _f32c(biases[i], "conv bias")
+            Co, Ci = w.shape[0], w.shape[1]
+            if hs[-1].shape[1] != Ci:
+                raise ValueError(f"conv layer {i}: expected {Ci} input channels, got {hs[-1].shape[1]}")
+            hs.append(_conv_call(hs[-1], w, 0, b, in_mask if i == 0 else None, in_keep, acts[i], None, 0,
+                                 shape, ksize, Ci, Co))
+        ctx.save_for_backward(*hs, *[w for w in weights], *( [in_mask] if in_mask is not None else []))
+        ctx.cfg = (in_keep, acts, ksize, n_layers, shape, [b is not None for b in biases], in_mask is not None)
+        return hs[-1]
+
+    @staticmethod
+    def backward(ctx, gout):
+        in_keep, acts, ksize, n, shape, has_bias, has_mask = ctx.cfg
+        saved = ctx.saved_tensors
+        hs, weights = saved[:n + 1], saved[n + 1:2 * n + 1]
+        in_mask = saved[2 * n + 1] if has_mask else None
+        gpre = _f32c(gout, "gout")
+        if acts[n - 1] != 0:     # last layer had an activation: fold its derivative in first
+            raise NotImplementedError("ConvAct with an activation on the output layer: use the unfused path")
+        gws, gbs = [None] * n, [None] * n
+        for i in reversed(range(n)):
+            w = weights[i]
+            Co, Ci = w.shape[0], w.shape[1]
+            first = (i == 0)
+            gws[i], gbs[i] = _conv_weight_grad(hs[i], in_mask if first else None, in_keep, gpre,
+                                               tuple(w.shape), has_bias[i], shape, ksize)
+            if first and not ctx.needs_input_grad[0]:
+                gpre = None
+                break
+            # d/d(input of layer i): conv of gpre with w^T (taps flipped); multiply by act'(h_{i})
+            gpre = _conv_call(gpre, w.contiguous(), 1, None, None, 0, 0, hs[i] if not first else None,
+                              acts[i - 1] if not first else 0, shape, ksize, Co, Ci)
+        gin = None
+        if gpre is not None:
+            gin = gpre if in_mask is None else mask_select(gpre, in_mask, in_keep)
+        return (gin, None, None, None, None, None, *gws, *gbs)
+
+
+def conv_stack(inp, weights, biases, acts, ksize, in_mask=None, in_keep=0):
+    """ConvAct forward: (B,Ci,*L) -> (B,Co,*L), circular 'same' convs with fused
+    activations; `in_mask`/`in_keep` fuse Mask.split into the first layer."""
+    acts = tuple(_C.ACT[a] for a in acts)
+    if in_mask is not None:
+        in_mask = _mask_u8(in_mask)
+    return _ConvStack.apply(inp, in_mask, int(in_keep), acts, int(ksize), len(weights), *weights, *biases)
+
+
+# ---------------------------------------------------------------------------- mcmc
+def metropolis_scan(logq, logp, log_u, ref_state):
+    """Sequential accept/reject on the device (mcmc.py:304-328).  `ref_state` is a
+    float64[2] CUDA tensor {ref, has_ref}, updated in place.  Returns
+    (accept uint8[B], idx int64[B], n_accept int64[1])."""
+    logq, logp = _f32c(logq, "logq"), _f32c(logp, "logp")
+    B = logq.shape[0]
+    accept = torch.empty((B,), dtype=torch.uint8, device=logq.device)
+    idx = torch.empty((B,), dtype=torch.int64, device=logq.device)
+    n_acc = torch.empty((1,), dtype=torch.int64, device=logq.device)
+    check(lib().nfk_metropolis_scan(dev(logq), dev(logp), dev(log_u, torch.float64), dev(ref_state, torch.float64),
+                                    dev(accept, torch.uint8), dev(idx, torch.int64), dev(n_acc, torch.int64),
+                                    B, stream()), "metropolis_scan")
+    return accept, idx, n_acc
+
+
+def gather_rows(src, idx, prev=None):
+    """dst[i] = src[idx[i]] (idx >= 0) or prev (idx < 0)  (mcmc.py:67-75)."""
+    src = _f32c(src, "src")
+    B = src.shape[0]
+    row = src.numel() // max(B, 1)
+    dst = torch.empty_like(src)
+    if prev is not None:
+        prev = _f32c(prev, "prev")
+        if prev.numel() != row:
+            raise ValueError("gather_rows: `prev` must be one row")
+    check(lib().nfk_gather_rows(dev(src), dev(idx, torch.int64), dev(prev), dev(dst), B, row, stream()),
+          "gather_rows")
+    return dst

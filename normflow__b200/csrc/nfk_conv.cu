@@ -20,6 +20,7 @@ using namespace nfk;
 struct ConvArgs {
     const float* in;
     const float* w;
+    int w_transposed;
     const float* bias;
     const uint8_t* in_mask;
     int in_keep;
@@ -37,7 +38,16 @@ __global__ void __launch_bounds__(128) conv_fwd_kernel(ConvArgs a) {
     const int co0 = blockIdx.y * CO;
     for (int i = threadIdx.x; i < a.Ci * a.T * CO; i += blockDim.x) {
         const int co = i % CO, r = i / CO;        // r = ci*T + t
-        wt[i] = (co0 + co < a.Co) ? a.w[(int64_t)(co0 + co) * a.Ci * a.T + r] : 0.f;
+        float v = 0.f;
+        if (co0 + co < a.Co) {
+            if (!a.w_transposed) {
+                v = a.w[(int64_t)(co0 + co) * a.Ci * a.T + r];
+            } else {                              // forward weight is [Ci][Co][T]; flip the taps
+                const int ci = r / a.T, t = r % a.T;
+                v = a.w[((int64_t)ci * a.Co + co0 + co) * a.T + (a.T - 1 - t)];
+            }
+        }
+        wt[i] = v;
     }
     __syncthreads();
     const int64_t b = blockIdx.x / a.tiles;
@@ -58,7 +68,7 @@ __global__ void __launch_bounds__(128) conv_fwd_kernel(ConvArgs a) {
     }
 }
 
-extern "C" int nfk_conv_circ_fwd(const float* in, const float* w, const float* bias,
+extern "C" int nfk_conv_circ_fwd(const float* in, const float* w, int w_transposed, const float* bias,
                                  const uint8_t* in_mask, int in_keep,
                                  int act, const float* dact_from, int dact_kind,
                                  float* out, nfk_lattice lat, int ksize,
@@ -66,7 +76,7 @@ extern "C" int nfk_conv_circ_fwd(const float* in, const float* w, const float* b
     if (!in || !w || !out || !lat_ok(lat) || ksize < 1 || ksize % 2 == 0 || Ci < 1 || Co < 1) return NFK_EINVAL;
     if (B <= 0) return NFK_OK;
     ConvArgs a;
-    a.in = in; a.w = w; a.bias = bias; a.in_mask = in_mask; a.in_keep = in_keep;
+    a.in = in; a.w = w; a.w_transposed = w_transposed; a.bias = bias; a.in_mask = in_mask; a.in_keep = in_keep;
     a.act = act; a.dact_from = dact_from; a.dact_kind = dact_kind; a.out = out;
     a.lat = to_lat(lat); a.ksize = ksize; a.Ci = Ci; a.Co = Co;
     a.V = (int)lat_volume(lat);

@@ -1,0 +1,182 @@
+"""Mask-based coupling layers (reference src/nn/scalar/couplings_.py).
+
+The reference splits the field into two zero-interleaved halves, runs each atomic step
+through ~10 (affine) to ~100 (spline) ATen launches and adds the halves back.  Here a
+step is: conditioner -> ONE kernel that reads the field and the conditioner output,
+tests the site's partition, applies the transform, passes frozen sites through and
+reduces log|det J| per sample.  `Coupling_` itself keeps the reference's generic
+split / atomic_* / cat dataflow for subclasses that only define `atomic_forward` and
+`atomic_backward`.
+"""
+
+import numpy as np
+import torch
+
+from .._core import Module_
+from ... import _ops, _C
+from .modules import ConvAct
+
+
+class Coupling_(Module_):
+    """A list of atomic coupling steps acting alternately on the two partitions of
+    `mask`; step k updates partition k % 2 conditioned on the other one
+    (reference couplings_.py:22-103)."""
+
+    def __init__(self, nets, *, mask, channels_axis=1, label='coupling_'):
+        super().__init__(label=label)
+        self.nets = torch.nn.ModuleList(nets)
+        self.mask = mask
+        self.channels_axis = channels_axis
+
+    # ---- generic dataflow (reference couplings_.py:54-78) -------------------------
+    def forward(self, x, log0=0):
+        parts = list(self.mask.split(x))
+        for k, net in enumerate(self.nets):
+            p = k % 2
+            parts[p], log0 = self.atomic_forward(x_active=parts[p], x_frozen=parts[1 - p],
+                                                 parity=p, net=net, log0=log0)
+        return self.mask.cat(*parts), log0
+
+    def backward(self, x, log0=0):
+        parts = list(self.mask.split(x))
+        for k in reversed(range(len(self.nets))):
+            p = k % 2
+            parts[p], log0 = self.atomic_backward(x_active=parts[p], x_frozen=parts[1 - p],
+                                                  parity=p, net=self.nets[k], log0=log0)
+        return self.mask.cat(*parts), log0
+
+    def atomic_forward(self, *, x_active, x_frozen, parity, net, log0=0):
+        raise NotImplementedError
+
+    def atomic_backward(self, *, x_active, x_frozen, parity, net, log0=0):
+        raise NotImplementedError
+
+    def preprocess_fz(self, x):
+        return x.unsqueeze(self.channels_axis)
+
+    def preprocess(self, x):
+        return x.unsqueeze(self.channels_axis)
+
+    def postprocess(self, x):
+        return x.squeeze(self.channels_axis)
+
+    def transfer(self, scale_factor=1, mask=None, **extra):
+        return self.__class__([net.transfer(scale_factor=scale_factor) for net in self.nets],
+                              mask=self.mask if mask is None else mask,
+                              label=self.label, channels_axis=self.channels_axis)
+
+    # ---- full-field fast path ------------------------------------------------------
+    def _conditioner(self, net, x, parity):
+        """Conditioner output for the step that updates partition `parity`: the net sees
+        the frozen partition only, zero elsewhere, as one channel (couplings_.py:88-89).
+        A ConvAct reads `x` directly and applies the partition test in its first layer."""
+        if self.channels_axis != 1:
+            raise NotImplementedError("the accelerated couplings assume channels_axis == 1")
+        frozen_keep = 0 if parity == 0 else 1       # mask value of the frozen partition
+        if isinstance(net, ConvAct) and net.fusable:
+            return net.forward_masked(x, self.mask._mask, frozen_keep)
+        return net(_ops.mask_select(x, self.mask._mask, frozen_keep).unsqueeze(1))
+
+    def _sweep(self, x, log0, inverse):
+        order = range(len(self.nets))
+        for k in (reversed(order) if inverse else order):
+            p = k % 2
+            out = self._conditioner(self.nets[k], x, p)
+            x, log0 = self._apply(x, out, p, log0, _C.FROZEN_COPY, inverse)
+        return x, log0
+
+    def _apply(self, x, out, parity, log0, frozen_mode, inverse):
+        raise NotImplementedError
+
+
+class ShiftCoupling_(Coupling_):
+    """x_active +- t(x_frozen); unit Jacobian (reference couplings_.py:107-116)."""
+
+    def forward(self, x, log0=0):
+        return self._sweep(x, log0, inverse=False)
+
+    def backward(self, x, log0=0):
+        return self._sweep(x, log0, inverse=True)
+
+    def _apply(self, x, out, parity, log0, frozen_mode, inverse):
+        return _ops.shift_apply(x, out, self.mask._mask, parity, frozen_mode, inverse), log0
+
+    def atomic_forward(self, *, x_active, x_frozen, parity, net, log0=0):
+        out = net(self.preprocess_fz(x_frozen))
+        return self._apply(x_active, out, parity, log0, _C.FROZEN_ZERO, False)
+
+    def atomic_backward(self, *, x_active, x_frozen, parity, net, log0=0):
+        out = net(self.preprocess_fz(x_frozen))
+        return self._apply(x_active, out, parity, log0, _C.FROZEN_ZERO, True)
+
+
+class AffineCoupling_(Coupling_):
+    """y = t + x exp(-|s|), log|J| = -sum |s|  (reference couplings_.py:120-139)."""
+
+    def forward(self, x, log0=0):
+        return self._sweep(x, log0, inverse=False)
+
+    def backward(self, x, log0=0):
+        return self._sweep(x, log0, inverse=True)
+
+    def _apply(self, x, out, parity, log0, frozen_mode, inverse):
+        return _ops.affine_apply(x, out, self.mask._mask, parity, log0, frozen_mode, inverse)
+
+    def atomic_forward(self, *, x_active, x_frozen, parity, net, log0=0):
+        out = net(self.preprocess_fz(x_frozen))
+        return self._apply(x_active, out, parity, log0, _C.FROZEN_ZERO, False)
+
+    def atomic_backward(self, *, x_active, x_frozen, parity, net, log0=0):
+        out = net(self.preprocess_fz(x_frozen))
+        return self._apply(x_active, out, parity, log0, _C.FROZEN_ZERO, True)
+
+
+class RQSplineCoupling_(Coupling_):
+    """Monotone rational-quadratic spline per site, knots from the conditioner
+    (reference couplings_.py:143-275).  With K knots the conditioner emits 3K-2
+    channels: K-1 bin widths and K-1 bin heights (softmax -> cumulative sum over
+    `xlim` / `ylim`) and K knot derivatives (softplus with beta = ln 2, so a zero
+    input gives derivative 1).
+
+        extrap = {'left': 'linear', 'right': 'linear'}   # straight lines outside xlim
+    """
+
+    def __init__(self, nets, *, mask, xlim=(0, 1), ylim=(0, 1), knots_x=None, knots_y=None,
+                 extrap={}, **kwargs):
+        super().__init__(nets, mask=mask, **kwargs)
+        if knots_x is not None or knots_y is not None:
+            raise NotImplementedError("RQSplineCoupling_ with fixed knots_x / knots_y is outside the "
+                                      "accelerated hot path")
+        self.xlim, self.xwidth = xlim, xlim[1] - xlim[0]
+        self.ylim, self.ywidth = ylim, ylim[1] - ylim[0]
+        self.knots_x, self.knots_y = knots_x, knots_y
+        self.extrap = extrap
+
+    def forward(self, x, log0=0):
+        return self._sweep(x, log0, inverse=False)
+
+    def backward(self, x, log0=0):
+        return self._sweep(x, log0, inverse=True)
+
+    def _params(self, out):
+        n = out.shape[self.channels_axis]
+        if (n + 2) % 3 != 0:
+            raise ValueError(f"conditioner emits {n} channels; an RQ spline needs 3K-2")
+        return _ops.rqs_params((n + 2) // 3, self.xlim, self.ylim, self.extrap)
+
+    def _apply(self, x, out, parity, log0, frozen_mode, inverse):
+        return _ops.rqs_apply(x, out, self.mask._mask, parity, self._params(out), log0, frozen_mode, inverse)
+
+    def atomic_forward(self, *, x_active, x_frozen, parity, net, log0=0):
+        out = net(self.preprocess_fz(x_frozen))
+        return self._apply(x_active, out, parity, log0, _C.FROZEN_ZERO, False)
+
+    def atomic_backward(self, *, x_active, x_frozen, parity, net, log0=0):
+        out = net(self.preprocess_fz(x_frozen))
+        return self._apply(x_active, out, parity, log0, _C.FROZEN_ZERO, True)
+
+    def transfer(self, scale_factor=1, mask=None, **extra):
+        return self.__class__([net.transfer(scale_factor=scale_factor) for net in self.nets],
+                              mask=self.mask if mask is None else mask, label=self.label,
+                              channels_axis=self.channels_axis, xlim=self.xlim, ylim=self.ylim,
+                              knots_x=self.knots_x, knots_y=self.knots_y, extrap=self.extrap)

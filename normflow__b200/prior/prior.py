@@ -1,0 +1,111 @@
+"""Prior distributions (reference src/prior/prior.py).
+
+`NormalPrior.sample_` draws the batch AND its log-density in one kernel: Philox4x32-10
++ Box-Muller writes x once and a block reduction yields logr[B] (the reference makes
+one sampling pass and ~5 elementwise passes, prior.py:23-36).
+"""
+
+import numpy as np
+import torch
+
+from .. import _ops
+
+
+class Prior:
+    """Interface of a prior: sample, sample_ (with log-density), log_prob, to, shape, nvar."""
+
+    propagate_density = False
+
+    def sample(self, batch_size=1):
+        raise NotImplementedError
+
+    def sample_(self, batch_size=1):
+        raise NotImplementedError
+
+    def log_prob(self, x):
+        raise NotImplementedError
+
+    @staticmethod
+    def manual_seed(seed):
+        """Same convention as the reference (prior.py:38-41): an int seeds torch's
+        default generator, which is where the Philox key is taken from."""
+        if isinstance(seed, int):
+            torch.manual_seed(seed)
+
+    @property
+    def nvar(self):
+        return int(np.prod(self.shape))
+
+
+class NormalPrior(Prior):
+    """Independent normal variables with site-wise `loc` and `scale`
+    (reference NormalPrior, prior.py:92-125).  Give either `shape` (standard normal)
+    or `loc` and `scale` tensors of the lattice shape."""
+
+    def __init__(self, loc=None, scale=None, shape=None, seed=None, **kwargs):
+        if shape is not None:
+            shape = (shape,) if isinstance(shape, int) else tuple(shape)
+            self._standard = True
+            loc, scale = torch.zeros(shape), torch.ones(shape)
+        else:
+            if loc is None or scale is None:
+                raise ValueError("NormalPrior needs `shape`, or `loc` and `scale`")
+            self._standard = False
+            loc, scale = torch.as_tensor(loc), torch.as_tensor(scale)
+            shape = tuple(loc.shape)
+        self.shape = shape
+        self._loc = loc.to(torch.float32).contiguous()
+        self._scale = scale.to(torch.float32).contiguous()
+        self._calls = 0          # Philox stream offset: one stream per draw
+        Prior.manual_seed(seed)
+
+    # the reference exposes the torch distribution object as `.dist`
+    @property
+    def dist(self):
+        return torch.distributions.normal.Normal(self._loc, self._scale)
+
+    def _args(self):
+        if self._standard:
+            return None, None
+        return self._loc, self._scale
+
+    def _draw(self, batch_size, with_logprob):
+        if not self._loc.is_cuda:
+            raise RuntimeError("NormalPrior: sampling runs on CUDA only; move the prior with "
+                               ".to('cuda') (normflow__b200 has no CPU fallback)")
+        loc, scale = self._args()
+        self._calls += 1
+        return _ops.prior_sample(int(batch_size), self.shape, loc, scale,
+                                 seed=torch.initial_seed(), offset=self._calls,
+                                 device=self._loc.device, with_logprob=with_logprob)
+
+    def sample(self, batch_size=1):
+        return self._draw(batch_size, False)[0]
+
+    def sample_(self, batch_size=1):
+        """(x, log r(x)) -- reference prior.py:26-28."""
+        return self._draw(batch_size, True)
+
+    def log_prob(self, x):
+        """sum over sites of the normal log-density (reference prior.py:30-36)."""
+        if self.propagate_density:
+            raise NotImplementedError("propagate_density is not part of the accelerated path")
+        loc, scale = self._args()
+        return _ops.prior_logprob(x, loc, scale)
+
+    def to(self, *args, **kwargs):
+        """Move loc/scale; samples are created on the same device (prior.py:110-116).
+        The kernels are float32, so a dtype request other than float32 is refused."""
+        dtype = kwargs.get('dtype', None)
+        for a in args:
+            if isinstance(a, torch.dtype):
+                dtype = a
+        if dtype not in (None, torch.float32):
+            raise TypeError("normflow__b200 runs in float32 only")
+        kwargs = {k: v for k, v in kwargs.items() if not (k == 'dtype' and v is None)}
+        self._loc = self._loc.to(*args, **kwargs)
+        self._scale = self._scale.to(*args, **kwargs)
+
+    @property
+    def parameters(self):
+        return dict(loc=self._loc, scale=self._scale)

@@ -164,7 +164,7 @@ int cpu_phi4_action_bwd(const float* phi, nfk_lattice lat, float w0, float w2, f
     return 0;
 }
 // same staging as conv_fwd_kernel<8>: weights re-laid as [Ci*T][8] per channel block
-int cpu_conv_circ_fwd(const float* in, const float* w, const float* bias, const uint8_t* in_mask, int in_keep,
+int cpu_conv_circ_fwd(const float* in, const float* w, int w_transposed, const float* bias, const uint8_t* in_mask, int in_keep,
                       int act, const float* dact_from, int dact_kind, float* out, nfk_lattice lat, int ksize,
                       int Ci, int Co, int64_t B) {
     const Lat l = make_lat(lat.ndim, lat.shape);
@@ -175,7 +175,16 @@ int cpu_conv_circ_fwd(const float* in, const float* w, const float* bias, const 
     for (int co0 = 0; co0 < Co; co0 += CO) {
         for (int i = 0; i < Ci * T * CO; ++i) {
             const int co = i % CO, r = i / CO;
-            wt[i] = (co0 + co < Co) ? w[(int64_t)(co0 + co) * Ci * T + r] : 0.f;
+            float v = 0.f;
+            if (co0 + co < Co) {
+                if (!w_transposed) {
+                    v = w[(int64_t)(co0 + co) * Ci * T + r];
+                } else {
+                    const int ci = r / T, t = r % T;
+                    v = w[((int64_t)ci * Co + co0 + co) * T + (T - 1 - t)];
+                }
+            }
+            wt[i] = v;
         }
         for (int64_t b = 0; b < B; ++b)
             for (int s = 0; s < V; ++s) {

@@ -263,7 +263,7 @@ def test_conv_layers(tag):
         b = f32(g[f"{tag}_b{i}"]) if f"{tag}_b{i}" in g.files else None
         Co, Ci = w.shape[:2]
         out = np.empty((B, Co) + shape, dtype=np.float32)
-        H.cpu_conv_circ_fwd(fp(h), fp(w), fp(b), None, 0, 1 if i < n - 1 else 0, None, 0, fp(out),
+        H.cpu_conv_circ_fwd(fp(h), fp(w), 0, fp(b), None, 0, 1 if i < n - 1 else 0, None, 0, fp(out),
                             lattice(shape), 3, Ci, Co, I64(B))
         h = out
     close(h, g[f"{tag}_out"])
@@ -285,7 +285,7 @@ def test_whole_rqs_stack_through_harness():
             Co, Ci = w.shape[:2]
             out = np.empty((B, Co) + shape, dtype=np.float32)
             # first layer reads the frozen partition only: mask.split fused in
-            H.cpu_conv_circ_fwd(fp(h), fp(w), None, up(mask) if i == 0 else None, 0 if p == 0 else 1,
+            H.cpu_conv_circ_fwd(fp(h), fp(w), 0, None, up(mask) if i == 0 else None, 0 if p == 0 else 1,
                                 1 if i < 2 else 0, None, 0, fp(out), lattice(shape), 3, Ci, Co, I64(B))
             h = out
         if k < 4:
@@ -339,3 +339,48 @@ def test_spline1d_knot_gradients(logistic, left, right, lim):
         for j in range(2):
             got[j * K] = got[j * K + K - 1] = 0.0
     close_grad(got, ref, tol=2e-5)
+
+
+@pytest.mark.parametrize("tag", ["d1", "d2", "d3", "d4"])
+def test_conv_backward_chain(tag):
+    """Data gradient through a ConvAct stack with the SAME conv routine run on the
+    transposed / tap-flipped weights and the activation derivative fused in its
+    epilogue (what ConvAct's backward does on the device); weight gradients formed
+    from those pre-activation gradients in numpy."""
+    from oracle import nf_oracle as O
+    g = load_golden("conv")
+    n = len(g[f"{tag}_hidden"]) + 1
+    x = f32(g[f"{tag}_x"])
+    B, shape = x.shape[0], x.shape[2:]
+    nd = len(shape)
+    ws = [f32(g[f"{tag}_w{i}"]) for i in range(n)]
+    bs = [f32(g[f"{tag}_b{i}"]) if f"{tag}_b{i}" in g.files else None for i in range(n)]
+    acts = [x]
+    for i in range(n):
+        Co, Ci = ws[i].shape[:2]
+        out = np.empty((B, Co) + shape, dtype=np.float32)
+        H.cpu_conv_circ_fwd(fp(acts[-1]), fp(ws[i]), 0, fp(bs[i]), None, 0, 1 if i < n - 1 else 0, None, 0,
+                            fp(out), lattice(shape), 3, Ci, Co, I64(B))
+        acts.append(out)
+    gpre = f32(g[f"{tag}_r"])
+    names = sorted(k for k in g.files if k.startswith(f"{tag}_grad_") and k.endswith("weight"))
+    for i in reversed(range(n)):
+        Co, Ci = ws[i].shape[:2]
+        # weight gradient: gw[o,c,tap] = sum_{b,s} gpre[b,o,s] in[b,c,s+tap-1]
+        gw = np.zeros(ws[i].shape)
+        import itertools
+        for tap in itertools.product(range(3), repeat=nd):
+            sh = acts[i].astype(np.float64)
+            for ax, t in enumerate(tap):
+                sh = np.roll(sh, -(t - 1), axis=2 + ax)
+            gw[(slice(None), slice(None)) + tap] = np.tensordot(
+                gpre.astype(np.float64), sh, axes=([0] + list(range(2, 2 + nd)), [0] + list(range(2, 2 + nd))))
+        ref = g[names[i]]
+        if tag == "d4":      # stored Conv4d layout (Co*k0, Ci, k,k,k) -> standard
+            ref = O.conv4d_lower_to_standard(ref, Co, 3)
+        close_grad(gw, ref, tol=2e-5)
+        gin = np.empty((B, Ci) + shape, dtype=np.float32)
+        H.cpu_conv_circ_fwd(fp(gpre), fp(ws[i]), 1, None, None, 0, 0, fp(acts[i]) if i > 0 else None, 1,
+                            fp(gin), lattice(shape), 3, Co, Ci, I64(B))
+        gpre = gin
+    close_grad(gpre, g[f"{tag}_gx"], tol=2e-5)

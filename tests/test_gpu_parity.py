@@ -1,0 +1,622 @@
+"""Parity tests proper: the CUDA path, called through the package's public API (which
+goes through the C ABI of libnormflow_b200.so), against
+  * the golden fixtures produced by the reference itself (tests/golden/*.npz),
+  * the numpy oracle on seeded inputs at sizes it finishes in seconds,
+  * size-independent properties at the full BASELINE sizes (round trips, known answers).
+Tolerance (north_star): fields / log|det J| / action / loss within 1e-5 * max(|ref|, 1);
+mask indexing and accept/reject decisions bit-exact."""
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import nf_oracle as O
+
+import normflow__b200 as nf
+from normflow__b200 import Model, _ops, _C, backward_sanitychecker
+from normflow__b200.action import ScalarPhi4Action
+from normflow__b200.mask import EvenOddMask
+from normflow__b200.nn import (ModuleList_, ConvAct, AffineCoupling_, RQSplineCoupling_, ShiftCoupling_,
+                               DistConvertor_, Expit_, Logit_)
+from normflow__b200.prior import NormalPrior
+from normflow__b200.lib.spline import RQSpline
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+ACTION = dict(kappa=0.67, m_sq=-4 * 0.67, lambd=0.5)
+
+
+def cu(a, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(a)).to(dtype).to(DEV)
+
+
+def close(got, ref, tol=1e-5):
+    got = got.detach().double().cpu().numpy() if torch.is_tensor(got) else np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    err = np.abs(got - ref)
+    bound = tol * np.maximum(np.abs(ref), 1.0)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    assert np.all(err <= bound), f"max excess {np.max(err / bound):.3g} (abs err {err.max():.3g})"
+
+
+def close_grad(got, ref, tol=1e-5):
+    """gradients: error against the scale of the whole gradient tensor"""
+    got = got.detach().double().cpu().numpy()
+    ref = np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    err = np.abs(got - ref).max()
+    assert err <= tol * max(np.abs(ref).max(), 1.0), f"abs err {err:.3g} vs scale {np.abs(ref).max():.3g}"
+
+
+def test_library_loaded_and_counts_launches():
+    n0 = _C.launch_count()
+    ScalarPhi4Action(**ACTION)(torch.zeros(2, 4, 4, device=DEV))
+    assert _C.launch_count() == n0 + 1
+
+
+# ------------------------------------------------------------------ masks
+def test_mask_kernels_bit_exact():
+    g = load_golden("masks")
+    for key in g.files:
+        if not key.endswith("_meta"):
+            continue
+        tag, meta = key[:-5], g[key]
+        parity, mu, shape = int(meta[0]), int(meta[1]), tuple(int(v) for v in meta[2:])
+        if tag.startswith("eo_"):
+            m = _ops.make_evenodd_mask(shape, parity, None if mu < 0 else mu, DEV)
+        else:
+            m = _ops.make_alongaxis_mask(shape, parity, mu, DEV)
+        assert np.array_equal(m.cpu().numpy(), g[tag + "_mask"])
+    big = _ops.make_evenodd_mask((16, 16, 16, 16), 0, None, DEV).cpu().numpy()
+    assert np.array_equal(big, EvenOddMask(shape=(16, 16, 16, 16))._mask.cpu().numpy())
+    assert big.sum() == big.size // 2
+
+
+def test_mask_split_cat_purify():
+    mask = EvenOddMask(shape=(6, 4))
+    x = torch.randn(3, 6, 4, device=DEV)
+    x0, x1 = mask.split(x)
+    m = mask._mask.float()
+    assert torch.equal(x0, x * m) and torch.equal(x1, x * (1 - m))
+    assert torch.equal(mask.cat(x0, x1), x)
+    assert torch.equal(mask.purify(x, 1), x * (1 - m))
+
+
+# ------------------------------------------------------------------ action
+def test_action_golden_and_gradient():
+    g = load_golden("action")
+    act = ScalarPhi4Action(**ACTION)
+    for i in range(9):
+        cfgs = cu(g[f"a{i}_cfgs"]).requires_grad_(True)
+        S = act(cfgs)
+        close(S, g[f"a{i}_S"])
+        (gr,) = torch.autograd.grad((S * cu(g[f"a{i}_gS"])).sum(), cfgs)
+        close(gr, g[f"a{i}_gcfgs"])
+        close(act.action_density(cfgs.detach()).reshape(6, -1).sum(1), g[f"a{i}_S"], tol=2e-5)
+    close(ScalarPhi4Action(kappa=0, m_sq=-1.2, lambd=0.5)(cu(g["zd_cfgs"])), g["zd_S"])
+    close(ScalarPhi4Action(kappa=0.5, m_sq=0.3, lambd=0.2, a=0.5)(cu(g["lat_cfgs"])), g["lat_S"])
+
+
+@pytest.mark.parametrize("shape,expect", [((16, 16), -123.84), ((64, 64), -1981.44), ((32, 32, 32), -15851.52),
+                                          ((16, 16, 16, 16), -31703.04)])
+def test_action_constant_field_full_sizes(shape, expect):
+    S = ScalarPhi4Action(**ACTION)(torch.full((3,) + shape, 1.5, device=DEV))
+    close(S, np.full(3, expect), tol=2e-6)
+
+
+def test_action_short_axes_and_oracle_large():
+    assert np.isclose(ScalarPhi4Action(kappa=1, m_sq=1, lambd=0)(cu([[3.0]])).item(), 4.5)
+    assert np.isclose(ScalarPhi4Action(kappa=1, m_sq=1, lambd=0)(cu([[1.0, 2.0]])).item(), 3.5)
+    rs = np.random.RandomState(5)
+    for shape in [(64, 64), (12, 10, 14), (6, 5, 7, 4)]:
+        x = rs.randn(5, *shape).astype(np.float32)
+        close(ScalarPhi4Action(**ACTION)(cu(x)), O.phi4_action(x.astype(np.float64), **ACTION))
+
+
+# ------------------------------------------------------------------ prior
+def test_prior_logprob_golden():
+    g = load_golden("prior")
+    close(NormalPrior(shape=(4, 6)).log_prob(cu(g["std_x"])), g["std_logr"])
+    prior = NormalPrior(loc=cu(g["gen_loc"]), scale=cu(g["gen_scale"]))
+    close(prior.log_prob(cu(g["gen_x"])), g["gen_logr"])
+
+
+def test_prior_sampler():
+    torch.manual_seed(1234)
+    prior = NormalPrior(shape=(64, 64))
+    x, logr = prior.sample_(512)
+    assert x.shape == (512, 64, 64) and logr.shape == (512,) and x.dtype == torch.float32
+    close(logr, O.normal_log_prob(x.double().cpu().numpy()))
+    close(prior.log_prob(x), O.normal_log_prob(x.double().cpu().numpy()))
+    n = x.numel()
+    assert abs(x.mean().item()) < 5 / np.sqrt(n) and abs(x.var().item() - 1) < 5 * np.sqrt(2 / n)
+    assert abs((x ** 4).mean().item() - 3) < 0.05
+    x2 = prior.sample(512)
+    assert not torch.equal(x, x2)                       # a new stream per call
+    assert abs(torch.corrcoef(torch.stack([x.ravel(), x2.ravel()]))[0, 1].item()) < 0.01
+    torch.manual_seed(1234)
+    again = NormalPrior(shape=(64, 64)).sample(512)     # same seed, same call index -> same draw
+    assert torch.equal(x, again)
+    # site-wise loc / scale
+    loc, scale = torch.linspace(-1, 1, 6, device=DEV).reshape(2, 3), torch.linspace(0.5, 2, 6, device=DEV).reshape(2, 3)
+    p2 = NormalPrior(loc=loc, scale=scale)
+    xs, lr = p2.sample_(40000)
+    assert torch.allclose(xs.mean(0), loc, atol=0.05) and torch.allclose(xs.std(0), scale, rtol=0.03)
+    close(lr, O.normal_log_prob(xs.double().cpu().numpy(), loc.double().cpu().numpy(), scale.double().cpu().numpy()),
+          tol=2e-5)
+    # zero-dim prior (config 1)
+    x0, l0 = NormalPrior(shape=1).sample_(128)
+    assert x0.shape == (128, 1)
+    close(l0, O.normal_log_prob(x0.double().cpu().numpy()))
+
+
+# ------------------------------------------------------------------ kernel-only coupling steps
+def test_affine_kernel_golden():
+    g = load_golden("affine_kernel")
+    mask = cu(g["mask"], torch.uint8)
+    out0 = cu(g["out"])
+    for parity in (0, 1):
+        m = g["mask"] if parity == 0 else 1 - g["mask"]
+        xa = cu(g["x"] * m).requires_grad_(True)
+        out = out0.clone().requires_grad_(True)
+        y, logJ = _ops.affine_apply(xa, out, mask, parity, 0, _C.FROZEN_ZERO)
+        close(y, g[f"p{parity}_fx"])
+        close(logJ, g[f"p{parity}_logJ"])
+        L = (y * cu(g["r"])).sum() + (logJ * cu(g["c"])).sum()
+        gx, go = torch.autograd.grad(L, [xa, out])
+        act = m.astype(bool)
+        close(gx[:, torch.as_tensor(act)], g[f"p{parity}_gx"][:, act])
+        close(go, g[f"p{parity}_gout"])
+        with torch.no_grad():
+            xi, li = _ops.affine_apply(y.detach(), out0, mask, parity, 0, _C.FROZEN_ZERO, inverse=True)
+        close(xi, g[f"p{parity}_xinv"])
+        close(li, g[f"p{parity}_loginv"])
+
+
+@pytest.mark.parametrize("tag,extrap", [("lin", dict(left='linear', right='linear')), ("none", {}),
+                                        ("mixed", dict(left='linear'))])
+def test_rqs_kernel_golden(tag, extrap):
+    g = load_golden("rqs_kernel")
+    mask = cu(g[f"{tag}_mask"], torch.uint8)
+    prm = _ops.rqs_params(10, (-5, 5), (-4, 6), extrap)
+    for parity in (0, 1):
+        m = g[f"{tag}_mask"] if parity == 0 else 1 - g[f"{tag}_mask"]
+        xa = cu(g[f"{tag}_x"] * m).requires_grad_(True)
+        out = cu(g[f"{tag}_out"]).requires_grad_(True)
+        y, logJ = _ops.rqs_apply(xa, out, mask, parity, prm, 0, _C.FROZEN_ZERO)
+        close(y, g[f"{tag}_p{parity}_fx"])
+        close(logJ, g[f"{tag}_p{parity}_logJ"])
+        L = (y * cu(g[f"{tag}_r"])).sum() + (logJ * cu(g[f"{tag}_c"])).sum()
+        gx, go = torch.autograd.grad(L, [xa, out])
+        close_grad(gx, g[f"{tag}_p{parity}_gx"])
+        close_grad(go, g[f"{tag}_p{parity}_gout"])
+        if tag == "lin":
+            with torch.no_grad():
+                xi, li = _ops.rqs_apply(y.detach(), out.detach(), mask, parity, prm, logJ.detach(),
+                                        _C.FROZEN_ZERO, inverse=True)
+            close(xi, (g[f"{tag}_x"] * m), tol=3e-5)
+            close(li, np.zeros(li.shape[0]), tol=3e-5)
+
+
+def test_rqs_every_supported_knot_count():
+    """K is a template parameter of the kernel: each instantiation against the oracle."""
+    rs = np.random.RandomState(2)
+    shape, B = (6, 6), 3
+    mask_np = O.evenodd_mask(shape)
+    mask = cu(mask_np, torch.uint8)
+    x = (rs.randn(B, *shape) * 2.5).astype(np.float32)
+    for K in (2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 16, 20, 24, 32):
+        out = (rs.randn(B, 3 * K - 2, *shape) * 0.5).astype(np.float32)
+        prm = _ops.rqs_params(K, (-5, 5), (-5, 5), dict(left='linear', right='linear'))
+        y, logJ = _ops.rqs_apply(cu(x), cu(out), mask, 1, prm, 0, _C.FROZEN_COPY)
+        xa = O.mask_purify(mask_np, x.astype(np.float64), 1)
+        fr, lr = O.rqs_atomic(xa, out.astype(np.float64), mask_np, 1, 0.0, xlim=(-5, 5), ylim=(-5, 5),
+                              extrap=dict(left='linear', right='linear'))
+        close(y, fr + x * mask_np, tol=2e-5)
+        close(logJ, lr, tol=2e-5)
+    with pytest.raises(RuntimeError, match="unsupported"):
+        _ops.rqs_apply(cu(x), cu(rs.randn(B, 37, *shape)), mask, 1,
+                       _ops.rqs_params(13, (-5, 5), (-5, 5), {}), 0, _C.FROZEN_COPY)
+
+
+# ------------------------------------------------------------------ conditioner
+def _load_convact(net, g, prefix):
+    convs = net._convs()
+    with torch.no_grad():
+        for i, conv in enumerate(convs):
+            if hasattr(conv, "_conv_lower_dim"):
+                conv._conv_lower_dim.weight.copy_(cu(g[f"{prefix}_wlower{i}"]))
+            else:
+                conv.weight.copy_(cu(g[f"{prefix}_w{i}"]))
+            if conv.bias is not None:
+                conv.bias.copy_(cu(g[f"{prefix}_b{i}"]))
+
+
+@pytest.mark.parametrize("tag,shape,hidden,P,bias", [("d1", (9,), (4,), 3, True), ("d2", (6, 5), (8, 8), 28, False),
+                                                     ("d3", (4, 3, 5), (4,), 2, True),
+                                                     ("d4", (3, 4, 3, 4), (3,), 2, True)])
+def test_convact_golden(tag, shape, hidden, P, bias):
+    g = load_golden("conv")
+    net = ConvAct(1, P, 3, conv_dim=len(shape), hidden_sizes=list(hidden),
+                  acts=(*['tanh'] * len(hidden), None), bias=bias).to(DEV)
+    _load_convact(net, g, tag)
+    x = cu(g[f"{tag}_x"]).requires_grad_(True)
+    out = net(x)
+    close(out, g[f"{tag}_out"])
+    grads = torch.autograd.grad((out * cu(g[f"{tag}_r"])).sum(), [x] + list(net.parameters()))
+    close_grad(grads[0], g[f"{tag}_gx"], tol=2e-5)
+    for (name, _), gr in zip(net.named_parameters(), grads[1:]):
+        close_grad(gr, g[f"{tag}_grad_{name}"], tol=2e-5)
+
+
+def test_convact_unfused_path_equals_fused():
+    torch.manual_seed(3)
+    fused = ConvAct(1, 2, 3, hidden_sizes=[4], acts=['tanh', None], bias=True).to(DEV)
+    slow = ConvAct(1, 2, 3, hidden_sizes=[4], acts=['abs', None], bias=True).to(DEV)     # 'abs' is not fusable
+    assert fused.fusable and not slow.fusable
+    x = torch.randn(2, 1, 8, 8, device=DEV)
+    ref = torch.nn.functional.conv2d(torch.nn.functional.pad(x, (1, 1, 1, 1), mode='circular'),
+                                     fused[0].weight, fused[0].bias)
+    close(fused[0](x), ref.double().cpu().numpy())
+    out = slow(x)
+    assert out.shape == (2, 2, 8, 8) and torch.isfinite(out).all()
+
+
+# ------------------------------------------------------------------ whole coupling stacks
+def _build_stack(g, bias):
+    shape = tuple(int(v) for v in g["shape"])
+    hidden = [int(v) for v in g["hidden"]]
+    acts = tuple(None if a == 'none' else str(a) for a in g["acts"])
+    mask = EvenOddMask(shape=shape)
+    nets_ = []
+    for bi, spec in enumerate(g["blocks"]):
+        kind, n_steps = str(spec).split(":")
+        P = {'affine': 2, 'shift': 1, 'rqs': 28}[kind]
+        nets = [ConvAct(1, P, 3, conv_dim=len(shape), hidden_sizes=hidden, acts=acts, bias=bias)
+                for _ in range(int(n_steps))]
+        if kind == 'affine':
+            cpl = AffineCoupling_(nets, mask=mask)
+        elif kind == 'shift':
+            cpl = ShiftCoupling_(nets, mask=mask)
+        else:
+            cpl = RQSplineCoupling_(nets, mask=mask, xlim=(-5, 5), ylim=(-5, 5),
+                                    extrap=dict(left='linear', right='linear'))
+        nets_.append(cpl)
+    net_ = ModuleList_(nets_)
+    net_.to(DEV)
+    for bi, cpl in enumerate(net_):
+        for k, net in enumerate(cpl.nets):
+            _load_convact(net, g, f"blk{bi}_step{k}")
+    return net_, shape
+
+
+@pytest.mark.parametrize("name,bias", [("cpl_affine_2d", False), ("cpl_rqs_2d", False), ("cpl_shift_1d", True),
+                                       ("cpl_mixed_3d", False), ("cpl_mixed_4d", True)])
+def test_coupling_stack_golden(name, bias):
+    g = load_golden(name)
+    net_, shape = _build_stack(g, bias)
+    x = cu(g["x"]).requires_grad_(True)
+    stack = net_.hack(x, log0=0)
+    for bi, (yb, lb) in enumerate(stack[1:]):
+        close(yb, g[f"blk{bi}_y"])
+        if torch.is_tensor(lb):
+            close(lb, g[f"blk{bi}_logJ"] + np.zeros(x.shape[0]))
+    y, logJ = stack[-1]
+    if not torch.is_tensor(logJ):
+        logJ = torch.zeros(x.shape[0], device=DEV)
+    prior, action = NormalPrior(shape=shape), ScalarPhi4Action(**ACTION)
+    prior.to(DEV)
+    logr, S = prior.log_prob(x.detach()), action(y)
+    close(S, g["S"])
+    # the reference's log_prob is differentiable in x; ours is a plain kernel: add its gradient by hand
+    loss = (logr - logJ + S).mean()
+    close(loss, g["loss"])
+    grads = torch.autograd.grad(loss, [x] + list(net_.parameters()))
+    gx = grads[0] - x.detach() / x.shape[0]            # d mean(logr) / dx = -x / B
+    close_grad(gx, g["gx"], tol=2e-5)
+    gi = 1
+    for bi, cpl in enumerate(net_):
+        for k, net in enumerate(cpl.nets):
+            for pname, _ in net.named_parameters():
+                close_grad(grads[gi], g[f"blk{bi}_step{k}_grad_{pname}"], tol=3e-5)
+                gi += 1
+    # inverse: back to x with a vanishing residual log-Jacobian
+    with torch.no_grad():
+        xb, lb = net_.backward(y.detach(), log0=logJ.detach())
+    close(xb, g["x"], tol=5e-5)
+    close(lb, np.zeros(x.shape[0]), tol=1e-4)
+
+
+def test_atomic_api_matches_full_field_path():
+    """The reference's split -> atomic_forward -> cat dataflow (generic Coupling_.forward)
+    gives the same result as the fused full-field sweep."""
+    from normflow__b200.nn.scalar.couplings_ import Coupling_
+    g = load_golden("cpl_rqs_2d")
+    net_, shape = _build_stack(g, False)
+    cpl = net_[0]
+    x = cu(g["x"])
+    with torch.no_grad():
+        y_fast, l_fast = cpl(x)
+        y_ref, l_ref = Coupling_.forward(cpl, x)
+        xb, lb = Coupling_.backward(cpl, y_ref, l_ref)
+    close(y_ref, g["blk0_y"])
+    close(l_ref, g["blk0_logJ"])
+    assert torch.allclose(y_fast, y_ref, atol=1e-6) and torch.allclose(l_fast, l_ref, atol=1e-4)
+    close(xb, g["x"], tol=5e-5)
+    # first atomic step against the golden intermediate
+    parts = list(cpl.mask.split(x))
+    fx, _ = cpl.atomic_forward(x_active=parts[0], x_frozen=parts[1], parity=0, net=cpl.nets[0], log0=0)
+    close(fx, g["blk0_step0_fx"])
+
+
+def test_arbitrary_torch_module_as_conditioner():
+    """The conditioner contract is `any torch module (B,1,*L) -> (B,P,*L)` (couplings_.py:124)."""
+    torch.manual_seed(0)
+    shape = (8, 8)
+    mask = EvenOddMask(shape=shape)
+    user_net = torch.nn.Sequential(torch.nn.Conv2d(1, 6, 3, padding='same', padding_mode='circular'),
+                                   torch.nn.SiLU(),
+                                   torch.nn.Conv2d(6, 2, 1)).to(DEV)
+    cpl = AffineCoupling_([user_net, user_net], mask=mask).to(DEV)
+    x = torch.randn(4, *shape, device=DEV, requires_grad=True)
+    y, logJ = cpl(x)
+    # oracle with the conditioner outputs supplied by torch itself
+    mk = mask._mask.cpu().numpy()
+    with torch.no_grad():
+        parts = [x.detach().double().cpu().numpy() * mk, x.detach().double().cpu().numpy() * (1 - mk)]
+        log = np.zeros(4)
+        for k in range(2):
+            p = k % 2
+            out = user_net(torch.as_tensor(parts[1 - p], dtype=torch.float32, device=DEV).unsqueeze(1))
+            parts[p], log = O.affine_atomic(parts[p], out.double().cpu().numpy(), mk, p, log)
+    close(y, parts[0] + parts[1], tol=2e-5)
+    close(logJ, log, tol=2e-5)
+    (y.sum() + logJ.sum()).backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in user_net.parameters())
+    assert torch.isfinite(x.grad).all()
+
+
+# ------------------------------------------------------------------ DistConvertor_ and friends
+def _load_distconv(net_, g, tag):
+    sp = net_.spline_layer_
+    with torch.no_grad():
+        sp.weights_x.copy_(cu(g[f"{tag}_wx"]))
+        sp.weights_y.copy_(cu(g[f"{tag}_wy"]))
+        if sp.weights_d is not None:
+            sp.weights_d.copy_(cu(g[f"{tag}_wd"]))
+
+
+@pytest.mark.parametrize("tag,kw", [("zd_sym", dict(symmetric=True)),
+                                    ("lat_sym_smooth", dict(symmetric=True, smooth=True)),
+                                    ("lat_asym", dict(symmetric=False))])
+def test_distconvertor_golden(tag, kw):
+    g = load_golden("distconv")
+    net_ = DistConvertor_(10, **kw)
+    net_.to(DEV)
+    _load_distconv(net_, g, tag)
+    x = cu(g[f"{tag}_x"]).requires_grad_(True)
+    y, logJ = net_(x)
+    close(y, g[f"{tag}_y"])
+    close(logJ, g[f"{tag}_logJ"])
+    L = (y * cu(g[f"{tag}_r"])).sum() + (logJ * cu(g[f"{tag}_c"])).sum()
+    grads = torch.autograd.grad(L, [x] + list(net_.parameters()))
+    close_grad(grads[0], g[f"{tag}_gx"])
+    for (name, _), gr in zip(net_.named_parameters(), grads[1:]):
+        close_grad(gr, g[f"{tag}_grad_{name}"], tol=3e-5)
+    with torch.no_grad():
+        xb, lb = net_.backward(y.detach(), log0=logJ.detach())
+    close(xb, g[f"{tag}_x"], tol=3e-5)
+    close(lb, np.zeros(x.shape[0]), tol=5e-5)
+
+
+def test_distconvertor_tails_and_unfused_layers():
+    torch.manual_seed(4)
+    net_ = DistConvertor_(10, symmetric=True)
+    net_.to(DEV)
+    with torch.no_grad():
+        for p in net_.parameters():
+            p.normal_(0, 0.5)
+    x = torch.linspace(-15, 15, 601, device=DEV).reshape(1, -1)
+    y, logJ = net_(x)
+    w = [p.detach().double().cpu().numpy() for p in net_.parameters()]
+    yr, lr = O.distconvertor(x.double().cpu().numpy(), 0.0, tuple(w), symmetric=True)
+    close(y, yr, tol=2e-5)
+    close(logJ, lr, tol=2e-5)
+    # the three layers run one by one agree with the fused chain where fp32 has the digits
+    xs = torch.randn(8, 5, device=DEV) * 1.5
+    y1, l1 = net_(xs)
+    y2, l2 = xs, 0
+    for layer in net_:
+        y2, l2 = layer.forward(y2, l2)
+    assert torch.allclose(y1, y2, atol=2e-4) and torch.allclose(l1, l2, atol=1e-3)
+    ye, le = Expit_()(xs)
+    close(ye, 1 / (1 + np.exp(-xs.double().cpu().numpy())))
+    xl, ll = Logit_()(ye, le)
+    close(xl, xs.double().cpu().numpy(), tol=1e-4)
+    close(ll, np.zeros(8), tol=1e-4)
+
+
+def test_rqspline_class_shared_knots():
+    g = load_golden("spline")
+    sp = RQSpline(knots_x=cu(g["s1_kx"]), knots_y=cu(g["s1_ky"]), knots_d=None, extrap=dict(left='anti'))
+    y, gr = sp(cu(g["s1_x"]), grad=True)
+    close(y, g["s1_y"], tol=2e-5)
+    close(gr, g["s1_g"], tol=3e-5)
+    inside = g["s1_x"] > 2 * g["s1_kx"][0] - g["s1_kx"][-1]
+    xi = sp.backward(cu(g["s1_y"]))
+    close(xi[torch.as_tensor(inside)], g["s1_x"][inside], tol=5e-5)
+
+
+def test_model_zero_dim_golden_and_logz():
+    g = load_golden("model_zero_dim")
+    net_ = DistConvertor_(10, symmetric=True)
+    net_.to(DEV)
+    with torch.no_grad():
+        for name, p in net_.named_parameters():
+            p.copy_(cu(g[f"w_{name}"]))
+    prior, action = NormalPrior(shape=1), ScalarPhi4Action(kappa=0, m_sq=-1.2, lambd=0.5)
+    prior.to(DEV)
+    x = cu(g["x"])
+    y, logJ = net_(x)
+    logq, logp = prior.log_prob(x) - logJ, -action(y)
+    close(y, g["y"])
+    close(logq, g["logq"])
+    close(logp, g["logp"])
+    loss = (logq - logp).mean()
+    close(loss, g["loss"])
+    grads = torch.autograd.grad(loss, list(net_.parameters()))
+    for (name, _), gr in zip(net_.named_parameters(), grads):
+        close_grad(gr, g[f"g_{name}"], tol=2e-5)
+
+
+def test_zero_dim_training_reaches_known_logz():
+    """Config 1 (examples/scalar_zerodim.py): analytic log Z = 1.112773; the reference's
+    published run reaches loss -1.1122, accept_rate 0.988 after 1000 epochs of 1024."""
+    torch.manual_seed(11)
+    np.random.seed(11)
+    model = Model(net_=DistConvertor_(10, symmetric=True), prior=NormalPrior(shape=1),
+                  action=ScalarPhi4Action(kappa=0, m_sq=-1.2, lambd=0.5))
+    model.device_handler.to(DEV)
+    model.fit(n_epochs=600, batch_size=1024, hyperparam=dict(lr=0.01, weight_decay=0.),
+              checkpoint_dict=dict(print_stride=300))
+    hist = model.fit.train_history
+    assert len(hist['loss']) == 600 and np.mean(hist['loss'][-50:]) < -1.10
+    logz_mean, logz_std = hist['logz'][-1]
+    assert abs(logz_mean - 1.112773) < 0.01
+    assert hist['accept_rate'][-1][0] > 0.9 and float(hist['ess'][-1]) > 0.97
+    (x, y, x_hat), (logJ, log0_hat) = backward_sanitychecker(model, return_details=True)
+    assert torch.allclose(x, x_hat, atol=1e-4) and log0_hat.abs().max() < 1e-3
+
+
+# ------------------------------------------------------------------ Metropolis
+def test_metropolis_kernel_golden_decisions():
+    g = load_golden("mcmc")
+    logq = cu(g["logqp"])
+    logp = torch.zeros_like(logq)
+    state = torch.zeros(2, dtype=torch.float64, device=DEV)
+    acc, idx, n = _ops.metropolis_scan(logq, logp, cu(np.log(g["u_first"]), torch.float64), state)
+    assert np.array_equal(acc.cpu().numpy().astype(bool), g["status_noref"])
+    assert np.array_equal(idx.cpu().numpy(), g["ind_noref"])
+    assert n.item() == g["status_noref"].sum() and state[1].item() == 1.0
+    state = torch.tensor([float(g["ref"]), 1.0], dtype=torch.float64, device=DEV)
+    acc, idx, n = _ops.metropolis_scan(logq, logp, cu(np.log(g["u_second"]), torch.float64), state)
+    assert np.array_equal(acc.cpu().numpy().astype(bool), g["status_ref"])
+    expect = g["ind_ref"].copy()
+    expect[:np.argmax(g["status_ref"])] = -1 if not g["status_ref"][0] else expect[0]
+    assert np.array_equal(idx.cpu().numpy(), expect)
+
+
+def test_mcmc_chain_state_across_calls_golden():
+    g = load_golden("mcmc")
+
+    class _M:
+        pass
+    sampler = nf.mcmc.MCMCSampler(_M())
+    for call in range(2):
+        np.random.seed(100 + call)
+        yo, lqo, lpo = sampler._accept_reject_step(cu(g[f"c{call}_y"]), cu(g[f"c{call}_logq"]),
+                                                   cu(g[f"c{call}_logp"]), bookkeeping=True)
+        assert np.array_equal(yo.cpu().numpy(), g[f"c{call}_yo"].astype(np.float32))
+        assert np.array_equal(lqo.cpu().numpy(), g[f"c{call}_logqo"].astype(np.float32))
+        assert np.array_equal(lpo.cpu().numpy(), g[f"c{call}_logpo"].astype(np.float32))
+        assert np.isclose(sampler.history.accept_rate[-1], float(g[f"c{call}_accept_rate"]))
+
+
+def test_metropolis_long_chain_vs_oracle():
+    rs = np.random.RandomState(9)
+    B = 16384
+    logq = rs.randn(B).astype(np.float32)
+    logp = (logq + rs.randn(B) * 0.5).astype(np.float32)
+    u = rs.rand(B)
+    state = torch.zeros(2, dtype=torch.float64, device=DEV)
+    acc, idx, n = _ops.metropolis_scan(cu(logq), cu(logp), cu(np.log(u), torch.float64), state)
+    ref = O.metropolis_accept_status(logq.astype(np.float64) - logp.astype(np.float64), u)
+    assert np.array_equal(acc.cpu().numpy().astype(bool), ref)
+    assert np.array_equal(idx.cpu().numpy(), O.metropolis_accept_indices(ref))
+    rows = torch.arange(B, device=DEV, dtype=torch.float32).reshape(B, 1).repeat(1, 4096)
+    out = _ops.gather_rows(rows, idx)
+    assert torch.equal(out[:, 0].long(), idx) and torch.equal(out[:, -1].long(), idx)
+
+
+# ------------------------------------------------------------------ BASELINE configs: oracle + full-size properties
+def _config_model(shape, blocks, hidden=(8, 8), seed=0):
+    torch.manual_seed(seed)
+    mask = EvenOddMask(shape=shape)
+    conv = dict(in_channels=1, hidden_sizes=list(hidden), kernel_size=3, conv_dim=len(shape),
+                acts=(*['tanh'] * len(hidden), None), bias=False)
+    nets_ = []
+    for kind, n in blocks:
+        if kind == 'affine':
+            nets_.append(AffineCoupling_([ConvAct(out_channels=2, **conv) for _ in range(n)], mask=mask))
+        else:
+            nets_.append(RQSplineCoupling_([ConvAct(out_channels=28, **conv) for _ in range(n)], mask=mask,
+                                           xlim=(-5, 5), ylim=(-5, 5), extrap=dict(left='linear', right='linear')))
+    model = Model(net_=ModuleList_(nets_), prior=NormalPrior(shape=shape), action=ScalarPhi4Action(**ACTION))
+    model.device_handler.to(DEV)
+    return model
+
+
+def _oracle_flow(model, x):
+    """Run the numpy oracle with the model's own weights."""
+    y, log = x.astype(np.float64), np.zeros(x.shape[0])
+    for cpl in model.net_:
+        mask = cpl.mask._mask.cpu().numpy()
+        kind = 'affine' if isinstance(cpl, AffineCoupling_) else 'rqs'
+        steps = []
+        for net in cpl.nets:
+            layers = [(c.standard_weight().detach().double().cpu().numpy(),
+                       None if c.bias is None else c.bias.detach().double().cpu().numpy()) for c in net._convs()]
+            kw = dict(xlim=(-5, 5), ylim=(-5, 5), extrap=dict(left='linear', right='linear')) if kind == 'rqs' else {}
+            steps.append(O.make_convact_step(kind, layers, list(net._acts), mask, **kw))
+        y, log = O.coupling_forward(y, log, mask, steps)
+    return y, log
+
+
+@pytest.mark.parametrize("shape,blocks,B", [((16, 16), [('affine', 4)], 64),            # config 2
+                                            ((64, 64), [('rqs', 4)], 6),                # config 3
+                                            ((32, 32, 32), [('affine', 1), ('rqs', 1)], 1),   # config 4 style
+                                            ((16, 16, 16, 16), [('affine', 1)], 1)])    # config 5 style (Conv4d)
+def test_baseline_configs_vs_oracle(shape, blocks, B):
+    model = _config_model(shape, blocks)
+    x = torch.randn(B, *shape, generator=torch.Generator('cpu').manual_seed(1234), dtype=torch.float32, device='cpu')
+    with torch.no_grad():
+        y, logJ = model.net_(x.to(DEV))
+        S = model.action(y)
+    yr, lr = _oracle_flow(model, x.numpy())
+    close(y, yr)
+    close(logJ, lr)
+    close(S, O.phi4_action(yr, **ACTION))
+
+
+@pytest.mark.parametrize("shape,blocks,B", [((64, 64), [('rqs', 4)], 2048), ((32, 32, 32), [('affine', 2), ('rqs', 2)], 64),
+                                            ((16, 16, 16, 16), [('affine', 2), ('rqs', 2)], 16)])
+def test_full_size_round_trip_and_logprob(shape, blocks, B):
+    """encode -> decode at BASELINE lattice sizes: net_.backward(net_(x)) == x, the two
+    log-Jacobians cancel, and posterior.log_prob(y) reproduces the sampler's log q."""
+    model = _config_model(shape, blocks, seed=1)
+    with torch.no_grad():
+        for p in model.net_.parameters():      # make the flow far from the identity
+            p.mul_(3.0)
+        y, logq, logp = model.posterior.sample__(B)
+        assert y.shape == (B,) + shape and torch.isfinite(y).all() and torch.isfinite(logq).all()
+        lq2 = model.posterior.log_prob(y)
+        scale = max(1.0, logq.abs().max().item())
+        assert (lq2 - logq).abs().max().item() < 3e-5 * scale
+        x = model.prior.sample(B)
+        yy, lj = model.net_(x)
+        xb, lb = model.net_.backward(yy, log0=lj)
+        assert (xb - x).abs().max().item() < 1e-4
+        assert lb.abs().max().item() < 3e-5 * max(1.0, lj.abs().max().item())
+        close(logp, -O.phi4_action(y[:4].double().cpu().numpy(), **ACTION), tol=1e-5) if B <= 64 else None
+
+
+def test_training_step_reduces_loss_config2():
+    model = _config_model((16, 16), [('affine', 4)], seed=2)
+    np.random.seed(0)
+    model.fit(n_epochs=60, batch_size=1024, hyperparam=dict(lr=2e-3, weight_decay=0.),
+              checkpoint_dict=dict(print_stride=30, print_batch_size=256))
+    loss = model.fit.train_history['loss']
+    assert np.isfinite(loss).all() and np.mean(loss[-10:]) < np.mean(loss[:10]) - 1.0
+    y = model.mcmc.sample(512)
+    assert y.shape == (512, 16, 16) and 0 < model.mcmc.history.accept_rate[-1] <= 1
