@@ -131,7 +131,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.sm, self.reasons, self.sm_max = [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self.ok = False
         try:
             import pynvml
@@ -153,7 +153,7 @@ class ClockSampler(threading.Thread):
             getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
             getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
         }
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 try:
@@ -165,10 +165,10 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(self.period)
+            self._halt.wait(self.period)
 
     def finish(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
         if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unavailable"]}

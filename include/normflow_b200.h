@@ -145,21 +145,22 @@ int nfk_rqs_bwd(const float* x, const float* out, const uint8_t* mask, int parit
 
 /* ------------------------------------------------- pointwise spline chain --
  * SplineNet_ / DistConvertor_ (nn/scalar/modules_.py:93-114, 277-302, 333-383):
- * one shared 1-D spline with explicit knots kx, ky, kd (float[K], device) applied
- * to every element; logistic != 0 wraps it as Expit_ -> spline -> Logit_ (the
- * DistConvertor_ chain) evaluated in complement form so the tails keep fp32
- * relative accuracy.  inverse != 0 evaluates ModuleList_.backward of the chain.
- * _bwd: VJP of the forward direction: gx[B][V] and gkx, gky, gkd (float[K],
- * ACCUMULATED with atomics: zero them first).                                   */
-int nfk_spline1d_fwd(const float* x, const float* kx, const float* ky, const float* kd,
-                     int K, int extrap_left, int extrap_right, int logistic, int inverse,
-                     const float* log_in, float* y, float* log_out,
+ * one shared 1-D spline with explicit knots applied to every element.
+ *   knots: float[5][K] (device) = kx | ky | kd | cx | cy, where cx = x_hi - kx and
+ *          cy = y_hi - ky are the same knots measured from the upper end (read only
+ *          when logistic != 0; the first 3K floats suffice otherwise).
+ * logistic != 0 wraps the spline as Expit_ -> spline -> Logit_ (the DistConvertor_
+ * chain, x_hi = y_hi = 1) evaluated in complement form -- every point of (0,1) is
+ * carried as (s, 1-s) and every knot as (k, 1-k) -- so the tails keep fp32 relative
+ * accuracy.  inverse != 0 evaluates ModuleList_.backward of the chain.
+ * _bwd: VJP of the forward direction: gx[B][V] and gknots float[5][K] (same layout;
+ * ACCUMULATED with atomics: zero it first).                                     */
+int nfk_spline1d_fwd(const float* x, const float* knots, int K, int extrap_left, int extrap_right,
+                     int logistic, int inverse, const float* log_in, float* y, float* log_out,
                      int64_t B, int64_t V, void* stream);
-int nfk_spline1d_bwd(const float* x, const float* kx, const float* ky, const float* kd,
-                     int K, int extrap_left, int extrap_right, int logistic,
-                     const float* gy, const float* glog,
-                     float* gx, float* gkx, float* gky, float* gkd,
-                     int64_t B, int64_t V, void* stream);
+int nfk_spline1d_bwd(const float* x, const float* knots, int K, int extrap_left, int extrap_right,
+                     int logistic, const float* gy, const float* glog,
+                     float* gx, float* gknots, int64_t B, int64_t V, void* stream);
 /* Expit_ / Logit_ alone (modules_.py:93-114); which = 0 expit, 1 logit.         */
 int nfk_logistic_fwd(const float* x, int which, const float* log_in, float* y, float* log_out,
                      int64_t B, int64_t V, void* stream);

@@ -49,8 +49,8 @@ _SIGNATURES = {
     "nfk_rqs_fwd": [c_f, c_f, c_f, c_i, c_i, RqsParams, c_f, c_f, c_f, c_l, c_l, c_f],
     "nfk_rqs_inv": [c_f, c_f, c_f, c_i, c_i, RqsParams, c_f, c_f, c_f, c_l, c_l, c_f],
     "nfk_rqs_bwd": [c_f, c_f, c_f, c_i, c_i, RqsParams, c_f, c_f, c_f, c_f, c_l, c_l, c_f],
-    "nfk_spline1d_fwd": [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_l, c_l, c_f],
-    "nfk_spline1d_bwd": [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f, c_f, c_l, c_l, c_f],
+    "nfk_spline1d_fwd": [c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_l, c_l, c_f],
+    "nfk_spline1d_bwd": [c_f, c_f, c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_l, c_l, c_f],
     "nfk_logistic_fwd": [c_f, c_i, c_f, c_f, c_f, c_l, c_l, c_f],
     "nfk_logistic_bwd": [c_f, c_i, c_f, c_f, c_f, c_l, c_l, c_f],
     "nfk_phi4_action_fwd": [c_f, Lattice, c_fl, c_fl, c_fl, c_f, c_l, c_f],

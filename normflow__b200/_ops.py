@@ -276,16 +276,17 @@ def logistic(x, which, log0=0):
 
 
 class _Spline1d(torch.autograd.Function):
+    """knots: float32 [3, K] (kx | ky | kd) or, for the logistic chain, [5, K] with the
+    complements cx = x_hi - kx and cy = y_hi - ky appended."""
+
     @staticmethod
-    def forward(ctx, x, kx, ky, kd, log_in, left, right, logistic_wrap):
-        x = _f32c(x, "x")
-        knots = torch.stack([_f32c(kx, "knots_x"), _f32c(ky, "knots_y"), _f32c(kd, "knots_d")]).contiguous()
+    def forward(ctx, x, knots, log_in, left, right, logistic_wrap):
+        x, knots = _f32c(x, "x"), _f32c(knots, "knots")
         K = knots.shape[1]
         B, V = _bv(x)
         y = torch.empty_like(x)
         log_out = torch.empty((B,), dtype=torch.float32, device=x.device)
-        p = knots.data_ptr()
-        check(lib().nfk_spline1d_fwd(dev(x), p, p + 4 * K, p + 8 * K, K, left, right, logistic_wrap, 0,
+        check(lib().nfk_spline1d_fwd(dev(x), dev(knots), K, left, right, logistic_wrap, 0,
                                      dev(log_in), dev(y), dev(log_out), B, V, stream()), "spline1d_fwd")
         ctx.save_for_backward(x, knots)
         ctx.cfg = (left, right, logistic_wrap, log_in is not None)
@@ -299,31 +300,36 @@ class _Spline1d(torch.autograd.Function):
         B, V = _bv(x)
         gy, glog = _f32c(gy, "gy"), _f32c(glog, "glog")
         gx = torch.empty_like(x)
-        gk = torch.zeros_like(knots)
-        p, q = knots.data_ptr(), gk.data_ptr()
-        check(lib().nfk_spline1d_bwd(dev(x), p, p + 4 * K, p + 8 * K, K, left, right, logistic_wrap,
-                                     dev(gy), dev(glog), dev(gx), q, q + 4 * K, q + 8 * K, B, V, stream()),
-              "spline1d_bwd")
-        return gx, gk[0], gk[1], gk[2], (glog if has_log else None), None, None, None
+        gk = torch.zeros((5, K), dtype=torch.float32, device=x.device)
+        check(lib().nfk_spline1d_bwd(dev(x), dev(knots), K, left, right, logistic_wrap,
+                                     dev(gy), dev(glog), dev(gx), dev(gk), B, V, stream()), "spline1d_bwd")
+        return gx, gk[:knots.shape[0]], (glog if has_log else None), None, None, None
 
 
-def spline1d(x, kx, ky, kd, log0=0, extrap=None, logistic_wrap=False, inverse=False):
+def _check_knots(knots, logistic_wrap):
+    rows = 5 if logistic_wrap else 3
+    if knots.dim() != 2 or knots.shape[0] != rows:
+        raise ValueError(f"spline1d expects knots of shape [{rows}, K], got {tuple(knots.shape)}")
+    if not 2 <= knots.shape[1] <= 64:
+        raise ValueError("spline1d supports 2..64 knots")
+
+
+def spline1d(x, knots, log0=0, extrap=None, logistic_wrap=False, inverse=False):
     """One shared 1-D RQ spline over every element (SplineNet_), optionally wrapped as
-    Expit_ -> spline -> Logit_ (DistConvertor_) in a single kernel."""
+    Expit_ -> spline -> Logit_ (DistConvertor_) in a single kernel.  `knots` is the
+    stacked [3, K] (or [5, K] for the chain) tensor described in _Spline1d."""
     extrap = extrap or {}
     left, right = _C.EXTRAP[extrap.get('left')], _C.EXTRAP[extrap.get('right')]
     log_in = as_log(log0, x)
+    _check_knots(knots, logistic_wrap)
     if not inverse:
-        return _Spline1d.apply(x, kx, ky, kd, log_in, left, right, int(bool(logistic_wrap)))
-    _no_grad_needed(x, kx, ky, kd, log_in)
-    x = _f32c(x, "x")
-    knots = torch.stack([_f32c(kx, "knots_x"), _f32c(ky, "knots_y"), _f32c(kd, "knots_d")]).contiguous()
-    K = knots.shape[1]
+        return _Spline1d.apply(x, knots, log_in, left, right, int(bool(logistic_wrap)))
+    _no_grad_needed(x, knots, log_in)
+    x, knots = _f32c(x, "x"), _f32c(knots, "knots")
     B, V = _bv(x)
     y = torch.empty_like(x)
     log_out = torch.empty((B,), dtype=torch.float32, device=x.device)
-    p = knots.data_ptr()
-    check(lib().nfk_spline1d_fwd(dev(x), p, p + 4 * K, p + 8 * K, K, left, right, int(bool(logistic_wrap)), 1,
+    check(lib().nfk_spline1d_fwd(dev(x), dev(knots), knots.shape[1], left, right, int(bool(logistic_wrap)), 1,
                                  dev(log_in), dev(y), dev(log_out), B, V, stream()), "spline1d_fwd(inverse)")
     return y, log_out
 

@@ -164,11 +164,11 @@ extern "C" int nfk_logistic_bwd(const float* x, int which, const float* gy, cons
 // walked grid-stride over the flattened [B*V] array when V is tiny, else with the
 // per-sample plan so the log-Jacobian reduces without atomics.
 struct SplineArgs {
-    const float *x, *kx, *ky, *kd;
+    const float *x, *knots;      // knots: [5][K] = kx | ky | kd | cx | cy
     Spline1dCfg cfg;
     int inverse;
     const float *gy, *glog;
-    float *y, *gx, *gk;     // gk: global [3K] accumulation (backward)
+    float *y, *gx, *gk;     // gk: global [5K] accumulation (backward)
     const float* log_in;
     float* log_out;
     int64_t B, V;
@@ -178,26 +178,22 @@ struct SplineArgs {
 
 template <bool BWD, bool SMALL>
 __global__ void __launch_bounds__(256) spline1d_kernel(SplineArgs a) {
-    __shared__ float knots[3 * NFK_MAX_KNOTS];
-    __shared__ float gacc[3 * NFK_MAX_KNOTS];
+    __shared__ float knots[5 * NFK_MAX_KNOTS];
+    __shared__ float gacc[5 * NFK_MAX_KNOTS];
     const int K = a.cfg.K;
-    for (int i = threadIdx.x; i < K; i += blockDim.x) {
-        knots[i] = a.kx[i];
-        knots[K + i] = a.ky[i];
-        knots[2 * K + i] = a.kd[i];
-    }
+    const int nk = a.cfg.logistic ? 5 * K : 3 * K;
+    for (int i = threadIdx.x; i < 5 * K; i += blockDim.x) knots[i] = i < nk ? a.knots[i] : 0.f;
     if (BWD)
-        for (int i = threadIdx.x; i < 3 * K; i += blockDim.x) gacc[i] = 0.f;
+        for (int i = threadIdx.x; i < 5 * K; i += blockDim.x) gacc[i] = 0.f;
     __syncthreads();
-    const float *kx = knots, *ky = knots + K, *kd = knots + 2 * K;
 
     if (SMALL) {            // one thread per sample
         const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
         if (b < a.B) {
             float acc = 0.f;
             for (int64_t s = 0; s < a.V; ++s) {
-                if (BWD) Spline1dBwdOp{a.x, kx, ky, kd, a.cfg, a.gy, a.glog, a.gx, gacc, a.V}(b, s);
-                else acc += Spline1dOp{a.x, kx, ky, kd, a.cfg, a.inverse, a.y, a.V}(b, s);
+                if (BWD) Spline1dBwdOp{a.x, knots, a.cfg, a.gy, a.glog, a.gx, gacc, a.V}(b, s);
+                else acc += Spline1dOp{a.x, knots, a.cfg, a.inverse, a.y, a.V}(b, s);
             }
             if (!BWD && a.log_out) a.log_out[b] = (a.log_in ? a.log_in[b] : 0.f) + acc;
         }
@@ -208,8 +204,8 @@ __global__ void __launch_bounds__(256) spline1d_kernel(SplineArgs a) {
         const int64_t s1 = s0 + a.chunk_len < a.V ? s0 + a.chunk_len : a.V;
         float acc = 0.f;
         for (int64_t s = s0 + threadIdx.x; s < s1; s += blockDim.x) {
-            if (BWD) Spline1dBwdOp{a.x, kx, ky, kd, a.cfg, a.gy, a.glog, a.gx, gacc, a.V}(b, s);
-            else acc += Spline1dOp{a.x, kx, ky, kd, a.cfg, a.inverse, a.y, a.V}(b, s);
+            if (BWD) Spline1dBwdOp{a.x, knots, a.cfg, a.gy, a.glog, a.gx, gacc, a.V}(b, s);
+            else acc += Spline1dOp{a.x, knots, a.cfg, a.inverse, a.y, a.V}(b, s);
         }
         if (!BWD && a.log_out) {
             acc = block_sum(acc);
@@ -221,7 +217,7 @@ __global__ void __launch_bounds__(256) spline1d_kernel(SplineArgs a) {
     }
     if (BWD) {
         __syncthreads();
-        for (int i = threadIdx.x; i < 3 * K; i += blockDim.x)
+        for (int i = threadIdx.x; i < 5 * K; i += blockDim.x)
             if (gacc[i] != 0.f) atomicAdd(a.gk + i, gacc[i]);
     }
 }
@@ -252,29 +248,24 @@ static int spline1d_launch(SplineArgs a, cudaStream_t st) {
     return check_launch();
 }
 
-extern "C" int nfk_spline1d_fwd(const float* x, const float* kx, const float* ky, const float* kd,
-                                int K, int extrap_left, int extrap_right, int logistic, int inverse,
-                                const float* log_in, float* y, float* log_out,
+extern "C" int nfk_spline1d_fwd(const float* x, const float* knots, int K, int extrap_left, int extrap_right,
+                                int logistic, int inverse, const float* log_in, float* y, float* log_out,
                                 int64_t B, int64_t V, void* stream) {
     SplineArgs a{};
-    if (!x || !kx || !ky || !kd || !y) return NFK_EINVAL;
+    if (!x || !knots || !y) return NFK_EINVAL;
     if (!spline_cfg(K, extrap_left, extrap_right, logistic, a.cfg)) return NFK_EINVAL;
-    a.x = x; a.kx = kx; a.ky = ky; a.kd = kd; a.inverse = inverse;
+    a.x = x; a.knots = knots; a.inverse = inverse;
     a.y = y; a.log_in = log_in; a.log_out = log_out; a.B = B; a.V = V;
     return spline1d_launch<false>(a, NFK_STREAM(stream));
 }
-extern "C" int nfk_spline1d_bwd(const float* x, const float* kx, const float* ky, const float* kd,
-                                int K, int extrap_left, int extrap_right, int logistic,
-                                const float* gy, const float* glog,
-                                float* gx, float* gkx, float* gky, float* gkd,
-                                int64_t B, int64_t V, void* stream) {
+extern "C" int nfk_spline1d_bwd(const float* x, const float* knots, int K, int extrap_left, int extrap_right,
+                                int logistic, const float* gy, const float* glog,
+                                float* gx, float* gknots, int64_t B, int64_t V, void* stream) {
     SplineArgs a{};
-    if (!x || !kx || !ky || !kd || !gy || !gx || !gkx) return NFK_EINVAL;
-    // the three knot gradients must be one contiguous [3K] buffer: gkx | gky | gkd
-    if (gky != gkx + K || gkd != gkx + 2 * K) return NFK_EINVAL;
+    if (!x || !knots || !gy || !gx || !gknots) return NFK_EINVAL;
     if (!spline_cfg(K, extrap_left, extrap_right, logistic, a.cfg)) return NFK_EINVAL;
-    a.x = x; a.kx = kx; a.ky = ky; a.kd = kd; a.gy = gy; a.glog = glog;
-    a.gx = gx; a.gk = gkx; a.B = B; a.V = V;
+    a.x = x; a.knots = knots; a.gy = gy; a.glog = glog;
+    a.gx = gx; a.gk = gknots; a.B = B; a.V = V;
     return spline1d_launch<true>(a, NFK_STREAM(stream));
 }
 

@@ -110,12 +110,12 @@ NFK_HD void rq_inverse(const RqSeg& s, float y, float& x, float& loginv) {
 //   a = th^2, b = th - a, c = 1 - 2 th + a
 //   N = m a + D0 b ; den = m + sig b ; y = Y0 + h N / den
 //   Q = D1 a + 2 m b + D0 c ; logg = 2 log m + log Q - 2 log den
-NFK_HD RqSegGrad rq_forward_vjp(const RqSeg& s, float x, float gy, float gl) {
+// `th`, `om` = theta and 1 - theta, handed in so callers can form them without cancellation.
+NFK_HD RqSegGrad rq_vjp_theta(const RqSeg& s, float th, float om, float gy, float gl) {
     const float m = s.h / s.w;
-    const float th = (x - s.X0) / s.w;
     const float a = th * th;
-    const float b = th - a;
-    const float c = 1.f - 2.f * th + a;
+    const float b = th * om;
+    const float c = om * om;
     const float sig = s.D0 + s.D1 - 2.f * m;
     const float den = m + sig * b;
     const float N = m * a + s.D0 * b;
@@ -145,6 +145,10 @@ NFK_HD RqSegGrad rq_forward_vjp(const RqSeg& s, float x, float gy, float gl) {
     r.gY0 = gy;
     r.gh = gh;
     return r;
+}
+NFK_HD RqSegGrad rq_forward_vjp(const RqSeg& s, float x, float gy, float gl) {
+    const float th = (x - s.X0) / s.w;
+    return rq_vjp_theta(s, th, 1.f - th, gy, gl);
 }
 
 // ---------------------------------------------------------------------------
@@ -457,31 +461,80 @@ NFK_HD float log_sc_from_x(float x) {
     return -a - 2.f * log1pf(expf(-a));
 }
 
-// f on (s, c): returns (s', c') and log f'(s).  Knots span [kx0, 1] -> [ky0, 1]
-// with kx[K-1] == ky[K-1] == 1 (DistConvertor_: xlim = ylim = (0,1) or (0.5,1)).
-NFK_HD void spline_unit_forward(const float* kx, const float* ky, const float* kd, int K,
-                                Unit u, Unit& v, float& logg) {
-    const int j = knots_segment(kx, K, u.s);
-    const RqSeg g = knots_seg(kx, ky, kd, j);
-    const float th = (u.s - g.X0) / g.w;
-    const float om = ((kx[j + 1] - 1.f) + u.c) / g.w;        // (X1 - s)/w without cancellation
+// Knots of the chain are handed over twice: kx, ky measured from the lower end and
+// cx = x_hi - kx, cy = y_hi - ky measured from the upper end (x_hi = y_hi = 1), both
+// built from cumulative softmax sums on their own side, so differences such as
+// (X1 - s) for s -> 1 carry no cancellation.  Without this a 1-ulp error of a knot near
+// 1 is amplified by 1/(bin width) and by 1/(1 - s').
+struct UnitKnots {
+    const float *kx, *ky, *kd, *cx, *cy;
+    int K;
+};
+
+// one located segment, offsets formed on the accurate side
+struct UnitSeg {
+    RqSeg g;         // X0, Y0 from the lower end; w, h from the accurate side
+    float cY1;       // y_hi - Y1
+    float cX1;       // x_hi - X1
+    float th, om;    // theta, 1 - theta  (by x for the forward map)
+    int j;
+    bool upx, upy;   // which representation was used (for the adjoints)
+};
+
+// number of interior knots strictly below the point (s, c = 1 - s)
+NFK_HD int unit_segment(const float* k, const float* ck, int K, Unit u) {
+    int lo = 1, hi = K - 1;
+    const bool up = u.s > 0.5f;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const bool below = up ? (ck[mid] > u.c) : (k[mid] < u.s);
+        if (below) lo = mid + 1; else hi = mid;
+    }
+    return lo - 1;
+}
+
+NFK_HD void unit_widths(const UnitKnots& k, int j, UnitSeg& sg) {
+    sg.j = j;
+    sg.upx = k.kx[j] >= 0.5f;
+    sg.upy = k.ky[j] >= 0.5f;
+    sg.g.X0 = k.kx[j];
+    sg.g.Y0 = k.ky[j];
+    sg.g.w = sg.upx ? k.cx[j] - k.cx[j + 1] : k.kx[j + 1] - k.kx[j];
+    sg.g.h = sg.upy ? k.cy[j] - k.cy[j + 1] : k.ky[j + 1] - k.ky[j];
+    sg.g.D0 = k.kd[j];
+    sg.g.D1 = k.kd[j + 1];
+    sg.cX1 = k.cx[j + 1];
+    sg.cY1 = k.cy[j + 1];
+}
+
+// f on (s, c): returns (s', c') and log f'(s).
+NFK_HD UnitSeg spline_unit_forward(const UnitKnots& k, Unit u, Unit& v, float& logg) {
+    UnitSeg sg;
+    unit_widths(k, unit_segment(k.kx, k.cx, k.K, u), sg);
+    const RqSeg& g = sg.g;
+    const bool up = u.s > 0.5f;
+    sg.th = (up ? k.cx[sg.j] - u.c : u.s - g.X0) / g.w;        // (s - X0)/w
+    sg.om = (up ? u.c - sg.cX1 : k.kx[sg.j + 1] - u.s) / g.w;   // (X1 - s)/w
+    const float th = sg.th, om = sg.om;
     const float m = g.h / g.w;
     const float sig = g.D0 + g.D1 - 2.f * m;
     const float den = m + sig * th * om;
     v.s = g.Y0 + g.h * th * (m * th + g.D0 * om) / den;
-    v.c = (1.f - ky[j + 1]) + g.h * om * (m * om + g.D1 * th) / den;   // Y1 - g0, exact identity
+    v.c = sg.cY1 + g.h * om * (m * om + g.D1 * th) / den;       // Y1 - g0: an exact identity
     const float Q = g.D1 * th * th + 2.f * m * th * om + g.D0 * om * om;
     logg = logf(m * m * Q / (den * den));
+    return sg;
 }
 
 // inverse of the above on (s', c').
-NFK_HD void spline_unit_inverse(const float* kx, const float* ky, const float* kd, int K,
-                                Unit v, Unit& u, float& loginv) {
-    const int j = knots_segment(ky, K, v.s);
-    const RqSeg g = knots_seg(kx, ky, kd, j);
+NFK_HD void spline_unit_inverse(const UnitKnots& k, Unit v, Unit& u, float& loginv) {
+    UnitSeg sg;
+    unit_widths(k, unit_segment(k.ky, k.cy, k.K, v), sg);
+    const RqSeg& g = sg.g;
+    const bool up = v.s > 0.5f;
     const float m = g.h / g.w;
-    const float eta = (v.s - g.Y0) / g.h;
-    const float ome = ((ky[j + 1] - 1.f) + v.c) / g.h;       // 1 - eta
+    const float eta = (up ? k.cy[sg.j] - v.c : v.s - g.Y0) / g.h;
+    const float ome = (up ? v.c - sg.cY1 : k.ky[sg.j + 1] - v.s) / g.h;      // 1 - eta
     float th, om;
     if (eta <= 0.5f) {
         th = rq_theta_from_eta(m, g.D0, g.D1, eta);
@@ -494,45 +547,56 @@ NFK_HD void spline_unit_inverse(const float* kx, const float* ky, const float* k
     const float den = m + sig * th * om;
     const float Q = g.D1 * th * th + 2.f * m * th * om + g.D0 * om * om;
     u.s = g.X0 + g.w * th;
-    u.c = (1.f - kx[j + 1]) + g.w * om;
+    u.c = sg.cX1 + g.w * om;
     loginv = -logf(m * m * Q / (den * den));
 }
 
 // DistConvertor_ forward (inverse = false) or ModuleList_.backward (inverse = true):
 //   y = logit(F(expit(x))),  logj = log(s c) + log F'(s) - log(s' c')
 // anti != 0: odd extension about 0 (xlim0 = ylim0 = 0.5, extrap left 'anti').
-NFK_HD void distconv_eval(const float* kx, const float* ky, const float* kd, int K, bool anti,
-                          bool inverse, float x, float& y, float& logj) {
+NFK_HD void distconv_eval(const UnitKnots& k, bool anti, bool inverse, float x, float& y, float& logj) {
     const float xa = anti ? fabsf(x) : x;
     const Unit u = expit_pair(xa);
     Unit v;
     float lg;
-    if (!inverse) spline_unit_forward(kx, ky, kd, K, u, v, lg);
-    else spline_unit_inverse(kx, ky, kd, K, u, v, lg);
-    const float ya = logf(v.s) - logf(v.c);
-    y = anti ? copysignf(ya, x) : ya;
-    logj = log_sc_from_x(xa) + lg - (logf(v.s) + logf(v.c));
+    if (!inverse) spline_unit_forward(k, u, v, lg);
+    else spline_unit_inverse(k, u, v, lg);
+    const float ls = logf(v.s), lc = logf(v.c);
+    y = anti ? copysignf(ls - lc, x) : ls - lc;
+    logj = log_sc_from_x(xa) + lg - (ls + lc);
 }
 
-// VJP of distconv_eval (forward direction).  Acc as in spline1d_backward.
+// VJP of distconv_eval (forward direction).  `acc(i, v)` accumulates into a [5K]
+// buffer laid out gkx | gky | gkd | gcx | gcy; the knot arrays of the two ends are
+// independent inputs here (the host chains both back to the weights).
 template <class Acc>
-NFK_HD float distconv_backward(const float* kx, const float* ky, const float* kd, int K, bool anti,
-                               float x, float gy, float gl, const Acc& acc) {
+NFK_HD float distconv_backward(const UnitKnots& k, bool anti, float x, float gy, float gl, const Acc& acc) {
+    const int K = k.K;
     const float xa = anti ? fabsf(x) : x;
     const float sgn = (anti && x < 0.f) ? -1.f : 1.f;
     const Unit u = expit_pair(xa);
     Unit v;
     float lg;
-    spline_unit_forward(kx, ky, kd, K, u, v, lg);
-    // y = sgn (log s' - log c'),  logj = log(s c) + lg - log s' - log c'
+    const UnitSeg sg = spline_unit_forward(k, u, v, lg);
+    // y = sgn (log s' - log c'),  logj = log(s c) + lg - log s' - log c',  c' = 1 - s'
     const float gya = sgn * gy;
     const float gsp = gya * (1.f / v.s + 1.f / v.c) - gl * (1.f / v.s - 1.f / v.c);
-    const int j = knots_segment(kx, K, u.s);
-    const RqSegGrad g = rq_forward_vjp(knots_seg(kx, ky, kd, j), u.s, gsp, gl);
-    acc(j, g.gX0 - g.gw);
-    acc(j + 1, g.gw);
-    acc(K + j, g.gY0 - g.gh);
-    acc(K + j + 1, g.gh);
+    const RqSegGrad g = rq_vjp_theta(sg.g, sg.th, sg.om, gsp, gl);
+    const int j = sg.j;
+    if (sg.upx) {            // X0 = 1 - cx[j], w = cx[j] - cx[j+1]
+        acc(3 * K + j, g.gw - g.gX0);
+        acc(3 * K + j + 1, -g.gw);
+    } else {                 // X0 = kx[j], w = kx[j+1] - kx[j]
+        acc(j, g.gX0 - g.gw);
+        acc(j + 1, g.gw);
+    }
+    if (sg.upy) {
+        acc(4 * K + j, g.gh - g.gY0);
+        acc(4 * K + j + 1, -g.gh);
+    } else {
+        acc(K + j, g.gY0 - g.gh);
+        acc(K + j + 1, g.gh);
+    }
     acc(2 * K + j, g.gD0);
     acc(2 * K + j + 1, g.gD1);
     const float gs = g.gx + gl * (1.f / u.s - 1.f / u.c);

@@ -265,9 +265,10 @@ struct LogisticBwdOp {
 };
 
 // ------------------------------------------------------------------ shared 1-D spline
+// knots: [5][K] = kx | ky | kd | cx | cy  (cx, cy only read by the logistic chain)
 struct Spline1dOp {
     const float* x;
-    const float *kx, *ky, *kd;   // knots (shared memory on the device)
+    const float* knots;          // shared memory on the device
     Spline1dCfg cfg;
     int inverse;
     float* y;
@@ -275,9 +276,12 @@ struct Spline1dOp {
     NFK_HD float operator()(int64_t b, int64_t s) const {
         const int64_t i = b * V + s;
         const float xv = NFK_LDG(x + i);
+        const int K = cfg.K;
+        const float *kx = knots, *ky = knots + K, *kd = knots + 2 * K;
         float yv, lj;
         if (cfg.logistic) {
-            distconv_eval(kx, ky, kd, cfg.K, cfg.left == kExtrapAnti, inverse != 0, xv, yv, lj);
+            const UnitKnots uk{kx, ky, kd, knots + 3 * K, knots + 4 * K, K};
+            distconv_eval(uk, cfg.left == kExtrapAnti, inverse != 0, xv, yv, lj);
         } else if (inverse) {
             spline1d_inverse(kx, ky, kd, cfg, xv, yv, lj);
         } else {
@@ -288,7 +292,7 @@ struct Spline1dOp {
     }
 };
 
-// accumulate into a [3K] buffer: atomics on the device, plain adds on the host
+// accumulate into a [5K] buffer: atomics on the device, plain adds on the host
 struct KnotAcc {
     float* buf;
     NFK_HD void operator()(int i, float v) const {
@@ -302,22 +306,26 @@ struct KnotAcc {
 
 struct Spline1dBwdOp {
     const float* x;
-    const float *kx, *ky, *kd;
+    const float* knots;
     Spline1dCfg cfg;
     const float* gy;
     const float* glog;
     float* gx;
-    float* gknots;        // [3K] accumulation buffer (shared memory on the device)
+    float* gknots;        // [5K] accumulation buffer (shared memory on the device)
     int64_t V;
     NFK_HD float operator()(int64_t b, int64_t s) const {
         const int64_t i = b * V + s;
         const float xv = NFK_LDG(x + i), g = NFK_LDG(gy + i);
         const float gl = glog ? NFK_LDG(glog + b) : 0.f;
         const KnotAcc acc{gknots};
-        if (cfg.logistic)
-            gx[i] = distconv_backward(kx, ky, kd, cfg.K, cfg.left == kExtrapAnti, xv, g, gl, acc);
-        else
+        const int K = cfg.K;
+        const float *kx = knots, *ky = knots + K, *kd = knots + 2 * K;
+        if (cfg.logistic) {
+            const UnitKnots uk{kx, ky, kd, knots + 3 * K, knots + 4 * K, K};
+            gx[i] = distconv_backward(uk, cfg.left == kExtrapAnti, xv, g, gl, acc);
+        } else {
             gx[i] = spline1d_backward(kx, ky, kd, cfg, xv, g, gl, acc);
+        }
         return 0.f;
     }
 };

@@ -46,10 +46,12 @@ class RQSpline:
     def __call__(self, x, **kwargs):
         return self.forward(x, **kwargs)
 
+    def _table(self):
+        return torch.stack([self.knots_x, self.knots_y, self.knots_d])
+
     def _run(self, x, grad, inverse):
         flat = x.reshape(1, -1)
-        y, _ = _ops.spline1d(flat, self.knots_x, self.knots_y, self.knots_d, 0, self.extrap,
-                             logistic_wrap=False, inverse=inverse)
+        y, _ = _ops.spline1d(flat, self._table(), 0, self.extrap, logistic_wrap=False, inverse=inverse)
         y = y.reshape(x.shape)
         if not grad:
             return y
@@ -60,8 +62,7 @@ class RQSpline:
         autograd through the forward kernel's own backward kernel."""
         with torch.enable_grad():
             xr = x.detach().reshape(1, -1).requires_grad_(True)
-            y, _ = _ops.spline1d(xr, self.knots_x.detach(), self.knots_y.detach(), self.knots_d.detach(),
-                                 0, self.extrap, logistic_wrap=False)
+            y, _ = _ops.spline1d(xr, self._table().detach(), 0, self.extrap, logistic_wrap=False)
             (g,) = torch.autograd.grad(y.sum(), xr)
         g = g.reshape(x.shape)
         return 1.0 / g if inverse else g

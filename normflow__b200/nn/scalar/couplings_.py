@@ -82,10 +82,10 @@ class Coupling_(Module_):
         for k in (reversed(order) if inverse else order):
             p = k % 2
             out = self._conditioner(self.nets[k], x, p)
-            x, log0 = self._apply(x, out, p, log0, _C.FROZEN_COPY, inverse)
+            x, log0 = self._transform(x, out, p, log0, _C.FROZEN_COPY, inverse)
         return x, log0
 
-    def _apply(self, x, out, parity, log0, frozen_mode, inverse):
+    def _transform(self, x, out, parity, log0, frozen_mode, inverse):
         raise NotImplementedError
 
 
@@ -98,16 +98,16 @@ class ShiftCoupling_(Coupling_):
     def backward(self, x, log0=0):
         return self._sweep(x, log0, inverse=True)
 
-    def _apply(self, x, out, parity, log0, frozen_mode, inverse):
+    def _transform(self, x, out, parity, log0, frozen_mode, inverse):
         return _ops.shift_apply(x, out, self.mask._mask, parity, frozen_mode, inverse), log0
 
     def atomic_forward(self, *, x_active, x_frozen, parity, net, log0=0):
         out = net(self.preprocess_fz(x_frozen))
-        return self._apply(x_active, out, parity, log0, _C.FROZEN_ZERO, False)
+        return self._transform(x_active, out, parity, log0, _C.FROZEN_ZERO, False)
 
     def atomic_backward(self, *, x_active, x_frozen, parity, net, log0=0):
         out = net(self.preprocess_fz(x_frozen))
-        return self._apply(x_active, out, parity, log0, _C.FROZEN_ZERO, True)
+        return self._transform(x_active, out, parity, log0, _C.FROZEN_ZERO, True)
 
 
 class AffineCoupling_(Coupling_):
@@ -119,16 +119,16 @@ class AffineCoupling_(Coupling_):
     def backward(self, x, log0=0):
         return self._sweep(x, log0, inverse=True)
 
-    def _apply(self, x, out, parity, log0, frozen_mode, inverse):
+    def _transform(self, x, out, parity, log0, frozen_mode, inverse):
         return _ops.affine_apply(x, out, self.mask._mask, parity, log0, frozen_mode, inverse)
 
     def atomic_forward(self, *, x_active, x_frozen, parity, net, log0=0):
         out = net(self.preprocess_fz(x_frozen))
-        return self._apply(x_active, out, parity, log0, _C.FROZEN_ZERO, False)
+        return self._transform(x_active, out, parity, log0, _C.FROZEN_ZERO, False)
 
     def atomic_backward(self, *, x_active, x_frozen, parity, net, log0=0):
         out = net(self.preprocess_fz(x_frozen))
-        return self._apply(x_active, out, parity, log0, _C.FROZEN_ZERO, True)
+        return self._transform(x_active, out, parity, log0, _C.FROZEN_ZERO, True)
 
 
 class RQSplineCoupling_(Coupling_):
@@ -164,16 +164,16 @@ class RQSplineCoupling_(Coupling_):
             raise ValueError(f"conditioner emits {n} channels; an RQ spline needs 3K-2")
         return _ops.rqs_params((n + 2) // 3, self.xlim, self.ylim, self.extrap)
 
-    def _apply(self, x, out, parity, log0, frozen_mode, inverse):
+    def _transform(self, x, out, parity, log0, frozen_mode, inverse):
         return _ops.rqs_apply(x, out, self.mask._mask, parity, self._params(out), log0, frozen_mode, inverse)
 
     def atomic_forward(self, *, x_active, x_frozen, parity, net, log0=0):
         out = net(self.preprocess_fz(x_frozen))
-        return self._apply(x_active, out, parity, log0, _C.FROZEN_ZERO, False)
+        return self._transform(x_active, out, parity, log0, _C.FROZEN_ZERO, False)
 
     def atomic_backward(self, *, x_active, x_frozen, parity, net, log0=0):
         out = net(self.preprocess_fz(x_frozen))
-        return self._apply(x_active, out, parity, log0, _C.FROZEN_ZERO, True)
+        return self._transform(x_active, out, parity, log0, _C.FROZEN_ZERO, True)
 
     def transfer(self, scale_factor=1, mask=None, **extra):
         return self.__class__([net.transfer(scale_factor=scale_factor) for net in self.nets],

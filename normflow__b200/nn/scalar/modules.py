@@ -247,21 +247,31 @@ class SplineNet(torch.nn.Module):
         self.weights_y = torch.nn.Parameter(torch.zeros(knots_len - 1))
         self.weights_d = None if smooth else torch.nn.Parameter(torch.zeros(knots_len))
 
-    def knots(self):
-        """(knots_x, knots_y, knots_d) as differentiable float32[K] tensors.  The last
-        knot is pinned to exactly xlim[1] / ylim[1] (the cumulative softmax sums to one)."""
+    def knots(self, both_ends=False):
+        """Differentiable float32 knot table [3, K] = knots_x | knots_y | knots_d, or with
+        both_ends=True [5, K] with xlim[1] - knots_x and ylim[1] - knots_y appended.
+
+        Every row is built from cumulative softmax sums on its own side: knots_x from
+        the left, its complement from the right (so a knot close to xlim[1] is known to
+        the relative precision of its distance from xlim[1], not of its value), and the
+        bin widths / heights used for the smooth derivatives are the softmax terms
+        themselves.  The end knots are exactly xlim / ylim."""
         def coords(w, lo, width):
-            inner = torch.cumsum(torch.softmax(w, dim=0), dim=0)[:-1]
-            ends = w.new_tensor([lo, lo + width])
-            return torch.cat([ends[:1], lo + width * inner, ends[1:]])
-        kx = coords(self.weights_x, self.xlim[0], self.xwidth)
-        ky = coords(self.weights_y, self.ylim[0], self.ywidth)
+            p = torch.softmax(w, dim=0)
+            zero = p.new_zeros(1)
+            left = torch.cat([zero, torch.cumsum(p, dim=0)[:-1]])               # sum_{i<j} p_i, j < K-1
+            right = torch.cat([torch.flip(torch.cumsum(torch.flip(p, [0]), 0), [0]), zero])   # sum_{i>=j} p_i
+            k = torch.cat([lo + width * left, p.new_full((1,), lo + width)])
+            return k, width * right, width * p
+        kx, cx, wx = coords(self.weights_x, self.xlim[0], self.xwidth)
+        ky, cy, wy = coords(self.weights_y, self.ylim[0], self.ywidth)
         if self.weights_d is None:
-            slope = (ky[1:] - ky[:-1]) / (kx[1:] - kx[:-1])
+            slope = wy / wx
             kd = torch.cat([slope[:1], 0.5 * (slope[1:] + slope[:-1]), slope[-1:]])
         else:
             kd = torch.nn.functional.softplus(self.weights_d, beta=float(np.log(2)))
-        return kx, ky, kd
+        rows = [kx, ky, kd, cx, cy] if both_ends else [kx, ky, kd]
+        return torch.stack(rows)
 
     def make_spline(self):
         kx, ky, kd = self.knots()

@@ -88,12 +88,10 @@ class SplineNet_(SplineNet, Module_):
         return self.spline_kwargs.get('extrap', {})
 
     def forward(self, x, log0=0):
-        kx, ky, kd = self.knots()
-        return _ops.spline1d(x, kx, ky, kd, log0, self._extrap())
+        return _ops.spline1d(x, self.knots(), log0, self._extrap())
 
     def backward(self, x, log0=0):
-        kx, ky, kd = self.knots()
-        return _ops.spline1d(x, kx, ky, kd, log0, self._extrap(), inverse=True)
+        return _ops.spline1d(x, self.knots(), log0, self._extrap(), inverse=True)
 
 
 class UnityDistConvertor_(SplineNet_):
@@ -196,8 +194,8 @@ class DistConvertor_(ModuleList_):
         return out
 
     def _chain(self, spline_, x, log0, inverse):
-        kx, ky, kd = spline_.knots()
-        return _ops.spline1d(x, kx, ky, kd, log0, spline_._extrap(), logistic_wrap=True, inverse=inverse)
+        return _ops.spline1d(x, spline_.knots(both_ends=True), log0, spline_._extrap(),
+                             logistic_wrap=True, inverse=inverse)
 
     def forward(self, x, log0=0):
         for kind, net_ in self._segments():

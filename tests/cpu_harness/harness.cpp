@@ -134,18 +134,18 @@ int cpu_logistic_bwd(const float* x, int which, const float* gy, const float* gl
     run_sites(LogisticBwdOp{x, which, gy, glog, gx, V}, B, V, nullptr, nullptr);
     return 0;
 }
-int cpu_spline1d_fwd(const float* x, const float* kx, const float* ky, const float* kd, int K,
-                     int extrap_left, int extrap_right, int logistic, int inverse, const float* log_in,
-                     float* y, float* log_out, int64_t B, int64_t V) {
+int cpu_spline1d_fwd(const float* x, const float* knots, int K, int extrap_left, int extrap_right,
+                     int logistic, int inverse, const float* log_in, float* y, float* log_out,
+                     int64_t B, int64_t V) {
     const Spline1dCfg cfg{K, extrap_left, extrap_right, logistic};
-    run_sites(Spline1dOp{x, kx, ky, kd, cfg, inverse, y, V}, B, V, log_in, log_out);
+    run_sites(Spline1dOp{x, knots, cfg, inverse, y, V}, B, V, log_in, log_out);
     return 0;
 }
-int cpu_spline1d_bwd(const float* x, const float* kx, const float* ky, const float* kd, int K,
-                     int extrap_left, int extrap_right, int logistic, const float* gy, const float* glog,
-                     float* gx, float* gk, int64_t B, int64_t V) {
+int cpu_spline1d_bwd(const float* x, const float* knots, int K, int extrap_left, int extrap_right,
+                     int logistic, const float* gy, const float* glog, float* gx, float* gk,
+                     int64_t B, int64_t V) {
     const Spline1dCfg cfg{K, extrap_left, extrap_right, logistic};
-    run_sites(Spline1dBwdOp{x, kx, ky, kd, cfg, gy, glog, gx, gk, V}, B, V, nullptr, nullptr);
+    run_sites(Spline1dBwdOp{x, knots, cfg, gy, glog, gx, gk, V}, B, V, nullptr, nullptr);
     return 0;
 }
 int cpu_phi4_action_fwd(const float* phi, nfk_lattice lat, float w0, float w2, float w4, float* S, int64_t B) {
