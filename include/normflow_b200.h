@@ -220,6 +220,25 @@ int nfk_metropolis_scan(const float* logq, const float* logp, const double* log_
 int nfk_gather_rows(const float* src, const int64_t* idx, const float* prev, float* dst,
                     int64_t B, int64_t row_elems, void* stream);
 
+/* -------------------------------------------------------- fused 2-D step ---
+ * One whole atomic coupling step on a 2-D lattice with a ConvAct(1 -> H -> H -> P)
+ * conditioner (3x3 circular convolutions, tanh, tanh, none; optional biases) in ONE
+ * kernel: Coupling_.forward's step k (couplings_.py:56-64) = Mask.split + conditioner
+ * (modules.py:131-145) + atomic_forward/backward (couplings_.py:123-139, 178-200).  The
+ * (B,P,L0,L1) conditioner output never reaches memory and its last layer is evaluated
+ * at the active sites only.  Forward evaluation only (sampling / log_prob); training
+ * uses the unfused kernels, which keep what autograd needs.
+ *   x, y: [B][L0][L1] (y != x), full-field semantics (frozen sites copied).
+ *   w1[H][1][3][3], w2[H][H][3][3], w3[P][H][3][3]; b1, b2, b3 may be NULL.  H == 8.
+ *   kind 0: affine (P = 2); kind 1: RQ spline (P = 3K-2, prm as in nfk_rqs_fwd).
+ *   mask_parity: the `parity` of EvenOddMask.make_mask; parity: the step's partition.
+ *   inverse != 0: the atomic_backward direction.                                   */
+int nfk_fused2d_step(const float* x, const float* w1, const float* b1, const float* w2,
+                     const float* b2, const float* w3, const float* b3, int H, int kind,
+                     nfk_rqs_params prm, int mask_parity, int parity, int inverse,
+                     const float* log_in, float* y, float* log_out,
+                     int L0, int L1, int64_t B, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

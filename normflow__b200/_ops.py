@@ -452,6 +452,32 @@ def conv_stack(inp, weights, biases, acts, ksize, in_mask=None, in_keep=0):
     return _ConvStack.apply(inp, in_mask, int(in_keep), acts, int(ksize), len(weights), *weights, *biases)
 
 
+FUSED2D_KNOTS = (4, 5, 6, 8, 10, 12, 16)
+
+
+def fused2d_step(x, weights, biases, kind, prm, mask_parity, parity, log0=0, inverse=False):
+    """A whole atomic coupling step (ConvAct(1->8->8->P) conditioner + affine / RQ-spline
+    transform) in one kernel, forward evaluation only.  x: (B, L0, L1); returns (y, log)."""
+    x = _f32c(x, "x")
+    if x.dim() != 3:
+        raise ValueError("fused2d_step needs a (B, L0, L1) field")
+    _no_grad_needed(x, *weights, *[b for b in biases if b is not None])
+    log_in = as_log(log0, x)
+    B, L0, L1 = x.shape
+    w = [_f32c(t, "conv weight") for t in weights]
+    b = [None if t is None else _f32c(t, "conv bias") for t in biases]
+    y = torch.empty_like(x)
+    log_out = torch.empty((B,), dtype=torch.float32, device=x.device)
+    if prm is None:
+        prm = _C.RqsParams(2, 0.0, 1.0, 0.0, 1.0, 0, 0)
+    with _C.timed("fused2d_step"):
+        check(lib().nfk_fused2d_step(dev(x), dev(w[0]), dev(b[0]), dev(w[1]), dev(b[1]), dev(w[2]), dev(b[2]),
+                                     int(w[0].shape[0]), int(kind), prm, int(mask_parity), int(parity),
+                                     int(bool(inverse)), dev(log_in), dev(y), dev(log_out), L0, L1, B, stream()),
+              "fused2d_step")
+    return y, log_out
+
+
 # ---------------------------------------------------------------------------- mcmc
 def metropolis_scan(logq, logp, log_u, ref_state):
     """Sequential accept/reject on the device (mcmc.py:304-328).  `ref_state` is a

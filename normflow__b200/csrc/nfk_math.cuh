@@ -157,6 +157,8 @@ NFK_HD RqSegGrad rq_forward_vjp(const RqSeg& s, float x, float gy, float gl) {
 //   channels [0, K-1)        -> bin widths  (softmax)
 //   channels [K-1, 2K-2)     -> bin heights (softmax)
 //   channels [2K-2, 3K-2)    -> knot derivatives (softplus)
+// Ld also offers pick(base, n, j) = channel base + j for a run-time j in [0, n): a plain
+// load for memory-backed channels, a select chain for channels held in registers.
 struct RqsCfg {
     float xlim0, xw, ylim0, yw;
     int left, right;   // kExtrapNone | kExtrapLinear
@@ -242,8 +244,8 @@ NFK_HD RqSeg rqs_segment(const Ld& ld, const RqsCfg& cfg, const RqsSite<K>& st) 
     s.w = pick<K - 1>(st.ex, st.j) * rx;
     s.Y0 = cfg.ylim0 + st.cumy * ry;
     s.h = pick<K - 1>(st.ey, st.j) * ry;
-    s.D0 = softplus_ln2(ld(2 * K - 2 + st.j));
-    s.D1 = softplus_ln2(ld(2 * K - 2 + st.j + 1));
+    s.D0 = softplus_ln2(ld.pick(2 * K - 2, K, st.j));
+    s.D1 = softplus_ln2(ld.pick(2 * K - 2, K, st.j + 1));
     return s;
 }
 
@@ -304,7 +306,7 @@ NFK_HD float rqs_site_backward(const Ld& ld, const RqsCfg& cfg, float x, float g
         for (int c = 0; c < 3 * K - 2; ++c) store(c, c == ch ? gD * softplus_ln2_grad(raw) : 0.f);
         return gy * D;
     }
-    const float raw0 = ld(2 * K - 2 + st.j), raw1 = ld(2 * K - 2 + st.j + 1);
+    const float raw0 = ld.pick(2 * K - 2, K, st.j), raw1 = ld.pick(2 * K - 2, K, st.j + 1);
     RqSeg s;
     const float rx = cfg.xw / st.sx, ry = cfg.yw / st.sy;
     const float exj = pick<K - 1>(st.ex, st.j), eyj = pick<K - 1>(st.ey, st.j);

@@ -162,6 +162,7 @@ struct ChanLoad {
     const float* base;    // &out[b][0][s]
     int64_t stride;       // V
     NFK_HD float operator()(int c) const { return NFK_LDG(base + c * stride); }
+    NFK_HD float pick(int c0, int, int j) const { return NFK_LDG(base + (c0 + j) * stride); }
 };
 struct ChanStore {
     float* base;

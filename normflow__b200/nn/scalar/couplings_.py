@@ -15,6 +15,7 @@ import torch
 from .._core import Module_
 from ... import _ops, _C
 from .modules import ConvAct
+from ...mask import EvenOddMask
 
 
 class Coupling_(Module_):
@@ -81,9 +82,33 @@ class Coupling_(Module_):
         order = range(len(self.nets))
         for k in (reversed(order) if inverse else order):
             p = k % 2
-            out = self._conditioner(self.nets[k], x, p)
+            net = self.nets[k]
+            if self._fused_kind is not None and self._fusable(net, x):
+                # conditioner + transform in ONE kernel: the (B,P,*L) tensor is never formed
+                convs = net._convs()
+                x, log0 = _ops.fused2d_step(x, [c.weight for c in convs], [c.bias for c in convs],
+                                            self._fused_kind, self._fused_params(convs[-1].out_channels),
+                                            self.mask.mask_kwargs.get('parity', 0), p, log0, inverse)
+                continue
+            out = self._conditioner(net, x, p)
             x, log0 = self._transform(x, out, p, log0, _C.FROZEN_COPY, inverse)
         return x, log0
+
+    _fused_kind = None          # 0 affine, 1 RQ spline; None: no fused kernel for this coupling
+
+    def _fused_params(self, n_channels):
+        return None
+
+    def _fusable(self, net, x):
+        """The single-kernel step applies to evaluation (no autograd graph wanted) of a 2-D
+        checkerboard coupling whose conditioner is ConvAct(1->8->8->P, 3x3, tanh)."""
+        if not (isinstance(net, ConvAct) and net.fused2d_ok):
+            return False
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in net.parameters())):
+            return False
+        if not (isinstance(self.mask, EvenOddMask) and self.mask.mask_kwargs.get('exclude_mu') is None):
+            return False
+        return x.dim() == 3 and x.shape[2] % 4 == 0 and x.is_cuda and self.channels_axis == 1
 
     def _transform(self, x, out, parity, log0, frozen_mode, inverse):
         raise NotImplementedError
@@ -112,6 +137,8 @@ class ShiftCoupling_(Coupling_):
 
 class AffineCoupling_(Coupling_):
     """y = t + x exp(-|s|), log|J| = -sum |s|  (reference couplings_.py:120-139)."""
+
+    _fused_kind = 0
 
     def forward(self, x, log0=0):
         return self._sweep(x, log0, inverse=False)
@@ -157,6 +184,17 @@ class RQSplineCoupling_(Coupling_):
 
     def backward(self, x, log0=0):
         return self._sweep(x, log0, inverse=True)
+
+    _fused_kind = 1
+
+    def _fused_params(self, n_channels):
+        return _ops.rqs_params((n_channels + 2) // 3, self.xlim, self.ylim, self.extrap)
+
+    def _fusable(self, net, x):
+        if not super()._fusable(net, x):
+            return False
+        n = net.conv_kwargs['out_channels']
+        return (n + 2) % 3 == 0 and (n + 2) // 3 in _ops.FUSED2D_KNOTS
 
     def _params(self, out):
         n = out.shape[self.channels_axis]

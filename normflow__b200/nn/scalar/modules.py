@@ -187,6 +187,17 @@ class ConvAct(torch.nn.Sequential):
     def _convs(self):
         return [m for m in self if hasattr(m, 'standard_weight')]
 
+    @property
+    def fused2d_ok(self):
+        """True for the shape the single-kernel 2-D coupling step is specialised for:
+        ConvAct(1 -> 8 -> 8 -> P), 3x3, tanh, tanh, none."""
+        kw = self.conv_kwargs
+        return (self._pre_act is None and kw['conv_dim'] == 2 and kw['kernel_size'] == 3
+                and kw['in_channels'] == 1 and list(kw['hidden_sizes']) == [8, 8]
+                and tuple(self._acts) == ('tanh', 'tanh', None)
+                and kw.get('padding', 'same') == 'same' and kw.get('padding_mode') == 'circular'
+                and all(k not in kw for k in ('stride', 'dilation', 'groups')))
+
     def forward_masked(self, x, mask, keep):
         """Conditioner output for a field x (B, *L) of which only the sites with
         mask == keep are visible (the frozen partition): Mask.split fused into the

@@ -12,6 +12,7 @@
 
 #include "../../include/normflow_b200.h"
 #include "../../normflow__b200/csrc/nfk_ops.cuh"
+#include "../../normflow__b200/csrc/nfk_fused.cuh"
 
 using namespace nfk;
 
@@ -200,6 +201,55 @@ int cpu_conv_circ_fwd(const float* in, const float* w, int w_transposed, const f
             }
     }
     return 0;
+}
+
+}  // extern "C"
+
+// host walk through the phases of fused2d_kernel (one "CTA" per sample, items in order)
+template <int KIND, int K>
+static void fused_host(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                       const float* w3, const float* b3, FusedGeom g, FusedXform xf, const float* log_in,
+                       float* y, float* log_out, int64_t B) {
+    constexpr int P = KIND == 0 ? 2 : 3 * K - 2;
+    constexpr int PP = (P + 3) / 4 * 4;
+    std::vector<float> buf(fused_smem_floats<PP>(g.L1, g.R), 0.f);
+    const FusedSmem m = fused_carve<PP>(buf.data(), g.L1, g.R);
+    for (int e = 0; e < fused_weight_elems<PP>(); ++e) fused_load_weight<P, PP>(m, w1, w2, w3, b1, b2, b3, e);
+    const int64_t V = (int64_t)g.L0 * g.L1;
+    for (int64_t b = 0; b < B; ++b) {
+        float lacc = 0.f;
+        for (int r0 = 0; r0 < g.L0; r0 += g.R) {
+            const int rows = g.L0 - r0 < g.R ? g.L0 - r0 : g.R;
+            for (int e = 0; e < (rows + 6) * g.WS; ++e) fused_load_x(g, m, x + b * V, r0, rows, e);
+            for (int it = 0; it < (rows + 4) * g.ncg; ++it)
+                fused_hidden_item<1>(g, m.xf, g.R + 6, m.w1s, m.b1s, m.h1s, g.R + 4, rows + 4, it);
+            for (int it = 0; it < (rows + 2) * g.ncg; ++it)
+                fused_hidden_item<kFH>(g, m.h1s, g.R + 4, m.w2s, m.b2s, m.h2s, g.R + 2, rows + 2, it);
+            for (int it = 0; it < rows * g.ncg; ++it) lacc += fused_out_item<KIND, K>(g, m, xf, r0, rows, y + b * V, it);
+        }
+        if (log_out) log_out[b] = (log_in ? log_in[b] : 0.f) + lacc;
+    }
+}
+
+extern "C" {
+
+int cpu_fused2d_step(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                     const float* w3, const float* b3, int H, int kind, nfk_rqs_params prm, int mask_parity,
+                     int parity, int inverse, const float* log_in, float* y, float* log_out, int L0, int L1,
+                     int64_t B, int R) {
+    if (H != kFH || L1 % 4 != 0) return NFK_EUNSUPPORTED;
+    FusedGeom g;
+    g.L0 = L0; g.L1 = L1; g.WS = L1 + 4; g.ncg = L1 / 4; g.R = R > L0 ? L0 : R;
+    g.mask_parity = mask_parity; g.active_val = parity == 0 ? 1 : 0;
+    FusedXform xf;
+    xf.inverse = inverse;
+    xf.cfg = to_cfg(prm);
+    if (kind == 0) { fused_host<0, 2>(x, w1, b1, w2, b2, w3, b3, g, xf, log_in, y, log_out, B); return 0; }
+    switch (prm.n_knots) {
+        case 4: fused_host<1, 4>(x, w1, b1, w2, b2, w3, b3, g, xf, log_in, y, log_out, B); return 0;
+        case 10: fused_host<1, 10>(x, w1, b1, w2, b2, w3, b3, g, xf, log_in, y, log_out, B); return 0;
+    }
+    return NFK_EUNSUPPORTED;
 }
 
 }  // extern "C"

@@ -362,3 +362,64 @@ def test_distconvertor_narrow_top_bin_is_well_conditioned():
     H.cpu_spline1d_fwd(fp(x), fp(kn), kn.shape[1], 0, 0, 1, 0, None, fp(y), fp(logJ), I64(x.shape[0]), I64(x[0].size))
     close(logJ, g[f"{tag}_logJ"])
     close(y, g[f"{tag}_y"])
+
+
+@pytest.mark.parametrize("name,kind,P", [("cpl_rqs_2d", 1, 28), ("cpl_affine_2d", 0, 2)])
+@pytest.mark.parametrize("R", [16, 4, 3])
+def test_fused_2d_step_phases(name, kind, P, R):
+    """The fused conditioner+transform kernel, phase by phase on the host: whole strips
+    (R >= L0), several strips (R = 4) and a ragged last strip (R = 3), forward and inverse."""
+    g = load_golden(name)
+    mask = np.ascontiguousarray(g["mask"])
+    x = f32(g["x"])
+    B, (L0, L1) = x.shape[0], x.shape[1:]
+    prm = RqsParams(10, -5.0, 5.0, -5.0, 5.0, 1, 1)
+    log = np.zeros(B, dtype=np.float32)
+    hist = []
+    for k in range(4):
+        w = [f32(g[f"blk0_step{k}_w{i}"]) for i in range(3)]
+        y, lo = np.empty_like(x), np.empty(B, dtype=np.float32)
+        assert H.cpu_fused2d_step(fp(x), fp(w[0]), None, fp(w[1]), None, fp(w[2]), None, 8, kind, prm, 0, k % 2, 0,
+                                  fp(log), fp(y), fp(lo), L0, L1, I64(B), R) == 0
+        hist.append((x, log, w))
+        x, log = y, lo
+        if k == 0:
+            close(y * (mask if k % 2 == 0 else 1 - mask), g["blk0_step0_fx"], tol=2e-5)
+    close(x, g["y"], tol=2e-5)
+    close(log, g["logJ"], tol=2e-5)
+    # inverse sweep restores the field and cancels the log-Jacobian
+    for k in reversed(range(4)):
+        xin, login, w = hist[k]
+        xb, lb = np.empty_like(x), np.empty(B, dtype=np.float32)
+        H.cpu_fused2d_step(fp(x), fp(w[0]), None, fp(w[1]), None, fp(w[2]), None, 8, kind, prm, 0, k % 2, 1,
+                           fp(log), fp(xb), fp(lb), L0, L1, I64(B), R)
+        x, log = xb, lb
+    close(x, g["x"], tol=1e-4)
+    close(log, np.zeros(B), tol=2e-4)
+
+
+def test_fused_2d_step_with_bias_and_odd_mask_parity():
+    """Biases, EvenOddMask(parity=1) and a non-square lattice against the unfused host ops."""
+    rs = np.random.RandomState(21)
+    B, L0, L1 = 2, 6, 12
+    x = f32(rs.randn(B, L0, L1) * 1.5)
+    w = [f32(rs.randn(8, 1, 3, 3) * 0.4), f32(rs.randn(8, 8, 3, 3) * 0.15), f32(rs.randn(28, 8, 3, 3) * 0.15)]
+    b = [f32(rs.randn(8) * 0.2), f32(rs.randn(8) * 0.2), f32(rs.randn(28) * 0.2)]
+    mask = np.empty((L0, L1), dtype=np.uint8)
+    H.cpu_mask_evenodd(up(mask), lattice((L0, L1)), 1, -1)
+    prm = RqsParams(10, -4.0, 4.0, -3.0, 5.0, 1, 1)
+    for parity in (0, 1):
+        h = x.reshape(B, 1, L0, L1)
+        for i in range(3):
+            Co, Ci = w[i].shape[:2]
+            out = np.empty((B, Co, L0, L1), dtype=np.float32)
+            H.cpu_conv_circ_fwd(fp(h), fp(w[i]), 0, fp(b[i]), up(mask) if i == 0 else None, 0 if parity == 0 else 1,
+                                1 if i < 2 else 0, None, 0, fp(out), lattice((L0, L1)), 3, Ci, Co, I64(B))
+            h = out
+        yr, lr = np.empty_like(x), np.empty(B, dtype=np.float32)
+        H.cpu_rqs_fwd(fp(x), fp(h), up(mask), parity, 1, prm, None, fp(yr), fp(lr), I64(B), I64(L0 * L1))
+        y, lo = np.empty_like(x), np.empty(B, dtype=np.float32)
+        assert H.cpu_fused2d_step(fp(x), fp(w[0]), fp(b[0]), fp(w[1]), fp(b[1]), fp(w[2]), fp(b[2]), 8, 1, prm, 1,
+                                  parity, 0, None, fp(y), fp(lo), L0, L1, I64(B), 4) == 0
+        close(y, yr.astype(np.float64), tol=2e-5)
+        close(lo, lr.astype(np.float64), tol=2e-5)

@@ -625,3 +625,44 @@ def test_training_step_reduces_loss_config2():
     assert np.isfinite(loss).all() and np.mean(loss[-10:]) < np.mean(loss[:10]) - 1.0
     y = model.mcmc.sample(512)
     assert y.shape == (512, 16, 16) and 0 < model.mcmc.history.accept_rate[-1] <= 1
+
+
+# ------------------------------------------------------------------ fused single-kernel coupling step
+@pytest.mark.parametrize("shape,blocks,B", [((64, 64), [('rqs', 4)], 33), ((16, 16), [('affine', 4)], 257),
+                                            ((24, 40), [('affine', 2), ('rqs', 3)], 5), ((8, 8), [('rqs', 2)], 3)])
+def test_fused_step_matches_unfused_and_oracle(shape, blocks, B):
+    """Without autograd the couplings run conditioner + transform as one kernel
+    (nfk_fused2d_step); with autograd they run the unfused kernels.  Same numbers."""
+    model = _config_model(shape, blocks, seed=5)
+    x = torch.randn(B, *shape, generator=torch.Generator('cpu').manual_seed(7), dtype=torch.float32,
+                    device='cpu').to(DEV)
+    n0 = _C.launch_count()
+    with torch.no_grad():
+        y_f, l_f = model.net_(x)
+    n_fused = _C.launch_count() - n0
+    assert n_fused == sum(n for _, n in blocks)          # exactly one launch per atomic step
+    y_u, l_u = model.net_(x.clone().requires_grad_(True))    # autograd on -> unfused path
+    assert torch.allclose(y_f, y_u.detach(), atol=2e-5, rtol=2e-5)
+    assert torch.allclose(l_f, l_u.detach(), atol=1e-5 * max(1.0, l_u.abs().max().item()))
+    if B <= 8:
+        yr, lr = _oracle_flow(model, x.cpu().numpy())
+        close(y_f, yr)
+        close(l_f, lr)
+    with torch.no_grad():
+        xb, lb = model.net_.backward(y_f, log0=l_f)
+    assert (xb - x).abs().max().item() < 1e-4 and lb.abs().max().item() < 1e-4 * max(1.0, l_f.abs().max().item())
+
+
+def test_fused_step_with_bias_and_mask_parity():
+    torch.manual_seed(9)
+    shape = (12, 8)
+    mask = EvenOddMask(shape=shape, parity=1)
+    nets = [ConvAct(1, 28, 3, conv_dim=2, hidden_sizes=[8, 8], acts=('tanh', 'tanh', None), bias=True)
+            for _ in range(3)]
+    cpl = RQSplineCoupling_(nets, mask=mask, xlim=(-4, 4), ylim=(-3, 5), extrap=dict(left='linear', right='linear'))
+    cpl.to(DEV)
+    x = torch.randn(6, *shape, device=DEV) * 1.5
+    with torch.no_grad():
+        y_f, l_f = cpl(x)
+    y_u, l_u = cpl(x.clone().requires_grad_(True))
+    assert torch.allclose(y_f, y_u.detach(), atol=2e-5, rtol=2e-5) and torch.allclose(l_f, l_u.detach(), atol=2e-4)
