@@ -2,6 +2,8 @@
 // One CTA per sample walks the lattice in strips of R rows; the per-sample log|det J| is
 // reduced once at the end (warp shuffles + shared memory), so it is deterministic.
 
+#include <stdlib.h>
+
 #include "nfk_common.cuh"
 #include "nfk_fused.cuh"
 
@@ -72,6 +74,19 @@ static int fused_launch(FusedArgs a, int64_t B, cudaStream_t st) {
 
 #define NFK_FUSED_K(X) X(4) X(5) X(6) X(8) X(10) X(12) X(16)
 
+namespace nfk {
+int fused2d_tc_step(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                    const float* w3, const float* b3, int kind, const nfk_rqs_params& prm, int mask_parity,
+                    int parity, int inverse, const float* log_in, float* y, float* log_out, int L0, int L1,
+                    int64_t B, cudaStream_t st);
+}
+
+// NFK_FUSED_TC=0 in the environment keeps the CUDA-core kernel (A/B timing and debugging)
+static bool tc_enabled() {
+    const char* e = getenv("NFK_FUSED_TC");      // read per call: tests flip it at run time
+    return !(e && e[0] == '0');
+}
+
 extern "C" int nfk_fused2d_step(const float* x, const float* w1, const float* b1, const float* w2,
                                 const float* b2, const float* w3, const float* b3, int H, int kind,
                                 nfk_rqs_params prm, int mask_parity, int parity, int inverse,
@@ -81,6 +96,16 @@ extern "C" int nfk_fused2d_step(const float* x, const float* w1, const float* b1
     if (H != kFH || L0 < 1 || L1 < 4 || L1 % 4 != 0 || (kind != 0 && kind != 1)) return NFK_EUNSUPPORTED;
     if (((uintptr_t)y % 16) != 0) return NFK_EINVAL;
     if (B <= 0) return NFK_OK;
+    if (kind == 1) {
+        if (prm.n_knots < 2 || !(prm.xlim1 > prm.xlim0) || !(prm.ylim1 > prm.ylim0)) return NFK_EINVAL;
+        if ((prm.extrap_left != NFK_EXTRAP_NONE && prm.extrap_left != NFK_EXTRAP_LINEAR) ||
+            (prm.extrap_right != NFK_EXTRAP_NONE && prm.extrap_right != NFK_EXTRAP_LINEAR)) return NFK_EINVAL;
+    }
+    if (tc_enabled()) {        // conditioner on the tensor cores when the geometry allows it
+        const int rc = fused2d_tc_step(x, w1, b1, w2, b2, w3, b3, kind, prm, mask_parity, parity, inverse, log_in, y,
+                                       log_out, L0, L1, B, NFK_STREAM(stream));
+        if (rc != NFK_EUNSUPPORTED) return rc;
+    }
     FusedArgs a;
     a.x = x; a.w1 = w1; a.b1 = b1; a.w2 = w2; a.b2 = b2; a.w3 = w3; a.b3 = b3;
     a.log_in = log_in; a.y = y; a.log_out = log_out;

@@ -1,0 +1,411 @@
+// nfk_fused_tc.cu -- kernel and launch of the tensor-core fused coupling step
+// (design notes: nfk_fused_tc.cuh).  Persistent CTAs (two per SM) loop over samples; per
+// sample the lattice is walked in strips of R rows.
+//
+// Per strip (rows = output rows, r0 = first lattice row), linear index = row * WS + slot,
+// slot = column + 1:
+//   x  strip : rows r0-3 .. r0+rows+2   fp32   [rows+6][WS]
+//   h1 strip : rows r0-2 .. r0+rows+1   fp16 hi/lo planes of 16-byte records (8 channels)
+//   h2 strip : rows r0-1 .. r0+rows     the same, split by the parity of the linear index
+//
+//   compute warps                                   MMA warp
+//   -------------                                   --------
+//   load x strip                    |barC|
+//   P1: h1 = tanh(conv1(x frozen))  -> arrive H1    sync H1: layer-2 tiles (9 MMAs each, N = 16),
+//   E2: per tile wait m2[j]; TMEM -> bias, tanh,             commit m2[j] per tile
+//       split -> h2                 -> arrive H2    sync H2: layer-3 tiles on ACTIVE sites
+//   E3: per tile wait m3[k]; TMEM -> spline/affine           (9 MMAs, N = 2 NP), commit m3[k]
+//       -> y into the x strip       |barC|
+//   copy the strip's rows to y      |barC|
+
+#include "nfk_common.cuh"
+#include "nfk_fused_tc.cuh"
+
+using namespace nfk;
+
+struct TcArgs {
+    const float *x, *w1, *b1, *w2, *b2, *w3, *b3, *log_in;
+    float *y, *log_out;
+    long long B;
+    TcGeom g;
+    RqsCfg cfg;
+};
+
+namespace {
+
+// 8 broadcast weights as two 128-bit shared loads
+__device__ __forceinline__ void load_w8(const float* p, float (&wv)[8]) {
+    const float4 t0 = reinterpret_cast<const float4*>(p)[0], t1 = reinterpret_cast<const float4*>(p)[1];
+    wv[0] = t0.x; wv[1] = t0.y; wv[2] = t0.z; wv[3] = t0.w; wv[4] = t1.x; wv[5] = t1.y; wv[6] = t1.z; wv[7] = t1.w;
+}
+
+__device__ __forceinline__ int wrap_idx(int v, int L) {
+    v %= L;
+    return v < 0 ? v + L : v;
+}
+
+// 8 channel values of one site -> the hi / lo fp16 records
+__device__ __forceinline__ void make_records(const float (&v)[8], uint4& hi, uint4& lo) {
+    float l[8], h[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) h[c] = tc_split(v[c], l[c]);
+    hi = make_uint4(tc_pack(h[0], h[1]), tc_pack(h[2], h[3]), tc_pack(h[4], h[5]), tc_pack(h[6], h[7]));
+    lo = make_uint4(tc_pack(l[0], l[1]), tc_pack(l[2], l[3]), tc_pack(l[4], l[5]), tc_pack(l[6], l[7]));
+}
+
+template <int KIND, int K, int INV>
+__global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs a) {
+    constexpr int P = KIND == 0 ? 2 : 3 * K - 2;
+    constexpr int NP = TcShape<P>::NP, N3 = TcShape<P>::N3;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const TcGeom& g = a.g;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int WS = g.WS, L0 = g.L0, L1 = g.L1;
+
+    float* xs = reinterpret_cast<float*>(smem + g.off_xs);
+    uint8_t* h1 = smem + g.off_h1 + kTcGuard * 16;            // record 0 of the hi plane
+    uint8_t* h2 = smem + g.off_h2 + kTcGuard * 16;            // record 0 of parity 0, hi plane
+    __half* B2 = reinterpret_cast<__half*>(smem + g.off_b2);  // [tap][kgroup][16][8]
+    __half* B3 = reinterpret_cast<__half*>(smem + g.off_b3);  // [tap][kgroup][N3][8]
+    float* w1s = reinterpret_cast<float*>(smem + g.off_w1);   // [tap][8] | b1[8] | b2[8] | b3[NP]
+    float* b1s = w1s + 72;
+    float* b2s = b1s + 8;
+    float* b3s = b2s + 8;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.off_bar);   // m2[16] | m3[8]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+    float* red = reinterpret_cast<float*>(tmem_slot + 2);             // 8 floats
+
+    // ---- one-time set-up: weights -> fp16 pair operands, barriers, TMEM -------------------
+    for (int e = tid; e < 9 * 16 * 8; e += kTcThreads) {                 // layer 2: N = [8 hi | 8 lo]
+        const int ci = e & 7, n = (e >> 3) & 15, t = e >> 7;
+        const int co = n & 7;
+        const float w = NFK_LDG(a.w2 + (co * 8 + ci) * 9 + t);
+        const __half hi = __float2half_rn(w);
+        const __half val = n < 8 ? hi : __float2half_rn((w - __half2float(hi)) * kLoScale);
+        B2[((t * 2 + 0) * 16 + n) * 8 + ci] = val;
+        B2[((t * 2 + 1) * 16 + n) * 8 + ci] = val;
+    }
+    for (int e = tid; e < 9 * N3 * 8; e += kTcThreads) {                 // layer 3: N = [NP hi | NP lo]
+        const int ci = e & 7, n = (e >> 3) % N3, t = (e >> 3) / N3;
+        const int p = n < NP ? n : n - NP;
+        __half val = __float2half_rn(0.f);
+        if (p < P) {
+            const float w = NFK_LDG(a.w3 + (p * 8 + ci) * 9 + t);
+            const __half hi = __float2half_rn(w);
+            val = n < NP ? hi : __float2half_rn((w - __half2float(hi)) * kLoScale);
+        }
+        B3[((t * 2 + 0) * N3 + n) * 8 + ci] = val;
+        B3[((t * 2 + 1) * N3 + n) * 8 + ci] = val;
+    }
+    for (int e = tid; e < 72 + 8 + 8 + NP; e += kTcThreads) {
+        float v;
+        if (e < 72) v = NFK_LDG(a.w1 + (e & 7) * 9 + (e >> 3));          // w1s[tap][co]
+        else if (e < 80) v = a.b1 ? NFK_LDG(a.b1 + e - 72) : 0.f;
+        else if (e < 88) v = a.b2 ? NFK_LDG(a.b2 + e - 80) : 0.f;
+        else v = (a.b3 && e - 88 < P) ? NFK_LDG(a.b3 + e - 88) : 0.f;
+        w1s[e] = v;
+    }
+    if (tid == 0) {
+        for (int i = 0; i < 24; ++i) tc::mbar_init(tc::smem_u32(bars + i), 1);
+        tc::fence_mbar_init();
+    }
+    if (warp == 8) tc::tmem_alloc(tc::smem_u32(tmem_slot), kTcTmemCols);
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const int cbase = tc_cbase(WS);
+
+    if (warp == 8) {
+        // =============================== MMA warp =========================================
+        const bool lead = tc::elect_one();
+        const uint32_t idesc2 = tc::make_idesc(0, 128, 16), idesc3 = tc::make_idesc(0, 128, N3);
+        const uint64_t a1_desc = tc::make_desc(tc::smem_u32(h1), g.h1_comp_bytes, 128);
+        const uint64_t a2_desc0 = tc::make_desc(tc::smem_u32(h2), g.h2_comp_bytes, 128);
+        const uint64_t a2_desc1 = tc::make_desc(tc::smem_u32(h2 + g.h2_par_bytes), g.h2_comp_bytes, 128);
+        const uint64_t b2_desc = tc::make_desc(tc::smem_u32(B2), 16 * 16, 128);
+        const uint64_t b3_desc = tc::make_desc(tc::smem_u32(B3), N3 * 16, 128);
+        for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
+            for (int r0 = 0; r0 < L0; r0 += g.R) {
+                const int rows = L0 - r0 < g.R ? L0 - r0 : g.R;
+                const int t2 = tc_tiles2(rows, WS), t3 = tc_tiles3(rows, WS, L1);
+                const int plin = (g.active_val - 1 + g.mask_parity - r0) & 1;
+                // ---- layer 2: out record i2 = 128 j + m reads h1 records i2 + WS + dr WS + dc
+                tc::bar_sync(kBarH1, kTcThreads);
+                tc::fence_after_sync();
+                if (lead) {
+                    for (int j = 0; j < t2; ++j) {
+#pragma unroll
+                        for (int t = 0; t < 9; ++t) {
+                            const int delta = (t / 3 - 1) * WS + (t % 3 - 1);
+                            tc::mma_f16(tmem + j * 16, tc::desc_advance(a1_desc, j * 128 + WS + delta),
+                                        tc::desc_advance(b2_desc, t * 2 * 16), idesc2, t > 0);
+                        }
+                        tc::mma_commit(tc::smem_u32(bars + j));
+                    }
+                }
+                __syncwarp();
+                // ---- layer 3: active record c (site s = 2c + plin) reads s + dr WS + dc
+                tc::bar_sync(kBarH2, kTcThreads);
+                tc::fence_after_sync();
+                if (lead) {
+                    for (int k = 0; k < t3; ++k) {
+#pragma unroll
+                        for (int t = 0; t < 9; ++t) {
+                            const int sh = plin + (t / 3 - 1) * WS + (t % 3 - 1);   // parity and offset of the source
+                            const uint64_t ad = (sh & 1) ? a2_desc1 : a2_desc0;
+                            tc::mma_f16(tmem + k * N3, tc::desc_advance(ad, cbase + k * 128 + (sh >> 1)),
+                                        tc::desc_advance(b3_desc, t * 2 * N3), idesc3, t > 0);
+                        }
+                        tc::mma_commit(tc::smem_u32(bars + 16 + k));
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ============================= compute warps ======================================
+        const int q = warp & 3, set = warp >> 2;
+        uint32_t ph2 = 0, ph3 = 0;                                 // phase parity per barrier (my tiles)
+        const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+        for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
+            const float* xb = a.x + b * (long long)L0 * L1;
+            float* yb = a.y + b * (long long)L0 * L1;
+            float lacc = 0.f;
+            for (int r0 = 0; r0 < L0; r0 += g.R) {
+                const int rows = L0 - r0 < g.R ? L0 - r0 : g.R;
+                const int t2 = tc_tiles2(rows, WS), t3 = tc_tiles3(rows, WS, L1);
+                const int plin = (g.active_val - 1 + g.mask_parity - r0) & 1;
+                // ---- x strip (periodic wrap by index)
+                for (int e = tid; e < (rows + 6) * WS; e += kTcComputeThreads) {
+                    const int j = e / WS, slot = e - j * WS;
+                    float v = 0.f;
+                    if (slot <= L1 + 1) v = NFK_LDG(xb + wrap_idx(r0 - 3 + j, L0) * L1 + wrap_idx(slot - 1, L1));
+                    xs[e] = v;
+                }
+                tc::bar_sync(kBarCompute, kTcComputeThreads);
+                // ---- P1: h1 rows j1 = 0 .. rows+3, two columns x 8 channels per item
+                {
+                    const int half = L1 >> 1, items = (rows + 4) * half;
+                    for (int it = tid; it < items; it += kTcComputeThreads) {
+                        const int j1 = it / half, c0 = (it - j1 * half) * 2;
+                        // window: x rows j1 .. j1+2 (strip rows), slots c0 .. c0+3; frozen sites only
+                        // mask bit of (row, col) = (1 - mask_parity + row + col) & 1; lattice row of x
+                        // strip row jx is r0 - 3 + jx, col = slot - 1
+                        const int bit0 = (1 - g.mask_parity + (r0 - 3 + j1) + (c0 - 1)) & 1;   // of win[0][0]
+                        const float m_even = (bit0 != g.active_val) ? 1.f : 0.f;            // keep win[dr][k], dr+k even
+                        const float m_odd = 1.f - m_even;
+                        float win[3][4];
+#pragma unroll
+                        for (int dr = 0; dr < 3; ++dr)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                win[dr][k] = xs[(j1 + dr) * WS + c0 + k] * (((dr + k) & 1) ? m_odd : m_even);
+                        float acc[2][8];
+#pragma unroll
+                        for (int s = 0; s < 2; ++s)
+#pragma unroll
+                            for (int co = 0; co < 8; ++co) acc[s][co] = b1s[co];
+#pragma unroll
+                        for (int dr = 0; dr < 3; ++dr)
+#pragma unroll
+                            for (int dc = 0; dc < 3; ++dc) {
+                                float wv[8];
+                                load_w8(w1s + (dr * 3 + dc) * 8, wv);
+#pragma unroll
+                                for (int co = 0; co < 8; ++co) {
+                                    acc[0][co] = fmaf(win[dr][dc], wv[co], acc[0][co]);
+                                    acc[1][co] = fmaf(win[dr][dc + 1], wv[co], acc[1][co]);
+                                }
+                            }
+#pragma unroll
+                        for (int s = 0; s < 2; ++s) {
+                            float v[8];
+#pragma unroll
+                            for (int co = 0; co < 8; ++co) v[co] = tanh_fast(acc[s][co]);
+                            uint4 hi, lo;
+                            make_records(v, hi, lo);
+                            const int col = c0 + s, i1 = j1 * WS + col + 1;
+                            *reinterpret_cast<uint4*>(h1 + i1 * 16) = hi;
+                            *reinterpret_cast<uint4*>(h1 + g.h1_comp_bytes + i1 * 16) = lo;
+                            if (col == 0) {                       // column L1 is column 0
+                                *reinterpret_cast<uint4*>(h1 + (i1 + L1) * 16) = hi;
+                                *reinterpret_cast<uint4*>(h1 + g.h1_comp_bytes + (i1 + L1) * 16) = lo;
+                            }
+                            if (col == L1 - 1) {                  // column -1 is column L1-1
+                                *reinterpret_cast<uint4*>(h1 + (i1 - L1) * 16) = hi;
+                                *reinterpret_cast<uint4*>(h1 + g.h1_comp_bytes + (i1 - L1) * 16) = lo;
+                            }
+                        }
+                    }
+                }
+                tc::fence_before_sync();
+                tc::fence_async_smem();
+                tc::bar_arrive(kBarH1, kTcThreads);
+                // ---- E2: accumulators of layer 2 -> h2 records
+                for (int j = set; j < t2; j += 2) {
+                    tc::mbar_wait(tc::smem_u32(bars + j), (ph2 >> j) & 1u);
+                    ph2 ^= 1u << j;
+                    tc::fence_after_sync();
+                    float acc[16];
+                    tc::tmem_ld16(lane_addr + j * 16, acc);
+                    tc::tmem_ld_wait();
+                    const int i2 = j * 128 + q * 32 + lane;
+                    const int j2 = i2 / WS, slot = i2 - j2 * WS;
+                    if (j2 < rows + 2 && slot >= 1 && slot <= L1) {
+                        float v[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            v[c] = tanh_fast(fmaf(acc[8 + c], 1.f / kLoScale, acc[c]) + b2s[c]);
+                        uint4 hi, lo;
+                        make_records(v, hi, lo);
+                        uint8_t* dst = h2 + (i2 & 1) * g.h2_par_bytes + (i2 >> 1) * 16;
+                        *reinterpret_cast<uint4*>(dst) = hi;
+                        *reinterpret_cast<uint4*>(dst + g.h2_comp_bytes) = lo;
+                        if (slot == 1 || slot == L1) {            // periodic copies: slot L1+1 / slot 0
+                            const int iw = slot == 1 ? i2 + L1 : i2 - L1;
+                            uint8_t* dw = h2 + (iw & 1) * g.h2_par_bytes + (iw >> 1) * 16;
+                            *reinterpret_cast<uint4*>(dw) = hi;
+                            *reinterpret_cast<uint4*>(dw + g.h2_comp_bytes) = lo;
+                        }
+                    }
+                }
+                tc::fence_before_sync();
+                tc::fence_async_smem();
+                tc::bar_arrive(kBarH2, kTcThreads);
+                // ---- E3: accumulators of layer 3 at the active sites -> transform
+                for (int k = set; k < t3; k += 2) {
+                    tc::mbar_wait(tc::smem_u32(bars + 16 + k), (ph3 >> k) & 1u);
+                    ph3 ^= 1u << k;
+                    tc::fence_after_sync();
+                    float prm[NP];
+#pragma unroll
+                    for (int ch = 0; ch < NP / 16; ++ch) {
+                        float hi[16], lo[16];
+                        tc::tmem_ld16(lane_addr + k * N3 + ch * 16, hi);
+                        tc::tmem_ld16(lane_addr + k * N3 + NP + ch * 16, lo);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int c = 0; c < 16; ++c)
+                            prm[ch * 16 + c] = fmaf(lo[c], 1.f / kLoScale, hi[c]) + b3s[ch * 16 + c];
+                    }
+                    const int s = 2 * (cbase + k * 128 + q * 32 + lane) + plin;
+                    const int j2 = s / WS, slot = s - j2 * WS;
+                    if (j2 >= 1 && j2 <= rows && slot >= 1 && slot <= L1) {
+                        float* px = xs + (j2 + 2) * WS + slot;
+                        const float xv = *px;
+                        float out, l;
+                        if (KIND == 0) {
+                            const float t = prm[0], sc = fabsf(prm[1]);
+                            if (!INV) { out = t + xv * expf(-sc); l = -sc; }
+                            else { out = (xv - t) * expf(sc); l = sc; }
+                        } else {
+                            const RegLoad<NP> ld{prm};
+                            if (!INV) rqs_site_forward<K>(ld, a.cfg, xv, out, l);
+                            else rqs_site_inverse<K>(ld, a.cfg, xv, out, l);
+                        }
+                        *px = out;
+                        lacc += l;
+                    }
+                }
+                tc::bar_sync(kBarCompute, kTcComputeThreads);
+                // ---- the strip's rows (active: transformed, frozen: copied) -> y
+                for (int e = tid; e < rows * L1; e += kTcComputeThreads) {
+                    const int j = e / L1, col = e - j * L1;
+                    yb[(r0 + j) * L1 + col] = xs[(j + 3) * WS + col + 1];
+                }
+                tc::bar_sync(kBarCompute, kTcComputeThreads);
+            }
+            // ---- log|det J| of the sample (deterministic: fixed reduction tree)
+            lacc = warp_sum(lacc);
+            if (lane == 0) red[warp] = lacc;
+            tc::bar_sync(kBarCompute, kTcComputeThreads);
+            if (tid == 0 && a.log_out) {
+                float tot = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) tot += red[w];
+                a.log_out[b] = (a.log_in ? a.log_in[b] : 0.f) + tot;
+            }
+            tc::bar_sync(kBarCompute, kTcComputeThreads);
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 8) tc::tmem_dealloc(tmem, kTcTmemCols);
+}
+
+template <int KIND, int K, int INV>
+int tc_launch(TcArgs a, cudaStream_t st) {
+    constexpr int P = KIND == 0 ? 2 : 3 * K - 2;
+    static int sm_count = 0;
+    static int max_smem = 0;
+    if (sm_count == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (sm_count <= 0) sm_count = 148;
+    }
+    // two CTAs per SM: each may use half of the SM's shared memory (minus the 1 KB system slice)
+    const uint32_t budget = (uint32_t)((max_smem > 0 ? max_smem : 227 * 1024) + 1024) / 2 - 1024;
+    int best = 0;
+    float best_cost = 1e30f;
+    TcGeom g = a.g;
+    for (int R = 2; R <= a.g.L0; ++R) {
+        if (!tc_plan<P>(g, R, budget)) continue;
+        const float c = tc_cost_per_row<P>(g.L0, g.L1, g.WS, R);
+        if (c < best_cost) { best_cost = c; best = R; }
+    }
+    if (best == 0) return NFK_EUNSUPPORTED;
+    tc_plan<P>(a.g, best, budget);
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(fused2d_tc_kernel<KIND, K, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)budget) != cudaSuccess) return NFK_ECUDA;
+        attr_set = true;
+    }
+    long long grid = 2LL * sm_count;
+    if (grid > a.B) grid = a.B;
+    fused2d_tc_kernel<KIND, K, INV><<<(unsigned)grid, kTcThreads, a.g.smem_bytes, st>>>(a);
+    return check_launch();
+}
+
+template <int KIND, int K>
+int tc_launch_dir(const TcArgs& a, int inverse, cudaStream_t st) {
+    return inverse ? tc_launch<KIND, K, 1>(a, st) : tc_launch<KIND, K, 0>(a, st);
+}
+
+}  // namespace
+
+namespace nfk {
+
+// Tensor-core fused step; NFK_EUNSUPPORTED when the geometry / knot count is outside what
+// this kernel covers (the caller then runs the CUDA-core kernel of nfk_fused.cu).
+int fused2d_tc_step(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                    const float* w3, const float* b3, int kind, const nfk_rqs_params& prm, int mask_parity,
+                    int parity, int inverse, const float* log_in, float* y, float* log_out, int L0, int L1,
+                    int64_t B, cudaStream_t st) {
+    if ((L0 & 1) || (L1 & 1) || L1 < 2 || L0 < 2) return NFK_EUNSUPPORTED;   // checkerboard must wrap consistently
+    TcArgs a;
+    a.x = x; a.w1 = w1; a.b1 = b1; a.w2 = w2; a.b2 = b2; a.w3 = w3; a.b3 = b3;
+    a.log_in = log_in; a.y = y; a.log_out = log_out; a.B = B;
+    a.g = TcGeom{};
+    a.g.L0 = L0; a.g.L1 = L1; a.g.WS = L1 + 3;
+    a.g.mask_parity = mask_parity; a.g.active_val = parity == 0 ? 1 : 0;
+    a.cfg = RqsCfg{0.f, 1.f, 0.f, 1.f, 0, 0};
+    if (kind == 0) return tc_launch_dir<0, 2>(a, inverse, st);
+    a.cfg = RqsCfg{prm.xlim0, prm.xlim1 - prm.xlim0, prm.ylim0, prm.ylim1 - prm.ylim0, prm.extrap_left,
+                   prm.extrap_right};
+    switch (prm.n_knots) {
+        case 4: return tc_launch_dir<1, 4>(a, inverse, st);
+        case 5: return tc_launch_dir<1, 5>(a, inverse, st);
+        case 6: return tc_launch_dir<1, 6>(a, inverse, st);
+        case 8: return tc_launch_dir<1, 8>(a, inverse, st);
+        case 10: return tc_launch_dir<1, 10>(a, inverse, st);
+        default: return NFK_EUNSUPPORTED;
+    }
+}
+
+}  // namespace nfk

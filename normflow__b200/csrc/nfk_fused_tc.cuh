@@ -1,0 +1,126 @@
+// nfk_fused_tc.cuh -- the fused 2-D coupling step with its conditioner on the tensor cores.
+//
+// Same operator as nfk_fused.cuh (Coupling_.forward step k, couplings_.py:56-64, with the
+// ConvAct(1 -> 8 -> 8 -> P) conditioner of modules.py:131-145 and the affine / RQ-spline
+// transform of couplings_.py:123-139, 178-262), but layers 2 and 3 of the conditioner run as
+// implicit GEMMs on tcgen05:
+//
+//   * operands are fp16 PAIRS: every activation / weight v is carried as v = hi + lo with
+//     hi = fp16(v), lo = fp16(v - hi) (weights: lo scaled by 2^11 to stay normal).  One
+//     kind::f16 MMA has K = 16 = [8 channels of hi | 8 channels of lo] of the activations
+//     against [w_hi ; w_hi] in accumulator columns [0, N) and [w_lo ; w_lo] in columns
+//     [N, 2N): acc = (a_hi + a_lo) w_hi + 2^-11 (a_hi + a_lo) w_lo' -- 22 significant bits
+//     per factor, fp32 accumulation in TMEM.  The 1e-5 parity contract rules out plain
+//     fp16 / bf16 / tf32 (hard part 1); this split costs ONE MMA per tap.
+//   * a strip of the lattice lives in shared memory as 16-byte records (one site = 8 fp16
+//     channels) in LINEAR order with an odd row stride WS = L1 + 3 (slot 0 / L1+1 hold the
+//     periodic wrap copies), so (i) an M = 128 tile of consecutive records is a valid
+//     K-major no-swizzle UMMA operand and a conv tap is a shifted start address, and (ii) the
+//     checkerboard parity of a site is the parity of its linear index: layer 3 runs on the
+//     ACTIVE sites only, from parity-split copies of h2 (index >> 1 within a parity plane).
+//   * one MMA warp issues; eight compute warps run layer 1 (CUDA cores), the TMEM epilogues
+//     (bias, tanh, fp16 split; spline) and the field I/O.  MMAs of a strip overlap with the
+//     epilogue of earlier tiles, and two CTAs per SM overlap each other's phases.
+//
+// Measured basis (scratch/tc_probe.cu on a B200): an M=128 kind::f16/tf32 MMA costs ~41
+// cycles for any N <= 32 (A-operand read bound), 50 at N = 64; the shifted-start layout and
+// the split reproduce fp64 to 4e-7 of sum|terms|.
+#pragma once
+
+#include <cuda_fp16.h>
+
+#include "nfk_fused.cuh"
+#include "nfk_tc.cuh"
+
+namespace nfk {
+
+constexpr int kTcComputeThreads = 256;      // warps 0..7
+constexpr int kTcThreads = 288;             // + the MMA warp (warp 8)
+constexpr int kTcTmemCols = 256;            // per CTA: two CTAs share the SM's 512 columns
+constexpr int kTcGuard = 8;                 // 16-byte records of slack in front of every plane
+constexpr float kLoScale = 2048.f;          // weights' lo part is stored times 2^11
+
+enum { kBarCompute = 1, kBarH1 = 2, kBarH2 = 3 };
+
+// launch geometry (host-computed, passed by value)
+struct TcGeom {
+    int L0, L1, WS;              // lattice rows, columns, WS = L1 + 3 (odd)
+    int R;                       // output rows per strip
+    int mask_parity, active_val;
+    // shared-memory map (byte offsets from the 1024-aligned base)
+    uint32_t off_xs, off_h1, off_h2, off_b2, off_b3, off_w1, off_bar;
+    uint32_t h1_comp_bytes;      // hi plane -> lo plane of h1
+    uint32_t h2_comp_bytes;      // hi plane -> lo plane of h2 (within a parity)
+    uint32_t h2_par_bytes;       // parity 0 -> parity 1
+    uint32_t smem_bytes;
+};
+
+NFK_HD int tc_div_up(int a, int b) { return (a + b - 1) / b; }
+// tiles of layer 2 / layer 3 for a strip with `rows` output rows
+NFK_HD int tc_tiles2(int rows, int WS) { return tc_div_up((rows + 2) * WS, 128); }
+NFK_HD int tc_cbase(int WS) { return (WS + 1) >> 1; }
+NFK_HD int tc_tiles3(int rows, int WS, int L1) {
+    // linear indices of the output sites in the h2 strip: rows 1..rows, slots 1..L1
+    const int s_max = rows * WS + L1;
+    return tc_div_up((s_max >> 1) - tc_cbase(WS) + 1, 128);
+}
+
+template <int P>
+struct TcShape {
+    static constexpr int NP = (P + 15) / 16 * 16;   // output channels padded to the MMA N granularity
+    static constexpr int N3 = 2 * NP;               // [hi block | lo block]
+};
+
+// Fills the geometry for a given R; returns false when it does not fit one CTA's budget.
+template <int P>
+inline bool tc_plan(TcGeom& g, int R, uint32_t smem_budget) {
+    const int WS = g.WS;
+    g.R = R;
+    const int t2 = tc_tiles2(R, WS), t3 = tc_tiles3(R, WS, g.L1);
+    if (t2 > 16 || t2 * 16 > kTcTmemCols || t3 > 8 || t3 * TcShape<P>::N3 > kTcTmemCols) return false;
+    auto align = [](uint32_t v) { return (v + 127u) & ~127u; };
+    uint32_t off = 0;
+    g.off_xs = off; off = align(off + (uint32_t)(R + 6) * WS * 4);
+    const int n1 = t2 * 128 + 2 * WS + 2;                                   // records an M2 tile may touch
+    g.h1_comp_bytes = align((uint32_t)(kTcGuard + n1) * 16);
+    g.off_h1 = off; off += 2 * g.h1_comp_bytes;
+    int n2 = tc_cbase(WS) + t3 * 128 + (WS + 1) / 2 + 2;                    // per parity plane
+    const int n2_min = ((R + 2) * WS + 1) / 2 + 1;
+    if (n2 < n2_min) n2 = n2_min;
+    g.h2_comp_bytes = align((uint32_t)(kTcGuard + n2) * 16);
+    g.h2_par_bytes = 2 * g.h2_comp_bytes;
+    g.off_h2 = off; off += 2 * g.h2_par_bytes;
+    g.off_b2 = off; off = align(off + 9 * 2 * 16 * 16);
+    g.off_b3 = off; off = align(off + 9 * 2 * TcShape<P>::N3 * 16);
+    g.off_w1 = off; off = align(off + (72 + 8 + 8 + TcShape<P>::NP) * 4);
+    g.off_bar = off; off = align(off + 24 * 8 + 64);
+    g.smem_bytes = off + 1024;                                              // room to align the base
+    return g.smem_bytes <= smem_budget;
+}
+
+// MMA + epilogue cost model of a strip height (cycles per lattice row, measured MMA costs):
+// used on the host to pick R
+template <int P>
+inline float tc_cost_per_row(int L0, int L1, int WS, int R) {
+    const float c2 = 9 * 41.f, c3 = 9 * (TcShape<P>::N3 <= 32 ? 42.f : TcShape<P>::N3 <= 64 ? 50.f : 66.f);
+    float total = 0.f;
+    for (int r0 = 0; r0 < L0; r0 += R) {
+        const int rows = L0 - r0 < R ? L0 - r0 : R;
+        total += tc_tiles2(rows, WS) * c2 + tc_tiles3(rows, WS, L1) * c3 + 600.f;   // + per-strip sync overhead
+    }
+    return total / L0;
+}
+
+// fp16 pair of a float: hi = rn11(v) (round to 11 significant bits in fp32, exact in fp16 for
+// normal fp16 magnitudes), lo = v - hi.  Returns hi; lo via reference.
+__device__ __forceinline__ float tc_split(float v, float& lo) {
+    const float hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+    lo = v - hi;
+    return hi;
+}
+__device__ __forceinline__ uint32_t tc_pack(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+}  // namespace nfk

@@ -1,0 +1,110 @@
+// nfk_tc.cuh -- thin inline-PTX wrappers for the sm_100a tensor-core path (tcgen05 / TMEM /
+// mbarrier), used by nfk_fused_tc.cu.  Device-only.
+//
+// Shared-memory operand convention used throughout (checked on a B200 with scratch/tc_probe.cu):
+//   K-major, SWIZZLE_NONE canonical layout: a "row" (one M or N index) of one K-group is 16
+//   contiguous bytes (8 fp16); 8 consecutive rows form a 128-byte core matrix; the next 8 rows
+//   follow at SBO = 128 bytes; the second K-group of the same rows lives LBO bytes further.
+//   The descriptor start address only has to be 16-byte aligned, so "row m of the tile" may be
+//   ANY run of consecutive 16-byte records: a convolution tap is a shifted start address.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nfk {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// 64-bit shared-memory matrix descriptor (Blackwell version 1, no swizzle, base offset 0)
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// descriptor of the same matrix starting `rows16` 16-byte records further (may be negative)
+__device__ __forceinline__ uint64_t desc_advance(uint64_t d, int rows16) {
+    return (d & ~(uint64_t)0x3FFF) | (uint64_t)(((uint32_t)(d & 0x3FFF) + (uint32_t)rows16) & 0x3FFF);
+}
+
+// instruction descriptor: D = f32, A/B format `fmt` (0 = f16, 1 = bf16, 2 = tf32), both K-major, dense
+__host__ __device__ inline uint32_t make_idesc(int fmt, int M, int N) {
+    uint32_t d = 0;
+    d |= 1u << 4;
+    d |= (uint32_t)fmt << 7;
+    d |= (uint32_t)fmt << 10;
+    d |= (uint32_t)(N >> 3) << 17;
+    d |= (uint32_t)(M >> 4) << 24;
+    return d;
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16 inputs (K = 16 per instruction), one CTA
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                 :: "r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier when every MMA issued so far by this thread has completed
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// try_wait suspends the thread for a hardware-defined slice (about a millisecond, measured)
+// before it reports failure; a wait that legitimately takes thousands of slices does not
+// exist in this library, so a lost arrival traps (CUDA error at the next sync) instead of
+// hanging the device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (int spin = 0; !ok; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (spin > 4000) __trap();
+    }
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(slot_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t tmem, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(cols) : "memory");
+}
+
+// 32 lanes x 16 columns: thread i of the warp receives lane (32 * (warp % 4) + i), 16 consecutive columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&r)[16]) {
+    uint32_t u[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+                   "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = __uint_as_float(u[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// generic-proxy shared-memory writes -> visible to the tensor core (async proxy)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
+
+// named barriers (id 0 is __syncthreads)
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+
+}  // namespace tc
+}  // namespace nfk

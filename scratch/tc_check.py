@@ -1,0 +1,67 @@
+"""GPU check of the tensor-core fused step against the CUDA-core fused step and the unfused kernels."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from normflow__b200 import _C, _ops
+
+torch.manual_seed(0)
+dev = 'cuda'
+
+def run(shape, K, B, kind, inverse=False, bias=False, mask_parity=0):
+    L0, L1 = shape
+    P = 2 if kind == 0 else 3 * K - 2
+    w = [torch.randn(8, 1, 3, 3, device=dev) / 3, torch.randn(8, 8, 3, 3, device=dev) / (72 ** 0.5),
+         torch.randn(P, 8, 3, 3, device=dev) / (72 ** 0.5)]
+    b = [torch.randn(8, device=dev) * 0.1, torch.randn(8, device=dev) * 0.1, torch.randn(P, device=dev) * 0.1] if bias else [None] * 3
+    x = torch.randn(B, L0, L1, device=dev) * 1.5
+    prm = _C.RqsParams(K, -5.0, 5.0, -5.0, 5.0, 1, 1) if kind == 1 else None
+    out = {}
+    for parity in (0, 1):
+        res = {}
+        for tc in ('0', '1'):
+            os.environ['NFK_FUSED_TC'] = tc
+            with torch.no_grad():
+                y, lj = _ops.fused2d_step(x, w, b, kind, prm, mask_parity, parity, 0, inverse)
+            torch.cuda.synchronize()
+            res[tc] = (y.double().cpu().numpy(), lj.double().cpu().numpy())
+        dy = np.abs(res['0'][0] - res['1'][0]) / np.maximum(np.abs(res['0'][0]), 1)
+        dl = np.abs(res['0'][1] - res['1'][1]) / np.maximum(np.abs(res['0'][1]), 1)
+        print(f"shape={shape} K={K} kind={kind} inv={inverse} bias={bias} mp={mask_parity} parity={parity}: "
+              f"max rel dy {dy.max():.3e} (at {np.unravel_index(dy.argmax(), dy.shape)})  max rel dlogJ {dl.max():.3e}  "
+              f"frac bad(>1e-5) {np.mean(dy > 1e-5):.4f}", flush=True)
+        if dy.max() > 1e-4:
+            bad = np.argwhere(dy > 1e-4)
+            print("   first bad sites:", bad[:12].tolist(), " rows hist:", np.bincount(bad[:, 1], minlength=L0).tolist())
+
+def timeit(shape, K, B):
+    L0, L1 = shape
+    P = 3 * K - 2
+    w = [torch.randn(8, 1, 3, 3, device=dev) / 3, torch.randn(8, 8, 3, 3, device=dev) / (72 ** 0.5),
+         torch.randn(P, 8, 3, 3, device=dev) / (72 ** 0.5)]
+    x = torch.randn(B, L0, L1, device=dev)
+    prm = _C.RqsParams(K, -5.0, 5.0, -5.0, 5.0, 1, 1)
+    for tc in ('0', '1'):
+        os.environ['NFK_FUSED_TC'] = tc
+        with torch.no_grad():
+            for _ in range(2):
+                _ops.fused2d_step(x, w, [None] * 3, 1, prm, 0, 0)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(8):
+                _ops.fused2d_step(x, w, [None] * 3, 1, prm, 0, i % 2)
+            e1.record()
+            torch.cuda.synchronize()
+        print(f"time shape={shape} K={K} B={B} tc={tc}: {e0.elapsed_time(e1) / 8:.3f} ms per step", flush=True)
+
+if __name__ == '__main__':
+    run((16, 16), 10, 4, 1)
+    run((64, 64), 10, 3, 1)
+    run((64, 64), 10, 3, 1, inverse=True)
+    run((64, 64), 10, 700, 1, bias=True, mask_parity=1)
+    run((16, 16), 2, 5, 0)
+    run((12, 20), 4, 5, 1, bias=True)
+    run((64, 64), 8, 5, 1)
+    timeit((64, 64), 10, 16384)
+    print("tc_check done")
