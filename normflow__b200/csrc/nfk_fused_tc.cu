@@ -57,8 +57,7 @@ template <int KIND, int K, int INV>
 __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs a) {
     constexpr int P = KIND == 0 ? 2 : 3 * K - 2;
     constexpr int NP = TcShape<P>::NP, N3 = TcShape<P>::N3;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(128) uint8_t smem[];
     const TcGeom& g = a.g;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int WS = g.WS, L0 = g.L0, L1 = g.L1;
@@ -69,8 +68,8 @@ __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs 
     __half* B2 = reinterpret_cast<__half*>(smem + g.off_b2);  // [tap][kgroup][16][8]
     __half* B3 = reinterpret_cast<__half*>(smem + g.off_b3);  // [tap][kgroup][N3][8]
     float* w1s = reinterpret_cast<float*>(smem + g.off_w1);   // [tap][8] | b1[8] | b2[8] | b3[NP]
-    float* b1s = w1s + 72;
-    float* b2s = b1s + 8;
+    float* b1s = w1s + 72;                                    // layer-1 weights and b1, b2 are stored times
+    float* b2s = b1s + 8;                                     // 2 log2(e): the tanh argument comes out scaled
     float* b3s = b2s + 8;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.off_bar);   // m2[16] | m3[8]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
@@ -100,9 +99,9 @@ __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs 
     }
     for (int e = tid; e < 72 + 8 + 8 + NP; e += kTcThreads) {
         float v;
-        if (e < 72) v = NFK_LDG(a.w1 + (e & 7) * 9 + (e >> 3));          // w1s[tap][co]
-        else if (e < 80) v = a.b1 ? NFK_LDG(a.b1 + e - 72) : 0.f;
-        else if (e < 88) v = a.b2 ? NFK_LDG(a.b2 + e - 80) : 0.f;
+        if (e < 72) v = kTwoLog2e * NFK_LDG(a.w1 + (e & 7) * 9 + (e >> 3));          // w1s[tap][co]
+        else if (e < 80) v = a.b1 ? kTwoLog2e * NFK_LDG(a.b1 + e - 72) : 0.f;
+        else if (e < 88) v = a.b2 ? kTwoLog2e * NFK_LDG(a.b2 + e - 80) : 0.f;
         else v = (a.b3 && e - 88 < P) ? NFK_LDG(a.b3 + e - 88) : 0.f;
         w1s[e] = v;
     }
@@ -170,6 +169,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs 
         const int q = warp & 3, set = warp >> 2;
         uint32_t ph2 = 0, ph3 = 0;                                 // phase parity per barrier (my tiles)
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+        const bool has_b3 = a.b3 != nullptr;
         for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
             const float* xb = a.x + b * (long long)L0 * L1;
             float* yb = a.y + b * (long long)L0 * L1;
@@ -178,65 +178,85 @@ __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs 
                 const int rows = L0 - r0 < g.R ? L0 - r0 : g.R;
                 const int t2 = tc_tiles2(rows, WS), t3 = tc_tiles3(rows, WS, L1);
                 const int plin = (g.active_val - 1 + g.mask_parity - r0) & 1;
-                // ---- x strip (periodic wrap by index)
-                for (int e = tid; e < (rows + 6) * WS; e += kTcComputeThreads) {
-                    const int j = e / WS, slot = e - j * WS;
-                    float v = 0.f;
-                    if (slot <= L1 + 1) v = NFK_LDG(xb + wrap_idx(r0 - 3 + j, L0) * L1 + wrap_idx(slot - 1, L1));
-                    xs[e] = v;
+                // ---- x strip: one warp per row, periodic wrap by index
+                for (int j = warp; j < rows + 6; j += 8) {
+                    const float* src = xb + wrap_idx(r0 - 3 + j, L0) * L1;
+                    float* dst = xs + j * WS;
+                    for (int slot = lane; slot < WS; slot += 32) {
+                        int c = slot - 1;
+                        c = c < 0 ? c + L1 : c;
+                        c = c >= L1 ? c - L1 : c;
+                        dst[slot] = NFK_LDG(src + c);
+                    }
                 }
                 tc::bar_sync(kBarCompute, kTcComputeThreads);
-                // ---- P1: h1 rows j1 = 0 .. rows+3, two columns x 8 channels per item
+                // ---- P1: h1 = tanh(conv1(x on the frozen sites)).  An item is a vertical pair of
+                // sites (rows 2 jp, 2 jp + 1 of the h1 strip, column c): one of the two is an ACTIVE
+                // site -- its 4 cross neighbours carry x, centre and diagonals are masked to zero --
+                // and the other a FROZEN one (centre + 4 diagonals).  The nine inputs are selected by
+                // the pair's orientation, so only the 72 non-zero FMAs of the 144 are issued, and
+                // lanes walk consecutive columns (conflict-free shared-memory traffic).
                 {
-                    const int half = L1 >> 1, items = (rows + 4) * half;
+                    const int npair = (rows + 5) >> 1, items = npair * L1;
                     for (int it = tid; it < items; it += kTcComputeThreads) {
-                        const int j1 = it / half, c0 = (it - j1 * half) * 2;
-                        // window: x rows j1 .. j1+2 (strip rows), slots c0 .. c0+3; frozen sites only
-                        // mask bit of (row, col) = (1 - mask_parity + row + col) & 1; lattice row of x
-                        // strip row jx is r0 - 3 + jx, col = slot - 1
-                        const int bit0 = (1 - g.mask_parity + (r0 - 3 + j1) + (c0 - 1)) & 1;   // of win[0][0]
-                        const float m_even = (bit0 != g.active_val) ? 1.f : 0.f;            // keep win[dr][k], dr+k even
-                        const float m_odd = 1.f - m_even;
-                        float win[3][4];
+                        const int jp = tc_div(it, g.magic_l1), c = it - jp * L1;
+                        const float* xw = xs + (2 * jp) * WS + c;                 // window rows 0..3, slots c..c+2
+                        // mask bit of the upper site (lattice row r0 - 2 + 2 jp, column c)
+                        const bool up_active = ((1 - g.mask_parity + r0 + c) & 1) == g.active_val;
+                        const float x01 = xw[1], x10 = xw[WS], x11 = xw[WS + 1], x12 = xw[WS + 2];
+                        const float x00 = xw[0], x02 = xw[2];
+                        const float x20 = xw[2 * WS], x21 = xw[2 * WS + 1], x22 = xw[2 * WS + 2];
+                        const float x30 = xw[3 * WS], x31 = xw[3 * WS + 1], x32 = xw[3 * WS + 2];
+                        float in[9];                                              // by weight tap kh * 3 + kw
+                        in[1] = up_active ? x01 : x11;    // active site: N, W, E, S
+                        in[3] = up_active ? x10 : x20;
+                        in[5] = up_active ? x12 : x22;
+                        in[7] = up_active ? x21 : x31;
+                        in[4] = up_active ? x21 : x11;    // frozen site: centre, NW, NE, SW, SE
+                        in[0] = up_active ? x10 : x00;
+                        in[2] = up_active ? x12 : x02;
+                        in[6] = up_active ? x30 : x20;
+                        in[8] = up_active ? x32 : x22;
+                        float acc[2][8];                                          // [0] active site, [1] frozen site
+                        {
+                            float bv[8];
+                            load_w8(b1s, bv);
 #pragma unroll
-                        for (int dr = 0; dr < 3; ++dr)
+                            for (int co = 0; co < 8; ++co) acc[0][co] = acc[1][co] = bv[co];
+                        }
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                win[dr][k] = xs[(j1 + dr) * WS + c0 + k] * (((dr + k) & 1) ? m_odd : m_even);
-                        float acc[2][8];
+                        for (int t = 0; t < 9; ++t) {
+                            float wv[8];
+                            load_w8(w1s + t * 8, wv);
+                            const int which = (t & 1) ? 0 : 1;                    // odd taps: cross -> active site
 #pragma unroll
-                        for (int s = 0; s < 2; ++s)
-#pragma unroll
-                            for (int co = 0; co < 8; ++co) acc[s][co] = b1s[co];
-#pragma unroll
-                        for (int dr = 0; dr < 3; ++dr)
-#pragma unroll
-                            for (int dc = 0; dc < 3; ++dc) {
-                                float wv[8];
-                                load_w8(w1s + (dr * 3 + dc) * 8, wv);
-#pragma unroll
-                                for (int co = 0; co < 8; ++co) {
-                                    acc[0][co] = fmaf(win[dr][dc], wv[co], acc[0][co]);
-                                    acc[1][co] = fmaf(win[dr][dc + 1], wv[co], acc[1][co]);
-                                }
-                            }
+                            for (int co = 0; co < 8; ++co) acc[which][co] = fmaf(in[t], wv[co], acc[which][co]);
+                        }
+                        uint4 rec[2][2];                                          // [site][hi / lo]
 #pragma unroll
                         for (int s = 0; s < 2; ++s) {
                             float v[8];
 #pragma unroll
-                            for (int co = 0; co < 8; ++co) v[co] = tanh_fast(acc[s][co]);
+                            for (int co = 0; co < 8; ++co) v[co] = tanh_from_scaled(acc[s][co]);
+                            make_records(v, rec[s][0], rec[s][1]);
+                        }
+                        const int i1 = (2 * jp) * WS + c + 1;
+#pragma unroll
+                        for (int s = 0; s < 2; ++s) {                             // s = 0 upper row, 1 lower row
+                            if (s == 1 && 2 * jp + 1 >= rows + 4) break;
+                            const bool take_active = (s == 0) == up_active;
                             uint4 hi, lo;
-                            make_records(v, hi, lo);
-                            const int col = c0 + s, i1 = j1 * WS + col + 1;
-                            *reinterpret_cast<uint4*>(h1 + i1 * 16) = hi;
-                            *reinterpret_cast<uint4*>(h1 + g.h1_comp_bytes + i1 * 16) = lo;
-                            if (col == 0) {                       // column L1 is column 0
-                                *reinterpret_cast<uint4*>(h1 + (i1 + L1) * 16) = hi;
-                                *reinterpret_cast<uint4*>(h1 + g.h1_comp_bytes + (i1 + L1) * 16) = lo;
-                            }
-                            if (col == L1 - 1) {                  // column -1 is column L1-1
-                                *reinterpret_cast<uint4*>(h1 + (i1 - L1) * 16) = hi;
-                                *reinterpret_cast<uint4*>(h1 + g.h1_comp_bytes + (i1 - L1) * 16) = lo;
+                            hi.x = take_active ? rec[0][0].x : rec[1][0].x; hi.y = take_active ? rec[0][0].y : rec[1][0].y;
+                            hi.z = take_active ? rec[0][0].z : rec[1][0].z; hi.w = take_active ? rec[0][0].w : rec[1][0].w;
+                            lo.x = take_active ? rec[0][1].x : rec[1][1].x; lo.y = take_active ? rec[0][1].y : rec[1][1].y;
+                            lo.z = take_active ? rec[0][1].z : rec[1][1].z; lo.w = take_active ? rec[0][1].w : rec[1][1].w;
+                            uint8_t* dst = h1 + (i1 + s * WS) * 16;
+                            *reinterpret_cast<uint4*>(dst) = hi;
+                            *reinterpret_cast<uint4*>(dst + g.h1_comp_bytes) = lo;
+                            if (c == 0 || c == L1 - 1) {                          // periodic copies: slot L1+1 / slot 0
+                                uint8_t* dw = c == 0 ? dst + L1 * 16 : dst - L1 * 16;
+                                *reinterpret_cast<uint4*>(dw) = hi;
+                                *reinterpret_cast<uint4*>(dw + g.h1_comp_bytes) = lo;
                             }
                         }
                     }
@@ -245,30 +265,34 @@ __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs 
                 tc::fence_async_smem();
                 tc::bar_arrive(kBarH1, kTcThreads);
                 // ---- E2: accumulators of layer 2 -> h2 records
-                for (int j = set; j < t2; j += 2) {
-                    tc::mbar_wait(tc::smem_u32(bars + j), (ph2 >> j) & 1u);
-                    ph2 ^= 1u << j;
-                    tc::fence_after_sync();
-                    float acc[16];
-                    tc::tmem_ld16(lane_addr + j * 16, acc);
-                    tc::tmem_ld_wait();
-                    const int i2 = j * 128 + q * 32 + lane;
-                    const int j2 = i2 / WS, slot = i2 - j2 * WS;
-                    if (j2 < rows + 2 && slot >= 1 && slot <= L1) {
-                        float v[8];
+                {
+                    float bv[8];
+                    load_w8(b2s, bv);
+                    for (int j = set; j < t2; j += 2) {
+                        tc::mbar_wait(tc::smem_u32(bars + j), (ph2 >> j) & 1u);
+                        ph2 ^= 1u << j;
+                        tc::fence_after_sync();
+                        float acc[16];
+                        tc::tmem_ld16(lane_addr + j * 16, acc);
+                        tc::tmem_ld_wait();
+                        const int i2 = j * 128 + q * 32 + lane;
+                        const int j2 = tc_div(i2, g.magic_ws), slot = i2 - j2 * WS;
+                        if (j2 < rows + 2 && slot >= 1 && slot <= L1) {
+                            float v[8];
 #pragma unroll
-                        for (int c = 0; c < 8; ++c)
-                            v[c] = tanh_fast(fmaf(acc[8 + c], 1.f / kLoScale, acc[c]) + b2s[c]);
-                        uint4 hi, lo;
-                        make_records(v, hi, lo);
-                        uint8_t* dst = h2 + (i2 & 1) * g.h2_par_bytes + (i2 >> 1) * 16;
-                        *reinterpret_cast<uint4*>(dst) = hi;
-                        *reinterpret_cast<uint4*>(dst + g.h2_comp_bytes) = lo;
-                        if (slot == 1 || slot == L1) {            // periodic copies: slot L1+1 / slot 0
-                            const int iw = slot == 1 ? i2 + L1 : i2 - L1;
-                            uint8_t* dw = h2 + (iw & 1) * g.h2_par_bytes + (iw >> 1) * 16;
-                            *reinterpret_cast<uint4*>(dw) = hi;
-                            *reinterpret_cast<uint4*>(dw + g.h2_comp_bytes) = lo;
+                            for (int c = 0; c < 8; ++c)
+                                v[c] = tanh_from_scaled(fmaf(acc[8 + c], kTwoLog2e / kLoScale, fmaf(acc[c], kTwoLog2e, bv[c])));
+                            uint4 hi, lo;
+                            make_records(v, hi, lo);
+                            uint8_t* dst = h2 + (i2 & 1) * g.h2_par_bytes + (i2 >> 1) * 16;
+                            *reinterpret_cast<uint4*>(dst) = hi;
+                            *reinterpret_cast<uint4*>(dst + g.h2_comp_bytes) = lo;
+                            if (slot == 1 || slot == L1) {            // periodic copies: slot L1+1 / slot 0
+                                const int iw = slot == 1 ? i2 + L1 : i2 - L1;
+                                uint8_t* dw = h2 + (iw & 1) * g.h2_par_bytes + (iw >> 1) * 16;
+                                *reinterpret_cast<uint4*>(dw) = hi;
+                                *reinterpret_cast<uint4*>(dw + g.h2_comp_bytes) = lo;
+                            }
                         }
                     }
                 }
@@ -288,33 +312,35 @@ __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs 
                         tc::tmem_ld16(lane_addr + k * N3 + NP + ch * 16, lo);
                         tc::tmem_ld_wait();
 #pragma unroll
-                        for (int c = 0; c < 16; ++c)
-                            prm[ch * 16 + c] = fmaf(lo[c], 1.f / kLoScale, hi[c]) + b3s[ch * 16 + c];
+                        for (int c = 0; c < 16; ++c) prm[ch * 16 + c] = fmaf(lo[c], 1.f / kLoScale, hi[c]);
+                    }
+                    if (has_b3) {
+#pragma unroll
+                        for (int c = 0; c < P; ++c) prm[c] += b3s[c];
                     }
                     const int s = 2 * (cbase + k * 128 + q * 32 + lane) + plin;
-                    const int j2 = s / WS, slot = s - j2 * WS;
+                    const int j2 = tc_div(s, g.magic_ws), slot = s - j2 * WS;
                     if (j2 >= 1 && j2 <= rows && slot >= 1 && slot <= L1) {
                         float* px = xs + (j2 + 2) * WS + slot;
                         const float xv = *px;
                         float out, l;
                         if (KIND == 0) {
                             const float t = prm[0], sc = fabsf(prm[1]);
-                            if (!INV) { out = t + xv * expf(-sc); l = -sc; }
-                            else { out = (xv - t) * expf(sc); l = sc; }
+                            if (!INV) { out = fmaf(xv, fast_ex2(-sc * kInvLn2), t); l = -sc; }
+                            else { out = (xv - t) * fast_ex2(sc * kInvLn2); l = sc; }
                         } else {
-                            const RegLoad<NP> ld{prm};
-                            if (!INV) rqs_site_forward<K>(ld, a.cfg, xv, out, l);
-                            else rqs_site_inverse<K>(ld, a.cfg, xv, out, l);
+                            tc_rqs<K, INV, NP>(prm, a.cfg, xv, out, l);
                         }
                         *px = out;
                         lacc += l;
                     }
                 }
                 tc::bar_sync(kBarCompute, kTcComputeThreads);
-                // ---- the strip's rows (active: transformed, frozen: copied) -> y
-                for (int e = tid; e < rows * L1; e += kTcComputeThreads) {
-                    const int j = e / L1, col = e - j * L1;
-                    yb[(r0 + j) * L1 + col] = xs[(j + 3) * WS + col + 1];
+                // ---- the strip's rows (active: transformed, frozen: copied) -> y, one warp per row
+                for (int j = warp; j < rows; j += 8) {
+                    const float* src = xs + (j + 3) * WS + 1;
+                    float* dst = yb + (r0 + j) * L1;
+                    for (int col = lane; col < L1; col += 32) dst[col] = src[col];
                 }
                 tc::bar_sync(kBarCompute, kTcComputeThreads);
             }
@@ -360,6 +386,8 @@ int tc_launch(TcArgs a, cudaStream_t st) {
     }
     if (best == 0) return NFK_EUNSUPPORTED;
     tc_plan<P>(a.g, best, budget);
+    a.g.magic_ws = (uint32_t)((0x100000000ULL + a.g.WS - 1) / a.g.WS);
+    a.g.magic_l1 = (uint32_t)((0x100000000ULL + a.g.L1 - 1) / a.g.L1);
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(fused2d_tc_kernel<KIND, K, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize,

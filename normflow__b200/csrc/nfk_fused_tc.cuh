@@ -47,13 +47,16 @@ struct TcGeom {
     int L0, L1, WS;              // lattice rows, columns, WS = L1 + 3 (odd)
     int R;                       // output rows per strip
     int mask_parity, active_val;
-    // shared-memory map (byte offsets from the 1024-aligned base)
+    // shared-memory map (byte offsets from the dynamic shared-memory base; 16-byte alignment suffices)
     uint32_t off_xs, off_h1, off_h2, off_b2, off_b3, off_w1, off_bar;
     uint32_t h1_comp_bytes;      // hi plane -> lo plane of h1
     uint32_t h2_comp_bytes;      // hi plane -> lo plane of h2 (within a parity)
     uint32_t h2_par_bytes;       // parity 0 -> parity 1
     uint32_t smem_bytes;
+    uint32_t magic_ws, magic_l1; // ceil(2^32 / WS), ceil(2^32 / L1): exact n / d for n d < 2^32
 };
+
+__device__ __forceinline__ int tc_div(int n, uint32_t magic) { return (int)__umulhi((uint32_t)n, magic); }
 
 NFK_HD int tc_div_up(int a, int b) { return (a + b - 1) / b; }
 // tiles of layer 2 / layer 3 for a strip with `rows` output rows
@@ -80,7 +83,7 @@ inline bool tc_plan(TcGeom& g, int R, uint32_t smem_budget) {
     if (t2 > 16 || t2 * 16 > kTcTmemCols || t3 > 8 || t3 * TcShape<P>::N3 > kTcTmemCols) return false;
     auto align = [](uint32_t v) { return (v + 127u) & ~127u; };
     uint32_t off = 0;
-    g.off_xs = off; off = align(off + (uint32_t)(R + 6) * WS * 4);
+    g.off_xs = off; off = align(off + (uint32_t)(R + 7) * WS * 4);      // + 1 row: P1 pairs may peek past the end
     const int n1 = t2 * 128 + 2 * WS + 2;                                   // records an M2 tile may touch
     g.h1_comp_bytes = align((uint32_t)(kTcGuard + n1) * 16);
     g.off_h1 = off; off += 2 * g.h1_comp_bytes;
@@ -94,7 +97,7 @@ inline bool tc_plan(TcGeom& g, int R, uint32_t smem_budget) {
     g.off_b3 = off; off = align(off + 9 * 2 * TcShape<P>::N3 * 16);
     g.off_w1 = off; off = align(off + (72 + 8 + 8 + TcShape<P>::NP) * 4);
     g.off_bar = off; off = align(off + 24 * 8 + 64);
-    g.smem_bytes = off + 1024;                                              // room to align the base
+    g.smem_bytes = off;
     return g.smem_bytes <= smem_budget;
 }
 
@@ -111,16 +114,134 @@ inline float tc_cost_per_row(int L0, int L1, int WS, int R) {
     return total / L0;
 }
 
-// fp16 pair of a float: hi = rn11(v) (round to 11 significant bits in fp32, exact in fp16 for
-// normal fp16 magnitudes), lo = v - hi.  Returns hi; lo via reference.
+// fp16 pair of a float: hi = v truncated to 11 significant bits (exact in fp16 for normal fp16
+// magnitudes), lo = v - hi (13 bits, of which fp16 keeps 11: 22 bits in all).
 __device__ __forceinline__ float tc_split(float v, float& lo) {
-    const float hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
     lo = v - hi;
     return hi;
 }
 __device__ __forceinline__ uint32_t tc_pack(float a, float b) {
-    const __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<const uint32_t*>(&h);
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));      // low half = a
+    return r;
+}
+
+// ---- fast scalar maths (MUFU based, 1-2 ulp): what the epilogues run per site
+__device__ __forceinline__ float fast_ex2(float v) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float fast_lg2(float v) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float fast_rcp(float v) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+constexpr float kTwoLog2e = 2.88539008177792681f;      // 2 log2(e)
+// tanh(u) from a = 2 log2(e) u:  1 - 2 / (2^a + 1)   (abs error ~1e-7; saturates cleanly)
+__device__ __forceinline__ float tanh_from_scaled(float a) {
+    return fmaf(-2.f, fast_rcp(fast_ex2(a) + 1.f), 1.f);
+}
+// log2(1 + 2^z), the softplus with beta = ln 2 (couplings_.py:173-176; identity above z ln2 > 20)
+__device__ __forceinline__ float fast_softplus_ln2(float z) {
+    const float e = fast_ex2(z);
+    const float r = e < 2.44140625e-4f ? e * (kInvLn2 - 0.5f * kInvLn2 * e) : fast_lg2(1.f + e);   // log1p series below 2^-12
+    return z * kLn2 > 20.f ? z : r;
+}
+
+// Rational-quadratic coupling spline at one site from the raw conditioner channels p[0..3K-2)
+// held in registers (same maths as rqs_site_forward / rqs_site_inverse in nfk_math.cuh --
+// couplings_.py:211-262, spline.py:154-287 -- arranged for registers: the bin is found by
+// comparing UNNORMALISED prefix sums, and every run-time index becomes a select chain).
+template <int K, int INV, int NPR>
+__device__ __forceinline__ void tc_rqs(const float (&p)[NPR], const RqsCfg& cfg, float v, float& out, float& l) {
+    constexpr float kL2e = 1.44269504088896341f;
+    float mx = p[0], my = p[K - 1];
+#pragma unroll
+    for (int c = 1; c < K - 1; ++c) {
+        mx = fmaxf(mx, p[c]);
+        my = fmaxf(my, p[K - 1 + c]);
+    }
+    mx *= -kL2e;
+    my *= -kL2e;
+    float rx[K - 1], ry[K - 1];          // running sums of the unnormalised softmax terms
+    float sx = 0.f, sy = 0.f;
+#pragma unroll
+    for (int c = 0; c < K - 1; ++c) {
+        sx += fast_ex2(fmaf(p[c], kL2e, mx));
+        sy += fast_ex2(fmaf(p[K - 1 + c], kL2e, my));
+        rx[c] = sx;
+        ry[c] = sy;
+    }
+    const float lo = INV ? cfg.ylim0 : cfg.xlim0, wd = INV ? cfg.yw : cfg.xw;
+    if (cfg.left == kExtrapLinear && v <= lo) {                 // spline.py:466-470
+        const float D = fast_softplus_ln2(p[2 * K - 2]);
+        if (!INV) { out = cfg.ylim0 + D * (v - cfg.xlim0); l = kLn2 * fast_lg2(D); }
+        else { out = cfg.xlim0 + __fdividef(v - cfg.ylim0, D); l = -kLn2 * fast_lg2(D); }
+        return;
+    }
+    if (cfg.right == kExtrapLinear && v > lo + wd) {            // spline.py:476-478
+        const float D = fast_softplus_ln2(p[3 * K - 3]);
+        if (!INV) { out = (cfg.ylim0 + cfg.yw) + D * (v - (cfg.xlim0 + cfg.xw)); l = kLn2 * fast_lg2(D); }
+        else { out = (cfg.xlim0 + cfg.xw) + __fdividef(v - (cfg.ylim0 + cfg.yw), D); l = -kLn2 * fast_lg2(D); }
+        return;
+    }
+    // segment j = number of interior knots strictly below v (searchsorted right=False + clamp):
+    // knot c+1 = lo + r[c] wd / s  <  v   <=>   r[c] < (v - lo) s / wd
+    const float ss = INV ? sy : sx;
+    const float t = (v - lo) * ss * fast_rcp(wd);
+    float cx = 0.f, cy = 0.f, ux = sx, uy = sy;                 // prefix sums below / at the end of the segment
+    float d0 = p[2 * K - 2], d1 = p[2 * K - 1];
+#pragma unroll
+    for (int c = 0; c < K - 2; ++c) {
+        const bool below = (INV ? ry[c] : rx[c]) < t;
+        cx = below ? rx[c] : cx;
+        cy = below ? ry[c] : cy;
+        d0 = below ? p[2 * K - 1 + c] : d0;
+        d1 = below ? p[2 * K + c] : d1;
+    }
+#pragma unroll
+    for (int c = K - 3; c >= 0; --c) {
+        const bool below = (INV ? ry[c] : rx[c]) < t;
+        ux = below ? ux : rx[c];
+        uy = below ? uy : ry[c];
+    }
+    const float qx = cfg.xw * fast_rcp(sx), qy = cfg.yw * fast_rcp(sy);
+    const float X0 = fmaf(cx, qx, cfg.xlim0), w = (ux - cx) * qx;
+    const float Y0 = fmaf(cy, qy, cfg.ylim0), h = (uy - cy) * qy;
+    const float D0 = fast_softplus_ln2(d0), D1 = fast_softplus_ln2(d1);
+    const float rw = fast_rcp(w);
+    const float m = h * rw;
+    const float sig = D0 + D1 - 2.f * m;
+    float th;
+    if (!INV) {
+        th = (v - X0) * rw;
+    } else {                                                    // stable root, cf. rq_theta_from_eta
+        const float eta = __fdividef(v - Y0, h);
+        const float a2 = fmaf(-sig, eta, D0 - m);
+        const float a1 = -a2 - m;
+        const float a0 = m * eta;
+        const float disc = fmaxf(fmaf(a1, a1, -4.f * a0 * a2), 0.f);
+        th = __fdividef(2.f * a0, sqrtf(disc) - a1);
+    }
+    const float om = 1.f - th, tom = th * om;
+    const float den = fmaf(sig, tom, m);
+    const float rden = fast_rcp(den);
+    const float Q = fmaf(D1 * th, th, fmaf(2.f * m, tom, D0 * om * om));
+    const float lg = kLn2 * fast_lg2(m * m * Q * rden * rden);
+    if (!INV) {
+        out = fmaf(h * fmaf(m * th, th, D0 * tom), rden, Y0);
+        l = lg;
+    } else {
+        out = fmaf(w, th, X0);
+        l = -lg;
+    }
 }
 
 }  // namespace nfk

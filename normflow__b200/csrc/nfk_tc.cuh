@@ -64,10 +64,10 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok = 0;
     for (int spin = 0; !ok; ++spin) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
                      "selp.u32 %0, 1, 0, p;\n\t}\n"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (spin > 4000) __trap();
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");     // suspend-time hint (ns)
+        if (spin > 400000) __trap();
     }
 }
 
