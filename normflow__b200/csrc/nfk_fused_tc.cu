@@ -18,6 +18,8 @@
 //       -> y into the x strip       |barC|
 //   copy the strip's rows to y      |barC|
 
+#include <type_traits>
+
 #include "nfk_common.cuh"
 #include "nfk_fused_tc.cuh"
 
@@ -29,7 +31,13 @@ struct TcArgs {
     long long B;
     TcGeom g;
     RqsCfg cfg;
+    long long* trace;      // debug: per-phase clock64 stamps of CTA 0 (NULL in production)
 };
+
+// debug hook (not part of the C ABI): a device buffer of 2 x 4096 int64 that CTA 0 fills with
+// clock64() stamps, [0, 4096) compute warps, [4096, 8192) MMA warp
+static long long* g_trace = nullptr;
+extern "C" void nfk_debug_tc_trace(long long* device_buffer) { g_trace = device_buffer; }
 
 namespace {
 
@@ -117,6 +125,15 @@ __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs 
     const uint32_t tmem = *tmem_slot;
     const int cbase = tc_cbase(WS);
 
+    // The CTA's work is the flat sequence of (sample, strip) units; both roles walk it in step.
+    struct Unit { long long b; int r0; };
+    const int Rr = g.R;
+    auto next_unit = [&](Unit u) {
+        u.r0 += Rr;
+        if (u.r0 >= L0) { u.r0 = 0; u.b += gridDim.x; }
+        return u;
+    };
+
     if (warp == 8) {
         // =============================== MMA warp =========================================
         const bool lead = tc::elect_one();
@@ -126,43 +143,50 @@ __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs 
         const uint64_t a2_desc1 = tc::make_desc(tc::smem_u32(h2 + g.h2_par_bytes), g.h2_comp_bytes, 128);
         const uint64_t b2_desc = tc::make_desc(tc::smem_u32(B2), 16 * 16, 128);
         const uint64_t b3_desc = tc::make_desc(tc::smem_u32(B3), N3 * 16, 128);
-        for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
-            for (int r0 = 0; r0 < L0; r0 += g.R) {
-                const int rows = L0 - r0 < g.R ? L0 - r0 : g.R;
-                const int t2 = tc_tiles2(rows, WS), t3 = tc_tiles3(rows, WS, L1);
-                const int plin = (g.active_val - 1 + g.mask_parity - r0) & 1;
-                // ---- layer 2: out record i2 = 128 j + m reads h1 records i2 + WS + dr WS + dc
-                tc::bar_sync(kBarH1, kTcThreads);
-                tc::fence_after_sync();
-                if (lead) {
-                    for (int j = 0; j < t2; ++j) {
+        int tn = 0;
+        auto stamp = [&](int) {
+            if (a.trace && blockIdx.x == 0 && lead && tn < 4000) a.trace[4096 + tn++] = clock64();
+        };
+        for (Unit u{blockIdx.x, 0}; u.b < a.B; u = next_unit(u)) {
+            const int r0 = u.r0, rows = L0 - r0 < Rr ? L0 - r0 : Rr;
+            const int t2 = tc_tiles2(rows, WS), t3 = tc_tiles3(rows, WS, L1);
+            const int plin = (g.active_val - 1 + g.mask_parity - r0) & 1;
+            // ---- layer 2: out record i2 = 128 j + m reads h1 records i2 + WS + dr WS + dc
+            stamp(0);
+            tc::bar_sync(kBarH1, kTcThreads);
+            tc::fence_after_sync();
+            stamp(1);
+            if (lead) {
+                for (int j = 0; j < t2; ++j) {
 #pragma unroll
-                        for (int t = 0; t < 9; ++t) {
-                            const int delta = (t / 3 - 1) * WS + (t % 3 - 1);
-                            tc::mma_f16(tmem + j * 16, tc::desc_advance(a1_desc, j * 128 + WS + delta),
-                                        tc::desc_advance(b2_desc, t * 2 * 16), idesc2, t > 0);
-                        }
-                        tc::mma_commit(tc::smem_u32(bars + j));
+                    for (int t = 0; t < 9; ++t) {
+                        const int delta = (t / 3 - 1) * WS + (t % 3 - 1);
+                        tc::mma_f16(tmem + j * 16, tc::desc_advance(a1_desc, j * 128 + WS + delta),
+                                    tc::desc_advance(b2_desc, t * 2 * 16), idesc2, t > 0);
                     }
+                    tc::mma_commit(tc::smem_u32(bars + j));
                 }
-                __syncwarp();
-                // ---- layer 3: active record c (site s = 2c + plin) reads s + dr WS + dc
-                tc::bar_sync(kBarH2, kTcThreads);
-                tc::fence_after_sync();
-                if (lead) {
-                    for (int k = 0; k < t3; ++k) {
-#pragma unroll
-                        for (int t = 0; t < 9; ++t) {
-                            const int sh = plin + (t / 3 - 1) * WS + (t % 3 - 1);   // parity and offset of the source
-                            const uint64_t ad = (sh & 1) ? a2_desc1 : a2_desc0;
-                            tc::mma_f16(tmem + k * N3, tc::desc_advance(ad, cbase + k * 128 + (sh >> 1)),
-                                        tc::desc_advance(b3_desc, t * 2 * N3), idesc3, t > 0);
-                        }
-                        tc::mma_commit(tc::smem_u32(bars + 16 + k));
-                    }
-                }
-                __syncwarp();
             }
+            __syncwarp();
+            stamp(2);
+            // ---- layer 3: active record c (site s = 2c + plin) reads s + dr WS + dc
+            tc::bar_sync(kBarH2, kTcThreads);
+            tc::fence_after_sync();
+            stamp(3);
+            if (lead) {
+                for (int k = 0; k < t3; ++k) {
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) {
+                        const int sh = plin + (t / 3 - 1) * WS + (t % 3 - 1);   // parity and offset of the source
+                        const uint64_t ad = (sh & 1) ? a2_desc1 : a2_desc0;
+                        tc::mma_f16(tmem + k * N3, tc::desc_advance(ad, cbase + k * 128 + (sh >> 1)),
+                                    tc::desc_advance(b3_desc, t * 2 * N3), idesc3, t > 0);
+                    }
+                    tc::mma_commit(tc::smem_u32(bars + 16 + k));
+                }
+            }
+            __syncwarp();
+            stamp(4);
         }
     } else {
         // ============================= compute warps ======================================
@@ -170,191 +194,287 @@ __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs 
         uint32_t ph2 = 0, ph3 = 0;                                 // phase parity per barrier (my tiles)
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
         const bool has_b3 = a.b3 != nullptr;
-        for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
-            const float* xb = a.x + b * (long long)L0 * L1;
-            float* yb = a.y + b * (long long)L0 * L1;
-            float lacc = 0.f;
-            for (int r0 = 0; r0 < L0; r0 += g.R) {
-                const int rows = L0 - r0 < g.R ? L0 - r0 : g.R;
-                const int t2 = tc_tiles2(rows, WS), t3 = tc_tiles3(rows, WS, L1);
-                const int plin = (g.active_val - 1 + g.mask_parity - r0) & 1;
-                // ---- x strip: one warp per row, periodic wrap by index
-                for (int j = warp; j < rows + 6; j += 8) {
-                    const float* src = xb + wrap_idx(r0 - 3 + j, L0) * L1;
-                    float* dst = xs + j * WS;
-                    for (int slot = lane; slot < WS; slot += 32) {
-                        int c = slot - 1;
-                        c = c < 0 ? c + L1 : c;
-                        c = c >= L1 ? c - L1 : c;
-                        dst[slot] = NFK_LDG(src + c);
+        const int xs_stride = (Rr + 7) * WS;                       // floats per x-strip buffer
+
+        // x strip of unit u: global loads into registers (issued early, consumed after the layer-2
+        // epilogue has hidden their latency), then stored into the strip buffer.  Element e of the
+        // strip is (row e / WS, slot e % WS); periodic wrap by index.
+        constexpr int kXPerThread = 6;                             // (R + 6) WS <= 6 * 256 (checked on the host)
+        float xr[kXPerThread];
+        auto xload_issue = [&](const Unit& u) {
+            const int rows = L0 - u.r0 < Rr ? L0 - u.r0 : Rr;
+            const float* xb = a.x + u.b * (long long)L0 * L1;
+            const int n = (rows + 6) * WS;
+#pragma unroll
+            for (int k = 0; k < kXPerThread; ++k) {
+                const int e = tid + k * kTcComputeThreads;
+                xr[k] = 0.f;
+                if (e < n) {
+                    const int j = tc_div(e, g.magic_ws), slot = e - j * WS;
+                    int r = u.r0 - 3 + j;
+                    r = r < 0 ? r + L0 : r;
+                    r = r >= L0 ? r - L0 : r;
+                    int c = slot - 1;
+                    c = c < 0 ? c + L1 : c;
+                    c = c >= L1 ? c - L1 : c;
+                    xr[k] = NFK_LDG(xb + r * L1 + c);
+                }
+            }
+        };
+        auto xload_store = [&](const Unit& u, float* xbuf) {
+            const int rows = L0 - u.r0 < Rr ? L0 - u.r0 : Rr;
+            const int n = (rows + 6) * WS;
+#pragma unroll
+            for (int k = 0; k < kXPerThread; ++k) {
+                const int e = tid + k * kTcComputeThreads;
+                if (e < n) xbuf[e] = xr[k];
+            }
+        };
+
+        // ---- P1: h1 = tanh(conv1(x on the frozen sites)).  An item is a vertical pair of sites
+        // (rows 2 jp, 2 jp + 1 of the h1 strip, column c): one of the two is an ACTIVE site -- its
+        // 4 cross neighbours carry x, centre and diagonals are masked to zero -- and the other a
+        // FROZEN one (centre + 4 diagonals).  The nine inputs are selected by the pair's
+        // orientation, so only the 72 non-zero FMAs of the 144 are issued, and lanes walk
+        // consecutive columns (conflict-free shared-memory traffic).
+        // NI items (it0, it0 + 256, ...) per trip share every weight fetched from shared memory
+        auto layer1_items = [&](auto ni_tag, int it0, int r0, int rows, const float* xbuf) {
+            constexpr int NI = decltype(ni_tag)::value;
+            float in[NI][9];                                              // by weight tap kh * 3 + kw
+            bool up_active[NI];
+            int jp[NI], cc[NI];
+#pragma unroll
+            for (int z = 0; z < NI; ++z) {
+                const int it = it0 + z * kTcComputeThreads;
+                jp[z] = tc_div(it, g.magic_l1);
+                cc[z] = it - jp[z] * L1;
+                const float* xw = xbuf + (2 * jp[z]) * WS + cc[z];        // window rows 0..3, slots c..c+2
+                // mask bit of the upper site (lattice row r0 - 2 + 2 jp, column c)
+                const bool ua = ((1 - g.mask_parity + r0 + cc[z]) & 1) == g.active_val;
+                up_active[z] = ua;
+                const float x00 = xw[0], x01 = xw[1], x02 = xw[2];
+                const float x10 = xw[WS], x11 = xw[WS + 1], x12 = xw[WS + 2];
+                const float x20 = xw[2 * WS], x21 = xw[2 * WS + 1], x22 = xw[2 * WS + 2];
+                const float x30 = xw[3 * WS], x31 = xw[3 * WS + 1], x32 = xw[3 * WS + 2];
+                in[z][1] = ua ? x01 : x11;    // active site: N, W, E, S
+                in[z][3] = ua ? x10 : x20;
+                in[z][5] = ua ? x12 : x22;
+                in[z][7] = ua ? x21 : x31;
+                in[z][4] = ua ? x21 : x11;    // frozen site: centre, NW, NE, SW, SE
+                in[z][0] = ua ? x10 : x00;
+                in[z][2] = ua ? x12 : x02;
+                in[z][6] = ua ? x30 : x20;
+                in[z][8] = ua ? x32 : x22;
+            }
+            float acc[NI][2][8];                                          // [item][0 active site / 1 frozen site][co]
+            {
+                float bv[8];
+                load_w8(b1s, bv);
+#pragma unroll
+                for (int z = 0; z < NI; ++z)
+#pragma unroll
+                    for (int co = 0; co < 8; ++co) acc[z][0][co] = acc[z][1][co] = bv[co];
+            }
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                float wv[8];
+                load_w8(w1s + t * 8, wv);
+                const int which = (t & 1) ? 0 : 1;                        // odd taps: cross -> active site
+#pragma unroll
+                for (int co = 0; co < 8; ++co)
+#pragma unroll
+                    for (int z = 0; z < NI; ++z) acc[z][which][co] = fmaf(in[z][t], wv[co], acc[z][which][co]);
+            }
+#pragma unroll
+            for (int z = 0; z < NI; ++z) {
+                uint4 rec[2][2];                                          // [site][hi / lo]
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    float v[8];
+#pragma unroll
+                    for (int co = 0; co < 8; ++co) v[co] = tanh_from_scaled(acc[z][s][co]);
+                    make_records(v, rec[s][0], rec[s][1]);
+                }
+                const int c = cc[z], i1 = (2 * jp[z]) * WS + c + 1;
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {                             // s = 0 upper row, 1 lower row
+                    if (s == 1 && 2 * jp[z] + 1 >= rows + 4) break;
+                    const bool take_active = (s == 0) == up_active[z];
+                    uint4 hi, lo;
+                    hi.x = take_active ? rec[0][0].x : rec[1][0].x; hi.y = take_active ? rec[0][0].y : rec[1][0].y;
+                    hi.z = take_active ? rec[0][0].z : rec[1][0].z; hi.w = take_active ? rec[0][0].w : rec[1][0].w;
+                    lo.x = take_active ? rec[0][1].x : rec[1][1].x; lo.y = take_active ? rec[0][1].y : rec[1][1].y;
+                    lo.z = take_active ? rec[0][1].z : rec[1][1].z; lo.w = take_active ? rec[0][1].w : rec[1][1].w;
+                    uint8_t* dst = h1 + (i1 + s * WS) * 16;
+                    *reinterpret_cast<uint4*>(dst) = hi;
+                    *reinterpret_cast<uint4*>(dst + g.h1_comp_bytes) = lo;
+                    if (c == 0 || c == L1 - 1) {                          // periodic copies: slot L1+1 / slot 0
+                        uint8_t* dw = c == 0 ? dst + L1 * 16 : dst - L1 * 16;
+                        *reinterpret_cast<uint4*>(dw) = hi;
+                        *reinterpret_cast<uint4*>(dw + g.h1_comp_bytes) = lo;
                     }
                 }
-                tc::bar_sync(kBarCompute, kTcComputeThreads);
-                // ---- P1: h1 = tanh(conv1(x on the frozen sites)).  An item is a vertical pair of
-                // sites (rows 2 jp, 2 jp + 1 of the h1 strip, column c): one of the two is an ACTIVE
-                // site -- its 4 cross neighbours carry x, centre and diagonals are masked to zero --
-                // and the other a FROZEN one (centre + 4 diagonals).  The nine inputs are selected by
-                // the pair's orientation, so only the 72 non-zero FMAs of the 144 are issued, and
-                // lanes walk consecutive columns (conflict-free shared-memory traffic).
-                {
-                    const int npair = (rows + 5) >> 1, items = npair * L1;
-                    for (int it = tid; it < items; it += kTcComputeThreads) {
-                        const int jp = tc_div(it, g.magic_l1), c = it - jp * L1;
-                        const float* xw = xs + (2 * jp) * WS + c;                 // window rows 0..3, slots c..c+2
-                        // mask bit of the upper site (lattice row r0 - 2 + 2 jp, column c)
-                        const bool up_active = ((1 - g.mask_parity + r0 + c) & 1) == g.active_val;
-                        const float x01 = xw[1], x10 = xw[WS], x11 = xw[WS + 1], x12 = xw[WS + 2];
-                        const float x00 = xw[0], x02 = xw[2];
-                        const float x20 = xw[2 * WS], x21 = xw[2 * WS + 1], x22 = xw[2 * WS + 2];
-                        const float x30 = xw[3 * WS], x31 = xw[3 * WS + 1], x32 = xw[3 * WS + 2];
-                        float in[9];                                              // by weight tap kh * 3 + kw
-                        in[1] = up_active ? x01 : x11;    // active site: N, W, E, S
-                        in[3] = up_active ? x10 : x20;
-                        in[5] = up_active ? x12 : x22;
-                        in[7] = up_active ? x21 : x31;
-                        in[4] = up_active ? x21 : x11;    // frozen site: centre, NW, NE, SW, SE
-                        in[0] = up_active ? x10 : x00;
-                        in[2] = up_active ? x12 : x02;
-                        in[6] = up_active ? x30 : x20;
-                        in[8] = up_active ? x32 : x22;
-                        float acc[2][8];                                          // [0] active site, [1] frozen site
-                        {
-                            float bv[8];
-                            load_w8(b1s, bv);
+            }
+        };
+        auto layer1 = [&](const Unit& u, const float* xbuf) {
+            const int r0 = u.r0, rows = L0 - r0 < Rr ? L0 - r0 : Rr;
+            const int npair = (rows + 5) >> 1, items = npair * L1;
+            int it0 = tid;
+            for (; it0 + kTcComputeThreads < items; it0 += 2 * kTcComputeThreads)
+                layer1_items(std::integral_constant<int, 2>{}, it0, r0, rows, xbuf);
+            if (it0 < items) layer1_items(std::integral_constant<int, 1>{}, it0, r0, rows, xbuf);
+        };
+
+        // one warp of each tile set polls the MMA barrier; the other three block in hardware
+        auto tile_wait = [&](uint64_t* bar, uint32_t parity) {
+            if (q == 0) tc::mbar_wait(tc::smem_u32(bar), parity);
+            tc::bar_sync(kBarSet0 + set, 128);
+            tc::fence_after_sync();
+        };
+
+        // ---- E2: accumulators of layer 2 -> h2 records
+        auto epilogue2 = [&](const Unit& u) {
+            const int rows = L0 - u.r0 < Rr ? L0 - u.r0 : Rr;
+            const int t2 = tc_tiles2(rows, WS);
+            float bv[8];
+            load_w8(b2s, bv);
+            for (int j = set; j < t2; j += 2) {
+                tile_wait(bars + j, (ph2 >> j) & 1u);
+                ph2 ^= 1u << j;
+                float acc[16];
+                tc::tmem_ld16(lane_addr + j * 16, acc);
+                tc::tmem_ld_wait();
+                const int i2 = j * 128 + q * 32 + lane;
+                const int j2 = tc_div(i2, g.magic_ws), slot = i2 - j2 * WS;
+                if (j2 < rows + 2 && slot >= 1 && slot <= L1) {
+                    float v[8];
 #pragma unroll
-                            for (int co = 0; co < 8; ++co) acc[0][co] = acc[1][co] = bv[co];
-                        }
-#pragma unroll
-                        for (int t = 0; t < 9; ++t) {
-                            float wv[8];
-                            load_w8(w1s + t * 8, wv);
-                            const int which = (t & 1) ? 0 : 1;                    // odd taps: cross -> active site
-#pragma unroll
-                            for (int co = 0; co < 8; ++co) acc[which][co] = fmaf(in[t], wv[co], acc[which][co]);
-                        }
-                        uint4 rec[2][2];                                          // [site][hi / lo]
-#pragma unroll
-                        for (int s = 0; s < 2; ++s) {
-                            float v[8];
-#pragma unroll
-                            for (int co = 0; co < 8; ++co) v[co] = tanh_from_scaled(acc[s][co]);
-                            make_records(v, rec[s][0], rec[s][1]);
-                        }
-                        const int i1 = (2 * jp) * WS + c + 1;
-#pragma unroll
-                        for (int s = 0; s < 2; ++s) {                             // s = 0 upper row, 1 lower row
-                            if (s == 1 && 2 * jp + 1 >= rows + 4) break;
-                            const bool take_active = (s == 0) == up_active;
-                            uint4 hi, lo;
-                            hi.x = take_active ? rec[0][0].x : rec[1][0].x; hi.y = take_active ? rec[0][0].y : rec[1][0].y;
-                            hi.z = take_active ? rec[0][0].z : rec[1][0].z; hi.w = take_active ? rec[0][0].w : rec[1][0].w;
-                            lo.x = take_active ? rec[0][1].x : rec[1][1].x; lo.y = take_active ? rec[0][1].y : rec[1][1].y;
-                            lo.z = take_active ? rec[0][1].z : rec[1][1].z; lo.w = take_active ? rec[0][1].w : rec[1][1].w;
-                            uint8_t* dst = h1 + (i1 + s * WS) * 16;
-                            *reinterpret_cast<uint4*>(dst) = hi;
-                            *reinterpret_cast<uint4*>(dst + g.h1_comp_bytes) = lo;
-                            if (c == 0 || c == L1 - 1) {                          // periodic copies: slot L1+1 / slot 0
-                                uint8_t* dw = c == 0 ? dst + L1 * 16 : dst - L1 * 16;
-                                *reinterpret_cast<uint4*>(dw) = hi;
-                                *reinterpret_cast<uint4*>(dw + g.h1_comp_bytes) = lo;
-                            }
-                        }
+                    for (int c = 0; c < 8; ++c)
+                        v[c] = tanh_from_scaled(fmaf(acc[8 + c], kTwoLog2e / kLoScale, fmaf(acc[c], kTwoLog2e, bv[c])));
+                    uint4 hi, lo;
+                    make_records(v, hi, lo);
+                    uint8_t* dst = h2 + (i2 & 1) * g.h2_par_bytes + (i2 >> 1) * 16;
+                    *reinterpret_cast<uint4*>(dst) = hi;
+                    *reinterpret_cast<uint4*>(dst + g.h2_comp_bytes) = lo;
+                    if (slot == 1 || slot == L1) {            // periodic copies: slot L1+1 / slot 0
+                        const int iw = slot == 1 ? i2 + L1 : i2 - L1;
+                        uint8_t* dw = h2 + (iw & 1) * g.h2_par_bytes + (iw >> 1) * 16;
+                        *reinterpret_cast<uint4*>(dw) = hi;
+                        *reinterpret_cast<uint4*>(dw + g.h2_comp_bytes) = lo;
                     }
                 }
-                tc::fence_before_sync();
-                tc::fence_async_smem();
-                tc::bar_arrive(kBarH1, kTcThreads);
-                // ---- E2: accumulators of layer 2 -> h2 records
-                {
-                    float bv[8];
-                    load_w8(b2s, bv);
-                    for (int j = set; j < t2; j += 2) {
-                        tc::mbar_wait(tc::smem_u32(bars + j), (ph2 >> j) & 1u);
-                        ph2 ^= 1u << j;
-                        tc::fence_after_sync();
-                        float acc[16];
-                        tc::tmem_ld16(lane_addr + j * 16, acc);
-                        tc::tmem_ld_wait();
-                        const int i2 = j * 128 + q * 32 + lane;
-                        const int j2 = tc_div(i2, g.magic_ws), slot = i2 - j2 * WS;
-                        if (j2 < rows + 2 && slot >= 1 && slot <= L1) {
-                            float v[8];
+            }
+        };
+
+        // ---- E3: accumulators of layer 3 at the active sites -> transform, y into the x strip
+        auto epilogue3 = [&](const Unit& u, float* xbuf) -> float {
+            const int r0 = u.r0, rows = L0 - r0 < Rr ? L0 - r0 : Rr;
+            const int t3 = tc_tiles3(rows, WS, L1);
+            const int plin = (g.active_val - 1 + g.mask_parity - r0) & 1;
+            float lsum = 0.f;
+            for (int k = set; k < t3; k += 2) {
+                tile_wait(bars + 16 + k, (ph3 >> k) & 1u);
+                ph3 ^= 1u << k;
+                float prm[NP];
 #pragma unroll
-                            for (int c = 0; c < 8; ++c)
-                                v[c] = tanh_from_scaled(fmaf(acc[8 + c], kTwoLog2e / kLoScale, fmaf(acc[c], kTwoLog2e, bv[c])));
-                            uint4 hi, lo;
-                            make_records(v, hi, lo);
-                            uint8_t* dst = h2 + (i2 & 1) * g.h2_par_bytes + (i2 >> 1) * 16;
-                            *reinterpret_cast<uint4*>(dst) = hi;
-                            *reinterpret_cast<uint4*>(dst + g.h2_comp_bytes) = lo;
-                            if (slot == 1 || slot == L1) {            // periodic copies: slot L1+1 / slot 0
-                                const int iw = slot == 1 ? i2 + L1 : i2 - L1;
-                                uint8_t* dw = h2 + (iw & 1) * g.h2_par_bytes + (iw >> 1) * 16;
-                                *reinterpret_cast<uint4*>(dw) = hi;
-                                *reinterpret_cast<uint4*>(dw + g.h2_comp_bytes) = lo;
-                            }
-                        }
-                    }
+                for (int ch = 0; ch < NP / 16; ++ch) {
+                    float hi[16], lo[16];
+                    tc::tmem_ld16(lane_addr + k * N3 + ch * 16, hi);
+                    tc::tmem_ld16(lane_addr + k * N3 + NP + ch * 16, lo);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) prm[ch * 16 + c] = fmaf(lo[c], 1.f / kLoScale, hi[c]);
                 }
-                tc::fence_before_sync();
-                tc::fence_async_smem();
-                tc::bar_arrive(kBarH2, kTcThreads);
-                // ---- E3: accumulators of layer 3 at the active sites -> transform
-                for (int k = set; k < t3; k += 2) {
-                    tc::mbar_wait(tc::smem_u32(bars + 16 + k), (ph3 >> k) & 1u);
-                    ph3 ^= 1u << k;
-                    tc::fence_after_sync();
-                    float prm[NP];
+                if (has_b3) {
 #pragma unroll
-                    for (int ch = 0; ch < NP / 16; ++ch) {
-                        float hi[16], lo[16];
-                        tc::tmem_ld16(lane_addr + k * N3 + ch * 16, hi);
-                        tc::tmem_ld16(lane_addr + k * N3 + NP + ch * 16, lo);
-                        tc::tmem_ld_wait();
-#pragma unroll
-                        for (int c = 0; c < 16; ++c) prm[ch * 16 + c] = fmaf(lo[c], 1.f / kLoScale, hi[c]);
-                    }
-                    if (has_b3) {
-#pragma unroll
-                        for (int c = 0; c < P; ++c) prm[c] += b3s[c];
-                    }
-                    const int s = 2 * (cbase + k * 128 + q * 32 + lane) + plin;
-                    const int j2 = tc_div(s, g.magic_ws), slot = s - j2 * WS;
-                    if (j2 >= 1 && j2 <= rows && slot >= 1 && slot <= L1) {
-                        float* px = xs + (j2 + 2) * WS + slot;
-                        const float xv = *px;
-                        float out, l;
-                        if (KIND == 0) {
-                            const float t = prm[0], sc = fabsf(prm[1]);
-                            if (!INV) { out = fmaf(xv, fast_ex2(-sc * kInvLn2), t); l = -sc; }
-                            else { out = (xv - t) * fast_ex2(sc * kInvLn2); l = sc; }
-                        } else {
-                            tc_rqs<K, INV, NP>(prm, a.cfg, xv, out, l);
-                        }
-                        *px = out;
-                        lacc += l;
-                    }
+                    for (int c = 0; c < P; ++c) prm[c] += b3s[c];
                 }
-                tc::bar_sync(kBarCompute, kTcComputeThreads);
-                // ---- the strip's rows (active: transformed, frozen: copied) -> y, one warp per row
+                const int s = 2 * (cbase + k * 128 + q * 32 + lane) + plin;
+                const int j2 = tc_div(s, g.magic_ws), slot = s - j2 * WS;
+                if (j2 >= 1 && j2 <= rows && slot >= 1 && slot <= L1) {
+                    float* px = xbuf + (j2 + 2) * WS + slot;
+                    const float xv = *px;
+                    float out, l;
+                    if (KIND == 0) {
+                        const float t = prm[0], sc = fabsf(prm[1]);
+                        if (!INV) { out = fmaf(xv, fast_ex2(-sc * kInvLn2), t); l = -sc; }
+                        else { out = (xv - t) * fast_ex2(sc * kInvLn2); l = sc; }
+                    } else {
+                        tc_rqs<K, INV, NP>(prm, a.cfg, xv, out, l);
+                    }
+                    *px = out;
+                    lsum += l;
+                }
+            }
+            return lsum;
+        };
+
+        // Software pipeline over units: while the tensor core runs layer 3 of unit i, the compute
+        // warps already build h1 of unit i+1 (its x strip was prefetched during E2 of unit i).
+        Unit cur{blockIdx.x, 0};
+        int buf = 0;
+        float lacc = 0.f;
+        int tn = 0;
+        auto stamp = [&](int) {
+            if (a.trace && blockIdx.x == 0 && tid == 0 && tn < 4000) a.trace[tn++] = clock64();
+        };
+        if (cur.b < a.B) {
+            xload_issue(cur);
+            xload_store(cur, xs);
+            tc::bar_sync(kBarCompute, kTcComputeThreads);
+            layer1(cur, xs);
+            tc::fence_before_sync();
+            tc::fence_async_smem();
+            tc::bar_arrive(kBarH1, kTcThreads);
+        }
+        while (cur.b < a.B) {
+            const Unit nxt = next_unit(cur);
+            const bool has_next = nxt.b < a.B;
+            float* xcur = xs + buf * xs_stride;
+            float* xnext = xs + (buf ^ 1) * xs_stride;
+            stamp(0);
+            if (has_next) xload_issue(nxt);                           // in flight while E2 runs
+            epilogue2(cur);
+            stamp(1);
+            tc::fence_before_sync();
+            tc::fence_async_smem();
+            tc::bar_arrive(kBarH2, kTcThreads);                       // layer 3 of `cur` may start
+            if (has_next) xload_store(nxt, xnext);
+            tc::bar_sync(kBarCompute, kTcComputeThreads);             // x of `nxt` visible; every layer-2 tile of `cur` consumed
+            stamp(2);
+            if (has_next) layer1(nxt, xnext);                         // overlaps layer 3 of `cur` on the tensor core
+            stamp(3);
+            lacc += epilogue3(cur, xcur);
+            stamp(4);
+            tc::bar_sync(kBarCompute, kTcComputeThreads);             // y of the strip complete in xcur
+            {   // the strip's rows (active: transformed, frozen: copied) -> y, one warp per row
+                const int rows = L0 - cur.r0 < Rr ? L0 - cur.r0 : Rr;
+                float* yb = a.y + cur.b * (long long)L0 * L1;
                 for (int j = warp; j < rows; j += 8) {
-                    const float* src = xs + (j + 3) * WS + 1;
-                    float* dst = yb + (r0 + j) * L1;
+                    const float* src = xcur + (j + 3) * WS + 1;
+                    float* dst = yb + (cur.r0 + j) * L1;
                     for (int col = lane; col < L1; col += 32) dst[col] = src[col];
                 }
+            }
+            if (cur.r0 + Rr >= L0) {      // last strip of the sample: log|det J| (fixed reduction tree)
+                lacc = warp_sum(lacc);
+                if (lane == 0) red[warp] = lacc;
                 tc::bar_sync(kBarCompute, kTcComputeThreads);
-            }
-            // ---- log|det J| of the sample (deterministic: fixed reduction tree)
-            lacc = warp_sum(lacc);
-            if (lane == 0) red[warp] = lacc;
-            tc::bar_sync(kBarCompute, kTcComputeThreads);
-            if (tid == 0 && a.log_out) {
-                float tot = 0.f;
+                if (tid == 0 && a.log_out) {
+                    float tot = 0.f;
 #pragma unroll
-                for (int w = 0; w < 8; ++w) tot += red[w];
-                a.log_out[b] = (a.log_in ? a.log_in[b] : 0.f) + tot;
+                    for (int w = 0; w < 8; ++w) tot += red[w];
+                    a.log_out[cur.b] = (a.log_in ? a.log_in[cur.b] : 0.f) + tot;
+                }
+                lacc = 0.f;
             }
-            tc::bar_sync(kBarCompute, kTcComputeThreads);
+            tc::fence_before_sync();                                  // TMEM reads of `cur` are done
+            tc::fence_async_smem();                                   // h1 of `nxt` is written
+            if (has_next) tc::bar_arrive(kBarH1, kTcThreads);         // layer 2 of `nxt` may start
+            tc::bar_sync(kBarCompute, kTcComputeThreads);             // xcur (and `red`) free for reuse
+            stamp(5);
+            cur = nxt;
+            buf ^= 1;
         }
     }
     tc::fence_before_sync();
@@ -419,6 +539,7 @@ int fused2d_tc_step(const float* x, const float* w1, const float* b1, const floa
     TcArgs a;
     a.x = x; a.w1 = w1; a.b1 = b1; a.w2 = w2; a.b2 = b2; a.w3 = w3; a.b3 = b3;
     a.log_in = log_in; a.y = y; a.log_out = log_out; a.B = B;
+    a.trace = g_trace;
     a.g = TcGeom{};
     a.g.L0 = L0; a.g.L1 = L1; a.g.WS = L1 + 3;
     a.g.mask_parity = mask_parity; a.g.active_val = parity == 0 ? 1 : 0;

@@ -40,7 +40,7 @@ constexpr int kTcTmemCols = 256;            // per CTA: two CTAs share the SM's 
 constexpr int kTcGuard = 8;                 // 16-byte records of slack in front of every plane
 constexpr float kLoScale = 2048.f;          // weights' lo part is stored times 2^11
 
-enum { kBarCompute = 1, kBarH1 = 2, kBarH2 = 3 };
+enum { kBarCompute = 1, kBarH1 = 2, kBarH2 = 3, kBarSet0 = 4 };   // kBarSet0 + {0, 1}: the two tile sets
 
 // launch geometry (host-computed, passed by value)
 struct TcGeom {
@@ -81,9 +81,10 @@ inline bool tc_plan(TcGeom& g, int R, uint32_t smem_budget) {
     g.R = R;
     const int t2 = tc_tiles2(R, WS), t3 = tc_tiles3(R, WS, g.L1);
     if (t2 > 16 || t2 * 16 > kTcTmemCols || t3 > 8 || t3 * TcShape<P>::N3 > kTcTmemCols) return false;
+    if ((R + 6) * WS > 6 * kTcComputeThreads) return false;                 // x strip staged in 6 registers per thread
     auto align = [](uint32_t v) { return (v + 127u) & ~127u; };
     uint32_t off = 0;
-    g.off_xs = off; off = align(off + (uint32_t)(R + 7) * WS * 4);      // + 1 row: P1 pairs may peek past the end
+    g.off_xs = off; off = align(off + 2u * (uint32_t)(R + 7) * WS * 4); // two strips (+ 1 row: P1 pairs may peek past the end)
     const int n1 = t2 * 128 + 2 * WS + 2;                                   // records an M2 tile may touch
     g.h1_comp_bytes = align((uint32_t)(kTcGuard + n1) * 16);
     g.off_h1 = off; off += 2 * g.h1_comp_bytes;
@@ -91,7 +92,7 @@ inline bool tc_plan(TcGeom& g, int R, uint32_t smem_budget) {
     const int n2_min = ((R + 2) * WS + 1) / 2 + 1;
     if (n2 < n2_min) n2 = n2_min;
     g.h2_comp_bytes = align((uint32_t)(kTcGuard + n2) * 16);
-    g.h2_par_bytes = 2 * g.h2_comp_bytes;
+    g.h2_par_bytes = 2 * g.h2_comp_bytes + 64;          // odd multiple of 64: the two parities hit different banks
     g.off_h2 = off; off += 2 * g.h2_par_bytes;
     g.off_b2 = off; off = align(off + 9 * 2 * 16 * 16);
     g.off_b3 = off; off = align(off + 9 * 2 * TcShape<P>::N3 * 16);

@@ -347,7 +347,11 @@ def test_atomic_api_matches_full_field_path():
         xb, lb = Coupling_.backward(cpl, y_ref, l_ref)
     close(y_ref, g["blk0_y"])
     close(l_ref, g["blk0_logJ"])
-    assert torch.allclose(y_fast, y_ref, atol=1e-6) and torch.allclose(l_fast, l_ref, atol=1e-4)
+    # the fused sweep (tensor-core conditioner) and the generic dataflow are two independent
+    # fp32-class evaluations: each is held to the 1e-5 contract against the reference
+    close(y_fast, g["blk0_y"])
+    close(l_fast, g["blk0_logJ"])
+    close(y_fast, y_ref.double().cpu().numpy(), tol=2e-5)
     close(xb, g["x"], tol=5e-5)
     # first atomic step against the golden intermediate
     parts = list(cpl.mask.split(x))
