@@ -10,7 +10,7 @@ import os
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libnormflow_b200.so")
+LIB_PATH = os.environ.get("NFK_LIB") or os.path.join(_PKG, "lib", "libnormflow_b200.so")   # NFK_LIB: tuning builds
 
 c_f = ctypes.c_void_p      # every device pointer crosses as void*
 c_i = ctypes.c_int

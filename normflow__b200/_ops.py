@@ -452,7 +452,17 @@ def conv_stack(inp, weights, biases, acts, ksize, in_mask=None, in_keep=0):
     return _ConvStack.apply(inp, in_mask, int(in_keep), acts, int(ksize), len(weights), *weights, *biases)
 
 
-FUSED2D_KNOTS = (4, 5, 6, 8, 10, 12, 16)
+FUSED2D_KNOTS = (4, 5, 6, 8, 10, 12, 16)      # CUDA-core kernel (nfk_fused.cu); needs L1 % 4 == 0
+FUSED2D_TC_KNOTS = (4, 5, 6, 8, 10)          # tensor-core kernel (nfk_fused_tc.cu); needs even L0, L1
+
+
+def fused2d_supported(L0, L1, n_knots=None):
+    """Whether nfk_fused2d_step covers a (L0, L1) lattice with an affine (n_knots None) or
+    RQ-spline conditioner: mirrors the dispatch in nfk_fused.cu / nfk_fused_tc.cu."""
+    tc = (2 <= L1 <= 160 and L0 >= 2 and L0 % 2 == 0 and L1 % 2 == 0          # strip + planes fit one CTA's share
+          and (n_knots is None or n_knots in FUSED2D_TC_KNOTS))
+    cc = L0 >= 1 and 4 <= L1 <= 512 and L1 % 4 == 0 and (n_knots is None or n_knots in FUSED2D_KNOTS)
+    return bool(tc or cc)
 
 
 def fused2d_step(x, weights, biases, kind, prm, mask_parity, parity, log0=0, inverse=False):

@@ -93,8 +93,7 @@ extern "C" int nfk_fused2d_step(const float* x, const float* w1, const float* b1
                                 const float* log_in, float* y, float* log_out,
                                 int L0, int L1, int64_t B, void* stream) {
     if (!x || !w1 || !w2 || !w3 || !y || x == y) return NFK_EINVAL;
-    if (H != kFH || L0 < 1 || L1 < 4 || L1 % 4 != 0 || (kind != 0 && kind != 1)) return NFK_EUNSUPPORTED;
-    if (((uintptr_t)y % 16) != 0) return NFK_EINVAL;
+    if (H != kFH || L0 < 1 || L1 < 1 || (kind != 0 && kind != 1)) return NFK_EUNSUPPORTED;
     if (B <= 0) return NFK_OK;
     if (kind == 1) {
         if (prm.n_knots < 2 || !(prm.xlim1 > prm.xlim0) || !(prm.ylim1 > prm.ylim0)) return NFK_EINVAL;
@@ -106,6 +105,9 @@ extern "C" int nfk_fused2d_step(const float* x, const float* w1, const float* b1
                                        log_out, L0, L1, B, NFK_STREAM(stream));
         if (rc != NFK_EUNSUPPORTED) return rc;
     }
+    // CUDA-core kernel: rows are walked in groups of four columns with 128-bit accesses
+    if (L1 < 4 || L1 % 4 != 0) return NFK_EUNSUPPORTED;
+    if (((uintptr_t)y % 16) != 0) return NFK_EINVAL;
     FusedArgs a;
     a.x = x; a.w1 = w1; a.b1 = b1; a.w2 = w2; a.b2 = b2; a.w3 = w3; a.b3 = b3;
     a.log_in = log_in; a.y = y; a.log_out = log_out;

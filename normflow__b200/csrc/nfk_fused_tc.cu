@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs 
     float* b3s = b2s + 8;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.off_bar);   // m2[16] | m3[8]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
-    float* red = reinterpret_cast<float*>(tmem_slot + 2);             // 8 floats
+    float* red = reinterpret_cast<float*>(tmem_slot + 2);             // one float per compute warp (<= 12)
 
     // ---- one-time set-up: weights -> fp16 pair operands, barriers, TMEM -------------------
     for (int e = tid; e < 9 * 16 * 8; e += kTcThreads) {                 // layer 2: N = [8 hi | 8 lo]
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs 
         for (int i = 0; i < 24; ++i) tc::mbar_init(tc::smem_u32(bars + i), 1);
         tc::fence_mbar_init();
     }
-    if (warp == 8) tc::tmem_alloc(tc::smem_u32(tmem_slot), kTcTmemCols);
+    if (warp == kTcComputeWarps) tc::tmem_alloc(tc::smem_u32(tmem_slot), kTcTmemCols);
     tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs 
         return u;
     };
 
-    if (warp == 8) {
+    if (warp == kTcComputeWarps) {
         // =============================== MMA warp =========================================
         const bool lead = tc::elect_one();
         const uint32_t idesc2 = tc::make_idesc(0, 128, 16), idesc3 = tc::make_idesc(0, 128, N3);
@@ -212,8 +212,10 @@ __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs 
                 if (e < n) {
                     const int j = tc_div(e, g.magic_ws), slot = e - j * WS;
                     int r = u.r0 - 3 + j;
-                    r = r < 0 ? r + L0 : r;
-                    r = r >= L0 ? r - L0 : r;
+                    r += r < 0 ? L0 : 0;                                  // twice: a 2-row lattice wraps twice
+                    r += r < 0 ? L0 : 0;
+                    r -= r >= L0 ? L0 : 0;
+                    r -= r >= L0 ? L0 : 0;
                     int c = slot - 1;
                     c = c < 0 ? c + L1 : c;
                     c = c >= L1 ? c - L1 : c;
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs 
             const int t2 = tc_tiles2(rows, WS);
             float bv[8];
             load_w8(b2s, bv);
-            for (int j = set; j < t2; j += 2) {
+            for (int j = set; j < t2; j += kTcSets) {
                 tile_wait(bars + j, (ph2 >> j) & 1u);
                 ph2 ^= 1u << j;
                 float acc[16];
@@ -372,7 +374,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs 
             const int t3 = tc_tiles3(rows, WS, L1);
             const int plin = (g.active_val - 1 + g.mask_parity - r0) & 1;
             float lsum = 0.f;
-            for (int k = set; k < t3; k += 2) {
+            for (int k = set; k < t3; k += kTcSets) {
                 tile_wait(bars + 16 + k, (ph3 >> k) & 1u);
                 ph3 ^= 1u << k;
                 float prm[NP];
@@ -450,7 +452,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs 
             {   // the strip's rows (active: transformed, frozen: copied) -> y, one warp per row
                 const int rows = L0 - cur.r0 < Rr ? L0 - cur.r0 : Rr;
                 float* yb = a.y + cur.b * (long long)L0 * L1;
-                for (int j = warp; j < rows; j += 8) {
+                for (int j = warp; j < rows; j += kTcComputeWarps) {
                     const float* src = xcur + (j + 3) * WS + 1;
                     float* dst = yb + (cur.r0 + j) * L1;
                     for (int col = lane; col < L1; col += 32) dst[col] = src[col];
@@ -463,7 +465,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs 
                 if (tid == 0 && a.log_out) {
                     float tot = 0.f;
 #pragma unroll
-                    for (int w = 0; w < 8; ++w) tot += red[w];
+                    for (int w = 0; w < kTcComputeWarps; ++w) tot += red[w];
                     a.log_out[cur.b] = (a.log_in ? a.log_in[cur.b] : 0.f) + tot;
                 }
                 lacc = 0.f;
@@ -479,7 +481,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs 
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 8) tc::tmem_dealloc(tmem, kTcTmemCols);
+    if (warp == kTcComputeWarps) tc::tmem_dealloc(tmem, kTcTmemCols);
 }
 
 template <int KIND, int K, int INV>

@@ -34,8 +34,13 @@
 
 namespace nfk {
 
-constexpr int kTcComputeThreads = 256;      // warps 0..7
-constexpr int kTcThreads = 288;             // + the MMA warp (warp 8)
+#ifndef NFK_TC_COMPUTE_WARPS
+#define NFK_TC_COMPUTE_WARPS 8
+#endif
+constexpr int kTcComputeWarps = NFK_TC_COMPUTE_WARPS;          // multiple of 4 (one warp per TMEM lane quarter)
+constexpr int kTcSets = kTcComputeWarps / 4;                   // tile sets working in parallel
+constexpr int kTcComputeThreads = 32 * kTcComputeWarps;
+constexpr int kTcThreads = kTcComputeThreads + 32;             // + the MMA warp (the last one)
 constexpr int kTcTmemCols = 256;            // per CTA: two CTAs share the SM's 512 columns
 constexpr int kTcGuard = 8;                 // 16-byte records of slack in front of every plane
 constexpr float kLoScale = 2048.f;          // weights' lo part is stored times 2^11
@@ -183,39 +188,38 @@ __device__ __forceinline__ void tc_rqs(const float (&p)[NPR], const RqsCfg& cfg,
     const float lo = INV ? cfg.ylim0 : cfg.xlim0, wd = INV ? cfg.yw : cfg.xw;
     if (cfg.left == kExtrapLinear && v <= lo) {                 // spline.py:466-470
         const float D = fast_softplus_ln2(p[2 * K - 2]);
-        if (!INV) { out = cfg.ylim0 + D * (v - cfg.xlim0); l = kLn2 * fast_lg2(D); }
-        else { out = cfg.xlim0 + __fdividef(v - cfg.ylim0, D); l = -kLn2 * fast_lg2(D); }
+        if (!INV) { out = cfg.ylim0 + D * (v - cfg.xlim0); l = logf(D); }
+        else { out = cfg.xlim0 + __fdividef(v - cfg.ylim0, D); l = -logf(D); }
         return;
     }
     if (cfg.right == kExtrapLinear && v > lo + wd) {            // spline.py:476-478
         const float D = fast_softplus_ln2(p[3 * K - 3]);
-        if (!INV) { out = (cfg.ylim0 + cfg.yw) + D * (v - (cfg.xlim0 + cfg.xw)); l = kLn2 * fast_lg2(D); }
-        else { out = (cfg.xlim0 + cfg.xw) + __fdividef(v - (cfg.ylim0 + cfg.yw), D); l = -kLn2 * fast_lg2(D); }
+        if (!INV) { out = (cfg.ylim0 + cfg.yw) + D * (v - (cfg.xlim0 + cfg.xw)); l = logf(D); }
+        else { out = (cfg.xlim0 + cfg.xw) + __fdividef(v - (cfg.ylim0 + cfg.yw), D); l = -logf(D); }
         return;
     }
     // segment j = number of interior knots strictly below v (searchsorted right=False + clamp):
     // knot c+1 = lo + r[c] wd / s  <  v   <=>   r[c] < (v - lo) s / wd
     const float ss = INV ? sy : sx;
     const float t = (v - lo) * ss * fast_rcp(wd);
-    float cx = 0.f, cy = 0.f, ux = sx, uy = sy;                 // prefix sums below / at the end of the segment
+    float cx = 0.f, cy = 0.f;                                   // prefix sums below the segment
+    float pw = p[0], ph = p[K - 1];                             // raw width / height channel of the segment
     float d0 = p[2 * K - 2], d1 = p[2 * K - 1];
 #pragma unroll
     for (int c = 0; c < K - 2; ++c) {
         const bool below = (INV ? ry[c] : rx[c]) < t;
         cx = below ? rx[c] : cx;
         cy = below ? ry[c] : cy;
+        pw = below ? p[c + 1] : pw;
+        ph = below ? p[K + c] : ph;
         d0 = below ? p[2 * K - 1 + c] : d0;
         d1 = below ? p[2 * K + c] : d1;
     }
-#pragma unroll
-    for (int c = K - 3; c >= 0; --c) {
-        const bool below = (INV ? ry[c] : rx[c]) < t;
-        ux = below ? ux : rx[c];
-        uy = below ? uy : ry[c];
-    }
+    // the segment's own softmax terms, re-evaluated (a difference of prefix sums would lose
+    // the low bits of a narrow bin)
     const float qx = cfg.xw * fast_rcp(sx), qy = cfg.yw * fast_rcp(sy);
-    const float X0 = fmaf(cx, qx, cfg.xlim0), w = (ux - cx) * qx;
-    const float Y0 = fmaf(cy, qy, cfg.ylim0), h = (uy - cy) * qy;
+    const float X0 = fmaf(cx, qx, cfg.xlim0), w = fast_ex2(fmaf(pw, kL2e, mx)) * qx;
+    const float Y0 = fmaf(cy, qy, cfg.ylim0), h = fast_ex2(fmaf(ph, kL2e, my)) * qy;
     const float D0 = fast_softplus_ln2(d0), D1 = fast_softplus_ln2(d1);
     const float rw = fast_rcp(w);
     const float m = h * rw;
@@ -235,7 +239,9 @@ __device__ __forceinline__ void tc_rqs(const float (&p)[NPR], const RqsCfg& cfg,
     const float den = fmaf(sig, tom, m);
     const float rden = fast_rcp(den);
     const float Q = fmaf(D1 * th, th, fmaf(2.f * m, tom, D0 * om * om));
-    const float lg = kLn2 * fast_lg2(m * m * Q * rden * rden);
+    // logf, not lg2.approx: log g is close to 0 at most sites and the approximation's ABSOLUTE error
+    // was measured to double the error of the per-sample log|det J| sum
+    const float lg = logf(m * m * Q * rden * rden);
     if (!INV) {
         out = fmaf(h * fmaf(m * th, th, D0 * tom), rden, Y0);
         l = lg;

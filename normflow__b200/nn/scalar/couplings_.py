@@ -96,6 +96,9 @@ class Coupling_(Module_):
 
     _fused_kind = None          # 0 affine, 1 RQ spline; None: no fused kernel for this coupling
 
+    def _fused_knots(self, net):
+        return None             # number of spline knots the conditioner parametrises (None: affine)
+
     def _fused_params(self, n_channels):
         return None
 
@@ -108,7 +111,8 @@ class Coupling_(Module_):
             return False
         if not (isinstance(self.mask, EvenOddMask) and self.mask.mask_kwargs.get('exclude_mu') is None):
             return False
-        return x.dim() == 3 and x.shape[2] % 4 == 0 and x.is_cuda and self.channels_axis == 1
+        return (x.dim() == 3 and x.is_cuda and self.channels_axis == 1
+                and _ops.fused2d_supported(x.shape[1], x.shape[2], self._fused_knots(net)))
 
     def _transform(self, x, out, parity, log0, frozen_mode, inverse):
         raise NotImplementedError
@@ -190,11 +194,9 @@ class RQSplineCoupling_(Coupling_):
     def _fused_params(self, n_channels):
         return _ops.rqs_params((n_channels + 2) // 3, self.xlim, self.ylim, self.extrap)
 
-    def _fusable(self, net, x):
-        if not super()._fusable(net, x):
-            return False
+    def _fused_knots(self, net):
         n = net.conv_kwargs['out_channels']
-        return (n + 2) % 3 == 0 and (n + 2) // 3 in _ops.FUSED2D_KNOTS
+        return (n + 2) // 3 if (n + 2) % 3 == 0 else -1
 
     def _params(self, out):
         n = out.shape[self.channels_axis]

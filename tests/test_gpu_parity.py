@@ -670,3 +670,75 @@ def test_fused_step_with_bias_and_mask_parity():
         y_f, l_f = cpl(x)
     y_u, l_u = cpl(x.clone().requires_grad_(True))
     assert torch.allclose(y_f, y_u.detach(), atol=2e-5, rtol=2e-5) and torch.allclose(l_f, l_u.detach(), atol=2e-4)
+
+
+# ------------------------------------------------------------------ tensor-core fused step (tcgen05)
+def _oracle_single_step(x, w, b, kind, parity, K, inverse, mask_parity=0, lim=(-5, 5)):
+    """One atomic step of the given parity with the numpy oracle (ConvAct(1->8->8->P) conditioner)."""
+    shape = x.shape[1:]
+    mask = O.evenodd_mask(shape, parity=mask_parity)
+    layers = [(t.double().cpu().numpy(), None if bb is None else bb.double().cpu().numpy()) for t, bb in zip(w, b)]
+    kw = dict(xlim=lim, ylim=lim, extrap=dict(left='linear', right='linear')) if kind == 1 else {}
+    step = O.make_convact_step('rqs' if kind == 1 else 'affine', layers, ['tanh', 'tanh', None], mask, **kw)
+    ident = lambda xa, xf, p, l0, inv: (xa, l0)
+    steps = [step] if parity == 0 else [ident, step]
+    return O.coupling_forward(x.double().cpu().numpy(), np.zeros(x.shape[0]), mask, steps, inverse=inverse)
+
+
+@pytest.mark.parametrize("shape,K,kind,B,bias,mask_parity,inverse", [
+    ((64, 64), 10, 1, 5, False, 0, False),      # BASELINE geometry: 5 strips, the last one ragged
+    ((64, 64), 10, 1, 3, True, 1, True),        # inverse direction, biases, EvenOddMask(parity=1)
+    ((16, 16), 10, 1, 700, False, 0, False),    # more samples than resident CTAs: the persistent loop
+    ((16, 16), 2, 0, 9, True, 0, False),        # affine
+    ((16, 16), 2, 0, 9, False, 1, True),
+    ((8, 12), 4, 1, 4, True, 0, False),         # non-square
+    ((6, 10), 5, 1, 3, False, 0, True),
+    ((2, 2), 6, 1, 7, True, 0, False),          # smallest lattice: every neighbour is a wrap
+    ((64, 32), 8, 1, 2, False, 1, False),
+    ((128, 128), 10, 1, 2, False, 0, False),    # wider rows: shorter strips
+])
+def test_tensor_core_fused_step_against_oracle(shape, K, kind, B, bias, mask_parity, inverse, monkeypatch):
+    """nfk_fused2d_step with its conditioner on tcgen05 (fp16-pair operands) against the float64
+    oracle, both partitions; and the CUDA-core kernel of the same entry point on the same inputs."""
+    from normflow__b200 import _ops
+    g = torch.Generator('cpu').manual_seed(11)
+    P = 2 if kind == 0 else 3 * K - 2
+    rnd = lambda *s, scale=1.0: (torch.randn(*s, generator=g, device='cpu') * scale).to(DEV)
+    w = [rnd(8, 1, 3, 3, scale=0.3), rnd(8, 8, 3, 3, scale=0.5 / 72 ** 0.5), rnd(P, 8, 3, 3, scale=0.5 / 72 ** 0.5)]
+    b = [rnd(8, scale=0.1), rnd(8, scale=0.1), rnd(P, scale=0.1)] if bias else [None] * 3
+    x = rnd(B, *shape, scale=1.3)
+    if inverse:
+        x = x.clamp(-4.7, 4.7)        # the reference's inverse is ill-conditioned outside [ylim] (SURVEY 7.3)
+    prm = _C.RqsParams(K, -5.0, 5.0, -5.0, 5.0, 1, 1) if kind == 1 else None
+    cuda_core_too = shape[1] % 4 == 0           # the CUDA-core kernel of the same entry point
+    for parity in (0, 1):
+        yo, lo = _oracle_single_step(x, w, b, kind, parity, K, inverse, mask_parity)
+        res = {}
+        for tc in (('1', '0') if cuda_core_too else ('1',)):
+            monkeypatch.setenv('NFK_FUSED_TC', tc)
+            with torch.no_grad():
+                y, lj = _ops.fused2d_step(x, w, b, kind, prm, mask_parity, parity, 0, inverse)
+            close(y, yo)
+            close(lj, lo)
+            res[tc] = y
+        # frozen sites are copied bit for bit by both kernels
+        frozen = torch.from_numpy(O.evenodd_mask(shape, parity=mask_parity) != (1 if parity == 0 else 0)).to(DEV)
+        assert all(torch.equal(r[:, frozen], x[:, frozen]) for r in res.values())
+
+
+def test_tensor_core_path_is_the_one_that_runs(monkeypatch):
+    """At the BASELINE geometry the fused entry point must take the tcgen05 kernel: the two kernels
+    differ in the last bits, so identical output would mean the dispatch silently fell back."""
+    from normflow__b200 import _ops
+    g = torch.Generator('cpu').manual_seed(3)
+    rnd = lambda *s, scale=1.0: (torch.randn(*s, generator=g, device='cpu') * scale).to(DEV)
+    w = [rnd(8, 1, 3, 3, scale=0.3), rnd(8, 8, 3, 3, scale=0.06), rnd(28, 8, 3, 3, scale=0.06)]
+    x = rnd(4, 64, 64)
+    prm = _C.RqsParams(10, -5.0, 5.0, -5.0, 5.0, 1, 1)
+    out = {}
+    for tc in ('1', '0'):
+        monkeypatch.setenv('NFK_FUSED_TC', tc)
+        with torch.no_grad():
+            out[tc] = _ops.fused2d_step(x, w, [None] * 3, 1, prm, 0, 0)[0]
+    assert not torch.equal(out['1'], out['0'])
+    assert torch.allclose(out['1'], out['0'], atol=2e-5, rtol=2e-5)
