@@ -19,7 +19,8 @@ The JSON line carries, besides the base contract:
                  ((8 + 4 P) B per site and step = 120 B at P = 28) over its mean
                  launch duration measured with CUDA events inside the timed steps, against
                  the measured copy bandwidth of MEASURED_PEAKS.json
-  cpu_baseline : the numpy oracle port of the same path timed on a bounded sample
+  cpu_baseline : the reference's operator sequence on torch CPU (oracle/torch_port.py, float64, all host
+                 threads) timed on a bounded sample
   e2e          : the same metric through the public API with HOST buffers: the prior draw
                  comes from pinned host memory (H2D inside the timed region) and log q,
                  log p are read back (D2H)
@@ -27,6 +28,7 @@ The JSON line carries, besides the base contract:
 
 import argparse
 import json
+import math
 import os
 import sys
 import threading
@@ -55,67 +57,62 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=16384, help="samples per GPU and step")
-    ap.add_argument("--cpu-batch", type=int, default=16, help="samples per step of the CPU arm")
+    ap.add_argument("--cpu-batch", type=int, default=256, help="samples per step of the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
 
 # --------------------------------------------------------------------------- CPU arm
-def oracle_model(seed=0):
-    """The same workload for the numpy oracle (test infrastructure; here as the CPU
-    baseline only).  Weights: fan-in scaled normal, float64."""
-    from oracle import nf_oracle as O
-    rs = np.random.RandomState(seed)
-    mask = O.evenodd_mask(LATTICE)
+def cpu_threads():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def time_cpu_port(batch, steps, warmup):
+    """The reference's CPU path for this workload: oracle/torch_port.py issues the same ATen
+    operator sequence as the reference (float64, ATen threads = all host cores).  Test
+    infrastructure used here only as the reported CPU baseline."""
+    import torch
+    from oracle import torch_port as T
+    threads = cpu_threads()
+    torch.set_num_threads(threads)
+    gen = torch.Generator('cpu').manual_seed(0)
     sizes = [1] + HIDDEN + [3 * KNOTS - 2]
-    steps = []
-    for _ in range(N_STEPS_FLOW):
-        layers = [(rs.randn(sizes[i + 1], sizes[i], 3, 3) / np.sqrt(9 * sizes[i]), None) for i in range(3)]
-        steps.append(O.make_convact_step('rqs', layers, ['tanh', 'tanh', None], mask, xlim=(-5, 5), ylim=(-5, 5),
-                                         extrap=dict(left='linear', right='linear')))
-    flow = lambda x, log0: O.coupling_forward(x, log0, mask, steps)
-    return O, flow, rs
+    nets = [[(torch.randn(sizes[i + 1], sizes[i], 3, 3, generator=gen, dtype=torch.float64, device='cpu')
+              / math.sqrt(9 * sizes[i])) for i in range(3)] for _ in range(N_STEPS_FLOW)]
+    mask = T.evenodd_mask(LATTICE)
 
-
-def blas_threads():
-    try:
-        from threadpoolctl import threadpool_info
-        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
-    except Exception:
-        return os.cpu_count() or 1
-
-
-def time_oracle(batch, steps, warmup):
-    O, flow, rs = oracle_model()
     def one():
-        x = rs.randn(batch, *LATTICE)
-        return O.posterior_sample__(x, flow, ACTION)
+        x = torch.randn(batch, *LATTICE, generator=gen, dtype=torch.float64, device='cpu')
+        with torch.no_grad():
+            return T.posterior_sample__(x, nets, mask, (-5.0, 5.0), (-5.0, 5.0), ACTION)
     for _ in range(warmup):
         one()
     t0 = time.perf_counter()
     for _ in range(steps):
         one()
     dt = time.perf_counter() - t0
-    return batch * steps / dt, dt
+    return batch * steps / dt, dt, threads
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path.  The reference is pure Python on torch
-    and cannot travel to the GPU box, so this times the oracle port (numpy, float64) of the
-    same workload on the host cores; each step is a bounded sample of `--cpu-batch` samples."""
+    """--impl reference: the reference's own CPU implementation of the path.  The reference is
+    pure Python on torch and cannot travel to the GPU box, so this times its restatement on the
+    same ATen operators (oracle/torch_port.py, float64, all host threads); each step is a bounded
+    sample of `--cpu-batch` samples of the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    value, dt = time_oracle(args.cpu_batch, args.steps, args.warmup)
-    cores = blas_threads()
-    sample = f"{args.cpu_batch} samples/step x {args.steps} steps of the same workload (numpy float64 oracle port)"
+    value, dt, cores = time_cpu_port(args.cpu_batch, args.steps, max(args.warmup, 1))
+    sample = (f"{args.cpu_batch} samples/step x {args.steps} steps of the same workload "
+              "(torch ATen float64 port of the reference's operator sequence)")
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "impl": "reference",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_step": args.cpu_batch, "lattice": list(LATTICE)},
+        "config": {"workload": WORKLOAD, "batch_per_gpu": args.batch, "lattice": list(LATTICE),
+                   "cpu_sample_per_step": args.cpu_batch},
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -332,9 +329,10 @@ def run_b200(args):
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         cb = args.cpu_batch
-        v, dt = time_oracle(cb, steps=6, warmup=1)
-        cpu = {"value": v, "unit": "samples/s", "cores": blas_threads(), "kind": "port",
-               "sample": f"{cb} samples/step x 6 steps of the same workload, numpy float64 oracle port, {dt:.1f} s"}
+        v, dt, cores = time_cpu_port(cb, steps=4, warmup=1)
+        cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+               "sample": f"{cb} samples/step x 4 steps of the same workload, torch ATen float64 port of the "
+                         f"reference's operator sequence, {dt:.1f} s"}
 
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,

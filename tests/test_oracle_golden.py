@@ -315,3 +315,27 @@ def test_zero_dim_logz_known_answer():
     S = O.phi4_action(xs[:, None], kappa=0, m_sq=-1.2, lambd=0.5)
     logz = np.log(np.trapezoid(np.exp(-S), xs))
     assert abs(logz - 1.112773) < 1e-6
+
+
+def test_torch_cpu_port_matches_numpy_oracle():
+    """oracle/torch_port.py (the CPU baseline bench.py times) against the numpy oracle on the
+    bench workload's operator chain at a small size."""
+    import torch
+    from oracle import torch_port as T
+    rs = np.random.RandomState(3)
+    shape, B, K = (8, 12), 5, 10
+    sizes = [1, 8, 8, 3 * K - 2]
+    nets_np = [[rs.randn(sizes[i + 1], sizes[i], 3, 3) / np.sqrt(9 * sizes[i]) for i in range(3)] for _ in range(3)]
+    x = rs.randn(B, *shape) * 1.5
+    mask = O.evenodd_mask(shape)
+    steps = [O.make_convact_step('rqs', [(w, None) for w in ws], ['tanh', 'tanh', None], mask, xlim=(-5, 5),
+                                 ylim=(-5, 5), extrap=dict(left='linear', right='linear')) for ws in nets_np]
+    action = dict(kappa=0.67, m_sq=-2.68, lambd=0.5)
+    y_np, logq_np, logp_np = O.posterior_sample__(x, lambda v, l0: O.coupling_forward(v, l0, mask, steps), action)
+    nets_t = [[torch.tensor(w, dtype=torch.float64, device='cpu') for w in ws] for ws in nets_np]
+    y_t, logq_t, logp_t = T.posterior_sample__(torch.tensor(x, dtype=torch.float64, device='cpu'), nets_t,
+                                               T.evenodd_mask(shape), (-5.0, 5.0), (-5.0, 5.0), action)
+    assert np.array_equal(T.evenodd_mask(shape).numpy(), mask)
+    np.testing.assert_allclose(y_t.numpy(), y_np, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(logq_t.numpy(), logq_np, rtol=1e-12, atol=1e-11)
+    np.testing.assert_allclose(logp_t.numpy(), logp_np, rtol=1e-12, atol=1e-11)
