@@ -742,3 +742,22 @@ def test_tensor_core_path_is_the_one_that_runs(monkeypatch):
             out[tc] = _ops.fused2d_step(x, w, [None] * 3, 1, prm, 0, 0)[0]
     assert not torch.equal(out['1'], out['0'])
     assert torch.allclose(out['1'], out['0'], atol=2e-5, rtol=2e-5)
+
+
+# ------------------------------------------------------------------ two GPUs: NCCL data parallel training
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (run under gpurun --gpus 2)")
+def test_spawnprocesses_two_gpus_nccl(tmp_path):
+    """model.device_handler.spawnprocesses(fit, nranks=2): one process per GPU, NCCL all-reduce of the
+    flat gradient buffer.  Both ranks must end with bit-identical parameters (same start by broadcast,
+    same averaged gradient every step) that differ from the start, and a finite loss."""
+    import mp_helpers
+    model = _config_model((16, 16), [('affine', 2), ('rqs', 2)], seed=21)
+    start = torch.cat([p.detach().flatten().cpu() for p in model.net_.parameters()])
+    model.device_handler.to('cpu')          # pickled to the children, which place it on their own GPU
+    model.device_handler.spawnprocesses(mp_helpers.fit_and_dump, 2, 12411, [5, 6], str(tmp_path), 5, 512)
+    r0 = torch.load(tmp_path / "rank0.pt")
+    r1 = torch.load(tmp_path / "rank1.pt")
+    assert r0["cuda"] == 0 and r1["cuda"] == 1
+    assert torch.equal(r0["params"], r1["params"])
+    assert not torch.allclose(r0["params"], start)
+    assert len(r0["loss"]) == 5 and np.isfinite(r0["loss"]).all()
