@@ -193,11 +193,143 @@ __global__ void __launch_bounds__(256) conv_bwd_weight_kernel(ConvWArgs a) {
     }
 }
 
+// ---------------------------------------------------------------- weight gradient, 2-D 3x3
+// The ConvAct layers of the BASELINE configs: 2-D lattice, 3x3 taps, Ci <= 8.  A persistent CTA
+// (blockIdx.y = block of CO_B output channels) walks samples in strips of R rows held in shared
+// memory -- the input strip with its periodic halo, the strip of d loss / d pre-activation -- and
+// each of its nine warps owns ONE tap: lanes walk 32 consecutive columns, a lane keeps the
+// CO_B x CI block of the weight gradient of its tap in registers (56 FMAs per 15 shared loads,
+// all conflict-free), summed over every site the lane visits in the whole launch; one shuffle
+// reduction and one atomicAdd per (CTA, weight) at the very end.
+struct Wgrad2dArgs {
+    const float* in;
+    const uint8_t* in_mask;
+    int in_keep;
+    const float* gpre;
+    float* gw;
+    float* gbias;
+    int L0, L1, R, Ci, Co;
+    long long B;
+};
+
+template <int CI, int CO_B>
+__global__ void __launch_bounds__(288, 2) conv2d_wgrad_kernel(Wgrad2dArgs a) {
+    extern __shared__ float sm[];
+    const int L0 = a.L0, L1 = a.L1, R = a.R, LW = L1 + 2;
+    float* in_s = sm;                               // [CI][R + 2][LW]
+    float* g_s = sm + CI * (R + 2) * LW;            // [CO_B][R][L1]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int kh = warp / 3, kw = warp % 3;         // this warp's tap
+    const int co0 = blockIdx.y * CO_B;
+    const int V = L0 * L1;
+    float acc[CO_B][CI];
+    float accb[CO_B];
+#pragma unroll
+    for (int co = 0; co < CO_B; ++co) {
+        accb[co] = 0.f;
+#pragma unroll
+        for (int ci = 0; ci < CI; ++ci) acc[co][ci] = 0.f;
+    }
+    for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
+        const float* in_b = a.in + b * (long long)CI * V;
+        const float* g_b = a.gpre + (b * a.Co + co0) * (long long)V;
+        for (int r0 = 0; r0 < L0; r0 += R) {
+            const int rows = L0 - r0 < R ? L0 - r0 : R;
+            __syncthreads();                        // previous strip consumed
+            // staging: one warp per (channel, row) line, lanes over the columns
+            for (int p = warp; p < CI * (rows + 2); p += 9) {
+                const int ci = p / (rows + 2), j = p - ci * (rows + 2);
+                int r = r0 - 1 + j;
+                r = r < 0 ? r + L0 : (r >= L0 ? r - L0 : r);
+                const float* src = in_b + ci * V + r * L1;
+                const uint8_t* msk = a.in_mask ? a.in_mask + r * L1 : nullptr;
+                float* dst = in_s + (ci * (R + 2) + j) * LW;
+                for (int k = lane; k < LW; k += 32) {
+                    int c = k - 1;
+                    c = c < 0 ? c + L1 : (c >= L1 ? c - L1 : c);
+                    float v = __ldg(src + c);
+                    if (msk && __ldg(msk + c) != (uint8_t)a.in_keep) v = 0.f;
+                    dst[k] = v;
+                }
+            }
+            for (int p = warp; p < CO_B * rows; p += 9) {
+                const int co = p / rows, j = p - co * rows;
+                const float* src = g_b + (long long)co * V + (r0 + j) * L1;
+                float* dst = g_s + (co * R + j) * L1;
+                const bool live = co0 + co < a.Co;
+                for (int c = lane; c < L1; c += 32) dst[c] = live ? __ldg(src + c) : 0.f;
+            }
+            __syncthreads();
+            for (int j = 0; j < rows; ++j)
+                for (int c = lane; c < L1; c += 32) {
+                    float gv[CO_B], xv[CI];
+#pragma unroll
+                    for (int co = 0; co < CO_B; ++co) gv[co] = g_s[(co * R + j) * L1 + c];
+#pragma unroll
+                    for (int ci = 0; ci < CI; ++ci) xv[ci] = in_s[(ci * (R + 2) + j + kh) * LW + c + kw];
+#pragma unroll
+                    for (int co = 0; co < CO_B; ++co) {
+#pragma unroll
+                        for (int ci = 0; ci < CI; ++ci) acc[co][ci] = fmaf(gv[co], xv[ci], acc[co][ci]);
+                    }
+                    if (warp == 4) {                // the centre-tap warp also sums the bias gradient
+#pragma unroll
+                        for (int co = 0; co < CO_B; ++co) accb[co] += gv[co];
+                    }
+                }
+        }
+    }
+#pragma unroll
+    for (int co = 0; co < CO_B; ++co) {
+#pragma unroll
+        for (int ci = 0; ci < CI; ++ci) {
+            const float v = warp_sum(acc[co][ci]);
+            if (lane == 0 && co0 + co < a.Co)
+                atomicAdd(a.gw + ((long long)(co0 + co) * CI + ci) * 9 + kh * 3 + kw, v);
+        }
+        if (warp == 4 && a.gbias) {
+            const float v = warp_sum(accb[co]);
+            if (lane == 0 && co0 + co < a.Co) atomicAdd(a.gbias + co0 + co, v);
+        }
+    }
+}
+
+template <int CI, int CO_B>
+static int wgrad2d_launch(Wgrad2dArgs a, cudaStream_t st) {
+    const int LW = a.L1 + 2;
+    int R = a.L0 < 16 ? a.L0 : 16;
+    auto bytes = [&](int r) { return (size_t)(CI * (r + 2) * LW + CO_B * r * a.L1) * sizeof(float); };
+    while (R > 1 && bytes(R) > 72 * 1024) R /= 2;
+    if (bytes(R) > 200 * 1024) return NFK_EUNSUPPORTED;
+    a.R = R;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(conv2d_wgrad_kernel<CI, CO_B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    const int ncb = (a.Co + CO_B - 1) / CO_B;
+    long long gx = (148LL * 2 + ncb - 1) / ncb;            // two CTAs per SM in all
+    if (gx > a.B) gx = a.B;
+    if (gx < 1) gx = 1;
+    conv2d_wgrad_kernel<CI, CO_B><<<dim3((unsigned)gx, ncb), 288, bytes(R), st>>>(a);
+    return check_launch();
+}
+
 extern "C" int nfk_conv_circ_bwd_weight(const float* in, const uint8_t* in_mask, int in_keep,
                                         const float* gpre, float* gw, float* gbias,
                                         nfk_lattice lat, int ksize, int Ci, int Co, int64_t B, void* stream) {
     if (!in || !gpre || !gw || !lat_ok(lat) || ksize < 1 || ksize % 2 == 0 || Ci < 1 || Co < 1) return NFK_EINVAL;
     if (B <= 0) return NFK_OK;
+    if (lat.ndim == 2 && ksize == 3 && (Ci == 1 || Ci == 8) && lat.shape[0] >= 2 && lat.shape[1] >= 2) {
+        Wgrad2dArgs w;
+        w.in = in; w.in_mask = in_mask; w.in_keep = in_keep; w.gpre = gpre; w.gw = gw; w.gbias = gbias;
+        w.L0 = lat.shape[0]; w.L1 = lat.shape[1]; w.R = 0; w.Ci = Ci; w.Co = Co; w.B = B;
+        int rc;
+        if (Ci == 1) rc = wgrad2d_launch<1, 8>(w, NFK_STREAM(stream));
+        else if (Co <= 8) rc = wgrad2d_launch<8, 8>(w, NFK_STREAM(stream));
+        else rc = wgrad2d_launch<8, 7>(w, NFK_STREAM(stream));
+        if (rc != NFK_EUNSUPPORTED) return rc;
+    }
     ConvWArgs a;
     a.in = in; a.in_mask = in_mask; a.in_keep = in_keep; a.gpre = gpre; a.gw = gw; a.gbias = gbias;
     a.lat = to_lat(lat); a.ksize = ksize; a.Ci = Ci; a.Co = Co; a.V = (int)lat_volume(lat);
