@@ -18,6 +18,8 @@
 //       -> y into the x strip       |barC|
 //   copy the strip's rows to y      |barC|
 
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "nfk_common.cuh"
@@ -369,11 +371,24 @@ __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs 
         };
 
         // ---- E3: accumulators of layer 3 at the active sites -> transform, y into the x strip
-        auto epilogue3 = [&](const Unit& u, float* xbuf) -> float {
+        // `next_cols` = TMEM columns layer 2 of the NEXT unit will overwrite (0: there is none).  A
+        // thread releases that unit's layer 2 (arrive on H1) as soon as it has drained every
+        // accumulator tile of its own that lives in those columns: layer 2 of the next unit then
+        // runs on the tensor core while the rest of this epilogue is still at work.
+        auto epilogue3 = [&](const Unit& u, float* xbuf, int next_cols) -> float {
             const int r0 = u.r0, rows = L0 - r0 < Rr ? L0 - r0 : Rr;
             const int t3 = tc_tiles3(rows, WS, L1);
             const int plin = (g.active_val - 1 + g.mask_parity - r0) & 1;
             float lsum = 0.f;
+            bool released = next_cols == 0;
+            auto release_if_clear = [&](int k_next) {             // k_next: my next tile (or >= t3)
+                if (!released && (k_next >= t3 || k_next * N3 >= next_cols)) {
+                    tc::fence_before_sync();                      // my TMEM reads so far are done
+                    tc::bar_arrive(kBarH1, kTcThreads);
+                    released = true;
+                }
+            };
+            release_if_clear(set);
             for (int k = set; k < t3; k += kTcSets) {
                 tile_wait(bars + 16 + k, (ph3 >> k) & 1u);
                 ph3 ^= 1u << k;
@@ -407,6 +422,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs 
                     *px = out;
                     lsum += l;
                 }
+                release_if_clear(k + kTcSets);
             }
             return lsum;
         };
@@ -444,9 +460,15 @@ __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs 
             if (has_next) xload_store(nxt, xnext);
             tc::bar_sync(kBarCompute, kTcComputeThreads);             // x of `nxt` visible; every layer-2 tile of `cur` consumed
             stamp(2);
-            if (has_next) layer1(nxt, xnext);                         // overlaps layer 3 of `cur` on the tensor core
+            int next_cols = 0;
+            if (has_next) {
+                layer1(nxt, xnext);                                   // overlaps layer 3 of `cur` on the tensor core
+                tc::fence_async_smem();                               // h1 of `nxt` visible to the tensor core
+                const int nrows = L0 - nxt.r0 < Rr ? L0 - nxt.r0 : Rr;
+                next_cols = 16 * tc_tiles2(nrows, WS);
+            }
             stamp(3);
-            lacc += epilogue3(cur, xcur);
+            lacc += epilogue3(cur, xcur, next_cols);                  // releases layer 2 of `nxt` on the way
             stamp(4);
             tc::bar_sync(kBarCompute, kTcComputeThreads);             // y of the strip complete in xcur
             {   // the strip's rows (active: transformed, frozen: copied) -> y, one warp per row
@@ -470,9 +492,6 @@ __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs 
                 }
                 lacc = 0.f;
             }
-            tc::fence_before_sync();                                  // TMEM reads of `cur` are done
-            tc::fence_async_smem();                                   // h1 of `nxt` is written
-            if (has_next) tc::bar_arrive(kBarH1, kTcThreads);         // layer 2 of `nxt` may start
             tc::bar_sync(kBarCompute, kTcComputeThreads);             // xcur (and `red`) free for reuse
             stamp(5);
             cur = nxt;
@@ -505,6 +524,11 @@ int tc_launch(TcArgs a, cudaStream_t st) {
         if (!tc_plan<P>(g, R, budget)) continue;
         const float c = tc_cost_per_row<P>(g.L0, g.L1, g.WS, R);
         if (c < best_cost) { best_cost = c; best = R; }
+    }
+    if (const char* e = getenv("NFK_TC_R")) {             // tuning override of the strip height
+        const int r = atoi(e);
+        TcGeom t = a.g;
+        if (r >= 2 && r <= a.g.L0 && tc_plan<P>(t, r, budget)) best = r;
     }
     if (best == 0) return NFK_EUNSUPPORTED;
     tc_plan<P>(a.g, best, budget);
