@@ -60,7 +60,7 @@ extern "C" int nfk_prior_normal_sample(float* x, float* logr, int64_t B, int64_t
 extern "C" int nfk_prior_normal_logprob(const float* x, float* logr, int64_t B, int64_t V,
                                         const float* loc, const float* scale, void* stream) {
     if (!x || !logr) return NFK_EINVAL;
-    return launch_sites(PriorLogProbOp{x, loc, scale, V}, B, V, nullptr, logr, NFK_STREAM(stream));
+    return launch_sites_vec<PriorLogProbOp4, 4>(PriorLogProbOp4{x, loc, scale, V}, B, V, nullptr, logr, NFK_STREAM(stream));
 }
 
 // ============================================================== affine / shift
@@ -270,16 +270,74 @@ extern "C" int nfk_spline1d_bwd(const float* x, const float* knots, int K, int e
 }
 
 // ============================================================== phi^4 action
+// 2-D lattices with L1 % 4 == 0: one CTA per sample, a thread owns 4 consecutive columns of a row
+// (128-bit loads of its row and the row above, one scalar for the left neighbour; the re-reads are
+// L1/L2 hits), so the kernel moves 4 bytes per site from HBM and does no index division per site.
+template <bool BWD>
+__global__ void __launch_bounds__(256) phi4_2d_kernel(const float* phi, int L0, int L1, float w0, float w2, float w4,
+                                                      const float* gS, float* out) {
+    const int64_t b = blockIdx.x;
+    const float* p = phi + b * (int64_t)L0 * L1;
+    const int nq = L1 >> 2;                                   // column quads per row
+    const float gs = BWD ? __ldg(gS + b) : 0.f;
+    float acc = 0.f;
+    for (int it = threadIdx.x; it < L0 * nq; it += blockDim.x) {
+        const int r = it / nq, c0 = (it - r * nq) * 4;
+        const int ru = r == 0 ? L0 - 1 : r - 1;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p + r * L1 + c0));
+        const float4 u = __ldg(reinterpret_cast<const float4*>(p + ru * L1 + c0));
+        const float lf = __ldg(p + r * L1 + (c0 == 0 ? L1 - 1 : c0 - 1));
+        if (!BWD) {
+            // sum_x w2 v^2 + w4 v^4 - w0 v (v(x - e0) + v(x - e1))   (scalar_action.py:40-46)
+            const float q0 = v.x * v.x, q1 = v.y * v.y, q2 = v.z * v.z, q3 = v.w * v.w;
+            acc += q0 * (w2 + w4 * q0) + q1 * (w2 + w4 * q1) + q2 * (w2 + w4 * q2) + q3 * (w2 + w4 * q3);
+            acc -= w0 * (v.x * (u.x + lf) + v.y * (u.y + v.x) + v.z * (u.z + v.y) + v.w * (u.w + v.z));
+        } else {
+            const int rd = r == L0 - 1 ? 0 : r + 1;
+            const float4 d = __ldg(reinterpret_cast<const float4*>(p + rd * L1 + c0));
+            const float rt = __ldg(p + r * L1 + (c0 + 4 == L1 ? 0 : c0 + 4));
+            float4 g;
+            g.x = gs * (v.x * (2.f * w2 + 4.f * w4 * v.x * v.x) - w0 * (u.x + d.x + lf + v.y));
+            g.y = gs * (v.y * (2.f * w2 + 4.f * w4 * v.y * v.y) - w0 * (u.y + d.y + v.x + v.z));
+            g.z = gs * (v.z * (2.f * w2 + 4.f * w4 * v.z * v.z) - w0 * (u.z + d.z + v.y + v.w));
+            g.w = gs * (v.w * (2.f * w2 + 4.f * w4 * v.w * v.w) - w0 * (u.w + d.w + v.z + rt));
+            *reinterpret_cast<float4*>(out + b * (int64_t)L0 * L1 + r * L1 + c0) = g;
+        }
+    }
+    if (!BWD) {
+        acc = block_sum(acc);
+        if (threadIdx.x == 0) out[b] = acc;
+    }
+}
+static bool phi4_2d_ok(const nfk_lattice& lat, const float* phi, const float* out) {
+    return lat.ndim == 2 && lat.shape[1] % 4 == 0 && lat.shape[1] >= 4 && lat.shape[0] >= 2 &&
+           ((uintptr_t)phi % 16) == 0 && ((uintptr_t)out % 16) == 0;
+}
+
 extern "C" int nfk_phi4_action_fwd(const float* phi, nfk_lattice lat, float w0, float w2, float w4,
                                    float* S, int64_t B, void* stream) {
     if (!phi || !S || !lat_ok(lat)) return NFK_EINVAL;
     const int64_t V = lat_volume(lat);
+    if (B > 0 && phi4_2d_ok(lat, phi, phi)) {
+        const int items = lat.shape[0] * (lat.shape[1] / 4);
+        const int th = items >= 256 ? 256 : (items + 31) / 32 * 32;
+        phi4_2d_kernel<false><<<(unsigned)B, th, 0, NFK_STREAM(stream)>>>(phi, lat.shape[0], lat.shape[1], w0, w2, w4,
+                                                                           nullptr, S);
+        return check_launch();
+    }
     return launch_sites(Phi4Op{phi, to_lat(lat), w0, w2, w4, V}, B, V, nullptr, S, NFK_STREAM(stream));
 }
 extern "C" int nfk_phi4_action_bwd(const float* phi, nfk_lattice lat, float w0, float w2, float w4,
                                    const float* gS, float* gphi, int64_t B, void* stream) {
     if (!phi || !gS || !gphi || !lat_ok(lat)) return NFK_EINVAL;
     const int64_t V = lat_volume(lat);
+    if (B > 0 && phi4_2d_ok(lat, phi, gphi)) {
+        const int items = lat.shape[0] * (lat.shape[1] / 4);
+        const int th = items >= 256 ? 256 : (items + 31) / 32 * 32;
+        phi4_2d_kernel<true><<<(unsigned)B, th, 0, NFK_STREAM(stream)>>>(phi, lat.shape[0], lat.shape[1], w0, w2, w4,
+                                                                          gS, gphi);
+        return check_launch();
+    }
     return launch_sites(Phi4BwdOp{phi, to_lat(lat), w0, w2, w4, gS, gphi, V}, B, V, nullptr, nullptr,
                         NFK_STREAM(stream));
 }

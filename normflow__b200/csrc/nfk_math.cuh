@@ -649,12 +649,17 @@ NFK_HD Philox philox4x32_10(uint64_t counter_lo, uint64_t counter_hi, uint64_t k
 NFK_HD void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
     const float u1 = (float)a * 2.3283064365386963e-10f + 1.1641532182693481e-10f;  // (a + 0.5) 2^-32
     const float u2 = (float)b * 2.3283064365386963e-10f + 1.1641532182693481e-10f;
-    const float r = sqrtf(-2.f * logf(u1));
-    const float ang = 6.283185307179586f * u2;
 #if defined(__CUDA_ARCH__)
+    // MUFU-based log / sin / cos: the draw is a sampler, not a parity path (the density that
+    // goes with it is computed from the very z it returns), and the generator is HBM-bound only
+    // with the fast forms.  The angle is kept in (-pi, pi] where __sincosf is accurate to 2^-21.
+    const float r = sqrtf(-2.f * __logf(u1));
+    const float ang = 6.283185307179586f * (u2 - 0.5f);
     float sn, cs;
-    sincosf(ang, &sn, &cs);
+    __sincosf(ang, &sn, &cs);
 #else
+    const float r = sqrtf(-2.f * logf(u1));
+    const float ang = 6.283185307179586f * (u2 - 0.5f);
     const float sn = sinf(ang), cs = cosf(ang);
 #endif
     z0 = r * cs;

@@ -52,6 +52,26 @@ struct PriorLogProbOp {
     }
 };
 
+// four consecutive sites (s % 4 == 0) with one 128-bit load when there is no loc / scale
+struct PriorLogProbOp4 {
+    const float* x;
+    const float* loc;
+    const float* scale;
+    int64_t V;
+    NFK_HD float operator()(int64_t b, int64_t s, int n) const {
+#if defined(__CUDA_ARCH__)
+        if (n == 4 && !loc && !scale && (((b * V + s) & 3) == 0)) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(x + b * V + s));
+            return -0.5f * (v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w) - 4.f * kLogSqrt2Pi;
+        }
+#endif
+        const PriorLogProbOp one{x, loc, scale, V};
+        float acc = 0.f;
+        for (int i = 0; i < n; ++i) acc += one(b, s + i);
+        return acc;
+    }
+};
+
 // NormalPrior.sample_: four consecutive sites per Philox call.
 struct PriorSampleOp {
     float* x;
@@ -67,6 +87,12 @@ struct PriorSampleOp {
         box_muller(r.c[0], r.c[1], z[0], z[1]);
         box_muller(r.c[2], r.c[3], z[2], z[3]);
         float acc = 0.f;
+#if defined(__CUDA_ARCH__)
+        if (n == 4 && !loc && !scale && (((b * V + s) & 3) == 0)) {       // the common case: one 128-bit store
+            *reinterpret_cast<float4*>(x + b * V + s) = make_float4(z[0], z[1], z[2], z[3]);
+            return -0.5f * (z[0] * z[0] + z[1] * z[1] + z[2] * z[2] + z[3] * z[3]) - 4.f * kLogSqrt2Pi;
+        }
+#endif
         for (int i = 0; i < n; ++i) {
             const float mu = loc ? NFK_LDG(loc + s + i) : 0.f;
             const float sg = scale ? NFK_LDG(scale + s + i) : 1.f;
