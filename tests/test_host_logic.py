@@ -269,3 +269,16 @@ def test_prepare_seeds():
     with pytest.raises(AssertionError):
         prepare_seeds(2, [1])
     assert isinstance(gen_seed(), int)
+
+
+def test_fused2d_supported_mirrors_kernel_dispatch():
+    """Which lattices take the single-kernel coupling step (nfk_fused.cu / nfk_fused_tc.cu dispatch)."""
+    from normflow__b200 import _ops
+    ok = _ops.fused2d_supported
+    assert ok(64, 64, 10) and ok(16, 16, None) and ok(2, 2, 6) and ok(6, 10, 5)      # tensor-core kernel: even sides
+    assert ok(7, 8, 10) and ok(5, 12, 16)                                            # CUDA-core kernel: L1 % 4 == 0
+    assert not ok(7, 10, 10)            # odd rows and L1 % 4 != 0: neither kernel
+    assert not ok(64, 64, 12) or 12 in _ops.FUSED2D_KNOTS                            # K = 12 only on the CUDA-core kernel
+    assert ok(64, 64, 12) and not ok(6, 10, 12)
+    assert not ok(64, 64, 7) and not ok(64, 64, -1)
+    assert not ok(3, 3, None)
