@@ -64,10 +64,17 @@ extern "C" int nfk_prior_normal_logprob(const float* x, float* logr, int64_t B, 
 }
 
 // ============================================================== affine / shift
+static bool affine_vec_ok(const float* x, const float* out, const uint8_t* mask, const float* y, int64_t V) {
+    return V % 4 == 0 && V > kSmallV && ((uintptr_t)x % 16) == 0 && ((uintptr_t)out % 16) == 0 &&
+           ((uintptr_t)y % 16) == 0 && ((uintptr_t)mask % 4) == 0;
+}
 extern "C" int nfk_affine_fwd(const float* x, const float* out, const uint8_t* mask, int parity,
                               int frozen_mode, const float* log_in, float* y, float* log_out,
                               int64_t B, int64_t V, void* stream) {
     if (!x || !out || !mask || !y) return NFK_EINVAL;
+    if (affine_vec_ok(x, out, mask, y, V))
+        return launch_sites_vec<AffineOp4<0>, 4>(AffineOp4<0>{x, out, mask, parity == 0 ? 1 : 0, frozen_mode, y, V},
+                                                 B, V, log_in, log_out, NFK_STREAM(stream));
     return launch_sites(AffineOp<0>{x, out, mask, parity == 0 ? 1 : 0, frozen_mode, y, V}, B, V, log_in,
                         log_out, NFK_STREAM(stream));
 }
@@ -75,6 +82,9 @@ extern "C" int nfk_affine_inv(const float* x, const float* out, const uint8_t* m
                               int frozen_mode, const float* log_in, float* y, float* log_out,
                               int64_t B, int64_t V, void* stream) {
     if (!x || !out || !mask || !y) return NFK_EINVAL;
+    if (affine_vec_ok(x, out, mask, y, V))
+        return launch_sites_vec<AffineOp4<1>, 4>(AffineOp4<1>{x, out, mask, parity == 0 ? 1 : 0, frozen_mode, y, V},
+                                                 B, V, log_in, log_out, NFK_STREAM(stream));
     return launch_sites(AffineOp<1>{x, out, mask, parity == 0 ? 1 : 0, frozen_mode, y, V}, B, V, log_in,
                         log_out, NFK_STREAM(stream));
 }

@@ -132,6 +132,46 @@ struct AffineOp {
     }
 };
 
+// four consecutive sites (s % 4 == 0, V % 4 == 0): 128-bit loads / stores of x, t, s, y
+template <int MODE>
+struct AffineOp4 {
+    const float* x;
+    const float* out;     // [B][2][V]
+    const uint8_t* mask;
+    int active_val;
+    int frozen_copy;
+    float* y;
+    int64_t V;
+    NFK_HD float operator()(int64_t b, int64_t s, int n) const {
+#if defined(__CUDA_ARCH__)
+        if (n == 4) {
+            const int64_t i = b * V + s;
+            const float4 xv = __ldg(reinterpret_cast<const float4*>(x + i));
+            const float4 tv = __ldg(reinterpret_cast<const float4*>(out + (2 * b) * V + s));
+            const float4 sv = __ldg(reinterpret_cast<const float4*>(out + (2 * b + 1) * V + s));
+            const uint32_t m = __ldg(reinterpret_cast<const uint32_t*>(mask + s));
+            const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, ta[4] = {tv.x, tv.y, tv.z, tv.w};
+            const float sa[4] = {sv.x, sv.y, sv.z, sv.w};
+            float ya[4], acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const bool active = (int)((m >> (8 * k)) & 0xFF) == active_val;
+                const float sc = fabsf(sa[k]);
+                const float tr = MODE == 0 ? ta[k] + xa[k] * expf(-sc) : (xa[k] - ta[k]) * expf(sc);
+                ya[k] = active ? tr : (frozen_copy ? xa[k] : 0.f);
+                acc += active ? (MODE == 0 ? -sc : sc) : 0.f;
+            }
+            *reinterpret_cast<float4*>(y + i) = make_float4(ya[0], ya[1], ya[2], ya[3]);
+            return acc;
+        }
+#endif
+        const AffineOp<MODE> one{x, out, mask, active_val, frozen_copy, y, V};
+        float acc = 0.f;
+        for (int k = 0; k < n; ++k) acc += one(b, s + k);
+        return acc;
+    }
+};
+
 struct AffineBwdOp {
     const float* x;
     const float* out;
