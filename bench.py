@@ -359,7 +359,7 @@ def run_b200(args):
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_gpu": B, "lattice": list(LATTICE),
-                   "l2": "per-step working set (x 268 MB, conditioner output 7.5 GB) is far larger than the 126 MB L2",
+                   "l2": "inputs larger than L2: every step draws a fresh 268 MB field batch (and writes 4 x 268 MB of intermediate fields), 126 MB L2",
                    "model_bytes_per_sample": step_bytes,
                    "hbm_model_frac_whole_step": step_bytes * value / world / 1e9 / pk["hbm_gbs"]},
         "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches),
