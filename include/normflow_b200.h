@@ -226,8 +226,10 @@ int nfk_gather_rows(const float* src, const int64_t* idx, const float* prev, flo
  * kernel: Coupling_.forward's step k (couplings_.py:56-64) = Mask.split + conditioner
  * (modules.py:131-145) + atomic_forward/backward (couplings_.py:123-139, 178-200).  The
  * (B,P,L0,L1) conditioner output never reaches memory and its last layer is evaluated
- * at the active sites only.  Forward evaluation only (sampling / log_prob); training
- * uses the unfused kernels, which keep what autograd needs.
+ * at the active sites only.  Evaluation only (sampling / log_prob); see
+ * nfk_fused2d_step_train for the training forward.  Two kernels sit behind it: the
+ * tcgen05 kernel (conditioner layers 2 and 3 as fp16-pair implicit GEMMs; even L0 and
+ * L1 <= 160, n_knots in {4,5,6,8,10}) and a CUDA-core kernel (L1 % 4 == 0, n_knots <= 16).
  *   x, y: [B][L0][L1] (y != x), full-field semantics (frozen sites copied).
  *   w1[H][1][3][3], w2[H][H][3][3], w3[P][H][3][3]; b1, b2, b3 may be NULL.  H == 8.
  *   kind 0: affine (P = 2); kind 1: RQ spline (P = 3K-2, prm as in nfk_rqs_fwd).
@@ -238,6 +240,20 @@ int nfk_fused2d_step(const float* x, const float* w1, const float* b1, const flo
                      nfk_rqs_params prm, int mask_parity, int parity, int inverse,
                      const float* log_in, float* y, float* log_out,
                      int L0, int L1, int64_t B, void* stream);
+
+/* The same step as the forward pass of TRAINING (Fitter.step, _normflowcore.py:275-294): besides y
+ * and log_out it stores what the gradient kernels need -- the post-activation hidden layers
+ * h1, h2 [B][H][L0][L1] and the conditioner output out[B][P][L0][L1] (defined at the active
+ * sites only) -- so that autograd can run nfk_rqs_bwd / nfk_affine_bwd and the convolution
+ * gradient kernels without re-evaluating the conditioner.  Forward direction only.  Runs on the
+ * tensor-core kernel; returns NFK_EUNSUPPORTED outside its geometry (even L0, L1 <= 160;
+ * n_knots in {4, 5, 6, 8, 10}), in which case the caller evaluates the layers one by one.   */
+int nfk_fused2d_step_train(const float* x, const float* w1, const float* b1, const float* w2,
+                           const float* b2, const float* w3, const float* b3, int H, int kind,
+                           nfk_rqs_params prm, int mask_parity, int parity,
+                           const float* log_in, float* y, float* log_out,
+                           float* h1, float* h2, float* out,
+                           int L0, int L1, int64_t B, void* stream);
 
 #ifdef __cplusplus
 }

@@ -61,6 +61,8 @@ _SIGNATURES = {
     "nfk_gather_rows": [c_f, c_f, c_f, c_f, c_l, c_l, c_f],
     "nfk_fused2d_step": [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, RqsParams, c_i, c_i, c_i,
                          c_f, c_f, c_f, c_i, c_i, c_l, c_f],
+    "nfk_fused2d_step_train": [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, RqsParams, c_i, c_i,
+                               c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_l, c_f],
 }
 
 _lib = None

@@ -421,26 +421,37 @@ class _ConvStack(torch.autograd.Function):
         saved = ctx.saved_tensors
         hs, weights = saved[:n + 1], saved[n + 1:2 * n + 1]
         in_mask = saved[2 * n + 1] if has_mask else None
-        gpre = _f32c(gout, "gout")
-        if acts[n - 1] != 0:     # last layer had an activation: fold its derivative in first
-            raise NotImplementedError("ConvAct with an activation on the output layer: use the unfused path")
-        gws, gbs = [None] * n, [None] * n
-        for i in reversed(range(n)):
-            w = weights[i]
-            Co, Ci = w.shape[0], w.shape[1]
-            first = (i == 0)
-            gws[i], gbs[i] = _conv_weight_grad(hs[i], in_mask if first else None, in_keep, gpre,
-                                               tuple(w.shape), has_bias[i], shape, ksize)
-            if first and not ctx.needs_input_grad[0]:
-                gpre = None
-                break
-            # d/d(input of layer i): conv of gpre with w^T (taps flipped); multiply by act'(h_{i})
-            gpre = _conv_call(gpre, w.contiguous(), 1, None, None, 0, 0, hs[i] if not first else None,
-                              acts[i - 1] if not first else 0, shape, ksize, Co, Ci)
-        gin = None
-        if gpre is not None:
-            gin = gpre if in_mask is None else mask_select(gpre, in_mask, in_keep)
+        gws, gbs, gin = _conv_stack_backward(hs[:n], weights, has_bias, acts, ksize, shape, in_mask, in_keep,
+                                             _f32c(gout, "gout"), ctx.needs_input_grad[0])
         return (gin, None, None, None, None, None, *gws, *gbs)
+
+
+def _conv_stack_backward(hs, weights, has_bias, acts, ksize, shape, in_mask, in_keep, gpre, need_input_grad):
+    """Gradients of a ConvAct stack.  hs[i] = input of layer i (hs[0] the stack's input, hs[i] the
+    post-activation output of layer i-1), gpre = d loss / d (output of the last layer, which has
+    no activation).  Walks the layers in reverse: one weight-gradient kernel plus one
+    data-gradient kernel (the same circular conv on transposed/flipped weights with act' fused in
+    its epilogue) per layer.  Returns (weight grads, bias grads, input grad or None)."""
+    n = len(weights)
+    if acts[n - 1] != 0:
+        raise NotImplementedError("ConvAct with an activation on the output layer: use the unfused path")
+    gws, gbs = [None] * n, [None] * n
+    for i in reversed(range(n)):
+        w = weights[i]
+        Co, Ci = w.shape[0], w.shape[1]
+        first = (i == 0)
+        gws[i], gbs[i] = _conv_weight_grad(hs[i], in_mask if first else None, in_keep, gpre,
+                                           tuple(w.shape), has_bias[i], shape, ksize)
+        if first and not need_input_grad:
+            gpre = None
+            break
+        # d/d(input of layer i): conv of gpre with w^T (taps flipped); multiply by act'(h_{i})
+        gpre = _conv_call(gpre, w.contiguous(), 1, None, None, 0, 0, hs[i] if not first else None,
+                          acts[i - 1] if not first else 0, shape, ksize, Co, Ci)
+    gin = None
+    if gpre is not None:
+        gin = gpre if in_mask is None else mask_select(gpre, in_mask, in_keep)
+    return gws, gbs, gin
 
 
 def conv_stack(inp, weights, biases, acts, ksize, in_mask=None, in_keep=0):
@@ -486,6 +497,71 @@ def fused2d_step(x, weights, biases, kind, prm, mask_parity, parity, log0=0, inv
                                      int(bool(inverse)), dev(log_in), dev(y), dev(log_out), L0, L1, B, stream()),
               "fused2d_step")
     return y, log_out
+
+
+class _FusedStepTrain(torch.autograd.Function):
+    """Forward of a training step through the tensor-core fused kernel (which also stores the
+    hidden layers and the conditioner output); backward through the transform's VJP kernel and
+    the convolution gradient kernels -- the conditioner is never evaluated layer by layer."""
+
+    @staticmethod
+    def forward(ctx, x, log_in, mask, kind, prm, mask_parity, parity, n_bias, *params):
+        w, b = params[:3], params[3:]
+        B, L0, L1 = x.shape
+        P = w[2].shape[0]
+        y = torch.empty_like(x)
+        log_out = torch.empty((B,), dtype=torch.float32, device=x.device)
+        h1 = torch.empty((B, 8, L0, L1), dtype=torch.float32, device=x.device)
+        h2 = torch.empty((B, 8, L0, L1), dtype=torch.float32, device=x.device)
+        out = torch.empty((B, P, L0, L1), dtype=torch.float32, device=x.device)
+        with _C.timed("fused2d_step_train"):
+            check(lib().nfk_fused2d_step_train(dev(x), dev(w[0]), dev(b[0]), dev(w[1]), dev(b[1]), dev(w[2]), dev(b[2]),
+                                               8, kind, prm, mask_parity, parity, dev(log_in), dev(y), dev(log_out),
+                                               dev(h1), dev(h2), dev(out), L0, L1, B, stream()), "fused2d_step_train")
+        ctx.save_for_backward(x, h1, h2, out, mask, *w)
+        ctx.cfg = (kind, prm, parity, log_in is not None, [t is not None for t in b])
+        return y, log_out
+
+    @staticmethod
+    def backward(ctx, gy, glog):
+        x, h1, h2, out, mask, *w = ctx.saved_tensors
+        kind, prm, parity, has_log, has_bias = ctx.cfg
+        B, L0, L1 = x.shape
+        V = L0 * L1
+        gy, glog = _f32c(gy, "gy"), _f32c(glog, "glog")
+        gx, gout = torch.empty_like(x), torch.empty_like(out)
+        if kind == 1:
+            with _C.timed("rqs_bwd"):
+                check(lib().nfk_rqs_bwd(dev(x), dev(out), dev(mask, torch.uint8), parity, _C.FROZEN_COPY, prm, dev(gy),
+                                        dev(glog), dev(gx), dev(gout), B, V, stream()), "rqs_bwd")
+        else:
+            check(lib().nfk_affine_bwd(dev(x), dev(out), dev(mask, torch.uint8), parity, _C.FROZEN_COPY, dev(gy),
+                                       dev(glog), dev(gx), dev(gout), B, V, stream()), "affine_bwd")
+        frozen_keep = 0 if parity == 0 else 1          # the conditioner saw the frozen partition only
+        acts = (_C.ACT['tanh'], _C.ACT['tanh'], _C.ACT[None])
+        gws, gbs, gin = _conv_stack_backward([x.unsqueeze(1), h1, h2], w, has_bias, acts, 3, (L0, L1), mask,
+                                             frozen_keep, gout, ctx.needs_input_grad[0])
+        if gin is not None:
+            gx = gx + gin.reshape(x.shape)
+        return (gx, glog if has_log else None, None, None, None, None, None, None, *gws, *gbs)
+
+
+def fused2d_train_supported(L0, L1, n_knots=None):
+    """Geometry of the tensor-core kernel (the only one with a training forward)."""
+    return (2 <= L1 <= 160 and L0 >= 2 and L0 % 2 == 0 and L1 % 2 == 0
+            and (n_knots is None or n_knots in FUSED2D_TC_KNOTS))
+
+
+def fused2d_step_train(x, weights, biases, kind, prm, mask, mask_parity, parity, log0=0):
+    """Differentiable atomic coupling step: fused forward, kernel-by-kernel backward."""
+    x = _f32c(x, "x")
+    log_in = as_log(log0, x)
+    w = [_f32c(t, "conv weight") for t in weights]
+    b = [None if t is None else _f32c(t, "conv bias") for t in biases]
+    if prm is None:
+        prm = _C.RqsParams(2, 0.0, 1.0, 0.0, 1.0, 0, 0)
+    return _FusedStepTrain.apply(x, log_in, _mask_u8(mask), int(kind), prm, int(mask_parity), int(parity),
+                                 sum(t is not None for t in b), *w, *b)
 
 
 # ---------------------------------------------------------------------------- mcmc

@@ -78,7 +78,7 @@ namespace nfk {
 int fused2d_tc_step(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                     const float* w3, const float* b3, int kind, const nfk_rqs_params& prm, int mask_parity,
                     int parity, int inverse, const float* log_in, float* y, float* log_out, int L0, int L1,
-                    int64_t B, cudaStream_t st);
+                    int64_t B, cudaStream_t st, float* save_h1, float* save_h2, float* save_out);
 }
 
 // NFK_FUSED_TC=0 in the environment keeps the CUDA-core kernel (A/B timing and debugging)
@@ -102,7 +102,7 @@ extern "C" int nfk_fused2d_step(const float* x, const float* w1, const float* b1
     }
     if (tc_enabled()) {        // conditioner on the tensor cores when the geometry allows it
         const int rc = fused2d_tc_step(x, w1, b1, w2, b2, w3, b3, kind, prm, mask_parity, parity, inverse, log_in, y,
-                                       log_out, L0, L1, B, NFK_STREAM(stream));
+                                       log_out, L0, L1, B, NFK_STREAM(stream), nullptr, nullptr, nullptr);
         if (rc != NFK_EUNSUPPORTED) return rc;
     }
     // CUDA-core kernel: rows are walked in groups of four columns with 128-bit accesses
@@ -128,4 +128,25 @@ extern "C" int nfk_fused2d_step(const float* x, const float* w1, const float* b1
 #undef X
         default: return NFK_EUNSUPPORTED;
     }
+}
+
+// Training forward of the same step: additionally stores the hidden layers and the conditioner
+// output (channel-major fp32) that nfk_rqs_bwd / nfk_affine_bwd and the convolution gradient
+// kernels consume.  Tensor-core kernel only: NFK_EUNSUPPORTED outside its geometry.
+extern "C" int nfk_fused2d_step_train(const float* x, const float* w1, const float* b1, const float* w2,
+                                      const float* b2, const float* w3, const float* b3, int H, int kind,
+                                      nfk_rqs_params prm, int mask_parity, int parity,
+                                      const float* log_in, float* y, float* log_out,
+                                      float* h1, float* h2, float* out,
+                                      int L0, int L1, int64_t B, void* stream) {
+    if (!x || !w1 || !w2 || !w3 || !y || !h1 || !h2 || !out || x == y) return NFK_EINVAL;
+    if (H != kFH || L0 < 1 || L1 < 1 || (kind != 0 && kind != 1)) return NFK_EUNSUPPORTED;
+    if (B <= 0) return NFK_OK;
+    if (kind == 1) {
+        if (prm.n_knots < 2 || !(prm.xlim1 > prm.xlim0) || !(prm.ylim1 > prm.ylim0)) return NFK_EINVAL;
+        if ((prm.extrap_left != NFK_EXTRAP_NONE && prm.extrap_left != NFK_EXTRAP_LINEAR) ||
+            (prm.extrap_right != NFK_EXTRAP_NONE && prm.extrap_right != NFK_EXTRAP_LINEAR)) return NFK_EINVAL;
+    }
+    return fused2d_tc_step(x, w1, b1, w2, b2, w3, b3, kind, prm, mask_parity, parity, 0, log_in, y, log_out, L0, L1,
+                           B, NFK_STREAM(stream), h1, h2, out);
 }

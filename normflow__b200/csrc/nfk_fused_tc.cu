@@ -34,6 +34,9 @@ struct TcArgs {
     TcGeom g;
     RqsCfg cfg;
     long long* trace;      // debug: per-phase clock64 stamps of CTA 0 (NULL in production)
+    // training forward (SAVE): what the backward kernels need, channel-major fp32
+    float *save_h1, *save_h2;   // [B][8][L0][L1] post-activation hidden layers
+    float *save_out;            // [B][P][L0][L1] conditioner output (written at the active sites only)
 };
 
 // debug hook (not part of the C ABI): a device buffer of 2 x 4096 int64 that CTA 0 fills with
@@ -63,7 +66,7 @@ __device__ __forceinline__ void make_records(const float (&v)[8], uint4& hi, uin
     lo = make_uint4(tc_pack(l[0], l[1]), tc_pack(l[2], l[3]), tc_pack(l[4], l[5]), tc_pack(l[6], l[7]));
 }
 
-template <int KIND, int K, int INV>
+template <int KIND, int K, int INV, bool SAVE>
 __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs a) {
     constexpr int P = KIND == 0 ? 2 : 3 * K - 2;
     constexpr int NP = TcShape<P>::NP, N3 = TcShape<P>::N3;
@@ -242,7 +245,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs 
         // orientation, so only the 72 non-zero FMAs of the 144 are issued, and lanes walk
         // consecutive columns (conflict-free shared-memory traffic).
         // NI items (it0, it0 + 256, ...) per trip share every weight fetched from shared memory
-        auto layer1_items = [&](auto ni_tag, int it0, int r0, int rows, const float* xbuf) {
+        auto layer1_items = [&](auto ni_tag, int it0, long long b, int r0, int rows, const float* xbuf) {
             constexpr int NI = decltype(ni_tag)::value;
             float in[NI][9];                                              // by weight tap kh * 3 + kw
             bool up_active[NI];
@@ -292,12 +295,12 @@ __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs 
 #pragma unroll
             for (int z = 0; z < NI; ++z) {
                 uint4 rec[2][2];                                          // [site][hi / lo]
+                float vv[2][8];
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
-                    float v[8];
 #pragma unroll
-                    for (int co = 0; co < 8; ++co) v[co] = tanh_from_scaled(acc[z][s][co]);
-                    make_records(v, rec[s][0], rec[s][1]);
+                    for (int co = 0; co < 8; ++co) vv[s][co] = tanh_from_scaled(acc[z][s][co]);
+                    make_records(vv[s], rec[s][0], rec[s][1]);
                 }
                 const int c = cc[z], i1 = (2 * jp[z]) * WS + c + 1;
 #pragma unroll
@@ -317,6 +320,15 @@ __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs 
                         *reinterpret_cast<uint4*>(dw) = hi;
                         *reinterpret_cast<uint4*>(dw + g.h1_comp_bytes) = lo;
                     }
+                    if (SAVE) {                                           // rows of the strip proper, not its halo
+                        const int j1 = 2 * jp[z] + s;
+                        if (j1 >= 2 && j1 < rows + 2) {
+                            float* dsth = a.save_h1 + (b * 8 * L0 + (r0 - 2 + j1)) * (long long)L1 + c;
+#pragma unroll
+                            for (int co = 0; co < 8; ++co)
+                                dsth[(long long)co * L0 * L1] = take_active ? vv[0][co] : vv[1][co];
+                        }
+                    }
                 }
             }
         };
@@ -325,8 +337,8 @@ __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs 
             const int npair = (rows + 5) >> 1, items = npair * L1;
             int it0 = tid;
             for (; it0 + kTcComputeThreads < items; it0 += 2 * kTcComputeThreads)
-                layer1_items(std::integral_constant<int, 2>{}, it0, r0, rows, xbuf);
-            if (it0 < items) layer1_items(std::integral_constant<int, 1>{}, it0, r0, rows, xbuf);
+                layer1_items(std::integral_constant<int, 2>{}, it0, u.b, r0, rows, xbuf);
+            if (it0 < items) layer1_items(std::integral_constant<int, 1>{}, it0, u.b, r0, rows, xbuf);
         };
 
         // one warp of each tile set polls the MMA barrier; the other three block in hardware
@@ -365,6 +377,11 @@ __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs 
                         uint8_t* dw = h2 + (iw & 1) * g.h2_par_bytes + (iw >> 1) * 16;
                         *reinterpret_cast<uint4*>(dw) = hi;
                         *reinterpret_cast<uint4*>(dw + g.h2_comp_bytes) = lo;
+                    }
+                    if (SAVE && j2 >= 1 && j2 <= rows) {
+                        float* dsth = a.save_h2 + (u.b * 8 * L0 + (u.r0 - 1 + j2)) * (long long)L1 + slot - 1;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) dsth[(long long)c * L0 * L1] = v[c];
                     }
                 }
             }
@@ -409,6 +426,11 @@ __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs 
                 const int s = 2 * (cbase + k * 128 + q * 32 + lane) + plin;
                 const int j2 = tc_div(s, g.magic_ws), slot = s - j2 * WS;
                 if (j2 >= 1 && j2 <= rows && slot >= 1 && slot <= L1) {
+                    if (SAVE) {
+                        float* dsto = a.save_out + (u.b * P * L0 + (r0 + j2 - 1)) * (long long)L1 + slot - 1;
+#pragma unroll
+                        for (int c = 0; c < P; ++c) dsto[(long long)c * L0 * L1] = prm[c];
+                    }
                     float* px = xbuf + (j2 + 2) * WS + slot;
                     const float xv = *px;
                     float out, l;
@@ -503,7 +525,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs 
     if (warp == kTcComputeWarps) tc::tmem_dealloc(tmem, kTcTmemCols);
 }
 
-template <int KIND, int K, int INV>
+template <int KIND, int K, int INV, bool SAVE>
 int tc_launch(TcArgs a, cudaStream_t st) {
     constexpr int P = KIND == 0 ? 2 : 3 * K - 2;
     static int sm_count = 0;
@@ -536,19 +558,20 @@ int tc_launch(TcArgs a, cudaStream_t st) {
     a.g.magic_l1 = (uint32_t)((0x100000000ULL + a.g.L1 - 1) / a.g.L1);
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(fused2d_tc_kernel<KIND, K, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(fused2d_tc_kernel<KIND, K, INV, SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)budget) != cudaSuccess) return NFK_ECUDA;
         attr_set = true;
     }
     long long grid = 2LL * sm_count;
     if (grid > a.B) grid = a.B;
-    fused2d_tc_kernel<KIND, K, INV><<<(unsigned)grid, kTcThreads, a.g.smem_bytes, st>>>(a);
+    fused2d_tc_kernel<KIND, K, INV, SAVE><<<(unsigned)grid, kTcThreads, a.g.smem_bytes, st>>>(a);
     return check_launch();
 }
 
 template <int KIND, int K>
 int tc_launch_dir(const TcArgs& a, int inverse, cudaStream_t st) {
-    return inverse ? tc_launch<KIND, K, 1>(a, st) : tc_launch<KIND, K, 0>(a, st);
+    if (a.save_out) return inverse ? NFK_EINVAL : tc_launch<KIND, K, 0, true>(a, st);
+    return inverse ? tc_launch<KIND, K, 1, false>(a, st) : tc_launch<KIND, K, 0, false>(a, st);
 }
 
 }  // namespace
@@ -560,12 +583,14 @@ namespace nfk {
 int fused2d_tc_step(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                     const float* w3, const float* b3, int kind, const nfk_rqs_params& prm, int mask_parity,
                     int parity, int inverse, const float* log_in, float* y, float* log_out, int L0, int L1,
-                    int64_t B, cudaStream_t st) {
+                    int64_t B, cudaStream_t st, float* save_h1, float* save_h2, float* save_out) {
     if ((L0 & 1) || (L1 & 1) || L1 < 2 || L0 < 2) return NFK_EUNSUPPORTED;   // checkerboard must wrap consistently
+    if ((save_h1 || save_h2 || save_out) && !(save_h1 && save_h2 && save_out)) return NFK_EINVAL;
     TcArgs a;
     a.x = x; a.w1 = w1; a.b1 = b1; a.w2 = w2; a.b2 = b2; a.w3 = w3; a.b3 = b3;
     a.log_in = log_in; a.y = y; a.log_out = log_out; a.B = B;
     a.trace = g_trace;
+    a.save_h1 = save_h1; a.save_h2 = save_h2; a.save_out = save_out;
     a.g = TcGeom{};
     a.g.L0 = L0; a.g.L1 = L1; a.g.WS = L1 + 3;
     a.g.mask_parity = mask_parity; a.g.active_val = parity == 0 ? 1 : 0;

@@ -10,6 +10,8 @@ split / atomic_* / cat dataflow for subclasses that only define `atomic_forward`
 """
 
 import numpy as np
+import os
+
 import torch
 
 from .._core import Module_
@@ -83,6 +85,14 @@ class Coupling_(Module_):
         for k in (reversed(order) if inverse else order):
             p = k % 2
             net = self.nets[k]
+            if (not inverse and self._fused_kind is not None and torch.is_grad_enabled()
+                    and self._fusable_train(net, x)):
+                # training forward: the same fused kernel, which also keeps what the gradient kernels need
+                convs = net._convs()
+                x, log0 = _ops.fused2d_step_train(x, [c.weight for c in convs], [c.bias for c in convs],
+                                                  self._fused_kind, self._fused_params(convs[-1].out_channels),
+                                                  self.mask._mask, self.mask.mask_kwargs.get('parity', 0), p, log0)
+                continue
             if self._fused_kind is not None and self._fusable(net, x):
                 # conditioner + transform in ONE kernel: the (B,P,*L) tensor is never formed
                 convs = net._convs()
@@ -113,6 +123,20 @@ class Coupling_(Module_):
             return False
         return (x.dim() == 3 and x.is_cuda and self.channels_axis == 1
                 and _ops.fused2d_supported(x.shape[1], x.shape[2], self._fused_knots(net)))
+
+    def _fusable_train(self, net, x):
+        """Same structural conditions, with an autograd graph wanted: needs the tensor-core kernel.
+        NFK_FUSED_TRAIN=0 in the environment keeps the layer-by-layer kernels (A/B tests)."""
+        if os.environ.get('NFK_FUSED_TRAIN') == '0':
+            return False
+        if not (isinstance(net, ConvAct) and net.fused2d_ok):
+            return False
+        if not (x.requires_grad or any(p.requires_grad for p in net.parameters())):
+            return False
+        if not (isinstance(self.mask, EvenOddMask) and self.mask.mask_kwargs.get('exclude_mu') is None):
+            return False
+        return (x.dim() == 3 and x.is_cuda and self.channels_axis == 1
+                and _ops.fused2d_train_supported(x.shape[1], x.shape[2], self._fused_knots(net)))
 
     def _transform(self, x, out, parity, log0, frozen_mode, inverse):
         raise NotImplementedError

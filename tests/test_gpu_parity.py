@@ -761,3 +761,29 @@ def test_spawnprocesses_two_gpus_nccl(tmp_path):
     assert torch.equal(r0["params"], r1["params"])
     assert not torch.allclose(r0["params"], start)
     assert len(r0["loss"]) == 5 and np.isfinite(r0["loss"]).all()
+
+
+@pytest.mark.parametrize("shape,blocks,B", [((16, 16), [('affine', 2), ('rqs', 2)], 6), ((64, 64), [('rqs', 2)], 3)])
+def test_fused_training_forward_gradients_match_layerwise_path(shape, blocks, B, monkeypatch):
+    """Training takes the tensor-core fused forward (nfk_fused2d_step_train) and differentiates through
+    the stored hidden layers; the layer-by-layer kernels (NFK_FUSED_TRAIN=0) must give the same loss
+    and the same gradients of the field and of every parameter."""
+    model = _config_model(shape, blocks, seed=13)
+    x0 = torch.randn(B, *shape, generator=torch.Generator('cpu').manual_seed(4), device='cpu').to(DEV)
+    res = {}
+    for flag in ('1', '0'):
+        monkeypatch.setenv('NFK_FUSED_TRAIN', flag)
+        for p in model.net_.parameters():
+            p.grad = None
+        x = x0.clone().requires_grad_(True)
+        n0 = _C.launch_count()
+        y, logJ = model.net_(x)
+        loss = (model.action(y) - logJ).mean()
+        loss.backward()
+        res[flag] = (loss.item(), x.grad.clone(), [p.grad.clone() for p in model.net_.parameters()],
+                     _C.launch_count() - n0)
+    assert abs(res['1'][0] - res['0'][0]) <= 1e-5 * max(1.0, abs(res['0'][0]))
+    close_grad(res['1'][1], res['0'][1].double().cpu().numpy(), tol=2e-5)
+    for g1, g0 in zip(res['1'][2], res['0'][2]):
+        close_grad(g1, g0.double().cpu().numpy(), tol=2e-5)
+    assert res['1'][3] < res['0'][3]          # fewer launches: no per-layer forward kernels
