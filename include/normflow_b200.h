@@ -200,6 +200,13 @@ int nfk_conv_circ_bwd_weight(const float* in, const uint8_t* in_mask, int in_kee
                              const float* gpre, float* gw, float* gbias,
                              nfk_lattice lat, int ksize, int Ci, int Co, int64_t B, void* stream);
 
+/* The same weight gradient when gpre is the gradient of a CHECKERBOARD coupling's conditioner
+ * output (couplings_.py:124,179 followed by purify, :126-127,186-187): it vanishes on every site
+ * with (sum of coordinates) % 2 != g_parity, so only the other half of the sites is visited.
+ * No input mask.  ACCUMULATES with atomics like nfk_conv_circ_bwd_weight.                */
+int nfk_conv_circ_bwd_weight_cb(const float* in, const float* gpre, int g_parity, float* gw, float* gbias,
+                                nfk_lattice lat, int ksize, int Ci, int Co, int64_t B, void* stream);
+
 /* ----------------------------------------------------------------- mcmc ----
  * Metropolis.calc_accept_status + calc_accept_indices (mcmc/mcmc.py:304-328),
  * sequential independence-Metropolis scan on the device (one warp):

@@ -57,6 +57,7 @@ _SIGNATURES = {
     "nfk_phi4_action_bwd": [c_f, Lattice, c_fl, c_fl, c_fl, c_f, c_f, c_l, c_f],
     "nfk_conv_circ_fwd": [c_f, c_f, c_i, c_f, c_f, c_i, c_i, c_f, c_i, c_f, Lattice, c_i, c_i, c_i, c_l, c_f],
     "nfk_conv_circ_bwd_weight": [c_f, c_f, c_i, c_f, c_f, c_f, Lattice, c_i, c_i, c_i, c_l, c_f],
+    "nfk_conv_circ_bwd_weight_cb": [c_f, c_f, c_i, c_f, c_f, Lattice, c_i, c_i, c_i, c_l, c_f],
     "nfk_metropolis_scan": [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_l, c_f],
     "nfk_gather_rows": [c_f, c_f, c_f, c_f, c_l, c_l, c_f],
     "nfk_fused2d_step": [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, RqsParams, c_i, c_i, c_i,

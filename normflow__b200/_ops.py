@@ -378,10 +378,17 @@ def _conv_call(inp, w, transposed, bias, in_mask, in_keep, act, dact_from, dact_
     return out
 
 
-def _conv_weight_grad(inp, in_mask, in_keep, gpre, w_shape, want_bias, shape, ksize):
+def _conv_weight_grad(inp, in_mask, in_keep, gpre, w_shape, want_bias, shape, ksize, g_parity=None):
     Co, Ci = w_shape[0], w_shape[1]
     gw = torch.zeros(w_shape, dtype=torch.float32, device=inp.device)
     gb = torch.zeros((Co,), dtype=torch.float32, device=inp.device) if want_bias else None
+    if g_parity is not None and in_mask is None:
+        # gpre lives on one checkerboard partition only: visit just those sites
+        with _C.timed(f"conv_circ_bwd_weight_cb[{Ci}->{Co}]"):
+            check(lib().nfk_conv_circ_bwd_weight_cb(dev(inp), dev(gpre), int(g_parity), dev(gw), dev(gb),
+                                                    _C.lattice(shape), int(ksize), int(Ci), int(Co),
+                                                    inp.shape[0], stream()), "conv_circ_bwd_weight_cb")
+        return gw, gb
     with _C.timed(f"conv_circ_bwd_weight[{Ci}->{Co}]"):
         check(lib().nfk_conv_circ_bwd_weight(dev(inp), dev(in_mask, torch.uint8), int(in_keep), dev(gpre),
                                              dev(gw), dev(gb), _C.lattice(shape), int(ksize), int(Ci), int(Co),
@@ -426,7 +433,8 @@ class _ConvStack(torch.autograd.Function):
         return (gin, None, None, None, None, None, *gws, *gbs)
 
 
-def _conv_stack_backward(hs, weights, has_bias, acts, ksize, shape, in_mask, in_keep, gpre, need_input_grad):
+def _conv_stack_backward(hs, weights, has_bias, acts, ksize, shape, in_mask, in_keep, gpre, need_input_grad,
+                         gpre_parity=None):
     """Gradients of a ConvAct stack.  hs[i] = input of layer i (hs[0] the stack's input, hs[i] the
     post-activation output of layer i-1), gpre = d loss / d (output of the last layer, which has
     no activation).  Walks the layers in reverse: one weight-gradient kernel plus one
@@ -441,7 +449,8 @@ def _conv_stack_backward(hs, weights, has_bias, acts, ksize, shape, in_mask, in_
         Co, Ci = w.shape[0], w.shape[1]
         first = (i == 0)
         gws[i], gbs[i] = _conv_weight_grad(hs[i], in_mask if first else None, in_keep, gpre,
-                                           tuple(w.shape), has_bias[i], shape, ksize)
+                                           tuple(w.shape), has_bias[i], shape, ksize,
+                                           g_parity=gpre_parity if i == n - 1 and n > 1 else None)
         if first and not need_input_grad:
             gpre = None
             break
@@ -519,13 +528,13 @@ class _FusedStepTrain(torch.autograd.Function):
                                                8, kind, prm, mask_parity, parity, dev(log_in), dev(y), dev(log_out),
                                                dev(h1), dev(h2), dev(out), L0, L1, B, stream()), "fused2d_step_train")
         ctx.save_for_backward(x, h1, h2, out, mask, *w)
-        ctx.cfg = (kind, prm, parity, log_in is not None, [t is not None for t in b])
+        ctx.cfg = (kind, prm, parity, mask_parity, log_in is not None, [t is not None for t in b])
         return y, log_out
 
     @staticmethod
     def backward(ctx, gy, glog):
         x, h1, h2, out, mask, *w = ctx.saved_tensors
-        kind, prm, parity, has_log, has_bias = ctx.cfg
+        kind, prm, parity, mask_parity, has_log, has_bias = ctx.cfg
         B, L0, L1 = x.shape
         V = L0 * L1
         gy, glog = _f32c(gy, "gy"), _f32c(glog, "glog")
@@ -539,8 +548,12 @@ class _FusedStepTrain(torch.autograd.Function):
                                        dev(glog), dev(gx), dev(gout), B, V, stream()), "affine_bwd")
         frozen_keep = 0 if parity == 0 else 1          # the conditioner saw the frozen partition only
         acts = (_C.ACT['tanh'], _C.ACT['tanh'], _C.ACT[None])
+        # gout is non-zero on the active partition only: sites with (row + col) % 2 == g_parity
+        # (mask bit = (1 - mask_parity + row + col) % 2, active <=> bit == (parity == 0))
+        active_val = 1 if parity == 0 else 0
+        g_parity = (active_val - 1 + mask_parity) % 2
         gws, gbs, gin = _conv_stack_backward([x.unsqueeze(1), h1, h2], w, has_bias, acts, 3, (L0, L1), mask,
-                                             frozen_keep, gout, ctx.needs_input_grad[0])
+                                             frozen_keep, gout, ctx.needs_input_grad[0], gpre_parity=g_parity)
         if gin is not None:
             gx = gx + gin.reshape(x.shape)
         return (gx, glog if has_log else None, None, None, None, None, None, None, *gws, *gbs)

@@ -210,9 +210,14 @@ struct Wgrad2dArgs {
     float* gbias;
     int L0, L1, R, Ci, Co;
     long long B;
+    int g_parity;             // SPARSE: gpre vanishes on sites with (row + col) % 2 != g_parity
 };
 
-template <int CI, int CO_B>
+// SPARSE: the gradient handed in is that of a checkerboard coupling's conditioner output, which
+// is non-zero on ONE partition only; lanes then walk the sites of that partition (every other
+// column, the offset alternating with the row), halving the FMAs at the price of 2-way bank
+// conflicts on the shared loads.
+template <int CI, int CO_B, bool SPARSE>
 __global__ void __launch_bounds__(288, 2) conv2d_wgrad_kernel(Wgrad2dArgs a) {
     extern __shared__ float sm[];
     const int L0 = a.L0, L1 = a.L1, R = a.R, LW = L1 + 2;
@@ -261,7 +266,9 @@ __global__ void __launch_bounds__(288, 2) conv2d_wgrad_kernel(Wgrad2dArgs a) {
             }
             __syncthreads();
             for (int j = 0; j < rows; ++j)
-                for (int c = lane; c < L1; c += 32) {
+                for (int cc = lane; cc < (SPARSE ? (L1 + 1) / 2 : L1); cc += 32) {
+                    const int c = SPARSE ? 2 * cc + ((a.g_parity + r0 + j) & 1) : cc;
+                    if (SPARSE && c >= L1) continue;
                     float gv[CO_B], xv[CI];
 #pragma unroll
                     for (int co = 0; co < CO_B; ++co) gv[co] = g_s[(co * R + j) * L1 + c];
@@ -294,7 +301,7 @@ __global__ void __launch_bounds__(288, 2) conv2d_wgrad_kernel(Wgrad2dArgs a) {
     }
 }
 
-template <int CI, int CO_B>
+template <int CI, int CO_B, bool SPARSE>
 static int wgrad2d_launch(Wgrad2dArgs a, cudaStream_t st) {
     const int LW = a.L1 + 2;
     int R = a.L0 < 16 ? a.L0 : 16;
@@ -304,30 +311,50 @@ static int wgrad2d_launch(Wgrad2dArgs a, cudaStream_t st) {
     a.R = R;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(conv2d_wgrad_kernel<CI, CO_B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(conv2d_wgrad_kernel<CI, CO_B, SPARSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
     const int ncb = (a.Co + CO_B - 1) / CO_B;
     long long gx = (148LL * 2 + ncb - 1) / ncb;            // two CTAs per SM in all
     if (gx > a.B) gx = a.B;
     if (gx < 1) gx = 1;
-    conv2d_wgrad_kernel<CI, CO_B><<<dim3((unsigned)gx, ncb), 288, bytes(R), st>>>(a);
+    conv2d_wgrad_kernel<CI, CO_B, SPARSE><<<dim3((unsigned)gx, ncb), 288, bytes(R), st>>>(a);
     return check_launch();
 }
+
+static int conv_bwd_weight_impl(const float* in, const uint8_t* in_mask, int in_keep, const float* gpre,
+                                int g_parity, float* gw, float* gbias, nfk_lattice lat, int ksize, int Ci, int Co,
+                                int64_t B, void* stream);
 
 extern "C" int nfk_conv_circ_bwd_weight(const float* in, const uint8_t* in_mask, int in_keep,
                                         const float* gpre, float* gw, float* gbias,
                                         nfk_lattice lat, int ksize, int Ci, int Co, int64_t B, void* stream) {
+    return conv_bwd_weight_impl(in, in_mask, in_keep, gpre, -1, gw, gbias, lat, ksize, Ci, Co, B, stream);
+}
+extern "C" int nfk_conv_circ_bwd_weight_cb(const float* in, const float* gpre, int g_parity, float* gw, float* gbias,
+                                           nfk_lattice lat, int ksize, int Ci, int Co, int64_t B, void* stream) {
+    if (g_parity != 0 && g_parity != 1) return NFK_EINVAL;
+    return conv_bwd_weight_impl(in, nullptr, 0, gpre, g_parity, gw, gbias, lat, ksize, Ci, Co, B, stream);
+}
+
+static int conv_bwd_weight_impl(const float* in, const uint8_t* in_mask, int in_keep, const float* gpre,
+                                int g_parity, float* gw, float* gbias, nfk_lattice lat, int ksize, int Ci, int Co,
+                                int64_t B, void* stream) {
     if (!in || !gpre || !gw || !lat_ok(lat) || ksize < 1 || ksize % 2 == 0 || Ci < 1 || Co < 1) return NFK_EINVAL;
     if (B <= 0) return NFK_OK;
     if (lat.ndim == 2 && ksize == 3 && (Ci == 1 || Ci == 8) && lat.shape[0] >= 2 && lat.shape[1] >= 2) {
         Wgrad2dArgs w;
         w.in = in; w.in_mask = in_mask; w.in_keep = in_keep; w.gpre = gpre; w.gw = gw; w.gbias = gbias;
         w.L0 = lat.shape[0]; w.L1 = lat.shape[1]; w.R = 0; w.Ci = Ci; w.Co = Co; w.B = B;
+        w.g_parity = g_parity;
+        // the checkerboard shortcut needs a consistent wrap (even sides); otherwise sum densely
+        const bool sparse = g_parity >= 0 && lat.shape[0] % 2 == 0 && lat.shape[1] % 2 == 0;
         int rc;
-        if (Ci == 1) rc = wgrad2d_launch<1, 8>(w, NFK_STREAM(stream));
-        else if (Co <= 8) rc = wgrad2d_launch<8, 8>(w, NFK_STREAM(stream));
-        else rc = wgrad2d_launch<8, 7>(w, NFK_STREAM(stream));
+        if (Ci == 1) rc = wgrad2d_launch<1, 8, false>(w, NFK_STREAM(stream));
+        else if (Co <= 8) rc = sparse ? wgrad2d_launch<8, 8, true>(w, NFK_STREAM(stream))
+                                      : wgrad2d_launch<8, 8, false>(w, NFK_STREAM(stream));
+        else rc = sparse ? wgrad2d_launch<8, 7, true>(w, NFK_STREAM(stream))
+                         : wgrad2d_launch<8, 7, false>(w, NFK_STREAM(stream));
         if (rc != NFK_EUNSUPPORTED) return rc;
     }
     ConvWArgs a;
