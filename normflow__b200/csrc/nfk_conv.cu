@@ -322,6 +322,137 @@ static int wgrad2d_launch(Wgrad2dArgs a, cudaStream_t st) {
     return check_launch();
 }
 
+// The same kernel with the strips streamed by cp.async into TWO shared-memory buffers: while the
+// warps accumulate strip i, the copies of strip i+1 are in flight (the synchronous version spends
+// more than half of its time staging).  Needs 16-byte aligned rows (L1 % 4 == 0) and no input mask.
+//   in_s row: [.. 3 pad | col -1 | cols 0..L1-1 (16-byte aligned) | col L1 | pad ..], stride L1 + 8
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool live) {
+    const int sz = live ? 16 : 0;                    // src-size 0: the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(src) : "memory");
+}
+
+template <int CI, int CO_B, bool SPARSE>
+__global__ void __launch_bounds__(288, 2) conv2d_wgrad_async_kernel(Wgrad2dArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const int L0 = a.L0, L1 = a.L1, R = a.R, LW = L1 + 8;
+    const int in_floats = CI * (R + 2) * LW, buf_floats = in_floats + CO_B * R * L1;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int kh = warp / 3, kw = warp % 3;
+    const int co0 = blockIdx.y * CO_B;
+    const int V = L0 * L1, nq = L1 >> 2;
+    const int strips = (L0 + R - 1) / R;
+    float acc[CO_B][CI];
+    float accb[CO_B];
+#pragma unroll
+    for (int co = 0; co < CO_B; ++co) {
+        accb[co] = 0.f;
+#pragma unroll
+        for (int ci = 0; ci < CI; ++ci) acc[co][ci] = 0.f;
+    }
+    const long long n_mine = a.B > blockIdx.x ? (a.B - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long units = n_mine * strips;
+
+    auto stage = [&](long long u, float* buf) {
+        const long long b = blockIdx.x + (u / strips) * gridDim.x;
+        const int r0 = (int)(u % strips) * R;
+        const int rows = L0 - r0 < R ? L0 - r0 : R;
+        const float* in_b = a.in + b * (long long)CI * V;
+        const float* g_b = a.gpre + (b * a.Co + co0) * (long long)V;
+        const uint32_t in_u = (uint32_t)__cvta_generic_to_shared(buf), g_u = in_u + in_floats * 4;
+        for (int p = warp; p < CI * (rows + 2); p += 9) {
+            const int ci = p / (rows + 2), j = p - ci * (rows + 2);
+            int r = r0 - 1 + j;
+            r = r < 0 ? r + L0 : (r >= L0 ? r - L0 : r);
+            const float* src = in_b + ci * V + r * L1;
+            const uint32_t dst = in_u + (uint32_t)((ci * (R + 2) + j) * LW) * 4;
+            for (int q = lane; q < nq; q += 32) cp_async16(dst + 16 + q * 16, src + q * 4, true);
+            if (lane == 0) cp_async4(dst + 12, src + L1 - 1);             // column -1
+            if (lane == 1) cp_async4(dst + 16 + L1 * 4, src);             // column L1
+        }
+        for (int p = warp; p < CO_B * rows; p += 9) {
+            const int co = p / rows, j = p - co * rows;
+            const bool live = co0 + co < a.Co;
+            const float* src = g_b + (long long)(live ? co : 0) * V + (r0 + j) * L1;
+            const uint32_t dst = g_u + (uint32_t)((co * R + j) * L1) * 4;
+            for (int q = lane; q < nq; q += 32) cp_async16(dst + q * 16, src + q * 4, live);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    if (units > 0) stage(0, sm);
+    for (long long u = 0; u < units; ++u) {
+        float* buf = sm + (u & 1) * buf_floats;
+        if (u + 1 < units) {
+            stage(u + 1, sm + ((u + 1) & 1) * buf_floats);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();                                                  // strip u has landed for everyone
+        const float* in_s = buf;
+        const float* g_s = buf + in_floats;
+        const int r0 = (int)(u % strips) * R;
+        const int rows = L0 - r0 < R ? L0 - r0 : R;
+        for (int j = 0; j < rows; ++j)
+            for (int cc = lane; cc < (SPARSE ? L1 / 2 : L1); cc += 32) {
+                const int c = SPARSE ? 2 * cc + ((a.g_parity + r0 + j) & 1) : cc;
+                float gv[CO_B], xv[CI];
+#pragma unroll
+                for (int co = 0; co < CO_B; ++co) gv[co] = g_s[(co * R + j) * L1 + c];
+#pragma unroll
+                for (int ci = 0; ci < CI; ++ci) xv[ci] = in_s[(ci * (R + 2) + j + kh) * LW + 3 + c + kw];
+#pragma unroll
+                for (int co = 0; co < CO_B; ++co) {
+#pragma unroll
+                    for (int ci = 0; ci < CI; ++ci) acc[co][ci] = fmaf(gv[co], xv[ci], acc[co][ci]);
+                }
+                if (warp == 4) {
+#pragma unroll
+                    for (int co = 0; co < CO_B; ++co) accb[co] += gv[co];
+                }
+            }
+        __syncthreads();                                                  // buffer free for the copies of strip u + 2
+    }
+#pragma unroll
+    for (int co = 0; co < CO_B; ++co) {
+#pragma unroll
+        for (int ci = 0; ci < CI; ++ci) {
+            const float v = warp_sum(acc[co][ci]);
+            if (lane == 0 && co0 + co < a.Co)
+                atomicAdd(a.gw + ((long long)(co0 + co) * CI + ci) * 9 + kh * 3 + kw, v);
+        }
+        if (warp == 4 && a.gbias) {
+            const float v = warp_sum(accb[co]);
+            if (lane == 0 && co0 + co < a.Co) atomicAdd(a.gbias + co0 + co, v);
+        }
+    }
+}
+
+template <int CI, int CO_B, bool SPARSE>
+static int wgrad2d_async_launch(Wgrad2dArgs a, cudaStream_t st) {
+    const int LW = a.L1 + 8;
+    auto bytes = [&](int r) { return 2 * (size_t)(CI * (r + 2) * LW + CO_B * r * a.L1) * sizeof(float); };
+    int R = a.L0 < 16 ? a.L0 : 16;
+    while (R > 1 && bytes(R) > 100 * 1024) R /= 2;                        // two CTAs per SM
+    if (bytes(R) > 100 * 1024) return NFK_EUNSUPPORTED;
+    a.R = R;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(conv2d_wgrad_async_kernel<CI, CO_B, SPARSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             100 * 1024);
+        attr_set = true;
+    }
+    const int ncb = (a.Co + CO_B - 1) / CO_B;
+    long long gx = (148LL * 2 + ncb - 1) / ncb;
+    if (gx > a.B) gx = a.B;
+    if (gx < 1) gx = 1;
+    conv2d_wgrad_async_kernel<CI, CO_B, SPARSE><<<dim3((unsigned)gx, ncb), 288, bytes(R), st>>>(a);
+    return check_launch();
+}
+
 static int conv_bwd_weight_impl(const float* in, const uint8_t* in_mask, int in_keep, const float* gpre,
                                 int g_parity, float* gw, float* gbias, nfk_lattice lat, int ksize, int Ci, int Co,
                                 int64_t B, void* stream);
@@ -349,7 +480,16 @@ static int conv_bwd_weight_impl(const float* in, const uint8_t* in_mask, int in_
         w.g_parity = g_parity;
         // the checkerboard shortcut needs a consistent wrap (even sides); otherwise sum densely
         const bool sparse = g_parity >= 0 && lat.shape[0] % 2 == 0 && lat.shape[1] % 2 == 0;
-        int rc;
+        int rc = NFK_EUNSUPPORTED;
+        const bool async_ok = Ci == 8 && !in_mask && lat.shape[1] % 4 == 0 && ((uintptr_t)in % 16) == 0 &&
+                              ((uintptr_t)gpre % 16) == 0;
+        if (async_ok) {                                       // strips streamed with cp.async, double-buffered
+            if (Co <= 8) rc = sparse ? wgrad2d_async_launch<8, 8, true>(w, NFK_STREAM(stream))
+                                     : wgrad2d_async_launch<8, 8, false>(w, NFK_STREAM(stream));
+            else rc = sparse ? wgrad2d_async_launch<8, 7, true>(w, NFK_STREAM(stream))
+                             : wgrad2d_async_launch<8, 7, false>(w, NFK_STREAM(stream));
+            if (rc != NFK_EUNSUPPORTED) return rc;
+        }
         if (Ci == 1) rc = wgrad2d_launch<1, 8, false>(w, NFK_STREAM(stream));
         else if (Co <= 8) rc = sparse ? wgrad2d_launch<8, 8, true>(w, NFK_STREAM(stream))
                                       : wgrad2d_launch<8, 8, false>(w, NFK_STREAM(stream));
