@@ -128,7 +128,9 @@ def dev(t, dtype=torch.float32, name="tensor"):
 
 
 def stream():
-    return torch.cuda.current_stream().cuda_stream
+    """Raw handle of torch's current CUDA stream on the current device (the C-level getters:
+    `torch.cuda.current_stream()` costs ~15 us of Python per call)."""
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 # ---------------------------------------------------------------------------

@@ -5,6 +5,7 @@ stream; tensors are only the memory they work on.  Nothing in this file computes
 the host and nothing falls back to eager PyTorch: a CPU tensor raises.
 """
 
+import functools
 import numbers
 
 import numpy as np
@@ -12,6 +13,19 @@ import torch
 
 from . import _C
 from ._C import dev, stream, check, lib
+
+
+def _native(fn):
+    """Run an op wrapper with __torch_function__ dispatch switched off.  Importing the package makes
+    CUDA the default device (as the reference does), which installs a Python-level function mode
+    that every torch call -- `.is_contiguous()`, `.data_ptr()`, `torch.empty` ... -- is routed
+    through; the wrappers make a few dozen such calls per kernel launch and pass `device=`
+    explicitly, so inside them the mode is pure overhead (it dominated the latency-bound configs)."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        with torch._C.DisableTorchFunction():
+            return fn(*args, **kwargs)
+    return wrapper
 
 
 def _f32c(t, name):
@@ -54,6 +68,7 @@ def _no_grad_needed(*tensors):
 # ---------------------------------------------------------------------------- masks
 class _MaskSelect(torch.autograd.Function):
     @staticmethod
+    @_native
     def forward(ctx, x, mask, keep):
         x = _f32c(x, "x")
         y = torch.empty_like(x)
@@ -64,15 +79,18 @@ class _MaskSelect(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_native
     def backward(ctx, gy):
         return _MaskSelect.apply(gy, ctx.mask, ctx.keep), None, None
 
 
+@_native
 def mask_select(x, mask, keep):
     """Mask.split / purify: x where mask == keep, 0 elsewhere (mask/mask.py:30-37)."""
     return _MaskSelect.apply(x, _mask_u8(mask), int(keep))
 
 
+@_native
 def make_evenodd_mask(shape, parity, exclude_mu, device):
     m = torch.empty(tuple(shape), dtype=torch.uint8, device=device)
     check(lib().nfk_mask_evenodd(dev(m, torch.uint8), _C.lattice(shape), int(parity),
@@ -80,6 +98,7 @@ def make_evenodd_mask(shape, parity, exclude_mu, device):
     return m
 
 
+@_native
 def make_alongaxis_mask(shape, parity, mu, device):
     m = torch.empty(tuple(shape), dtype=torch.uint8, device=device)
     check(lib().nfk_mask_alongaxis(dev(m, torch.uint8), _C.lattice(shape), int(parity), int(mu), stream()),
@@ -88,6 +107,7 @@ def make_alongaxis_mask(shape, parity, mu, device):
 
 
 # ---------------------------------------------------------------------------- prior
+@_native
 def prior_sample(batch_size, shape, loc, scale, seed, offset, device, with_logprob=True):
     """x = loc + scale * N(0,1) and (optionally) its log-density summed per sample."""
     shape = tuple(int(v) for v in shape)
@@ -101,6 +121,7 @@ def prior_sample(batch_size, shape, loc, scale, seed, offset, device, with_logpr
     return x, logr
 
 
+@_native
 def prior_logprob(x, loc, scale):
     x = _f32c(x, "x")
     B = x.shape[0]
@@ -118,6 +139,7 @@ def _bv(x):
 
 class _AffineFwd(torch.autograd.Function):
     @staticmethod
+    @_native
     def forward(ctx, x, out, log_in, mask, parity, frozen_mode):
         x, out = _f32c(x, "x"), _f32c(out, "conditioner output")
         B, V = _bv(x)
@@ -132,6 +154,7 @@ class _AffineFwd(torch.autograd.Function):
         return y, log_out
 
     @staticmethod
+    @_native
     def backward(ctx, gy, glog):
         x, out, mask = ctx.saved_tensors
         parity, frozen_mode, has_log = ctx.cfg
@@ -143,6 +166,7 @@ class _AffineFwd(torch.autograd.Function):
         return gx, gout, (glog if has_log else None), None, None, None
 
 
+@_native
 def affine_apply(x, out, mask, parity, log0=0, frozen_mode=_C.FROZEN_COPY, inverse=False):
     """AffineCoupling_.atomic_forward/backward (couplings_.py:123-139)."""
     mask = _mask_u8(mask)
@@ -161,6 +185,7 @@ def affine_apply(x, out, mask, parity, log0=0, frozen_mode=_C.FROZEN_COPY, inver
 
 class _Shift(torch.autograd.Function):
     @staticmethod
+    @_native
     def forward(ctx, x, out, mask, parity, frozen_mode, sign):
         x, out = _f32c(x, "x"), _f32c(out, "conditioner output")
         B, V = _bv(x)
@@ -174,6 +199,7 @@ class _Shift(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_native
     def backward(ctx, gy):
         parity, frozen_mode, sign, oshape = ctx.cfg
         gy = _f32c(gy, "gy")
@@ -183,6 +209,7 @@ class _Shift(torch.autograd.Function):
         return gx, (sign * g_act).reshape(oshape), None, None, None, None
 
 
+@_native
 def shift_apply(x, out, mask, parity, frozen_mode=_C.FROZEN_COPY, inverse=False):
     """ShiftCoupling_.atomic_forward/backward (couplings_.py:110-116)."""
     return _Shift.apply(x, out, _mask_u8(mask), int(parity), int(frozen_mode), -1.0 if inverse else 1.0)
@@ -201,6 +228,7 @@ def rqs_params(n_knots, xlim, ylim, extrap):
 
 class _RqsFwd(torch.autograd.Function):
     @staticmethod
+    @_native
     def forward(ctx, x, out, log_in, mask, parity, frozen_mode, prm):
         x, out = _f32c(x, "x"), _f32c(out, "conditioner output")
         B, V = _bv(x)
@@ -217,6 +245,7 @@ class _RqsFwd(torch.autograd.Function):
         return y, log_out
 
     @staticmethod
+    @_native
     def backward(ctx, gy, glog):
         x, out, mask = ctx.saved_tensors
         parity, frozen_mode, prm, has_log = ctx.cfg
@@ -229,6 +258,7 @@ class _RqsFwd(torch.autograd.Function):
         return gx, gout, (glog if has_log else None), None, None, None, None
 
 
+@_native
 def rqs_apply(x, out, mask, parity, prm, log0=0, frozen_mode=_C.FROZEN_COPY, inverse=False):
     """RQSplineCoupling_.atomic_forward/backward incl. make_spline (couplings_.py:178-262)."""
     mask = _mask_u8(mask)
@@ -248,6 +278,7 @@ def rqs_apply(x, out, mask, parity, prm, log0=0, frozen_mode=_C.FROZEN_COPY, inv
 # ---------------------------------------------------------------------------- pointwise chains
 class _Logistic(torch.autograd.Function):
     @staticmethod
+    @_native
     def forward(ctx, x, log_in, which):
         x = _f32c(x, "x")
         B, V = _bv(x)
@@ -260,6 +291,7 @@ class _Logistic(torch.autograd.Function):
         return y, log_out
 
     @staticmethod
+    @_native
     def backward(ctx, gy, glog):
         (x,) = ctx.saved_tensors
         which, has_log = ctx.cfg
@@ -270,6 +302,7 @@ class _Logistic(torch.autograd.Function):
         return gx, (glog if has_log else None), None
 
 
+@_native
 def logistic(x, which, log0=0):
     """Expit_ (which=0) / Logit_ (which=1) forward with log-Jacobian (modules_.py:93-114)."""
     return _Logistic.apply(x, as_log(log0, x), int(which))
@@ -280,6 +313,7 @@ class _Spline1d(torch.autograd.Function):
     complements cx = x_hi - kx and cy = y_hi - ky appended."""
 
     @staticmethod
+    @_native
     def forward(ctx, x, knots, log_in, left, right, logistic_wrap):
         x, knots = _f32c(x, "x"), _f32c(knots, "knots")
         K = knots.shape[1]
@@ -293,6 +327,7 @@ class _Spline1d(torch.autograd.Function):
         return y, log_out
 
     @staticmethod
+    @_native
     def backward(ctx, gy, glog):
         x, knots = ctx.saved_tensors
         left, right, logistic_wrap, has_log = ctx.cfg
@@ -314,6 +349,7 @@ def _check_knots(knots, logistic_wrap):
         raise ValueError("spline1d supports 2..64 knots")
 
 
+@_native
 def spline1d(x, knots, log0=0, extrap=None, logistic_wrap=False, inverse=False):
     """One shared 1-D RQ spline over every element (SplineNet_), optionally wrapped as
     Expit_ -> spline -> Logit_ (DistConvertor_) in a single kernel.  `knots` is the
@@ -337,6 +373,7 @@ def spline1d(x, knots, log0=0, extrap=None, logistic_wrap=False, inverse=False):
 # ---------------------------------------------------------------------------- action
 class _Phi4(torch.autograd.Function):
     @staticmethod
+    @_native
     def forward(ctx, phi, w0, w2, w4):
         phi = _f32c(phi, "cfgs")
         B = phi.shape[0]
@@ -349,6 +386,7 @@ class _Phi4(torch.autograd.Function):
         return S
 
     @staticmethod
+    @_native
     def backward(ctx, gS):
         (phi,) = ctx.saved_tensors
         lat, w0, w2, w4 = ctx.cfg
@@ -359,6 +397,7 @@ class _Phi4(torch.autograd.Function):
         return gphi, None, None, None
 
 
+@_native
 def phi4_action(cfgs, w0, w2, w4):
     """ScalarPhi4Action.action (scalar_action.py:38-46)."""
     if cfgs.ndim < 2:
@@ -405,6 +444,7 @@ class _ConvStack(torch.autograd.Function):
     """
 
     @staticmethod
+    @_native
     def forward(ctx, inp, in_mask, in_keep, acts, ksize, n_layers, *params):
         inp = _f32c(inp, "conditioner input")
         weights, biases = params[:n_layers], params[n_layers:]
@@ -423,6 +463,7 @@ class _ConvStack(torch.autograd.Function):
         return hs[-1]
 
     @staticmethod
+    @_native
     def backward(ctx, gout):
         in_keep, acts, ksize, n, shape, has_bias, has_mask = ctx.cfg
         saved = ctx.saved_tensors
@@ -463,6 +504,7 @@ def _conv_stack_backward(hs, weights, has_bias, acts, ksize, shape, in_mask, in_
     return gws, gbs, gin
 
 
+@_native
 def conv_stack(inp, weights, biases, acts, ksize, in_mask=None, in_keep=0):
     """ConvAct forward: (B,Ci,*L) -> (B,Co,*L), circular 'same' convs with fused
     activations; `in_mask`/`in_keep` fuse Mask.split into the first layer."""
@@ -485,6 +527,7 @@ def fused2d_supported(L0, L1, n_knots=None):
     return bool(tc or cc)
 
 
+@_native
 def fused2d_step(x, weights, biases, kind, prm, mask_parity, parity, log0=0, inverse=False):
     """A whole atomic coupling step (ConvAct(1->8->8->P) conditioner + affine / RQ-spline
     transform) in one kernel, forward evaluation only.  x: (B, L0, L1); returns (y, log)."""
@@ -514,6 +557,7 @@ class _FusedStepTrain(torch.autograd.Function):
     the convolution gradient kernels -- the conditioner is never evaluated layer by layer."""
 
     @staticmethod
+    @_native
     def forward(ctx, x, log_in, mask, kind, prm, mask_parity, parity, n_bias, *params):
         w, b = params[:3], params[3:]
         B, L0, L1 = x.shape
@@ -532,6 +576,7 @@ class _FusedStepTrain(torch.autograd.Function):
         return y, log_out
 
     @staticmethod
+    @_native
     def backward(ctx, gy, glog):
         x, h1, h2, out, mask, *w = ctx.saved_tensors
         kind, prm, parity, mask_parity, has_log, has_bias = ctx.cfg
@@ -565,6 +610,7 @@ def fused2d_train_supported(L0, L1, n_knots=None):
             and (n_knots is None or n_knots in FUSED2D_TC_KNOTS))
 
 
+@_native
 def fused2d_step_train(x, weights, biases, kind, prm, mask, mask_parity, parity, log0=0):
     """Differentiable atomic coupling step: fused forward, kernel-by-kernel backward."""
     x = _f32c(x, "x")
@@ -578,6 +624,7 @@ def fused2d_step_train(x, weights, biases, kind, prm, mask, mask_parity, parity,
 
 
 # ---------------------------------------------------------------------------- mcmc
+@_native
 def metropolis_scan(logq, logp, log_u, ref_state):
     """Sequential accept/reject on the device (mcmc.py:304-328).  `ref_state` is a
     float64[2] CUDA tensor {ref, has_ref}, updated in place.  Returns
@@ -593,6 +640,7 @@ def metropolis_scan(logq, logp, log_u, ref_state):
     return accept, idx, n_acc
 
 
+@_native
 def gather_rows(src, idx, prev=None):
     """dst[i] = src[idx[i]] (idx >= 0) or prev (idx < 0)  (mcmc.py:67-75)."""
     src = _f32c(src, "src")
