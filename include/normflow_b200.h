@@ -103,6 +103,12 @@ int nfk_mask_select(const float* x, const uint8_t* mask, int keep, float* y,
 int nfk_prior_normal_sample(float* x, float* logr, int64_t B, int64_t V,
                             const float* loc, const float* scale,
                             uint64_t seed, uint64_t offset, void* stream);
+/* The same draw with the generator state in device memory: state[0] = Philox key (seed),
+ * state[1] = stream offset, advanced by one on the stream after the draw -- the form that can
+ * be captured in a CUDA graph (every replay draws a fresh batch).                          */
+int nfk_prior_normal_sample_dev(float* x, float* logr, int64_t B, int64_t V,
+                                const float* loc, const float* scale,
+                                uint64_t* state, void* stream);
 int nfk_prior_normal_logprob(const float* x, float* logr, int64_t B, int64_t V,
                              const float* loc, const float* scale, void* stream);
 

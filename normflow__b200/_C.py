@@ -41,6 +41,7 @@ _SIGNATURES = {
     "nfk_mask_alongaxis": [c_f, Lattice, c_i, c_i, c_f],
     "nfk_mask_select": [c_f, c_f, c_i, c_f, c_l, c_l, c_f],
     "nfk_prior_normal_sample": [c_f, c_f, c_l, c_l, c_f, c_f, c_u64, c_u64, c_f],
+    "nfk_prior_normal_sample_dev": [c_f, c_f, c_l, c_l, c_f, c_f, c_f, c_f],
     "nfk_prior_normal_logprob": [c_f, c_f, c_l, c_l, c_f, c_f, c_f],
     "nfk_affine_fwd": [c_f, c_f, c_f, c_i, c_i, c_f, c_f, c_f, c_l, c_l, c_f],
     "nfk_affine_inv": [c_f, c_f, c_f, c_i, c_i, c_f, c_f, c_f, c_l, c_l, c_f],

@@ -91,6 +91,10 @@ class Fitter:
         self.hyperparam = dict(lr=0.001, weight_decay=0.01)
         self.checkpoint_dict = dict(display=False, print_stride=100, print_batch_size=1024,
                                     print_extra_func=None, snapshot_path=None, epochs_run=0)
+        # Opt-in: replay the whole optimisation step (draw, flow, action, backward, optimiser) as ONE
+        # captured CUDA graph.  For small lattices the step is pure launch latency (tens of kernels of
+        # a few microseconds each); see _train_graph.  Also switched on by NFK_CUDA_GRAPH=1.
+        self.cuda_graph = os.environ.get('NFK_CUDA_GRAPH') == '1'
 
     def __call__(self, n_epochs=1000, save_every=None, batch_size=64,
                  optimizer_class=torch.optim.AdamW, scheduler=None, loss_fn=None,
@@ -122,9 +126,24 @@ class Fitter:
 
         # (the reference's test for parameter groups, `'_groups' is net_.__dict__.keys()`,
         # is never true, so it always optimises net_.parameters(); kept that way)
-        self.optimizer = optimizer_class(self._model.net_.parameters(), **self.hyperparam)
+        hyper = dict(self.hyperparam)
+        self._graph_ok = self._graph_mode_possible(optimizer_class, scheduler, hyper)
+        if self._graph_ok:
+            hyper['fused'] = True       # one kernel over all parameters; honours the device-side NaN guard
+            hyper['capturable'] = True  # step counters live on the device
+        self.optimizer = optimizer_class(self._model.net_.parameters(), **hyper)
         self.scheduler = None if scheduler is None else scheduler(self.optimizer)
         return self.train(n_epochs, batch_size, save_every)
+
+    def _graph_mode_possible(self, optimizer_class, scheduler, hyper):
+        """Graph mode needs: the switch, one rank, CUDA parameters, no scheduler (a captured step has
+        its learning rate baked in) and an optimiser with a fused, capturable implementation."""
+        if not self.cuda_graph or scheduler is not None or self._model.device_handler.nranks != 1:
+            return False
+        if optimizer_class not in (torch.optim.AdamW, torch.optim.Adam) or 'fused' in hyper or 'capturable' in hyper:
+            return False
+        params = list(self._model.net_.parameters())
+        return bool(params) and all(p.is_cuda for p in params)
 
     # ---- snapshots ({"MODEL_STATE", "EPOCHS_RUN"}, reference :221-247) -------------
     def _load_snapshot(self):
@@ -155,13 +174,84 @@ class Fitter:
         self.train_batch_size = batch_size
         t_start = time.time()
         loss = None
-        for epoch in range(1, n_epochs + 1):
-            loss, _ = self.step()
+        n_eager = n_epochs
+        if getattr(self, '_graph_ok', False) and n_epochs > self._GRAPH_WARMUP:
+            n_eager = self._GRAPH_WARMUP          # the first steps run eagerly: they are the graph's warm-up
+        for epoch in range(1, n_eager + 1):
+            loss = self.step()[0]
             self.checkpoint(epoch, loss, save_every)
             if self.scheduler is not None:
                 self.scheduler.step()
+        if n_eager < n_epochs:
+            # drop the eager autograd graph first: its AccumulateGrad nodes are tied to the stream the
+            # eager steps ran on, and a capture may not depend on the legacy default stream
+            loss = None
+            loss = self._train_graph(n_eager + 1, n_epochs, save_every)
         if n_epochs > 0 and self._model.device_handler.rank == 0:
             print(f"({loss.device}) Time = {time.time() - t_start:.3g} sec.")
+
+    _GRAPH_WARMUP = 3
+
+    def _train_graph(self, first_epoch, n_epochs, save_every):
+        """Epochs first_epoch..n_epochs as replays of one captured CUDA graph of `step`.
+
+        What makes the step capturable: every kernel of this package is enqueued on the current
+        stream without host synchronisation; the prior keeps its Philox state on the device
+        (`NormalPrior.use_device_state`), so each replay draws a fresh batch; the reference's
+        host-side `if isnan(loss)` becomes the fused optimiser's `found_inf` flag (the update is
+        skipped on the device); the loss of every epoch goes to a device buffer that is read back
+        only when something is printed or saved."""
+        model = self._model
+        dev = next(model.net_.parameters()).device
+        model.prior.use_device_state(True)
+        n_graph = n_epochs - first_epoch + 1
+        loss_buf = torch.zeros(n_graph, dtype=torch.float32, device=dev)
+        slot = torch.zeros(1, dtype=torch.int64, device=dev)
+        found_inf = torch.zeros((), dtype=torch.float32, device=dev)
+        n_skipped = torch.zeros((), dtype=torch.float32, device=dev)
+        self.optimizer.found_inf = found_inf
+
+        def body():
+            x, logr = model.prior.sample_(self.train_batch_size)
+            y, logJ = model.net_(x)
+            loss = self.loss_fn(logr - logJ, -model.action(y))
+            loss.backward()
+            found_inf.copy_(1.0 - torch.isfinite(loss.detach()).to(torch.float32))
+            n_skipped.add_(found_inf)
+            self.optimizer.step()                       # no-op on the device when found_inf is set
+            loss_buf.index_copy_(0, slot, loss.detach().reshape(1))
+            slot.add_(1)
+            return loss
+
+        self.optimizer.zero_grad(set_to_none=True)      # gradients get allocated inside the graph's pool
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_loss = body()
+        # (capturing does not execute: epoch `first_epoch` is the first replay)
+        flushed = 0
+
+        def flush(upto):                                # device losses -> train_history (one sync)
+            nonlocal flushed
+            if upto > flushed and model.device_handler.rank == 0:
+                self.train_history['loss'].extend(loss_buf[flushed:upto].tolist())
+            flushed = max(flushed, upto)
+
+        print_stride = self.checkpoint_dict['print_stride']
+        snapshot_path = self.checkpoint_dict['snapshot_path']
+        for epoch in range(first_epoch, n_epochs + 1):
+            graph.replay()
+            diag = epoch == 1 or epoch == 10 or epoch % print_stride == 0
+            save = snapshot_path is not None and epoch % save_every == 0
+            if diag or save:
+                flush(epoch - first_epoch + 1)
+                self._checkpoint_tail(epoch, save_every)
+        flush(n_graph)
+        skipped = int(n_skipped.item())
+        if skipped:
+            print(f"OOPS: loss was divergent in {skipped} step(s) -> no *step* was taken there.")
+        del self.optimizer.found_inf
+        return static_loss.detach()
 
     def step(self):
         """One optimisation step on a fresh batch (reference Fitter.step, :275-294)."""
@@ -190,8 +280,17 @@ class Fitter:
 
         if rank == 0:
             self.train_history['loss'].append(loss.item())
-            if snapshot_path is not None and (epoch % save_every == 0):
-                self._save_snapshot(epoch)
+        self._checkpoint_tail(epoch, save_every)
+
+    def _checkpoint_tail(self, epoch, save_every):
+        """Snapshot and diagnostics of an epoch whose loss is already in train_history."""
+        handler = self._model.device_handler
+        rank = handler.rank
+        print_stride = self.checkpoint_dict['print_stride']
+        print_batch_size = self.checkpoint_dict['print_batch_size'] // handler.nranks
+        snapshot_path = self.checkpoint_dict['snapshot_path']
+        if rank == 0 and snapshot_path is not None and (epoch % save_every == 0):
+            self._save_snapshot(epoch)
 
         if epoch == 1 or epoch == 10 or (epoch % print_stride == 0):
             _, logq, logp = self._model.posterior.sample__(print_batch_size)

@@ -108,12 +108,19 @@ def make_alongaxis_mask(shape, parity, mu, device):
 
 # ---------------------------------------------------------------------------- prior
 @_native
-def prior_sample(batch_size, shape, loc, scale, seed, offset, device, with_logprob=True):
-    """x = loc + scale * N(0,1) and (optionally) its log-density summed per sample."""
+def prior_sample(batch_size, shape, loc, scale, seed, offset, device, with_logprob=True, state=None):
+    """x = loc + scale * N(0,1) and (optionally) its log-density summed per sample.
+    `state`: int64[2] CUDA tensor {seed, offset} -- the generator state kept on the device and
+    advanced by the draw (CUDA-graph capturable); otherwise `seed` / `offset` are host integers."""
     shape = tuple(int(v) for v in shape)
     V = int(np.prod(shape)) if len(shape) else 1
     x = torch.empty((batch_size,) + shape, dtype=torch.float32, device=device)
     logr = torch.empty((batch_size,), dtype=torch.float32, device=device) if with_logprob else None
+    if state is not None:
+        with _C.timed("prior_normal_sample"):
+            check(lib().nfk_prior_normal_sample_dev(dev(x), dev(logr), batch_size, V, dev(loc), dev(scale),
+                                                    dev(state, torch.int64), stream()), "prior_normal_sample_dev")
+        return x, logr
     with _C.timed("prior_normal_sample"):
         check(lib().nfk_prior_normal_sample(dev(x), dev(logr), batch_size, V, dev(loc), dev(scale),
                                             int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1), stream()),

@@ -54,8 +54,23 @@ extern "C" int nfk_prior_normal_sample(float* x, float* logr, int64_t B, int64_t
                                        const float* loc, const float* scale,
                                        uint64_t seed, uint64_t offset, void* stream) {
     if (!x) return NFK_EINVAL;
-    return launch_sites_vec<PriorSampleOp, 4>(PriorSampleOp{x, loc, scale, V, seed, offset}, B, V,
+    return launch_sites_vec<PriorSampleOp, 4>(PriorSampleOp{x, loc, scale, V, seed, offset, nullptr}, B, V,
                                               nullptr, logr, NFK_STREAM(stream));
+}
+
+// The same draw with the Philox key and stream offset read from DEVICE memory, and the offset
+// advanced by a one-thread kernel behind it: a captured CUDA graph then draws fresh numbers at
+// every replay (host-side (seed, offset) arguments would be frozen into the graph).
+static __global__ void advance_offset_kernel(uint64_t* state) { state[1] += 1; }
+extern "C" int nfk_prior_normal_sample_dev(float* x, float* logr, int64_t B, int64_t V,
+                                           const float* loc, const float* scale,
+                                           uint64_t* state, void* stream) {
+    if (!x || !state) return NFK_EINVAL;
+    const int rc = launch_sites_vec<PriorSampleOp, 4>(PriorSampleOp{x, loc, scale, V, 0, 0, state}, B, V,
+                                                      nullptr, logr, NFK_STREAM(stream));
+    if (rc != NFK_OK) return rc;
+    advance_offset_kernel<<<1, 1, 0, NFK_STREAM(stream)>>>(state);
+    return check_launch();
 }
 extern "C" int nfk_prior_normal_logprob(const float* x, float* logr, int64_t B, int64_t V,
                                         const float* loc, const float* scale, void* stream) {

@@ -79,10 +79,12 @@ struct PriorSampleOp {
     const float* scale;
     int64_t V;
     uint64_t seed, offset;
+    const uint64_t* state;    // device {seed, offset} (overrides the two values above) or null
     // sites [s, s+n), n <= 4, s % 4 == 0
     NFK_HD float operator()(int64_t b, int64_t s, int n) const {
         const uint64_t quads = (uint64_t)((V + 3) / 4);
-        const Philox r = philox4x32_10((uint64_t)b * quads + (uint64_t)(s >> 2), offset, seed);
+        const uint64_t sd = state ? NFK_LDG(state) : seed, of = state ? NFK_LDG(state + 1) : offset;
+        const Philox r = philox4x32_10((uint64_t)b * quads + (uint64_t)(s >> 2), of, sd);
         float z[4];
         box_muller(r.c[0], r.c[1], z[0], z[1]);
         box_muller(r.c[2], r.c[3], z[2], z[3]);

@@ -57,7 +57,20 @@ class NormalPrior(Prior):
         self._loc = loc.to(torch.float32).contiguous()
         self._scale = scale.to(torch.float32).contiguous()
         self._calls = 0          # Philox stream offset: one stream per draw
+        self._state = None       # device-resident {seed, offset}: see use_device_state()
         Prior.manual_seed(seed)
+
+    def use_device_state(self, enable=True):
+        """Keep the generator state (Philox key, stream offset) in device memory, advanced by every
+        draw on the stream.  Needed when draws are captured in a CUDA graph (Fitter's graph mode):
+        host-side offsets would be frozen into the graph and every replay would repeat the batch."""
+        if not enable:
+            self._state = None
+        elif self._state is None:
+            if not self._loc.is_cuda:
+                raise RuntimeError("NormalPrior.use_device_state: move the prior to CUDA first")
+            seed = torch.initial_seed() & (2 ** 63 - 1)
+            self._state = torch.tensor([seed, self._calls + 1], dtype=torch.int64, device=self._loc.device)
 
     # the reference exposes the torch distribution object as `.dist`
     @property
@@ -75,6 +88,9 @@ class NormalPrior(Prior):
                                ".to('cuda') (normflow__b200 has no CPU fallback)")
         loc, scale = self._args()
         self._calls += 1
+        if self._state is not None:
+            return _ops.prior_sample(int(batch_size), self.shape, loc, scale, 0, 0, self._loc.device,
+                                     with_logprob=with_logprob, state=self._state)
         return _ops.prior_sample(int(batch_size), self.shape, loc, scale,
                                  seed=torch.initial_seed(), offset=self._calls,
                                  device=self._loc.device, with_logprob=with_logprob)
@@ -105,6 +121,8 @@ class NormalPrior(Prior):
         kwargs = {k: v for k, v in kwargs.items() if not (k == 'dtype' and v is None)}
         self._loc = self._loc.to(*args, **kwargs)
         self._scale = self._scale.to(*args, **kwargs)
+        if self._state is not None and self._state.device != self._loc.device:
+            self._state = self._state.to(self._loc.device) if self._loc.is_cuda else None
 
     @property
     def parameters(self):
