@@ -465,20 +465,45 @@ NFK_HD int tap_neighbor(const Lat& lat, int s, const int* c, int t, int ksize) {
     return n;
 }
 
-// acc[co] += sum_{ci,t} w[(ci*T + t)*CO + co] * in[b][ci][nbr(s,t)]   for one site
+// acc[co] += sum_{ci,t} w[(ci*T + t)*CO + co] * in[b][ci][nbr(s,t)]   for one site.
+// The taps are walked as four nested loops (unused dimensions have one tap), each level keeping
+// its periodic coordinate incrementally: one modulo per level and site instead of ndim per tap,
+// which is what made the 27- and 81-tap (3-D, 4-D) convolutions index-bound.  Tap order = the
+// weight layout: last dimension fastest.
 template <int CO>
 NFK_HD void conv_site(const float* in_b, const float* wt, const uint8_t* in_mask, int in_keep,
                       const Lat& lat, int s, int Ci, int T, int ksize, int64_t V, float* acc) {
     int c[4];
     site_coords(lat, s, c);
-    for (int t = 0; t < T; ++t) {
-        const int n = tap_neighbor(lat, s, c, t, ksize);
-        if (in_mask && NFK_LDG(in_mask + n) != (uint8_t)in_keep) continue;
-        for (int ci = 0; ci < Ci; ++ci) {
-            const float v = NFK_LDG(in_b + ci * V + n);
-            const float* wr = wt + (ci * T + t) * CO;
+    const int half = ksize / 2;
+    int k[4], start[4];
+    for (int d = 0; d < 4; ++d) {
+        k[d] = d < lat.ndim ? ksize : 1;
+        int v = d < lat.ndim ? (c[d] - half) % lat.shape[d] : 0;
+        start[d] = v < 0 ? v + lat.shape[d] : v;
+    }
+    int t = 0;
+    int x0 = start[0];
+    for (int t0 = 0; t0 < k[0]; ++t0, x0 = x0 + 1 == lat.shape[0] ? 0 : x0 + 1) {
+        const int n0 = x0 * lat.stride[0];
+        int x1 = start[1];
+        for (int t1 = 0; t1 < k[1]; ++t1, x1 = x1 + 1 == lat.shape[1] ? 0 : x1 + 1) {
+            const int n1 = n0 + x1 * lat.stride[1];
+            int x2 = start[2];
+            for (int t2 = 0; t2 < k[2]; ++t2, x2 = x2 + 1 == lat.shape[2] ? 0 : x2 + 1) {
+                const int n2 = n1 + x2 * lat.stride[2];
+                int x3 = start[3];
+                for (int t3 = 0; t3 < k[3]; ++t3, ++t, x3 = x3 + 1 == lat.shape[3] ? 0 : x3 + 1) {
+                    const int n = n2 + x3 * lat.stride[3];
+                    if (in_mask && NFK_LDG(in_mask + n) != (uint8_t)in_keep) continue;
+                    for (int ci = 0; ci < Ci; ++ci) {
+                        const float v = NFK_LDG(in_b + ci * V + n);
+                        const float* wr = wt + (ci * T + t) * CO;
 #pragma unroll
-            for (int co = 0; co < CO; ++co) acc[co] = fmaf(v, wr[co], acc[co]);
+                        for (int co = 0; co < CO; ++co) acc[co] = fmaf(v, wr[co], acc[co]);
+                    }
+                }
+            }
         }
     }
 }
