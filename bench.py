@@ -276,8 +276,17 @@ def run_b200(args):
         # The step's input arrives in host memory.  It is copied in chunks on a copy stream while
         # the compute stream evaluates the chunks already on the device (public API calls per
         # chunk: prior.log_prob, net_, action), so the PCIe transfer hides behind the kernels.
-        n_chunks = 8 if B % 8 == 0 and B >= 1024 else 1
-        cb = B // n_chunks
+        # chunk boundaries: whole waves of the fused kernel's persistent grid (2 CTAs per SM), a short
+        # first chunk so that compute starts early, then ~1/8 of the batch each
+        wave = 2 * torch.cuda.get_device_properties(local).multi_processor_count
+        bounds = [0]
+        if B >= 16 * wave:
+            bounds.append(2 * wave)
+            step_c = max(wave, (B // 8) // wave * wave)
+            while bounds[-1] + step_c < B:
+                bounds.append(bounds[-1] + step_c)
+        bounds.append(B)
+        n_chunks = len(bounds) - 1
         x_dev = torch.empty(B, *LATTICE, dtype=torch.float32, device="cuda")
         res_dev = torch.empty(2, B, dtype=torch.float32, device="cuda")
         copy_stream = torch.cuda.Stream()
@@ -288,16 +297,18 @@ def run_b200(args):
             copy_stream.wait_stream(main)                 # x_dev of the previous step is consumed
             with torch.cuda.stream(copy_stream):
                 for c in range(n_chunks):
-                    x_dev[c * cb:(c + 1) * cb].copy_(host_x[c * cb:(c + 1) * cb], non_blocking=True)
+                    lo, hi = bounds[c], bounds[c + 1]
+                    x_dev[lo:hi].copy_(host_x[lo:hi], non_blocking=True)
                     ready[c].record(copy_stream)
             with torch.no_grad():
                 for c in range(n_chunks):
+                    lo, hi = bounds[c], bounds[c + 1]
                     main.wait_event(ready[c])
-                    x = x_dev[c * cb:(c + 1) * cb]
+                    x = x_dev[lo:hi]
                     logr = model.prior.log_prob(x)
                     yy, logJ = model.net_(x)
-                    res_dev[0, c * cb:(c + 1) * cb] = logr - logJ
-                    res_dev[1, c * cb:(c + 1) * cb] = -model.action(yy)
+                    res_dev[0, lo:hi] = logr - logJ
+                    res_dev[1, lo:hi] = -model.action(yy)
                 host_out.copy_(res_dev, non_blocking=True)
             torch.cuda.synchronize()
 
