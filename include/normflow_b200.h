@@ -268,6 +268,41 @@ int nfk_fused2d_step_train(const float* x, const float* w1, const float* b1, con
                            float* h1, float* h2, float* out,
                            int L0, int L1, int64_t B, void* stream);
 
+/* ------------------------------------------------- PSD block (spectral part) ---
+ * PSDBlock_ / FFTNet_ (psd_.py:25-40, fftflow_.py:121-131,167-180): the real-to-complex
+ * and complex-to-real transforms are cuFFT calls made by the host package; these entries
+ * are everything between them.  Spectra are complex64 half-spectra [B][Kc] passed as
+ * float pairs, Kc = prod(L[:-1]) * last_half, last_half = L[-1]/2 + 1.
+ *
+ * nfk_psd_weights_fwd: w[k] = ipsd[k]^(-1/2) (inverse != 0: ^(+1/2), the FFTNet_.backward
+ *   direction) and logj[0] = sum_k m_k log w[k] with m_k = 2 - [col == 0] - [col ==
+ *   last_half-1], col = k % last_half (FFTNet_.log_jacobian, fftflow_.py:167-178).
+ * nfk_psd_weights_bwd: g_ipsd from gw[Kc] (may be NULL) and glogj[1] (may be NULL).     */
+int nfk_psd_weights_fwd(const float* ipsd, int64_t Kc, int last_half, int inverse,
+                        float* w, float* logj, void* stream);
+int nfk_psd_weights_bwd(const float* ipsd, const float* w, const float* gw, const float* glogj,
+                        int64_t Kc, int last_half, int inverse, float* g_ipsd, void* stream);
+/* nfk_psd_scale: Y[b][k] = X[b][k] * w[k] (Y may alias X).  With zero_mode != NULL the k = 0
+ *   element becomes (zero_scale * zero_mode[b], 0) instead: PSDBlock_.forward subtracts the
+ *   sample mean before the transform and adds the mean-field net's output afterwards
+ *   (psd_.py:28-32), i.e. it replaces the zero mode by V * y_mf[b].
+ * nfk_psd_scale_bwd: gX = gY * w (gX may be NULL or alias gY; 0 at a replaced zero mode),
+ *   g_zero[b] = zero_scale * Re gY[b][0] (required iff replace_zero), and, when gw != NULL,
+ *   gw[k] = sum_b Re(conj(X[b][k]) gY[b][k]) through the workspace gw_part
+ *   [nfk_psd_chunks(B, Kc)][Kc] (deterministic two-stage sum, no atomics).               */
+int nfk_psd_scale(const float* X, const float* w, const float* zero_mode, float zero_scale,
+                  float* Y, int64_t B, int64_t Kc, void* stream);
+int nfk_psd_scale_bwd(const float* X, const float* gY, const float* w, int replace_zero,
+                      float zero_scale, float* gX, float* gw, float* gw_part, float* g_zero,
+                      int64_t B, int64_t Kc, void* stream);
+int nfk_psd_chunks(int64_t B, int64_t Kc);
+/* MeanFieldNet_ applied to a whole field (meanfield_.py:26-32, 42-48):
+ * nfk_sample_mean: mean[b] = scale * sum_v x[b][v]   (scale = 1/V for the mean; the same
+ *   kernel with scale = 1 is the adjoint of nfk_sample_shift with respect to delta);
+ * nfk_sample_shift: y[b][v] = x[b][v] + delta[b]     (y may alias x).                    */
+int nfk_sample_mean(const float* x, int64_t B, int64_t V, float scale, float* mean, void* stream);
+int nfk_sample_shift(const float* x, const float* delta, float* y, int64_t B, int64_t V, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,6 +65,13 @@ _SIGNATURES = {
                          c_f, c_f, c_f, c_i, c_i, c_l, c_f],
     "nfk_fused2d_step_train": [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, RqsParams, c_i, c_i,
                                c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_l, c_f],
+    "nfk_psd_weights_fwd": [c_f, c_l, c_i, c_i, c_f, c_f, c_f],
+    "nfk_psd_weights_bwd": [c_f, c_f, c_f, c_f, c_l, c_i, c_i, c_f, c_f],
+    "nfk_psd_scale": [c_f, c_f, c_f, c_fl, c_f, c_l, c_l, c_f],
+    "nfk_psd_scale_bwd": [c_f, c_f, c_f, c_i, c_fl, c_f, c_f, c_f, c_f, c_l, c_l, c_f],
+    "nfk_psd_chunks": [c_l, c_l],
+    "nfk_sample_mean": [c_f, c_l, c_l, c_fl, c_f, c_f],
+    "nfk_sample_shift": [c_f, c_f, c_f, c_l, c_l, c_f],
 }
 
 _lib = None

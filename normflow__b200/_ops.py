@@ -412,6 +412,168 @@ def phi4_action(cfgs, w0, w2, w4):
     return _Phi4.apply(cfgs, float(w0), float(w2), float(w4))
 
 
+# ---------------------------------------------------------------------------- PSD block
+class _PsdWeights(torch.autograd.Function):
+    @staticmethod
+    @_native
+    def forward(ctx, ipsd, last_half, inverse):
+        ipsd = _f32c(ipsd, "ipsd")
+        Kc = ipsd.numel()
+        w = torch.empty_like(ipsd)
+        logj = torch.empty((1,), dtype=torch.float32, device=ipsd.device)
+        check(lib().nfk_psd_weights_fwd(dev(ipsd), Kc, last_half, inverse, dev(w), dev(logj), stream()),
+              "psd_weights_fwd")
+        ctx.save_for_backward(ipsd, w)
+        ctx.cfg = (Kc, last_half, inverse)
+        return w, logj
+
+    @staticmethod
+    @_native
+    def backward(ctx, gw, glogj):
+        ipsd, w = ctx.saved_tensors
+        Kc, last_half, inverse = ctx.cfg
+        gw = None if gw is None else _f32c(gw, "gw")
+        glogj = None if glogj is None else _f32c(glogj, "glogj")
+        g = torch.empty_like(ipsd)
+        check(lib().nfk_psd_weights_bwd(dev(ipsd), dev(w), dev(gw), dev(glogj), Kc, last_half, inverse,
+                                        dev(g), stream()), "psd_weights_bwd")
+        return g, None, None
+
+
+@_native
+def psd_weights(ipsd, inverse=False):
+    """Spectral weights w = ipsd^(-1/2) (inverse: ipsd^(+1/2)) with the shape of `ipsd`
+    (the rfftn half-spectrum of the lattice) and the 0-dim log-Jacobian of multiplying the
+    spectrum by them (FFTNet_.forward/backward + log_jacobian, fftflow_.py:121-131,167-178)."""
+    if ipsd.ndim < 1:
+        raise ValueError("ipsd must have the shape of the half-spectrum")
+    w, logj = _PsdWeights.apply(ipsd, int(ipsd.shape[-1]), 1 if inverse else 0)
+    return w, logj.reshape(())
+
+
+def _c64(t, name):
+    if not t.is_cuda:
+        raise RuntimeError(f"normflow_b200: {name} is on '{t.device}'; the hot path runs on CUDA only "
+                           "(no CPU fallback)")
+    if t.dtype != torch.complex64:
+        raise TypeError(f"normflow_b200: {name} must be complex64 (got {t.dtype})")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class _PsdScale(torch.autograd.Function):
+    @staticmethod
+    @_native
+    def forward(ctx, X, w, zero_mode, zero_scale, inplace):
+        X = _c64(X, "spectrum")
+        w = _f32c(w, "w")
+        Kc = w.numel()
+        B = X.numel() // Kc
+        if zero_mode is not None:
+            zero_mode = _f32c(zero_mode, "zero_mode").reshape(-1)
+            if zero_mode.numel() != B:
+                raise ValueError("zero_mode must hold one value per sample")
+        Y = X if inplace else torch.empty_like(X)
+        with _C.timed("psd_scale"):
+            check(lib().nfk_psd_scale(dev(X, torch.complex64), dev(w), dev(zero_mode), zero_scale,
+                                      dev(Y, torch.complex64), B, Kc, stream()), "psd_scale")
+        if inplace:
+            ctx.mark_dirty(X)
+        ctx.save_for_backward(X if ctx.needs_input_grad[1] else None, w)
+        ctx.cfg = (B, Kc, zero_mode is not None, zero_scale)
+        return Y
+
+    @staticmethod
+    @_native
+    def backward(ctx, gY):
+        X, w = ctx.saved_tensors
+        B, Kc, replace, zero_scale = ctx.cfg
+        gY = _c64(gY, "gY")
+        need_x, need_w, need_z = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        gX = torch.empty_like(gY) if need_x else None
+        gw = gw_part = g_zero = None
+        if need_w:
+            gw = torch.empty_like(w)
+            gw_part = torch.empty((int(lib().nfk_psd_chunks(B, Kc)), Kc), dtype=torch.float32, device=w.device)
+        if replace:
+            g_zero = torch.empty((B,), dtype=torch.float32, device=w.device)
+        check(lib().nfk_psd_scale_bwd(dev(X, torch.complex64) if need_w else None, dev(gY, torch.complex64),
+                                      dev(w), 1 if replace else 0, zero_scale,
+                                      dev(gX, torch.complex64) if need_x else None, dev(gw), dev(gw_part),
+                                      dev(g_zero), B, Kc, stream()), "psd_scale_bwd")
+        return gX, gw, (g_zero if need_z else None), None, None
+
+
+@_native
+def psd_scale(X, w, zero_mode=None, zero_scale=1.0):
+    """Y = X * w over the trailing (half-spectrum) axes of the complex64 tensor X; with
+    `zero_mode` (one float per sample) the k = 0 element of every sample is replaced by
+    zero_scale * zero_mode.  Works in place when no gradient is being recorded."""
+    if tuple(X.shape[X.ndim - w.ndim:]) != tuple(w.shape):
+        raise ValueError(f"spectrum {tuple(X.shape)} does not end with the weights' shape {tuple(w.shape)}")
+    recording = torch.is_grad_enabled() and (X.requires_grad or w.requires_grad or
+                                             (zero_mode is not None and zero_mode.requires_grad))
+    return _PsdScale.apply(X, w, zero_mode, float(zero_scale), not recording and X.is_contiguous())
+
+
+def _sample_sum(x, scale):
+    B = x.shape[0]
+    V = x.numel() // max(B, 1)
+    out = torch.empty((B,), dtype=torch.float32, device=x.device)
+    check(lib().nfk_sample_mean(dev(x), B, V, scale, dev(out), stream()), "sample_mean")
+    return out
+
+
+class _SampleMean(torch.autograd.Function):
+    @staticmethod
+    @_native
+    def forward(ctx, x):
+        x = _f32c(x, "x")
+        ctx.shape = tuple(x.shape)
+        return _sample_sum(x, 1.0 / max(x.numel() // max(x.shape[0], 1), 1))
+
+    @staticmethod
+    @_native
+    def backward(ctx, g):
+        shape = ctx.shape
+        V = int(np.prod(shape[1:]))
+        return (g / V).reshape(-1, *[1] * (len(shape) - 1)).expand(shape)
+
+
+class _SampleShift(torch.autograd.Function):
+    @staticmethod
+    @_native
+    def forward(ctx, x, delta):
+        x = _f32c(x, "x")
+        delta = _f32c(delta, "delta").reshape(-1)
+        B = x.shape[0]
+        if delta.numel() != B:
+            raise ValueError("delta must hold one value per sample")
+        y = torch.empty_like(x)
+        check(lib().nfk_sample_shift(dev(x), dev(delta), dev(y), B, x.numel() // max(B, 1), stream()),
+              "sample_shift")
+        ctx.dshape = None
+        return y
+
+    @staticmethod
+    @_native
+    def backward(ctx, gy):
+        gy = _f32c(gy, "gy")
+        gd = _sample_sum(gy, 1.0) if ctx.needs_input_grad[1] else None
+        return gy, gd
+
+
+@_native
+def sample_mean(x):
+    """Mean over everything but the batch axis -> float32[B] (meanfield_.py:29, psd_.py:28)."""
+    return _SampleMean.apply(x)
+
+
+@_native
+def sample_shift(x, delta):
+    """x[b, ...] + delta[b] (meanfield_.py:31)."""
+    return _SampleShift.apply(x, delta)
+
+
 # ---------------------------------------------------------------------------- conditioner
 def _conv_call(inp, w, transposed, bias, in_mask, in_keep, act, dact_from, dact_kind, shape, ksize, Ci, Co):
     B = inp.shape[0]

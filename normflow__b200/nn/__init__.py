@@ -9,3 +9,7 @@ from .scalar.modules_ import UnityDistConvertor_, PhaseDistConvertor_  # noqa: F
 
 from .scalar.couplings_ import Coupling_, ShiftCoupling_, AffineCoupling_  # noqa: F401
 from .scalar.couplings_ import RQSplineCoupling_  # noqa: F401
+
+from .scalar.fftflow_ import FFTNet_, IPSD, FreeScalar  # noqa: F401
+from .scalar.meanfield_ import MeanFieldNet_  # noqa: F401
+from .scalar.psd_ import PSDBlock_  # noqa: F401

@@ -4,7 +4,8 @@ A numpy float64 restatement of the reference's algorithm for the
 `Model.fit / posterior.sample / mcmc.sample` inner loop (NormalPrior log-prob,
 checkerboard masks, affine / shift / rational-quadratic-spline couplings with
 log|det J|, DistConvertor_, circular ConvAct conditioner, phi^4 action,
-Metropolis accept/reject).  Every function cites the reference file:line it
+Metropolis accept/reject) and of the PSDBlock_ that opens examples/scalar_affine.py
+(MeanFieldNet_ + FFTNet_/IPSD).  Every function cites the reference file:line it
 follows (paths relative to /root/reference/).
 
 Only `tests/`, `__graft_entry__.smoke()` and the `cpu_baseline` / `--impl
@@ -497,6 +498,86 @@ def distconvertor(x, log0, weights, *, symmetric, inverse=False, stable_inverse=
     x, log0 = splinenet_forward(x, log0, knots, extrap, inverse=inverse,
                                 stable_inverse=stable_inverse)
     return logit_forward(x, log0)
+
+
+# =============================================================================
+# PSDBlock_ = MeanFieldNet_ + FFTNet_  (src/nn/scalar/psd_.py, meanfield_.py, fftflow_.py)
+# =============================================================================
+def lattice_k2(lat_shape):
+    """FreeScalar.calc_lattice_k2 + outer_lattice_k2, fftflow_.py:317-349: sum over axes of
+    4 sin^2(k/2) with k = linspace(0, 2 pi (1 - 1/n), n), last axis trimmed to n//2 + 1."""
+    grids = [4 * np.sin(np.linspace(0, 2 * np.pi * (1 - 1 / n), n) / 2) ** 2 for n in lat_shape]
+    total = grids[0]
+    for g in grids[1:]:
+        total = total[..., None] + g
+    return total[..., :(1 + lat_shape[-1] // 2)]
+
+
+def ipsd_forward(norm_k2, weights, logy, ignore_zeromode=False):
+    """IPSD.forward, fftflow_.py:232-239: y0 + y1 * SplineNet(norm_k2) with SplineNet's default
+    limits (0, 1) and no extrapolation (modules.py:318-330); the k = 0 entry set to 1 when
+    the zero mode is ignored.  `weights` = (weights_x, weights_y, weights_d | None)."""
+    knots = splinenet_knots(*weights, xlim=(0.0, 1.0), ylim=(0.0, 1.0))
+    spline = RQSpline(*knots, extrap={})
+    s, _ = spline.forward(norm_k2.ravel())
+    sigma = np.exp(logy[0]) + np.exp(logy[1]) * s.reshape(norm_k2.shape)
+    if ignore_zeromode:
+        sigma[tuple([0] * norm_k2.ndim)] = 1
+    return sigma
+
+
+def fftnet_log_jacobian(w):
+    """FFTNet_.log_jacobian, fftflow_.py:167-180 (all axes of w are lattice axes)."""
+    return 2 * np.sum(np.log(w)) - np.sum(np.log(w[..., 0:1])) - np.sum(np.log(w[..., -1:]))
+
+
+def fftnet(x, log0, ipsd, inverse=False):
+    """FFTNet_.forward / backward, fftflow_.py:121-131."""
+    w = 1 / ipsd ** 0.5
+    axes = tuple(range(-ipsd.ndim, 0))
+    spec = np.fft.rfftn(x, axes=axes)
+    spec = spec / w if inverse else spec * w
+    logj = fftnet_log_jacobian(w)
+    return np.fft.irfftn(spec, axes=axes), (log0 - logj if inverse else log0 + logj)
+
+
+def scalenet(x, log0, raw_weight, inverse=False):
+    """ScaleNet_, modules_.py:44-69."""
+    w = softplus_ln2(raw_weight)
+    nvar = np.prod(x.shape[1:])
+    if inverse:
+        return x / w, log0 - np.log(w) * nvar * np.ones(x.shape[0])
+    return x * w, log0 + np.log(w) * nvar * np.ones(x.shape[0])
+
+
+def meanfieldnet(x_mean, log0, rvol, weights, *, symmetric, final_scale=None, inverse=False):
+    """MeanFieldNet_.forward / backward with `rvol` given (meanfield_.py:33-36, 49-52): the
+    DistConvertor_ [Expit_, SplineNet_, Logit_ (, ScaleNet_)] acts on x_mean * rvol.
+    `final_scale`: raw `_weight` of the trailing ScaleNet_ or None."""
+    v = x_mean * rvol
+    if inverse:
+        if final_scale is not None:
+            v, log0 = scalenet(v, log0, final_scale, inverse=True)
+        v, log0 = distconvertor(v, log0, weights, symmetric=symmetric, inverse=True)
+    else:
+        v, log0 = distconvertor(v, log0, weights, symmetric=symmetric)
+        if final_scale is not None:
+            v, log0 = scalenet(v, log0, final_scale)
+    return v / rvol, log0
+
+
+def psdblock(x, log0, *, mf_weights, mf_symmetric, mf_final_scale, ipsd, inverse=False):
+    """PSDBlock_.forward / backward, psd_.py:25-40.  mf_weights=None stands for Identity_."""
+    axes = tuple(range(1, x.ndim))
+    rvol = np.prod(x.shape[1:]) ** 0.5
+    x_mean = np.mean(x, axis=axes).reshape(-1, *[1 for _ in axes])
+    if mf_weights is None:
+        y_mf, logj_mf = x_mean, 0
+    else:
+        y_mf, logj_mf = meanfieldnet(x_mean, 0, rvol, mf_weights, symmetric=mf_symmetric,
+                                     final_scale=mf_final_scale, inverse=inverse)
+    y_fft, logj_fft = fftnet(x - x_mean, 0, ipsd, inverse=inverse)
+    return y_mf + y_fft, log0 + logj_mf + logj_fft
 
 
 # =============================================================================

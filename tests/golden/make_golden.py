@@ -34,7 +34,8 @@ from normflow_ref.mask import EvenOddMask, AlongAxesEvenOddMask  # noqa: E402
 from normflow_ref.action import ScalarPhi4Action  # noqa: E402
 from normflow_ref.prior import NormalPrior  # noqa: E402
 from normflow_ref.nn import (ModuleList_, ConvAct, AffineCoupling_, ShiftCoupling_,  # noqa: E402
-                             RQSplineCoupling_, DistConvertor_)
+                             RQSplineCoupling_, DistConvertor_, Identity_,
+                             FFTNet_, MeanFieldNet_, PSDBlock_)
 from normflow_ref.lib.spline import RQSpline  # noqa: E402
 from normflow_ref.mcmc.mcmc import Metropolis, MCMCSampler  # noqa: E402
 from normflow_ref import Model  # noqa: E402
@@ -431,23 +432,169 @@ def gen_model_zero_dim():
         res[f"g_{n}"] = npy(gval)
     save("model_zero_dim", **res)
 
+# -----------------------------------------------------------------------------
+def _randomise(net_, scale=0.3):
+    """float32-representable random parameters; IPSD's `logy` keeps its built value plus
+    a small offset (it sets the overall scale of the spectrum)."""
+    for n, p in net_.named_parameters():
+        if n.endswith('logy'):
+            p.data = f32(p.data + 0.1 * torch.randn_like(p))
+        else:
+            p.data = f32(torch.randn_like(p) * scale)
+
+
+def _psd_record(tag, blk, x, res, seed):
+    """forward, hack parts, inverse and reference-autograd gradients of one PSDBlock_ / FFTNet_."""
+    B = x.shape[0]
+    x.requires_grad_(True)
+    y, logJ = blk(x)
+    logJ_full = logJ if (torch.is_tensor(logJ) and logJ.dim() > 0) else torch.zeros(B) + logJ
+    r, c = randn32(*x.shape, seed=seed + 1), randn32(B, seed=seed + 2)
+    L = (y * r).sum() + (logJ_full * c).sum()
+    names = [n for n, _ in blk.named_parameters()]
+    grads = torch.autograd.grad(L, [x] + list(blk.parameters()))
+    with torch.no_grad():
+        xb, lb = blk.backward(y.detach(), log0=logJ_full.detach())
+        # the inverse direction on an independent input (not just the round trip)
+        yi, li = blk.backward(x.detach())
+    li = li if (torch.is_tensor(li) and li.dim() > 0) else torch.zeros(B) + li
+    res.update({f"{tag}_x": npy(x), f"{tag}_y": npy(y), f"{tag}_logJ": npy(logJ_full),
+                f"{tag}_r": npy(r), f"{tag}_c": npy(c), f"{tag}_gx": npy(grads[0]),
+                f"{tag}_rt_x": npy(xb), f"{tag}_rt_log": npy(lb),
+                f"{tag}_inv_y": npy(yi), f"{tag}_inv_logJ": npy(li),
+                f"{tag}_param_names": np.array(names)})
+    for n, p, g in zip(names, blk.parameters(), grads[1:]):
+        res[f"{tag}_w_{n}"] = npy(p)
+        res[f"{tag}_grad_{n}"] = npy(g)
+    fft = blk.fftnet_ if hasattr(blk, 'fftnet_') else blk
+    res[f"{tag}_ipsd"] = npy(fft.ipsd)
+    res[f"{tag}_norm_lat_k2"] = npy(fft.norm_lat_k2)
+    res[f"{tag}_max_lat_k2"] = npy(fft.max_lat_k2)
+    res[f"{tag}_lat_shape"] = np.array(fft.lat_shape)
+    if hasattr(blk, '_hack'):
+        with torch.no_grad():
+            stack = blk._hack(x.detach())
+        (xm, _), (ymf, lmf), (yfft, lfft), _ = stack
+        res.update({f"{tag}_x_mean": npy(xm), f"{tag}_y_mf": npy(ymf), f"{tag}_logJ_mf": npy(lmf),
+                    f"{tag}_y_fft": npy(yfft), f"{tag}_logJ_fft": npy(lfft)})
+
+
+def gen_psd():
+    """PSDBlock_ / MeanFieldNet_ / FFTNet_ (first block of examples/scalar_affine.py:71-77)."""
+    res = {}
+    # the example's block on a 2-D lattice with unequal sides
+    torch.manual_seed(131)
+    lat = (8, 6)
+    mf = MeanFieldNet_.build(knots_len=10, symmetric=True, final_scale=True, smooth=True)
+    ff = FFTNet_.build(lat, knots_len=10, ignore_zeromode=True)
+    blk = PSDBlock_(mfnet_=mf, fftnet_=ff)
+    _randomise(blk)
+    _psd_record("ex2d", blk, randn32(5, *lat, seed=132), res, seed=133)
+    # 3-D, identity mean field (knots0_len <= 1 in the example), zero mode kept, non-unit a
+    torch.manual_seed(141)
+    lat = (4, 6, 4)
+    ff = FFTNet_.build(lat, knots_len=6, eff_mass2=0.7, eff_kappa=1.3, a=0.5)
+    blk = PSDBlock_(mfnet_=Identity_(), fftnet_=ff)
+    _randomise(blk)
+    _psd_record("id3d", blk, randn32(3, *lat, seed=142), res, seed=143)
+    # FFTNet_ on its own, 1-D, identity spline (knots_len < 2), zero mode kept
+    torch.manual_seed(151)
+    lat = (10,)
+    ff = FFTNet_.build(lat, knots_len=1, eff_mass2=0.5)
+    _randomise(ff)
+    _psd_record("fft1d", ff, randn32(4, *lat, seed=152), res, seed=153)
+    # FFTNet_ on its own, 2-D, asymmetric mean-field variant not involved; 4x4 with zero mode ignored
+    torch.manual_seed(161)
+    lat = (4, 4)
+    ff = FFTNet_.build(lat, knots_len=5, ignore_zeromode=True)
+    _randomise(ff)
+    _psd_record("fft2d", ff, randn32(6, *lat, seed=162), res, seed=163)
+    save("psd", **res)
+
+
+def gen_model_psd_affine():
+    """The whole net of examples/scalar_affine.py:61-114 on 8x8 (smaller spline sizes): PSDBlock_,
+    DistConvertor_, AffineCoupling_ x 4, DistConvertor_; loss and gradients of Fitter.step."""
+    torch.manual_seed(171)
+    lat = (8, 8)
+    mf = MeanFieldNet_.build(knots_len=10, symmetric=True, final_scale=True, smooth=True)
+    ff = FFTNet_.build(lat, knots_len=10, ignore_zeromode=True)
+    conv = dict(in_channels=1, out_channels=2, hidden_sizes=[8, 8], kernel_size=3,
+                padding_mode='circular', conv_dim=2, acts=('tanh', 'tanh', None), bias=False)
+    net_ = ModuleList_([
+        PSDBlock_(mfnet_=mf, fftnet_=ff),
+        DistConvertor_(12, symmetric=True, smooth=True),
+        AffineCoupling_([ConvAct(**conv) for _ in range(4)], mask=EvenOddMask(shape=lat)),
+        DistConvertor_(12, symmetric=True, smooth=True)])
+    for n, p in net_.named_parameters():
+        if n.endswith('logy'):
+            p.data = f32(p.data + 0.1 * torch.randn_like(p))
+        elif p.dim() > 1:
+            p.data = f32(p.data)                     # conv weights: torch default init
+        else:
+            p.data = f32(torch.randn_like(p) * 0.3)
+    prior = NormalPrior(shape=lat)
+    action = ScalarPhi4Action(**ACTION)
+    model = Model(net_=net_, prior=prior, action=action)
+    x = randn32(6, *lat, seed=172)
+    logr = prior.log_prob(x)
+    stack = net_.hack(x, log0=0)
+    y, logJ = stack[-1]
+    logq, logp = logr - logJ, -action(y)
+    loss = model.fit.calc_kl_mean(logq, logp)
+    grads = torch.autograd.grad(loss, list(net_.parameters()))
+    res = dict(x=npy(x), y=npy(y), logq=npy(logq), logp=npy(logp), loss=npy(loss),
+               lat_shape=np.array(lat), param_names=np.array([n for n, _ in net_.named_parameters()]))
+    for i, (xi, li) in enumerate(stack[1:]):
+        res[f"blk{i}_y"], res[f"blk{i}_logJ"] = npy(xi), npy(li)
+    for (n, p), g in zip(net_.named_parameters(), grads):
+        res[f"w_{n}"] = npy(p)
+        res[f"g_{n}"] = npy(g)
+    with torch.no_grad():
+        xb, lb = net_.backward(y.detach(), log0=logJ.detach())
+    res["inv_x"], res["inv_log"] = npy(xb), npy(lb)
+    save("model_psd_affine", **res)
+
 
 if __name__ == "__main__":
-    gen_masks()
-    gen_action()
-    gen_prior()
-    gen_spline()
-    gen_rqs_kernel_only()
-    gen_affine_kernel_only()
-    gen_distconv()
-    gen_mcmc()
-    gen_conv()
-    gen_model_zero_dim()
+    only = set(sys.argv[1:])           # e.g. `make_golden.py psd model_psd_affine`
+
+    def wanted(name):
+        return not only or name in only
+    if wanted("masks"):
+        gen_masks()
+    if wanted("action"):
+        gen_action()
+    if wanted("prior"):
+        gen_prior()
+    if wanted("spline"):
+        gen_spline()
+    if wanted("rqs_kernel_only"):
+        gen_rqs_kernel_only()
+    if wanted("affine_kernel_only"):
+        gen_affine_kernel_only()
+    if wanted("distconv"):
+        gen_distconv()
+    if wanted("mcmc"):
+        gen_mcmc()
+    if wanted("conv"):
+        gen_conv()
+    if wanted("model_zero_dim"):
+        gen_model_zero_dim()
     # whole coupling stacks: config-2 style (affine), config-3 style (rqs), 1-D shift,
     # 3-D mixed (config-4 style), 4-D with Conv4d (config-5 style)
-    gen_coupling("cpl_affine_2d", (8, 8), 4, [("affine", 4)], seed=10)
-    gen_coupling("cpl_rqs_2d", (8, 8), 3, [("rqs", 4)], seed=20)
-    gen_coupling("cpl_shift_1d", (10,), 4, [("shift", 2)], seed=30, hidden=(4,), bias=True)
-    gen_coupling("cpl_mixed_3d", (4, 4, 4), 2, [("affine", 2), ("rqs", 2)], seed=40, hidden=(4, 4))
-    gen_coupling("cpl_mixed_4d", (4, 4, 4, 4), 2, [("affine", 2), ("rqs", 2)], seed=50, hidden=(4,),
-                 bias=True)
+    if wanted("cpl_affine_2d"):
+        gen_coupling("cpl_affine_2d", (8, 8), 4, [("affine", 4)], seed=10)
+    if wanted("cpl_rqs_2d"):
+        gen_coupling("cpl_rqs_2d", (8, 8), 3, [("rqs", 4)], seed=20)
+    if wanted("cpl_shift_1d"):
+        gen_coupling("cpl_shift_1d", (10,), 4, [("shift", 2)], seed=30, hidden=(4,), bias=True)
+    if wanted("cpl_mixed_3d"):
+        gen_coupling("cpl_mixed_3d", (4, 4, 4), 2, [("affine", 2), ("rqs", 2)], seed=40, hidden=(4, 4))
+    if wanted("cpl_mixed_4d"):
+        gen_coupling("cpl_mixed_4d", (4, 4, 4, 4), 2, [("affine", 2), ("rqs", 2)], seed=50, hidden=(4,),
+                     bias=True)
+    if wanted("psd"):
+        gen_psd()
+    if wanted("model_psd_affine"):
+        gen_model_psd_affine()
