@@ -303,6 +303,19 @@ int nfk_psd_chunks(int64_t B, int64_t Kc);
 int nfk_sample_mean(const float* x, int64_t B, int64_t V, float scale, float* mean, void* stream);
 int nfk_sample_shift(const float* x, const float* delta, float* y, int64_t B, int64_t V, void* stream);
 
+/* ---------------------------------------------------------------- knot table ---
+ * SplineNet.make_spline for ONE shared spline (modules.py:369-391): K-1 raw widths wx, K-1 raw
+ * heights wy and K raw derivatives wd (NULL: smooth derivatives, spline.py:125-152) -> table
+ * float32[5][K] = knots_x | knots_y | knots_d | (xlo+xw) - knots_x | (ylo+yw) - knots_y, the
+ * last two accumulated from the right end (what nfk_spline1d_* takes as its both-ends table;
+ * the first three rows are the reference's knots).  2 <= K <= 256.  _bwd: gradients of the raw
+ * parameters from g_table[5][K] (gwd required iff wd != NULL).                              */
+int nfk_knots_fwd(const float* wx, const float* wy, const float* wd, int K, float xlo, float xw,
+                  float ylo, float yw, float* table, void* stream);
+int nfk_knots_bwd(const float* wx, const float* wy, const float* wd, int K, float xlo, float xw,
+                  float ylo, float yw, const float* g_table, float* gwx, float* gwy, float* gwd,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,8 @@ _SIGNATURES = {
     "nfk_psd_scale": [c_f, c_f, c_f, c_fl, c_f, c_l, c_l, c_f],
     "nfk_psd_scale_bwd": [c_f, c_f, c_f, c_i, c_fl, c_f, c_f, c_f, c_f, c_l, c_l, c_f],
     "nfk_psd_chunks": [c_l, c_l],
+    "nfk_knots_fwd": [c_f, c_f, c_f, c_i, c_fl, c_fl, c_fl, c_fl, c_f, c_f],
+    "nfk_knots_bwd": [c_f, c_f, c_f, c_i, c_fl, c_fl, c_fl, c_fl, c_f, c_f, c_f, c_f, c_f],
     "nfk_sample_mean": [c_f, c_l, c_l, c_fl, c_f, c_f],
     "nfk_sample_shift": [c_f, c_f, c_f, c_l, c_l, c_f],
 }

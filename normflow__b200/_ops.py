@@ -412,6 +412,44 @@ def phi4_action(cfgs, w0, w2, w4):
     return _Phi4.apply(cfgs, float(w0), float(w2), float(w4))
 
 
+# ---------------------------------------------------------------------------- knot table
+class _KnotTable(torch.autograd.Function):
+    @staticmethod
+    @_native
+    def forward(ctx, wx, wy, wd, lims):
+        wx, wy = _f32c(wx, "weights_x"), _f32c(wy, "weights_y")
+        wd = None if wd is None else _f32c(wd, "weights_d")
+        K = wx.numel() + 1
+        if wy.numel() != K - 1 or (wd is not None and wd.numel() != K):
+            raise ValueError("weights_x / weights_y need K-1 entries and weights_d K")
+        table = torch.empty((5, K), dtype=torch.float32, device=wx.device)
+        check(lib().nfk_knots_fwd(dev(wx), dev(wy), dev(wd), K, *lims, dev(table), stream()), "knots_fwd")
+        ctx.save_for_backward(wx, wy, wd)
+        ctx.cfg = (K, lims)
+        return table
+
+    @staticmethod
+    @_native
+    def backward(ctx, g):
+        wx, wy, wd = ctx.saved_tensors
+        K, lims = ctx.cfg
+        g = _f32c(g, "g_table")
+        gwx, gwy = torch.empty_like(wx), torch.empty_like(wy)
+        gwd = None if wd is None else torch.empty_like(wd)
+        check(lib().nfk_knots_bwd(dev(wx), dev(wy), dev(wd), K, *lims, dev(g), dev(gwx), dev(gwy), dev(gwd),
+                                  stream()), "knots_bwd")
+        return gwx, gwy, gwd, None
+
+
+@_native
+def knot_table(weights_x, weights_y, weights_d, xlim, ylim):
+    """SplineNet.make_spline for one shared spline (modules.py:369-391) in one launch: float32[5, K]
+    = knots_x | knots_y | knots_d | xlim[1] - knots_x | ylim[1] - knots_y (the last two summed from
+    the right end).  weights_d=None -> smooth derivatives."""
+    lims = (float(xlim[0]), float(xlim[1] - xlim[0]), float(ylim[0]), float(ylim[1] - ylim[0]))
+    return _KnotTable.apply(weights_x, weights_y, weights_d, lims)
+
+
 # ---------------------------------------------------------------------------- PSD block
 class _PsdWeights(torch.autograd.Function):
     @staticmethod

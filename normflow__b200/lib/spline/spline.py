@@ -47,7 +47,8 @@ class RQSpline:
         return self.forward(x, **kwargs)
 
     def _table(self):
-        return torch.stack([self.knots_x, self.knots_y, self.knots_d])
+        packed = getattr(self, '_packed', None)
+        return packed if packed is not None else torch.stack([self.knots_x, self.knots_y, self.knots_d])
 
     def _run(self, x, grad, inverse):
         flat = x.reshape(1, -1)

@@ -266,27 +266,15 @@ class SplineNet(torch.nn.Module):
         the left, its complement from the right (so a knot close to xlim[1] is known to
         the relative precision of its distance from xlim[1], not of its value), and the
         bin widths / heights used for the smooth derivatives are the softmax terms
-        themselves.  The end knots are exactly xlim / ylim."""
-        def coords(w, lo, width):
-            p = torch.softmax(w, dim=0)
-            zero = p.new_zeros(1)
-            left = torch.cat([zero, torch.cumsum(p, dim=0)[:-1]])               # sum_{i<j} p_i, j < K-1
-            right = torch.cat([torch.flip(torch.cumsum(torch.flip(p, [0]), 0), [0]), zero])   # sum_{i>=j} p_i
-            k = torch.cat([lo + width * left, p.new_full((1,), lo + width)])
-            return k, width * right, width * p
-        kx, cx, wx = coords(self.weights_x, self.xlim[0], self.xwidth)
-        ky, cy, wy = coords(self.weights_y, self.ylim[0], self.ywidth)
-        if self.weights_d is None:
-            slope = wy / wx
-            kd = torch.cat([slope[:1], 0.5 * (slope[1:] + slope[:-1]), slope[-1:]])
-        else:
-            kd = torch.nn.functional.softplus(self.weights_d, beta=float(np.log(2)))
-        rows = [kx, ky, kd, cx, cy] if both_ends else [kx, ky, kd]
-        return torch.stack(rows)
+        themselves.  The end knots are exactly xlim / ylim.  One kernel (`nfk_knots_*`)."""
+        table = _ops.knot_table(self.weights_x, self.weights_y, self.weights_d, self.xlim, self.ylim)
+        return table if both_ends else table[:3]
 
     def make_spline(self):
-        kx, ky, kd = self.knots()
-        return self.Spline(knots_x=kx, knots_y=ky, knots_d=kd, **self.spline_kwargs)
+        table = self.knots()
+        spline = self.Spline(knots_x=table[0], knots_y=table[1], knots_d=table[2], **self.spline_kwargs)
+        spline._packed = table        # the kernel's input as it stands: no re-stacking of the rows
+        return spline
 
     def forward(self, x):
         return self.make_spline()(x.ravel()).reshape(x.shape)

@@ -118,6 +118,46 @@ def test_sample_mean_and_shift(B, shape):
     close_grad(gd, r.astype(np.float64).reshape(B, -1).sum(1), tol=2e-6)
 
 
+# ------------------------------------------------------------------ knot table (SplineNet.make_spline)
+def _knots_torch64(wx, wy, wd, xlim, ylim):
+    """modules.py:369-391 with torch float64 ops on the CPU (differentiable)."""
+    def coord(w, lim):
+        p = torch.softmax(w, 0)
+        left = torch.cat([p.new_zeros(1), torch.cumsum(p, 0)])
+        return lim[0] + (lim[1] - lim[0]) * left, (lim[1] - lim[0]) * p
+    kx, bx = coord(wx, xlim)
+    ky, by = coord(wy, ylim)
+    if wd is None:
+        s = by / bx
+        kd = torch.cat([s[:1], 0.5 * (s[1:] + s[:-1]), s[-1:]])
+    else:
+        kd = torch.nn.functional.softplus(wd, beta=float(np.log(2)))
+    return torch.stack([kx, ky, kd, xlim[1] - kx, ylim[1] - ky])
+
+
+@pytest.mark.parametrize("K,smooth,xlim,ylim", [(2, True, (0, 1), (0, 1)), (2, False, (0.5, 1), (0.5, 1)),
+                                                (10, False, (0, 1), (0, 1)), (10, True, (0.5, 1), (0.5, 1)),
+                                                (50, True, (-2, 3), (0, 7)), (200, False, (0, 1), (-1, 1))])
+def test_knot_table_kernel_and_adjoint(K, smooth, xlim, ylim):
+    g = torch.Generator('cpu').manual_seed(K)
+    wx = torch.randn(K - 1, generator=g, device='cpu')
+    wy = torch.randn(K - 1, generator=g, device='cpu')
+    wd = None if smooth else torch.randn(K, generator=g, device='cpu') * 3
+    if wd is not None:
+        wd[0] = 40.0        # beyond the softplus threshold
+    r = torch.randn(5, K, generator=g, device='cpu')
+    ref_in = [t.double().requires_grad_(True) for t in (wx, wy) + (() if smooth else (wd,))]
+    ref = _knots_torch64(ref_in[0], ref_in[1], None if smooth else ref_in[2], xlim, ylim)
+    ref_g = torch.autograd.grad((ref * r.double()).sum(), ref_in)
+    dev_in = [t.to(DEV).requires_grad_(True) for t in (wx, wy) + (() if smooth else (wd,))]
+    table = _ops.knot_table(dev_in[0], dev_in[1], None if smooth else dev_in[2], xlim, ylim)
+    close(table, ref.detach().numpy(), tol=2e-7 if K < 100 else 1e-6)
+    assert float(table[0, -1]) == float(np.float32(xlim[1])) and float(table[3, -1]) == 0.0
+    got_g = torch.autograd.grad((table * r.to(DEV)).sum(), dev_in)
+    for a, b in zip(got_g, ref_g):
+        close_grad(a, b.numpy(), tol=2e-6)
+
+
 # ------------------------------------------------------------------ modules against the reference's outputs
 def _build_case(g, tag):
     lat = tuple(int(v) for v in g[f"{tag}_lat_shape"])
