@@ -17,7 +17,7 @@ import time
 import numpy as np
 import torch
 
-from .mcmc import MCMCSampler
+from .mcmc import MCMCSampler, BlockedMCMCSampler
 from .lib.combo import estimate_logz, fmt_val_err
 from .device import ModelDeviceHandler
 
@@ -41,6 +41,7 @@ class Model:
         self.posterior = Posterior(self)
         self.raw_dist = self.posterior      # older alias kept by the reference
         self.mcmc = MCMCSampler(self)
+        self.blocked_mcmc = BlockedMCMCSampler(self)
         self.device_handler = ModelDeviceHandler(self)
 
     def transform(self, x):

@@ -72,8 +72,11 @@ class _MaskSelect(torch.autograd.Function):
     def forward(ctx, x, mask, keep):
         x = _f32c(x, "x")
         y = torch.empty_like(x)
-        B = x.shape[0]
-        check(lib().nfk_mask_select(dev(x), dev(mask, torch.uint8), keep, dev(y), B, x.numel() // max(B, 1),
+        # the mask covers the trailing (lattice) axes; every leading axis -- batch, channels -- is a row
+        V = mask.numel()
+        if x.ndim < mask.ndim or tuple(x.shape[x.ndim - mask.ndim:]) != tuple(mask.shape):
+            raise ValueError(f"field of shape {tuple(x.shape)} does not end with the mask's shape {tuple(mask.shape)}")
+        check(lib().nfk_mask_select(dev(x), dev(mask, torch.uint8), keep, dev(y), x.numel() // max(V, 1), V,
                                     stream()), "mask_select")
         ctx.mask, ctx.keep = mask, keep
         return y

@@ -1,1 +1,1 @@
-from .mcmc import MCMCSampler, MCMCHistory, Metropolis  # noqa: F401
+from .mcmc import MCMCSampler, BlockedMCMCSampler, MCMCHistory, Metropolis  # noqa: F401

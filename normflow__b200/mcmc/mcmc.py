@@ -120,6 +120,84 @@ class MCMCSampler:
         return -self._model.action(y) - action_logz
 
 
+class BlockedMCMCSampler(MCMCSampler):
+    """Metropolis chain whose proposals redraw ONE block of the prior variables at a time
+    (reference BlockedMCMCSampler, mcmc.py:132-219): a sweep visits the n_blocks blocks in order,
+    each proposal is a single-configuration flow evaluation, accepted against the running
+    log q - log p with log-uniforms drawn on the host as the reference draws them.
+
+    The chain is sequential by construction (one configuration, one decision at a time); what
+    this version saves is the flow evaluation the reference repeats after every sweep -- the
+    state left by a sweep is the last accepted proposal, whose (y, logq, logp) are already known.
+    """
+
+    @torch.no_grad()
+    def sample__(self, batch_size=1, n_blocks=1, bookkeeping=False):
+        prior, net_ = self._model.prior, self._model.net_
+        if self._ref['sample'] is not None:
+            x = net_.backward(self._ref['sample'].unsqueeze(0))[0]
+            logqp_ref = self._ref['logqp']
+        else:
+            print("Starting from scratch & setting logqp_ref to None")
+            x = prior.sample(1)
+            logqp_ref = None
+        nvar = prior.nvar
+        if isinstance(n_blocks, int):
+            block_len = nvar // n_blocks
+            assert block_len * n_blocks == nvar
+        else:
+            block_len, n_blocks = nvar, 1
+        prior.setup_blockupdater(block_len)
+
+        cfgs = torch.empty((batch_size, *prior.shape), dtype=torch.float32, device=x.device)
+        logq = torch.empty((batch_size,), dtype=torch.float32, device=x.device)
+        logp = torch.empty((batch_size,), dtype=torch.float32, device=x.device)
+        accept_seq = np.empty((batch_size, n_blocks), dtype=bool)
+        current = None                      # (y, logq, logp) of the configuration x stands for
+        for ind in range(batch_size):
+            accept_seq[ind], logqp_ref, current = self.sweep(x, n_blocks, logqp_ref, current=current,
+                                                             return_state=True)
+            cfgs[ind:ind + 1], logq[ind:ind + 1], logp[ind:ind + 1] = current
+
+        self._ref['sample'] = cfgs[-1].clone()
+        self._ref['logq'], self._ref['logp'] = float(logq[-1]), float(logp[-1])
+        self._ref['logqp'] = float(logq[-1].double() - logp[-1].double())
+        self.history.bookkeeping(accept_rate=np.mean(accept_seq))
+        if bookkeeping:
+            self.history.bookkeeping(logq=logq, logp=logp)
+            self.history.bookkeeping(accept_seq=accept_seq.ravel())
+        return cfgs, logq, logp
+
+    def _evaluate(self, x):
+        y, logJ = self._model.net_(x)
+        return y, self._model.prior.log_prob(x) - logJ, -self._model.action(y)
+
+    @torch.no_grad()
+    def sweep(self, x, n_blocks=1, logqp_ref=None, current=None, return_state=False):
+        """One in-place sweep over the blocks of x (shape (1, *lattice)); returns the accept flags and
+        the updated reference log q - log p (mcmc.py:196-219)."""
+        prior = self._model.prior
+        accept_seq = np.empty(n_blocks, dtype=bool)
+        lrand_arr = np.log(np.random.rand(n_blocks))
+        for ind in range(n_blocks):
+            prior.blockupdater(x, ind)
+            proposal = self._evaluate(x)
+            logqp = float((proposal[1].double() - proposal[2].double())[0])      # the step's one host sync
+            if ind == 0 and logqp_ref is None:
+                accept_seq[ind] = True
+            else:
+                accept_seq[ind] = lrand_arr[ind] < logqp_ref - logqp
+            if accept_seq[ind]:
+                logqp_ref, current = logqp, proposal
+            else:
+                prior.blockupdater.restore(x, ind)
+        if not return_state:
+            return accept_seq, logqp_ref
+        if current is None:                 # every proposal rejected and no earlier evaluation at hand
+            current = self._evaluate(x)
+        return accept_seq, logqp_ref, current
+
+
 class MCMCHistory:
     """Bookkeeping lists of a simulation (reference MCMCHistory, mcmc.py:223-294)."""
 

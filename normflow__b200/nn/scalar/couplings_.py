@@ -244,3 +244,102 @@ class RQSplineCoupling_(Coupling_):
                               mask=self.mask if mask is None else mask, label=self.label,
                               channels_axis=self.channels_axis, xlim=self.xlim, ylim=self.ylim,
                               knots_x=self.knots_x, knots_y=self.knots_y, extrap=self.extrap)
+
+
+class MultiRQSplineCoupling_(Coupling_):
+    """One rational-quadratic spline per extra channel of the data (reference
+    couplings_.py:279-436): the field is (B, S, *L) with S = len(xlims) components, the
+    conditioner sees the frozen partition of all components, (B, 1, S, *L), and emits
+    S * (3K-2) channels, the i-th block of 3K-2 parametrising the spline of component i.
+
+    The S components are S independent per-site splines, so they run as ONE launch of the
+    spline kernel on the (B*S, *L) view of the field whenever the components share their limits
+    and extrapolation (the default), and as S launches otherwise.
+    """
+
+    def __init__(self, nets, *, mask, xlims=[(0, 1), (0, 1)], ylims=[(0, 1), (0, 1)],
+                 knots_x=[None, None], knots_y=[None, None], extraps=[{}, {}], **kwargs):
+        super().__init__(nets, mask=mask, **kwargs)
+        if any(k is not None for k in knots_x) or any(k is not None for k in knots_y):
+            raise NotImplementedError("MultiRQSplineCoupling_ with fixed knots_x / knots_y is outside the "
+                                      "accelerated hot path")
+        if not (len(xlims) == len(ylims) == len(extraps)):
+            raise ValueError("xlims, ylims and extraps must have one entry per spline")
+        if self.channels_axis != 1:
+            raise NotImplementedError("the accelerated couplings assume channels_axis == 1")
+        self.num_splines = len(xlims)
+        self.xlims, self.ylims = xlims, ylims
+        self.xwidths = [lim[1] - lim[0] for lim in xlims]
+        self.ywidths = [lim[1] - lim[0] for lim in ylims]
+        self.knots_x, self.knots_y = knots_x, knots_y
+        self.extraps = extraps
+
+    def _uniform(self):
+        first = (tuple(self.xlims[0]), tuple(self.ylims[0]), dict(self.extraps[0]))
+        return all((tuple(a), tuple(b), dict(c)) == first
+                   for a, b, c in zip(self.xlims, self.ylims, self.extraps))
+
+    def _check(self, x, out):
+        S = self.num_splines
+        if x.dim() != 2 + len(self.mask.shape) or x.shape[1] != S:
+            raise ValueError(f"MultiRQSplineCoupling_ with {S} splines expects data of shape (B, {S}, *lattice), "
+                             f"got {tuple(x.shape)}")
+        if out.shape[1] % S != 0 or (out.shape[1] // S + 2) % 3 != 0 or tuple(out.shape[2:]) != tuple(x.shape[2:]):
+            raise ValueError(f"conditioner output {tuple(out.shape)}: need {S} x (3K-2) channels on the lattice")
+        return out.shape[1] // S
+
+    def _transform(self, x, out, parity, log0, frozen_mode, inverse):
+        P = self._check(x, out)
+        B, S, lat = x.shape[0], self.num_splines, tuple(x.shape[2:])
+        K = (P + 2) // 3
+        if self._uniform():
+            prm = _ops.rqs_params(K, self.xlims[0], self.ylims[0], self.extraps[0])
+            y, logj = _ops.rqs_apply(x.reshape(B * S, *lat), out.reshape(B * S, P, *lat), self.mask._mask,
+                                     parity, prm, 0, frozen_mode, inverse)
+            return y.reshape(B, S, *lat), log0 + logj.reshape(B, S).sum(dim=1)
+        ys = []
+        for i in range(S):
+            prm = _ops.rqs_params(K, self.xlims[i], self.ylims[i], self.extraps[i])
+            yi, log0 = _ops.rqs_apply(x[:, i].contiguous(), out[:, i * P:(i + 1) * P].contiguous(),
+                                      self.mask._mask, parity, prm, log0, frozen_mode, inverse)
+            ys.append(yi)
+        return torch.stack(ys, dim=1), log0
+
+    def _frozen(self, x, parity):
+        B, S, lat = x.shape[0], x.shape[1], tuple(x.shape[2:])
+        keep = 0 if parity == 0 else 1
+        return _ops.mask_select(x.reshape(B * S, *lat), self.mask._mask, keep).reshape(B, S, *lat)
+
+    def _multi_sweep(self, x, log0, inverse):
+        order = range(len(self.nets))
+        for k in (reversed(order) if inverse else order):
+            p = k % 2
+            out = self.nets[k](self.preprocess_fz(self._frozen(x, p)))
+            x, log0 = self._transform(x, out, p, log0, _C.FROZEN_COPY, inverse)
+        return x, log0
+
+    def forward(self, x, log0=0):
+        return self._multi_sweep(x, log0, inverse=False)
+
+    def backward(self, x, log0=0):
+        return self._multi_sweep(x, log0, inverse=True)
+
+    def atomic_forward(self, *, x_active, x_frozen, parity, net, log0=0):
+        out = net(self.preprocess_fz(x_frozen))
+        return self._transform(x_active, out, parity, log0, _C.FROZEN_ZERO, False)
+
+    def atomic_backward(self, *, x_active, x_frozen, parity, net, log0=0):
+        out = net(self.preprocess_fz(x_frozen))
+        return self._transform(x_active, out, parity, log0, _C.FROZEN_ZERO, True)
+
+    def preprocess(self, x):
+        return torch.tensor_split(x, self.num_splines, dim=self.channels_axis)
+
+    def postprocess(self, xs):
+        return torch.cat(xs, dim=self.channels_axis)
+
+    def transfer(self, scale_factor=1, mask=None, **extra):
+        return self.__class__([net.transfer(scale_factor=scale_factor) for net in self.nets],
+                              mask=self.mask if mask is None else mask, label=self.label,
+                              channels_axis=self.channels_axis, xlims=self.xlims, ylims=self.ylims,
+                              knots_x=self.knots_x, knots_y=self.knots_y, extraps=self.extraps)

@@ -5,6 +5,8 @@ carries every point of (0,1) as the pair (s, 1-s), so the tails keep float32 rel
 accuracy, and reduces the three log-Jacobians per sample in the same pass.
 """
 
+import copy
+
 import numpy as np
 import torch
 
@@ -160,6 +162,11 @@ class DistConvertor_(ModuleList_):
         super().__init__(nets_)
         self.label = label
         self.symmetric = symmetric
+
+    def transfer(self, **kwargs):
+        """A pointwise map does not depend on the lattice: a deep copy.  (The reference inherits
+        ModuleList_.transfer here, which calls DistConvertor_(list_of_layers) and raises TypeError.)"""
+        return copy.deepcopy(self)
 
     def _layer(self, label):
         for net_ in self:

@@ -109,6 +109,16 @@ class NormalPrior(Prior):
         loc, scale = self._args()
         return _ops.prior_logprob(x, loc, scale)
 
+    def setup_blockupdater(self, block_len):
+        """Attach `self.blockupdater`, which redraws one block of `block_len` consecutive variables
+        of a batch in place (prior.py:106-112; like the reference it takes loc / scale of the first
+        block for every block).  Its draws come from a Philox stream range of their own, far from
+        the one `sample` walks, so proposals never repeat values this prior has already produced."""
+        chopped = NormalPrior(loc=self._loc.reshape(-1)[:block_len], scale=self._scale.reshape(-1)[:block_len])
+        chopped._standard = self._standard
+        chopped._calls = (1 << 40) + self._calls
+        self.blockupdater = BlockUpdater(chopped, block_len)
+
     def to(self, *args, **kwargs):
         """Move loc/scale; samples are created on the same device (prior.py:110-116).
         The kernels are float32, so a dtype request other than float32 is refused."""
@@ -127,3 +137,24 @@ class NormalPrior(Prior):
     @property
     def parameters(self):
         return dict(loc=self._loc, scale=self._scale)
+
+
+class BlockUpdater:
+    """In-place redraw / restore of block `block_ind` of every sample of a batch, the field seen
+    as (B, n_blocks, block_len) (reference BlockUpdater, prior.py:161-178)."""
+
+    def __init__(self, chopped_prior, block_len):
+        self.block_len = block_len
+        self.chopped_prior = chopped_prior
+        self.backup_block = None
+
+    def _blocks(self, x):
+        return x.view(x.shape[0], -1, self.block_len)
+
+    def __call__(self, x, block_ind):
+        blocks = self._blocks(x)
+        self.backup_block = blocks[:, block_ind].clone()
+        blocks[:, block_ind] = self.chopped_prior.sample(x.shape[0])
+
+    def restore(self, x, block_ind, restore_ind=slice(None)):
+        self._blocks(x)[restore_ind, block_ind] = self.backup_block[restore_ind]

@@ -450,6 +450,41 @@ def make_convact_step(kind, layers, acts, mask, **kw):
     return step
 
 
+def multi_rqs_atomic(x_active, out, mask, parity, log0, *, xlims, ylims, extraps, inverse=False):
+    """MultiRQSplineCoupling_.atomic_forward / atomic_backward, couplings_.py:313-336 with
+    make_spline :349-413 (no fixed knots): data (B,S,*L); `out` (B, S*(3K-2), *L) split into S equal
+    blocks, block i parametrising the spline of component i; log g summed over components."""
+    S = len(xlims)
+    P = out.shape[1] // S
+    ys = []
+    for i in range(S):
+        yi, log0 = rqs_atomic(x_active[:, i], out[:, i * P:(i + 1) * P], mask, parity, log0,
+                              xlim=xlims[i], ylim=ylims[i], extrap=extraps[i], inverse=inverse)
+        ys.append(yi)
+    return np.stack(ys, axis=1), log0
+
+
+def make_multi_rqs_step(layers, acts, mask, **kw):
+    """Atomic step of MultiRQSplineCoupling_ whose conditioner takes the S components of the frozen
+    field as input channels (the (B,1,S,*L) tensor of preprocess_fz with its unit axis squeezed)."""
+    def step(x_active, x_frozen, parity, log0, inverse):
+        out = convact_forward(x_frozen, layers, acts)
+        return multi_rqs_atomic(x_active, out, mask, parity, log0, inverse=inverse, **kw)
+    return step
+
+
+def cntr_coupling_forward(x, control, log0, mask, steps, inverse=False):
+    """DirectCntrCoupling_.forward / backward, cntr_couplings_.py:20-52: as coupling_forward, but
+    step 0 is conditioned on `control` instead of the frozen partition."""
+    parts = list(mask_split(mask, x))
+    order = range(len(steps))
+    for k in (reversed(order) if inverse else order):
+        p = k % 2
+        frozen = control if k == 0 else parts[1 - p]
+        parts[p], log0 = steps[k](parts[p], frozen, p, log0, inverse)
+    return parts[0] + parts[1], log0
+
+
 # =============================================================================
 # DistConvertor_  (src/nn/scalar/modules_.py:93-114, 277-302, 333-383)
 # =============================================================================
@@ -626,6 +661,40 @@ def mcmc_accept_reject(y, logq, logp, uniforms, ref):
 # =============================================================================
 # whole-path drivers
 # =============================================================================
+def blocked_mcmc(x, evaluate, proposals, log_uniforms, n_samples, n_blocks, logqp_ref=None):
+    """BlockedMCMCSampler.sample__ + sweep, mcmc.py:143-219, for one chain.
+    x: (1, *L) prior-space configuration (modified in place); evaluate(x) -> (y, logq, logp);
+    proposals: iterator of block redraws (1, block_len); log_uniforms: iterator of arrays of
+    n_blocks log-uniforms, one per sweep.  Returns cfgs, logq, logp, accept flags, last logqp_ref."""
+    shape = x.shape
+    block_len = x.size // n_blocks
+    cfgs, logqs, logps = [], [], []
+    accept = np.empty((n_samples, n_blocks), dtype=bool)
+    for ind in range(n_samples):
+        lrand = next(log_uniforms)
+        for b in range(n_blocks):
+            view = x.reshape(1, -1, block_len)
+            backup = view[:, b].copy()
+            view[:, b] = next(proposals)
+            x = view.reshape(shape)
+            _, logq, logp = evaluate(x)
+            if b == 0 and logqp_ref is None:
+                accept[ind, b] = True
+            else:
+                accept[ind, b] = lrand[b] < logqp_ref - (logq - logp)[0]
+            if accept[ind, b]:
+                logqp_ref = float((logq - logp)[0])
+            else:
+                view = x.reshape(1, -1, block_len)
+                view[:, b] = backup
+                x = view.reshape(shape)
+        y, logq, logp = evaluate(x)
+        cfgs.append(y[0])
+        logqs.append(logq[0])
+        logps.append(logp[0])
+    return np.stack(cfgs), np.array(logqs), np.array(logps), accept, logqp_ref, x
+
+
 def posterior_sample__(x, flow, action_kwargs, loc=0.0, scale=1.0):
     """Posterior.sample_ / sample__, src/_normflowcore.py:87-111, with the prior
     draw `x` passed in: returns (y, logq, logp)."""

@@ -35,9 +35,10 @@ from normflow_ref.action import ScalarPhi4Action  # noqa: E402
 from normflow_ref.prior import NormalPrior  # noqa: E402
 from normflow_ref.nn import (ModuleList_, ConvAct, AffineCoupling_, ShiftCoupling_,  # noqa: E402
                              RQSplineCoupling_, DistConvertor_, Identity_,
-                             FFTNet_, MeanFieldNet_, PSDBlock_)
+                             FFTNet_, MeanFieldNet_, PSDBlock_, MultiRQSplineCoupling_,
+                             CntrAffineCoupling_, CntrRQSplineCoupling_, CntrShiftCoupling_)
 from normflow_ref.lib.spline import RQSpline  # noqa: E402
-from normflow_ref.mcmc.mcmc import Metropolis, MCMCSampler  # noqa: E402
+from normflow_ref.mcmc.mcmc import Metropolis, MCMCSampler, BlockedMCMCSampler  # noqa: E402
 from normflow_ref import Model  # noqa: E402
 
 assert torch.get_default_dtype() == torch.float64
@@ -556,6 +557,173 @@ def gen_model_psd_affine():
     save("model_psd_affine", **res)
 
 
+def gen_snapshot():
+    """On-disk formats written BY THE REFERENCE: a training snapshot
+    {"MODEL_STATE", "EPOCHS_RUN"} saved by Fitter._save_snapshot (_normflowcore.py:236-247) after
+    3 CPU epochs of the scalar_affine example net on 8x8, the same weights as a text blob
+    (ModuleList_.get_weights_blob, nn/_core.py:108-111), the flow's output on a fixed input, and the
+    state_dict layout of a 4-D net (Conv4d keys)."""
+    import shutil
+    torch.manual_seed(181)
+    lat = (8, 8)
+    mf = MeanFieldNet_.build(knots_len=10, symmetric=True, final_scale=True, smooth=True)
+    ff = FFTNet_.build(lat, knots_len=10, ignore_zeromode=True)
+    conv = dict(in_channels=1, out_channels=2, hidden_sizes=[8, 8], kernel_size=3,
+                padding_mode='circular', conv_dim=2, acts=('tanh', 'tanh', None), bias=False)
+    net_ = ModuleList_([
+        PSDBlock_(mfnet_=mf, fftnet_=ff),
+        DistConvertor_(12, symmetric=True, smooth=True),
+        AffineCoupling_([ConvAct(**conv) for _ in range(4)], mask=EvenOddMask(shape=lat)),
+        DistConvertor_(12, symmetric=True, smooth=True)])
+    model = Model(net_=net_, prior=NormalPrior(shape=lat), action=ScalarPhi4Action(**ACTION))
+    tmp = tempfile.mkdtemp()
+    model.fit(n_epochs=3, batch_size=32, save_every=3,
+              checkpoint_dict=dict(print_stride=10, snapshot_path=os.path.join(tmp, "ref_affine.E0.tar")))
+    shutil.copy(os.path.join(tmp, "ref_affine.E3.tar"), os.path.join(HERE, "ref_affine.E3.tar"))
+    with open(os.path.join(HERE, "ref_affine_blob.txt"), "w") as fh:
+        fh.write(net_.get_weights_blob() + "\n")
+    x = randn32(4, *lat, seed=182)
+    with torch.no_grad():
+        y, logJ = net_(x)
+    res = dict(x=npy(x), y=npy(y), logJ=npy(logJ),
+               keys=np.array(list(net_.state_dict().keys())),
+               shapes=np.array([",".join(map(str, v.shape)) for v in net_.state_dict().values()]),
+               dtypes=np.array([str(v.dtype) for v in net_.state_dict().values()]))
+    # 4-D net: layout only
+    torch.manual_seed(183)
+    lat4 = (4, 4, 4, 4)
+    conv4 = dict(in_channels=1, out_channels=2, hidden_sizes=[4], kernel_size=3, padding_mode='circular',
+                 conv_dim=4, acts=('tanh', None), bias=True)
+    net4 = ModuleList_([AffineCoupling_([ConvAct(**conv4) for _ in range(2)], mask=EvenOddMask(shape=lat4))])
+    res["keys4d"] = np.array(list(net4.state_dict().keys()))
+    res["shapes4d"] = np.array([",".join(map(str, v.shape)) for v in net4.state_dict().values()])
+    save("snapshot_layout", **res)
+    print("wrote ref_affine.E3.tar", os.path.getsize(os.path.join(HERE, "ref_affine.E3.tar")), "bytes")
+
+
+class SqueezeChannel(torch.nn.Module):
+    """Conditioner wrapper for multi-component data: Coupling_.preprocess_fz hands the frozen field
+    over as (B, 1, S, *L); the convolution wants the S components as its input channels."""
+
+    def __init__(self, net):
+        super().__init__()
+        self.net = net
+
+    def forward(self, x):
+        return self.net(x.squeeze(1))
+
+
+def _record_flow(tag, net_, x, res, seed, inv_in):
+    B = x.shape[0]
+    x.requires_grad_(True)
+    y, logJ = net_(x)
+    if not (torch.is_tensor(logJ) and logJ.dim() > 0):
+        logJ = torch.zeros(B) + logJ
+    r, c = randn32(*x.shape, seed=seed + 1), randn32(B, seed=seed + 2)
+    L = (y * r).sum() + (logJ * c).sum()
+    names = [n for n, _ in net_.named_parameters()]
+    grads = torch.autograd.grad(L, [x] + list(net_.parameters()), allow_unused=True)
+    # the inverse direction on in-range points only: the reference's inverse loses all digits on the
+    # linear-extrapolation segments (a2 ~ 1e-16 in spline.py:262-281), where there is nothing to pin
+    with torch.no_grad():
+        xb, lb = net_.backward(inv_in, log0=c)
+    res.update({f"{tag}_x": npy(x), f"{tag}_y": npy(y), f"{tag}_logJ": npy(logJ), f"{tag}_r": npy(r),
+                f"{tag}_c": npy(c), f"{tag}_gx": npy(grads[0]), f"{tag}_inv_in": npy(inv_in),
+                f"{tag}_inv_x": npy(xb), f"{tag}_inv_log": npy(lb), f"{tag}_param_names": np.array(names)})
+    for n, p, g in zip(names, net_.parameters(), grads[1:]):
+        res[f"{tag}_w_{n}"] = npy(p)
+        res[f"{tag}_grad_{n}"] = npy(g if g is not None else torch.zeros_like(p))
+
+
+def gen_rank4_couplings():
+    """MultiRQSplineCoupling_ (couplings_.py:279-436) and the controlled couplings
+    (cntr_couplings_.py) on small lattices."""
+    res = {}
+    lat = (4, 6)
+    mask = EvenOddMask(shape=lat)
+    K = 5
+    lin = dict(left='linear', right='linear')
+    for tag, xlims, ylims, extraps in [
+            ("multi_uniform", [(-3, 3)] * 2, [(-3, 3)] * 2, [lin, lin]),
+            ("multi_mixed", [(-3, 3), (-2, 2.5), (-4, 4)], [(-3, 3), (-2, 2.5), (-4, 4)], [lin, lin, {}])]:
+        torch.manual_seed(191)
+        S = len(xlims)
+        nets = [SqueezeChannel(ConvAct(S, S * (3 * K - 2), 3, hidden_sizes=[4], acts=('tanh', None)))
+                for _ in range(3)]
+        for n in nets:
+            round_params(n)
+        cpl = MultiRQSplineCoupling_(nets, mask=mask, xlims=xlims, ylims=ylims, extraps=extraps,
+                                     knots_x=[None] * S, knots_y=[None] * S)
+        x = f32(randn32(3, S, *lat, seed=192) * 1.5)
+        inv_in = f32(torch.tanh(randn32(3, S, *lat, seed=196)) * 1.8)
+        _record_flow(tag, cpl, x, res, seed=193, inv_in=inv_in)
+    # controlled couplings: the generator hands out a recorded control field
+    for tag, cls, P, kw in [("cntr_affine", CntrAffineCoupling_, 2, {}),
+                            ("cntr_shift", CntrShiftCoupling_, 1, {}),
+                            ("cntr_rqs", CntrRQSplineCoupling_, 3 * K - 2,
+                             dict(xlim=(-4, 4), ylim=(-4, 4), extrap=lin))]:
+        torch.manual_seed(201)
+        nets = [ConvAct(1, P, 3, hidden_sizes=[4], acts=('tanh', None)) for _ in range(3)]
+        for n in nets:
+            round_params(n)
+        control = randn32(3, *lat, seed=202)
+        cpl = cls(nets, mask=mask, control_generator=lambda B, c=control: c[:B], **kw)
+        x = f32(randn32(3, *lat, seed=203) * 1.5)
+        inv_in = f32(torch.tanh(randn32(3, *lat, seed=206)) * 1.8)
+        cpl(x.detach())                  # a forward call sets the control used by backward
+        _record_flow(tag, cpl, x, res, seed=204, inv_in=inv_in)
+        res[f"{tag}_control"] = npy(control)
+    save("rank4_couplings", **res)
+
+
+def gen_blocked_mcmc():
+    """BlockedMCMCSampler (mcmc.py:132-219) on a 4x4 lattice with an affine flow: the block proposals
+    drawn by the reference are recorded so that the same chain can be replayed elsewhere; decisions
+    use np.random (seed 9) as in the reference."""
+    torch.manual_seed(211)
+    lat = (4, 4)
+    nets = [ConvAct(1, 2, 3, hidden_sizes=[4], acts=('tanh', None)) for _ in range(2)]
+    for n in nets:
+        round_params(n)
+    net_ = ModuleList_([AffineCoupling_(nets, mask=EvenOddMask(shape=lat))])
+    prior = NormalPrior(shape=lat)
+    model = Model(net_=net_, prior=prior, action=ScalarPhi4Action(**ACTION))
+    sampler = BlockedMCMCSampler(model)
+    x0 = randn32(1, *lat, seed=212)
+    draws = []
+    g = torch.Generator('cpu').manual_seed(213)
+
+    def fake_sample(batch_size=1):
+        return x0.clone()
+    prior.sample = fake_sample
+    orig_setup = prior.setup_blockupdater
+
+    def setup(block_len):
+        orig_setup(block_len)
+
+        def chopped_sample(batch_size=1):
+            d = torch.randn(batch_size, block_len, generator=g, dtype=torch.float32).double()
+            draws.append(npy(d))
+            return d
+        prior.blockupdater.chopped_prior.sample = chopped_sample
+    prior.setup_blockupdater = setup
+    res = dict(x0=npy(x0), lat=np.array(lat))
+    np.random.seed(9)
+    for call, (B, nb) in enumerate([(6, 4), (5, 4), (4, 2)]):
+        cfgs, logq, logp = sampler.sample__(batch_size=B, n_blocks=nb, bookkeeping=True)
+        res.update({f"call{call}_cfgs": npy(cfgs), f"call{call}_logq": npy(logq), f"call{call}_logp": npy(logp),
+                    f"call{call}_accept_seq": sampler.history.accept_seq[-1],
+                    f"call{call}_accept_rate": np.array(sampler.history.accept_rate[-1]),
+                    f"call{call}_shape": np.array([B, nb])})
+    res["draws"] = np.concatenate([d.ravel() for d in draws])
+    res["draw_lens"] = np.array([d.size for d in draws])
+    for key, val in conv_layers(nets[0]).items():
+        res[f"step0_{key}"] = val
+    for key, val in conv_layers(nets[1]).items():
+        res[f"step1_{key}"] = val
+    save("blocked_mcmc", **res)
+
+
 if __name__ == "__main__":
     only = set(sys.argv[1:])           # e.g. `make_golden.py psd model_psd_affine`
 
@@ -598,3 +766,9 @@ if __name__ == "__main__":
         gen_psd()
     if wanted("model_psd_affine"):
         gen_model_psd_affine()
+    if wanted("snapshot"):
+        gen_snapshot()
+    if wanted("rank4_couplings"):
+        gen_rank4_couplings()
+    if wanted("blocked_mcmc"):
+        gen_blocked_mcmc()
