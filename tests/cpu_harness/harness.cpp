@@ -13,6 +13,7 @@
 #include "../../include/normflow_b200.h"
 #include "../../normflow__b200/csrc/nfk_ops.cuh"
 #include "../../normflow__b200/csrc/nfk_fused.cuh"
+#include "../../normflow__b200/csrc/nfk_knots.cuh"
 
 using namespace nfk;
 
@@ -36,6 +37,17 @@ static RqsCfg to_cfg(const nfk_rqs_params& p) {
 #define FOR_EACH_K(X) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(14) X(16) X(20) X(24) X(32)
 
 extern "C" {
+
+int cpu_knots_fwd(const float* wx, const float* wy, const float* wd, int K, float xlo, float xw, float ylo,
+                  float yw, float* table) {
+    knots_fwd_body(KnotArgs{wx, wy, wd, K, xlo, xw, ylo, yw}, table);
+    return 0;
+}
+int cpu_knots_bwd(const float* wx, const float* wy, const float* wd, int K, float xlo, float xw, float ylo,
+                  float yw, const float* g, float* gwx, float* gwy, float* gwd) {
+    knots_bwd_body(KnotArgs{wx, wy, wd, K, xlo, xw, ylo, yw}, g, gwx, gwy, gwd);
+    return 0;
+}
 
 int cpu_mask_evenodd(uint8_t* mask, nfk_lattice lat, int parity, int exclude_mu) {
     const Lat l = make_lat(lat.ndim, lat.shape);

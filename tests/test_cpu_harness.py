@@ -167,17 +167,51 @@ def test_rqs_kernel(tag, left, right):
 
 
 def _knots(wx, wy, wd, lim, both_ends=True):
-    """Knot table exactly as the python layer builds it: float32, cumulative softmax sums
-    from both ends (normflow__b200.nn.scalar.modules.SplineNet.knots)."""
-    import torch
-    from normflow__b200.nn.scalar.modules import SplineNet
-    net = SplineNet(len(wx) + 1, xlim=lim, ylim=lim, smooth=wd is None)
-    with torch.no_grad():
-        net.weights_x.copy_(torch.as_tensor(np.asarray(wx), dtype=torch.float32))
-        net.weights_y.copy_(torch.as_tensor(np.asarray(wy), dtype=torch.float32))
-        if wd is not None:
-            net.weights_d.copy_(torch.as_tensor(np.asarray(wd), dtype=torch.float32))
-        return f32(net.knots(both_ends=both_ends).cpu().numpy())
+    """Knot table exactly as the product builds it: the knot kernel's own arithmetic
+    (nfk_knots.cuh) -- float32 table, cumulative softmax sums from both ends."""
+    wx, wy = f32(wx), f32(wy)
+    wd = None if wd is None else f32(wd)
+    K = len(wx) + 1
+    table = np.empty((5, K), dtype=np.float32)
+    H.cpu_knots_fwd(fp(wx), fp(wy), fp(wd), K, ctypes.c_float(lim[0]), ctypes.c_float(lim[1] - lim[0]),
+                    ctypes.c_float(lim[0]), ctypes.c_float(lim[1] - lim[0]), fp(table))
+    return table if both_ends else table[:3].copy()
+
+
+def test_knot_table_against_oracle_and_central_differences():
+    """nfk_knots.cuh forward vs the oracle's splinenet_knots (SplineNet.make_spline, modules.py:369-391)
+    and its adjoint vs central differences of the oracle, smooth and free derivatives."""
+    from oracle import nf_oracle as O
+    rs = np.random.RandomState(2)
+    for K, smooth, lim in [(2, True, (0.0, 1.0)), (10, False, (0.5, 1.0)), (12, True, (0.0, 1.0)), (50, False, (-2.0, 3.0))]:
+        wx, wy = f32(rs.randn(K - 1)), f32(rs.randn(K - 1))
+        wd = None if smooth else f32(rs.randn(K) * 2)
+        table = _knots(wx, wy, wd, lim)
+
+        def ref_table(wx_, wy_, wd_):
+            kx, ky, kd = O.splinenet_knots(wx_, wy_, wd_, xlim=lim, ylim=lim)
+            if kd is None:
+                kd = O.smooth_derivatives(kx, ky, 0)
+            return np.stack([kx, ky, kd, lim[1] - kx, lim[1] - ky])
+        args64 = [wx.astype(np.float64), wy.astype(np.float64)] + ([] if smooth else [wd.astype(np.float64)])
+        ref = ref_table(args64[0], args64[1], None if smooth else args64[2])
+        close(table, ref, tol=3e-7)
+        assert table[0, -1] == np.float32(lim[1]) and table[3, -1] == 0
+        r = f32(rs.randn(5, K))
+        gwx, gwy = np.empty(K - 1, dtype=np.float32), np.empty(K - 1, dtype=np.float32)
+        gwd = None if smooth else np.empty(K, dtype=np.float32)
+        H.cpu_knots_bwd(fp(wx), fp(wy), fp(wd), K, ctypes.c_float(lim[0]), ctypes.c_float(lim[1] - lim[0]),
+                        ctypes.c_float(lim[0]), ctypes.c_float(lim[1] - lim[0]), fp(r), fp(gwx), fp(gwy), fp(gwd))
+        for j, got in enumerate([gwx, gwy] + ([] if smooth else [gwd])):
+            num = np.empty_like(got, dtype=np.float64)
+            for i in range(len(got)):
+                vals = []
+                for sgn in (1, -1):
+                    a = [v.copy() for v in args64]
+                    a[j][i] += sgn * 1e-6
+                    vals.append((ref_table(a[0], a[1], None if smooth else a[2]) * r).sum())
+                num[i] = (vals[0] - vals[1]) / 2e-6
+            close_grad(got, num, tol=2e-6)
 
 
 @pytest.mark.parametrize("tag,symmetric", [("zd_sym", True), ("lat_sym_smooth", True), ("lat_asym", False)])
