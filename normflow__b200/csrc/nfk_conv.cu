@@ -367,6 +367,7 @@ struct Wgrad2dArgs {
     int L0, L1, R, Ci, Co;
     long long B;
     int g_parity;             // SPARSE: gpre vanishes on sites with (row + col) % 2 != g_parity
+    int G;                    // small-lattice kernel: samples staged together per pipeline step
 };
 
 // SPARSE: the gradient handed in is that of a checkerboard coupling's conditioner output, which
@@ -397,49 +398,75 @@ __global__ void __launch_bounds__(288, 2) conv2d_wgrad_kernel(Wgrad2dArgs a) {
         for (int r0 = 0; r0 < L0; r0 += R) {
             const int rows = L0 - r0 < R ? L0 - r0 : R;
             __syncthreads();                        // previous strip consumed
-            // staging: one warp per (channel, row) line, lanes over the columns
-            for (int p = warp; p < CI * (rows + 2); p += 9) {
-                const int ci = p / (rows + 2), j = p - ci * (rows + 2);
-                int r = r0 - 1 + j;
-                r = r < 0 ? r + L0 : (r >= L0 ? r - L0 : r);
-                const float* src = in_b + ci * V + r * L1;
-                const uint8_t* msk = a.in_mask ? a.in_mask + r * L1 : nullptr;
-                float* dst = in_s + (ci * (R + 2) + j) * LW;
-                for (int k = lane; k < LW; k += 32) {
+            if (L1 < 32) {
+                // short rows: every element is one item of a flat list spread over the CTA
+                for (int it = tid; it < CI * (rows + 2) * LW; it += 288) {
+                    const int p = it / LW, k = it - p * LW;
+                    const int ci = p / (rows + 2), j = p - ci * (rows + 2);
+                    int r = r0 - 1 + j;
+                    r = r < 0 ? r + L0 : (r >= L0 ? r - L0 : r);
                     int c = k - 1;
                     c = c < 0 ? c + L1 : (c >= L1 ? c - L1 : c);
-                    float v = __ldg(src + c);
-                    if (msk && __ldg(msk + c) != (uint8_t)a.in_keep) v = 0.f;
-                    dst[k] = v;
+                    float v = __ldg(in_b + ci * V + r * L1 + c);
+                    if (a.in_mask && __ldg(a.in_mask + r * L1 + c) != (uint8_t)a.in_keep) v = 0.f;
+                    in_s[(ci * (R + 2) + j) * LW + k] = v;
                 }
-            }
-            for (int p = warp; p < CO_B * rows; p += 9) {
-                const int co = p / rows, j = p - co * rows;
-                const float* src = g_b + (long long)co * V + (r0 + j) * L1;
-                float* dst = g_s + (co * R + j) * L1;
-                const bool live = co0 + co < a.Co;
-                for (int c = lane; c < L1; c += 32) dst[c] = live ? __ldg(src + c) : 0.f;
+                for (int it = tid; it < CO_B * rows * L1; it += 288) {
+                    const int p = it / L1, c = it - p * L1;
+                    const int co = p / rows, j = p - co * rows;
+                    g_s[(co * R + j) * L1 + c] = co0 + co < a.Co ? __ldg(g_b + (long long)co * V + (r0 + j) * L1 + c) : 0.f;
+                }
+            } else {
+                // staging: one warp per (channel, row) line, lanes over the columns
+                for (int p = warp; p < CI * (rows + 2); p += 9) {
+                    const int ci = p / (rows + 2), j = p - ci * (rows + 2);
+                    int r = r0 - 1 + j;
+                    r = r < 0 ? r + L0 : (r >= L0 ? r - L0 : r);
+                    const float* src = in_b + ci * V + r * L1;
+                    const uint8_t* msk = a.in_mask ? a.in_mask + r * L1 : nullptr;
+                    float* dst = in_s + (ci * (R + 2) + j) * LW;
+                    for (int k = lane; k < LW; k += 32) {
+                        int c = k - 1;
+                        c = c < 0 ? c + L1 : (c >= L1 ? c - L1 : c);
+                        float v = __ldg(src + c);
+                        if (msk && __ldg(msk + c) != (uint8_t)a.in_keep) v = 0.f;
+                        dst[k] = v;
+                    }
+                }
+                for (int p = warp; p < CO_B * rows; p += 9) {
+                    const int co = p / rows, j = p - co * rows;
+                    const float* src = g_b + (long long)co * V + (r0 + j) * L1;
+                    float* dst = g_s + (co * R + j) * L1;
+                    const bool live = co0 + co < a.Co;
+                    for (int c = lane; c < L1; c += 32) dst[c] = live ? __ldg(src + c) : 0.f;
+                }
             }
             __syncthreads();
-            for (int j = 0; j < rows; ++j)
-                for (int cc = lane; cc < (SPARSE ? (L1 + 1) / 2 : L1); cc += 32) {
-                    const int c = SPARSE ? 2 * cc + ((a.g_parity + r0 + j) & 1) : cc;
-                    if (SPARSE && c >= L1) continue;
-                    float gv[CO_B], xv[CI];
+            auto site = [&](int j, int cc) {
+                const int c = SPARSE ? 2 * cc + ((a.g_parity + r0 + j) & 1) : cc;
+                if (SPARSE && c >= L1) return;
+                float gv[CO_B], xv[CI];
 #pragma unroll
-                    for (int co = 0; co < CO_B; ++co) gv[co] = g_s[(co * R + j) * L1 + c];
+                for (int co = 0; co < CO_B; ++co) gv[co] = g_s[(co * R + j) * L1 + c];
 #pragma unroll
-                    for (int ci = 0; ci < CI; ++ci) xv[ci] = in_s[(ci * (R + 2) + j + kh) * LW + c + kw];
+                for (int ci = 0; ci < CI; ++ci) xv[ci] = in_s[(ci * (R + 2) + j + kh) * LW + c + kw];
 #pragma unroll
-                    for (int co = 0; co < CO_B; ++co) {
+                for (int co = 0; co < CO_B; ++co) {
 #pragma unroll
-                        for (int ci = 0; ci < CI; ++ci) acc[co][ci] = fmaf(gv[co], xv[ci], acc[co][ci]);
-                    }
-                    if (warp == 4) {                // the centre-tap warp also sums the bias gradient
-#pragma unroll
-                        for (int co = 0; co < CO_B; ++co) accb[co] += gv[co];
-                    }
+                    for (int ci = 0; ci < CI; ++ci) acc[co][ci] = fmaf(gv[co], xv[ci], acc[co][ci]);
                 }
+                if (warp == 4) {                // the centre-tap warp also sums the bias gradient
+#pragma unroll
+                    for (int co = 0; co < CO_B; ++co) accb[co] += gv[co];
+                }
+            };
+            const int ncols = SPARSE ? (L1 + 1) / 2 : L1;
+            if (L1 < 32) {                      // short rows: lanes walk the flattened (row, column) sites
+                for (int t = lane; t < rows * ncols; t += 32) site(t / ncols, t % ncols);
+            } else {
+                for (int j = 0; j < rows; ++j)
+                    for (int cc = lane; cc < ncols; cc += 32) site(j, cc);
+            }
         }
     }
 #pragma unroll
@@ -609,6 +636,142 @@ static int wgrad2d_async_launch(Wgrad2dArgs a, cudaStream_t st) {
     return check_launch();
 }
 
+// Small lattices (a whole sample is one short strip, rows shorter than a warp): the kernel above
+// leaves most lanes idle (lanes map to columns) and pays two barriers per sample.  Here G samples are
+// staged per pipeline step, every copy is one item of a flat list spread over the CTA, and the lanes of
+// a tap's warp walk the flattened (sample, row, column) sites of the group.
+template <int CI, int CO_B, bool SPARSE>
+__global__ void __launch_bounds__(288, 2) conv2d_wgrad_small_kernel(Wgrad2dArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const int L0 = a.L0, L1 = a.L1, LW = L1 + 8, G = a.G;
+    const int in_floats = CI * (L0 + 2) * LW, slot_floats = in_floats + CO_B * L0 * L1;
+    const int buf_floats = G * slot_floats;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int kh = warp / 3, kw = warp % 3;
+    const int co0 = blockIdx.y * CO_B;
+    const int V = L0 * L1, nq = L1 >> 2;
+    float acc[CO_B][CI];
+    float accb[CO_B];
+#pragma unroll
+    for (int co = 0; co < CO_B; ++co) {
+        accb[co] = 0.f;
+#pragma unroll
+        for (int ci = 0; ci < CI; ++ci) acc[co][ci] = 0.f;
+    }
+    const long long n_mine = a.B > blockIdx.x ? (a.B - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long units = (n_mine + G - 1) / G;
+    const int in_lines = CI * (L0 + 2), g_lines = CO_B * L0;
+    const int in_items = in_lines * (nq + 2), g_items = g_lines * nq;
+
+    auto stage = [&](long long u, float* buf) {
+        const long long k0 = u * G;
+        const int ns = (int)(n_mine - k0 < G ? n_mine - k0 : G);
+        for (int it = tid; it < ns * in_items; it += 288) {
+            const int s = it / in_items, r1 = it - s * in_items;
+            const int line = r1 / (nq + 2), q = r1 - line * (nq + 2);
+            const int ci = line / (L0 + 2), j = line - ci * (L0 + 2);
+            int r = j - 1;
+            r = r < 0 ? r + L0 : (r >= L0 ? r - L0 : r);
+            const long long b = blockIdx.x + (k0 + s) * gridDim.x;
+            const float* src = a.in + (b * CI + ci) * (long long)V + r * L1;
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(buf + s * slot_floats + line * LW);
+            if (q < nq) cp_async16(dst + 16 + q * 16, src + q * 4, true);
+            else if (q == nq) cp_async4(dst + 12, src + L1 - 1);          // column -1
+            else cp_async4(dst + 16 + L1 * 4, src);                       // column L1
+        }
+        for (int it = tid; it < ns * g_items; it += 288) {
+            const int s = it / g_items, r1 = it - s * g_items;
+            const int line = r1 / nq, q = r1 - line * nq;
+            const int co = line / L0, j = line - co * L0;
+            const bool live = co0 + co < a.Co;
+            const long long b = blockIdx.x + (k0 + s) * gridDim.x;
+            const float* src = a.gpre + (b * a.Co + co0 + (live ? co : 0)) * (long long)V + j * L1;
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(buf + s * slot_floats + in_floats + line * L1);
+            cp_async16(dst + q * 16, src + q * 4, live);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    const int ncols = SPARSE ? L1 / 2 : L1;
+    const int per_sample = L0 * ncols;
+    if (units > 0) stage(0, sm);
+    for (long long u = 0; u < units; ++u) {
+        float* buf = sm + (u & 1) * buf_floats;
+        if (u + 1 < units) {
+            stage(u + 1, sm + ((u + 1) & 1) * buf_floats);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const long long k0 = u * G;
+        const int ns = (int)(n_mine - k0 < G ? n_mine - k0 : G);
+        for (int t = lane; t < ns * per_sample; t += 32) {
+            const int s = t / per_sample, r1 = t - s * per_sample;
+            const int j = r1 / ncols, cc = r1 - j * ncols;
+            const int c = SPARSE ? 2 * cc + ((a.g_parity + j) & 1) : cc;
+            const float* in_s = buf + s * slot_floats;
+            const float* g_s = in_s + in_floats;
+            float gv[CO_B], xv[CI];
+#pragma unroll
+            for (int co = 0; co < CO_B; ++co) gv[co] = g_s[(co * L0 + j) * L1 + c];
+#pragma unroll
+            for (int ci = 0; ci < CI; ++ci) xv[ci] = in_s[(ci * (L0 + 2) + j + kh) * LW + 3 + c + kw];
+#pragma unroll
+            for (int co = 0; co < CO_B; ++co) {
+#pragma unroll
+                for (int ci = 0; ci < CI; ++ci) acc[co][ci] = fmaf(gv[co], xv[ci], acc[co][ci]);
+            }
+            if (warp == 4) {
+#pragma unroll
+                for (int co = 0; co < CO_B; ++co) accb[co] += gv[co];
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int co = 0; co < CO_B; ++co) {
+#pragma unroll
+        for (int ci = 0; ci < CI; ++ci) {
+            const float v = warp_sum(acc[co][ci]);
+            if (lane == 0 && co0 + co < a.Co)
+                atomicAdd(a.gw + ((long long)(co0 + co) * CI + ci) * 9 + kh * 3 + kw, v);
+        }
+        if (warp == 4 && a.gbias) {
+            const float v = warp_sum(accb[co]);
+            if (lane == 0 && co0 + co < a.Co) atomicAdd(a.gbias + co0 + co, v);
+        }
+    }
+}
+
+// applies when one sample is at most 512 sites and its rows are shorter than a warp
+static bool wgrad2d_small_ok(const Wgrad2dArgs& a) { return a.L1 < 32 && a.L0 * a.L1 <= 512; }
+
+template <int CI, int CO_B, bool SPARSE>
+static int wgrad2d_small_launch(Wgrad2dArgs a, cudaStream_t st) {
+    const int LW = a.L1 + 8;
+    const size_t slot = (size_t)(CI * (a.L0 + 2) * LW + CO_B * a.L0 * a.L1) * sizeof(float);
+    int G = (int)(1024 / (a.L0 * a.L1));                                  // ~1024 sites per step
+    if (G < 1) G = 1;
+    if (G > 16) G = 16;
+    while (G > 1 && 2 * G * slot > 100 * 1024) --G;
+    if (2 * G * slot > 100 * 1024) return NFK_EUNSUPPORTED;
+    a.G = G;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(conv2d_wgrad_small_kernel<CI, CO_B, SPARSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             100 * 1024);
+        attr_set = true;
+    }
+    const int ncb = (a.Co + CO_B - 1) / CO_B;
+    long long gx = (148LL * 2 + ncb - 1) / ncb;
+    const long long groups = (a.B + G - 1) / G;
+    if (gx > groups) gx = groups;
+    if (gx < 1) gx = 1;
+    conv2d_wgrad_small_kernel<CI, CO_B, SPARSE><<<dim3((unsigned)gx, ncb), 288, 2 * G * slot, st>>>(a);
+    return check_launch();
+}
+
 static int conv_bwd_weight_impl(const float* in, const uint8_t* in_mask, int in_keep, const float* gpre,
                                 int g_parity, float* gw, float* gbias, nfk_lattice lat, int ksize, int Ci, int Co,
                                 int64_t B, void* stream);
@@ -639,6 +802,13 @@ static int conv_bwd_weight_impl(const float* in, const uint8_t* in_mask, int in_
         int rc = NFK_EUNSUPPORTED;
         const bool async_ok = Ci == 8 && !in_mask && lat.shape[1] % 4 == 0 && ((uintptr_t)in % 16) == 0 &&
                               ((uintptr_t)gpre % 16) == 0;
+        if (async_ok && wgrad2d_small_ok(w)) {                // small lattices: groups of samples per step
+            if (Co <= 8) rc = sparse ? wgrad2d_small_launch<8, 8, true>(w, NFK_STREAM(stream))
+                                     : wgrad2d_small_launch<8, 8, false>(w, NFK_STREAM(stream));
+            else rc = sparse ? wgrad2d_small_launch<8, 7, true>(w, NFK_STREAM(stream))
+                             : wgrad2d_small_launch<8, 7, false>(w, NFK_STREAM(stream));
+            if (rc != NFK_EUNSUPPORTED) return rc;
+        }
         if (async_ok) {                                       // strips streamed with cp.async, double-buffered
             if (Co <= 8) rc = sparse ? wgrad2d_async_launch<8, 8, true>(w, NFK_STREAM(stream))
                                      : wgrad2d_async_launch<8, 8, false>(w, NFK_STREAM(stream));

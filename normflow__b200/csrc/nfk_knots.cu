@@ -10,7 +10,8 @@
 //   table[3] = xlo + xw - knots_x, accumulated from the right end (sum_{i>=j} p_i), exact 0 at the end
 //   table[4] = ylo + yw - knots_y, likewise
 //
-// K is a few tens at most: one thread walks the arrays in double precision.
+// K is a few tens at most: one warp, double precision (exponentials strided over the lanes, running
+// sums on lane 0).
 #include "nfk_common.cuh"
 #include "nfk_knots.cuh"
 
@@ -18,13 +19,19 @@
 
 namespace nfk {
 
+struct KnotWarpSync {
+    __device__ void operator()() const { __syncwarp(); }
+};
+
 __global__ void knots_fwd_kernel(KnotArgs a, float* __restrict__ table) {
-    if (threadIdx.x == 0) knots_fwd_body(a, table);
+    __shared__ KnotScratch scratch;
+    knots_fwd_body(a, table, scratch, (int)threadIdx.x, 32, KnotWarpSync{});
 }
 
 __global__ void knots_bwd_kernel(KnotArgs a, const float* __restrict__ g, float* __restrict__ gwx,
                                  float* __restrict__ gwy, float* __restrict__ gwd) {
-    if (threadIdx.x == 0) knots_bwd_body(a, g, gwx, gwy, gwd);
+    __shared__ KnotScratch scratch;
+    knots_bwd_body(a, g, gwx, gwy, gwd, scratch, (int)threadIdx.x, 32, KnotWarpSync{});
 }
 
 }  // namespace nfk

@@ -40,12 +40,14 @@ extern "C" {
 
 int cpu_knots_fwd(const float* wx, const float* wy, const float* wd, int K, float xlo, float xw, float ylo,
                   float yw, float* table) {
-    knots_fwd_body(KnotArgs{wx, wy, wd, K, xlo, xw, ylo, yw}, table);
+    KnotScratch scratch;
+    knots_fwd_body(KnotArgs{wx, wy, wd, K, xlo, xw, ylo, yw}, table, scratch, 0, 1, KnotNoSync{});
     return 0;
 }
 int cpu_knots_bwd(const float* wx, const float* wy, const float* wd, int K, float xlo, float xw, float ylo,
                   float yw, const float* g, float* gwx, float* gwy, float* gwd) {
-    knots_bwd_body(KnotArgs{wx, wy, wd, K, xlo, xw, ylo, yw}, g, gwx, gwy, gwd);
+    KnotScratch scratch;
+    knots_bwd_body(KnotArgs{wx, wy, wd, K, xlo, xw, ylo, yw}, g, gwx, gwy, gwd, scratch, 0, 1, KnotNoSync{});
     return 0;
 }
 
