@@ -4,16 +4,36 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/normflow_b200.h"
 #include "nfk_ops.cuh"
 
 namespace nfk {
 
-extern unsigned long long g_launches;   // counted on the host at every launch
+extern std::atomic<unsigned long long> g_launches;   // counted on the host at every launch
 
 inline int check_launch() {
-    ++g_launches;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ECUDA;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel: raise it once per
+// (kernel, device), whichever thread gets there first.  `Kernel` is the kernel itself (a non-type
+// template parameter), so every instantiation has its own flags.
+template <auto Kernel>
+inline int ensure_dynamic_smem(int bytes) {
+    static std::atomic<unsigned long long> done[2] = {{0ull}, {0ull}};     // devices 0..127
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return NFK_ECUDA;
+    const bool tracked = dev >= 0 && dev < 128;
+    if (tracked && (done[dev >> 6].load(std::memory_order_acquire) >> (dev & 63) & 1ull)) return NFK_OK;
+    if (cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return NFK_ECUDA;
+    }
+    if (tracked) done[dev >> 6].fetch_or(1ull << (dev & 63), std::memory_order_release);
+    return NFK_OK;
 }
 
 inline Lat to_lat(const nfk_lattice& l) { return make_lat(l.ndim, l.shape); }

@@ -206,11 +206,7 @@ static int conv2d_tile_launch(const float* in, const float* w, int w_transposed,
     a.L0 = L0; a.L1 = L1; a.R = R; a.Ci = Ci; a.Co = Co; a.strips = (L0 + R - 1) / R;
     const size_t smem = (size_t)(kC2Chunk * (R + 2) * (L1 + 8) + kC2Chunk * 72) * sizeof(float);
     if (smem > 160 * 1024) return NFK_EUNSUPPORTED;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(conv2d_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        attr_set = true;
-    }
+    if (ensure_dynamic_smem<conv2d_tile_kernel>(160 * 1024) != NFK_OK) return NFK_ECUDA;
     const int threads = (R * nq + 31) / 32 * 32;
     conv2d_tile_kernel<<<dim3((unsigned)(B * a.strips), (unsigned)((Co + 7) / 8)), threads, smem, st>>>(a);
     return check_launch();
@@ -248,8 +244,8 @@ extern "C" int nfk_conv_circ_fwd(const float* in, const float* w, int w_transpos
     cudaStream_t st = NFK_STREAM(stream);
 #define LAUNCH(N)                                                                                     \
     {                                                                                                 \
-        if (smem > 48 * 1024)                                                                         \
-            cudaFuncSetAttribute(conv_fwd_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (smem > 48 * 1024 && ensure_dynamic_smem<conv_fwd_kernel<N>>(200 * 1024) != NFK_OK)        \
+            return NFK_ECUDA;                                                                         \
         conv_fwd_kernel<N><<<grid, threads, smem, st>>>(a);                                           \
     }
     switch (CO) {
@@ -492,11 +488,7 @@ static int wgrad2d_launch(Wgrad2dArgs a, cudaStream_t st) {
     while (R > 1 && bytes(R) > 72 * 1024) R /= 2;
     if (bytes(R) > 200 * 1024) return NFK_EUNSUPPORTED;
     a.R = R;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(conv2d_wgrad_kernel<CI, CO_B, SPARSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
+    if (ensure_dynamic_smem<conv2d_wgrad_kernel<CI, CO_B, SPARSE>>(200 * 1024) != NFK_OK) return NFK_ECUDA;
     const int ncb = (a.Co + CO_B - 1) / CO_B;
     long long gx = (148LL * 2 + ncb - 1) / ncb;            // two CTAs per SM in all
     if (gx > a.B) gx = a.B;
@@ -622,12 +614,7 @@ static int wgrad2d_async_launch(Wgrad2dArgs a, cudaStream_t st) {
     while (R > 1 && bytes(R) > 100 * 1024) R /= 2;                        // two CTAs per SM
     if (bytes(R) > 100 * 1024) return NFK_EUNSUPPORTED;
     a.R = R;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(conv2d_wgrad_async_kernel<CI, CO_B, SPARSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             100 * 1024);
-        attr_set = true;
-    }
+    if (ensure_dynamic_smem<conv2d_wgrad_async_kernel<CI, CO_B, SPARSE>>(100 * 1024) != NFK_OK) return NFK_ECUDA;
     const int ncb = (a.Co + CO_B - 1) / CO_B;
     long long gx = (148LL * 2 + ncb - 1) / ncb;
     if (gx > a.B) gx = a.B;
@@ -757,12 +744,7 @@ static int wgrad2d_small_launch(Wgrad2dArgs a, cudaStream_t st) {
     while (G > 1 && 2 * G * slot > 100 * 1024) --G;
     if (2 * G * slot > 100 * 1024) return NFK_EUNSUPPORTED;
     a.G = G;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(conv2d_wgrad_small_kernel<CI, CO_B, SPARSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             100 * 1024);
-        attr_set = true;
-    }
+    if (ensure_dynamic_smem<conv2d_wgrad_small_kernel<CI, CO_B, SPARSE>>(100 * 1024) != NFK_OK) return NFK_ECUDA;
     const int ncb = (a.Co + CO_B - 1) / CO_B;
     long long gx = (148LL * 2 + ncb - 1) / ncb;
     const long long groups = (a.B + G - 1) / G;

@@ -63,11 +63,7 @@ static int fused_launch(FusedArgs a, int64_t B, cudaStream_t st) {
     int threads = ((R + 2) * a.g.ncg + 31) / 32 * 32;
     if (threads > 288) threads = 288;
     if (threads < 32) threads = 32;
-    static bool attr_set = false;          // per instantiation
-    if (!attr_set) {
-        cudaFuncSetAttribute(fused2d_kernel<KIND, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
+    if (ensure_dynamic_smem<fused2d_kernel<KIND, K>>(200 * 1024) != NFK_OK) return NFK_ECUDA;
     fused2d_kernel<KIND, K><<<(unsigned)B, threads, smem, st>>>(a);
     return check_launch();
 }

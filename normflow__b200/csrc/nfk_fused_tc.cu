@@ -528,15 +528,18 @@ __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs 
 template <int KIND, int K, int INV, bool SAVE>
 int tc_launch(TcArgs a, cudaStream_t st) {
     constexpr int P = KIND == 0 ? 2 : 3 * K - 2;
-    static int sm_count = 0;
-    static int max_smem = 0;
-    if (sm_count == 0) {
+    // every GPU of a B200 box is the same part: queried once (thread-safe static initialisation)
+    struct Props { int sm_count, max_smem; };
+    static const Props props = [] {
+        Props p{0, 0};
         int dev = 0;
         cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        if (sm_count <= 0) sm_count = 148;
-    }
+        cudaDeviceGetAttribute(&p.sm_count, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&p.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (p.sm_count <= 0) p.sm_count = 148;
+        return p;
+    }();
+    const int sm_count = props.sm_count, max_smem = props.max_smem;
     // two CTAs per SM: each may use half of the SM's shared memory (minus the 1 KB system slice)
     const uint32_t budget = (uint32_t)((max_smem > 0 ? max_smem : 227 * 1024) + 1024) / 2 - 1024;
     int best = 0;
@@ -556,12 +559,7 @@ int tc_launch(TcArgs a, cudaStream_t st) {
     tc_plan<P>(a.g, best, budget);
     a.g.magic_ws = (uint32_t)((0x100000000ULL + a.g.WS - 1) / a.g.WS);
     a.g.magic_l1 = (uint32_t)((0x100000000ULL + a.g.L1 - 1) / a.g.L1);
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(fused2d_tc_kernel<KIND, K, INV, SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)budget) != cudaSuccess) return NFK_ECUDA;
-        attr_set = true;
-    }
+    if (ensure_dynamic_smem<fused2d_tc_kernel<KIND, K, INV, SAVE>>((int)budget) != NFK_OK) return NFK_ECUDA;
     long long grid = 2LL * sm_count;
     if (grid > a.B) grid = a.B;
     fused2d_tc_kernel<KIND, K, INV, SAVE><<<(unsigned)grid, kTcThreads, a.g.smem_bytes, st>>>(a);

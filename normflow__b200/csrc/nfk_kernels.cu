@@ -6,7 +6,7 @@
 #include "nfk_common.cuh"
 
 namespace nfk {
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
 }
 using namespace nfk;
 
@@ -22,7 +22,7 @@ extern "C" const char* nfk_strerror(int code) {
     }
 }
 extern "C" int nfk_version(void) { return 100; }
-extern "C" uint64_t nfk_launch_count(void) { return g_launches; }
+extern "C" uint64_t nfk_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 // ============================================================== masks
 __global__ void mask_kernel(uint8_t* mask, Lat lat, int V, int parity, int mu, int along) {
