@@ -233,6 +233,17 @@ int nfk_metropolis_scan(const float* logq, const float* logp, const double* log_
 int nfk_gather_rows(const float* src, const int64_t* idx, const float* prev, float* dst,
                     int64_t B, int64_t row_elems, void* stream);
 
+/* Weight (and bias) gradient of a 2-D 3x3 circular convolution with 8 input channels on the tensor cores
+ * (tcgen05): gw[Co][8][3][3] += sum over batch and sites of gpre x shifted in, gbias[Co] += sum gpre
+ * (adjoint of ConvAct's layers, modules.py:131-145; same contract as nfk_conv_circ_bwd_weight[_cb], the
+ * caller zeroes gw / gbias).  g_parity -1: gpre dense; 0 / 1: gpre vanishes off that checkerboard
+ * partition and only its sites are visited.  Operands are split into tf32 pairs (float32 exponent range,
+ * relative accuracy 2^-22), accumulation is fp32.  NFK_EUNSUPPORTED unless Ci == 8, Co <= 32, 16-byte
+ * aligned inputs, L1 % 8 == 0 (checkerboard form: L1 % 16 == 0, even L0) and at most 64 (active) columns
+ * per row; the caller then uses nfk_conv_circ_bwd_weight[_cb].                                       */
+int nfk_conv2d_wgrad_tc(const float* in, const float* gpre, int g_parity, float* gw, float* gbias,
+                        int L0, int L1, int Ci, int Co, int64_t B, void* stream);
+
 /* -------------------------------------------------------- fused 2-D step ---
  * One whole atomic coupling step on a 2-D lattice with a ConvAct(1 -> H -> H -> P)
  * conditioner (3x3 circular convolutions, tanh, tanh, none; optional biases) in ONE

@@ -34,6 +34,7 @@ class RqsParams(ctypes.Structure):
 EXTRAP = {None: 0, 'none': 0, 'linear': 1, 'anti': 2, 'anti-periodic': 2}
 ACT = {None: 0, 'none': 0, 'tanh': 1, 'relu': 2, 'leaky_relu': 3, 'softplus': 4, 'abs': 5}
 FROZEN_ZERO, FROZEN_COPY = 0, 1
+EUNSUPPORTED = -2          # NFK_EUNSUPPORTED: the entry declines this configuration
 
 # name -> argument types (return type is always int unless stated)
 _SIGNATURES = {
@@ -59,6 +60,7 @@ _SIGNATURES = {
     "nfk_conv_circ_fwd": [c_f, c_f, c_i, c_f, c_f, c_i, c_i, c_f, c_i, c_f, Lattice, c_i, c_i, c_i, c_l, c_f],
     "nfk_conv_circ_bwd_weight": [c_f, c_f, c_i, c_f, c_f, c_f, Lattice, c_i, c_i, c_i, c_l, c_f],
     "nfk_conv_circ_bwd_weight_cb": [c_f, c_f, c_i, c_f, c_f, Lattice, c_i, c_i, c_i, c_l, c_f],
+    "nfk_conv2d_wgrad_tc": [c_f, c_f, c_i, c_f, c_f, c_i, c_i, c_i, c_i, c_l, c_f],
     "nfk_metropolis_scan": [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_l, c_f],
     "nfk_gather_rows": [c_f, c_f, c_f, c_f, c_l, c_l, c_f],
     "nfk_fused2d_step": [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, RqsParams, c_i, c_i, c_i,

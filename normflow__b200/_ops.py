@@ -6,6 +6,7 @@ the host and nothing falls back to eager PyTorch: a CPU tensor raises.
 """
 
 import functools
+import os
 import numbers
 
 import numpy as np
@@ -631,6 +632,20 @@ def _conv_weight_grad(inp, in_mask, in_keep, gpre, w_shape, want_bias, shape, ks
     Co, Ci = w_shape[0], w_shape[1]
     gw = torch.zeros(w_shape, dtype=torch.float32, device=inp.device)
     gb = torch.zeros((Co,), dtype=torch.float32, device=inp.device) if want_bias else None
+    # The tensor-core kernel pays for laying the operands out (im2col in shared memory) whatever Co is; it wins
+    # where the CUDA-core kernel is slowest: checkerboard-sparse gradients of a wide last layer (8 -> 3K-2).
+    # NFK_WGRAD_TC=1 uses it wherever it applies, =0 never.
+    mode = os.environ.get('NFK_WGRAD_TC')
+    want_tc = mode == '1' or (mode != '0' and g_parity is not None and Co >= 16)
+    if in_mask is None and len(shape) == 2 and int(ksize) == 3 and Ci == 8 and Co <= 32 and want_tc:
+        # tensor-core kernel (tf32-pair operands, fp32 accumulation); declines geometries it does not cover
+        with _C.timed(f"conv2d_wgrad_tc[{Ci}->{Co}]"):
+            rc = lib().nfk_conv2d_wgrad_tc(dev(inp), dev(gpre), -1 if g_parity is None else int(g_parity), dev(gw),
+                                           dev(gb), int(shape[0]), int(shape[1]), int(Ci), int(Co),
+                                           inp.shape[0], stream())
+        if rc != _C.EUNSUPPORTED:
+            check(rc, "conv2d_wgrad_tc")
+            return gw, gb
     if g_parity is not None and in_mask is None:
         # gpre lives on one checkerboard partition only: visit just those sites
         with _C.timed(f"conv_circ_bwd_weight_cb[{Ci}->{Co}]"):

@@ -831,3 +831,57 @@ def test_cuda_graph_training_zero_dim_converges_to_logz():
     assert abs(loss[-50:].mean() + 1.112773) < 0.06          # the reference's own log: -1.052 after 500 epochs
     # replays do not go through the host wrappers: far fewer host-side launches than epochs x kernels
     assert _C.launch_count() - n0 < 600
+
+
+# ------------------------------------------------------------------ tensor-core weight gradient
+def _wgrad_reference(x, g):
+    """gw[co,ci,kh,kw] = sum_{b,r,c} g[b,co,r,c] x[b,ci,r+kh-1,c+kw-1] (periodic), float64 numpy."""
+    x, g = x.astype(np.float64), g.astype(np.float64)
+    gw = np.zeros((g.shape[1], x.shape[1], 3, 3))
+    for kh in range(3):
+        for kw in range(3):
+            xs = np.roll(x, shift=(1 - kh, 1 - kw), axis=(2, 3))
+            gw[:, :, kh, kw] = np.einsum('bors,bcrs->oc', g, xs)
+    return gw, g.sum(axis=(0, 2, 3))
+
+
+@pytest.mark.parametrize("B,Co,L0,L1,parity", [(2, 28, 8, 8, 0), (3, 28, 8, 8, None), (5, 8, 16, 16, 1), (4, 2, 6, 12, 0),
+                                               (3, 28, 64, 64, 1), (3, 8, 64, 64, None), (2, 28, 128, 128, 0),
+                                               (2, 8, 10, 128, None), (3, 32, 2, 8, None), (150, 28, 32, 32, 1),
+                                               (3, 28, 16, 16, 0), (2, 5, 7, 24, None)])
+def test_tensor_core_weight_gradient(B, Co, L0, L1, parity, monkeypatch):
+    """nfk_conv2d_wgrad_tc (tf32-pair operands on tcgen05, fp32 accumulation) against a float64 restatement
+    and against the CUDA-core kernel, for gradients ~1/B in size spread over several orders of magnitude."""
+    rng = np.random.RandomState(B * 131 + Co)
+    x = np.tanh(rng.randn(B, 8, L0, L1)).astype(np.float32)
+    g = (rng.randn(B, Co, L0, L1) * 1e-4 * np.exp(2 * rng.randn(B, Co, 1, 1))).astype(np.float32)
+    if parity is not None:
+        rr = np.arange(L0)[:, None] + np.arange(L1)[None, :]
+        g = g * ((rr % 2) == parity)
+        g = g.astype(np.float32)
+    ref_w, ref_b = _wgrad_reference(x, g)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("NFK_WGRAD_TC", mode)
+        n0 = _C.launch_count()
+        out[mode] = _ops._conv_weight_grad(cu(x), None, 0, cu(g), (Co, 8, 3, 3), True, (L0, L1), 3, parity)
+        launches = _C.launch_count() - n0
+        assert launches == 1
+    for mode in ("1", "0"):
+        gw, gb = out[mode]
+        err_w = np.abs(gw.double().cpu().numpy() - ref_w).max() / np.abs(ref_w).max()
+        err_b = np.abs(gb.double().cpu().numpy() - ref_b).max() / np.abs(ref_b).max()
+        assert err_w < 3e-6 and err_b < 3e-6, (mode, err_w, err_b)
+
+
+def test_tensor_core_weight_gradient_declines_what_it_does_not_cover():
+    x = torch.randn(2, 8, 6, 6, device=DEV)                 # L1 % 4 != 0
+    g = torch.randn(2, 4, 6, 6, device=DEV)
+    gw = torch.zeros(4, 8, 3, 3, device=DEV)
+    rc = _C.lib().nfk_conv2d_wgrad_tc(_C.dev(x), _C.dev(g), -1, _C.dev(gw), None, 6, 6, 8, 4, 2, _C.stream())
+    assert rc == _C.EUNSUPPORTED
+    rc = _C.lib().nfk_conv2d_wgrad_tc(_C.dev(x), _C.dev(g), -1, _C.dev(gw), None, 6, 6, 4, 4, 2, _C.stream())
+    assert rc == _C.EUNSUPPORTED
+    gw2, _ = _ops._conv_weight_grad(x, None, 0, g, (4, 8, 3, 3), False, (6, 6), 3, None)      # falls back
+    ref_w, _ = _wgrad_reference(x.cpu().numpy(), g.cpu().numpy())
+    close_grad(gw2, ref_w)
