@@ -200,6 +200,13 @@ int nfk_conv_circ_fwd(const float* in, const float* w, int w_transposed, const f
                       int act, const float* dact_from, int dact_kind,
                       float* out, nfk_lattice lat, int ksize,
                       int Ci, int Co, int64_t B, void* stream);
+/* The same layer for an input known to vanish off one checkerboard partition (in_parity: the parity of
+ * row + column of its non-zero sites) -- the data gradient of a checkerboard coupling's conditioner, whose
+ * incoming gradient lives on the updated partition only (couplings_.py:56-64).  Same result as
+ * nfk_conv_circ_fwd; on 2-D 3x3 layers the products with the known zeros are not computed.          */
+int nfk_conv_circ_fwd_cb(const float* in, int in_parity, const float* w, int w_transposed,
+                         const float* bias, int act, const float* dact_from, int dact_kind,
+                         float* out, nfk_lattice lat, int ksize, int Ci, int Co, int64_t B, void* stream);
 /* gw[Co][Ci][ksize^ndim] += sum_{b,s} gpre[b][co][s] * in[b][ci][s + tap]  and
  * gbias[Co] += sum gpre (gbias may be NULL).  ACCUMULATES with atomics.         */
 int nfk_conv_circ_bwd_weight(const float* in, const uint8_t* in_mask, int in_keep,

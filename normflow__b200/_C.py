@@ -58,6 +58,7 @@ _SIGNATURES = {
     "nfk_phi4_action_fwd": [c_f, Lattice, c_fl, c_fl, c_fl, c_f, c_l, c_f],
     "nfk_phi4_action_bwd": [c_f, Lattice, c_fl, c_fl, c_fl, c_f, c_f, c_l, c_f],
     "nfk_conv_circ_fwd": [c_f, c_f, c_i, c_f, c_f, c_i, c_i, c_f, c_i, c_f, Lattice, c_i, c_i, c_i, c_l, c_f],
+    "nfk_conv_circ_fwd_cb": [c_f, c_i, c_f, c_i, c_f, c_i, c_f, c_i, c_f, Lattice, c_i, c_i, c_i, c_l, c_f],
     "nfk_conv_circ_bwd_weight": [c_f, c_f, c_i, c_f, c_f, c_f, Lattice, c_i, c_i, c_i, c_l, c_f],
     "nfk_conv_circ_bwd_weight_cb": [c_f, c_f, c_i, c_f, c_f, Lattice, c_i, c_i, c_i, c_l, c_f],
     "nfk_conv2d_wgrad_tc": [c_f, c_f, c_i, c_f, c_f, c_i, c_i, c_i, c_i, c_l, c_f],

@@ -617,9 +617,17 @@ def sample_shift(x, delta):
 
 
 # ---------------------------------------------------------------------------- conditioner
-def _conv_call(inp, w, transposed, bias, in_mask, in_keep, act, dact_from, dact_kind, shape, ksize, Ci, Co):
+def _conv_call(inp, w, transposed, bias, in_mask, in_keep, act, dact_from, dact_kind, shape, ksize, Ci, Co,
+               in_parity=None):
     B = inp.shape[0]
     out = torch.empty((B, Co) + tuple(shape), dtype=torch.float32, device=inp.device)
+    if in_parity is not None and in_mask is None:
+        # `inp` lives on one checkerboard partition only: products with the known zeros are skipped
+        with _C.timed(f"conv_circ_fwd_cb[{Ci}->{Co}]"):
+            check(lib().nfk_conv_circ_fwd_cb(dev(inp), int(in_parity), dev(w), int(transposed), dev(bias), int(act),
+                                             dev(dact_from), int(dact_kind), dev(out), _C.lattice(shape),
+                                             int(ksize), int(Ci), int(Co), B, stream()), "conv_circ_fwd_cb")
+        return out
     with _C.timed(f"conv_circ_fwd[{Ci}->{Co}]"):
         check(lib().nfk_conv_circ_fwd(dev(inp), dev(w), int(transposed), dev(bias), dev(in_mask, torch.uint8),
                                       int(in_keep), int(act), dev(dact_from), int(dact_kind), dev(out),
@@ -722,7 +730,8 @@ def _conv_stack_backward(hs, weights, has_bias, acts, ksize, shape, in_mask, in_
             break
         # d/d(input of layer i): conv of gpre with w^T (taps flipped); multiply by act'(h_{i})
         gpre = _conv_call(gpre, w.contiguous(), 1, None, None, 0, 0, hs[i] if not first else None,
-                          acts[i - 1] if not first else 0, shape, ksize, Co, Ci)
+                          acts[i - 1] if not first else 0, shape, ksize, Co, Ci,
+                          in_parity=gpre_parity if i == n - 1 else None)
     gin = None
     if gpre is not None:
         gin = gpre if in_mask is None else mask_select(gpre, in_mask, in_keep)

@@ -86,9 +86,29 @@ struct Conv2dArgs {
     int dact_kind;
     float* out;
     int L0, L1, R, Ci, Co, strips;
+    int in_parity;               // >= 0: `in` vanishes off that checkerboard partition (zero products are skipped)
 };
 
 constexpr int kC2Chunk = 8;      // input channels per shared-memory stage
+
+// 4 columns x 8 output channels += 3 x 6 window (x) 9 x 8 weights of one input channel.  SPARSE: the window
+// entry (dr, k + dc) is known to be zero unless (dr + dc + k + A0) is even, and its products are left out.
+template <bool SPARSE, int A0>
+__device__ __forceinline__ void conv2d_tile_fma(const float (&win)[3][6], const float* __restrict__ w_ci,
+                                                float (&acc)[4][8]) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const float4 w0 = *reinterpret_cast<const float4*>(w_ci + t * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(w_ci + t * 8 + 4);
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (SPARSE && ((t / 3 + t % 3 + k + A0) & 1)) continue;
+#pragma unroll
+            for (int co = 0; co < 8; ++co) acc[k][co] = fmaf(win[t / 3][k + t % 3], wv[co], acc[k][co]);
+        }
+    }
+}
 
 __global__ void __launch_bounds__(256) conv2d_tile_kernel(Conv2dArgs a) {
     extern __shared__ __align__(16) float sm2[];
@@ -101,7 +121,10 @@ __global__ void __launch_bounds__(256) conv2d_tile_kernel(Conv2dArgs a) {
     const int rows = L0 - r0 < R ? L0 - r0 : R;
     const int co0 = blockIdx.y * 8;
     const int V = L0 * L1;
-    const int j = tid / nq, c0 = (tid - j * nq) * 4;                   // my row of the strip, my 4 columns
+    // my row of the strip and my 4 columns.  The two rows a warp usually spans are two apart (low two bits of
+    // the row index swapped), so that a warp sees ONE row parity and the sparse variants below do not diverge.
+    const int jj = tid / nq, c0 = (tid - jj * nq) * 4;
+    const int j = (R % 4 == 0) ? ((jj & ~3) | ((jj & 1) << 1) | ((jj >> 1) & 1)) : jj;
     const bool live = j < rows;
     float acc[4][8];
 #pragma unroll
@@ -158,16 +181,11 @@ __global__ void __launch_bounds__(256) conv2d_tile_kernel(Conv2dArgs a) {
 #pragma unroll
                     for (int k = 0; k < 6; ++k) win[dr][k] = p[k];
                 }
-#pragma unroll
-                for (int t = 0; t < 9; ++t) {
-                    const float4 w0 = *reinterpret_cast<const float4*>(w_s + (ci * 9 + t) * 8);
-                    const float4 w1 = *reinterpret_cast<const float4*>(w_s + (ci * 9 + t) * 8 + 4);
-                    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-                    for (int co = 0; co < 8; ++co)
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) acc[k][co] = fmaf(win[t / 3][k + t % 3], wv[co], acc[k][co]);
-                }
+                // input site (r0 + j + dr - 1, c0 + k + dc - 1) is on the partition iff dr + dc + k + a0 is even
+                const float* w_ci = w_s + ci * 72;
+                if (a.in_parity < 0) conv2d_tile_fma<false, 0>(win, w_ci, acc);
+                else if ((r0 + j + a.in_parity) & 1) conv2d_tile_fma<true, 1>(win, w_ci, acc);
+                else conv2d_tile_fma<true, 0>(win, w_ci, acc);
             }
         }
     }
@@ -194,7 +212,7 @@ __global__ void __launch_bounds__(256) conv2d_tile_kernel(Conv2dArgs a) {
 // load-bound either way), 16-byte aligned tensors
 static int conv2d_tile_launch(const float* in, const float* w, int w_transposed, const float* bias,
                               const uint8_t* in_mask, int in_keep, int act, const float* dact_from, int dact_kind,
-                              float* out, int L0, int L1, int Ci, int Co, int64_t B, cudaStream_t st) {
+                              float* out, int L0, int L1, int Ci, int Co, int64_t B, int in_parity, cudaStream_t st) {
     const int nq = L1 / 4;
     if (nq > 256) return NFK_EUNSUPPORTED;
     int R = 256 / nq;
@@ -204,6 +222,7 @@ static int conv2d_tile_launch(const float* in, const float* w, int w_transposed,
     a.in = in; a.w = w; a.w_transposed = w_transposed; a.bias = bias; a.in_mask = in_mask; a.in_keep = in_keep;
     a.act = act; a.dact_from = dact_from; a.dact_kind = dact_kind; a.out = out;
     a.L0 = L0; a.L1 = L1; a.R = R; a.Ci = Ci; a.Co = Co; a.strips = (L0 + R - 1) / R;
+    a.in_parity = (in_parity >= 0 && L0 % 2 == 0 && L1 % 2 == 0 && in_mask == nullptr) ? in_parity : -1;
     const size_t smem = (size_t)(kC2Chunk * (R + 2) * (L1 + 8) + kC2Chunk * 72) * sizeof(float);
     if (smem > 160 * 1024) return NFK_EUNSUPPORTED;
     if (ensure_dynamic_smem<conv2d_tile_kernel>(160 * 1024) != NFK_OK) return NFK_ECUDA;
@@ -212,11 +231,33 @@ static int conv2d_tile_launch(const float* in, const float* w, int w_transposed,
     return check_launch();
 }
 
+static int conv_fwd_impl(const float* in, const float* w, int w_transposed, const float* bias,
+                         const uint8_t* in_mask, int in_keep, int act, const float* dact_from, int dact_kind,
+                         float* out, nfk_lattice lat, int ksize, int Ci, int Co, int64_t B, int in_parity,
+                         void* stream);
+
 extern "C" int nfk_conv_circ_fwd(const float* in, const float* w, int w_transposed, const float* bias,
                                  const uint8_t* in_mask, int in_keep,
                                  int act, const float* dact_from, int dact_kind,
                                  float* out, nfk_lattice lat, int ksize,
                                  int Ci, int Co, int64_t B, void* stream) {
+    return conv_fwd_impl(in, w, w_transposed, bias, in_mask, in_keep, act, dact_from, dact_kind, out, lat, ksize,
+                         Ci, Co, B, -1, stream);
+}
+
+extern "C" int nfk_conv_circ_fwd_cb(const float* in, int in_parity, const float* w, int w_transposed,
+                                    const float* bias, int act, const float* dact_from, int dact_kind,
+                                    float* out, nfk_lattice lat, int ksize, int Ci, int Co, int64_t B,
+                                    void* stream) {
+    if (in_parity != 0 && in_parity != 1) return NFK_EINVAL;
+    return conv_fwd_impl(in, w, w_transposed, bias, nullptr, 0, act, dact_from, dact_kind, out, lat, ksize,
+                         Ci, Co, B, in_parity, stream);
+}
+
+static int conv_fwd_impl(const float* in, const float* w, int w_transposed, const float* bias,
+                         const uint8_t* in_mask, int in_keep, int act, const float* dact_from, int dact_kind,
+                         float* out, nfk_lattice lat, int ksize, int Ci, int Co, int64_t B, int in_parity,
+                         void* stream) {
     if (!in || !w || !out || !lat_ok(lat) || ksize < 1 || ksize % 2 == 0 || Ci < 1 || Co < 1) return NFK_EINVAL;
     if (B <= 0) return NFK_OK;
     if (lat.ndim == 2 && ksize == 3 && Co >= 4 && lat.shape[1] % 4 == 0 && lat.shape[0] >= 2 && lat.shape[1] >= 4 &&
@@ -224,7 +265,7 @@ extern "C" int nfk_conv_circ_fwd(const float* in, const float* w, int w_transpos
         ((uintptr_t)out % 16) == 0 && (!dact_from || ((uintptr_t)dact_from % 16) == 0) &&
         (!in_mask || ((uintptr_t)in_mask % 4) == 0)) {
         const int rc = conv2d_tile_launch(in, w, w_transposed, bias, in_mask, in_keep, act, dact_from, dact_kind, out,
-                                          lat.shape[0], lat.shape[1], Ci, Co, B, NFK_STREAM(stream));
+                                          lat.shape[0], lat.shape[1], Ci, Co, B, in_parity, NFK_STREAM(stream));
         if (rc != NFK_EUNSUPPORTED) return rc;
     }
     ConvArgs a;

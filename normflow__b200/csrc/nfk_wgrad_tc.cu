@@ -118,7 +118,14 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad2d_tc_kernel(WgTcArgs a) {
 
     // operand buffer s: [hi part | lo part]
     auto part = [&](int s, int lo) { return smem + (size_t)(2 * s + lo) * part_bytes; };
-    auto is_drain = [&](long long i) { return ((i + 1) % a.drain_every == 0) || (i + 1 == n_tiles); };
+    // drain points: every `drain_every` tiles and after the last one (a running counter, no division)
+    struct DrainClock {
+        int every, since;
+        __device__ bool tick(bool last) {                                 // call once per tile, in order
+            if (++since == every || last) { since = 0; return true; }
+            return false;
+        }
+    };
 
     if (tid == 0) {
         for (int i = 0; i < 3; ++i) tc::mbar_init(tc::smem_u32(bars + i), 1);
@@ -176,15 +183,22 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad2d_tc_kernel(WgTcArgs a) {
         }
 
         // ---- raw rows: one line (a lattice row of one channel) per thread and pass
-        auto issue = [&](long long i) {
+        // a tile cursor: (sample, strip) of tile i, advanced without divisions
+        struct Cursor { long long b; int strip; };
+        const int step_b = (int)(gridDim.x / strips), step_s = (int)(gridDim.x % strips);
+        auto advance = [&](Cursor& c) {
+            c.b += step_b;
+            c.strip += step_s;
+            if (c.strip >= strips) { c.strip -= strips; ++c.b; }
+        };
+        auto issue = [&](long long i, const Cursor& cur, int stg) {
             if (i >= n_tiles) {                                           // keeps the group count in step
                 asm volatile("cp.async.commit_group;" ::: "memory");
                 return;
             }
-            const long long u = blockIdx.x + i * gridDim.x;
-            const long long b = u / strips;
-            const int r0 = (int)(u - b * strips) * R;
-            float* raw = reinterpret_cast<float*>(raw0 + (size_t)(i % kRawStages) * a.raw_bytes);
+            const long long b = cur.b;
+            const int r0 = cur.strip * R;
+            float* raw = reinterpret_cast<float*>(raw0 + (size_t)stg * a.raw_bytes);
             for (int line = tid; line < x_lines + g_lines; line += kProducerThreads) {
                 const float* srcp;
                 float* dstp;
@@ -232,18 +246,27 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad2d_tc_kernel(WgTcArgs a) {
             tc::bar_arrive(kBarDrained, kDrainWarps * 32 + 32);
         };
 
-        issue(0);
-        issue(1);
-        for (long long i = 0; i < n_tiles; ++i) {
+        Cursor cur{(long long)(blockIdx.x / strips), (int)(blockIdx.x % strips)}, ahead = cur;
+        issue(0, ahead, 0);
+        advance(ahead);
+        issue(1, ahead, 1 % kRawStages);
+        advance(ahead);
+        DrainClock clock{a.drain_every, 0};
+        bool drain_due = false;                                           // tile i - 1 ended a drain interval
+        int stage = 0, stage_ahead = 2 % kRawStages;
+        for (long long i = 0; i < n_tiles; ++i, advance(cur)) {
             const int s = (int)(i & 1);
-            if (warp < kDrainWarps && i > 0 && is_drain(i - 1)) drain();
+            if (warp < kDrainWarps && drain_due) drain();
+            drain_due = clock.tick(i + 1 == n_tiles);
             asm volatile("cp.async.wait_group 1;" ::: "memory");          // all but the newest group: tile i is here
             tc::bar_sync(kBarProducers, kProducerThreads);    // ... for everyone, and the stage of tile i - 1 is free
-            issue(i + 2);
+            issue(i + 2, ahead, stage_ahead);
+            advance(ahead);
+            stage_ahead = stage_ahead + 1 == kRawStages ? 0 : stage_ahead + 1;
             tc::mbar_wait(tc::smem_u32(bars + s), (uint32_t)(((i >> 1) & 1) ^ 1));     // MMAs of tile i - 2 done
-            const long long u = blockIdx.x + i * gridDim.x;
-            const int r0 = (int)(u % strips) * R;
-            const float* raw = reinterpret_cast<const float*>(raw0 + (size_t)(i % kRawStages) * a.raw_bytes);
+            const int r0 = cur.strip * R;
+            const float* raw = reinterpret_cast<const float*>(raw0 + (size_t)stage * a.raw_bytes);
+            stage = stage + 1 == kRawStages ? 0 : stage + 1;
             unsigned char* hi = part(s, 0);
             unsigned char* lo = part(s, 1);
 #pragma unroll
@@ -308,6 +331,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad2d_tc_kernel(WgTcArgs a) {
         // =============================== MMA warp ==============================================
         const bool lead = tc::elect_one();
         const uint32_t idesc = tc::make_idesc(2, 128, 32);               // tf32 operands, K = 8 per instruction
+        DrainClock clock{a.drain_every, 0};
         uint32_t acc_on = 0;
         for (long long i = 0; i < n_tiles; ++i) {
             const int s = (int)(i & 1);
@@ -329,7 +353,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad2d_tc_kernel(WgTcArgs a) {
                 tc::mma_commit(tc::smem_u32(bars + s));                   // buffer s free when these complete
             }
             __syncwarp();
-            if (is_drain(i)) {
+            if (clock.tick(i + 1 == n_tiles)) {
                 if (lead) tc::mma_commit(tc::smem_u32(bars + 2));
                 __syncwarp();
                 tc::bar_sync(kBarDrained, kDrainWarps * 32 + 32);         // registers hold the partial sums

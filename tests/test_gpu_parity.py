@@ -871,7 +871,9 @@ def test_tensor_core_weight_gradient(B, Co, L0, L1, parity, monkeypatch):
         gw, gb = out[mode]
         err_w = np.abs(gw.double().cpu().numpy() - ref_w).max() / np.abs(ref_w).max()
         err_b = np.abs(gb.double().cpu().numpy() - ref_b).max() / np.abs(ref_b).max()
-        assert err_w < 3e-6 and err_b < 3e-6, (mode, err_w, err_b)
+        # contract: 1e-5 of the tensor's scale; the tensor-core accumulator (drained every 4 tiles) stays within ~3e-6
+        bound = 6e-6 if mode == "1" else 2e-6
+        assert err_w < bound and err_b < bound, (mode, err_w, err_b)
 
 
 def test_tensor_core_weight_gradient_declines_what_it_does_not_cover():
@@ -885,3 +887,29 @@ def test_tensor_core_weight_gradient_declines_what_it_does_not_cover():
     gw2, _ = _ops._conv_weight_grad(x, None, 0, g, (4, 8, 3, 3), False, (6, 6), 3, None)      # falls back
     ref_w, _ = _wgrad_reference(x.cpu().numpy(), g.cpu().numpy())
     close_grad(gw2, ref_w)
+
+
+@pytest.mark.parametrize("B,Ci,Co,L0,L1,parity", [(3, 28, 8, 64, 64, 1), (2, 28, 8, 16, 16, 0), (2, 8, 8, 6, 8, 1),
+                                                  (2, 2, 8, 10, 12, 0), (2, 28, 8, 7, 8, 1), (5, 28, 8, 32, 128, 0)])
+def test_checkerboard_conv_skips_only_zero_products(B, Ci, Co, L0, L1, parity):
+    """nfk_conv_circ_fwd_cb (data gradient of a checkerboard coupling's last conditioner layer) gives what the
+    dense kernel gives on an input that vanishes off the partition -- transposed weights, fused act'."""
+    rng = np.random.RandomState(L0 * 7 + L1)
+    g = rng.randn(B, Ci, L0, L1).astype(np.float32)
+    rr = np.arange(L0)[:, None] + np.arange(L1)[None, :]
+    g = (g * ((rr % 2) == parity)).astype(np.float32)
+    w = (rng.randn(Ci, Co, 3, 3) * 0.3).astype(np.float32)          # forward layer's weight (Ci = its outputs)
+    h = np.tanh(rng.randn(B, Co, L0, L1)).astype(np.float32)
+    dense = _ops._conv_call(cu(g), cu(w), 1, None, None, 0, 0, cu(h), _C.ACT['tanh'], (L0, L1), 3, Ci, Co)
+    sparse = _ops._conv_call(cu(g), cu(w), 1, None, None, 0, 0, cu(h), _C.ACT['tanh'], (L0, L1), 3, Ci, Co,
+                             in_parity=parity)
+    scale = float(dense.abs().max())
+    assert float((dense - sparse).abs().max()) <= 2e-6 * scale
+    # and against a float64 restatement: out[b,co] = (1 - h^2) * sum_{ci,taps} g[b,ci](shifted) w[ci,co](flipped)
+    ref = np.zeros((B, Co, L0, L1))
+    for kh in range(3):
+        for kw in range(3):
+            gs = np.roll(g.astype(np.float64), shift=(kh - 1, kw - 1), axis=(2, 3))
+            ref += np.einsum('birs,io->bors', gs, w[:, :, kh, kw].astype(np.float64))
+    ref *= 1 - h.astype(np.float64) ** 2
+    close_grad(sparse, ref, tol=2e-6)
