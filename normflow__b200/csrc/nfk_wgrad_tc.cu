@@ -52,12 +52,16 @@ constexpr int kBRow0 = 96;                                  // first B (gpre) ro
 constexpr int kOnesRow = 72;
 constexpr int kGroupBytes = kRowsPerGroup * 16;             // LBO
 constexpr int kMaxKT = 64;                                  // sites per tile
-constexpr int kSlots = 1;                                   // im2col tasks (8 sites each) per producer thread: 24 * 8 + 32 * 8 at most
+constexpr int kSlots = 2;                                   // im2col tasks (8 sites of one operand row) per producer thread
+constexpr int kCpSlots = 4;                                 // cp.async chunks per producer thread and tile
 constexpr int kTmemCols = 32;                               // D: 128 lanes x 32 columns
 constexpr int kRawStages = 3;                                // raw-row stages in flight (cp.async)
 constexpr int kBarFull0 = 1, kBarDrained = 3, kBarProducers = 4;   // named barriers (0 is __syncthreads)
 
+__device__ long long g_wg_trace[2048];      // debug: phase time stamps of CTA 0 (NFK_WGRAD_TRACE=1)
+
 struct WgTcArgs {
+    int trace;
     const float* in;        // [B][8][L0][L1]
     const float* g;         // [B][Co][L0][L1]
     float* gw;              // [Co][8][3][3], accumulated into
@@ -149,27 +153,28 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad2d_tc_kernel(WgTcArgs a) {
         // raw fp32 rows of the NEXT tile stream in with cp.async while the current tile's rows (already in
         // shared memory) are split into fp16 pairs and laid out as MMA operands.  A thread's share of the
         // work is the same for every tile, so it is decoded once.
-        const int a_tasks = 8 * 3 * ngroups, g_tasks = Co * ngroups;
+        const int a_tasks = 8 * 9 * ngroups, g_tasks = Co * ngroups;      // one (channel, tap) / one gpre channel x 8 sites
         const int x_lines = 8 * (R + 2), g_lines = Co * R;
         const int RS = a.row_stride;
         const int gr_off = 8 * a.xch_stride;                              // gpre rows follow the input rows (floats)
         unsigned char* raw0 = smem + (size_t)4 * part_bytes;
 
-        // ---- im2col task slots: kind 0 = input patch rows (three column taps), 1 = gpre row, -1 = none
-        int kind[kSlots], src[kSlots], dst[kSlots], cc0s[kSlots], jrow[kSlots];
+        // ---- im2col task slots: kind 0 = input patch row of one tap, 1 = gpre row, -1 = none
+        int kind[kSlots], src[kSlots], dst[kSlots], cc0s[kSlots], jrow[kSlots], kws[kSlots];
 #pragma unroll
         for (int k = 0; k < kSlots; ++k) {
             const int t = tid + k * kProducerThreads;
-            kind[k] = -1; src[k] = dst[k] = cc0s[k] = jrow[k] = 0;
+            kind[k] = -1; src[k] = dst[k] = cc0s[k] = jrow[k] = kws[k] = 0;
             if (t < a_tasks) {
                 const int ci = t & 7, rest = t >> 3;
-                const int kg = rest % ngroups, kh = rest / ngroups;
+                const int kg = rest % ngroups, tap = rest / ngroups;
                 const int j = kg / gpr;
                 kind[k] = 0;
                 cc0s[k] = (kg - j * gpr) * 8;
                 jrow[k] = j;
-                src[k] = ci * a.xch_stride + (j + kh) * RS + 4;              // column 0 of the staged row
-                dst[k] = 2 * kg * kGroupBytes + (kh * 3 * 8 + ci) * 16;    // + kw * 128 per column tap
+                kws[k] = tap % 3;
+                src[k] = ci * a.xch_stride + (j + tap / 3) * RS + 4;         // column 0 of the staged row
+                dst[k] = 2 * kg * kGroupBytes + (tap * 8 + ci) * 16;
             } else if (t < a_tasks + g_tasks) {
                 const int tg = t - a_tasks;
                 const int co = tg % Co, kg = tg / Co;
@@ -182,7 +187,41 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad2d_tc_kernel(WgTcArgs a) {
             }
         }
 
-        // ---- raw rows: one line (a lattice row of one channel) per thread and pass
+        // ---- cp.async slots: the 16-byte chunks of every staged line, spread evenly over the producers.
+        // Chunk 0 of a line is the wrapped group in front (columns L1-4 .. L1-1), the last one the wrapped
+        // group behind (columns 0 .. 3).
+        const int cpl = (L1 >> 2) + 2;                                    // chunks per line
+        const int n_chunks = (x_lines + g_lines) * cpl;
+        int cp_dst[kCpSlots], cp_ch[kCpSlots], cp_row[kCpSlots], cp_col[kCpSlots];      // cp_ch < 0: none; >= 8: gpre channel + 8
+#pragma unroll
+        // full rounds go to every thread; the remainder goes to the HIGHEST thread ids, which are the ones
+        // with fewer im2col tasks (those are dealt from thread 0 upwards)
+        const int full_rounds = n_chunks / kProducerThreads, rem_chunks = n_chunks - full_rounds * kProducerThreads;
+        for (int k = 0; k < kCpSlots; ++k) {
+            int c = -1;
+            if (k < full_rounds) c = tid + k * kProducerThreads;
+            else if (k == full_rounds && kProducerThreads - 1 - tid < rem_chunks)
+                c = full_rounds * kProducerThreads + (kProducerThreads - 1 - tid);
+            cp_dst[k] = cp_row[k] = cp_col[k] = 0;
+            cp_ch[k] = -1;
+            if (c >= 0) {
+                const int line = c / cpl, q = c - line * cpl;
+                cp_col[k] = q == 0 ? L1 - 4 : (q == cpl - 1 ? 0 : 4 * (q - 1));
+                if (line < x_lines) {
+                    const int ci = line / (R + 2), jj = line - ci * (R + 2);
+                    cp_ch[k] = ci;
+                    cp_row[k] = jj - 1;                                   // lattice row = r0 + cp_row (wrapped)
+                    cp_dst[k] = (ci * a.xch_stride + jj * RS + 4 * q) * 4;
+                } else {
+                    const int lg = line - x_lines;
+                    const int co = lg / R, j = lg - co * R;
+                    cp_ch[k] = 8 + co;
+                    cp_row[k] = j;
+                    cp_dst[k] = (gr_off + co * a.gch_stride + j * RS + 4 * q) * 4;
+                }
+            }
+        }
+
         // a tile cursor: (sample, strip) of tile i, advanced without divisions
         struct Cursor { long long b; int strip; };
         const int step_b = (int)(gridDim.x / strips), step_s = (int)(gridDim.x % strips);
@@ -192,37 +231,27 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad2d_tc_kernel(WgTcArgs a) {
             if (c.strip >= strips) { c.strip -= strips; ++c.b; }
         };
         auto issue = [&](long long i, const Cursor& cur, int stg) {
-            if (i >= n_tiles) {                                           // keeps the group count in step
-                asm volatile("cp.async.commit_group;" ::: "memory");
-                return;
-            }
-            const long long b = cur.b;
-            const int r0 = cur.strip * R;
-            float* raw = reinterpret_cast<float*>(raw0 + (size_t)stg * a.raw_bytes);
-            for (int line = tid; line < x_lines + g_lines; line += kProducerThreads) {
-                const float* srcp;
-                float* dstp;
-                bool live = true;
-                if (line < x_lines) {
-                    const int ci = line / (R + 2), jj = line - ci * (R + 2);
-                    int rr = r0 - 1 + jj;
-                    rr = rr < 0 ? rr + L0 : rr;
-                    while (rr >= L0) rr -= L0;
-                    srcp = a.in + ((b * 8 + ci) * L0 + rr) * (long long)L1;
-                    dstp = raw + ci * a.xch_stride + jj * RS;
-                } else {
-                    const int lg = line - x_lines;
-                    const int co = lg / R, j = lg - co * R;
-                    live = r0 + j < L0;                                   // rows past the lattice: zero-filled
-                    srcp = a.g + ((b * Co + co) * L0 + (live ? r0 + j : 0)) * (long long)L1;
-                    dstp = raw + gr_off + co * a.gch_stride + j * RS;
+            if (i < n_tiles) {
+                const int r0 = cur.strip * R;
+                const uint32_t raw = tc::smem_u32(raw0 + (size_t)stg * a.raw_bytes);
+                const float* in_b = a.in + cur.b * 8 * (long long)L0 * L1;
+                const float* g_b = a.g + cur.b * Co * (long long)L0 * L1;
+#pragma unroll
+                for (int k = 0; k < kCpSlots; ++k) {
+                    if (cp_ch[k] < 0) continue;
+                    int rr = r0 + cp_row[k];
+                    if (cp_ch[k] < 8) {
+                        rr = rr < 0 ? rr + L0 : rr;
+                        while (rr >= L0) rr -= L0;
+                        cp_async16(raw + cp_dst[k], in_b + ((long long)cp_ch[k] * L0 + rr) * L1 + cp_col[k], true);
+                    } else {
+                        const bool live = rr < L0;                        // rows past the lattice: zero-filled
+                        cp_async16(raw + cp_dst[k], g_b + ((long long)(cp_ch[k] - 8) * L0 + (live ? rr : 0)) * L1 + cp_col[k],
+                                   live);
+                    }
                 }
-                const uint32_t d = tc::smem_u32(dstp);
-                cp_async16(d, srcp + L1 - 4, live);                       // columns -4 .. -1
-                for (int q = 0; q < (L1 >> 2); ++q) cp_async16(d + 16 + 16 * q, srcp + 4 * q, live);
-                cp_async16(d + 16 + 4 * L1, srcp, live);                  // columns L1 .. L1 + 3
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");          // (an empty group keeps the count in step)
         };
 
         float acc[32];                                                    // drain warps: partial sums of my TMEM lane
@@ -252,18 +281,27 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad2d_tc_kernel(WgTcArgs a) {
         issue(1, ahead, 1 % kRawStages);
         advance(ahead);
         DrainClock clock{a.drain_every, 0};
+        int tn = 0;
+        auto stamp = [&]() {
+            if (a.trace && blockIdx.x == 0 && tid == 160 && tn < 1000) g_wg_trace[tn++] = clock64();
+        };
         bool drain_due = false;                                           // tile i - 1 ended a drain interval
         int stage = 0, stage_ahead = 2 % kRawStages;
         for (long long i = 0; i < n_tiles; ++i, advance(cur)) {
             const int s = (int)(i & 1);
             if (warp < kDrainWarps && drain_due) drain();
             drain_due = clock.tick(i + 1 == n_tiles);
+            stamp();
             asm volatile("cp.async.wait_group 1;" ::: "memory");          // all but the newest group: tile i is here
+            stamp();
             tc::bar_sync(kBarProducers, kProducerThreads);    // ... for everyone, and the stage of tile i - 1 is free
+            stamp();
             issue(i + 2, ahead, stage_ahead);
             advance(ahead);
             stage_ahead = stage_ahead + 1 == kRawStages ? 0 : stage_ahead + 1;
+            stamp();
             tc::mbar_wait(tc::smem_u32(bars + s), (uint32_t)(((i >> 1) & 1) ^ 1));     // MMAs of tile i - 2 done
+            stamp();
             const int r0 = cur.strip * R;
             const float* raw = reinterpret_cast<const float*>(raw0 + (size_t)stage * a.raw_bytes);
             stage = stage + 1 == kRawStages ? 0 : stage + 1;
@@ -276,30 +314,33 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad2d_tc_kernel(WgTcArgs a) {
                 const float* row = raw + src[k];
                 const int cc0 = cc0s[k];
                 if (kind[k] == 0) {
-                    // the three column taps of eight consecutive active sites of one (channel, row tap):
-                    // columns c0 - 1 ... c0 + (SPARSE ? 15 : 8), c0 = first active column
-                    constexpr int NV = SPARSE ? 5 : 4;
+                    // eight consecutive active sites of one (channel, tap): columns c0 + o + (SPARSE ? 2 e : e),
+                    // o = kw - 1 (+ the row's parity offset), read as aligned groups of four starting at or below
+                    const int o = kws[k] - 1 + par;                       // -1 .. 2, the same for the whole warp
+                    const float* base = row + (SPARSE ? 2 * cc0 : cc0) + (o < 0 ? -4 : 0);
+                    constexpr int NV = SPARSE ? 5 : 3;
                     float v[4 * NV];
-                    const int c0 = SPARSE ? 2 * cc0 + par : cc0;
-                    if (SPARSE && par) {                                  // c0 - 1 is a multiple of four (warp-uniform)
-                        load_row<NV>(row + c0 - 1, v);
+                    load_row<NV>(base, v);
+                    float vals[8];
+                    switch (o) {
+                        case -1:
 #pragma unroll
-                        for (int kw = 0; kw < 3; ++kw) {
-                            float vals[8];
+                            for (int e = 0; e < 8; ++e) vals[e] = v[3 + (SPARSE ? 2 * e : e)];
+                            break;
+                        case 0:
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) vals[e] = v[2 * e + kw];
-                            split_store(vals, hi + dst[k] + kw * 128, lo + dst[k] + kw * 128);
-                        }
-                    } else {
-                        load_row<NV>(row + c0 - 4, v);
+                            for (int e = 0; e < 8; ++e) vals[e] = v[(SPARSE ? 2 * e : e)];
+                            break;
+                        case 1:
 #pragma unroll
-                        for (int kw = 0; kw < 3; ++kw) {
-                            float vals[8];
+                            for (int e = 0; e < 8; ++e) vals[e] = v[1 + (SPARSE ? 2 * e : e)];
+                            break;
+                        default:
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) vals[e] = v[3 + (SPARSE ? 2 * e : e) + kw];
-                            split_store(vals, hi + dst[k] + kw * 128, lo + dst[k] + kw * 128);
-                        }
+                            for (int e = 0; e < 8; ++e) vals[e] = v[2 + (SPARSE ? 2 * e : e)];
+                            break;
                     }
+                    split_store(vals, hi + dst[k], lo + dst[k]);
                 } else {
                     constexpr int NV = SPARSE ? 4 : 2;
                     float v[4 * NV];
@@ -310,8 +351,10 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad2d_tc_kernel(WgTcArgs a) {
                     split_store(vals, hi + dst[k], lo + dst[k]);
                 }
             }
+            stamp();
             tc::fence_async_smem();                                       // my records -> visible to the tensor core
             tc::bar_arrive(kBarFull0 + s, kProducerThreads + 32);
+            stamp();
         }
         if (warp < kDrainWarps && n_tiles > 0) {
             drain();                                                      // the last tile is always a drain point
@@ -332,25 +375,35 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad2d_tc_kernel(WgTcArgs a) {
         const bool lead = tc::elect_one();
         const uint32_t idesc = tc::make_idesc(2, 128, 32);               // tf32 operands, K = 8 per instruction
         DrainClock clock{a.drain_every, 0};
+        constexpr uint64_t kStepDesc = (2 * kGroupBytes) >> 4;            // never carries out of the 14-bit address field
+        uint64_t d_a_hi[2], d_a_lo[2], d_b_hi[2], d_b_lo[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const uint32_t hi = tc::smem_u32(part(s, 0)), lo = tc::smem_u32(part(s, 1));
+            d_a_hi[s] = tc::make_desc(hi, kGroupBytes, 128);
+            d_a_lo[s] = tc::make_desc(lo, kGroupBytes, 128);
+            d_b_hi[s] = tc::make_desc(hi + kBRow0 * 16, kGroupBytes, 128);
+            d_b_lo[s] = tc::make_desc(lo + kBRow0 * 16, kGroupBytes, 128);
+        }
         uint32_t acc_on = 0;
         for (long long i = 0; i < n_tiles; ++i) {
             const int s = (int)(i & 1);
+            if (a.trace && blockIdx.x == 0 && lead && i < 250) g_wg_trace[1024 + 4 * i] = clock64();
             tc::bar_sync(kBarFull0 + s, kProducerThreads + 32);           // tile i is in buffer s
             tc::fence_after_sync();
+            if (a.trace && blockIdx.x == 0 && lead && i < 250) g_wg_trace[1024 + 4 * i + 1] = clock64();
             if (lead) {
-                const uint32_t hi = tc::smem_u32(part(s, 0)), lo = tc::smem_u32(part(s, 1));
+                // descriptors of k-step 0; a k-step (two k-groups) further is +2 * kGroupBytes / 16 in the address field
+                uint64_t a_hi = d_a_hi[s], a_lo = d_a_lo[s], b_hi = d_b_hi[s], b_lo = d_b_lo[s];
                 for (int ks = 0; ks < (KT >> 3); ++ks) {
-                    const uint32_t o = (uint32_t)ks * 2u * kGroupBytes;
-                    const uint64_t a_hi = tc::make_desc(hi + o, kGroupBytes, 128);
-                    const uint64_t a_lo = tc::make_desc(lo + o, kGroupBytes, 128);
-                    const uint64_t b_hi = tc::make_desc(hi + o + kBRow0 * 16, kGroupBytes, 128);
-                    const uint64_t b_lo = tc::make_desc(lo + o + kBRow0 * 16, kGroupBytes, 128);
                     tc::mma_tf32(tmem, a_hi, b_hi, idesc, acc_on);
                     tc::mma_tf32(tmem, a_hi, b_lo, idesc, 1u);
                     tc::mma_tf32(tmem, a_lo, b_hi, idesc, 1u);
                     acc_on = 1u;
+                    a_hi += kStepDesc; a_lo += kStepDesc; b_hi += kStepDesc; b_lo += kStepDesc;
                 }
                 tc::mma_commit(tc::smem_u32(bars + s));                   // buffer s free when these complete
+                if (a.trace && blockIdx.x == 0 && i < 250) g_wg_trace[1024 + 4 * i + 2] = clock64();
             }
             __syncwarp();
             if (clock.tick(i + 1 == n_tiles)) {
@@ -410,6 +463,13 @@ extern "C" int nfk_conv2d_wgrad_tc(const float* in, const float* gpre, int g_par
     a.xch_stride = bank_spread((R + 2) * a.row_stride);
     a.gch_stride = bank_spread(R * a.row_stride);
     a.raw_bytes = (8 * a.xch_stride + Co * a.gch_stride) * (int)sizeof(float);
+    {   // per-thread slot capacity of the producers
+        const int groups = a.KT / 8;
+        const int tasks = (72 + Co) * groups;
+        const int chunks = (8 * (R + 2) + Co * R) * (L1 / 4 + 2);
+        if (tasks > kSlots * kProducerThreads || chunks > kCpSlots * kProducerThreads) return NFK_EUNSUPPORTED;
+    }
+    a.trace = getenv("NFK_WGRAD_TRACE") ? 1 : 0;
     a.drain_every = 4;
     if (const char* e = getenv("NFK_WGRAD_DRAIN")) {                      // tuning knob
         const int v = atoi(e);
@@ -417,4 +477,9 @@ extern "C" int nfk_conv2d_wgrad_tc(const float* in, const float* gpre, int g_par
     }
     cudaStream_t st = NFK_STREAM(stream);
     return sparse ? launch<true>(a, st) : launch<false>(a, st);
+}
+
+extern "C" int nfk_debug_wgrad_trace(long long* host_out, int n) {
+    return cudaMemcpyFromSymbol(host_out, g_wg_trace, sizeof(long long) * (size_t)(n < 2048 ? n : 2048)) == cudaSuccess
+               ? NFK_OK : NFK_ECUDA;
 }
