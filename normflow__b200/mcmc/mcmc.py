@@ -154,9 +154,10 @@ class BlockedMCMCSampler(MCMCSampler):
         logp = torch.empty((batch_size,), dtype=torch.float32, device=x.device)
         accept_seq = np.empty((batch_size, n_blocks), dtype=bool)
         current = None                      # (y, logq, logp) of the configuration x stands for
+        evaluate = self._make_evaluator(x)
         for ind in range(batch_size):
             accept_seq[ind], logqp_ref, current = self.sweep(x, n_blocks, logqp_ref, current=current,
-                                                             return_state=True)
+                                                             return_state=True, evaluate=evaluate)
             cfgs[ind:ind + 1], logq[ind:ind + 1], logp[ind:ind + 1] = current
 
         self._ref['sample'] = cfgs[-1].clone()
@@ -168,33 +169,64 @@ class BlockedMCMCSampler(MCMCSampler):
             self.history.bookkeeping(accept_seq=accept_seq.ravel())
         return cfgs, logq, logp
 
+    cuda_graph = True       # replay the single-configuration evaluation as one CUDA graph (CUDA tensors only)
+
     def _evaluate(self, x):
         y, logJ = self._model.net_(x)
         return y, self._model.prior.log_prob(x) - logJ, -self._model.action(y)
 
+    def _make_evaluator(self, x):
+        """The evaluation of the ONE configuration buffer `x`, as a callable.  A sweep is a chain of
+        single-configuration flow evaluations, each a dozen or more launches of a few microseconds: captured
+        once per `sample__` call and replayed, it is one graph launch per proposal.  The callable returns
+        buffers that the next call overwrites."""
+        if not (self.cuda_graph and x.is_cuda):
+            return lambda: self._evaluate(x)
+        try:
+            side = torch.cuda.Stream(device=x.device)
+            side.wait_stream(torch.cuda.current_stream(x.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):                   # first-use initialisation happens outside the capture
+                    self._evaluate(x)
+            torch.cuda.current_stream(x.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self._evaluate(x)
+        except Exception as err:                     # e.g. a user conditioner that cannot be captured
+            print(f"BlockedMCMCSampler: CUDA graph capture failed ({type(err).__name__}); evaluating eagerly")
+            torch.cuda.synchronize(x.device)
+            return lambda: self._evaluate(x)
+
+        def replay():
+            graph.replay()
+            return out
+        return replay
+
     @torch.no_grad()
-    def sweep(self, x, n_blocks=1, logqp_ref=None, current=None, return_state=False):
+    def sweep(self, x, n_blocks=1, logqp_ref=None, current=None, return_state=False, evaluate=None):
         """One in-place sweep over the blocks of x (shape (1, *lattice)); returns the accept flags and
         the updated reference log q - log p (mcmc.py:196-219)."""
         prior = self._model.prior
+        if evaluate is None:
+            evaluate = lambda: self._evaluate(x)
         accept_seq = np.empty(n_blocks, dtype=bool)
         lrand_arr = np.log(np.random.rand(n_blocks))
         for ind in range(n_blocks):
             prior.blockupdater(x, ind)
-            proposal = self._evaluate(x)
+            proposal = evaluate()
             logqp = float((proposal[1].double() - proposal[2].double())[0])      # the step's one host sync
             if ind == 0 and logqp_ref is None:
                 accept_seq[ind] = True
             else:
                 accept_seq[ind] = lrand_arr[ind] < logqp_ref - logqp
             if accept_seq[ind]:
-                logqp_ref, current = logqp, proposal
+                logqp_ref, current = logqp, tuple(t.clone() for t in proposal)     # the evaluator reuses its buffers
             else:
                 prior.blockupdater.restore(x, ind)
         if not return_state:
             return accept_seq, logqp_ref
         if current is None:                 # every proposal rejected and no earlier evaluation at hand
-            current = self._evaluate(x)
+            current = tuple(t.clone() for t in evaluate())
         return accept_seq, logqp_ref, current
 
 
