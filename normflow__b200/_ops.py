@@ -654,6 +654,9 @@ def _conv_weight_grad(inp, in_mask, in_keep, gpre, w_shape, want_bias, shape, ks
         if rc != _C.EUNSUPPORTED:
             check(rc, "conv2d_wgrad_tc")
             return gw, gb
+    if in_mask is not None and Ci == 1 and len(shape) == 2 and int(ksize) == 3:
+        # first layer: apply Mask.split once (one cheap pass) so that the streamed weight-gradient kernel can be used
+        inp, in_mask = mask_select(inp, in_mask, in_keep), None
     if g_parity is not None and in_mask is None:
         # gpre lives on one checkerboard partition only: visit just those sites
         with _C.timed(f"conv_circ_bwd_weight_cb[{Ci}->{Co}]"):

@@ -839,6 +839,13 @@ static int conv_bwd_weight_impl(const float* in, const uint8_t* in_mask, int in_
                              : wgrad2d_async_launch<8, 7, false>(w, NFK_STREAM(stream));
             if (rc != NFK_EUNSUPPORTED) return rc;
         }
+        // one input channel without a mask (the caller has applied Mask.split): the streamed kernel again
+        if (Ci == 1 && !in_mask && Co <= 8 && lat.shape[1] % 4 == 0 && ((uintptr_t)in % 16) == 0 &&
+            ((uintptr_t)gpre % 16) == 0) {
+            rc = wgrad2d_small_ok(w) ? wgrad2d_small_launch<1, 8, false>(w, NFK_STREAM(stream))
+                                     : wgrad2d_async_launch<1, 8, false>(w, NFK_STREAM(stream));
+            if (rc != NFK_EUNSUPPORTED) return rc;
+        }
         if (Ci == 1) rc = wgrad2d_launch<1, 8, false>(w, NFK_STREAM(stream));
         else if (Co <= 8) rc = sparse ? wgrad2d_launch<8, 8, true>(w, NFK_STREAM(stream))
                                       : wgrad2d_launch<8, 8, false>(w, NFK_STREAM(stream));
