@@ -110,9 +110,12 @@ __device__ __forceinline__ void conv2d_tile_fma(const float (&win)[3][6], const 
     }
 }
 
+// L1C, RC > 0: row length / rows per strip fixed at compile time (shared-memory addresses become base + immediate)
+template <int L1C, int RC>
 __global__ void __launch_bounds__(256) conv2d_tile_kernel(Conv2dArgs a) {
     extern __shared__ __align__(16) float sm2[];
-    const int L0 = a.L0, L1 = a.L1, R = a.R, LW = L1 + 8;            // interior at +4 (16-byte aligned), halos at +3, +4+L1
+    const int L0 = a.L0, L1 = L1C > 0 ? L1C : a.L1, R = RC > 0 ? RC : a.R;
+    const int LW = L1 + 8;                                             // interior at +4 (16-byte aligned), halos at +3, +4+L1
     float* in_s = sm2;                                                 // [kC2Chunk][R + 2][LW]
     float* w_s = sm2 + kC2Chunk * (R + 2) * LW;                        // [kC2Chunk][9][8]
     const int tid = threadIdx.x, nq = L1 >> 2;
@@ -225,9 +228,18 @@ static int conv2d_tile_launch(const float* in, const float* w, int w_transposed,
     a.in_parity = (in_parity >= 0 && L0 % 2 == 0 && L1 % 2 == 0 && in_mask == nullptr) ? in_parity : -1;
     const size_t smem = (size_t)(kC2Chunk * (R + 2) * (L1 + 8) + kC2Chunk * 72) * sizeof(float);
     if (smem > 160 * 1024) return NFK_EUNSUPPORTED;
-    if (ensure_dynamic_smem<conv2d_tile_kernel>(160 * 1024) != NFK_OK) return NFK_ECUDA;
     const int threads = (R * nq + 31) / 32 * 32;
-    conv2d_tile_kernel<<<dim3((unsigned)(B * a.strips), (unsigned)((Co + 7) / 8)), threads, smem, st>>>(a);
+    const dim3 grid((unsigned)(B * a.strips), (unsigned)((Co + 7) / 8));
+    if (L1 == 64 && R == 16) {
+        if (ensure_dynamic_smem<conv2d_tile_kernel<64, 16>>(160 * 1024) != NFK_OK) return NFK_ECUDA;
+        conv2d_tile_kernel<64, 16><<<grid, threads, smem, st>>>(a);
+    } else if (L1 == 32 && R == 32) {
+        if (ensure_dynamic_smem<conv2d_tile_kernel<32, 32>>(160 * 1024) != NFK_OK) return NFK_ECUDA;
+        conv2d_tile_kernel<32, 32><<<grid, threads, smem, st>>>(a);
+    } else {
+        if (ensure_dynamic_smem<conv2d_tile_kernel<0, 0>>(160 * 1024) != NFK_OK) return NFK_ECUDA;
+        conv2d_tile_kernel<0, 0><<<grid, threads, smem, st>>>(a);
+    }
     return check_launch();
 }
 
@@ -550,10 +562,13 @@ __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(src) : "memory");
 }
 
-template <int CI, int CO_B, bool SPARSE>
+// L1C, RC > 0: row length and rows per strip fixed at compile time, which turns every shared-memory address
+// of the inner loop into base + immediate (with run-time strides the kernel spent 40 % of its instructions on
+// integer address arithmetic and spilled its accumulators; ncu, 64x64).
+template <int CI, int CO_B, bool SPARSE, int L1C = 0, int RC = 0>
 __global__ void __launch_bounds__(288, 2) conv2d_wgrad_async_kernel(Wgrad2dArgs a) {
     extern __shared__ __align__(16) float sm[];
-    const int L0 = a.L0, L1 = a.L1, R = a.R, LW = L1 + 8;
+    const int L0 = a.L0, L1 = L1C > 0 ? L1C : a.L1, R = RC > 0 ? RC : a.R, LW = L1 + 8;
     const int in_floats = CI * (R + 2) * LW, buf_floats = in_floats + CO_B * R * L1;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int kh = warp / 3, kw = warp % 3;
@@ -655,12 +670,21 @@ static int wgrad2d_async_launch(Wgrad2dArgs a, cudaStream_t st) {
     while (R > 1 && bytes(R) > 100 * 1024) R /= 2;                        // two CTAs per SM
     if (bytes(R) > 100 * 1024) return NFK_EUNSUPPORTED;
     a.R = R;
-    if (ensure_dynamic_smem<conv2d_wgrad_async_kernel<CI, CO_B, SPARSE>>(100 * 1024) != NFK_OK) return NFK_ECUDA;
     const int ncb = (a.Co + CO_B - 1) / CO_B;
     long long gx = (148LL * 2 + ncb - 1) / ncb;
     if (gx > a.B) gx = a.B;
     if (gx < 1) gx = 1;
-    conv2d_wgrad_async_kernel<CI, CO_B, SPARSE><<<dim3((unsigned)gx, ncb), 288, bytes(R), st>>>(a);
+    const dim3 grid((unsigned)gx, ncb);
+    if (a.L1 == 64 && R == 8) {                                           // the benchmark geometry: compile-time strides
+        if (ensure_dynamic_smem<conv2d_wgrad_async_kernel<CI, CO_B, SPARSE, 64, 8>>(100 * 1024) != NFK_OK) return NFK_ECUDA;
+        conv2d_wgrad_async_kernel<CI, CO_B, SPARSE, 64, 8><<<grid, 288, bytes(R), st>>>(a);
+    } else if (a.L1 == 32 && R == 16) {
+        if (ensure_dynamic_smem<conv2d_wgrad_async_kernel<CI, CO_B, SPARSE, 32, 16>>(100 * 1024) != NFK_OK) return NFK_ECUDA;
+        conv2d_wgrad_async_kernel<CI, CO_B, SPARSE, 32, 16><<<grid, 288, bytes(R), st>>>(a);
+    } else {
+        if (ensure_dynamic_smem<conv2d_wgrad_async_kernel<CI, CO_B, SPARSE>>(100 * 1024) != NFK_OK) return NFK_ECUDA;
+        conv2d_wgrad_async_kernel<CI, CO_B, SPARSE><<<grid, 288, bytes(R), st>>>(a);
+    }
     return check_launch();
 }
 
