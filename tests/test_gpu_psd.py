@@ -440,3 +440,30 @@ def test_example_net_trains_eager_and_graph():
         losses[mode] = hist
     np.testing.assert_allclose(losses[True][:5], losses[False][:5], rtol=2e-4, atol=2e-3)
     np.testing.assert_allclose(losses[True], losses[False], rtol=5e-2, atol=0.5)
+
+
+def test_example_scripts_run(tmp_path, capsys):
+    """examples/scalar_zerodim.py and examples/scalar_affine.py (this package's versions of the reference's two
+    example scripts) train, write a snapshot in the reference's format and pass the backward sanity check."""
+    import importlib.util
+    import os
+    from conftest import ROOT
+
+    def load(name):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "examples", name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+
+    torch.manual_seed(1)
+    np.random.seed(1)
+    model = load("scalar_zerodim").main(n_epochs=300, batch_size=1024, print_stride=100)
+    assert np.mean(model.fit.train_history['loss'][-20:]) < -1.05
+    snap = tmp_path / "affine.E0.tar"
+    model = load("scalar_affine").main(lat_shape=(8, 8), n_epochs=40, batch_size=128, print_stride=20,
+                                       snapshot_path=str(snap), save_every=20, knots2_len=12, knots4_len=12)
+    hist = np.array(model.fit.train_history['loss'])
+    assert len(hist) == 40 and np.isfinite(hist).all() and hist[-5:].mean() < hist[:5].mean()
+    assert (tmp_path / "affine.E20.tar").exists() and (tmp_path / "affine.E40.tar").exists()
+    out = capsys.readouterr().out
+    assert "Sanity check is OK" in out
