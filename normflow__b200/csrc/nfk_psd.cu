@@ -15,6 +15,7 @@
 // Lh = L[-1]/2+1), w real [Kc].  All three are HBM-bound streams: 16 B per spectrum
 // element forward (8 in place), 24 B backward.
 #include "nfk_common.cuh"
+#include "nfk_psd.cuh"
 
 #define NFK_STREAM(s) reinterpret_cast<cudaStream_t>(s)
 
@@ -39,34 +40,25 @@ __device__ __forceinline__ double block_sum_f64(double v) {
     return v;
 }
 
-__device__ __forceinline__ float psd_mult(int64_t k, int Lh) {
-    const int col = (int)(k % Lh);
-    return 2.f - (col == 0 ? 1.f : 0.f) - (col == Lh - 1 ? 1.f : 0.f);
-}
-
 // one CTA; Kc is at most a few 10^4 and this runs once per flow evaluation
 __global__ void psd_weights_kernel(const float* __restrict__ ipsd, int64_t Kc, int Lh, int inverse,
                                    float* __restrict__ w, float* __restrict__ logj) {
     double acc = 0.0;
     for (int64_t k = threadIdx.x; k < Kc; k += blockDim.x) {
         const float s = ipsd[k];
-        w[k] = inverse ? sqrtf(s) : 1.f / sqrtf(s);
-        acc += (double)psd_mult(k, Lh) * (double)logf(s);
+        w[k] = psd_weight(s, inverse);
+        acc += psd_logj_term(k, Lh, s);
     }
     acc = block_sum_f64(acc);
     if (threadIdx.x == 0) logj[0] = (float)((inverse ? 0.5 : -0.5) * acc);
 }
 
-// g_ipsd = sign/2 * (gw*w + glogj*m) / ipsd      (sign = -1 forward map, +1 inverse map)
 __global__ void psd_weights_bwd_kernel(const float* __restrict__ ipsd, const float* __restrict__ w,
                                        const float* __restrict__ gw, const float* __restrict__ glogj,
                                        int64_t Kc, int Lh, int inverse, float* __restrict__ g_ipsd) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= Kc) return;
-    const float gl = glogj ? glogj[0] : 0.f;
-    const float gwk = gw ? gw[k] : 0.f;
-    const float v = 0.5f * (gwk * w[k] + gl * psd_mult(k, Lh)) / ipsd[k];
-    g_ipsd[k] = inverse ? v : -v;
+    g_ipsd[k] = psd_weight_grad(k, Lh, ipsd[k], w[k], gw ? gw[k] : 0.f, glogj ? glogj[0] : 0.f, inverse);
 }
 
 // grid = (ceil(Kc / threads), sample chunks); a thread owns one k and walks its chunk of

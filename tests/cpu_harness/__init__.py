@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 SRC = os.path.join(HERE, "harness.cpp")
 OUT = os.path.join(HERE, "_build", "harness.so")
-DEPS = [SRC] + [os.path.join(ROOT, "normflow__b200", "csrc", f) for f in ("nfk_math.cuh", "nfk_ops.cuh", "nfk_knots.cuh")]
+DEPS = [SRC] + [os.path.join(ROOT, "normflow__b200", "csrc", f) for f in ("nfk_math.cuh", "nfk_ops.cuh", "nfk_knots.cuh", "nfk_psd.cuh")]
 
 
 class Lattice(ctypes.Structure):

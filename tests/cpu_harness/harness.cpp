@@ -14,6 +14,7 @@
 #include "../../normflow__b200/csrc/nfk_ops.cuh"
 #include "../../normflow__b200/csrc/nfk_fused.cuh"
 #include "../../normflow__b200/csrc/nfk_knots.cuh"
+#include "../../normflow__b200/csrc/nfk_psd.cuh"
 
 using namespace nfk;
 
@@ -37,6 +38,21 @@ static RqsCfg to_cfg(const nfk_rqs_params& p) {
 #define FOR_EACH_K(X) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(14) X(16) X(20) X(24) X(32)
 
 extern "C" {
+
+int cpu_psd_weights_fwd(const float* ipsd, int64_t Kc, int Lh, int inverse, float* w, float* logj) {
+    double acc = 0.0;
+    for (int64_t k = 0; k < Kc; ++k) {
+        w[k] = psd_weight(ipsd[k], inverse);
+        acc += psd_logj_term(k, Lh, ipsd[k]);
+    }
+    logj[0] = (float)((inverse ? 0.5 : -0.5) * acc);
+    return 0;
+}
+int cpu_psd_weights_bwd(const float* ipsd, const float* w, const float* gw, float glogj, int64_t Kc, int Lh,
+                        int inverse, float* g_ipsd) {
+    for (int64_t k = 0; k < Kc; ++k) g_ipsd[k] = psd_weight_grad(k, Lh, ipsd[k], w[k], gw[k], glogj, inverse);
+    return 0;
+}
 
 int cpu_knots_fwd(const float* wx, const float* wy, const float* wd, int K, float xlo, float xw, float ylo,
                   float yw, float* table) {

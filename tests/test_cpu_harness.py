@@ -457,3 +457,37 @@ def test_fused_2d_step_with_bias_and_odd_mask_parity():
                                   parity, 0, None, fp(y), fp(lo), L0, L1, I64(B), 4) == 0
         close(y, yr.astype(np.float64), tol=2e-5)
         close(lo, lr.astype(np.float64), tol=2e-5)
+
+
+@pytest.mark.parametrize("shape", [(8, 4), (6,), (4, 6, 3), (16, 9), (5, 1)])
+@pytest.mark.parametrize("inverse", [0, 1])
+def test_psd_weights_arithmetic(shape, inverse):
+    """nfk_psd.cuh (the spectral-weight kernel's own code): w = ipsd^(-+1/2) and the log-Jacobian against the
+    oracle's FFTNet_.log_jacobian (fftflow_.py:167-180); its adjoint against central differences of the oracle."""
+    from oracle import nf_oracle as O
+    rs = np.random.RandomState(len(shape) * 10 + inverse)
+    ipsd = f32(rs.rand(*shape) * 3 + 0.05)
+    Kc, Lh = ipsd.size, shape[-1]
+    w, logj = np.empty_like(ipsd), np.empty(1, dtype=np.float32)
+    H.cpu_psd_weights_fwd(fp(ipsd), I64(Kc), Lh, inverse, fp(w), fp(logj))
+
+    def ref(v):
+        wr = 1 / v ** 0.5
+        lj = O.fftnet_log_jacobian(wr)
+        return (1 / wr, -lj) if inverse else (wr, lj)
+    wr, lr = ref(ipsd.astype(np.float64))
+    close(w, wr, tol=2e-7)
+    close(logj, lr, tol=1e-6)
+    r, c = f32(rs.randn(*shape)), 0.7
+    g = np.empty_like(ipsd)
+    H.cpu_psd_weights_bwd(fp(ipsd), fp(w), fp(r), ctypes.c_float(c), I64(Kc), Lh, inverse, fp(g))
+    num = np.empty(ipsd.shape)
+    for idx in np.ndindex(*ipsd.shape):
+        vals = []
+        for sgn in (1, -1):
+            v = ipsd.astype(np.float64).copy()
+            v[idx] += sgn * 1e-6
+            wv, lv = ref(v)
+            vals.append((wv * r).sum() + c * lv)
+        num[idx] = (vals[0] - vals[1]) / 2e-6
+    close_grad(g, num, tol=5e-6)
