@@ -515,16 +515,18 @@ NFK_HD UnitSeg spline_unit_forward(const UnitKnots& k, Unit u, Unit& v, float& l
     unit_widths(k, unit_segment(k.kx, k.cx, k.K, u), sg);
     const RqSeg& g = sg.g;
     const bool up = u.s > 0.5f;
-    sg.th = (up ? k.cx[sg.j] - u.c : u.s - g.X0) / g.w;        // (s - X0)/w
-    sg.om = (up ? u.c - sg.cX1 : k.kx[sg.j + 1] - u.s) / g.w;   // (X1 - s)/w
+    const float rw = 1.f / g.w;                                   // one reciprocal serves theta, omega and the slope
+    sg.th = (up ? k.cx[sg.j] - u.c : u.s - g.X0) * rw;           // (s - X0)/w
+    sg.om = (up ? u.c - sg.cX1 : k.kx[sg.j + 1] - u.s) * rw;     // (X1 - s)/w
     const float th = sg.th, om = sg.om;
-    const float m = g.h / g.w;
+    const float m = g.h * rw;
     const float sig = g.D0 + g.D1 - 2.f * m;
-    const float den = m + sig * th * om;
-    v.s = g.Y0 + g.h * th * (m * th + g.D0 * om) / den;
-    v.c = sg.cY1 + g.h * om * (m * om + g.D1 * th) / den;       // Y1 - g0: an exact identity
+    const float rden = 1.f / (m + sig * th * om);
+    v.s = g.Y0 + g.h * th * (m * th + g.D0 * om) * rden;
+    v.c = sg.cY1 + g.h * om * (m * om + g.D1 * th) * rden;       // Y1 - g0: an exact identity
     const float Q = g.D1 * th * th + 2.f * m * th * om + g.D0 * om * om;
-    logg = logf(m * m * Q / (den * den));
+    const float mr = m * rden;
+    logg = logf(mr * mr * Q);
     return sg;
 }
 
@@ -535,8 +537,9 @@ NFK_HD void spline_unit_inverse(const UnitKnots& k, Unit v, Unit& u, float& logi
     const RqSeg& g = sg.g;
     const bool up = v.s > 0.5f;
     const float m = g.h / g.w;
-    const float eta = (up ? k.cy[sg.j] - v.c : v.s - g.Y0) / g.h;
-    const float ome = (up ? v.c - sg.cY1 : k.ky[sg.j + 1] - v.s) / g.h;      // 1 - eta
+    const float rh = 1.f / g.h;
+    const float eta = (up ? k.cy[sg.j] - v.c : v.s - g.Y0) * rh;
+    const float ome = (up ? v.c - sg.cY1 : k.ky[sg.j + 1] - v.s) * rh;      // 1 - eta
     float th, om;
     if (eta <= 0.5f) {
         th = rq_theta_from_eta(m, g.D0, g.D1, eta);
@@ -550,7 +553,8 @@ NFK_HD void spline_unit_inverse(const UnitKnots& k, Unit v, Unit& u, float& logi
     const float Q = g.D1 * th * th + 2.f * m * th * om + g.D0 * om * om;
     u.s = g.X0 + g.w * th;
     u.c = sg.cX1 + g.w * om;
-    loginv = -logf(m * m * Q / (den * den));
+    const float mr = m / den;
+    loginv = -logf(mr * mr * Q);
 }
 
 // DistConvertor_ forward (inverse = false) or ModuleList_.backward (inverse = true):
@@ -558,14 +562,19 @@ NFK_HD void spline_unit_inverse(const UnitKnots& k, Unit v, Unit& u, float& logi
 // anti != 0: odd extension about 0 (xlim0 = ylim0 = 0.5, extrap left 'anti').
 NFK_HD void distconv_eval(const UnitKnots& k, bool anti, bool inverse, float x, float& y, float& logj) {
     const float xa = anti ? fabsf(x) : x;
-    const Unit u = expit_pair(xa);
+    // expit_pair and log_sc_from_x share e^{-|x|}
+    const float a = fabsf(xa), e = expf(-a);
+    const float big = 1.f / (1.f + e), small = e * big;
+    Unit u;
+    u.s = xa >= 0.f ? big : small;
+    u.c = xa >= 0.f ? small : big;
     Unit v;
     float lg;
     if (!inverse) spline_unit_forward(k, u, v, lg);
     else spline_unit_inverse(k, u, v, lg);
     const float ls = logf(v.s), lc = logf(v.c);
     y = anti ? copysignf(ls - lc, x) : ls - lc;
-    logj = log_sc_from_x(xa) + lg - (ls + lc);
+    logj = (-a - 2.f * log1pf(e)) + lg - (ls + lc);
 }
 
 // VJP of distconv_eval (forward direction).  `acc(i, v)` accumulates into a [5K]
