@@ -62,20 +62,25 @@ struct RqSegGrad {
 //   m = h/w, theta = (x - X0)/w, omega = 1 - theta
 //   y    = Y0 + h theta (m theta + D0 omega) / (m + (D0 + D1 - 2m) theta omega)
 //   dydx = m^2 (D1 theta^2 + 2 m theta omega + D0 omega^2) / (...)^2
-NFK_HD void rq_eval_theta(const RqSeg& s, float th, float om, float& y, float& logg) {
-    const float m = s.h / s.w;
+// `m` = h / w is handed in so that callers who already hold 1 / w do not divide twice.
+NFK_HD void rq_eval_theta_m(const RqSeg& s, float m, float th, float om, float& y, float& logg) {
     const float sig = s.D0 + s.D1 - 2.f * m;
     const float tom = th * om;
-    const float den = m + sig * tom;
+    const float rden = 1.f / (m + sig * tom);
     const float N = m * th * th + s.D0 * tom;
-    y = s.Y0 + s.h * N / den;
+    y = s.Y0 + s.h * N * rden;
     const float Q = s.D1 * th * th + 2.f * m * tom + s.D0 * om * om;
-    logg = logf(m * m * Q / (den * den));
+    const float mr = m * rden;
+    logg = logf(mr * mr * Q);
+}
+NFK_HD void rq_eval_theta(const RqSeg& s, float th, float om, float& y, float& logg) {
+    rq_eval_theta_m(s, s.h / s.w, th, om, y, logg);
 }
 
 NFK_HD void rq_forward(const RqSeg& s, float x, float& y, float& logg) {
-    const float th = (x - s.X0) / s.w;
-    rq_eval_theta(s, th, 1.f - th, y, logg);
+    const float rw = 1.f / s.w;
+    const float th = (x - s.X0) * rw;
+    rq_eval_theta_m(s, s.h * rw, th, 1.f - th, y, logg);
 }
 
 // theta solving  a2 theta^2 + a1 theta + a0 = 0  for eta = (y - Y0)/h
@@ -98,10 +103,10 @@ NFK_HD void rq_inverse(const RqSeg& s, float y, float& x, float& loginv) {
     const float th = rq_theta_from_eta(m, s.D0, s.D1, eta);
     const float om = 1.f - th;
     const float sig = s.D0 + s.D1 - 2.f * m;
-    const float den = m + sig * th * om;
+    const float mr = m / (m + sig * th * om);
     const float Q = s.D1 * th * th + 2.f * m * th * om + s.D0 * om * om;
     x = s.X0 + s.w * th;
-    loginv = -logf(m * m * Q / (den * den));
+    loginv = -logf(mr * mr * Q);
 }
 
 // Vector-Jacobian product of (y, logg) = rq_forward(seg, x):
@@ -112,7 +117,8 @@ NFK_HD void rq_inverse(const RqSeg& s, float y, float& x, float& loginv) {
 //   Q = D1 a + 2 m b + D0 c ; logg = 2 log m + log Q - 2 log den
 // `th`, `om` = theta and 1 - theta, handed in so callers can form them without cancellation.
 NFK_HD RqSegGrad rq_vjp_theta(const RqSeg& s, float th, float om, float gy, float gl) {
-    const float m = s.h / s.w;
+    const float rw = 1.f / s.w;
+    const float m = s.h * rw;
     const float a = th * th;
     const float b = th * om;
     const float c = om * om;
@@ -137,7 +143,6 @@ NFK_HD RqSegGrad rq_vjp_theta(const RqSeg& s, float th, float om, float gy, floa
     gm -= 2.f * gsig;
     ga += gc - gb;
     const float gth = -2.f * gc + gb + 2.f * th * ga;
-    const float rw = 1.f / s.w;
     gh += gm * rw;
     r.gw = -gm * m * rw - gth * th * rw;
     r.gx = gth * rw;
@@ -147,7 +152,7 @@ NFK_HD RqSegGrad rq_vjp_theta(const RqSeg& s, float th, float om, float gy, floa
     return r;
 }
 NFK_HD RqSegGrad rq_forward_vjp(const RqSeg& s, float x, float gy, float gl) {
-    const float th = (x - s.X0) / s.w;
+    const float th = (x - s.X0) / s.w;          // (rq_vjp_theta forms its own 1 / w; the compiler merges the two)
     return rq_vjp_theta(s, th, 1.f - th, gy, gl);
 }
 
@@ -308,7 +313,8 @@ NFK_HD float rqs_site_backward(const Ld& ld, const RqsCfg& cfg, float x, float g
     }
     const float raw0 = ld.pick(2 * K - 2, K, st.j), raw1 = ld.pick(2 * K - 2, K, st.j + 1);
     RqSeg s;
-    const float rx = cfg.xw / st.sx, ry = cfg.yw / st.sy;
+    const float isx = 1.f / st.sx, isy = 1.f / st.sy;              // one reciprocal per softmax normaliser
+    const float rx = cfg.xw * isx, ry = cfg.yw * isy;
     const float exj = pick<K - 1>(st.ex, st.j), eyj = pick<K - 1>(st.ey, st.j);
     s.X0 = cfg.xlim0 + st.cumx * rx;
     s.w = exj * rx;
@@ -319,8 +325,8 @@ NFK_HD float rqs_site_backward(const Ld& ld, const RqsCfg& cfg, float x, float g
     const RqSegGrad g = rq_forward_vjp(s, x, gy, gl);
     // chain through X0 = xlim0 + xw sum_{i<j} p_i, w = xw p_j, p = softmax(raw):
     //   d/draw_k = xw p_k ( gX0 ([k<j] - C_j) + gw ([k==j] - p_j) )
-    const float Cx = st.cumx / st.sx, px = exj / st.sx;
-    const float Cy = st.cumy / st.sy, py = eyj / st.sy;
+    const float Cx = st.cumx * isx, px = exj * isx;
+    const float Cy = st.cumy * isy, py = eyj * isy;
 #pragma unroll
     for (int k = 0; k < K - 1; ++k) {
         const float below = k < st.j ? 1.f : 0.f, here = k == st.j ? 1.f : 0.f;
