@@ -93,26 +93,34 @@ constexpr int kC2Chunk = 8;      // input channels per shared-memory stage
 
 // NC columns x 8 output channels += 3 x (NC + 2) window (x) 9 x 8 weights of one input channel.  SPARSE: the window
 // entry (dr, k + dc) is known to be zero unless (dr + dc + k + A0) is even, and its products are left out.
-template <bool SPARSE, int A0, int NC>
+template <bool SPARSE, int A0, int NC, int NCO>
 __device__ __forceinline__ void conv2d_tile_fma(const float (&win)[3][NC + 2], const float* __restrict__ w_ci,
-                                                float (&acc)[NC][8]) {
+                                                float (&acc)[NC][NCO]) {
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
-        const float4 w0 = *reinterpret_cast<const float4*>(w_ci + t * 8);
-        const float4 w1 = *reinterpret_cast<const float4*>(w_ci + t * 8 + 4);
-        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        float wv[NCO];
+        if (NCO == 8) {
+            const float4 w0 = *reinterpret_cast<const float4*>(w_ci + t * 8);
+            const float4 w1 = *reinterpret_cast<const float4*>(w_ci + t * 8 + 4);
+            wv[0] = w0.x; wv[1 % NCO] = w0.y; wv[2 % NCO] = w0.z; wv[3 % NCO] = w0.w;
+            wv[4 % NCO] = w1.x; wv[5 % NCO] = w1.y; wv[6 % NCO] = w1.z; wv[7 % NCO] = w1.w;
+        } else {
+#pragma unroll
+            for (int co = 0; co < NCO; ++co) wv[co] = w_ci[t * 8 + co];
+        }
 #pragma unroll
         for (int k = 0; k < NC; ++k) {
             if (SPARSE && ((t / 3 + t % 3 + k + A0) & 1)) continue;
 #pragma unroll
-            for (int co = 0; co < 8; ++co) acc[k][co] = fmaf(win[t / 3][k + t % 3], wv[co], acc[k][co]);
+            for (int co = 0; co < NCO; ++co) acc[k][co] = fmaf(win[t / 3][k + t % 3], wv[co], acc[k][co]);
         }
     }
 }
 
 // L1C, RC > 0: row length / rows per strip fixed at compile time (shared-memory addresses become base + immediate).
 // NC: columns per thread (4 or 8; with 8 every weight fetched from shared memory feeds twice the FMAs).
-template <int L1C, int RC, int NC>
+// NCO: output channels per CTA (8, or 1 for the thin 8 -> 1 data gradient of the first conditioner layer).
+template <int L1C, int RC, int NC, int NCO>
 __global__ void __launch_bounds__(256) conv2d_tile_kernel(Conv2dArgs a) {
     extern __shared__ __align__(16) float sm2[];
     const int L0 = a.L0, L1 = L1C > 0 ? L1C : a.L1, R = RC > 0 ? RC : a.R;
@@ -123,7 +131,7 @@ __global__ void __launch_bounds__(256) conv2d_tile_kernel(Conv2dArgs a) {
     const long long b = blockIdx.x / a.strips;
     const int r0 = (int)(blockIdx.x % a.strips) * R;
     const int rows = L0 - r0 < R ? L0 - r0 : R;
-    const int co0 = blockIdx.y * 8;
+    const int co0 = blockIdx.y * NCO;
     const int V = L0 * L1;
     // my row of the strip and my NC columns.  The rows a warp spans are two apart (within groups of 2 * rows-per-warp
     // rows the even ones come first), so that a warp sees ONE row parity and the sparse variants do not diverge.
@@ -131,11 +139,11 @@ __global__ void __launch_bounds__(256) conv2d_tile_kernel(Conv2dArgs a) {
     const int rpw = (npr <= 32 && 32 % npr == 0) ? 32 / npr : 1;
     const int j = (rpw > 1 && R % (2 * rpw) == 0) ? (jj / (2 * rpw)) * (2 * rpw) + (jj % rpw) * 2 + (jj / rpw) % 2 : jj;
     const bool live = j < rows;
-    float acc[NC][8];
+    float acc[NC][NCO];
 #pragma unroll
     for (int k = 0; k < NC; ++k)
 #pragma unroll
-        for (int co = 0; co < 8; ++co) acc[k][co] = (a.bias && co0 + co < a.Co) ? __ldg(a.bias + co0 + co) : 0.f;
+        for (int co = 0; co < NCO; ++co) acc[k][co] = (a.bias && co0 + co < a.Co) ? __ldg(a.bias + co0 + co) : 0.f;
     const float* in_b = a.in + b * (long long)a.Ci * V;
     for (int ci0 = 0; ci0 < a.Ci; ci0 += kC2Chunk) {
         const int nci = a.Ci - ci0 < kC2Chunk ? a.Ci - ci0 : kC2Chunk;
@@ -194,15 +202,15 @@ __global__ void __launch_bounds__(256) conv2d_tile_kernel(Conv2dArgs a) {
                 }
                 // input site (r0 + j + dr - 1, c0 + k + dc - 1) is on the partition iff dr + dc + k + a0 is even
                 const float* w_ci = w_s + ci * 72;
-                if (a.in_parity < 0) conv2d_tile_fma<false, 0, NC>(win, w_ci, acc);
-                else if ((r0 + j + a.in_parity) & 1) conv2d_tile_fma<true, 1, NC>(win, w_ci, acc);
-                else conv2d_tile_fma<true, 0, NC>(win, w_ci, acc);
+                if (a.in_parity < 0) conv2d_tile_fma<false, 0, NC, NCO>(win, w_ci, acc);
+                else if ((r0 + j + a.in_parity) & 1) conv2d_tile_fma<true, 1, NC, NCO>(win, w_ci, acc);
+                else conv2d_tile_fma<true, 0, NC, NCO>(win, w_ci, acc);
             }
         }
     }
     if (!live) return;
 #pragma unroll
-    for (int co = 0; co < 8; ++co) {
+    for (int co = 0; co < NCO; ++co) {
         if (co0 + co >= a.Co) break;
         const long long o = ((b * a.Co + co0 + co) * (long long)L0 + r0 + j) * L1 + c0;
 #pragma unroll
@@ -243,16 +251,27 @@ static int conv2d_tile_launch(const float* in, const float* w, int w_transposed,
     const size_t smem = (size_t)(kC2Chunk * (R + 2) * (L1 + 8) + kC2Chunk * 72) * sizeof(float);
     if (smem > 160 * 1024) return NFK_EUNSUPPORTED;
     const int threads = (R * npr + 31) / 32 * 32;
+    if (Co == 1) {                                                        // thin layer: one output channel per CTA
+        const dim3 grid1((unsigned)(B * a.strips), 1u);
+        if (L1 == 64 && R == 16) {
+            if (ensure_dynamic_smem<conv2d_tile_kernel<64, 16, NC, 1>>(160 * 1024) != NFK_OK) return NFK_ECUDA;
+            conv2d_tile_kernel<64, 16, NC, 1><<<grid1, threads, smem, st>>>(a);
+        } else {
+            if (ensure_dynamic_smem<conv2d_tile_kernel<0, 0, NC, 1>>(160 * 1024) != NFK_OK) return NFK_ECUDA;
+            conv2d_tile_kernel<0, 0, NC, 1><<<grid1, threads, smem, st>>>(a);
+        }
+        return check_launch();
+    }
     const dim3 grid((unsigned)(B * a.strips), (unsigned)((Co + 7) / 8));
     if (L1 == 64 && R == 16) {                                            // the benchmark geometry: compile-time strides
-        if (ensure_dynamic_smem<conv2d_tile_kernel<64, 16, NC>>(160 * 1024) != NFK_OK) return NFK_ECUDA;
-        conv2d_tile_kernel<64, 16, NC><<<grid, threads, smem, st>>>(a);
+        if (ensure_dynamic_smem<conv2d_tile_kernel<64, 16, NC, 8>>(160 * 1024) != NFK_OK) return NFK_ECUDA;
+        conv2d_tile_kernel<64, 16, NC, 8><<<grid, threads, smem, st>>>(a);
     } else if (L1 == 32 && R == 32) {
-        if (ensure_dynamic_smem<conv2d_tile_kernel<32, 32, NC>>(160 * 1024) != NFK_OK) return NFK_ECUDA;
-        conv2d_tile_kernel<32, 32, NC><<<grid, threads, smem, st>>>(a);
+        if (ensure_dynamic_smem<conv2d_tile_kernel<32, 32, NC, 8>>(160 * 1024) != NFK_OK) return NFK_ECUDA;
+        conv2d_tile_kernel<32, 32, NC, 8><<<grid, threads, smem, st>>>(a);
     } else {
-        if (ensure_dynamic_smem<conv2d_tile_kernel<0, 0, NC>>(160 * 1024) != NFK_OK) return NFK_ECUDA;
-        conv2d_tile_kernel<0, 0, NC><<<grid, threads, smem, st>>>(a);
+        if (ensure_dynamic_smem<conv2d_tile_kernel<0, 0, NC, 8>>(160 * 1024) != NFK_OK) return NFK_ECUDA;
+        conv2d_tile_kernel<0, 0, NC, 8><<<grid, threads, smem, st>>>(a);
     }
     return check_launch();
 }
@@ -286,7 +305,7 @@ static int conv_fwd_impl(const float* in, const float* w, int w_transposed, cons
                          void* stream) {
     if (!in || !w || !out || !lat_ok(lat) || ksize < 1 || ksize % 2 == 0 || Ci < 1 || Co < 1) return NFK_EINVAL;
     if (B <= 0) return NFK_OK;
-    if (lat.ndim == 2 && ksize == 3 && Co >= 4 && lat.shape[1] % 4 == 0 && lat.shape[0] >= 2 && lat.shape[1] >= 4 &&
+    if (lat.ndim == 2 && ksize == 3 && (Co >= 4 || (Co == 1 && Ci >= 4)) && lat.shape[1] % 4 == 0 && lat.shape[0] >= 2 && lat.shape[1] >= 4 &&
         B * (int64_t)((lat.shape[0] + 0) ) < (int64_t(1) << 31) && ((uintptr_t)in % 16) == 0 &&
         ((uintptr_t)out % 16) == 0 && (!dact_from || ((uintptr_t)dact_from % 16) == 0) &&
         (!in_mask || ((uintptr_t)in_mask % 4) == 0)) {
