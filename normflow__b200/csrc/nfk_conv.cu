@@ -608,13 +608,16 @@ __global__ void __launch_bounds__(288, 2) conv2d_wgrad_async_kernel(Wgrad2dArgs 
     const int co0 = blockIdx.y * CO_B;
     const int V = L0 * L1, nq = L1 >> 2;
     const int strips = (L0 + R - 1) / R;
-    float acc[CO_B][CI];
+    // One input channel: a tap per warp would mean 9 shared-memory loads per 8 FMAs.  Instead every warp takes
+    // rows of the strip and keeps all 9 taps (8 x 9 accumulators per lane): 17 loads per 72 FMAs.
+    constexpr bool kRowWarps = (CI == 1 && !SPARSE);
+    float acc[CO_B][kRowWarps ? 9 : CI];
     float accb[CO_B];
 #pragma unroll
     for (int co = 0; co < CO_B; ++co) {
         accb[co] = 0.f;
 #pragma unroll
-        for (int ci = 0; ci < CI; ++ci) acc[co][ci] = 0.f;
+        for (int ci = 0; ci < (kRowWarps ? 9 : CI); ++ci) acc[co][ci] = 0.f;
     }
     const long long n_mine = a.B > blockIdx.x ? (a.B - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const long long units = n_mine * strips;
@@ -660,37 +663,69 @@ __global__ void __launch_bounds__(288, 2) conv2d_wgrad_async_kernel(Wgrad2dArgs 
         const float* g_s = buf + in_floats;
         const int r0 = (int)(u % strips) * R;
         const int rows = L0 - r0 < R ? L0 - r0 : R;
-        for (int j = 0; j < rows; ++j)
-            for (int cc = lane; cc < (SPARSE ? L1 / 2 : L1); cc += 32) {
-                const int c = SPARSE ? 2 * cc + ((a.g_parity + r0 + j) & 1) : cc;
-                float gv[CO_B], xv[CI];
+        if constexpr (kRowWarps) {
+            for (int j = warp; j < rows; j += 9)
+                for (int c = lane; c < L1; c += 32) {
+                    float gv[CO_B], xv[9];
 #pragma unroll
-                for (int co = 0; co < CO_B; ++co) gv[co] = g_s[(co * R + j) * L1 + c];
+                    for (int co = 0; co < CO_B; ++co) gv[co] = g_s[(co * R + j) * L1 + c];
 #pragma unroll
-                for (int ci = 0; ci < CI; ++ci) xv[ci] = in_s[(ci * (R + 2) + j + kh) * LW + 3 + c + kw];
+                    for (int t = 0; t < 9; ++t) xv[t] = in_s[(j + t / 3) * LW + 3 + c + t % 3];
 #pragma unroll
-                for (int co = 0; co < CO_B; ++co) {
+                    for (int co = 0; co < CO_B; ++co) {
 #pragma unroll
-                    for (int ci = 0; ci < CI; ++ci) acc[co][ci] = fmaf(gv[co], xv[ci], acc[co][ci]);
+                        for (int t = 0; t < 9; ++t) acc[co][t] = fmaf(gv[co], xv[t], acc[co][t]);
+                        accb[co] += gv[co];
+                    }
                 }
-                if (warp == 4) {
+        } else {
+            for (int j = 0; j < rows; ++j)
+                for (int cc = lane; cc < (SPARSE ? L1 / 2 : L1); cc += 32) {
+                    const int c = SPARSE ? 2 * cc + ((a.g_parity + r0 + j) & 1) : cc;
+                    float gv[CO_B], xv[CI];
 #pragma unroll
-                    for (int co = 0; co < CO_B; ++co) accb[co] += gv[co];
+                    for (int co = 0; co < CO_B; ++co) gv[co] = g_s[(co * R + j) * L1 + c];
+#pragma unroll
+                    for (int ci = 0; ci < CI; ++ci) xv[ci] = in_s[(ci * (R + 2) + j + kh) * LW + 3 + c + kw];
+#pragma unroll
+                    for (int co = 0; co < CO_B; ++co) {
+#pragma unroll
+                        for (int ci = 0; ci < CI; ++ci) acc[co][ci] = fmaf(gv[co], xv[ci], acc[co][ci]);
+                    }
+                    if (warp == 4) {
+#pragma unroll
+                        for (int co = 0; co < CO_B; ++co) accb[co] += gv[co];
+                    }
                 }
-            }
+        }
         __syncthreads();                                                  // buffer free for the copies of strip u + 2
     }
+    if constexpr (kRowWarps) {
 #pragma unroll
-    for (int co = 0; co < CO_B; ++co) {
+        for (int co = 0; co < CO_B; ++co) {
 #pragma unroll
-        for (int ci = 0; ci < CI; ++ci) {
-            const float v = warp_sum(acc[co][ci]);
-            if (lane == 0 && co0 + co < a.Co)
-                atomicAdd(a.gw + ((long long)(co0 + co) * CI + ci) * 9 + kh * 3 + kw, v);
+            for (int t = 0; t < 9; ++t) {
+                const float v = warp_sum(acc[co][t]);
+                if (lane == 0 && co0 + co < a.Co) atomicAdd(a.gw + (long long)(co0 + co) * 9 + t, v);
+            }
+            if (a.gbias) {
+                const float v = warp_sum(accb[co]);
+                if (lane == 0 && co0 + co < a.Co) atomicAdd(a.gbias + co0 + co, v);
+            }
         }
-        if (warp == 4 && a.gbias) {
-            const float v = warp_sum(accb[co]);
-            if (lane == 0 && co0 + co < a.Co) atomicAdd(a.gbias + co0 + co, v);
+    } else {
+#pragma unroll
+        for (int co = 0; co < CO_B; ++co) {
+#pragma unroll
+            for (int ci = 0; ci < CI; ++ci) {
+                const float v = warp_sum(acc[co][ci]);
+                if (lane == 0 && co0 + co < a.Co)
+                    atomicAdd(a.gw + ((long long)(co0 + co) * CI + ci) * 9 + kh * 3 + kw, v);
+            }
+            if (warp == 4 && a.gbias) {
+                const float v = warp_sum(accb[co]);
+                if (lane == 0 && co0 + co < a.Co) atomicAdd(a.gbias + co0 + co, v);
+            }
         }
     }
 }
@@ -711,6 +746,9 @@ static int wgrad2d_async_launch(Wgrad2dArgs a, cudaStream_t st) {
     if (a.L1 == 64 && R == 8) {                                           // the benchmark geometry: compile-time strides
         if (ensure_dynamic_smem<conv2d_wgrad_async_kernel<CI, CO_B, SPARSE, 64, 8>>(100 * 1024) != NFK_OK) return NFK_ECUDA;
         conv2d_wgrad_async_kernel<CI, CO_B, SPARSE, 64, 8><<<grid, 288, bytes(R), st>>>(a);
+    } else if (a.L1 == 64 && R == 16) {                                   // (one input channel)
+        if (ensure_dynamic_smem<conv2d_wgrad_async_kernel<CI, CO_B, SPARSE, 64, 16>>(100 * 1024) != NFK_OK) return NFK_ECUDA;
+        conv2d_wgrad_async_kernel<CI, CO_B, SPARSE, 64, 16><<<grid, 288, bytes(R), st>>>(a);
     } else if (a.L1 == 32 && R == 16) {
         if (ensure_dynamic_smem<conv2d_wgrad_async_kernel<CI, CO_B, SPARSE, 32, 16>>(100 * 1024) != NFK_OK) return NFK_ECUDA;
         conv2d_wgrad_async_kernel<CI, CO_B, SPARSE, 32, 16><<<grid, 288, bytes(R), st>>>(a);
