@@ -157,6 +157,52 @@ extern "C" int nfk_rqs_inv(const float* x, const float* out, const uint8_t* mask
                            float* y, float* log_out, int64_t B, int64_t V, void* stream) {
     return rqs_apply<1>(x, out, mask, parity, frozen_mode, prm, log_in, y, log_out, B, V, NFK_STREAM(stream));
 }
+// Spline VJP with TWO adjacent sites per thread.  On a checkerboard exactly one site of such a pair is
+// active: one thread per site leaves every other lane of a warp idle through the (long) spline adjoint, while
+// one thread per pair keeps all lanes busy and writes each gradient channel as one 8-byte store (value, 0).
+struct PairStore {
+    float2* base;        // &gout[b][0][s0] viewed as pairs
+    int64_t stride2;     // V / 2
+    int slot;            // which site of the pair is active
+    __device__ __forceinline__ void operator()(int c, float v) const {
+        base[c * stride2] = slot == 0 ? make_float2(v, 0.f) : make_float2(0.f, v);
+    }
+};
+
+template <int K>
+__global__ void __launch_bounds__(256) rqs_bwd_pair_kernel(RqsBwdOp<K> op, int64_t n_pairs, int64_t half_v) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_pairs) return;
+    const int64_t b = idx / half_v, s0 = 2 * (idx - b * half_v);
+    const bool a0 = site_active(op.mask, s0, op.active_val), a1 = site_active(op.mask, s0 + 1, op.active_val);
+    if (a0 == a1) {                          // not a checkerboard pair: the two sites one after the other
+        op(b, s0);
+        op(b, s0 + 1);
+        return;
+    }
+    const int slot = a0 ? 0 : 1;
+    const int64_t i0 = b * op.V + s0;
+    const float2 g = *reinterpret_cast<const float2*>(op.gy + i0);
+    const int64_t o = (int64_t)(3 * K - 2) * b * op.V + s0;
+    const ChanLoad ld{op.out + o + slot, op.V};
+    const PairStore st{reinterpret_cast<float2*>(op.gout + o), half_v, slot};
+    const float gl = op.glog ? __ldg(op.glog + b) : 0.f;
+    const float ga = rqs_site_backward<K>(ld, op.cfg, __ldg(op.x + i0 + slot), slot == 0 ? g.x : g.y, gl, st);
+    const float gf = op.frozen_copy ? (slot == 0 ? g.y : g.x) : 0.f;
+    *reinterpret_cast<float2*>(op.gx + i0) = slot == 0 ? make_float2(ga, gf) : make_float2(gf, ga);
+}
+
+template <int K>
+static int launch_rqs_bwd(const RqsBwdOp<K>& op, int64_t B, int64_t V, cudaStream_t st) {
+    const bool pairs = V % 2 == 0 && V >= 64 &&
+                       (((uintptr_t)op.gy | (uintptr_t)op.gx | (uintptr_t)op.gout) % 8 == 0);
+    if (!pairs) return launch_sites(op, B, V, nullptr, nullptr, st);
+    const int64_t n_pairs = B * (V / 2);
+    if (n_pairs <= 0) return NFK_OK;
+    rqs_bwd_pair_kernel<K><<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>(op, n_pairs, V / 2);
+    return check_launch();
+}
+
 extern "C" int nfk_rqs_bwd(const float* x, const float* out, const uint8_t* mask, int parity,
                            int frozen_mode, nfk_rqs_params prm, const float* gy, const float* glog,
                            float* gx, float* gout, int64_t B, int64_t V, void* stream) {
@@ -165,7 +211,7 @@ extern "C" int nfk_rqs_bwd(const float* x, const float* out, const uint8_t* mask
     if (!rqs_cfg(prm, cfg)) return NFK_EINVAL;
     const int av = parity == 0 ? 1 : 0;
     switch (prm.n_knots) {
-#define X(KK) case KK: return launch_sites(RqsBwdOp<KK>{x, out, mask, av, frozen_mode, cfg, gy, glog, gx, gout, V}, B, V, nullptr, nullptr, NFK_STREAM(stream));
+#define X(KK) case KK: return launch_rqs_bwd(RqsBwdOp<KK>{x, out, mask, av, frozen_mode, cfg, gy, glog, gx, gout, V}, B, V, NFK_STREAM(stream));
         NFK_FOR_EACH_K(X)
 #undef X
         default: return NFK_EUNSUPPORTED;
