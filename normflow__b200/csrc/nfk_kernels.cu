@@ -132,6 +132,19 @@ static bool rqs_cfg(const nfk_rqs_params& p, RqsCfg& c) {
 #define NFK_FOR_EACH_K(X) \
     X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(14) X(16) X(20) X(24) X(32)
 
+// Two adjacent sites per thread: on a checkerboard one of them runs the spline and the other is a copy, so no
+// lane of a warp idles through the long branch (with one thread per site every other lane does).
+template <class Op>
+struct PairSites {
+    Op op;
+    NFK_HD float operator()(int64_t b, int64_t p) const { return op(b, 2 * p) + op(b, 2 * p + 1); }
+};
+template <class Op>
+static int launch_site_pairs(const Op& op, int64_t B, int64_t V, const float* log_in, float* log_out, cudaStream_t st) {
+    if (V % 2 == 0 && V >= 128) return launch_sites(PairSites<Op>{op}, B, V / 2, log_in, log_out, st);
+    return launch_sites(op, B, V, log_in, log_out, st);
+}
+
 template <int MODE>
 static int rqs_apply(const float* x, const float* out, const uint8_t* mask, int parity, int frozen_mode,
                      nfk_rqs_params prm, const float* log_in, float* y, float* log_out,
@@ -141,7 +154,7 @@ static int rqs_apply(const float* x, const float* out, const uint8_t* mask, int 
     if (!rqs_cfg(prm, cfg)) return NFK_EINVAL;
     const int av = parity == 0 ? 1 : 0;
     switch (prm.n_knots) {
-#define X(KK) case KK: return launch_sites(RqsOp<KK, MODE>{x, out, mask, av, frozen_mode, cfg, y, V}, B, V, log_in, log_out, st);
+#define X(KK) case KK: return launch_site_pairs(RqsOp<KK, MODE>{x, out, mask, av, frozen_mode, cfg, y, V}, B, V, log_in, log_out, st);
         NFK_FOR_EACH_K(X)
 #undef X
         default: return NFK_EUNSUPPORTED;
