@@ -282,3 +282,64 @@ def test_fused2d_supported_mirrors_kernel_dispatch():
     assert ok(64, 64, 12) and not ok(6, 10, 12)
     assert not ok(64, 64, 7) and not ok(64, 64, -1)
     assert not ok(3, 3, None)
+
+
+# ------------------------------------------------------------------ blocked MCMC host logic (CPU)
+def test_blocked_mcmc_host_logic_replays_reference_chain():
+    """BlockedMCMCSampler's control flow (sweeps, restore on reject, reuse of the accepted proposal, chain state
+    across calls) with the numerics supplied by the oracle on the host: replaying the reference's recorded block
+    proposals and np.random stream must reproduce its accept flags bit for bit and its chain to rounding."""
+    from oracle import nf_oracle as O
+    from test_oracle_rank4 import blocked_setup
+    from normflow__b200.mcmc import BlockedMCMCSampler
+    from normflow__b200.prior.prior import BlockUpdater
+
+    g = load_golden("blocked_mcmc")
+    evaluate, inverse = blocked_setup(g)
+    lens, flat = g["draw_lens"], g["draws"]
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    draws = iter([torch.from_numpy(flat[offs[i]:offs[i + 1]].reshape(1, -1).copy()) for i in range(len(lens))])
+    lat = tuple(int(v) for v in g["lat"])
+
+    class Chopped:
+        def sample(self, batch_size=1):
+            return next(draws)
+
+    class HostPrior:
+        shape, nvar = lat, int(np.prod(lat))
+
+        def sample(self, batch_size=1):
+            return torch.from_numpy(g["x0"].copy())
+
+        def setup_blockupdater(self, block_len):
+            self.blockupdater = BlockUpdater(Chopped(), block_len)
+
+        def log_prob(self, x):
+            return torch.from_numpy(O.normal_log_prob(x.double().numpy()))
+
+    class HostNet:
+        def __call__(self, x, log0=0):
+            self.last = evaluate(x.double().numpy())
+            y, logq, _ = self.last
+            return torch.from_numpy(y), torch.from_numpy(O.normal_log_prob(x.double().numpy()) - logq)
+
+        def backward(self, y, log0=0):
+            return torch.from_numpy(inverse(y.double().numpy())), 0
+
+    class HostModel:
+        prior, net_ = HostPrior(), HostNet()
+
+        def action(self, y):
+            return torch.from_numpy(-self.net_.last[2])
+
+    sampler = BlockedMCMCSampler(HostModel())
+    np.random.seed(9)
+    for call in range(3):
+        B, nb = (int(v) for v in g[f"call{call}_shape"])
+        cfgs, logq, logp = sampler.sample__(batch_size=B, n_blocks=nb, bookkeeping=True)
+        assert np.array_equal(sampler.history.accept_seq[-1], g[f"call{call}_accept_seq"])
+        np.testing.assert_allclose(cfgs.numpy(), g[f"call{call}_cfgs"], rtol=2e-6, atol=2e-6)
+        np.testing.assert_allclose(logq.numpy(), g[f"call{call}_logq"], rtol=2e-6, atol=2e-5)
+        np.testing.assert_allclose(logp.numpy(), g[f"call{call}_logp"], rtol=2e-6, atol=2e-5)
+        assert abs(sampler.history.accept_rate[-1] - float(g[f"call{call}_accept_rate"])) < 1e-12
+    assert next(draws, None) is None
