@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(256) site_kernel_vec(Op op, int64_t V, int chu
     const int64_t s0 = chunk * chunk_len;
     const int64_t s1 = s0 + chunk_len < V ? s0 + chunk_len : V;
     float acc = 0.f;
+#pragma unroll 4
     for (int64_t s = s0 + (int64_t)threadIdx.x * VEC; s < s1; s += (int64_t)blockDim.x * VEC) {
         const int64_t left = s1 - s;
         acc += op(b, s, left < VEC ? (int)left : VEC);

@@ -72,9 +72,32 @@ extern "C" int nfk_prior_normal_sample_dev(float* x, float* logr, int64_t B, int
     advance_offset_kernel<<<1, 1, 0, NFK_STREAM(stream)>>>(state);
     return check_launch();
 }
+// Standard normal, mid-sized samples: ONE WARP per sample (8 loads of 16 bytes in flight per lane, a shuffle
+// reduction, no block barrier) -- a CTA per sample spends as long in its two barriers as in its 16 KB of loads.
+__global__ void __launch_bounds__(256) prior_logprob_warp_kernel(const float* __restrict__ x, float* __restrict__ logr,
+                                                                int64_t B, int64_t V) {
+    const int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const int lane = threadIdx.x & 31;
+    const float4* p = reinterpret_cast<const float4*>(x + b * V);
+    const int nq = (int)(V >> 2);
+    float acc = 0.f;
+#pragma unroll 8
+    for (int q = lane; q < nq; q += 32) {
+        const float4 v = __ldg(p + q);
+        acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) logr[b] = -0.5f * acc - (float)V * kLogSqrt2Pi;
+}
+
 extern "C" int nfk_prior_normal_logprob(const float* x, float* logr, int64_t B, int64_t V,
                                         const float* loc, const float* scale, void* stream) {
     if (!x || !logr) return NFK_EINVAL;
+    if (!loc && !scale && B >= 1024 && V % 4 == 0 && V >= 512 && V <= 32768 && ((uintptr_t)x % 16) == 0) {
+        prior_logprob_warp_kernel<<<(unsigned)((B + 7) / 8), 256, 0, NFK_STREAM(stream)>>>(x, logr, B, V);
+        return check_launch();
+    }
     return launch_sites_vec<PriorLogProbOp4, 4>(PriorLogProbOp4{x, loc, scale, V}, B, V, nullptr, logr, NFK_STREAM(stream));
 }
 
@@ -365,6 +388,7 @@ __global__ void __launch_bounds__(256) phi4_2d_kernel(const float* phi, int L0, 
     const int nq = L1 >> 2;                                   // column quads per row
     const float gs = BWD ? __ldg(gS + b) : 0.f;
     float acc = 0.f;
+#pragma unroll 4
     for (int it = threadIdx.x; it < L0 * nq; it += blockDim.x) {
         const int r = it / nq, c0 = (it - r * nq) * 4;
         const int ru = r == 0 ? L0 - 1 : r - 1;
@@ -393,6 +417,30 @@ __global__ void __launch_bounds__(256) phi4_2d_kernel(const float* phi, int L0, 
         if (threadIdx.x == 0) out[b] = acc;
     }
 }
+// forward action, one warp per sample (same arithmetic as phi4_2d_kernel<false>; no block barrier)
+__global__ void __launch_bounds__(256) phi4_2d_warp_kernel(const float* phi, int L0, int L1, float w0, float w2, float w4,
+                                                           float* out, int64_t B) {
+    const int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const int lane = threadIdx.x & 31;
+    const float* p = phi + b * (int64_t)L0 * L1;
+    const int nq = L1 >> 2;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int it = lane; it < L0 * nq; it += 32) {
+        const int r = it / nq, c0 = (it - r * nq) * 4;
+        const int ru = r == 0 ? L0 - 1 : r - 1;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p + r * L1 + c0));
+        const float4 u = __ldg(reinterpret_cast<const float4*>(p + ru * L1 + c0));
+        const float lf = __ldg(p + r * L1 + (c0 == 0 ? L1 - 1 : c0 - 1));
+        const float q0 = v.x * v.x, q1 = v.y * v.y, q2 = v.z * v.z, q3 = v.w * v.w;
+        acc += q0 * (w2 + w4 * q0) + q1 * (w2 + w4 * q1) + q2 * (w2 + w4 * q2) + q3 * (w2 + w4 * q3);
+        acc -= w0 * (v.x * (u.x + lf) + v.y * (u.y + v.x) + v.z * (u.z + v.y) + v.w * (u.w + v.z));
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[b] = acc;
+}
+
 static bool phi4_2d_ok(const nfk_lattice& lat, const float* phi, const float* out) {
     return lat.ndim == 2 && lat.shape[1] % 4 == 0 && lat.shape[1] >= 4 && lat.shape[0] >= 2 &&
            ((uintptr_t)phi % 16) == 0 && ((uintptr_t)out % 16) == 0;
@@ -402,6 +450,11 @@ extern "C" int nfk_phi4_action_fwd(const float* phi, nfk_lattice lat, float w0, 
                                    float* S, int64_t B, void* stream) {
     if (!phi || !S || !lat_ok(lat)) return NFK_EINVAL;
     const int64_t V = lat_volume(lat);
+    if (B >= 1024 && phi4_2d_ok(lat, phi, phi) && V >= 512 && V <= 32768) {
+        phi4_2d_warp_kernel<<<(unsigned)((B + 7) / 8), 256, 0, NFK_STREAM(stream)>>>(phi, lat.shape[0], lat.shape[1],
+                                                                                      w0, w2, w4, S, B);
+        return check_launch();
+    }
     if (B > 0 && phi4_2d_ok(lat, phi, phi)) {
         const int items = lat.shape[0] * (lat.shape[1] / 4);
         const int th = items >= 256 ? 256 : (items + 31) / 32 * 32;
