@@ -54,6 +54,49 @@ class Posterior:
 
     def __init__(self, model):
         self._model = model
+        # Opt-in (launch-bound lattices): replay prior draw + flow + action of one batch size as ONE captured
+        # CUDA graph.  The returned tensors are the graph's output buffers, overwritten by the next call with the
+        # same batch size -- clone what must outlive it.
+        self.cuda_graph = False
+        self._graphs = {}
+
+    def _graph_key(self, batch_size):
+        params = tuple(p.data_ptr() for p in self._model.net_.parameters())
+        return (int(batch_size), params, id(self._model.prior), id(self._model.action))
+
+    def _sample_graph(self, batch_size):
+        """(y, logq, logp) of a fresh batch through a CUDA graph captured on first use of this batch size (and
+        re-captured if the parameters have been re-allocated).  Parameter VALUES are read at replay, so training
+        between calls is seen; the prior's generator state lives on the device and advances inside the graph."""
+        key = self._graph_key(batch_size)
+        entry = self._graphs.get(batch_size)
+        if entry is None or entry[0] != key:
+            prior = self._model.prior
+            prior.use_device_state()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):                   # first-use initialisation outside the capture
+                    self._sample_eager(batch_size)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self._sample_eager(batch_size)
+            entry = (key, graph, out)
+            self._graphs[batch_size] = entry
+        entry[1].replay()
+        return entry[2]
+
+    def _sample_eager(self, batch_size):
+        x, logr = self._model.prior.sample_(batch_size)
+        y, logJ = self._model.net_(x)
+        return y, logr - logJ, -self._model.action(y)
+
+    def _graph_ok(self, kwargs):
+        if not self.cuda_graph or kwargs.get('preprocess_func') is not None:
+            return False
+        params = list(self._model.net_.parameters())
+        return bool(params) and all(p.is_cuda for p in params) and hasattr(self._model.prior, 'use_device_state')
 
     @torch.no_grad()
     def sample(self, batch_size=1, **kwargs):
@@ -62,6 +105,8 @@ class Posterior:
     @torch.no_grad()
     def sample_(self, batch_size=1, preprocess_func=None):
         """(y, log q(y)); `preprocess_func(x, logr)` may edit the prior draw first."""
+        if self._graph_ok(dict(preprocess_func=preprocess_func)):
+            return self._sample_graph(batch_size)[:2]
         x, logr = self._model.prior.sample_(batch_size)
         if preprocess_func is not None:
             x, logr = preprocess_func(x, logr)
@@ -71,6 +116,8 @@ class Posterior:
     @torch.no_grad()
     def sample__(self, batch_size=1, **kwargs):
         """(y, log q(y), log p(y) + log z): the benchmark's "flow fwd + logJ + action"."""
+        if self._graph_ok(kwargs):
+            return self._sample_graph(batch_size)
         y, logq = self.sample_(batch_size=batch_size, **kwargs)
         return y, logq, -self._model.action(y)
 
