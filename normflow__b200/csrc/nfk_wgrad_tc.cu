@@ -29,7 +29,7 @@
 //     CTA per SM.
 //
 // Needs: Ci == 8, Co <= 32, 16-byte aligned tensors, L1 % 8 == 0 (SPARSE: L1 % 16 == 0 and even L0) and at
-// most 128 (active) columns per row.  Otherwise NFK_EUNSUPPORTED (the caller falls back to the
+// most 64 (active) columns per row.  Otherwise NFK_EUNSUPPORTED (the caller falls back to the
 // CUDA-core kernels).
 #include <stdlib.h>
 
