@@ -1,8 +1,6 @@
 """Controlled couplings (reference src/nn/scalar/cntr_couplings_.py): the first atomic step is
 conditioned on an external `control` field instead of the frozen partition of the data."""
 
-import torch
-
 from ... import _C
 from .couplings_ import Coupling_, ShiftCoupling_, AffineCoupling_, RQSplineCoupling_, MultiRQSplineCoupling_
 

@@ -9,7 +9,6 @@ split / atomic_* / cat dataflow for subclasses that only define `atomic_forward`
 `atomic_backward`.
 """
 
-import numpy as np
 import os
 
 import torch

@@ -9,10 +9,9 @@ wraps indices instead of materialising a padded copy.
 
 import copy
 
-import numpy as np
 import torch
 
-from ... import _ops, _C
+from ... import _ops
 from ...lib.spline import RQSpline
 
 

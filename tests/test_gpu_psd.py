@@ -12,7 +12,7 @@ from oracle import nf_oracle as O
 from test_oracle_psd import CASES, psd_params
 
 import normflow__b200 as nf  # noqa: F401  (default device / dtype)
-from normflow__b200 import Model, _ops, _C
+from normflow__b200 import Model, _ops
 from normflow__b200.action import ScalarPhi4Action
 from normflow__b200.mask import EvenOddMask
 from normflow__b200.nn import (ModuleList_, ConvAct, AffineCoupling_, DistConvertor_, Identity_,

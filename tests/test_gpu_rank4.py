@@ -7,7 +7,6 @@ import pytest
 import torch
 
 from conftest import load_golden
-from oracle import nf_oracle as O
 from test_oracle_rank4 import MULTI, CNTR, blocked_setup
 
 import normflow__b200 as nf  # noqa: F401
