@@ -418,17 +418,19 @@ __global__ void __launch_bounds__(256) phi4_2d_kernel(const float* phi, int L0, 
     }
 }
 // forward action, one warp per sample (same arithmetic as phi4_2d_kernel<false>; no block barrier)
+// SH >= 0: the number of column quads per row is 2^SH (row / column from shifts instead of a division)
+template <int SH>
 __global__ void __launch_bounds__(256) phi4_2d_warp_kernel(const float* phi, int L0, int L1, float w0, float w2, float w4,
                                                            float* out, int64_t B) {
     const int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (b >= B) return;
     const int lane = threadIdx.x & 31;
     const float* p = phi + b * (int64_t)L0 * L1;
-    const int nq = L1 >> 2;
+    const int nq = SH >= 0 ? (1 << SH) : (L1 >> 2);
     float acc = 0.f;
 #pragma unroll 4
     for (int it = lane; it < L0 * nq; it += 32) {
-        const int r = it / nq, c0 = (it - r * nq) * 4;
+        const int r = SH >= 0 ? (it >> SH) : it / nq, c0 = (it - r * nq) * 4;
         const int ru = r == 0 ? L0 - 1 : r - 1;
         const float4 v = __ldg(reinterpret_cast<const float4*>(p + r * L1 + c0));
         const float4 u = __ldg(reinterpret_cast<const float4*>(p + ru * L1 + c0));
@@ -451,8 +453,13 @@ extern "C" int nfk_phi4_action_fwd(const float* phi, nfk_lattice lat, float w0, 
     if (!phi || !S || !lat_ok(lat)) return NFK_EINVAL;
     const int64_t V = lat_volume(lat);
     if (B >= 1024 && phi4_2d_ok(lat, phi, phi) && V >= 512 && V <= 32768) {
-        phi4_2d_warp_kernel<<<(unsigned)((B + 7) / 8), 256, 0, NFK_STREAM(stream)>>>(phi, lat.shape[0], lat.shape[1],
-                                                                                      w0, w2, w4, S, B);
+        const unsigned blocks = (unsigned)((B + 7) / 8);
+        if (lat.shape[1] == 64)
+            phi4_2d_warp_kernel<4><<<blocks, 256, 0, NFK_STREAM(stream)>>>(phi, lat.shape[0], 64, w0, w2, w4, S, B);
+        else if (lat.shape[1] == 32)
+            phi4_2d_warp_kernel<3><<<blocks, 256, 0, NFK_STREAM(stream)>>>(phi, lat.shape[0], 32, w0, w2, w4, S, B);
+        else
+            phi4_2d_warp_kernel<-1><<<blocks, 256, 0, NFK_STREAM(stream)>>>(phi, lat.shape[0], lat.shape[1], w0, w2, w4, S, B);
         return check_launch();
     }
     if (B > 0 && phi4_2d_ok(lat, phi, phi)) {
