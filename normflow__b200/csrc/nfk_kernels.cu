@@ -443,6 +443,33 @@ __global__ void __launch_bounds__(256) phi4_2d_warp_kernel(const float* phi, int
     if (lane == 0) out[b] = acc;
 }
 
+// forward action, one warp per sample, every site loaded ONCE: a lane owns one column quad over a contiguous
+// range of rows and walks down it (the row above is the previous iteration's registers, the left neighbour one
+// shuffle).  Needs 32 % (L1 / 4) == 0 and L0 divisible by the 32 / (L1 / 4) row ranges of a warp.
+__global__ void __launch_bounds__(256) phi4_2d_colwalk_kernel(const float* phi, int L0, int L1, float w0, float w2,
+                                                              float w4, float* out, int64_t B) {
+    const int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= B) return;                                      // (whole warps leave together)
+    const int lane = threadIdx.x & 31;
+    const int nq = L1 >> 2, g = lane / nq, q = lane - g * nq;
+    const int rows_per = L0 / (32 / nq), r_begin = g * rows_per;
+    const int src_left = g * nq + (q == 0 ? nq - 1 : q - 1);
+    const float* col = phi + b * (int64_t)L0 * L1 + 4 * q;
+    float4 up = __ldg(reinterpret_cast<const float4*>(col + (int64_t)((r_begin == 0 ? L0 : r_begin) - 1) * L1));
+    float acc = 0.f;
+#pragma unroll 8
+    for (int i = 0; i < rows_per; ++i) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(col + (int64_t)(r_begin + i) * L1));
+        const float lf = __shfl_sync(0xffffffffu, v.w, src_left);
+        const float q0 = v.x * v.x, q1 = v.y * v.y, q2 = v.z * v.z, q3 = v.w * v.w;
+        acc += q0 * (w2 + w4 * q0) + q1 * (w2 + w4 * q1) + q2 * (w2 + w4 * q2) + q3 * (w2 + w4 * q3);
+        acc -= w0 * (v.x * (up.x + lf) + v.y * (up.y + v.x) + v.z * (up.z + v.y) + v.w * (up.w + v.z));
+        up = v;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[b] = acc;
+}
+
 static bool phi4_2d_ok(const nfk_lattice& lat, const float* phi, const float* out) {
     return lat.ndim == 2 && lat.shape[1] % 4 == 0 && lat.shape[1] >= 4 && lat.shape[0] >= 2 &&
            ((uintptr_t)phi % 16) == 0 && ((uintptr_t)out % 16) == 0;
@@ -454,6 +481,11 @@ extern "C" int nfk_phi4_action_fwd(const float* phi, nfk_lattice lat, float w0, 
     const int64_t V = lat_volume(lat);
     if (B >= 1024 && phi4_2d_ok(lat, phi, phi) && V >= 512 && V <= 32768) {
         const unsigned blocks = (unsigned)((B + 7) / 8);
+        const int nq = lat.shape[1] / 4;
+        if (nq <= 32 && 32 % nq == 0 && lat.shape[0] % (32 / nq) == 0) {
+            phi4_2d_colwalk_kernel<<<blocks, 256, 0, NFK_STREAM(stream)>>>(phi, lat.shape[0], lat.shape[1], w0, w2, w4, S, B);
+            return check_launch();
+        }
         if (lat.shape[1] == 64)
             phi4_2d_warp_kernel<4><<<blocks, 256, 0, NFK_STREAM(stream)>>>(phi, lat.shape[0], 64, w0, w2, w4, S, B);
         else if (lat.shape[1] == 32)
