@@ -6,7 +6,7 @@ conditioner, K=10 knots, batch 16384 per GPU), on N GPUs of one node.
     python bench.py --gpus 1 --steps 10 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference ...      # the CPU arm: the oracle port on the host cores
+    python bench.py --impl reference ...      # the CPU arm: the unmodified reference on the host cores
 
 One "step" = one pass of the hot path over one synthetic batch: NormalPrior draw with
 log-density -> four checkerboard RQ-spline coupling steps (conditioner + spline +
@@ -15,22 +15,31 @@ log|det J|) -> phi^4 action, i.e. `model.posterior.sample__(B)`.  Ranks are inde
 divided by the slowest rank's device time.
 
 The JSON line carries, besides the base contract:
-  roofline     : the dominant HBM-bound kernel (the RQ-spline apply), algorithmic bytes
-                 ((8 + 4 P) B per site and step = 120 B at P = 28) over its mean
-                 launch duration measured with CUDA events inside the timed steps, against
-                 the measured copy bandwidth of MEASURED_PEAKS.json
-  cpu_baseline : the reference's operator sequence on torch CPU (oracle/torch_port.py, float64, all host
-                 threads) timed on a bounded sample
+  roofline     : the dominant kernel (the fused coupling step), algorithmic bytes (SURVEY 8d:
+                 (8 + 4 P) B per site and step = 120 B at P = 28) over its mean launch duration
+                 measured with CUDA events inside the timed steps, against the measured copy
+                 bandwidth of MEASURED_PEAKS.json
+  cpu_baseline : the UNMODIFIED reference (staged into oracle/_ref by oracle/stage_ref.py, float64,
+                 all host threads) timed on a bounded sample; the ATen port (oracle/torch_port.py)
+                 only if the staged copy is missing
   e2e          : the same metric through the public API with HOST buffers: the prior draw
                  comes from pinned host memory (H2D inside the timed region; the copy of step
                  i+1 runs on a second stream while step i is evaluated) and log q, log p are
-                 read back (D2H) with a stream sync every step
+                 read back (D2H) with a stream sync every step; `e2e.with_fields` also brings the
+                 transformed fields y (268 MB per step) back to pinned host memory
+  train_step   : `model.fit.step()` of the same model at the same batch per GPU -- prior draw, flow,
+                 action, backward, ONE flat-gradient ncclAllReduce (avg), fused AdamW -- samples/s over
+                 all ranks, fraction of the 1 440 V byte model, the collective's measured time
+  mcmc         : `model.mcmc.sample(B)` (flow + device Metropolis scan + row gather)
+  configs      : the other named workloads of BASELINE.json (configs[0], [1], [3], [4]): sampling and
+                 training samples/s, fraction of the SURVEY 8d HBM bound, reference CPU beside them
 """
 
 import argparse
 import json
 import math
 import os
+import subprocess
 import sys
 import threading
 import time
@@ -41,11 +50,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-LATTICE = (64, 64)
-KNOTS = 10
-HIDDEN = [8, 8]
+import bench_configs as BC   # noqa: E402
+
+CFG = BC.CONFIGS[3]
+LATTICE = CFG['lattice']
+KNOTS = BC.KNOTS
+HIDDEN = BC.HIDDEN
 N_STEPS_FLOW = 4
-ACTION = dict(kappa=0.67, m_sq=-4 * 0.67, lambd=0.5)
+ACTION = BC.ACTION
 METRIC = "samples/sec (flow fwd+logJ+action) 64^2 phi^4"
 WORKLOAD = ("configs[2]: 2-D scalar phi^4 64x64, RQ-spline coupling x4 (K=10, xlim=ylim=(-5,5), linear "
             "extrapolation), ConvAct(1->8->8->28, k=3, tanh, circular, no bias) conditioner")
@@ -61,6 +73,8 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=256, help="samples per step of the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip train_step / mcmc / configs")
+    ap.add_argument("--train-batch", type=int, default=None, help="samples per GPU of the training step (default: --batch)")
     return ap.parse_args()
 
 
@@ -96,17 +110,50 @@ def time_cpu_port(batch, steps, warmup):
     return batch * steps / dt, dt, threads
 
 
+def reference_jobs(jobs, timeout=900):
+    """Run oracle/ref_runner.py jobs ([config, what, batch, steps, warmup], ...) in ONE child process with
+    the GPUs hidden (the reference makes CUDA its default device when it sees one) and return the parsed
+    JSON lines, or None when the staged reference is missing."""
+    if not os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "normflow_ref")):
+        return None
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run([sys.executable, "-m", "oracle.ref_runner", "--jobs", json.dumps(jobs)], cwd=ROOT, env=env,
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
+    except subprocess.TimeoutExpired:
+        return None
+    out = []
+    for ln in r.stdout.splitlines():
+        ln = ln.strip()
+        if ln.startswith("{"):
+            try:
+                out.append(json.loads(ln))
+            except ValueError:
+                pass
+    if len(out) != len(jobs):
+        sys.stderr.write(r.stderr[-2000:])
+        return None
+    return out
+
+
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path.  The reference is
-    pure Python on torch and cannot travel to the GPU box, so this times its restatement on the
-    same ATen operators (oracle/torch_port.py, float64, all host threads); each step is a bounded
-    sample of `--cpu-batch` samples of the same workload."""
+    """--impl reference: the reference's own CPU implementation of the path -- the UNMODIFIED package staged
+    into oracle/_ref (float64, its default; all host threads), `model.posterior.sample__` on a bounded sample
+    of `--cpu-batch` samples per step of the same workload.  Falls back to the ATen port of its operator
+    sequence (oracle/torch_port.py) only when the staged copy is absent."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    value, dt, cores = time_cpu_port(args.cpu_batch, args.steps, max(args.warmup, 1))
-    sample = (f"{args.cpu_batch} samples/step x {args.steps} steps of the same workload "
-              "(torch ATen float64 port of the reference's operator sequence)")
+    res = reference_jobs([[3, "sample", args.cpu_batch, args.steps, max(args.warmup, 1)]])
+    if res and "samples_per_s" in res[0]:
+        value, dt, cores, kind = res[0]["samples_per_s"], res[0]["seconds"], res[0]["threads"], "reference"
+        what = "the unmodified reference (oracle/_ref/normflow_ref, float64) model.posterior.sample__"
+    else:
+        value, dt, cores = time_cpu_port(args.cpu_batch, args.steps, max(args.warmup, 1))
+        kind, what = "port", "torch ATen float64 port of the reference's operator sequence"
+    sample = f"{args.cpu_batch} samples/step x {args.steps} steps of the same workload ({what})"
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "impl": "reference",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -114,7 +161,7 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_gpu": args.batch, "lattice": list(LATTICE),
                    "cpu_sample_per_step": args.cpu_batch},
-        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -174,19 +221,9 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------- GPU arm
-def build_model(torch):
-    from normflow__b200 import Model
-    from normflow__b200.action import ScalarPhi4Action
-    from normflow__b200.mask import EvenOddMask
-    from normflow__b200.nn import ModuleList_, ConvAct, RQSplineCoupling_
-    from normflow__b200.prior import NormalPrior
-    torch.manual_seed(0)
-    mask = EvenOddMask(shape=LATTICE)
-    nets = [ConvAct(1, 3 * KNOTS - 2, 3, conv_dim=2, hidden_sizes=HIDDEN, acts=('tanh', 'tanh', None), bias=False)
-            for _ in range(N_STEPS_FLOW)]
-    net_ = ModuleList_([RQSplineCoupling_(nets, mask=mask, xlim=(-5, 5), ylim=(-5, 5),
-                                          extrap=dict(left='linear', right='linear'))])
-    model = Model(prior=NormalPrior(shape=LATTICE), net_=net_, action=ScalarPhi4Action(**ACTION))
+def build_model(torch, config=3):
+    import normflow__b200
+    model = BC.build_model(normflow__b200, BC.CONFIGS[config])
     model.device_handler.to('cuda')
     return model
 
@@ -206,6 +243,140 @@ def ncu_traffic():
         with open(path) as fh:
             return json.load(fh).get("dram_bytes_per_launch")
     return None
+
+
+def _timed_loop(torch, dist, world, barrier, fn, steps, warmup):
+    """ms per call of fn(): `warmup` untimed calls, then `steps` calls between barrier + synchronize,
+    CUDA events on the launching stream, max over ranks."""
+    for _ in range(warmup):
+        fn()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    return ms
+
+
+def _prepare_training(torch, model, world, rank, batch):
+    """What Model.fit does before its epoch loop (normflow__b200/_normflowcore.py Fitter.__call__), without the
+    printing: data-parallel placement (flat gradient buffer, one all-reduce per step), fused AdamW, device-side
+    divergence guard -- so that `model.fit.step()` can be timed call by call."""
+    fit, handler = model.fit, model.device_handler
+    if world > 1 and handler.nranks != world:
+        handler.ddp_wrapper(rank, world, device=torch.device("cuda", torch.cuda.current_device()))
+    params = list(model.net_.parameters())
+    fit.loss_fn = fit.calc_kl_mean
+    fit.optimizer = torch.optim.AdamW(params, lr=1e-3, weight_decay=0.01, fused=True)
+    fit.scheduler = None
+    fit._guard = dict(found_inf=torch.zeros((), dtype=torch.float32, device=params[0].device),
+                      n_skipped=torch.zeros((), dtype=torch.float32, device=params[0].device))
+    fit.optimizer.found_inf = fit._guard['found_inf']
+    fit.train_batch_size = batch
+    return sum(p.numel() for p in params)
+
+
+def run_extras(args, torch, dist, model, world, rank, barrier, pk):
+    """train_step / mcmc at the headline configuration and the table of the other named workloads.
+    Every figure: all ranks run, device-timed, max over ranks; samples/s = all ranks' samples / that time."""
+    from normflow__b200 import _C
+    hbm = pk["hbm_gbs"] * 1e9
+    out = {}
+    B = args.batch
+
+    # ---- mcmc.sample at the headline configuration ------------------------------------------------------
+    np.random.seed(7 + rank)
+    ms = _timed_loop(torch, dist, world, barrier, lambda: model.mcmc.sample(B), steps=min(args.steps, 5), warmup=2)
+    out["mcmc"] = {"what": "model.mcmc.sample(B): flow + device Metropolis scan + row gather (independent chain per rank)",
+                   "config": BC.CONFIGS[3]['name'], "batch_per_gpu": B, "samples_per_s": world * B / (ms * 1e-3),
+                   "ms_per_step": ms, "accept_rate_last": float(model.mcmc.history.accept_rate[-1])}
+    model.mcmc._reset_chain()
+    torch.cuda.empty_cache()
+
+    # ---- the training step at the headline configuration (the north-star scaling target) ---------------
+    def train_entry(config, m, batch, steps, warmup):
+        cfg = BC.CONFIGS[config]
+        n_par = _prepare_training(torch, m, world, rank, batch)
+        handler = m.device_handler
+        timer = _C.KernelTimer()
+        orig_sync = handler.sync_gradients
+
+        def timed_sync():
+            if world == 1:
+                return orig_sync()
+            with timer.record("allreduce"):
+                orig_sync()
+        handler.sync_gradients = timed_sync
+        try:
+            ms_t = _timed_loop(torch, dist, world, barrier, m.fit.step, steps=steps, warmup=warmup)
+        finally:
+            handler.sync_gradients = orig_sync
+        coll = timer.summary().get("allreduce")
+        rate = world * batch / (ms_t * 1e-3)
+        bytes_s = BC.train_bytes_per_sample(cfg)
+        entry = {"what": "model.fit.step(): prior draw, flow, action, backward, flat-gradient all-reduce, fused AdamW",
+                 "config": cfg['name'], "batch_per_gpu": batch, "samples_per_s": rate, "ms_per_step": ms_t,
+                 "model_bytes_per_sample": bytes_s, "hbm_model_frac": bytes_s * rate / world / hbm,
+                 "collective": None if world == 1 else {
+                     "name": "ncclAllReduce (avg) of the flat float32 gradient buffer, on the compute stream",
+                     "bytes": 4 * n_par, "avg_us": None if coll is None else 1e3 * coll["avg_ms"],
+                     "share_of_step": None if coll is None else coll["avg_ms"] / ms_t}}
+        return entry
+
+    tb = args.train_batch or B
+    out["train_step"] = train_entry(3, model, tb, steps=min(args.steps, 4), warmup=2)
+    model.fit.optimizer = None
+    torch.cuda.empty_cache()
+
+    # ---- the other named workloads ------------------------------------------------------------------------
+    table = {}
+    plan = {   # config: (sampling batch per GPU, steps, training batch per GPU, steps)
+        1: (BC.CONFIGS[1]['batch'], 50, BC.CONFIGS[1]['batch'], 50),
+        2: (BC.CONFIGS[2]['batch'], 50, BC.CONFIGS[2]['batch'], 20),
+        4: (max(BC.CONFIGS[4]['batch'] // world, 1), 2, 512, 2),        # 4096 global (SURVEY 8d); training at the 8-GPU share
+        5: (BC.CONFIGS[5]['batch'], 2, 128, 2),                          # 2048 per GPU; training batch bounded by memory
+    }
+    for config, (sb, ss, tbatch, ts) in plan.items():
+        cfg = BC.CONFIGS[config]
+        m = build_model(torch, config)
+        torch.manual_seed(4321 + rank)
+        ms_s = _timed_loop(torch, dist, world, barrier, lambda: m.posterior.sample__(sb), steps=ss, warmup=2 if config < 4 else 1)
+        rate = world * sb / (ms_s * 1e-3)
+        fb = BC.fwd_bytes_per_sample(cfg)
+        entry = {"config": cfg['name'], "lattice": list(cfg['lattice']),
+                 "sample": {"batch_per_gpu": sb, "samples_per_s": rate, "ms_per_step": ms_s,
+                            "model_bytes_per_sample": fb, "hbm_model_frac": fb * rate / world / hbm}}
+        torch.cuda.empty_cache()
+        entry["train"] = {k: v for k, v in train_entry(config, m, tbatch, steps=ts, warmup=2 if config < 4 else 1).items()
+                          if k not in ("what", "config")}
+        table[str(config)] = entry
+        del m
+        torch.cuda.empty_cache()
+    out["configs"] = table
+    return out
+
+
+def attach_cpu(extras, results):
+    """Put the reference's CPU figures (oracle/ref_runner.py jobs) beside the GPU ones."""
+    for r in results:
+        if "samples_per_s" not in r:
+            continue
+        cpu = {"samples_per_s": r["samples_per_s"], "cores": r["threads"], "kind": "reference", "dtype": "f64",
+               "sample": f"{r['batch']} samples/step x {r['steps']} steps, {r['seconds']:.1f} s"}
+        c, what = int(r["config"]), r["what"]
+        if c == 3:
+            key = {"train": "train_step", "mcmc": "mcmc"}.get(what)
+            if key and key in extras:
+                extras[key]["cpu_reference"] = cpu
+        elif str(c) in extras.get("configs", {}):
+            extras["configs"][str(c)][what if what != "mcmc" else "mcmc"]["cpu_reference"] = cpu
 
 
 def run_b200(args):
@@ -311,7 +482,14 @@ def run_b200(args):
                     x_dev[buf][lo:hi].copy_(host_x[lo:hi], non_blocking=True)
                     ready[buf][c].record(copy_stream)
 
-        def e2e_run(n_steps):
+        host_y = None
+        d2h_stream = torch.cuda.Stream()
+        y_done = torch.cuda.Event()
+
+        def e2e_run(n_steps, with_fields=False):
+            """with_fields: the transformed fields y (B x V floats) also go back to pinned host memory, on a
+            third stream, overlapping the next step's kernels; the copy of step i is awaited before step i + 1
+            hands over its own fields (and at the end), so every copy lies inside the timed region."""
             main = torch.cuda.current_stream()
             for ev in consumed:
                 ev.record(main)
@@ -327,11 +505,21 @@ def run_b200(args):
                         yy, logJ = model.net_(x)
                         torch.sub(logr, logJ, out=res_dev[0, lo:hi])
                         torch.neg(model.action(yy), out=res_dev[1, lo:hi])
+                        if with_fields:
+                            y_done.synchronize()               # the host buffer is free (previous step's fields landed)
+                            d2h_stream.wait_stream(main)
+                            with torch.cuda.stream(d2h_stream):
+                                host_y[lo:hi].copy_(yy, non_blocking=True)
+                            yy.record_stream(d2h_stream)
+                            if c == len(bnd) - 2:
+                                y_done.record(d2h_stream)
                     consumed[buf].record(main)
                     if i + 1 < n_steps:
                         enqueue_copy(i + 1)
                     host_out.copy_(res_dev, non_blocking=True)
                 main.synchronize()                         # this step's result is in host memory
+            if with_fields:
+                y_done.synchronize()
 
         e2e_run(2)
         torch.cuda.synchronize()
@@ -350,6 +538,33 @@ def run_b200(args):
                "chunks_first_step": n_chunks,
                "pipeline": "two device input buffers: the pinned-host batch of step i+1 is copied on a second stream "
                            "while step i is evaluated (all copies inside the timed region); per-step D2H + stream sync"}
+        # second figure: the fields y come back too (the full result of sample__)
+        host_y = torch.empty(B, *LATTICE, dtype=torch.float32, device="cpu").pin_memory()
+        y_done.record(torch.cuda.current_stream())
+        e2e_run(2, with_fields=True)
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        e2e_run(args.steps, with_fields=True)
+        torch.cuda.synchronize()
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = t.item()
+        e2e["with_fields"] = {"value": world * B * args.steps / dt, "unit": "samples/s",
+                              "h2d_bytes_per_step": int(B * V * 4), "d2h_bytes_per_step": int(B * V * 4 + 2 * B * 4),
+                              "note": "as `e2e`, plus the transformed fields y copied to pinned host memory on a third "
+                                      "stream (overlaps the next step; awaited inside the timed region)"}
+        del host_y, host_x, x_dev
+
+    pk, pk_src = peaks()
+    extras = None
+    if not args.no_extras:
+        del y, logq, logp
+        torch.cuda.empty_cache()
+        extras = run_extras(args, torch, dist, model, world, rank, barrier, pk)
 
     if rank != 0:
         if world > 1:
@@ -357,7 +572,6 @@ def run_b200(args):
         return
 
     # ---- roofline of the dominant HBM-bound kernel --------------------------------------
-    pk, pk_src = peaks()
     P = 3 * KNOTS - 2
     # dominant kernel: the fused coupling step when the model takes that path, else the
     # unfused RQ-spline apply.  Both are scored under the SAME algorithmic byte model
@@ -390,10 +604,26 @@ def run_b200(args):
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         cb = args.cpu_batch
-        v, dt, cores = time_cpu_port(cb, steps=4, warmup=1)
-        cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
-               "sample": f"{cb} samples/step x 4 steps of the same workload, torch ATen float64 port of the "
-                         f"reference's operator sequence, {dt:.1f} s"}
+        jobs = [[3, "sample", cb, 4, 1]]
+        if extras is not None:                  # the other workloads beside their GPU numbers, bounded samples
+            jobs += [[3, "train", 64, 2, 1], [3, "mcmc", 128, 2, 1],
+                     [1, "sample", 128, 20, 2], [1, "train", 128, 20, 2],
+                     [2, "sample", 1024, 3, 1], [2, "train", 512, 3, 1],
+                     [4, "sample", 4, 1, 1], [4, "train", 2, 1, 1],
+                     [5, "sample", 2, 1, 1], [5, "train", 1, 1, 1]]
+        res = reference_jobs(jobs)
+        if res and "samples_per_s" in res[0]:
+            r0 = res[0]
+            cpu = {"value": r0["samples_per_s"], "unit": "samples/s", "cores": r0["threads"], "kind": "reference",
+                   "sample": f"{cb} samples/step x 4 steps of the same workload: the unmodified reference "
+                             f"(oracle/_ref/normflow_ref, float64) model.posterior.sample__, {r0['seconds']:.1f} s"}
+            if extras is not None:
+                attach_cpu(extras, res[1:])
+        else:
+            v, dt, cores = time_cpu_port(cb, steps=4, warmup=1)
+            cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                   "sample": f"{cb} samples/step x 4 steps of the same workload, torch ATen float64 port of the "
+                             f"reference's operator sequence, {dt:.1f} s (staged reference oracle/_ref missing)"}
 
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
@@ -406,6 +636,8 @@ def run_b200(args):
         "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cpu, "kernels": kernel_table,
     }
+    if extras is not None:
+        line.update(extras)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

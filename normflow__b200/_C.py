@@ -137,6 +137,11 @@ def dev(t, dtype=torch.float32, name="tensor"):
         raise TypeError(f"normflow_b200: {name} must be {dtype}, got {t.dtype}")
     if not t.is_contiguous():
         raise ValueError(f"normflow_b200: {name} must be contiguous")
+    if t.get_device() != torch._C._cuda_getDevice():
+        # the op wrappers (_ops._native) switch to the tensors' device; a pointer of another GPU on
+        # the current device's stream would be an illegal address on the device, so refuse it here
+        raise RuntimeError(f"normflow_b200: {name} lives on cuda:{t.get_device()} but the current device is "
+                           f"cuda:{torch._C._cuda_getDevice()}: all tensors of one call must share a device")
     return t.data_ptr()
 
 

@@ -143,6 +143,8 @@ class Fitter:
         # captured CUDA graph.  For small lattices the step is pure launch latency (tens of kernels of
         # a few microseconds each); see _train_graph.  Also switched on by NFK_CUDA_GRAPH=1.
         self.cuda_graph = os.environ.get('NFK_CUDA_GRAPH') == '1'
+        self._pending_losses = []     # device scalars of the epochs since the last flush
+        self._guard = None
 
     def __call__(self, n_epochs=1000, save_every=None, batch_size=64,
                  optimizer_class=torch.optim.AdamW, scheduler=None, loss_fn=None,
@@ -176,22 +178,49 @@ class Fitter:
         # is never true, so it always optimises net_.parameters(); kept that way)
         hyper = dict(self.hyperparam)
         self._graph_ok = self._graph_mode_possible(optimizer_class, scheduler, hyper)
+        params = list(self._model.net_.parameters())
+        on_cuda = bool(params) and all(p.is_cuda for p in params)
         if self._graph_ok:
             hyper['fused'] = True       # one kernel over all parameters; honours the device-side NaN guard
             hyper['capturable'] = True  # step counters live on the device
-        self.optimizer = optimizer_class(self._model.net_.parameters(), **hyper)
+        elif (on_cuda and optimizer_class in (torch.optim.AdamW, torch.optim.Adam)
+              and 'fused' not in hyper and not hyper.get('foreach')):
+            hyper['fused'] = True       # eager default on CUDA: one launch instead of a foreach chain
+        self.optimizer = optimizer_class(params, **hyper)
         self.scheduler = None if scheduler is None else scheduler(self.optimizer)
+        # Device-side divergence guard (the reference's host-side `if isnan(loss)`, :289): the fused optimisers
+        # skip their update when `found_inf` is set, so neither the eager nor the captured step waits for the
+        # GPU.  Any other optimiser keeps the host-side test.
+        self._guard = None
+        if hyper.get('fused') and on_cuda:
+            dev = params[0].device
+            self._guard = dict(found_inf=torch.zeros((), dtype=torch.float32, device=dev),
+                               n_skipped=torch.zeros((), dtype=torch.float32, device=dev))
+            self.optimizer.found_inf = self._guard['found_inf']
         return self.train(n_epochs, batch_size, save_every)
 
     def _graph_mode_possible(self, optimizer_class, scheduler, hyper):
-        """Graph mode needs: the switch, one rank, CUDA parameters, no scheduler (a captured step has
-        its learning rate baked in) and an optimiser with a fused, capturable implementation."""
-        if not self.cuda_graph or scheduler is not None or self._model.device_handler.nranks != 1:
+        """Graph mode needs: the switch, CUDA parameters, no scheduler (a captured step has its learning
+        rate baked in) and an optimiser with a fused, capturable implementation (`fused=True` in the
+        hyperparameters is what graph mode sets anyway; only an explicit False declines).  With several
+        ranks the gradient all-reduce is captured with the step (NCCL is capturable)."""
+        if not self.cuda_graph:
             return False
-        if optimizer_class not in (torch.optim.AdamW, torch.optim.Adam) or 'fused' in hyper or 'capturable' in hyper:
-            return False
+        why = None
         params = list(self._model.net_.parameters())
-        return bool(params) and all(p.is_cuda for p in params)
+        if scheduler is not None:
+            why = "a learning-rate scheduler is set (a captured step has its learning rate baked in)"
+        elif optimizer_class not in (torch.optim.AdamW, torch.optim.Adam):
+            why = f"{optimizer_class.__name__} has no fused, capturable implementation"
+        elif hyper.get('fused', True) is False or hyper.get('capturable', True) is False:
+            why = "hyperparam asks for fused=False / capturable=False"
+        elif not params or not all(p.is_cuda for p in params):
+            why = "the parameters are not on a CUDA device"
+        if why is not None:
+            if self._model.device_handler.rank == 0:
+                print(f"fit: cuda_graph requested but declined -- {why}; training eagerly")
+            return False
+        return True
 
     # ---- snapshots ({"MODEL_STATE", "EPOCHS_RUN"}, reference :221-247) -------------
     def _load_snapshot(self):
@@ -234,11 +263,31 @@ class Fitter:
             # drop the eager autograd graph first: its AccumulateGrad nodes are tied to the stream the
             # eager steps ran on, and a capture may not depend on the legacy default stream
             loss = None
+            self._flush_losses()
             loss = self._train_graph(n_eager + 1, n_epochs, save_every)
+        self._flush_losses()
+        self._report_skipped()
         if n_epochs > 0 and self._model.device_handler.rank == 0:
             print(f"({loss.device}) Time = {time.time() - t_start:.3g} sec.")
 
     _GRAPH_WARMUP = 3
+
+    def _set_found_inf(self, loss):
+        """found_inf <- 1 when this step must not be taken, evaluated on the device.  One rank: the loss is not
+        finite (the reference's test, :289).  Several ranks: the AVERAGED gradient is not finite -- a loss that
+        diverged on any rank poisons it on every rank, so all ranks skip the same steps and stay in step."""
+        guard, handler = self._guard, self._model.device_handler
+        probe = loss.detach() if handler.nranks == 1 or handler._flat_grad is None else handler._flat_grad.sum()
+        guard['found_inf'].copy_(1.0 - torch.isfinite(probe).to(torch.float32))
+        guard['n_skipped'].add_(guard['found_inf'])
+
+    def _report_skipped(self):
+        if getattr(self, '_guard', None) is None:
+            return
+        skipped = int(self._guard['n_skipped'].item())
+        if skipped:
+            print(f"OOPS: loss was divergent in {skipped} step(s) -> no *step* was taken there.")
+            self._guard['n_skipped'].zero_()
 
     def _train_graph(self, first_epoch, n_epochs, save_every):
         """Epochs first_epoch..n_epochs as replays of one captured CUDA graph of `step`.
@@ -248,40 +297,43 @@ class Fitter:
         (`NormalPrior.use_device_state`), so each replay draws a fresh batch; the reference's
         host-side `if isnan(loss)` becomes the fused optimiser's `found_inf` flag (the update is
         skipped on the device); the loss of every epoch goes to a device buffer that is read back
-        only when something is printed or saved."""
-        model = self._model
+        only when something is printed or saved.  With several ranks the flat-gradient all-reduce
+        (NCCL) is part of the captured step."""
+        model, handler = self._model, self._model.device_handler
         dev = next(model.net_.parameters()).device
         model.prior.use_device_state(True)
         n_graph = n_epochs - first_epoch + 1
         loss_buf = torch.zeros(n_graph, dtype=torch.float32, device=dev)
         slot = torch.zeros(1, dtype=torch.int64, device=dev)
-        found_inf = torch.zeros((), dtype=torch.float32, device=dev)
-        n_skipped = torch.zeros((), dtype=torch.float32, device=dev)
-        self.optimizer.found_inf = found_inf
+        multi = handler.nranks > 1
 
         def body():
             x, logr = model.prior.sample_(self.train_batch_size)
             y, logJ = model.net_(x)
             loss = self.loss_fn(logr - logJ, -model.action(y))
+            if multi:
+                handler.zero_grad()                     # the flat buffer, in place
             loss.backward()
-            found_inf.copy_(1.0 - torch.isfinite(loss.detach()).to(torch.float32))
-            n_skipped.add_(found_inf)
+            handler.sync_gradients()
+            self._set_found_inf(loss)
             self.optimizer.step()                       # no-op on the device when found_inf is set
             loss_buf.index_copy_(0, slot, loss.detach().reshape(1))
             slot.add_(1)
             return loss
 
-        self.optimizer.zero_grad(set_to_none=True)      # gradients get allocated inside the graph's pool
+        if not multi:
+            self.optimizer.zero_grad(set_to_none=True)  # gradients get allocated inside the graph's pool
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        # thread-local capture mode: NCCL's watchdog thread may query events while this thread captures
+        with torch.cuda.graph(graph, capture_error_mode="thread_local" if multi else "global"):
             static_loss = body()
         # (capturing does not execute: epoch `first_epoch` is the first replay)
         flushed = 0
 
         def flush(upto):                                # device losses -> train_history (one sync)
             nonlocal flushed
-            if upto > flushed and model.device_handler.rank == 0:
+            if upto > flushed and handler.rank == 0:
                 self.train_history['loss'].extend(loss_buf[flushed:upto].tolist())
             flushed = max(flushed, upto)
 
@@ -295,14 +347,11 @@ class Fitter:
                 flush(epoch - first_epoch + 1)
                 self._checkpoint_tail(epoch, save_every)
         flush(n_graph)
-        skipped = int(n_skipped.item())
-        if skipped:
-            print(f"OOPS: loss was divergent in {skipped} step(s) -> no *step* was taken there.")
-        del self.optimizer.found_inf
         return static_loss.detach()
 
     def step(self):
-        """One optimisation step on a fresh batch (reference Fitter.step, :275-294)."""
+        """One optimisation step on a fresh batch (reference Fitter.step, :275-294).  No host
+        synchronisation when the optimiser is a fused Adam / AdamW (the default on CUDA)."""
         model, handler = self._model, self._model.device_handler
         x, logr = model.prior.sample_(self.train_batch_size)
         y, logJ = model.net_(x)
@@ -313,22 +362,33 @@ class Fitter:
         handler.zero_grad(self.optimizer)
         loss.backward()
         handler.sync_gradients()          # one flat all-reduce when nranks > 1
-        if torch.isnan(loss):
+        if getattr(self, '_guard', None) is not None:
+            self._set_found_inf(loss)
+            self.optimizer.step()         # skipped on the device when the guard is set
+        elif torch.isnan(loss):
             print("OOPS: loss is divergent -> no *step* is taken.")
         else:
             self.optimizer.step()
         return loss, logq - logp
 
     def checkpoint(self, epoch, loss, save_every):
-        handler = self._model.device_handler
-        rank = handler.rank
+        """Book-keeping of an eager epoch.  The loss stays a device scalar until something is printed or
+        saved (or training ends): `train_history['loss']` is filled in batches, without a sync per epoch
+        (the reference calls `loss.item()` every epoch, :305)."""
+        if self._model.device_handler.rank == 0:
+            self._pending_losses.append(loss.detach())
         print_stride = self.checkpoint_dict['print_stride']
-        print_batch_size = self.checkpoint_dict['print_batch_size'] // handler.nranks
         snapshot_path = self.checkpoint_dict['snapshot_path']
-
-        if rank == 0:
-            self.train_history['loss'].append(loss.item())
+        diag = epoch == 1 or epoch == 10 or epoch % print_stride == 0
+        if diag or (snapshot_path is not None and epoch % save_every == 0) or len(self._pending_losses) >= 4096:
+            self._flush_losses()
         self._checkpoint_tail(epoch, save_every)
+
+    def _flush_losses(self):
+        pending = self._pending_losses
+        if pending:
+            self.train_history['loss'].extend(torch.stack(pending).tolist())
+            pending.clear()
 
     def _checkpoint_tail(self, epoch, save_every):
         """Snapshot and diagnostics of an epoch whose loss is already in train_history."""

@@ -25,8 +25,28 @@ def _native(fn):
     @functools.wraps(fn)
     def wrapper(*args, **kwargs):
         with torch._C.DisableTorchFunction():
+            # The C entry points launch on the CURRENT device and torch's current stream of it.  A model
+            # that lives on another GPU (device_handler.to('cuda:1'), a snapshot loaded to cuda:{rank})
+            # is served by making its device current for the call, as ATen does for its own kernels.
+            index = _cuda_index(args, kwargs)
+            if index >= 0 and index != torch._C._cuda_getDevice():
+                with torch.cuda.device(index):
+                    return fn(*args, **kwargs)
             return fn(*args, **kwargs)
     return wrapper
+
+
+def _cuda_index(args, kwargs):
+    """Device index of the first CUDA tensor (or explicit CUDA torch.device) among the arguments, -1 if none."""
+    for a in args:
+        if isinstance(a, torch.Tensor):
+            if a.is_cuda:
+                return a.get_device()
+        elif isinstance(a, torch.device) and a.type == 'cuda' and a.index is not None:
+            return a.index
+    if kwargs:
+        return _cuda_index(tuple(kwargs.values()), None)
+    return -1
 
 
 def _f32c(t, name):

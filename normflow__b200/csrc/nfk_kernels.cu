@@ -544,8 +544,12 @@ __global__ void metropolis_kernel(const float* logq, const float* logp, const do
             const int n = B - base < 32 ? (int)(B - base) : 32;
             for (int k = 0; k < n; ++k) {
                 const double l = sl[k];
-                if (!has_ref) { ref = l; has_ref = true; }      // mcmc.py:308-309
-                const bool acc = su[k] < ref - l;               // mcmc.py:313
+                // mcmc.py:308-309: the proposal that initialises the chain is its own reference, and
+                // log u < 0 accepts it -- made unconditional so that a NaN log q - log p (a diverged
+                // model) cannot leave the chain without a state for the gather below
+                const bool init = !has_ref;
+                if (init) { ref = l; has_ref = true; }
+                const bool acc = init || su[k] < ref - l;       // mcmc.py:313
                 if (acc) { ref = l; last = base + k; ++count; }
                 sa[k] = acc;
                 si[k] = last;
@@ -578,7 +582,7 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* src, cons
                                                           float* dst, int64_t row, int vec_ok) {
     const int64_t i = blockIdx.x;
     const int64_t j = idx[i];
-    const float* from = j >= 0 ? src + j * row : prev;
+    const float* from = (j >= 0 || prev == nullptr) ? src + (j >= 0 ? j : 0) * row : prev;   // no state yet: row 0, as mcmc.py:67-68
     float* to = dst + i * row;
     if (vec_ok) {
         const float4* f4 = reinterpret_cast<const float4*>(from);
@@ -592,7 +596,7 @@ __global__ void gather_scalar_kernel(const float* src, const int64_t* idx, const
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
     const int64_t j = idx[i];
-    dst[i] = j >= 0 ? src[j] : prev[0];
+    dst[i] = j >= 0 ? src[j] : (prev ? prev[0] : src[0]);
 }
 extern "C" int nfk_gather_rows(const float* src, const int64_t* idx, const float* prev, float* dst,
                                int64_t B, int64_t row_elems, void* stream) {

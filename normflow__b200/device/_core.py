@@ -83,8 +83,11 @@ class ModelDeviceHandler:
         if self._flat_grad is None:
             self.flatten_gradients()
         self._reattach()
-        dist.all_reduce(self._flat_grad, op=dist.ReduceOp.SUM)
-        self._flat_grad.div_(self.nranks)
+        if dist.get_backend() == 'nccl':
+            dist.all_reduce(self._flat_grad, op=dist.ReduceOp.AVG)     # ncclAvg: one launch
+        else:                                                          # gloo (CPU tests) has no AVG
+            dist.all_reduce(self._flat_grad, op=dist.ReduceOp.SUM)
+            self._flat_grad.div_(self.nranks)
 
     def _reattach(self):
         """Autograd accumulates in place into an existing .grad, so the views normally
@@ -106,6 +109,9 @@ class ModelDeviceHandler:
         if self.nranks == 1:
             return x
         y = x.clone()
+        if dist.get_backend() == 'nccl':
+            dist.all_reduce(y, op=dist.ReduceOp.AVG)
+            return y
         dist.all_reduce(y, op=dist.ReduceOp.SUM)
         return y / self.nranks
 

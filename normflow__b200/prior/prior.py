@@ -57,6 +57,7 @@ class NormalPrior(Prior):
         self._loc = loc.to(torch.float32).contiguous()
         self._scale = scale.to(torch.float32).contiguous()
         self._calls = 0          # Philox stream offset: one stream per draw
+        self._block_calls = 0    # the same for the block proposals of setup_blockupdater (persistent across calls)
         self._state = None       # device-resident {seed, offset}: see use_device_state()
         Prior.manual_seed(seed)
 
@@ -114,9 +115,17 @@ class NormalPrior(Prior):
         of a batch in place (prior.py:106-112; like the reference it takes loc / scale of the first
         block for every block).  Its draws come from a Philox stream range of their own, far from
         the one `sample` walks, so proposals never repeat values this prior has already produced."""
+        old = getattr(self, 'blockupdater', None)
+        if old is not None:
+            # the block stream keeps its place: a new updater (or a repeated call with the same block
+            # length, which is what BlockedMCMCSampler.sample__ does every call) continues after the last
+            # block draw instead of replaying the sequence of proposals from its start
+            self._block_calls = old.chopped_prior._calls - (1 << 40)
+            if old.block_len == block_len and old.chopped_prior._loc.device == self._loc.device:
+                return
         chopped = NormalPrior(loc=self._loc.reshape(-1)[:block_len], scale=self._scale.reshape(-1)[:block_len])
         chopped._standard = self._standard
-        chopped._calls = (1 << 40) + self._calls
+        chopped._calls = (1 << 40) + max(self._block_calls, self._calls)
         self.blockupdater = BlockUpdater(chopped, block_len)
 
     def to(self, *args, **kwargs):

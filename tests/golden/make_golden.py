@@ -180,7 +180,7 @@ def conv_layers(net):
     return ws
 
 
-def gen_coupling(name, shape, B, blocks, seed, hidden=(8, 8), bias=False, acts=None):
+def gen_coupling(name, shape, B, blocks, seed, hidden=(8, 8), bias=False, acts=None, per_step=True):
     """blocks: list of ('affine'|'shift'|'rqs', n_steps).  Records every block's
     output (ModuleList_.hack), the inverse, and reference-autograd gradients of
     loss = mean(logr - logJ + S) w.r.t. x and every parameter."""
@@ -240,7 +240,7 @@ def gen_coupling(name, shape, B, blocks, seed, hidden=(8, 8), bias=False, acts=N
     with torch.no_grad():
         cpl = net_[0]
         parts = list(cpl.mask.split(x))
-        for k, net in enumerate(cpl.nets):
+        for k, net in enumerate(cpl.nets if per_step else []):   # (per_step=False: large lattices, keep the file small)
             p = k % 2
             o = net(parts[1 - p].unsqueeze(1))
             out[f"blk0_step{k}_out"] = npy(o)
@@ -762,6 +762,13 @@ if __name__ == "__main__":
     if wanted("cpl_mixed_4d"):
         gen_coupling("cpl_mixed_4d", (4, 4, 4, 4), 2, [("affine", 2), ("rqs", 2)], seed=50, hidden=(4,),
                      bias=True)
+    # multi-strip 2-D geometries (the fused tensor-core forward walks several strips per sample; the
+    # training forward + tensor-core weight gradient + checkerboard data gradient are pinned to the
+    # reference's autograd here, not to the layer-wise path)
+    if wanted("cpl_rqs_2d_32"):
+        gen_coupling("cpl_rqs_2d_32", (32, 32), 2, [("rqs", 2)], seed=60, per_step=False)
+    if wanted("cpl_mixed_2d_40x24"):
+        gen_coupling("cpl_mixed_2d_40x24", (40, 24), 2, [("affine", 2), ("rqs", 2)], seed=70, per_step=False)
     if wanted("psd"):
         gen_psd()
     if wanted("model_psd_affine"):

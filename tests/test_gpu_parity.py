@@ -292,7 +292,10 @@ def _build_stack(g, bias):
 
 
 @pytest.mark.parametrize("name,bias", [("cpl_affine_2d", False), ("cpl_rqs_2d", False), ("cpl_shift_1d", True),
-                                       ("cpl_mixed_3d", False), ("cpl_mixed_4d", True)])
+                                       ("cpl_mixed_3d", False), ("cpl_mixed_4d", True),
+                                       # multi-strip geometries: the fused training forward, the tensor-core weight
+                                       # gradient and the checkerboard data gradient against REFERENCE autograd
+                                       ("cpl_rqs_2d_32", False), ("cpl_mixed_2d_40x24", False)])
 def test_coupling_stack_golden(name, bias):
     g = load_golden(name)
     net_, shape = _build_stack(g, bias)
@@ -585,17 +588,27 @@ def _oracle_flow(model, x):
 @pytest.mark.parametrize("shape,blocks,B", [((16, 16), [('affine', 4)], 64),            # config 2
                                             ((64, 64), [('rqs', 4)], 6),                # config 3
                                             ((32, 32, 32), [('affine', 1), ('rqs', 1)], 1),   # config 4 style
-                                            ((16, 16, 16, 16), [('affine', 1)], 1)])    # config 5 style (Conv4d)
+                                            ((16, 16, 16, 16), [('affine', 1)], 1),     # config 5 style (Conv4d)
+                                            # the FULL named stacks, per element at 1e-5:
+                                            ((32, 32, 32), [('affine', 4), ('rqs', 4)], 2),           # config 4
+                                            ((16, 16, 16, 16), [('affine', 4), ('rqs', 4)] * 2, 1)])  # config 5
 def test_baseline_configs_vs_oracle(shape, blocks, B):
     model = _config_model(shape, blocks)
     x = torch.randn(B, *shape, generator=torch.Generator('cpu').manual_seed(1234), dtype=torch.float32, device='cpu')
     with torch.no_grad():
         y, logJ = model.net_(x.to(DEV))
         S = model.action(y)
+        xb, lb = model.net_.backward(y, log0=logJ)
     yr, lr = _oracle_flow(model, x.numpy())
     close(y, yr)
     close(logJ, lr)
     close(S, O.phi4_action(yr, **ACTION))
+    # inverse of the whole stack: back to the prior draw, residual log-Jacobian ~ 0 (float32 inverse of
+    # up to 16 coupling steps; achieved values are printed -- run with -s -- and quoted in DESIGN.md 5)
+    inv_err = (xb.cpu() - x).abs().max().item()
+    inv_log = lb.abs().max().item() / max(1.0, float(np.abs(lr).max()))
+    print(f"[inverse] {shape} {blocks}: max |x_back - x| = {inv_err:.2e}, residual log / max(1, |logJ|) = {inv_log:.2e}")
+    assert inv_err < 2e-4 and inv_log < 1e-5
 
 
 @pytest.mark.parametrize("shape,blocks,B", [((64, 64), [('rqs', 4)], 2048), ((32, 32, 32), [('affine', 2), ('rqs', 2)], 64),
@@ -726,6 +739,33 @@ def test_tensor_core_fused_step_against_oracle(shape, K, kind, B, bias, mask_par
         assert all(torch.equal(r[:, frozen], x[:, frozen]) for r in res.values())
 
 
+@pytest.mark.parametrize("scale,y_max,y_p999,logj_max", [(1.0, 1.0, 0.5, 1.0), (2.0, 3.0, 1.0, 1.0)])
+def test_float32_conditioning_envelope(scale, y_max, y_p999, logj_max, monkeypatch):
+    """Pins the float32 conditioning envelope of DESIGN.md 5 (32 x 32, K = 10, one atomic step against the
+    float64 oracle; excess = error / (1e-5 max(|ref|, 1))).  At initialisation-scale conditioner weights (x1)
+    the 1e-5 contract holds per element; at twice that scale log|det J| and 99.9 % of the field elements
+    still hold it and the worst element stays within 3x (measured in round 1: 1.33x tcgen05 / 1.20x CUDA
+    cores) -- a regression of either fused kernel shows up here before it shows up in a trained flow."""
+    from normflow__b200 import _ops
+    K, kind, shape, B, P = 10, 1, (32, 32), 24, 28
+    prm = _C.RqsParams(K, -5.0, 5.0, -5.0, 5.0, 1, 1)
+    g = torch.Generator('cpu').manual_seed(11)
+    rnd = lambda *s, sc=1.0: (torch.randn(*s, generator=g, device='cpu') * sc).to(DEV)
+    w = [rnd(8, 1, 3, 3, sc=0.3 * scale), rnd(8, 8, 3, 3, sc=scale * 0.5 / 72 ** 0.5),
+         rnd(P, 8, 3, 3, sc=scale * 0.5 / 72 ** 0.5)]
+    x = rnd(B, *shape, sc=1.3)
+    yo, lo = _oracle_single_step(x, w, [None] * 3, kind, 0, K, False, 0)
+    for tc in ('1', '0'):
+        monkeypatch.setenv('NFK_FUSED_TC', tc)
+        with torch.no_grad():
+            y, lj = _ops.fused2d_step(x, w, [None] * 3, kind, prm, 0, 0, 0, False)
+        dy = np.abs(y.double().cpu().numpy() - yo) / np.maximum(np.abs(yo), 1) / 1e-5
+        dl = np.abs(lj.double().cpu().numpy() - lo) / np.maximum(np.abs(lo), 1) / 1e-5
+        print(f"[envelope] weights x{scale} tc={tc}: y excess max {dy.max():.2f} p99.9 {np.quantile(dy, 0.999):.2f}, "
+              f"logJ excess max {dl.max():.2f}")
+        assert dy.max() <= y_max and np.quantile(dy, 0.999) <= y_p999 and dl.max() <= logj_max
+
+
 def test_tensor_core_path_is_the_one_that_runs(monkeypatch):
     """At the BASELINE geometry the fused entry point must take the tcgen05 kernel: the two kernels
     differ in the last bits, so identical output would mean the dispatch silently fell back."""
@@ -742,6 +782,26 @@ def test_tensor_core_path_is_the_one_that_runs(monkeypatch):
             out[tc] = _ops.fused2d_step(x, w, [None] * 3, 1, prm, 0, 0)[0]
     assert not torch.equal(out['1'], out['0'])
     assert torch.allclose(out['1'], out['0'], atol=2e-5, rtol=2e-5)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (run under gpurun --gpus 2)")
+def test_model_on_a_device_that_is_not_current():
+    """A model moved to cuda:1 while cuda:0 is the current device must run there (the op wrappers make
+    the tensors' device current for the launch, as ATen does), and mixing devices in one call raises."""
+    assert torch.cuda.current_device() == 0
+    model = _config_model((16, 16), [('rqs', 2)], seed=4)
+    model.device_handler.to('cuda:1')
+    y, logq, logp = model.posterior.sample__(32)
+    assert y.device == torch.device('cuda', 1) and torch.cuda.current_device() == 0
+    close(logp, -O.phi4_action(y.double().cpu().numpy(), **ACTION))
+    x = model.prior.sample(4)
+    yr, lr = _oracle_flow(model, x.cpu().numpy())
+    with torch.no_grad():
+        yy, lj = model.net_(x)
+    close(yy, yr)
+    close(lj, lr)
+    with pytest.raises(RuntimeError):
+        model.net_(x.to('cuda:0'))
 
 
 # ------------------------------------------------------------------ two GPUs: NCCL data parallel training
@@ -761,6 +821,21 @@ def test_spawnprocesses_two_gpus_nccl(tmp_path):
     assert torch.equal(r0["params"], r1["params"])
     assert not torch.allclose(r0["params"], start)
     assert len(r0["loss"]) == 5 and np.isfinite(r0["loss"]).all()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (run under gpurun --gpus 2)")
+def test_two_gpus_graph_mode_captures_the_allreduce(tmp_path):
+    """Graph mode with two ranks: after three eager steps the whole step INCLUDING the NCCL all-reduce is
+    captured once and replayed; the ranks stay bit-identical and the loss history has every epoch."""
+    import mp_helpers
+    model = _config_model((16, 16), [('affine', 2), ('rqs', 2)], seed=22)
+    start = torch.cat([p.detach().flatten().cpu() for p in model.net_.parameters()])
+    model.device_handler.to('cpu')
+    model.device_handler.spawnprocesses(mp_helpers.fit_graph_and_dump, 2, 12433, [7, 8], str(tmp_path), 12, 512)
+    r0 = torch.load(tmp_path / "rank0.pt")
+    r1 = torch.load(tmp_path / "rank1.pt")
+    assert torch.equal(r0["params"], r1["params"]) and not torch.allclose(r0["params"], start)
+    assert len(r0["loss"]) == 12 and np.isfinite(r0["loss"]).all()
 
 
 @pytest.mark.parametrize("shape,blocks,B", [((16, 16), [('affine', 2), ('rqs', 2)], 6), ((64, 64), [('rqs', 2)], 3)])

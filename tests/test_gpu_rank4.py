@@ -217,3 +217,32 @@ def test_blocked_mcmc_with_its_own_generator():
     assert torch.equal(x.view(3, 2, 8)[:, 0], keep.view(3, 2, 8)[:, 0]) and not torch.equal(x, keep)
     model.prior.blockupdater.restore(x, 1)
     assert torch.equal(x, keep)
+
+
+def test_blocked_mcmc_block_stream_advances_across_calls(monkeypatch):
+    """Consecutive blocked_mcmc.sample__ calls must PROPOSE different block values: the block updater's
+    Philox stream keeps its place across calls -- also when the block length changes in between -- (the
+    reference draws fresh torch RNG values every time, prior.py:161-178) instead of restarting with every
+    setup_blockupdater."""
+    from normflow__b200.nn import DistConvertor_
+    from normflow__b200.prior.prior import BlockUpdater
+    torch.manual_seed(5)
+    np.random.seed(5)
+    model = Model(net_=DistConvertor_(6, symmetric=True), prior=NormalPrior(shape=(4, 4)),
+                  action=ScalarPhi4Action(kappa=0.3, m_sq=-1.2, lambd=0.5))
+    model.device_handler.to(DEV)
+    seen = []
+    orig = BlockUpdater.__call__
+
+    def recording(self, x, block_ind):
+        orig(self, x, block_ind)
+        seen[-1].append(self._blocks(x)[:, block_ind].clone().flatten())
+    monkeypatch.setattr(BlockUpdater, '__call__', recording)
+    for n_blocks in (4, 4, 2):
+        seen.append([])
+        model.blocked_mcmc.sample__(batch_size=3, n_blocks=n_blocks)
+    draws = [torch.cat(v).cpu().numpy() for v in seen]
+    assert [d.size for d in draws] == [3 * 16, 3 * 16, 3 * 16]
+    for i in range(3):
+        for j in range(i + 1, 3):                      # no proposal value of one call repeats in another
+            assert np.intersect1d(draws[i], draws[j]).size == 0

@@ -209,7 +209,8 @@ def _run_stack(g, inverse=False):
     return mask, flows
 
 
-@pytest.mark.parametrize("name", ["cpl_affine_2d", "cpl_rqs_2d", "cpl_shift_1d", "cpl_mixed_3d", "cpl_mixed_4d"])
+@pytest.mark.parametrize("name", ["cpl_affine_2d", "cpl_rqs_2d", "cpl_shift_1d", "cpl_mixed_3d", "cpl_mixed_4d",
+                                  "cpl_rqs_2d_32", "cpl_mixed_2d_40x24"])
 def test_coupling_stack_golden(name):
     g = load_golden(name)
     mask, flows = _run_stack(g)
