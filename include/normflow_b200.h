@@ -51,6 +51,9 @@ extern "C" {
 #define NFK_EXTRAP_NONE   0   /* first / last segment extended                   */
 #define NFK_EXTRAP_LINEAR 1   /* straight line with the end-knot derivative      */
 #define NFK_EXTRAP_ANTI   2   /* point mirror about the end knot                 */
+#define NFK_EXTRAP_PERIODIC 3 /* even mirror image about the end knot (spline.py:502-508, 518-524): shared 1-D
+                                 knots only, forward direction only (the map is not monotone); the slope
+                                 changes sign there, so log_out is NaN for a sample with such a point    */
 
 /* activations of the ConvAct conditioner (nn/scalar/modules.py:43-54) */
 #define NFK_ACT_NONE       0
@@ -235,6 +238,14 @@ int nfk_conv_circ_bwd_weight_cb(const float* in, const float* gpre, int g_parity
 int nfk_metropolis_scan(const float* logq, const float* logp, const double* log_u,
                         double* ref_inout, uint8_t* accept, int64_t* idx, int64_t* n_accept,
                         int64_t B, void* stream);
+/* MCMCSampler.estimate_accept_rate (mcmc/mcmc.py:117-124; Resampler('shuffling'),
+ * lib/stats/resampler.py:62-64): acceptance rates of R chains built from R permutations
+ * of the same N values, one warp per chain, all chains concurrently.
+ * logqp float64[N] (device); perm int64[R][N] (NULL: identity); log_u float64[R][N] =
+ * np.log(np.random.rand(N)) per chain, drawn on the host in the reference's order;
+ * rates float64[R] = mean accept flag of chain r (its first proposal is accepted).  */
+int nfk_metropolis_rates(const double* logqp, const int64_t* perm, const double* log_u,
+                         double* rates, int64_t N, int64_t R, void* stream);
 /* index_select(0, idx) (mcmc.py:73-75): dst[i][:] = idx[i] >= 0 ? src[idx[i]][:] :
  * prev[:]  (prev may be NULL when no idx is negative).                          */
 int nfk_gather_rows(const float* src, const int64_t* idx, const float* prev, float* dst,

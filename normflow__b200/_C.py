@@ -31,7 +31,7 @@ class RqsParams(ctypes.Structure):
                 ("extrap_left", ctypes.c_int32), ("extrap_right", ctypes.c_int32)]
 
 
-EXTRAP = {None: 0, 'none': 0, 'linear': 1, 'anti': 2, 'anti-periodic': 2}
+EXTRAP = {None: 0, 'none': 0, 'linear': 1, 'anti': 2, 'anti-periodic': 2, 'periodic': 3}
 ACT = {None: 0, 'none': 0, 'tanh': 1, 'relu': 2, 'leaky_relu': 3, 'softplus': 4, 'abs': 5}
 FROZEN_ZERO, FROZEN_COPY = 0, 1
 EUNSUPPORTED = -2          # NFK_EUNSUPPORTED: the entry declines this configuration
@@ -63,6 +63,7 @@ _SIGNATURES = {
     "nfk_conv_circ_bwd_weight_cb": [c_f, c_f, c_i, c_f, c_f, Lattice, c_i, c_i, c_i, c_l, c_f],
     "nfk_conv2d_wgrad_tc": [c_f, c_f, c_i, c_f, c_f, c_i, c_i, c_i, c_i, c_l, c_f],
     "nfk_metropolis_scan": [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_l, c_f],
+    "nfk_metropolis_rates": [c_f, c_f, c_f, c_f, c_l, c_l, c_f],
     "nfk_gather_rows": [c_f, c_f, c_f, c_f, c_l, c_l, c_f],
     "nfk_fused2d_step": [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, RqsParams, c_i, c_i, c_i,
                          c_f, c_f, c_f, c_i, c_i, c_l, c_f],

@@ -898,6 +898,19 @@ def metropolis_scan(logq, logp, log_u, ref_state):
 
 
 @_native
+def metropolis_rates(logqp, perm, log_u):
+    """Acceptance rates of R shuffled chains (mcmc.py:117-124): logqp float64[N], perm int64[R, N] (or
+    None), log_u float64[R, N] -> float64[R], all on the device; one launch, no synchronisation."""
+    R, N = log_u.shape
+    if logqp.numel() != N or (perm is not None and tuple(perm.shape) != (R, N)):
+        raise ValueError("metropolis_rates: logqp [N], perm [R, N], log_u [R, N]")
+    rates = torch.empty((R,), dtype=torch.float64, device=logqp.device)
+    check(lib().nfk_metropolis_rates(dev(logqp, torch.float64), dev(perm, torch.int64), dev(log_u, torch.float64),
+                                     dev(rates, torch.float64), N, R, stream()), "metropolis_rates")
+    return rates
+
+
+@_native
 def gather_rows(src, idx, prev=None):
     """dst[i] = src[idx[i]] (idx >= 0) or prev (idx < 0)  (mcmc.py:67-75)."""
     src = _f32c(src, "src")

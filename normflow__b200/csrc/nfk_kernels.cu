@@ -331,8 +331,8 @@ __global__ void __launch_bounds__(256) spline1d_kernel(SplineArgs a) {
 
 static bool spline_cfg(int K, int left, int right, int logistic, Spline1dCfg& c) {
     if (K < 2 || K > NFK_MAX_KNOTS) return false;
-    if (left < 0 || left > 2 || right < 0 || right > 2) return false;
-    if (logistic && (right != NFK_EXTRAP_NONE || left == NFK_EXTRAP_LINEAR)) return false;
+    if (left < 0 || left > NFK_EXTRAP_PERIODIC || right < 0 || right > NFK_EXTRAP_PERIODIC) return false;
+    if (logistic && (right != NFK_EXTRAP_NONE || left == NFK_EXTRAP_LINEAR || left == NFK_EXTRAP_PERIODIC)) return false;
     c.K = K; c.left = left; c.right = right; c.logistic = logistic;
     return true;
 }
@@ -361,6 +361,7 @@ extern "C" int nfk_spline1d_fwd(const float* x, const float* knots, int K, int e
     SplineArgs a{};
     if (!x || !knots || !y) return NFK_EINVAL;
     if (!spline_cfg(K, extrap_left, extrap_right, logistic, a.cfg)) return NFK_EINVAL;
+    if (inverse && (extrap_left == NFK_EXTRAP_PERIODIC || extrap_right == NFK_EXTRAP_PERIODIC)) return NFK_EINVAL;
     a.x = x; a.knots = knots; a.inverse = inverse;
     a.y = y; a.log_in = log_in; a.log_out = log_out; a.B = B; a.V = V;
     return spline1d_launch<false>(a, NFK_STREAM(stream));
@@ -574,6 +575,47 @@ extern "C" int nfk_metropolis_scan(const float* logq, const float* logp, const d
     if (!logq || !logp || !log_u || !ref_inout || !accept || !idx) return NFK_EINVAL;
     if (B <= 0) return NFK_OK;
     metropolis_kernel<<<1, 32, 0, NFK_STREAM(stream)>>>(logq, logp, log_u, ref_inout, accept, idx, n_accept, B);
+    return check_launch();
+}
+
+// ---- acceptance rate of R shuffled chains (MCMCSampler.estimate_accept_rate, mcmc.py:117-124)
+// The reference builds R chains from R random permutations of the same log q - log p values and
+// walks each one in a host loop; here chain r is one CTA of one warp: the lanes gather
+// l[perm[r][i]] and log u[r][i] 32 at a time, lane 0 walks the decisions (as metropolis_kernel).
+// Every chain starts without a reference, so its first proposal is accepted (mcmc.py:308-313).
+__global__ void metropolis_rates_kernel(const double* l, const int64_t* perm, const double* log_u,
+                                        double* rates, int64_t N) {
+    __shared__ double sl[32], su[32];
+    const int lane = threadIdx.x;
+    const int64_t* pr = perm ? perm + (int64_t)blockIdx.x * N : nullptr;
+    const double* ur = log_u + (int64_t)blockIdx.x * N;
+    double ref = 0.0;
+    int64_t count = 0;
+    for (int64_t base = 0; base < N; base += 32) {
+        const int64_t i = base + lane;
+        if (i < N) {
+            sl[lane] = l[pr ? pr[i] : i];
+            su[lane] = ur[i];
+        }
+        __syncwarp();
+        if (lane == 0) {
+            const int n = N - base < 32 ? (int)(N - base) : 32;
+            for (int k = 0; k < n; ++k) {
+                const double v = sl[k];
+                const bool init = base == 0 && k == 0;
+                if (init) ref = v;
+                if (init || su[k] < ref - v) { ref = v; ++count; }
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) rates[blockIdx.x] = (double)count / (double)N;
+}
+extern "C" int nfk_metropolis_rates(const double* logqp, const int64_t* perm, const double* log_u,
+                                    double* rates, int64_t N, int64_t R, void* stream) {
+    if (!logqp || !log_u || !rates) return NFK_EINVAL;
+    if (N <= 0 || R <= 0) return NFK_OK;
+    metropolis_rates_kernel<<<(unsigned)R, 32, 0, NFK_STREAM(stream)>>>(logqp, perm, log_u, rates, N);
     return check_launch();
 }
 

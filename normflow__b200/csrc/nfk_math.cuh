@@ -33,6 +33,7 @@ constexpr float kLogSqrt2Pi = 0.91893853320467274f;
 constexpr int kExtrapNone = 0;
 constexpr int kExtrapLinear = 1;
 constexpr int kExtrapAnti = 2;
+constexpr int kExtrapPeriodic = 3;   // 1-D shared-knot splines only (spline.py:502-508, 518-524): even mirror image
 
 // ---------------------------------------------------------------------------
 // softplus with beta = ln 2:  log2(1 + 2^z); torch switches to the identity when
@@ -343,7 +344,7 @@ NFK_HD float rqs_site_backward(const Ld& ld, const RqsCfg& cfg, float x, float g
 // Shared 1-D spline with explicit knots (SplineNet_ / DistConvertor_).
 struct Spline1dCfg {
     int K;
-    int left, right;   // kExtrapNone | kExtrapLinear | kExtrapAnti
+    int left, right;   // kExtrapNone | kExtrapLinear | kExtrapAnti | kExtrapPeriodic
     int logistic;      // wrap as expit -> spline -> logit
 };
 
@@ -378,14 +379,19 @@ NFK_HD void spline1d_forward(const float* kx, const float* ky, const float* kd,
     if (x <= Xa) {
         if (cfg.left == kExtrapLinear) { y = Ya + kd[0] * (x - Xa); logg = logf(kd[0]); return; }
         if (cfg.left == kExtrapAnti && x < Xa) { x = 2.f * Xa - x; refl = 1; }
+        if (cfg.left == kExtrapPeriodic && x < Xa) { x = 2.f * Xa - x; refl = 3; }
     } else if (x > Xb) {
         if (cfg.right == kExtrapLinear) { y = Yb + kd[K - 1] * (x - Xb); logg = logf(kd[K - 1]); return; }
         if (cfg.right == kExtrapAnti) { x = 2.f * Xb - x; refl = 2; }
+        if (cfg.right == kExtrapPeriodic) { x = 2.f * Xb - x; refl = 3; }
     }
     const int j = knots_segment(kx, K, x);
     rq_forward(knots_seg(kx, ky, kd, j), x, y, logg);
     if (refl == 1) y = 2.f * Ya - y;
     if (refl == 2) y = 2.f * Yb - y;
+    // periodic: y(2 X_end - x) = y(x), the slope changes sign -- its logarithm does not exist (the
+    // reference's torch.log of the negative derivative is NaN as well)
+    if (refl == 3) logg = logf(-1.f);
 }
 
 NFK_HD void spline1d_inverse(const float* kx, const float* ky, const float* kd,
@@ -421,6 +427,7 @@ NFK_HD float spline1d_backward(const float* kx, const float* ky, const float* kd
             return gy * D;
         }
         if (cfg.left == kExtrapAnti && x < Xa) { x = 2.f * Xa - x; refl = 1; }
+        if (cfg.left == kExtrapPeriodic && x < Xa) { x = 2.f * Xa - x; refl = 3; }
     } else if (x > Xb) {
         if (cfg.right == kExtrapLinear) {
             const float D = kd[K - 1];
@@ -428,6 +435,19 @@ NFK_HD float spline1d_backward(const float* kx, const float* ky, const float* kd
             return gy * D;
         }
         if (cfg.right == kExtrapAnti) { x = 2.f * Xb - x; refl = 2; }
+        if (cfg.right == kExtrapPeriodic) { x = 2.f * Xb - x; refl = 4; }
+    }
+    if (refl >= 3) {                      // periodic: y = f(2 X_end - x); no log-derivative term
+        const int jp = knots_segment(kx, K, x);
+        const RqSegGrad gp = rq_forward_vjp(knots_seg(kx, ky, kd, jp), x, gy, 0.f);
+        acc(jp, gp.gX0 - gp.gw);
+        acc(jp + 1, gp.gw);
+        acc(K + jp, gp.gY0 - gp.gh);
+        acc(K + jp + 1, gp.gh);
+        acc(2 * K + jp, gp.gD0);
+        acc(2 * K + jp + 1, gp.gD1);
+        acc(refl == 3 ? 0 : K - 1, 2.f * gp.gx);
+        return -gp.gx;
     }
     // mirrored: y = 2 Y_end - f(2 X_end - x)  ->  the inner value receives -gy
     const float gyi = refl ? -gy : gy;

@@ -3,7 +3,7 @@
 AugmentKnots :392-540).
 
 The evaluation -- bin search, segment value and derivative, extrapolation by a
-straight line or by the anti-periodic mirror image -- is one kernel
+straight line, the anti-periodic or the periodic mirror image -- is one kernel
 (`nfk_spline1d_*`); extra fiducial knots are never materialised.  Per-site knots
 (a knot tensor with batch / lattice axes) exist only inside the coupling kernels,
 see nn.RQSplineCoupling_.
@@ -19,8 +19,10 @@ class RQSpline:
 
     knots_* : float32[K] tensors (K >= 2).  knots_d=None -> each knot takes the mean
               slope of its two segments, end knots the slope of their own segment.
-    extrap  : dict(left=..., right=...) with None (end segment extended), 'linear' or
-              'anti' / 'anti-periodic'.
+    extrap  : dict(left=..., right=...) with None (end segment extended), 'linear',
+              'anti' / 'anti-periodic' (point mirror about the end knot) or 'periodic' (even mirror
+              image; the end knot's derivative must be zero; forward direction only -- the map is
+              not monotone there and the derivative returned with grad=True is negative).
     """
 
     def __init__(self, knots_x=None, knots_y=None, knots_d=None, knots_axis=-1, extrap={}):
@@ -29,9 +31,9 @@ class RQSpline:
                                       "RQSplineCoupling_'s fused kernel")
         if knots_d is None:
             knots_d = self.smooth_derivatives(knots_x, knots_y)
-        for side in ('left', 'right'):
-            if extrap.get(side) == 'periodic':
-                raise NotImplementedError("RQSpline: 'periodic' extrapolation is not implemented")
+        for side, end in (('left', 0), ('right', -1)):
+            if extrap.get(side) == 'periodic' and float(knots_d[end]) != 0.0:
+                raise Exception("Oops: derivative at periodic bc must be zero.")    # spline.py:504-505, 520-521
         self.knots_x, self.knots_y, self.knots_d = knots_x, knots_y, knots_d
         self.knots_axis = knots_axis
         self.extrap = dict(extrap)
@@ -74,6 +76,9 @@ class RQSpline:
 
     def backward(self, y, grad=False, squeezed=False):
         """Inverse map; with grad=True also dx/dy."""
+        if 'periodic' in (self.extrap.get('left'), self.extrap.get('right')):
+            raise NotImplementedError("RQSpline.backward: a periodically continued spline is not monotone "
+                                      "(the reference's searchsorted over its mirrored knots_y is undefined too)")
         return self._run(y, grad, inverse=True)
 
 

@@ -108,9 +108,24 @@ class MCMCSampler:
     @staticmethod
     @torch.no_grad()
     def estimate_accept_rate(logqp, n_resamples=10, method='shuffling'):
-        """Acceptance rate (mean, std) of chains built from shuffled copies of logqp.
-        A device tensor is brought to the host ONCE (the reference iterates over CUDA
-        elements, one sync each)."""
+        """Acceptance rate (mean, std) of chains built from shuffled copies of logqp (mcmc.py:117-124).
+
+        A CUDA tensor stays on the device: the `n_resamples` permutations come from torch.randperm on
+        the device and the uniforms from np.random.rand on the host -- the generators, and the order
+        of their calls, that the reference uses for a tensor argument -- and the chains run
+        concurrently, one warp each (`nfk_metropolis_rates`); one small device-to-host read returns
+        the rates.  (The reference walks every chain in a host loop over CUDA elements, one
+        synchronisation per element.)  Host arrays take the reference's own host loop."""
+        if isinstance(logqp, torch.Tensor) and logqp.is_cuda and method == 'shuffling' and logqp.dim() == 1:
+            n = logqp.shape[0]
+            perms, log_u = [], np.empty((n_resamples, n))
+            for r in range(n_resamples):              # per resample: randperm, then rand (resampler.py:62-64, mcmc.py:312)
+                perms.append(torch.randperm(n, device=logqp.device))
+                log_u[r] = np.log(np.random.rand(n))
+            rates = _ops.metropolis_rates(logqp.double().contiguous(), torch.stack(perms),
+                                          torch.from_numpy(log_u).to(logqp.device))
+            rates = rates.cpu().numpy()
+            return np.mean(rates), np.std(rates)
         if isinstance(logqp, torch.Tensor):
             logqp = seize(logqp).astype(np.float64)
         rate = lambda v: np.mean(Metropolis.calc_accept_status(v))

@@ -198,13 +198,24 @@ class RQSplineCoupling_(Coupling_):
     def __init__(self, nets, *, mask, xlim=(0, 1), ylim=(0, 1), knots_x=None, knots_y=None,
                  extrap={}, **kwargs):
         super().__init__(nets, mask=mask, **kwargs)
-        if knots_x is not None or knots_y is not None:
-            raise NotImplementedError("RQSplineCoupling_ with fixed knots_x / knots_y is outside the "
-                                      "accelerated hot path")
         self.xlim, self.xwidth = xlim, xlim[1] - xlim[0]
         self.ylim, self.ywidth = ylim, ylim[1] - ylim[0]
         self.knots_x, self.knots_y = knots_x, knots_y
         self.extrap = extrap
+        # Fixed knots (couplings_.py:246-258): the conditioner then parametrises only the other coordinate and
+        # the derivatives (2K-1 channels), or the derivatives alone (K channels).  The spline kernel takes bin
+        # WIDTHS as softmax logits, so a fixed coordinate enters as the constant channels log(width_i) over the
+        # limits (knots[0], knots[-1]) -- softmax of those logits gives back the widths to float32 rounding.
+        self._fixed = {}
+        for name, knots in (('x', knots_x), ('y', knots_y)):
+            if knots is None:
+                continue
+            k = torch.as_tensor(knots, dtype=torch.float64).reshape(-1).cpu()
+            if k.numel() < 2 or not bool((k[1:] > k[:-1]).all()):
+                raise ValueError(f"knots_{name} must be a 1-D increasing sequence of at least 2 knots")
+            logits = torch.log((k[1:] - k[:-1]) / (k[-1] - k[0])).to(torch.float32)
+            self.register_buffer(f"_fixed_logits_{name}", logits, persistent=False)
+            self._fixed[name] = (float(k[0]), float(k[-1]), k.numel())
 
     def forward(self, x, log0=0):
         return self._sweep(x, log0, inverse=False)
@@ -218,6 +229,8 @@ class RQSplineCoupling_(Coupling_):
         return _ops.rqs_params((n_channels + 2) // 3, self.xlim, self.ylim, self.extrap)
 
     def _fused_knots(self, net):
+        if self._fixed:
+            return -1                       # the single-kernel step parametrises all three knot arrays
         n = net.conv_kwargs['out_channels']
         return (n + 2) // 3 if (n + 2) % 3 == 0 else -1
 
@@ -225,9 +238,37 @@ class RQSplineCoupling_(Coupling_):
         n = out.shape[self.channels_axis]
         if (n + 2) % 3 != 0:
             raise ValueError(f"conditioner emits {n} channels; an RQ spline needs 3K-2")
-        return _ops.rqs_params((n + 2) // 3, self.xlim, self.ylim, self.extrap)
+        xlim = self._fixed['x'][:2] if 'x' in self._fixed else self.xlim
+        ylim = self._fixed['y'][:2] if 'y' in self._fixed else self.ylim
+        return _ops.rqs_params((n + 2) // 3, xlim, ylim, self.extrap)
+
+    def _with_fixed_knots(self, out):
+        """Conditioner output -> the full (K-1, K-1, K) channel layout of the spline kernel."""
+        if not self._fixed:
+            return out
+        ax = self.channels_axis
+        n = out.shape[ax]
+        both = len(self._fixed) == 2
+        K = n if both else (n + 2) // 2
+        if (not both and 2 * K - 1 != n) or any(v[2] != K for v in self._fixed.values()):
+            raise ValueError(f"conditioner emits {n} channels, which does not match the fixed knots "
+                             f"({ {k: v[2] for k, v in self._fixed.items()} } knots)")
+
+        def const(name):
+            shape = [1] * out.dim()
+            shape[ax] = K - 1
+            full = list(out.shape)
+            full[ax] = K - 1
+            return getattr(self, f"_fixed_logits_{name}").to(out.device).reshape(shape).expand(full)
+        if both:
+            parts = [const('x'), const('y'), out]
+        else:
+            free, d = out.split((K - 1, K), dim=ax)
+            parts = [const('x'), free, d] if 'x' in self._fixed else [free, const('y'), d]
+        return torch.cat(parts, dim=ax)
 
     def _transform(self, x, out, parity, log0, frozen_mode, inverse):
+        out = self._with_fixed_knots(out)
         return _ops.rqs_apply(x, out, self.mask._mask, parity, self._params(out), log0, frozen_mode, inverse)
 
     def atomic_forward(self, *, x_active, x_frozen, parity, net, log0=0):

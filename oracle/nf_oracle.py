@@ -164,11 +164,27 @@ def to_coord(w, axis):
     return np.concatenate([np.zeros(pad_shape, dtype=c.dtype), c], axis=axis)
 
 
-def knots_from_raw(out, *, xlim, ylim, axis=1):
-    """RQSplineCoupling_.make_spline, src/nn/scalar/couplings_.py:211-262
-    (the knots_x is None and knots_y is None branch): split the conditioner
-    output into (K-1, K-1, K) channels."""
+def knots_from_raw(out, *, xlim, ylim, axis=1, knots_x=None, knots_y=None):
+    """RQSplineCoupling_.make_spline, src/nn/scalar/couplings_.py:211-262: split the
+    conditioner output into (K-1, K-1, K) channels; with fixed 1-D `knots_x` and / or
+    `knots_y` (:246-258) into (K-1, K) or K channels -- the fixed coordinate is used
+    as it stands, broadcast over batch and lattice."""
     n = out.shape[axis]
+    if knots_x is not None or knots_y is not None:
+        def fixed(k):
+            shape = [1] * out.ndim
+            shape[axis] = -1
+            full = list(out.shape)
+            full[axis] = len(k)
+            return np.broadcast_to(np.asarray(k, dtype=np.float64).reshape(shape), full)
+        if knots_x is not None and knots_y is not None:
+            return fixed(knots_x), fixed(knots_y), softplus_ln2(out)
+        m = (n + 2) // 2
+        assert 2 * m - 1 == n, "conditioner must emit 2K-1 channels when one coordinate is fixed"
+        free, d_ = np.split(out, [m - 1], axis=axis)
+        if knots_x is not None:
+            return fixed(knots_x), to_coord(free, axis) * (ylim[1] - ylim[0]) + ylim[0], softplus_ln2(d_)
+        return to_coord(free, axis) * (xlim[1] - xlim[0]) + xlim[0], fixed(knots_y), softplus_ln2(d_)
     m = (n + 2) // 3
     assert 3 * m - 2 == n, "conditioner must emit 3K-2 channels"
     x_, y_, d_ = np.split(out, [m - 1, 2 * (m - 1)], axis=axis)
@@ -406,9 +422,9 @@ def shift_atomic(x_active, out, mask, parity, log0, inverse=False):
 
 
 def rqs_atomic(x_active, out, mask, parity, log0, *, xlim, ylim, extrap,
-               inverse=False, stable_inverse=False):
+               inverse=False, stable_inverse=False, knots_x=None, knots_y=None):
     """RQSplineCoupling_.atomic_forward / atomic_backward, couplings_.py:178-200."""
-    kx, ky, kd = knots_from_raw(out, xlim=xlim, ylim=ylim, axis=1)
+    kx, ky, kd = knots_from_raw(out, xlim=xlim, ylim=ylim, axis=1, knots_x=knots_x, knots_y=knots_y)
     spline = RQSpline(kx, ky, kd, axis=1, extrap=extrap, stable_inverse=stable_inverse)
     xa = x_active[:, None]
     fx, g = spline.backward(xa) if inverse else spline.forward(xa)

@@ -165,6 +165,62 @@ def gen_spline():
     save("spline", **out)
 
 
+def gen_spline_extra():
+    """(a) `periodic` extrapolation (spline.py:502-508, 518-524) of a shared-knot RQSpline whose end
+    derivatives are zero: values and derivatives in range, in the mirrored range and beyond it.
+    (b) RQSplineCoupling_ with FIXED knots_x and / or knots_y (couplings_.py:246-258): outputs, log J,
+    inverse and reference-autograd gradients."""
+    out = {}
+    g = torch.Generator('cpu').manual_seed(77)
+    K = 7
+    wx, wy = torch.rand(K - 1, generator=g) + 0.3, torch.rand(K - 1, generator=g) + 0.3
+    kx = f32(torch.cat([torch.zeros(1), torch.cumsum(wx / wx.sum(), 0)]) * 3 - 1)         # [-1, 2]
+    ky = f32(torch.cat([torch.zeros(1), torch.cumsum(wy / wy.sum(), 0)]) * 2 + 0.5)       # [0.5, 2.5]
+    kd = f32(torch.rand(K, generator=g) * 1.2 + 0.3)
+    kd[0], kd[-1] = 0.0, 0.0
+    x = f32(torch.rand(400, generator=g) * 11 - 5)      # [-5, 6]: both mirror images ([-4,-1], [2,5]) and beyond
+    out.update(per_kx=npy(kx), per_ky=npy(ky), per_kd=npy(kd), per_x=npy(x))
+    for name, extrap in {"perleft": dict(left='periodic'), "perright": dict(right='periodic'),
+                         "perboth": dict(left='periodic', right='periodic'),
+                         "perleft_antiright": dict(left='periodic', right='anti')}.items():
+        sp = RQSpline(knots_x=kx, knots_y=ky, knots_d=kd, extrap=extrap)
+        y, gr = sp(x, grad=True)
+        out[f"{name}_y"], out[f"{name}_g"] = npy(y), npy(gr)
+    # fixed knots in the coupling
+    shape, B, m = (6, 4), 3, 6
+    mask = EvenOddMask(shape=shape)
+    fx = f32(torch.tensor([-3.0, -1.7, -0.4, 0.3, 1.9, 3.0]))
+    fy = f32(torch.tensor([-2.5, -1.0, -0.2, 0.9, 1.4, 2.5]))
+    out.update(fix_kx=npy(fx), fix_ky=npy(fy), fix_shape=np.array(shape))
+    cases = {"fixx": (dict(knots_x=fx), 2 * m - 1, dict(left='linear', right='linear')),
+             "fixy": (dict(knots_y=fy), 2 * m - 1, {}),
+             "fixxy": (dict(knots_x=fx, knots_y=fy), m, {})}
+    for ci, (tag, (kw, P, extrap)) in enumerate(cases.items()):
+        torch.manual_seed(300 + ci)
+        nets = [ConvAct(1, P, 3, conv_dim=2, hidden_sizes=[4], acts=['tanh', None], bias=True) for _ in range(2)]
+        for n in nets:
+            round_params(n)
+        cpl = RQSplineCoupling_(nets, mask=mask, xlim=(-3, 3), ylim=(-2.5, 2.5), extrap=extrap, **kw)
+        xx = f32(randn32(B, *shape, seed=400 + ci) * 1.6).requires_grad_(True)
+        y, logJ = cpl(xx, log0=0)
+        loss = (y ** 2).sum(dim=(1, 2)).mean() - logJ.mean()
+        params = list(cpl.parameters())
+        grads = torch.autograd.grad(loss, [xx] + params)
+        out.update({f"{tag}_x": npy(xx), f"{tag}_y": npy(y), f"{tag}_logJ": npy(logJ), f"{tag}_loss": npy(loss),
+                    f"{tag}_gx": npy(grads[0])})
+        gi = 1
+        for k, net in enumerate(cpl.nets):
+            for key, val in conv_layers(net).items():
+                out[f"{tag}_step{k}_{key}"] = val
+            for pname, p_ in net.named_parameters():
+                out[f"{tag}_step{k}_grad_{pname}"] = npy(grads[gi])
+                gi += 1
+        with torch.no_grad():
+            xb, lb = cpl.backward(y.detach(), log0=logJ.detach())
+        out[f"{tag}_inv_x"], out[f"{tag}_inv_log"] = npy(xb), npy(lb)
+    save("spline_extra", **out)
+
+
 def conv_layers(net):
     """Export ConvAct weights in standard (Co, Ci, *k) shape."""
     ws = {}
@@ -737,6 +793,8 @@ if __name__ == "__main__":
         gen_prior()
     if wanted("spline"):
         gen_spline()
+    if wanted("spline_extra"):
+        gen_spline_extra()
     if wanted("rqs_kernel_only"):
         gen_rqs_kernel_only()
     if wanted("affine_kernel_only"):

@@ -336,6 +336,31 @@ def test_whole_rqs_stack_through_harness():
     close(log, g["logJ"])
 
 
+@pytest.mark.parametrize("name,left,right", [("perleft", 3, 0), ("perright", 0, 3), ("perboth", 3, 3),
+                                             ("perleft_antiright", 3, 2)])
+def test_spline1d_periodic_mode(name, left, right):
+    """kExtrapPeriodic in the kernels' functor: values against the reference fixture; the derivative through
+    the VJP (negative on the mirror image, where the forward's log-derivative is NaN like the reference's)."""
+    g = load_golden("spline_extra")
+    kn = f32(np.stack([g["per_kx"], g["per_ky"], g["per_kd"]]))
+    K = kn.shape[1]
+    x = f32(g["per_x"][None, :])
+    # beyond the mirror image the reference extends the outermost mirrored segment; the kernel extends the
+    # matching in-range segment -- the same function -- unless the far side has its own rule: compare where
+    # at most one reflection applies
+    lo, hi = g["per_kx"][0], g["per_kx"][-1]
+    ok = (x[0] > 2 * lo - hi) & (x[0] < 2 * hi - lo)
+    y, lj = np.empty_like(x), np.empty(1, dtype=np.float32)
+    H.cpu_spline1d_fwd(fp(x), fp(kn), K, left, right, 0, 0, None, fp(y), fp(lj), I64(1), I64(x.size))
+    close(y[0][ok], g[f"{name}_y"][ok], tol=2e-5)
+    assert np.isnan(lj[0])
+    gx, gk = np.empty_like(x), np.zeros(5 * K, dtype=np.float32)
+    ones, zero = f32(np.ones_like(x)), f32(np.zeros(1))
+    H.cpu_spline1d_bwd(fp(x), fp(kn), K, left, right, 0, fp(ones), fp(zero), fp(gx), fp(gk), I64(1), I64(x.size))
+    close(gx[0][ok], g[f"{name}_g"][ok], tol=5e-5)
+    assert (gx[0][ok] < 0).any()
+
+
 @pytest.mark.parametrize("logistic,left,right,lim", [(1, 2, 0, (0.5, 1.0)), (1, 0, 0, (0.0, 1.0)),
                                                       (0, 1, 1, (-2.0, 3.0)), (0, 2, 0, (0.0, 2.0)),
                                                       (0, 0, 2, (-1.0, 1.0))])

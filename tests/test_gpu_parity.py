@@ -460,6 +460,64 @@ def test_rqspline_class_shared_knots():
     close(xi[torch.as_tensor(inside)], g["s1_x"][inside], tol=5e-5)
 
 
+@pytest.mark.parametrize("name,extrap", [("perleft", dict(left='periodic')), ("perright", dict(right='periodic')),
+                                         ("perboth", dict(left='periodic', right='periodic')),
+                                         ("perleft_antiright", dict(left='periodic', right='anti'))])
+def test_rqspline_periodic_extrapolation_golden(name, extrap):
+    """RQSpline(extrap='periodic') (spline.py:502-508, 518-524): value and (negative) derivative on the mirror
+    image against the reference; a non-zero end derivative raises like the reference; no inverse."""
+    g = load_golden("spline_extra")
+    kx, ky, kd = cu(g["per_kx"]), cu(g["per_ky"]), cu(g["per_kd"])
+    sp = RQSpline(knots_x=kx, knots_y=ky, knots_d=kd, extrap=extrap)
+    x = cu(g["per_x"])
+    lo, hi = g["per_kx"][0], g["per_kx"][-1]
+    ok = (g["per_x"] > 2 * lo - hi) & (g["per_x"] < 2 * hi - lo)     # at most one reflection (see the harness test)
+    y, gr = sp(x, grad=True)
+    close(y.cpu().numpy()[ok], g[f"{name}_y"][ok], tol=2e-5)
+    close(gr.cpu().numpy()[ok], g[f"{name}_g"][ok], tol=5e-5)
+    assert (gr < 0).any()
+    with pytest.raises(Exception, match="derivative at periodic bc must be zero"):
+        RQSpline(knots_x=kx, knots_y=ky, knots_d=kd + 0.5, extrap=extrap)
+    with pytest.raises(NotImplementedError):
+        sp.backward(y)
+
+
+@pytest.mark.parametrize("tag", ["fixx", "fixy", "fixxy"])
+def test_rqs_coupling_with_fixed_knots_golden(tag):
+    """RQSplineCoupling_(knots_x=..., knots_y=...) (couplings_.py:246-258): field, log J, inverse and every
+    gradient against the reference's own outputs / autograd."""
+    g = load_golden("spline_extra")
+    shape = tuple(int(v) for v in g["fix_shape"])
+    kw, P, extrap = {"fixx": (dict(knots_x=cu(g["fix_kx"])), 11, dict(left='linear', right='linear')),
+                     "fixy": (dict(knots_y=cu(g["fix_ky"])), 11, {}),
+                     "fixxy": (dict(knots_x=cu(g["fix_kx"]), knots_y=cu(g["fix_ky"])), 6, {})}[tag]
+    mask = EvenOddMask(shape=shape)
+    nets = [ConvAct(1, P, 3, conv_dim=2, hidden_sizes=[4], acts=['tanh', None], bias=True) for _ in range(2)]
+    cpl = RQSplineCoupling_(nets, mask=mask, xlim=(-3, 3), ylim=(-2.5, 2.5), extrap=extrap, **kw)
+    cpl.to(DEV)
+    for k, net in enumerate(cpl.nets):
+        _load_convact(net, g, f"{tag}_step{k}")
+    x = cu(g[f"{tag}_x"]).requires_grad_(True)
+    y, logJ = cpl(x, log0=0)
+    close(y, g[f"{tag}_y"])
+    close(logJ, g[f"{tag}_logJ"])
+    loss = (y ** 2).sum(dim=(1, 2)).mean() - logJ.mean()
+    close(loss, g[f"{tag}_loss"])
+    grads = torch.autograd.grad(loss, [x] + list(cpl.parameters()))
+    close_grad(grads[0], g[f"{tag}_gx"], tol=2e-5)
+    gi = 1
+    for k, net in enumerate(cpl.nets):
+        for pname, _ in net.named_parameters():
+            close_grad(grads[gi], g[f"{tag}_step{k}_grad_{pname}"], tol=3e-5)
+            gi += 1
+    with torch.no_grad():
+        y2, l2 = cpl(x.detach())                      # evaluation path (no autograd graph)
+        close(y2, g[f"{tag}_y"])
+        xb, lb = cpl.backward(y.detach(), log0=logJ.detach())
+    close(xb, g[f"{tag}_x"], tol=5e-5)
+    close(lb, np.zeros(x.shape[0]), tol=1e-4)
+
+
 def test_model_zero_dim_golden_and_logz():
     g = load_golden("model_zero_dim")
     net_ = DistConvertor_(10, symmetric=True)
@@ -549,6 +607,34 @@ def test_metropolis_long_chain_vs_oracle():
     rows = torch.arange(B, device=DEV, dtype=torch.float32).reshape(B, 1).repeat(1, 4096)
     out = _ops.gather_rows(rows, idx)
     assert torch.equal(out[:, 0].long(), idx) and torch.equal(out[:, -1].long(), idx)
+
+
+def test_estimate_accept_rate_on_device_matches_host_loop():
+    """MCMCSampler.estimate_accept_rate for a CUDA tensor (mcmc.py:117-124): ten shuffled chains as ten warps
+    of nfk_metropolis_rates.  With the same torch / numpy seeds the reference's procedure -- torch.randperm on
+    the device, np.random.rand on the host, a host loop over every chain (restated by the oracle) -- gives the
+    same acceptance count for every chain, hence the same mean and std."""
+    from normflow__b200.mcmc import MCMCSampler
+    n = 3000
+    rs = np.random.RandomState(5)
+    logqp = cu(rs.randn(n) * 1.5 + 0.3)
+    torch.manual_seed(3)
+    np.random.seed(3)
+    mean, std = MCMCSampler.estimate_accept_rate(logqp)
+    torch.manual_seed(3)
+    np.random.seed(3)
+    host = logqp.double().cpu().numpy()
+    rates = []
+    for _ in range(10):
+        perm = torch.randperm(n, device=DEV).cpu().numpy()
+        rates.append(np.mean(O.metropolis_accept_status(host[perm], np.random.rand(n))))
+    assert mean == pytest.approx(np.mean(rates), abs=1e-15) and std == pytest.approx(np.std(rates), abs=1e-15)
+    assert 0.05 < mean < 0.95
+    # the kernel alone, identity permutation, against the oracle's flags
+    u = rs.rand(2, n)
+    r = _ops.metropolis_rates(logqp.double(), None, cu(np.log(u), torch.float64)).cpu().numpy()
+    for k in range(2):
+        assert r[k] == np.mean(O.metropolis_accept_status(host, u[k]))
 
 
 # ------------------------------------------------------------------ BASELINE configs: oracle + full-size properties

@@ -340,3 +340,44 @@ def test_torch_cpu_port_matches_numpy_oracle():
     np.testing.assert_allclose(y_t.numpy(), y_np, rtol=1e-12, atol=1e-12)
     np.testing.assert_allclose(logq_t.numpy(), logq_np, rtol=1e-12, atol=1e-11)
     np.testing.assert_allclose(logp_t.numpy(), logp_np, rtol=1e-12, atol=1e-11)
+
+
+# ------------------------------------------------------------------ periodic extrapolation, fixed knots
+@pytest.mark.parametrize("name,extrap", [("perleft", dict(left='periodic')), ("perright", dict(right='periodic')),
+                                         ("perboth", dict(left='periodic', right='periodic')),
+                                         ("perleft_antiright", dict(left='periodic', right='anti'))])
+def test_periodic_extrapolation_golden(name, extrap):
+    """AugmentKnots 'periodic' (spline.py:502-508, 518-524): even mirror image, derivative sign flipped."""
+    g = load_golden("spline_extra")
+    sp = O.RQSpline(g["per_kx"], g["per_ky"], g["per_kd"], extrap=extrap)
+    y, gr = sp.forward(g["per_x"])
+    np.testing.assert_allclose(y, g[f"{name}_y"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(gr, g[f"{name}_g"], rtol=1e-10, atol=1e-12)
+    assert (g[f"{name}_g"] < 0).any()          # the fixture does visit the mirrored range
+
+
+def _fixed_knot_steps(g, tag):
+    mask = O.evenodd_mask(tuple(int(v) for v in g["fix_shape"]))
+    kw = {"fixx": dict(knots_x=g["fix_kx"], extrap=dict(left='linear', right='linear')),
+          "fixy": dict(knots_y=g["fix_ky"], extrap={}),
+          "fixxy": dict(knots_x=g["fix_kx"], knots_y=g["fix_ky"], extrap={})}[tag]
+    steps = []
+    for k in range(2):
+        layers = [(g[f"{tag}_step{k}_w{i}"], g[f"{tag}_step{k}_b{i}"]) for i in range(2)]
+        steps.append(O.make_convact_step('rqs', layers, ['tanh', None], mask, xlim=(-3, 3), ylim=(-2.5, 2.5),
+                                         stable_inverse=True, **kw))
+    return mask, steps
+
+
+@pytest.mark.parametrize("tag", ["fixx", "fixy", "fixxy"])
+def test_fixed_knots_coupling_golden(tag):
+    """RQSplineCoupling_(knots_x=..., knots_y=...) (couplings_.py:246-258)."""
+    g = load_golden("spline_extra")
+    mask, steps = _fixed_knot_steps(g, tag)
+    x = g[f"{tag}_x"]
+    y, log = O.coupling_forward(x, np.zeros(x.shape[0]), mask, steps)
+    np.testing.assert_allclose(y, g[f"{tag}_y"], rtol=1e-10, atol=1e-11)
+    np.testing.assert_allclose(log, g[f"{tag}_logJ"], rtol=1e-10, atol=1e-10)
+    xb, lb = O.coupling_forward(y, log, mask, steps, inverse=True)
+    np.testing.assert_allclose(xb, x, rtol=1e-8, atol=1e-8)
+    np.testing.assert_allclose(lb, 0.0, atol=1e-8)
