@@ -11,7 +11,7 @@ shape, blocks = (16,) * 4, [('affine', 4), ('rqs', 4)] * 2
 if len(sys.argv) > 1 and sys.argv[1] == '3d':
     shape, blocks = (32,) * 3, [('affine', 4), ('rqs', 4)]
 model = T._config_model(shape, blocks)
-x = torch.randn(1, *shape, generator=torch.Generator('cpu').manual_seed(1234), dtype=torch.float32)
+x = torch.randn(1, *shape, generator=torch.Generator('cpu').manual_seed(1234), dtype=torch.float32, device='cpu')
 ex = lambda got, ref: float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1)) / 1e-5)
 with torch.no_grad():
     stack = model.net_.hack(x.cuda(), log0=0)
