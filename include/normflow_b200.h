@@ -297,6 +297,26 @@ int nfk_fused2d_step_train(const float* x, const float* w1, const float* b1, con
                            float* h1, float* h2, float* out,
                            int L0, int L1, int64_t B, void* stream);
 
+/* ------------------------------------------------ fused N-D step (2-D .. 4-D) ---
+ * The same atomic coupling step (couplings_.py:56-64) on a lattice of 2 to 4 dimensions -- ConvAct(1 -> H -> H -> P)
+ * conditioner with 3^D-tap circular convolutions (modules.py:131-145; ConvNd / Conv4d, convNd.py:84-127), tanh,
+ * tanh, none -- with layers 2 and 3 of the conditioner on the tensor cores (tcgen05 fp16-pair implicit GEMM) and
+ * the affine / RQ-spline transform fused into the last layer's epilogue; the (B, P, *L) conditioner output is
+ * never formed.  Evaluation only (sampling / log_prob).  The hidden layers pass between the three kernels as
+ * fp16-pair records in `workspace` (32 bytes per site each).
+ *   x, y: [B][*lat.shape] (y != x), full-field semantics;  w1[H][1][3^D], w2[H][H][3^D], w3[P][H][3^D] in the
+ *   standard (Co, Ci, *k) layout (Conv4d: its (Co, Ci, k0, k, k, k) view); b1, b2, b3 may be NULL;  H == 8.
+ *   kind / prm / mask_parity / parity / inverse / log_in / log_out as for nfk_fused2d_step.
+ *   workspace: device buffer of at least nfk_fusednd_workspace(...) bytes, 256-byte aligned.
+ * NFK_EUNSUPPORTED (from either entry) unless every lattice extent is even and >= 2, n_knots in {4,5,6,8,10}
+ * and a tile of the lattice fits shared memory; the caller then evaluates the layers one by one.           */
+int64_t nfk_fusednd_workspace(nfk_lattice lat, int kind, int n_knots, int64_t B);
+int nfk_fusednd_step(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                     const float* w3, const float* b3, int H, int kind, nfk_rqs_params prm,
+                     nfk_lattice lat, int mask_parity, int parity, int inverse,
+                     const float* log_in, float* y, float* log_out, int64_t B,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------- PSD block (spectral part) ---
  * PSDBlock_ / FFTNet_ (psd_.py:25-40, fftflow_.py:121-131,167-180): the real-to-complex
  * and complex-to-real transforms are cuFFT calls made by the host package; these entries

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libnormflow_b200.so")
-SOURCES = ["nfk_kernels.cu", "nfk_conv.cu", "nfk_fused.cu", "nfk_fused_tc.cu", "nfk_psd.cu", "nfk_knots.cu", "nfk_wgrad_tc.cu"]
+SOURCES = ["nfk_kernels.cu", "nfk_conv.cu", "nfk_fused.cu", "nfk_fused_tc.cu", "nfk_psd.cu", "nfk_knots.cu", "nfk_wgrad_tc.cu", "nfk_convnd_tc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -808,6 +808,44 @@ def fused2d_step(x, weights, biases, kind, prm, mask_parity, parity, log0=0, inv
     return y, log_out
 
 
+def fusednd_supported(shape, n_knots):
+    """True when nfk_fusednd_step covers a lattice of this shape (2-D .. 4-D, even extents) and knot count
+    (None: affine)."""
+    shape = tuple(int(v) for v in shape)
+    if not 2 <= len(shape) <= 4 or any(v < 2 or v % 2 for v in shape):
+        return False
+    kind, K = (0, 2) if n_knots is None else (1, int(n_knots))
+    return int(lib().nfk_fusednd_workspace(_C.lattice(shape), kind, K, 1)) > 0
+
+
+@_native
+def fusednd_step(x, weights, biases, kind, prm, mask_parity, parity, log0=0, inverse=False):
+    """A whole atomic coupling step on a 2-D .. 4-D lattice (ConvAct(1->8->8->P) conditioner with its layers 2
+    and 3 on the tensor cores + affine / RQ-spline transform fused into the last layer), forward evaluation
+    only.  x: (B, *L); returns (y, log)."""
+    x = _f32c(x, "x")
+    _no_grad_needed(x, *weights, *[b for b in biases if b is not None])
+    log_in = as_log(log0, x)
+    B, shape = x.shape[0], tuple(x.shape[1:])
+    w = [_f32c(t, "conv weight") for t in weights]
+    b = [None if t is None else _f32c(t, "conv bias") for t in biases]
+    if prm is None:
+        prm = _C.RqsParams(2, 0.0, 1.0, 0.0, 1.0, 0, 0)
+    lat = _C.lattice(shape)
+    need = int(lib().nfk_fusednd_workspace(lat, int(kind), prm.n_knots, B))
+    if need <= 0:
+        check(need if need < 0 else _C.EUNSUPPORTED, "fusednd_workspace")
+    y = torch.empty_like(x)
+    log_out = torch.empty((B,), dtype=torch.float32, device=x.device)
+    workspace = torch.empty((need,), dtype=torch.uint8, device=x.device)     # torch allocations are 512-byte aligned
+    with _C.timed("fusednd_step"):
+        check(lib().nfk_fusednd_step(dev(x), dev(w[0]), dev(b[0]), dev(w[1]), dev(b[1]), dev(w[2]), dev(b[2]),
+                                     int(w[0].shape[0]), int(kind), prm, lat, int(mask_parity), int(parity),
+                                     int(bool(inverse)), dev(log_in), dev(y), dev(log_out), B,
+                                     dev(workspace, torch.uint8), need, stream()), "fusednd_step")
+    return y, log_out
+
+
 class _FusedStepTrain(torch.autograd.Function):
     """Forward of a training step through the tensor-core fused kernel (which also stores the
     hidden layers and the conditioner output); backward through the transform's VJP kernel and

@@ -99,6 +99,12 @@ class Coupling_(Module_):
                                             self._fused_kind, self._fused_params(convs[-1].out_channels),
                                             self.mask.mask_kwargs.get('parity', 0), p, log0, inverse)
                 continue
+            if self._fused_kind is not None and self._fusable_nd(net, x):
+                convs = net._convs()
+                x, log0 = _ops.fusednd_step(x, [c.standard_weight() for c in convs], [c.bias for c in convs],
+                                            self._fused_kind, self._fused_params(convs[-1].out_channels),
+                                            self.mask.mask_kwargs.get('parity', 0), p, log0, inverse)
+                continue
             out = self._conditioner(net, x, p)
             x, log0 = self._transform(x, out, p, log0, _C.FROZEN_COPY, inverse)
         return x, log0
@@ -122,6 +128,21 @@ class Coupling_(Module_):
             return False
         return (x.dim() == 3 and x.is_cuda and self.channels_axis == 1
                 and _ops.fused2d_supported(x.shape[1], x.shape[2], self._fused_knots(net)))
+
+    def _fusable_nd(self, net, x):
+        """Evaluation of a 3-D / 4-D checkerboard coupling whose conditioner is ConvAct(1->8->8->P, 3^D taps,
+        tanh): layers 2 and 3 on the tensor cores, transform fused into the last one (nfk_fusednd_step).
+        NFK_FUSED_ND=0 in the environment keeps the layer-by-layer kernels (A/B tests)."""
+        if os.environ.get('NFK_FUSED_ND') == '0':
+            return False
+        if not (isinstance(net, ConvAct) and net.fusednd_ok):
+            return False
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in net.parameters())):
+            return False
+        if not (isinstance(self.mask, EvenOddMask) and self.mask.mask_kwargs.get('exclude_mu') is None):
+            return False
+        return (x.is_cuda and self.channels_axis == 1 and x.dim() == net.conv_kwargs['conv_dim'] + 1
+                and _ops.fusednd_supported(x.shape[1:], self._fused_knots(net)))
 
     def _fusable_train(self, net, x):
         """Same structural conditions, with an autograd graph wanted: needs the tensor-core kernel.

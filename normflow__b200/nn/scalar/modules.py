@@ -197,6 +197,16 @@ class ConvAct(torch.nn.Sequential):
                 and kw.get('padding', 'same') == 'same' and kw.get('padding_mode') == 'circular'
                 and all(k not in kw for k in ('stride', 'dilation', 'groups')))
 
+    @property
+    def fusednd_ok(self):
+        """The same conditioner shape in 3-D / 4-D (Conv3d / Conv4d layers): the N-D tensor-core step."""
+        kw = self.conv_kwargs
+        return (self._pre_act is None and kw['conv_dim'] in (3, 4) and kw['kernel_size'] == 3
+                and kw['in_channels'] == 1 and list(kw['hidden_sizes']) == [8, 8]
+                and tuple(self._acts) == ('tanh', 'tanh', None)
+                and kw.get('padding', 'same') == 'same' and kw.get('padding_mode') == 'circular'
+                and all(k not in kw for k in ('stride', 'dilation', 'groups')))
+
     def forward_masked(self, x, mask, keep):
         """Conditioner output for a field x (B, *L) of which only the sites with
         mask == keep are visible (the frozen partition): Mask.split fused into the
