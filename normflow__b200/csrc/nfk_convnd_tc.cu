@@ -33,29 +33,32 @@ using namespace nfk;
 
 namespace {
 
-constexpr int kNdThreads = 160;      // warps 0-3: loader + epilogue (one TMEM lane quarter each), warp 4: loader + MMA issue
-constexpr int kNdMaxTaps = 81;
+constexpr int kNdThreads = 160;      // warps 0-3: epilogue (one TMEM lane quarter each), warp 4: one thread loads and issues MMAs
 constexpr int kNdMaxSlots = 32;      // TMEM accumulator ring (512 columns / 16)
 constexpr int kNdTmemCols = 512;     // one CTA per SM (enforced through the shared-memory request)
 constexpr uint32_t kNdMinSmem = 120 * 1024;
 
+// Geometry.  Every array has four entries: the lattice's D axes occupy the LAST D of them, the leading ones are
+// dummies (extent 1, stride 0), so that device loops have a fixed trip count of four and constant indices.
 struct NdGeom {
-    int D, taps;
+    int D, taps, ngroups;        // ngroups = 3^(D-2): groups of the nine taps of the two innermost axes
     int L[4], T[4], ntile[4], box[4], bstride[4];
-    int gstride[4];              // lattice strides in sites
-    uint32_t magic_box[4];       // ceil(2^32 / box[d])
-    uint32_t magic_ntile[4];     // ceil(2^32 / ntile[d])
+    int lo[4], hi[4];            // interior box coordinates (1 .. T; 0 .. 0 for a dummy axis)
+    int off[4];                  // lattice coordinate = origin + box coordinate - off
+    int gstride[4];              // lattice strides in sites (unpadded field x, y)
+    int pstride[4];              // strides of the PADDED record arrays (extent L + 2 per axis)
+    uint32_t magic_box[4], magic_ntile[4];
     int nbox, first, span, nt, tiles_per_sample;
-    int V;
-    int nslots, bdup;
-    int nchunk;                  // tap chunks accumulated in separate TMEM columns and summed by the epilogue
-    uint32_t comp_bytes;         // hi plane -> lo plane of the box
+    int V, Vp;                   // sites per sample; padded record positions per sample and plane
+    int split, nruns, run_rec;   // the box as `nruns` contiguous runs of `run_rec` records of the padded array
+    int nslots, bdup, nchunk;
+    uint32_t comp_bytes;         // hi plane -> lo plane of the box in shared memory
     uint32_t off_a, off_b, off_tab, off_bar, smem_bytes;
     int mask_parity, active_val;
 };
 
 struct NdArgs {
-    const uint4* in_rec;         // [B][2][V]: hi plane, lo plane of 16-byte records
+    const uint4* in_rec;         // [B][2][Vp]: hi plane, lo plane of 16-byte records, halo images included
     uint4* out_rec;              // hidden layer: the same layout
     const __half* bimg;          // B operand image prepared by nd_prep_weights_kernel
     const float* bias;           // [Co] or NULL
@@ -103,14 +106,52 @@ __device__ __forceinline__ void nd_records(const float (&v)[8], uint4& hi, uint4
     lo = make_uint4(tc_pack(l[0], l[1]), tc_pack(l[2], l[3]), tc_pack(l[4], l[5]), tc_pack(l[6], l[7]));
 }
 
+// Writes the records of lattice site c into a padded record array (position c + 1 on every axis) together with
+// its periodic images: a site on a face of the lattice also lives in the opposite halo (coordinate 0 -> L + 1,
+// L - 1 -> 0), a site on an edge / corner in every combination of them -- the consumer's tile + halo is then a
+// plain sub-box of the array that a bulk copy can fetch.  Axes with pstride 0 are dummies.
+template <int ND>
+__device__ __forceinline__ void nd_store_site(uint4* hi_plane, int Vp, const int (&c)[ND], const int (&L)[ND],
+                                              const int (&ps)[ND], const uint4& hi, const uint4& lo) {
+    int main_off[ND], alt_off[ND];
+    bool has[ND];
+    bool any = false;
+    int base = 0;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        main_off[d] = (c[d] + 1) * ps[d];
+        has[d] = ps[d] != 0 && (c[d] == 0 || c[d] == L[d] - 1);
+        alt_off[d] = c[d] == 0 ? (L[d] + 1) * ps[d] : 0;
+        any = any || has[d];
+        base += main_off[d];
+    }
+    hi_plane[base] = hi;
+    hi_plane[Vp + base] = lo;
+    if (!any) return;
+#pragma unroll
+    for (int mask = 1; mask < (1 << ND); ++mask) {
+        bool ok = true;
+        int o = 0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            if ((mask >> d) & 1) { ok = ok && has[d]; o += alt_off[d]; }
+            else o += main_off[d];
+        }
+        if (ok) {
+            hi_plane[o] = hi;
+            hi_plane[Vp + o] = lo;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------- layer 1
 struct NdLat {
-    int L[4];
+    int L[4];                    // the D lattice extents first (unlike NdGeom), the rest 1
     int gstride[4];
-    int V;
+    int pstride[4];
+    uint32_t magic_L[4];
+    int V, Vp;
 };
-
-constexpr int nd_pow3(int n) { return n <= 0 ? 1 : 3 * nd_pow3(n - 1); }
 
 // h1 = tanh(conv(x on the frozen partition)) as records.  A thread owns the sites (.., 2i) and (.., 2i + 1) of
 // the innermost axis: the frozen one of the two sees the taps with an even number of unit steps, the active one
@@ -119,7 +160,7 @@ template <int D>
 __global__ void __launch_bounds__(256) nd_layer1_kernel(const float* __restrict__ x, const float* __restrict__ w1,
                                                         const float* __restrict__ b1, uint4* __restrict__ out_rec,
                                                         const NdLat lat, int mask_parity, int active_val, long long B) {
-    constexpr int TAPS = nd_pow3(D);
+    constexpr int TAPS = D == 2 ? 9 : (D == 3 ? 27 : 81);
     __shared__ __align__(16) float ws[TAPS * 8];
     __shared__ __align__(16) float bs[8];
     for (int e = threadIdx.x; e < TAPS * 8; e += blockDim.x) ws[e] = kTwoLog2e * NFK_LDG(w1 + (e & 7) * TAPS + (e >> 3));
@@ -128,27 +169,35 @@ __global__ void __launch_bounds__(256) nd_layer1_kernel(const float* __restrict_
     const int pairs = lat.V >> 1;
     const int bps = (pairs + 255) >> 8;
     const long long b = blockIdx.x / bps;
-    const int pi = (int)(blockIdx.x % bps) * 256 + threadIdx.x;
+    const int pi = (int)(blockIdx.x - b * bps) * 256 + threadIdx.x;
     if (b >= B || pi >= pairs) return;
-    int c[D];
+    int Ld[D], gs[D], ps[D], c[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) { Ld[d] = lat.L[d]; gs[d] = lat.gstride[d]; ps[d] = lat.pstride[d]; }
     int rem = 2 * pi, csum = 0;
 #pragma unroll
     for (int d = D - 1; d >= 0; --d) {
-        c[d] = rem % lat.L[d];
-        rem /= lat.L[d];
+        const int q = nd_div(rem, Ld[d], lat.magic_L[d]);
+        c[d] = rem - q * Ld[d];
+        rem = q;
         csum += c[d];
     }
-    int idx[D > 1 ? D - 1 : 1][3];
+    // neighbour index contributions of the outer axes (slots 0..2 <-> the D - 1 outer lattice axes, right aligned)
+    int idx[3][3];
 #pragma unroll
-    for (int d = 0; d < D - 1; ++d)
+    for (int j = 0; j < 3; ++j) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) idx[d][k] = nd_wrap1(c[d] + k - 1, lat.L[d]) * lat.gstride[d];
+        for (int k = 0; k < 3; ++k) {
+            const int d = j - (4 - D);                     // lattice axis of slot j (negative: no such axis)
+            idx[j][k] = d >= 0 ? nd_wrap1(c[d >= 0 ? d : 0] + k - 1, Ld[d >= 0 ? d : 0]) * gs[d >= 0 ? d : 0] : 0;
+        }
+    }
     int xi[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        int v = c[D - 1] + k - 1;                       // in [-1, L + 1]; L >= 2
-        v += v < 0 ? lat.L[D - 1] : 0;
-        v -= v >= lat.L[D - 1] ? lat.L[D - 1] : 0;
+        int v = c[D - 1] + k - 1;                          // in [-1, L]; the pair starts at an even coordinate
+        v += v < 0 ? Ld[D - 1] : 0;
+        v -= v >= Ld[D - 1] ? Ld[D - 1] : 0;
         xi[k] = v;
     }
     const bool f_first = ((1 - mask_parity + csum) & 1) != active_val;     // the pair's first site is a frozen one
@@ -160,34 +209,37 @@ __global__ void __launch_bounds__(256) nd_layer1_kernel(const float* __restrict_
     }
     float accF[8], accA[8];
     {
-        float bv[8];
         const float4 t0 = reinterpret_cast<const float4*>(bs)[0], t1 = reinterpret_cast<const float4*>(bs)[1];
-        bv[0] = t0.x; bv[1] = t0.y; bv[2] = t0.z; bv[3] = t0.w; bv[4] = t1.x; bv[5] = t1.y; bv[6] = t1.z; bv[7] = t1.w;
+        const float bv[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
 #pragma unroll
         for (int co = 0; co < 8; ++co) accF[co] = accA[co] = bv[co];
     }
     const float* xb = x + b * (long long)lat.V;
 #pragma unroll
-    for (int t = 0; t < TAPS; ++t) {
-        int base = 0, steps = 0;
+    for (int k0 = 0; k0 < (D >= 4 ? 3 : 1); ++k0) {
 #pragma unroll
-        for (int d = 0; d < D - 1; ++d) {
-            const int k = (t / nd_pow3(D - 1 - d)) % 3;
-            base += idx[d][k];
-            steps += k != 1;
-        }
-        const int kl = t % 3;
-        steps += kl != 1;
-        const bool even = (steps & 1) == 0;
-        const float v = NFK_LDG(xb + base + (even ? xF[kl] : xA[kl]));
-        const float4 w0 = reinterpret_cast<const float4*>(ws + t * 8)[0], w1v = reinterpret_cast<const float4*>(ws + t * 8)[1];
-        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1v.x, w1v.y, w1v.z, w1v.w};
-        if (even) {
+        for (int k1 = 0; k1 < (D >= 3 ? 3 : 1); ++k1) {
 #pragma unroll
-            for (int co = 0; co < 8; ++co) accF[co] = fmaf(v, wv[co], accF[co]);
-        } else {
+            for (int k2 = 0; k2 < 3; ++k2) {
 #pragma unroll
-            for (int co = 0; co < 8; ++co) accA[co] = fmaf(v, wv[co], accA[co]);
+                for (int kl = 0; kl < 3; ++kl) {
+                    const int t = ((k0 * (D >= 3 ? 3 : 1) + k1) * 3 + k2) * 3 + kl;
+                    const int steps = (D >= 4 && k0 != 1) + (D >= 3 && k1 != 1) + (k2 != 1) + (kl != 1);
+                    const int base = (D >= 4 ? idx[0][k0] : 0) + (D >= 3 ? idx[1][k1] : 0) + idx[2][k2];
+                    const bool even = (steps & 1) == 0;
+                    const float v = NFK_LDG(xb + base + (even ? xF[kl] : xA[kl]));
+                    const float4 w0 = reinterpret_cast<const float4*>(ws + t * 8)[0];
+                    const float4 w1v = reinterpret_cast<const float4*>(ws + t * 8)[1];
+                    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1v.x, w1v.y, w1v.z, w1v.w};
+                    if (even) {
+#pragma unroll
+                        for (int co = 0; co < 8; ++co) accF[co] = fmaf(v, wv[co], accF[co]);
+                    } else {
+#pragma unroll
+                        for (int co = 0; co < 8; ++co) accA[co] = fmaf(v, wv[co], accA[co]);
+                    }
+                }
+            }
         }
     }
     float vF[8], vA[8];
@@ -199,15 +251,29 @@ __global__ void __launch_bounds__(256) nd_layer1_kernel(const float* __restrict_
     uint4 hF, lF, hA, lA;
     nd_records(vF, hF, lF);
     nd_records(vA, hA, lA);
-    uint4* ob = out_rec + b * 2LL * lat.V + 2 * pi;
-    ob[f_first ? 0 : 1] = hF;
-    ob[f_first ? 1 : 0] = hA;
-    ob[lat.V + (f_first ? 0 : 1)] = lF;
-    ob[lat.V + (f_first ? 1 : 0)] = lA;
+    uint4* ob = out_rec + b * 2LL * lat.Vp;
+    int cF[D], cA[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) cF[d] = cA[d] = c[d];
+    cF[D - 1] += f_first ? 0 : 1;
+    cA[D - 1] += f_first ? 1 : 0;
+    nd_store_site<D>(ob, lat.Vp, cF, Ld, ps, hF, lF);
+    nd_store_site<D>(ob, lat.Vp, cA, Ld, ps, hA, lA);
 }
 
 // ------------------------------------------------------------------------------------------- layers 2 and 3
+__device__ __forceinline__ void nd_bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void nd_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+
 // MODE 0: hidden layer (8 -> 8, tanh) -> records.  MODE 1: last layer (8 -> P) + transform of the field.
+// No CTA-wide barrier inside the unit loop: one thread of warp 4 fetches the box of a unit with bulk copies
+// (the tile and its halo are contiguous runs of the padded record array), issues the MMAs of its M tiles into a
+// ring of TMEM accumulator slots and commits each to an mbarrier; the four epilogue warps drain the ring.
 template <int MODE, int KIND, int K, int INV>
 __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a) {
     constexpr int P = MODE == 0 ? 8 : (KIND == 0 ? 2 : 3 * K - 2);
@@ -215,32 +281,22 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
     extern __shared__ __align__(128) uint8_t smem[];
     const NdGeom& g = a.g;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int D = g.D;
 
     uint8_t* A = smem + g.off_a;
     uint8_t* Bs = smem + g.off_b;
-    int* delta = reinterpret_cast<int*>(smem + g.off_tab);
-    float* bias_s = reinterpret_cast<float*>(delta + 96);
+    float* bias_s = reinterpret_cast<float*>(smem + g.off_tab);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + g.off_bar);
     uint64_t* empty = full + kNdMaxSlots;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(empty + kNdMaxSlots);
-    float* red = reinterpret_cast<float*>(tmem_slot + 2);
+    uint64_t* loaded = empty + kNdMaxSlots;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(loaded + 1);
 
     // ---- one-time set-up ---------------------------------------------------------------------------
     {
         const int n16 = g.taps * g.bdup * N2;                         // 16-byte rows of the B image
         const uint4* src = reinterpret_cast<const uint4*>(a.bimg);
         for (int e = tid; e < n16; e += kNdThreads) reinterpret_cast<uint4*>(Bs)[e] = src[e];
-        for (int t = tid; t < g.taps; t += kNdThreads) {
-            int rem = t, dl = 0;
-            for (int d = D - 1; d >= 0; --d) {
-                dl += (rem % 3 - 1) * g.bstride[d];
-                rem /= 3;
-            }
-            delta[t] = dl;
-        }
         for (int c = tid; c < NH; c += kNdThreads) {
-            float v = (a.bias && c < P) ? NFK_LDG(a.bias + c) : 0.f;
+            const float v = (a.bias && c < P) ? NFK_LDG(a.bias + c) : 0.f;
             bias_s[c] = MODE == 0 ? kTwoLog2e * v : v;
         }
         if (tid == 0) {
@@ -248,6 +304,7 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                 tc::mbar_init(tc::smem_u32(full + i), 1);
                 tc::mbar_init(tc::smem_u32(empty + i), 4);
             }
+            tc::mbar_init(tc::smem_u32(loaded), 1);
             tc::fence_mbar_init();
         }
         if (warp == 4) tc::tmem_alloc(tc::smem_u32(tmem_slot), kNdTmemCols);
@@ -257,79 +314,118 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
         tc::fence_after_sync();
     }
     const uint32_t tmem = *tmem_slot;
-    const uint32_t a_base = tc::smem_u32(A);
-    const uint64_t a_desc = tc::make_desc(a_base, g.comp_bytes, 128);
-    const uint64_t b_desc = tc::make_desc(tc::smem_u32(Bs), g.bdup == 2 ? N2 * 16 : 0, 128);
-    const uint32_t idesc = tc::make_idesc(0, 128, N2);
-    const bool lead = tc::elect_one();
     const long long nunits = a.B * g.tiles_per_sample;
     const int nslots = g.nslots;
-    uint32_t it = 0;                       // M tiles issued so far: the same sequence in every role
+    const int cols_per_slot = g.nchunk * N2;
 
-    for (long long unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
-        const long long b = unit / g.tiles_per_sample;
+    // tile origin (lattice coordinates) of a unit
+    auto unit_origin = [&](long long unit, long long& b, int (&org)[4]) {
+        b = unit / g.tiles_per_sample;
         int trem = (int)(unit - b * g.tiles_per_sample);
-        int org[4] = {0, 0, 0, 0};
-        for (int d = D - 1; d >= 0; --d) {
+#pragma unroll
+        for (int d = 3; d >= 0; --d) {
             const int q = nd_div(trem, g.ntile[d], g.magic_ntile[d]);
             org[d] = (trem - q * g.ntile[d]) * g.T[d];
             trem = q;
         }
-        // ---- the tile and its halo -> shared memory (periodic wrap by index) --------------------------
-        {
-            const uint4* src = a.in_rec + b * 2LL * g.V;
-            for (int j = tid; j < g.nbox; j += kNdThreads) {
-                int rem = j, site = 0;
-                for (int d = D - 1; d >= 0; --d) {
-                    const int q = nd_div(rem, g.box[d], g.magic_box[d]);
-                    const int i = rem - q * g.box[d];
-                    rem = q;
-                    site += nd_wrap1(org[d] + i - 1, g.L[d]) * g.gstride[d];
-                }
-                tc::cp_async16(a_base + j * 16, src + site);
-                tc::cp_async16(a_base + g.comp_bytes + j * 16, src + g.V + site);
-            }
-            tc::cp_async_wait_all();
-            tc::fence_async_smem();
-            __syncthreads();
-            tc::fence_after_sync();
-        }
-        float lsum = 0.f;
-        if (warp == 4) {
-            // =============================== MMA issue ======================================================
-            if (lead) {
-                for (int m = 0; m < g.nt; ++m) {
-                    const uint32_t n = it + m;
-                    const int slot = n % nslots;
-                    tc::mbar_wait(tc::smem_u32(empty + slot), ((n / nslots) & 1u) ^ 1u);
+    };
+
+    if (warp == 4) {
+        // =============================== loads + MMA issue (one thread) ===================================
+        if (tc::elect_one()) {
+            const uint32_t a_base = tc::smem_u32(A);
+            const uint64_t a_desc = tc::make_desc(a_base, g.comp_bytes, 128);
+            const uint64_t b_desc = tc::make_desc(tc::smem_u32(Bs), g.bdup == 2 ? N2 * 16 : 0, 128);
+            const uint32_t idesc = tc::make_idesc(0, 128, N2);
+            const uint32_t loaded_bar = tc::smem_u32(loaded);
+            const int s2 = g.bstride[2];
+            const int gpc = g.ngroups / g.nchunk;                    // tap groups per accumulation chain
+            const int bstep = g.bdup * N2;
+            int slot = 0;
+            uint32_t ring_phase = 0, load_phase = 0;
+            int last_slot = -1;
+            uint32_t last_phase = 0;
+            for (long long unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+                long long b;
+                int org[4];
+                unit_origin(unit, b, org);
+                // the box may be overwritten once every MMA of the previous unit has completed
+                if (last_slot >= 0) tc::mbar_wait(tc::smem_u32(full + last_slot), last_phase);
+                {
+                    const uint4* src = a.in_rec + b * 2LL * g.Vp;
+                    const uint32_t run_bytes = (uint32_t)g.run_rec * 16;
+                    nd_expect_tx(loaded_bar, 2u * g.nruns * run_bytes);
+                    for (int k = 0; k < g.nruns; ++k) {
+                        int rem = k, so = 0;
+#pragma unroll
+                        for (int d = 3; d >= 0; --d) {
+                            if (d < g.split) {
+                                const int q = nd_div(rem, g.box[d], g.magic_box[d]);
+                                so += (org[d] + rem - q * g.box[d]) * g.pstride[d];
+                                rem = q;
+                            } else if (d == g.split) {
+                                so += org[d] * g.pstride[d];
+                            }
+                        }
+                        nd_bulk_load(a_base + k * run_bytes, src + so, run_bytes, loaded_bar);
+                        nd_bulk_load(a_base + g.comp_bytes + k * run_bytes, src + g.Vp + so, run_bytes, loaded_bar);
+                    }
+                    tc::mbar_wait(loaded_bar, load_phase);
+                    load_phase ^= 1u;
                     tc::fence_after_sync();
-                    const uint64_t ad = tc::desc_advance(a_desc, g.first + m * 128);
+                }
+                for (int m = 0; m < g.nt; ++m) {
+                    tc::mbar_wait(tc::smem_u32(empty + slot), ring_phase ^ 1u);
+                    tc::fence_after_sync();
                     // The tensor core adds into its fp32 accumulator with truncation, so the error of a long
                     // accumulation chain grows linearly with its length: the 3^D taps are cut into `nchunk`
                     // chains, each in its own TMEM columns, which the epilogue adds up with round-to-nearest
-                    const int per = (g.taps + g.nchunk - 1) / g.nchunk;
-                    for (int t = 0; t < g.taps; ++t) {
-                        const int ch = t / per;
-                        tc::mma_f16(tmem + (slot * g.nchunk + ch) * N2, tc::desc_advance(ad, delta[t]),
-                                    tc::desc_advance(b_desc, t * g.bdup * N2), idesc, t - ch * per > 0);
+                    const uint64_t ad0 = tc::desc_advance(a_desc, g.first + m * 128);
+                    uint64_t bd = b_desc;
+                    uint32_t acc = tmem + slot * cols_per_slot;
+                    int in_chain = 0;
+                    for (int o = 0; o < g.ngroups; ++o) {
+                        // offset of the outer taps of this group: o enumerates (k0, k1) of the two outer axes
+                        int od;
+                        if (g.ngroups == 9) od = (o / 3 - 1) * g.bstride[0] + (o % 3 - 1) * g.bstride[1];
+                        else if (g.ngroups == 3) od = (o - 1) * g.bstride[1];
+                        else od = 0;
+                        const uint64_t ad = tc::desc_advance(ad0, od);
+#pragma unroll
+                        for (int i = 0; i < 9; ++i) {
+                            const int dl = (i / 3 - 1) * s2 + (i % 3 - 1);
+                            tc::mma_f16(acc, tc::desc_advance(ad, dl), tc::desc_advance(bd, i * bstep), idesc,
+                                        (in_chain | i) != 0);
+                        }
+                        bd = tc::desc_advance(bd, 9 * bstep);
+                        if (++in_chain == gpc) { in_chain = 0; acc += N2; }
                     }
                     tc::mma_commit(tc::smem_u32(full + slot));
+                    last_slot = slot;
+                    last_phase = ring_phase;
+                    if (++slot == nslots) { slot = 0; ring_phase ^= 1u; }
                 }
             }
-            __syncwarp();
-        } else {
-            // =============================== epilogue =======================================================
-            const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+        }
+        __syncwarp();
+    } else {
+        // =============================== epilogue =======================================================
+        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+        int slot = 0;
+        uint32_t ring_phase = 0;
+        for (long long unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+            long long b;
+            int org[4];
+            unit_origin(unit, b, org);
+            float lsum = 0.f;
             for (int m = 0; m < g.nt; ++m) {
-                const uint32_t n = it + m;
-                const int slot = n % nslots;
-                tc::mbar_wait(tc::smem_u32(full + slot), (n / nslots) & 1u);
+                tc::mbar_wait(tc::smem_u32(full + slot), ring_phase);
                 tc::fence_after_sync();
                 float hi[NH], lo[NH];
 #pragma unroll
                 for (int c = 0; c < NH; ++c) hi[c] = lo[c] = 0.f;
-                for (int tc_chunk = 0; tc_chunk < g.nchunk; ++tc_chunk) {
-                    const uint32_t col = lane_addr + (slot * g.nchunk + tc_chunk) * N2;
+                for (int ch = 0; ch < g.nchunk; ++ch) {
+                    const uint32_t col = lane_addr + slot * cols_per_slot + ch * N2;
                     if (NH == 8) {
                         float acc[16];
                         tc::tmem_ld16(col, acc);
@@ -338,32 +434,35 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                         for (int c = 0; c < 8; ++c) { hi[c] += acc[c]; lo[c] += acc[8 + c]; }
                     } else {
 #pragma unroll
-                        for (int ch = 0; ch < NH / 8; ++ch) {
+                        for (int q8 = 0; q8 < NH / 8; ++q8) {
                             float h8[8], l8[8];
-                            tc::tmem_ld8(col + ch * 8, h8);
-                            tc::tmem_ld8(col + NH + ch * 8, l8);
+                            tc::tmem_ld8(col + q8 * 8, h8);
+                            tc::tmem_ld8(col + NH + q8 * 8, l8);
                             tc::tmem_ld_wait();
 #pragma unroll
-                            for (int c = 0; c < 8; ++c) { hi[ch * 8 + c] += h8[c]; lo[ch * 8 + c] += l8[c]; }
+                            for (int c = 0; c < 8; ++c) { hi[q8 * 8 + c] += h8[c]; lo[q8 * 8 + c] += l8[c]; }
                         }
                     }
                 }
                 tc::fence_before_sync();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(tc::smem_u32(empty + slot));     // the accumulator slot is free again
+                if (++slot == nslots) { slot = 0; ring_phase ^= 1u; }
                 // which site is this row?
                 const int r = m * 128 + warp * 32 + lane;
                 if (r >= g.span) continue;
                 int rem = g.first + r, site = 0, csum = 0;
+                int cc[4];
                 bool interior = true;
-                for (int d = D - 1; d >= 0; --d) {
+#pragma unroll
+                for (int d = 3; d >= 0; --d) {
                     const int q = nd_div(rem, g.box[d], g.magic_box[d]);
                     const int i = rem - q * g.box[d];
                     rem = q;
-                    interior = interior && i >= 1 && i <= g.T[d];
-                    const int c = org[d] + i - 1;
-                    site += c * g.gstride[d];
-                    csum += c;
+                    interior = interior && i >= g.lo[d] && i <= g.hi[d];
+                    cc[d] = org[d] + i - g.off[d];
+                    site += cc[d] * g.gstride[d];
+                    csum += cc[d];
                 }
                 if (!interior) continue;
                 if (MODE == 0) {
@@ -373,9 +472,7 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                         v[c] = tanh_from_scaled(fmaf(lo[c], kTwoLog2e / kLoScale, fmaf(hi[c], kTwoLog2e, bias_s[c])));
                     uint4 rh, rl;
                     nd_records(v, rh, rl);
-                    uint4* ob = a.out_rec + b * 2LL * g.V + site;
-                    ob[0] = rh;
-                    ob[g.V] = rl;
+                    nd_store_site<4>(a.out_rec + b * 2LL * g.Vp, g.Vp, cc, g.L, g.pstride, rh, rl);
                 } else {
                     const float xv = NFK_LDG(a.x + b * (long long)g.V + site);
                     float out = xv;
@@ -396,17 +493,13 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                     a.y[b * (long long)g.V + site] = out;
                 }
             }
+            if (MODE == 1) {
+                lsum = warp_sum(lsum);
+                if (lane == 0) atomicAdd(a.log_out + b, lsum);
+            }
         }
-        it += g.nt;
-        if (MODE == 1) {
-            lsum = warp_sum(lsum);
-            if (lane == 0) red[warp] = lsum;
-        }
-        tc::fence_before_sync();
-        __syncthreads();                       // every MMA of the unit has completed: box and `red` reusable
-        tc::fence_after_sync();
-        if (MODE == 1 && tid == 0) atomicAdd(a.log_out + b, red[0] + red[1] + red[2] + red[3]);
     }
+    tc::fence_before_sync();
     __syncthreads();
     if (warp == 4) tc::tmem_dealloc(tmem, kNdTmemCols);
 }
@@ -417,68 +510,89 @@ uint32_t nd_magic(int d) { return (uint32_t)((0x100000000ULL + d - 1) / d); }
 // cycles of one M = 128 MMA by accumulator width (measured, scratch/tc_probe.cu)
 float nd_mma_cycles(int N2) { return N2 <= 32 ? 42.f : N2 <= 64 ? 52.f : 68.f; }
 
+// Fills the lattice part of the geometry: the D axes right-aligned in the four slots.
+void nd_lattice(NdGeom& g, const nfk_lattice& lat) {
+    const int D = lat.ndim, r0 = 4 - D;
+    g.D = D;
+    g.taps = 1;
+    for (int d = 0; d < D; ++d) g.taps *= 3;
+    g.ngroups = g.taps / 9;
+    for (int j = 0; j < 4; ++j) g.L[j] = j >= r0 ? lat.shape[j - r0] : 1;
+    int gs = 1, ps = 1;
+    for (int j = 3; j >= 0; --j) {
+        const bool real = j >= r0;
+        g.gstride[j] = real ? gs : 0;
+        g.pstride[j] = real ? ps : 0;
+        if (real) { gs *= g.L[j]; ps *= g.L[j] + 2; }
+        g.off[j] = real ? 1 : 0;
+    }
+    g.V = gs;
+    g.Vp = ps;
+}
+
 // Chooses the tile of a (sample, tile) unit: trailing axes whole, one axis cut into divisors, leading axes one
 // site thick; minimises modelled cycles per output site subject to the shared-memory budget.
 bool nd_plan(NdGeom& g, int N2, int bdup, uint32_t budget) {
-    const int D = g.D;
-    g.taps = 1;
-    for (int d = 0; d < D; ++d) g.taps *= 3;
-    g.gstride[D - 1] = 1;
-    for (int d = D - 2; d >= 0; --d) g.gstride[d] = g.gstride[d + 1] * g.L[d + 1];
-    g.V = g.gstride[0] * g.L[0];
+    const int r0 = 4 - g.D;
     g.bdup = bdup;
     auto align = [](uint32_t v) { return (v + 127u) & ~127u; };
     float best = 1e30f;
     NdGeom bg = g;
     bool found = false;
-    for (int split = 0; split < D; ++split) {
+    for (int split = r0; split < 4; ++split) {
         for (int t = 1; t <= g.L[split]; ++t) {
             if (g.L[split] % t) continue;
             NdGeom c = g;
             int outputs = 1;
-            for (int d = 0; d < D; ++d) {
-                c.T[d] = d < split ? 1 : (d == split ? t : g.L[d]);
-                c.ntile[d] = g.L[d] / c.T[d];
-                c.box[d] = c.T[d] + 2;
-                outputs *= c.T[d];
+            for (int j = 0; j < 4; ++j) {
+                const bool real = j >= r0;
+                c.T[j] = !real ? 1 : (j < split ? 1 : (j == split ? t : g.L[j]));
+                c.ntile[j] = g.L[j] / c.T[j];
+                c.box[j] = real ? c.T[j] + 2 : 1;
+                c.lo[j] = real ? 1 : 0;
+                c.hi[j] = real ? c.T[j] : 0;
+                outputs *= c.T[j];
             }
-            c.bstride[D - 1] = 1;
-            for (int d = D - 2; d >= 0; --d) c.bstride[d] = c.bstride[d + 1] * c.box[d + 1];
-            long long nbox = (long long)c.bstride[0] * c.box[0];
+            c.bstride[3] = 1;
+            for (int j = 2; j >= 0; --j) c.bstride[j] = c.bstride[j + 1] * c.box[j + 1];
+            const long long nbox = (long long)c.bstride[0] * c.box[0];
             if (nbox > 8000) continue;
             c.nbox = (int)nbox;
             c.first = 0;
             c.span = 1;
             c.tiles_per_sample = 1;
-            for (int d = 0; d < D; ++d) {
-                c.first += c.bstride[d];
-                c.span += (c.T[d] - 1) * c.bstride[d];
-                c.tiles_per_sample *= c.ntile[d];
-                c.magic_box[d] = nd_magic(c.box[d]);
-                c.magic_ntile[d] = nd_magic(c.ntile[d]);
+            for (int j = 0; j < 4; ++j) {
+                c.first += c.lo[j] * c.bstride[j];
+                c.span += (c.hi[j] - c.lo[j]) * c.bstride[j];
+                c.tiles_per_sample *= c.ntile[j];
+                c.magic_box[j] = nd_magic(c.box[j]);
+                c.magic_ntile[j] = nd_magic(c.ntile[j]);
             }
             c.nt = (c.span + 127) / 128;
+            c.split = split;
+            c.run_rec = c.bstride[split] * c.box[split];
+            c.nruns = c.nbox / c.run_rec;
             c.comp_bytes = align((uint32_t)(c.nbox + 128) * 16);
             uint32_t off = 0;
             c.off_a = off; off += 2 * c.comp_bytes;
             c.off_b = off; off = align(off + (uint32_t)c.taps * bdup * N2 * 16);
-            c.off_tab = off; off = align(off + 96 * 4 + 64 * 4);
-            c.off_bar = off; off = align(off + 2 * kNdMaxSlots * 8 + 64);
+            c.off_tab = off; off = align(off + 64 * 4);
+            c.off_bar = off; off = align(off + (2 * kNdMaxSlots + 1) * 8 + 64);
             c.smem_bytes = off < kNdMinSmem ? kNdMinSmem : off;      // > half an SM: one CTA per SM owns all of TMEM
             if (c.smem_bytes > budget) continue;
-            // accumulation chains of about nine taps where TMEM allows two tiles in flight (4-D only: measured, the
-            // 27-tap chain of a 3-D layer is still within the parity contract and its extra TMEM reads are not free)
+            // accumulation chains of nine taps (27 for wide accumulators) on 4-D lattices, where TMEM still holds two
+            // tiles in flight; measured: the 27-tap chain of a 3-D layer is within the parity contract as it stands
             c.nchunk = 1;
-            if (D == 4) c.nchunk = 256 / N2 < 9 ? 256 / N2 : 9;
+            if (c.D == 4) c.nchunk = 9 * N2 <= 170 ? 9 : (3 * N2 <= 256 ? 3 : 1);
             if (const char* e = getenv("NFK_ND_CHUNKS")) {
                 const int v = atoi(e);
-                if (v >= 1 && v * N2 <= kNdTmemCols && v <= c.taps) c.nchunk = v;
+                if (v >= 1 && c.ngroups % v == 0 && v * N2 <= kNdTmemCols) c.nchunk = v;
             }
             c.nslots = kNdTmemCols / (N2 * c.nchunk);
             if (c.nslots > kNdMaxSlots) c.nslots = kNdMaxSlots;
             const float eff = (float)outputs / (c.nt * 128.f);
-            const float cost = c.taps * nd_mma_cycles(N2) / (128.f * eff) + 0.7f * (float)c.nbox / outputs +
-                               600.f / outputs;
+            const float cost = c.taps * nd_mma_cycles(N2) / (128.f * eff) + 0.15f * (float)c.nbox / outputs +
+                               2500.f / outputs;
             if (cost < best) { best = cost; bg = c; found = true; }
         }
     }
@@ -532,9 +646,9 @@ bool nd_lattice_ok(const nfk_lattice& lat) {
     long long v = 1;
     for (int d = 0; d < lat.ndim; ++d) {
         if (lat.shape[d] < 2 || (lat.shape[d] & 1)) return false;     // the checkerboard must wrap consistently
-        v *= lat.shape[d];
+        v *= lat.shape[d] + 2;
     }
-    return v < (1LL << 28);
+    return v < (1LL << 27);
 }
 
 bool nd_knots_ok(int kind, int n_knots) {
@@ -544,14 +658,12 @@ bool nd_knots_ok(int kind, int n_knots) {
 struct NdWorkspace {
     long long rec_bytes, img2_bytes, img3_bytes, total;
 };
-NdWorkspace nd_workspace(const nfk_lattice& lat, int kind, int n_knots, long long B, int bdup) {
-    long long V = 1, taps = 1;
-    for (int d = 0; d < lat.ndim; ++d) { V *= lat.shape[d]; taps *= 3; }
+NdWorkspace nd_workspace(const NdGeom& g, int kind, int n_knots, long long B, int bdup) {
     auto al = [](long long v) { return (v + 255) / 256 * 256; };
     NdWorkspace w;
-    w.rec_bytes = al(B * V * 32);
-    w.img2_bytes = al(taps * bdup * 16 * 16);
-    w.img3_bytes = al(taps * bdup * 2 * nd_hi_cols(kind, n_knots) * 16);
+    w.rec_bytes = al(B * g.Vp * 32LL);
+    w.img2_bytes = al((long long)g.taps * bdup * 16 * 16);
+    w.img3_bytes = al((long long)g.taps * bdup * 2 * nd_hi_cols(kind, n_knots) * 16);
     w.total = 2 * w.rec_bytes + w.img2_bytes + w.img3_bytes;
     return w;
 }
@@ -563,13 +675,12 @@ NdWorkspace nd_workspace(const nfk_lattice& lat, int kind, int n_knots, long lon
 extern "C" int64_t nfk_fusednd_workspace(nfk_lattice lat, int kind, int n_knots, int64_t B) {
     if (!nd_lattice_ok(lat) || (kind != 0 && kind != 1) || !nd_knots_ok(kind, n_knots)) return NFK_EUNSUPPORTED;
     NdGeom g{};
-    g.D = lat.ndim;
-    for (int d = 0; d < lat.ndim; ++d) g.L[d] = lat.shape[d];
+    nd_lattice(g, lat);
     const int bdup = nd_bdup();
     const uint32_t budget = (uint32_t)nd_props().max_smem;
     NdGeom g2 = g, g3 = g;
     if (!nd_plan(g2, 16, bdup, budget) || !nd_plan(g3, 2 * nd_hi_cols(kind, n_knots), bdup, budget)) return NFK_EUNSUPPORTED;
-    return nd_workspace(lat, kind, n_knots, B > 0 ? B : 1, bdup).total;
+    return nd_workspace(g, kind, n_knots, B > 0 ? B : 1, bdup).total;
 }
 
 extern "C" int nfk_fusednd_step(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
@@ -591,14 +702,13 @@ extern "C" int nfk_fusednd_step(const float* x, const float* w1, const float* b1
     const int bdup = nd_bdup();
     const uint32_t budget = (uint32_t)nd_props().max_smem;
     NdGeom g{};
-    g.D = D;
-    for (int d = 0; d < D; ++d) g.L[d] = lat.shape[d];
+    nd_lattice(g, lat);
     g.mask_parity = mask_parity;
     g.active_val = parity == 0 ? 1 : 0;
     NdGeom g2 = g, g3 = g;
     const int NH3 = nd_hi_cols(kind, prm.n_knots);
     if (!nd_plan(g2, 16, bdup, budget) || !nd_plan(g3, 2 * NH3, bdup, budget)) return NFK_EUNSUPPORTED;
-    const NdWorkspace ws = nd_workspace(lat, kind, prm.n_knots, B, bdup);
+    const NdWorkspace ws = nd_workspace(g, kind, prm.n_knots, B, bdup);
     if (workspace_bytes < ws.total || ((uintptr_t)workspace % 256) != 0) return NFK_EINVAL;
     uint8_t* wsp = static_cast<uint8_t*>(workspace);
     uint4* h1 = reinterpret_cast<uint4*>(wsp);
@@ -607,14 +717,21 @@ extern "C" int nfk_fusednd_step(const float* x, const float* w1, const float* b1
     __half* img3 = reinterpret_cast<__half*>(wsp + 2 * ws.rec_bytes + ws.img2_bytes);
     const int P = kind == 0 ? 2 : 3 * prm.n_knots - 2;
 
-    nd_prep_weights_kernel<<<32, 256, 0, st>>>(w2, 8, g2.taps, 8, bdup, img2);
+    nd_prep_weights_kernel<<<32, 256, 0, st>>>(w2, 8, g.taps, 8, bdup, img2);
     if (int e = check_launch()) return e;
-    nd_prep_weights_kernel<<<32, 256, 0, st>>>(w3, P, g3.taps, NH3, bdup, img3);
+    nd_prep_weights_kernel<<<32, 256, 0, st>>>(w3, P, g.taps, NH3, bdup, img3);
     if (int e = check_launch()) return e;
 
     NdLat nl{};
-    for (int d = 0; d < 4; ++d) { nl.L[d] = d < D ? g2.L[d] : 1; nl.gstride[d] = d < D ? g2.gstride[d] : 0; }
-    nl.V = g2.V;
+    for (int d = 0; d < 4; ++d) {
+        const int j = d + 4 - D;                      // NdLat keeps the lattice axes first
+        nl.L[d] = d < D ? g.L[j] : 1;
+        nl.gstride[d] = d < D ? g.gstride[j] : 0;
+        nl.pstride[d] = d < D ? g.pstride[j] : 0;
+        nl.magic_L[d] = nd_magic(nl.L[d]);
+    }
+    nl.V = g.V;
+    nl.Vp = g.Vp;
     const int pairs = nl.V / 2;
     const long long blocks = B * ((pairs + 255) / 256);
     if (blocks >= (1LL << 31)) return NFK_EUNSUPPORTED;
