@@ -33,7 +33,8 @@ using namespace nfk;
 
 namespace {
 
-constexpr int kNdThreads = 160;      // warps 0-3: epilogue (one TMEM lane quarter each), warp 4: one thread loads and issues MMAs
+constexpr int kNdEpiWarps = 8;       // epilogue warps: two per TMEM lane quarter, alternating M tiles
+constexpr int kNdThreads = 32 * kNdEpiWarps + 32;   // + warp 8: one thread loads and issues MMAs
 constexpr int kNdMaxSlots = 32;      // TMEM accumulator ring (512 columns / 16)
 constexpr int kNdTmemCols = 512;     // one CTA per SM (enforced through the shared-memory request)
 constexpr uint32_t kNdMinSmem = 120 * 1024;
@@ -113,34 +114,24 @@ __device__ __forceinline__ void nd_records(const float (&v)[8], uint4& hi, uint4
 template <int ND>
 __device__ __forceinline__ void nd_store_site(uint4* hi_plane, int Vp, const int (&c)[ND], const int (&L)[ND],
                                               const int (&ps)[ND], const uint4& hi, const uint4& lo) {
-    int main_off[ND], alt_off[ND];
-    bool has[ND];
-    bool any = false;
-    int base = 0;
+    int diff[ND];                       // image position - main position along an axis that has an image
+    int hasmask = 0, base = 0;
 #pragma unroll
     for (int d = 0; d < ND; ++d) {
-        main_off[d] = (c[d] + 1) * ps[d];
-        has[d] = ps[d] != 0 && (c[d] == 0 || c[d] == L[d] - 1);
-        alt_off[d] = c[d] == 0 ? (L[d] + 1) * ps[d] : 0;
-        any = any || has[d];
-        base += main_off[d];
+        const int m = (c[d] + 1) * ps[d];
+        const bool has = ps[d] != 0 && (c[d] == 0 || c[d] == L[d] - 1);
+        diff[d] = (c[d] == 0 ? (L[d] + 1) * ps[d] : 0) - m;
+        hasmask |= has ? 1 << d : 0;
+        base += m;
     }
     hi_plane[base] = hi;
     hi_plane[Vp + base] = lo;
-    if (!any) return;
+    for (int mask = hasmask; mask; mask = (mask - 1) & hasmask) {      // the non-empty subsets of `hasmask`
+        int o = base;
 #pragma unroll
-    for (int mask = 1; mask < (1 << ND); ++mask) {
-        bool ok = true;
-        int o = 0;
-#pragma unroll
-        for (int d = 0; d < ND; ++d) {
-            if ((mask >> d) & 1) { ok = ok && has[d]; o += alt_off[d]; }
-            else o += main_off[d];
-        }
-        if (ok) {
-            hi_plane[o] = hi;
-            hi_plane[Vp + o] = lo;
-        }
+        for (int d = 0; d < ND; ++d) o += (mask >> d) & 1 ? diff[d] : 0;
+        hi_plane[o] = hi;
+        hi_plane[Vp + o] = lo;
     }
 }
 
@@ -307,7 +298,7 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
             tc::mbar_init(tc::smem_u32(loaded), 1);
             tc::fence_mbar_init();
         }
-        if (warp == 4) tc::tmem_alloc(tc::smem_u32(tmem_slot), kNdTmemCols);
+        if (warp == kNdEpiWarps) tc::tmem_alloc(tc::smem_u32(tmem_slot), kNdTmemCols);
         tc::fence_async_smem();
         tc::fence_before_sync();
         __syncthreads();
@@ -330,7 +321,7 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
         }
     };
 
-    if (warp == 4) {
+    if (warp == kNdEpiWarps) {
         // =============================== loads + MMA issue (one thread) ===================================
         if (tc::elect_one()) {
             const uint32_t a_base = tc::smem_u32(A);
@@ -410,15 +401,21 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
         __syncwarp();
     } else {
         // =============================== epilogue =======================================================
-        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+        const int quarter = warp & 3, half = warp >> 2;            // TMEM lanes 32 quarter .. +31; tiles of my parity
+        const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
         int slot = 0;
         uint32_t ring_phase = 0;
+        uint32_t tile_no = 0;                                      // M tiles of this CTA so far (all units)
         for (long long unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
             long long b;
             int org[4];
             unit_origin(unit, b, org);
             float lsum = 0.f;
-            for (int m = 0; m < g.nt; ++m) {
+            for (int m = 0; m < g.nt; ++m, ++tile_no) {
+                if ((int)(tile_no & 1u) != half) {                 // the other warp of my quarter takes this tile
+                    if (++slot == nslots) { slot = 0; ring_phase ^= 1u; }
+                    continue;
+                }
                 tc::mbar_wait(tc::smem_u32(full + slot), ring_phase);
                 tc::fence_after_sync();
                 float hi[NH], lo[NH];
@@ -449,7 +446,7 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                 if (lane == 0) tc::mbar_arrive(tc::smem_u32(empty + slot));     // the accumulator slot is free again
                 if (++slot == nslots) { slot = 0; ring_phase ^= 1u; }
                 // which site is this row?
-                const int r = m * 128 + warp * 32 + lane;
+                const int r = m * 128 + quarter * 32 + lane;
                 if (r >= g.span) continue;
                 int rem = g.first + r, site = 0, csum = 0;
                 int cc[4];
@@ -501,7 +498,7 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 4) tc::tmem_dealloc(tmem, kNdTmemCols);
+    if (warp == kNdEpiWarps) tc::tmem_dealloc(tmem, kNdTmemCols);
 }
 
 // ------------------------------------------------------------------------------------------- host side
