@@ -356,11 +356,47 @@ def run_extras(args, torch, dist, model, world, rank, barrier, pk):
         torch.cuda.empty_cache()
         entry["train"] = {k: v for k, v in train_entry(config, m, tbatch, steps=ts, warmup=2 if config < 4 else 1).items()
                           if k not in ("what", "config")}
+        if config < 3:
+            # launch-bound workloads: the whole optimisation step -- with several ranks including the NCCL all-reduce --
+            # replayed as ONE captured CUDA graph (Fitter.cuda_graph).  Two Model.fit runs of different length through
+            # the public API, wall clock around each; the difference is `extra` graph replays.
+            entry["train_graph"] = train_graph_entry(torch, dist, world, rank, barrier, config, tbatch)
         table[str(config)] = entry
         del m
         torch.cuda.empty_cache()
     out["configs"] = table
     return out
+
+
+def train_graph_entry(torch, dist, world, rank, barrier, config, batch, base=23, extra=200):
+    import contextlib
+    import io
+
+    def timed_fit(n_epochs):
+        m = build_model(torch, config)
+        if world > 1:
+            m.device_handler.ddp_wrapper(rank, world, device=torch.device("cuda", torch.cuda.current_device()))
+        m.fit.cuda_graph = True
+        barrier()
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            m.fit(n_epochs=n_epochs, batch_size=batch, hyperparam=dict(lr=1e-3, weight_decay=0.01),
+                  checkpoint_dict=dict(print_stride=10 ** 9, print_batch_size=128 * world, snapshot_path=None))
+        torch.cuda.synchronize()
+        barrier()
+        dt = time.perf_counter() - t0
+        del m
+        return dt
+    timed_fit(base)                              # first use: capture costs, allocator warm-up
+    t_short, t_long = timed_fit(base), timed_fit(base + extra)
+    dt = max(t_long - t_short, 1e-9) / extra
+    if world > 1:
+        t = torch.tensor([dt], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = t.item()
+    return {"what": "model.fit with fit.cuda_graph = True: one graph replay per epoch (all-reduce captured when n_gpus > 1)",
+            "batch_per_gpu": batch, "samples_per_s": world * batch / dt, "ms_per_step": 1e3 * dt,
+            "method": f"(wall time of fit({base + extra} epochs) - fit({base} epochs)) / {extra}"}
 
 
 def attach_cpu(extras, results):
