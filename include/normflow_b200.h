@@ -303,14 +303,16 @@ int nfk_fused2d_step_train(const float* x, const float* w1, const float* b1, con
  * tanh, none -- with layers 2 and 3 of the conditioner on the tensor cores (tcgen05 fp16-pair implicit GEMM) and
  * the affine / RQ-spline transform fused into the last layer's epilogue; the (B, P, *L) conditioner output is
  * never formed.  Evaluation only (sampling / log_prob).  The hidden layers pass between the three kernels as
- * fp16-pair records in `workspace` (32 bytes per site each).
+ * fp16-pair records in `workspace` (4 H bytes per site each).
  *   x, y: [B][*lat.shape] (y != x), full-field semantics;  w1[H][1][3^D], w2[H][H][3^D], w3[P][H][3^D] in the
- *   standard (Co, Ci, *k) layout (Conv4d: its (Co, Ci, k0, k, k, k) view); b1, b2, b3 may be NULL;  H == 8.
+ *   standard (Co, Ci, *k) layout (Conv4d: its (Co, Ci, k0, k, k, k) view); b1, b2, b3 may be NULL;
+ *   hidden width H in {8, 16, 32, 64} (channel groups of 8: one MMA per tap and group; H = 64 runs layer 2 in two
+ *   passes of 32 output channels).
  *   kind / prm / mask_parity / parity / inverse / log_in / log_out as for nfk_fused2d_step.
  *   workspace: device buffer of at least nfk_fusednd_workspace(...) bytes, 256-byte aligned.
  * NFK_EUNSUPPORTED (from either entry) unless every lattice extent is even and >= 2, n_knots in {4,5,6,8,10}
  * and a tile of the lattice fits shared memory; the caller then evaluates the layers one by one.           */
-int64_t nfk_fusednd_workspace(nfk_lattice lat, int kind, int n_knots, int64_t B);
+int64_t nfk_fusednd_workspace(nfk_lattice lat, int H, int kind, int n_knots, int64_t B);
 int nfk_fusednd_step(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                      const float* w3, const float* b3, int H, int kind, nfk_rqs_params prm,
                      nfk_lattice lat, int mask_parity, int parity, int inverse,

@@ -104,7 +104,7 @@ def lib():
         fn = getattr(handle, name)
         fn.argtypes = argtypes
         fn.restype = c_i
-    handle.nfk_fusednd_workspace.argtypes = [Lattice, c_i, c_i, c_l]
+    handle.nfk_fusednd_workspace.argtypes = [Lattice, c_i, c_i, c_i, c_l]
     handle.nfk_fusednd_workspace.restype = c_l
     handle.nfk_strerror.argtypes = [c_i]
     handle.nfk_strerror.restype = ctypes.c_char_p

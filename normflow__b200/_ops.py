@@ -808,19 +808,19 @@ def fused2d_step(x, weights, biases, kind, prm, mask_parity, parity, log0=0, inv
     return y, log_out
 
 
-def fusednd_supported(shape, n_knots):
-    """True when nfk_fusednd_step covers a lattice of this shape (2-D .. 4-D, even extents) and knot count
-    (None: affine)."""
+def fusednd_supported(shape, n_knots, hidden=8):
+    """True when nfk_fusednd_step covers a lattice of this shape (2-D .. 4-D, even extents), knot count
+    (None: affine) and hidden width (8, 16, 32 or 64)."""
     shape = tuple(int(v) for v in shape)
     if not 2 <= len(shape) <= 4 or any(v < 2 or v % 2 for v in shape):
         return False
     kind, K = (0, 2) if n_knots is None else (1, int(n_knots))
-    return int(lib().nfk_fusednd_workspace(_C.lattice(shape), kind, K, 1)) > 0
+    return int(lib().nfk_fusednd_workspace(_C.lattice(shape), int(hidden), kind, K, 1)) > 0
 
 
 @_native
 def fusednd_step(x, weights, biases, kind, prm, mask_parity, parity, log0=0, inverse=False):
-    """A whole atomic coupling step on a 2-D .. 4-D lattice (ConvAct(1->8->8->P) conditioner with its layers 2
+    """A whole atomic coupling step on a 2-D .. 4-D lattice (ConvAct(1->H->H->P) conditioner with its layers 2
     and 3 on the tensor cores + affine / RQ-spline transform fused into the last layer), forward evaluation
     only.  x: (B, *L); returns (y, log)."""
     x = _f32c(x, "x")
@@ -832,7 +832,7 @@ def fusednd_step(x, weights, biases, kind, prm, mask_parity, parity, log0=0, inv
     if prm is None:
         prm = _C.RqsParams(2, 0.0, 1.0, 0.0, 1.0, 0, 0)
     lat = _C.lattice(shape)
-    need = int(lib().nfk_fusednd_workspace(lat, int(kind), prm.n_knots, B))
+    need = int(lib().nfk_fusednd_workspace(lat, int(w[0].shape[0]), int(kind), prm.n_knots, B))
     if need <= 0:
         check(need if need < 0 else _C.EUNSUPPORTED, "fusednd_workspace")
     y = torch.empty_like(x)

@@ -22,6 +22,7 @@
 // dropped.  A persistent CTA per SM walks (sample, tile) units: cp.async box load -> MMAs of every M tile, each
 // committed to its own mbarrier -> epilogue warps drain the TMEM accumulator ring behind the MMA stream.
 
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "nfk_common.cuh"
@@ -34,7 +35,12 @@ using namespace nfk;
 namespace {
 
 constexpr int kNdEpiWarps = 8;       // epilogue warps: two per TMEM lane quarter, alternating M tiles
-constexpr int kNdThreads = 32 * kNdEpiWarps + 32;   // + warp 8: one thread loads and issues MMAs
+#ifndef NFK_ND_ISSUERS
+#define NFK_ND_ISSUERS 2
+#endif
+constexpr int kNdIssuers = NFK_ND_ISSUERS;   // MMA-issuing warps (one elected thread each; M tiles dealt round robin): the
+                                     // issuing thread's ~11 instructions per MMA, not the tensor pipe, pace one issuer
+constexpr int kNdThreads = 32 * (kNdEpiWarps + kNdIssuers);
 constexpr int kNdMaxSlots = 32;      // TMEM accumulator ring (512 columns / 16)
 constexpr int kNdTmemCols = 512;     // one CTA per SM (enforced through the shared-memory request)
 constexpr uint32_t kNdMinSmem = 120 * 1024;
@@ -53,13 +59,16 @@ struct NdGeom {
     int V, Vp;                   // sites per sample; padded record positions per sample and plane
     int split, nruns, run_rec;   // the box as `nruns` contiguous runs of `run_rec` records of the padded array
     int nslots, bdup, nchunk;
-    uint32_t comp_bytes;         // hi plane -> lo plane of the box in shared memory
+    int G;                       // input channel groups of 8 (hidden width / 8)
+    int npass;                   // hidden layer: passes over the output channels (32 per pass at most)
+    uint32_t comp_bytes;         // hi plane -> lo plane of the box in shared memory (planes: [group][hi | lo])
+    uint32_t b_bytes;            // B operand image of one pass
     uint32_t off_a, off_b, off_tab, off_bar, smem_bytes;
     int mask_parity, active_val;
 };
 
 struct NdArgs {
-    const uint4* in_rec;         // [B][2][Vp]: hi plane, lo plane of 16-byte records, halo images included
+    const uint4* in_rec;         // [B][G][2][Vp]: per channel group a hi and a lo plane of 16-byte records, halo images included
     uint4* out_rec;              // hidden layer: the same layout
     const __half* bimg;          // B operand image prepared by nd_prep_weights_kernel
     const float* bias;           // [Co] or NULL
@@ -80,21 +89,29 @@ __device__ __forceinline__ int nd_wrap1(int c, int L) {     // c in [-1, L]
     return c;
 }
 
-// weights [Co][8][taps] (standard (Co, Ci, *k) layout) -> B operand image [tap][bdup][N2][8] fp16:
-// rows [0, NH) the hi parts, rows [NH, 2 NH) the lo parts times 2^11 (zero rows beyond Co)
-__global__ void nd_prep_weights_kernel(const float* w, int Co, int taps, int NH, int bdup, __half* img) {
-    const int N2 = 2 * NH;
-    const int total = taps * N2 * 8;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-        const int ci = e & 7, n = (e >> 3) % N2, t = (e >> 3) / N2;
-        const int p = n < NH ? n : n - NH;
+// weights [Co][Ci][taps] (standard (Co, Ci, *k) layout) -> B operand images, one per pass over the output channels:
+// [pass][tap][group of 8 input channels][N2][8] fp16; rows [0, NH) the hi parts of output channels pass * NH + n,
+// rows [NH, 2 NH) their lo parts times 2^11 (zero rows beyond Co).  Both K groups of an MMA (activations hi | lo)
+// read the same rows (descriptor LBO = 0), or `bdup` = 2 copies of them.
+__global__ void nd_prep_weights_kernel(const float* w, int Co, int Ci, int taps, int NH, int npass, int bdup, __half* img) {
+    const int N2 = 2 * NH, G = Ci / 8;
+    const long long total = (long long)npass * taps * G * N2 * 8;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int ci = (int)(e & 7);
+        long long r = e >> 3;
+        const int n = (int)(r % N2); r /= N2;
+        const int gi = (int)(r % G); r /= G;
+        const int t = (int)(r % taps);
+        const int pass = (int)(r / taps);
+        const int p = pass * NH + (n < NH ? n : n - NH);
         __half val = __float2half_rn(0.f);
         if (p < Co) {
-            const float v = w[((long long)p * 8 + ci) * taps + t];
+            const float v = w[((long long)p * Ci + gi * 8 + ci) * taps + t];
             const __half hi = __float2half_rn(v);
             val = n < NH ? hi : __float2half_rn((v - __half2float(hi)) * kLoScale);
         }
-        for (int kg = 0; kg < bdup; ++kg) img[(((long long)t * bdup + kg) * N2 + n) * 8 + ci] = val;
+        for (int kg = 0; kg < bdup; ++kg)
+            img[((((long long)pass * taps + t) * G + gi) * bdup + kg) * N2 * 8 + n * 8 + ci] = val;
     }
 }
 
@@ -154,8 +171,10 @@ __global__ void __launch_bounds__(256) nd_layer1_kernel(const float* __restrict_
     constexpr int TAPS = D == 2 ? 9 : (D == 3 ? 27 : 81);
     __shared__ __align__(16) float ws[TAPS * 8];
     __shared__ __align__(16) float bs[8];
-    for (int e = threadIdx.x; e < TAPS * 8; e += blockDim.x) ws[e] = kTwoLog2e * NFK_LDG(w1 + (e & 7) * TAPS + (e >> 3));
-    if (threadIdx.x < 8) bs[threadIdx.x] = b1 ? kTwoLog2e * NFK_LDG(b1 + threadIdx.x) : 0.f;
+    const int gidx = blockIdx.y, G = gridDim.y;              // this block's group of 8 output channels
+    for (int e = threadIdx.x; e < TAPS * 8; e += blockDim.x)
+        ws[e] = kTwoLog2e * NFK_LDG(w1 + (gidx * 8 + (e & 7)) * TAPS + (e >> 3));
+    if (threadIdx.x < 8) bs[threadIdx.x] = b1 ? kTwoLog2e * NFK_LDG(b1 + gidx * 8 + threadIdx.x) : 0.f;
     __syncthreads();
     const int pairs = lat.V >> 1;
     const int bps = (pairs + 255) >> 8;
@@ -242,7 +261,7 @@ __global__ void __launch_bounds__(256) nd_layer1_kernel(const float* __restrict_
     uint4 hF, lF, hA, lA;
     nd_records(vF, hF, lF);
     nd_records(vA, hA, lA);
-    uint4* ob = out_rec + b * 2LL * lat.Vp;
+    uint4* ob = out_rec + (b * G + gidx) * 2LL * lat.Vp;
     int cF[D], cA[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) cF[d] = cA[d] = c[d];
@@ -261,13 +280,15 @@ __device__ __forceinline__ void nd_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
 }
 
-// MODE 0: hidden layer (8 -> 8, tanh) -> records.  MODE 1: last layer (8 -> P) + transform of the field.
-// No CTA-wide barrier inside the unit loop: one thread of warp 4 fetches the box of a unit with bulk copies
-// (the tile and its halo are contiguous runs of the padded record array), issues the MMAs of its M tiles into a
-// ring of TMEM accumulator slots and commits each to an mbarrier; the four epilogue warps drain the ring.
+// MODE 0: hidden layer (H -> OC of the H output channels per pass, tanh) -> records; the template argument K
+// carries OC (8, 16 or 32).  MODE 1: last layer (H -> P) + transform of the field.
+// No CTA-wide barrier inside the unit loop: one thread of the last warp fetches the box of a unit with bulk
+// copies (the tile and its halo are contiguous runs of the padded record arrays, one pair of planes per group of
+// 8 input channels), issues the MMAs of its M tiles -- taps x channel groups, K = 16 = 8 channels hi | lo each --
+// into a ring of TMEM accumulator slots and commits each tile to an mbarrier; the epilogue warps drain the ring.
 template <int MODE, int KIND, int K, int INV>
 __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a) {
-    constexpr int P = MODE == 0 ? 8 : (KIND == 0 ? 2 : 3 * K - 2);
+    constexpr int P = MODE == 0 ? K : (KIND == 0 ? 2 : 3 * K - 2);
     constexpr int NH = (P + 7) / 8 * 8, N2 = 2 * NH;
     extern __shared__ __align__(128) uint8_t smem[];
     const NdGeom& g = a.g;
@@ -283,11 +304,9 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
 
     // ---- one-time set-up ---------------------------------------------------------------------------
     {
-        const int n16 = g.taps * g.bdup * N2;                         // 16-byte rows of the B image
-        const uint4* src = reinterpret_cast<const uint4*>(a.bimg);
-        for (int e = tid; e < n16; e += kNdThreads) reinterpret_cast<uint4*>(Bs)[e] = src[e];
-        for (int c = tid; c < NH; c += kNdThreads) {
-            const float v = (a.bias && c < P) ? NFK_LDG(a.bias + c) : 0.f;
+        const int nbias = MODE == 0 ? g.npass * NH : NH;
+        for (int c = tid; c < nbias; c += kNdThreads) {
+            const float v = (a.bias && (MODE == 0 || c < P)) ? NFK_LDG(a.bias + c) : 0.f;
             bias_s[c] = MODE == 0 ? kTwoLog2e * v : v;
         }
         if (tid == 0) {
@@ -305,12 +324,16 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
         tc::fence_after_sync();
     }
     const uint32_t tmem = *tmem_slot;
-    const long long nunits = a.B * g.tiles_per_sample;
+    const long long per_pass = a.B * g.tiles_per_sample;
+    const long long nunits = per_pass * g.npass;
     const int nslots = g.nslots;
     const int cols_per_slot = g.nchunk * N2;
+    const int G = g.G;
 
-    // tile origin (lattice coordinates) of a unit
-    auto unit_origin = [&](long long unit, long long& b, int (&org)[4]) {
+    // pass over the output channels, sample and tile origin (lattice coordinates) of a unit
+    auto unit_origin = [&](long long unit, int& pass, long long& b, int (&org)[4]) {
+        pass = (int)(unit / per_pass);
+        unit -= pass * per_pass;
         b = unit / g.tiles_per_sample;
         int trem = (int)(unit - b * g.tiles_per_sample);
 #pragma unroll
@@ -321,31 +344,45 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
         }
     };
 
-    if (warp == kNdEpiWarps) {
-        // =============================== loads + MMA issue (one thread) ===================================
+    if (warp >= kNdEpiWarps) {
+        // =============================== loads + MMA issue (one elected thread per issuer warp) ===========
+        const int iw = warp - kNdEpiWarps;                            // issuer 0 also fetches the boxes
         if (tc::elect_one()) {
             const uint32_t a_base = tc::smem_u32(A);
+            const uint32_t b_base = tc::smem_u32(Bs);
             const uint64_t a_desc = tc::make_desc(a_base, g.comp_bytes, 128);
-            const uint64_t b_desc = tc::make_desc(tc::smem_u32(Bs), g.bdup == 2 ? N2 * 16 : 0, 128);
+            const uint64_t b_desc = tc::make_desc(b_base, g.bdup == 2 ? N2 * 16 : 0, 128);
             const uint32_t idesc = tc::make_idesc(0, 128, N2);
             const uint32_t loaded_bar = tc::smem_u32(loaded);
             const int s2 = g.bstride[2];
-            const int gpc = g.ngroups / g.nchunk;                    // tap groups per accumulation chain
-            const int bstep = g.bdup * N2;
+            // steps (nine taps of one channel group) per accumulation chain
+            const int chain_len = (g.ngroups * G + g.nchunk - 1) / g.nchunk;
+            const int bstep = g.bdup * N2;                           // B rows per (tap, channel group)
+            const int gstep = (int)(2 * g.comp_bytes >> 4);          // records between the planes of two channel groups
             int slot = 0;
             uint32_t ring_phase = 0, load_phase = 0;
-            int last_slot = -1;
-            uint32_t last_phase = 0;
+            int last_slot[kNdIssuers], cur_pass = -1;                // last tile of every issuer in the previous unit
+            uint32_t last_phase[kNdIssuers];
+#pragma unroll
+            for (int w = 0; w < kNdIssuers; ++w) { last_slot[w] = -1; last_phase[w] = 0; }
             for (long long unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
                 long long b;
-                int org[4];
-                unit_origin(unit, b, org);
-                // the box may be overwritten once every MMA of the previous unit has completed
-                if (last_slot >= 0) tc::mbar_wait(tc::smem_u32(full + last_slot), last_phase);
-                {
-                    const uint4* src = a.in_rec + b * 2LL * g.Vp;
+                int org[4], pass;
+                unit_origin(unit, pass, b, org);
+                if (iw == 0) {
+                    // box (and weights) may be overwritten once every MMA of the previous unit has completed
+#pragma unroll
+                    for (int w = 0; w < kNdIssuers; ++w)
+                        if (last_slot[w] >= 0) tc::mbar_wait(tc::smem_u32(full + last_slot[w]), last_phase[w]);
                     const uint32_t run_bytes = (uint32_t)g.run_rec * 16;
-                    nd_expect_tx(loaded_bar, 2u * g.nruns * run_bytes);
+                    uint32_t tx = 2u * G * g.nruns * run_bytes;
+                    if (pass != cur_pass) tx += g.b_bytes;
+                    nd_expect_tx(loaded_bar, tx);
+                    if (pass != cur_pass) {
+                        nd_bulk_load(b_base, reinterpret_cast<const uint8_t*>(a.bimg) + (size_t)pass * g.b_bytes,
+                                     g.b_bytes, loaded_bar);
+                        cur_pass = pass;
+                    }
                     for (int k = 0; k < g.nruns; ++k) {
                         int rem = k, so = 0;
 #pragma unroll
@@ -358,42 +395,62 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                                 so += org[d] * g.pstride[d];
                             }
                         }
-                        nd_bulk_load(a_base + k * run_bytes, src + so, run_bytes, loaded_bar);
-                        nd_bulk_load(a_base + g.comp_bytes + k * run_bytes, src + g.Vp + so, run_bytes, loaded_bar);
+                        for (int gi = 0; gi < G; ++gi) {
+                            const uint4* src = a.in_rec + (b * G + gi) * 2LL * g.Vp + so;
+                            const uint32_t dst = a_base + (uint32_t)gi * 2u * g.comp_bytes + k * run_bytes;
+                            nd_bulk_load(dst, src, run_bytes, loaded_bar);
+                            nd_bulk_load(dst + g.comp_bytes, src + g.Vp, run_bytes, loaded_bar);
+                        }
                     }
-                    tc::mbar_wait(loaded_bar, load_phase);
-                    load_phase ^= 1u;
-                    tc::fence_after_sync();
                 }
+                tc::mbar_wait(loaded_bar, load_phase);
+                load_phase ^= 1u;
+                tc::fence_after_sync();
                 for (int m = 0; m < g.nt; ++m) {
+                    // a TMEM slot belongs to one issuer (and one epilogue half) for good: its mbarrier phases are
+                    // then walked by one thread in order, which is what a parity wait can tell apart
+                    const int mine = slot % kNdIssuers;
+                    last_slot[mine] = slot;
+                    last_phase[mine] = ring_phase;
+                    if (mine != iw) {                                  // another issuer's tile
+                        if (++slot == nslots) { slot = 0; ring_phase ^= 1u; }
+                        continue;
+                    }
                     tc::mbar_wait(tc::smem_u32(empty + slot), ring_phase ^ 1u);
                     tc::fence_after_sync();
                     // The tensor core adds into its fp32 accumulator with truncation, so the error of a long
-                    // accumulation chain grows linearly with its length: the 3^D taps are cut into `nchunk`
-                    // chains, each in its own TMEM columns, which the epilogue adds up with round-to-nearest
+                    // accumulation chain grows linearly with its length: the taps x channel groups MMAs of a tile
+                    // are cut into `nchunk` chains, each in its own TMEM columns, which the epilogue adds up with
+                    // round-to-nearest
                     const uint64_t ad0 = tc::desc_advance(a_desc, g.first + m * 128);
                     uint64_t bd = b_desc;
                     uint32_t acc = tmem + slot * cols_per_slot;
-                    int in_chain = 0;
+                    int cnt = 0;
                     for (int o = 0; o < g.ngroups; ++o) {
                         // offset of the outer taps of this group: o enumerates (k0, k1) of the two outer axes
                         int od;
                         if (g.ngroups == 9) od = (o / 3 - 1) * g.bstride[0] + (o % 3 - 1) * g.bstride[1];
                         else if (g.ngroups == 3) od = (o - 1) * g.bstride[1];
                         else od = 0;
-                        const uint64_t ad = tc::desc_advance(ad0, od);
+                        uint64_t ad = tc::desc_advance(ad0, od);
+                        uint64_t bdg = bd;
+                        // one compact copy of the nine unrolled taps, looped over the channel groups; a chain is a
+                        // whole number of such steps
+#pragma unroll 1
+                        for (int gi = 0; gi < G; ++gi) {
 #pragma unroll
-                        for (int i = 0; i < 9; ++i) {
-                            const int dl = (i / 3 - 1) * s2 + (i % 3 - 1);
-                            tc::mma_f16(acc, tc::desc_advance(ad, dl), tc::desc_advance(bd, i * bstep), idesc,
-                                        (in_chain | i) != 0);
+                            for (int i = 0; i < 9; ++i) {
+                                const int dl = (i / 3 - 1) * s2 + (i % 3 - 1);
+                                tc::mma_f16(acc, tc::desc_advance(ad, dl), tc::desc_advance(bdg, i * G * bstep), idesc,
+                                            (cnt | i) != 0);
+                            }
+                            if (++cnt == chain_len) { cnt = 0; acc += N2; }
+                            ad = tc::desc_advance(ad, gstep);
+                            bdg = tc::desc_advance(bdg, bstep);
                         }
-                        bd = tc::desc_advance(bd, 9 * bstep);
-                        if (++in_chain == gpc) { in_chain = 0; acc += N2; }
+                        bd = tc::desc_advance(bd, 9 * G * bstep);
                     }
                     tc::mma_commit(tc::smem_u32(full + slot));
-                    last_slot = slot;
-                    last_phase = ring_phase;
                     if (++slot == nslots) { slot = 0; ring_phase ^= 1u; }
                 }
             }
@@ -405,14 +462,13 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
         const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
         int slot = 0;
         uint32_t ring_phase = 0;
-        uint32_t tile_no = 0;                                      // M tiles of this CTA so far (all units)
         for (long long unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
             long long b;
-            int org[4];
-            unit_origin(unit, b, org);
+            int org[4], pass;
+            unit_origin(unit, pass, b, org);
             float lsum = 0.f;
-            for (int m = 0; m < g.nt; ++m, ++tile_no) {
-                if ((int)(tile_no & 1u) != half) {                 // the other warp of my quarter takes this tile
+            for (int m = 0; m < g.nt; ++m) {
+                if ((slot & 1) != half) {                          // the other warp of my quarter owns this slot
                     if (++slot == nslots) { slot = 0; ring_phase ^= 1u; }
                     continue;
                 }
@@ -463,13 +519,19 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                 }
                 if (!interior) continue;
                 if (MODE == 0) {
-                    float v[8];
+                    const int Gout = g.npass * (NH / 8);            // channel groups of the output array
 #pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        v[c] = tanh_from_scaled(fmaf(lo[c], kTwoLog2e / kLoScale, fmaf(hi[c], kTwoLog2e, bias_s[c])));
-                    uint4 rh, rl;
-                    nd_records(v, rh, rl);
-                    nd_store_site<4>(a.out_rec + b * 2LL * g.Vp, g.Vp, cc, g.L, g.pstride, rh, rl);
+                    for (int q8 = 0; q8 < NH / 8; ++q8) {
+                        float v[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            v[c] = tanh_from_scaled(fmaf(lo[q8 * 8 + c], kTwoLog2e / kLoScale,
+                                                         fmaf(hi[q8 * 8 + c], kTwoLog2e, bias_s[pass * NH + q8 * 8 + c])));
+                        uint4 rh, rl;
+                        nd_records(v, rh, rl);
+                        nd_store_site<4>(a.out_rec + (b * Gout + pass * (NH / 8) + q8) * 2LL * g.Vp, g.Vp, cc, g.L,
+                                         g.pstride, rh, rl);
+                    }
                 } else {
                     const float xv = NFK_LDG(a.x + b * (long long)g.V + site);
                     float out = xv;
@@ -529,9 +591,12 @@ void nd_lattice(NdGeom& g, const nfk_lattice& lat) {
 
 // Chooses the tile of a (sample, tile) unit: trailing axes whole, one axis cut into divisors, leading axes one
 // site thick; minimises modelled cycles per output site subject to the shared-memory budget.
-bool nd_plan(NdGeom& g, int N2, int bdup, uint32_t budget) {
+bool nd_plan(NdGeom& g, int N2, int G, int npass, int bdup, uint32_t budget) {
     const int r0 = 4 - g.D;
     g.bdup = bdup;
+    g.G = G;
+    g.npass = npass;
+    g.b_bytes = (uint32_t)g.taps * G * bdup * N2 * 16;
     auto align = [](uint32_t v) { return (v + 127u) & ~127u; };
     float best = 1e30f;
     NdGeom bg = g;
@@ -571,24 +636,34 @@ bool nd_plan(NdGeom& g, int N2, int bdup, uint32_t budget) {
             c.nruns = c.nbox / c.run_rec;
             c.comp_bytes = align((uint32_t)(c.nbox + 128) * 16);
             uint32_t off = 0;
-            c.off_a = off; off += 2 * c.comp_bytes;
-            c.off_b = off; off = align(off + (uint32_t)c.taps * bdup * N2 * 16);
+            if ((long long)2 * G * c.comp_bytes + c.b_bytes > (long long)budget) continue;
+            c.off_a = off; off += 2 * G * c.comp_bytes;
+            c.off_b = off; off = align(off + c.b_bytes);
             c.off_tab = off; off = align(off + 64 * 4);
             c.off_bar = off; off = align(off + (2 * kNdMaxSlots + 1) * 8 + 64);
             c.smem_bytes = off < kNdMinSmem ? kNdMinSmem : off;      // > half an SM: one CTA per SM owns all of TMEM
             if (c.smem_bytes > budget) continue;
-            // accumulation chains of nine taps (27 for wide accumulators) on 4-D lattices, where TMEM still holds two
-            // tiles in flight; measured: the 27-tap chain of a 3-D layer is within the parity contract as it stands
-            c.nchunk = 1;
-            if (c.D == 4) c.nchunk = 9 * N2 <= 170 ? 9 : (3 * N2 <= 256 ? 3 : 1);
-            if (const char* e = getenv("NFK_ND_CHUNKS")) {
-                const int v = atoi(e);
-                if (v >= 1 && c.ngroups % v == 0 && v * N2 <= kNdTmemCols) c.nchunk = v;
+            // Accumulation chains, in steps of nine MMAs (the taps of the two innermost axes for one channel group):
+            // one step where the extra TMEM columns are cheap (narrow accumulators), at most three otherwise (measured:
+            // 27 MMAs are within the parity contract, 81 are not), as far as TMEM still holds two tiles in flight.
+            {
+                const int steps = c.ngroups * G;
+                c.nchunk = steps * N2 <= 170 ? steps : (steps + 2) / 3;
+                if (c.nchunk * N2 > 256) c.nchunk = 256 / N2 > 0 ? 256 / N2 : 1;
+                if (const char* e = getenv("NFK_ND_CHUNKS")) {
+                    const int v = atoi(e);
+                    if (v >= 1 && v * N2 <= kNdTmemCols && v <= steps) c.nchunk = v;
+                }
             }
             c.nslots = kNdTmemCols / (N2 * c.nchunk);
             if (c.nslots > kNdMaxSlots) c.nslots = kNdMaxSlots;
+            {   // a slot is owned by one issuer and one epilogue half (see the kernel): a multiple of both counts
+                const int mult = (kNdIssuers % 2) ? 2 * kNdIssuers : kNdIssuers;
+                c.nslots -= c.nslots % mult;
+                if (c.nslots < mult) continue;
+            }
             const float eff = (float)outputs / (c.nt * 128.f);
-            const float cost = c.taps * nd_mma_cycles(N2) / (128.f * eff) + 0.15f * (float)c.nbox / outputs +
+            const float cost = c.taps * G * nd_mma_cycles(N2) / (128.f * eff) + 0.15f * G * (float)c.nbox / outputs +
                                2500.f / outputs;
             if (cost < best) { best = cost; bg = c; found = true; }
         }
@@ -622,7 +697,7 @@ int nd_launch(NdArgs a, cudaStream_t st) {
     const NdProps& pr = nd_props();
     if (ensure_dynamic_smem<convnd_tc_kernel<MODE, KIND, K, INV>>(pr.max_smem) != NFK_OK) return NFK_ECUDA;
     long long grid = pr.sm_count;
-    const long long nunits = a.B * a.g.tiles_per_sample;
+    const long long nunits = a.B * a.g.tiles_per_sample * a.g.npass;
     if (grid > nunits) grid = nunits;
     convnd_tc_kernel<MODE, KIND, K, INV><<<(unsigned)grid, kNdThreads, a.g.smem_bytes, st>>>(a);
     return check_launch();
@@ -652,32 +727,39 @@ bool nd_knots_ok(int kind, int n_knots) {
     return kind == 0 || n_knots == 4 || n_knots == 5 || n_knots == 6 || n_knots == 8 || n_knots == 10;
 }
 
+// hidden layers: output channels per pass (32 at most: 64 accumulator columns)
+int nd_oc(int H) { return H < 32 ? H : 32; }
+
 struct NdWorkspace {
     long long rec_bytes, img2_bytes, img3_bytes, total;
 };
-NdWorkspace nd_workspace(const NdGeom& g, int kind, int n_knots, long long B, int bdup) {
+NdWorkspace nd_workspace(const NdGeom& g, int H, int kind, int n_knots, long long B, int bdup) {
     auto al = [](long long v) { return (v + 255) / 256 * 256; };
+    const int G = H / 8;
     NdWorkspace w;
-    w.rec_bytes = al(B * g.Vp * 32LL);
-    w.img2_bytes = al((long long)g.taps * bdup * 16 * 16);
-    w.img3_bytes = al((long long)g.taps * bdup * 2 * nd_hi_cols(kind, n_knots) * 16);
+    w.rec_bytes = al(B * G * g.Vp * 32LL);
+    w.img2_bytes = al((long long)(H / nd_oc(H)) * g.taps * G * bdup * 2 * nd_oc(H) * 16);
+    w.img3_bytes = al((long long)g.taps * G * bdup * 2 * nd_hi_cols(kind, n_knots) * 16);
     w.total = 2 * w.rec_bytes + w.img2_bytes + w.img3_bytes;
     return w;
 }
+
+bool nd_width_ok(int H) { return H == 8 || H == 16 || H == 32 || H == 64; }
 
 }  // namespace
 
 /* Workspace (bytes) nfk_fusednd_step needs for this problem, or a negative NFK_E* code when the step is outside
  * what the kernels cover (the caller then runs the layer-by-layer kernels). */
-extern "C" int64_t nfk_fusednd_workspace(nfk_lattice lat, int kind, int n_knots, int64_t B) {
-    if (!nd_lattice_ok(lat) || (kind != 0 && kind != 1) || !nd_knots_ok(kind, n_knots)) return NFK_EUNSUPPORTED;
+extern "C" int64_t nfk_fusednd_workspace(nfk_lattice lat, int H, int kind, int n_knots, int64_t B) {
+    if (!nd_lattice_ok(lat) || !nd_width_ok(H) || (kind != 0 && kind != 1) || !nd_knots_ok(kind, n_knots)) return NFK_EUNSUPPORTED;
     NdGeom g{};
     nd_lattice(g, lat);
     const int bdup = nd_bdup();
     const uint32_t budget = (uint32_t)nd_props().max_smem;
     NdGeom g2 = g, g3 = g;
-    if (!nd_plan(g2, 16, bdup, budget) || !nd_plan(g3, 2 * nd_hi_cols(kind, n_knots), bdup, budget)) return NFK_EUNSUPPORTED;
-    return nd_workspace(g, kind, n_knots, B > 0 ? B : 1, bdup).total;
+    if (!nd_plan(g2, 2 * nd_oc(H), H / 8, H / nd_oc(H), bdup, budget) ||
+        !nd_plan(g3, 2 * nd_hi_cols(kind, n_knots), H / 8, 1, bdup, budget)) return NFK_EUNSUPPORTED;
+    return nd_workspace(g, H, kind, n_knots, B > 0 ? B : 1, bdup).total;
 }
 
 extern "C" int nfk_fusednd_step(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
@@ -686,7 +768,7 @@ extern "C" int nfk_fusednd_step(const float* x, const float* w1, const float* b1
                                 const float* log_in, float* y, float* log_out, int64_t B,
                                 void* workspace, int64_t workspace_bytes, void* stream) {
     if (!x || !w1 || !w2 || !w3 || !y || !log_out || !workspace || x == y) return NFK_EINVAL;
-    if (H != 8 || (kind != 0 && kind != 1) || !nd_lattice_ok(lat)) return NFK_EUNSUPPORTED;
+    if (!nd_width_ok(H) || (kind != 0 && kind != 1) || !nd_lattice_ok(lat)) return NFK_EUNSUPPORTED;
     if (!nd_knots_ok(kind, prm.n_knots)) return NFK_EUNSUPPORTED;
     if (B <= 0) return NFK_OK;
     if (kind == 1) {
@@ -695,7 +777,7 @@ extern "C" int nfk_fusednd_step(const float* x, const float* w1, const float* b1
             (prm.extrap_right != NFK_EXTRAP_NONE && prm.extrap_right != NFK_EXTRAP_LINEAR)) return NFK_EINVAL;
     }
     cudaStream_t st = NFK_STREAM(stream);
-    const int D = lat.ndim;
+    const int D = lat.ndim, G = H / 8, OC = nd_oc(H), npass = H / OC;
     const int bdup = nd_bdup();
     const uint32_t budget = (uint32_t)nd_props().max_smem;
     NdGeom g{};
@@ -704,8 +786,14 @@ extern "C" int nfk_fusednd_step(const float* x, const float* w1, const float* b1
     g.active_val = parity == 0 ? 1 : 0;
     NdGeom g2 = g, g3 = g;
     const int NH3 = nd_hi_cols(kind, prm.n_knots);
-    if (!nd_plan(g2, 16, bdup, budget) || !nd_plan(g3, 2 * NH3, bdup, budget)) return NFK_EUNSUPPORTED;
-    const NdWorkspace ws = nd_workspace(g, kind, prm.n_knots, B, bdup);
+    if (!nd_plan(g2, 2 * OC, G, npass, bdup, budget) || !nd_plan(g3, 2 * NH3, G, 1, bdup, budget)) return NFK_EUNSUPPORTED;
+    if (getenv("NFK_ND_DEBUG")) {                      // tile plan of the two tensor-core layers (tuning aid)
+        for (const NdGeom* q : {&g2, &g3})
+            fprintf(stderr, "nfk_fusednd: T = %d %d %d %d  box %d  tiles/unit %d (span %d)  runs %d x %d rec  G %d  passes %d  "
+                    "chains %d  slots %d  smem %u B\n", q->T[0], q->T[1], q->T[2], q->T[3], q->nbox, q->nt, q->span, q->nruns,
+                    q->run_rec, q->G, q->npass, q->nchunk, q->nslots, q->smem_bytes);
+    }
+    const NdWorkspace ws = nd_workspace(g, H, kind, prm.n_knots, B, bdup);
     if (workspace_bytes < ws.total || ((uintptr_t)workspace % 256) != 0) return NFK_EINVAL;
     uint8_t* wsp = static_cast<uint8_t*>(workspace);
     uint4* h1 = reinterpret_cast<uint4*>(wsp);
@@ -714,9 +802,9 @@ extern "C" int nfk_fusednd_step(const float* x, const float* w1, const float* b1
     __half* img3 = reinterpret_cast<__half*>(wsp + 2 * ws.rec_bytes + ws.img2_bytes);
     const int P = kind == 0 ? 2 : 3 * prm.n_knots - 2;
 
-    nd_prep_weights_kernel<<<32, 256, 0, st>>>(w2, 8, g.taps, 8, bdup, img2);
+    nd_prep_weights_kernel<<<64, 256, 0, st>>>(w2, H, H, g.taps, OC, npass, bdup, img2);
     if (int e = check_launch()) return e;
-    nd_prep_weights_kernel<<<32, 256, 0, st>>>(w3, P, g.taps, NH3, bdup, img3);
+    nd_prep_weights_kernel<<<64, 256, 0, st>>>(w3, P, H, g.taps, NH3, 1, bdup, img3);
     if (int e = check_launch()) return e;
 
     NdLat nl{};
@@ -732,17 +820,22 @@ extern "C" int nfk_fusednd_step(const float* x, const float* w1, const float* b1
     const int pairs = nl.V / 2;
     const long long blocks = B * ((pairs + 255) / 256);
     if (blocks >= (1LL << 31)) return NFK_EUNSUPPORTED;
+    const dim3 grid1((unsigned)blocks, (unsigned)G);
     switch (D) {
-        case 2: nd_layer1_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(x, w1, b1, h1, nl, mask_parity, g.active_val, B); break;
-        case 3: nd_layer1_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(x, w1, b1, h1, nl, mask_parity, g.active_val, B); break;
-        default: nd_layer1_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(x, w1, b1, h1, nl, mask_parity, g.active_val, B); break;
+        case 2: nd_layer1_kernel<2><<<grid1, 256, 0, st>>>(x, w1, b1, h1, nl, mask_parity, g.active_val, B); break;
+        case 3: nd_layer1_kernel<3><<<grid1, 256, 0, st>>>(x, w1, b1, h1, nl, mask_parity, g.active_val, B); break;
+        default: nd_layer1_kernel<4><<<grid1, 256, 0, st>>>(x, w1, b1, h1, nl, mask_parity, g.active_val, B); break;
     }
     if (int e = check_launch()) return e;
 
     NdArgs a2{};
     a2.in_rec = h1; a2.out_rec = h2; a2.bimg = img2; a2.bias = b2; a2.B = B; a2.g = g2;
     a2.cfg = RqsCfg{0.f, 1.f, 0.f, 1.f, 0, 0};
-    if (int e = nd_launch<0, 0, 2, 0>(a2, st)) return e;
+    int e2;
+    if (OC == 8) e2 = nd_launch<0, 0, 8, 0>(a2, st);
+    else if (OC == 16) e2 = nd_launch<0, 0, 16, 0>(a2, st);
+    else e2 = nd_launch<0, 0, 32, 0>(a2, st);
+    if (e2) return e2;
 
     init_log_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(log_in, log_out, B);
     if (int e = check_launch()) return e;

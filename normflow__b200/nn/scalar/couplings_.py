@@ -130,8 +130,9 @@ class Coupling_(Module_):
                 and _ops.fused2d_supported(x.shape[1], x.shape[2], self._fused_knots(net)))
 
     def _fusable_nd(self, net, x):
-        """Evaluation of a 3-D / 4-D checkerboard coupling whose conditioner is ConvAct(1->8->8->P, 3^D taps,
-        tanh): layers 2 and 3 on the tensor cores, transform fused into the last one (nfk_fusednd_step).
+        """Evaluation of a checkerboard coupling whose conditioner is ConvAct(1->H->H->P, 3^D taps, tanh) on a
+        2-D .. 4-D lattice, H in {8, 16, 32, 64} (2-D with H = 8 has taken the single-kernel step before this is
+        asked): layers 2 and 3 on the tensor cores, transform fused into the last one (nfk_fusednd_step).
         NFK_FUSED_ND=0 in the environment keeps the layer-by-layer kernels (A/B tests)."""
         if os.environ.get('NFK_FUSED_ND') == '0':
             return False
@@ -142,7 +143,7 @@ class Coupling_(Module_):
         if not (isinstance(self.mask, EvenOddMask) and self.mask.mask_kwargs.get('exclude_mu') is None):
             return False
         return (x.is_cuda and self.channels_axis == 1 and x.dim() == net.conv_kwargs['conv_dim'] + 1
-                and _ops.fusednd_supported(x.shape[1:], self._fused_knots(net)))
+                and _ops.fusednd_supported(x.shape[1:], self._fused_knots(net), net.conv_kwargs['hidden_sizes'][0]))
 
     def _fusable_train(self, net, x):
         """Same structural conditions, with an autograd graph wanted: needs the tensor-core kernel.

@@ -199,10 +199,14 @@ class ConvAct(torch.nn.Sequential):
 
     @property
     def fusednd_ok(self):
-        """The same conditioner shape in 3-D / 4-D (Conv3d / Conv4d layers): the N-D tensor-core step."""
+        """The conditioner shape of the N-D tensor-core step: ConvAct(1 -> H -> H -> P) with H in {8, 16, 32, 64},
+        3^D taps, tanh, tanh, none, on a 2-D, 3-D or 4-D lattice (Conv2d / Conv3d / Conv4d layers).  (The 2-D, H = 8
+        case is also `fused2d_ok` and takes the single-kernel step.)"""
         kw = self.conv_kwargs
-        return (self._pre_act is None and kw['conv_dim'] in (3, 4) and kw['kernel_size'] == 3
-                and kw['in_channels'] == 1 and list(kw['hidden_sizes']) == [8, 8]
+        hidden = list(kw['hidden_sizes'])
+        return (self._pre_act is None and kw['conv_dim'] in (2, 3, 4) and kw['kernel_size'] == 3
+                and kw['in_channels'] == 1 and len(hidden) == 2 and hidden[0] == hidden[1]
+                and hidden[0] in (8, 16, 32, 64)
                 and tuple(self._acts) == ('tanh', 'tanh', None)
                 and kw.get('padding', 'same') == 'same' and kw.get('padding_mode') == 'circular'
                 and all(k not in kw for k in ('stride', 'dilation', 'groups')))

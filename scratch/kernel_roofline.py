@@ -1,5 +1,5 @@
 """Per-kernel roofline at BASELINE config-3 sizes: algorithmic bytes / CUDA-event time
-against the measured HBM copy peak.  Writes profiles/r01_kernel_roofline.json."""
+against the measured HBM copy peak.  Writes profiles/r02_kernel_roofline.json."""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

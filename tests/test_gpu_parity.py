@@ -889,6 +889,56 @@ def test_nd_tensor_core_step_against_oracle(shape, K, kind, B, bias, mask_parity
     assert torch.equal(y2, y) and torch.allclose(lj2, lj + 2.5, rtol=1e-6, atol=1e-4)
 
 
+@pytest.mark.parametrize("shape,H,K,kind,B,bias,inverse", [
+    ((16, 24), 16, 10, 1, 3, True, False),
+    ((16, 24), 32, 10, 1, 3, False, True),
+    ((64, 64), 64, 10, 1, 2, False, False),        # the "real dense GEMM" width of SURVEY 8d
+    ((16, 16), 64, 2, 0, 3, True, False),
+    ((8, 8, 8), 16, 8, 1, 2, True, False),
+    ((8, 8, 8), 32, 10, 1, 2, False, False),
+    ((4, 4, 4, 4), 16, 10, 1, 2, False, False),
+])
+def test_nd_tensor_core_step_hidden_widths(shape, H, K, kind, B, bias, inverse):
+    """ConvAct(1 -> H -> H -> P) for H = 16, 32, 64 (modules.py:120-159 takes any hidden_sizes): one MMA per tap
+    and group of 8 input channels, layer 2 of H = 64 in two passes of 32 output channels; float64 oracle."""
+    from normflow__b200 import _ops
+    D = len(shape)
+    g = torch.Generator('cpu').manual_seed(23)
+    P = 2 if kind == 0 else 3 * K - 2
+    k3 = (3,) * D
+    rnd = lambda *s, scale=1.0: (torch.randn(*s, generator=g, device='cpu') * scale).to(DEV)
+    fan = H * 3 ** D
+    w = [rnd(H, 1, *k3, scale=0.9 / 3 ** (D / 2)), rnd(H, H, *k3, scale=0.5 / fan ** 0.5), rnd(P, H, *k3, scale=0.5 / fan ** 0.5)]
+    b = [rnd(H, scale=0.1), rnd(H, scale=0.1), rnd(P, scale=0.1)] if bias else [None] * 3
+    x = rnd(B, *shape, scale=1.3)
+    if inverse:
+        x = x.clamp(-4.7, 4.7)
+    prm = _C.RqsParams(K, -5.0, 5.0, -5.0, 5.0, 1, 1) if kind == 1 else None
+    assert _ops.fusednd_supported(shape, K if kind == 1 else None, H)
+    for parity in (0, 1):
+        yo, lo = _oracle_single_step(x, w, b, kind, parity, K, inverse, 0)
+        with torch.no_grad():
+            y, lj = _ops.fusednd_step(x, w, b, kind, prm, 0, parity, 0, inverse)
+        close(y, yo)
+        close(lj, lo)
+
+
+def test_wide_conditioner_takes_the_tensor_core_path(monkeypatch):
+    """A 2-D coupling with hidden_sizes [32, 32] evaluates through nfk_fusednd_step, not the layer-by-layer kernels."""
+    model = _config_model((16, 16), [('affine', 2), ('rqs', 2)], hidden=(32, 32), seed=3)
+    x = model.prior.sample(5)
+    out = {}
+    for flag in ('1', '0'):
+        monkeypatch.setenv('NFK_FUSED_ND', flag)
+        with torch.no_grad():
+            out[flag] = model.net_(x)
+    assert not torch.equal(out['1'][0], out['0'][0])
+    assert torch.allclose(out['1'][0], out['0'][0], atol=3e-5, rtol=3e-5)
+    yr, lr = _oracle_flow(model, x.cpu().numpy())
+    close(out['1'][0], yr)
+    close(out['1'][1], lr)
+
+
 def test_nd_step_is_the_path_taken_in_3d_and_4d(monkeypatch):
     """Evaluation of a 3-D / 4-D coupling must go through nfk_fusednd_step (same numbers as the layer-by-layer
     kernels up to float32 rounding, but not bit-identical)."""
