@@ -139,8 +139,9 @@ __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs 
         return u;
     };
 
-    if (warp == kTcComputeWarps) {
-        // =============================== MMA warp =========================================
+    if (warp >= kTcComputeWarps) {
+        // =============================== MMA warps ========================================
+        const int iw = warp - kTcComputeWarps;                     // this issuer takes tiles iw, iw + kTcIssuers, ...
         const bool lead = tc::elect_one();
         const uint32_t idesc2 = tc::make_idesc(0, 128, 16), idesc3 = tc::make_idesc(0, 128, N3);
         const uint64_t a1_desc = tc::make_desc(tc::smem_u32(h1), g.h1_comp_bytes, 128);
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs 
         const uint64_t b3_desc = tc::make_desc(tc::smem_u32(B3), N3 * 16, 128);
         int tn = 0;
         auto stamp = [&](int) {
-            if (a.trace && blockIdx.x == 0 && lead && tn < 4000) a.trace[4096 + tn++] = clock64();
+            if (a.trace && blockIdx.x == 0 && lead && iw == 0 && tn < 4000) a.trace[4096 + tn++] = clock64();
         };
         for (Unit u{blockIdx.x, 0}; u.b < a.B; u = next_unit(u)) {
             const int r0 = u.r0, rows = L0 - r0 < Rr ? L0 - r0 : Rr;
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs 
             tc::fence_after_sync();
             stamp(1);
             if (lead) {
-                for (int j = 0; j < t2; ++j) {
+                for (int j = iw; j < t2; j += kTcIssuers) {
 #pragma unroll
                     for (int t = 0; t < 9; ++t) {
                         const int delta = (t / 3 - 1) * WS + (t % 3 - 1);
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) fused2d_tc_kernel(const TcArgs 
             tc::fence_after_sync();
             stamp(3);
             if (lead) {
-                for (int k = 0; k < t3; ++k) {
+                for (int k = iw; k < t3; k += kTcIssuers) {
 #pragma unroll
                     for (int t = 0; t < 9; ++t) {
                         const int sh = plin + (t / 3 - 1) * WS + (t % 3 - 1);   // parity and offset of the source

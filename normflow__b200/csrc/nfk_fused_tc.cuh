@@ -40,7 +40,15 @@ namespace nfk {
 constexpr int kTcComputeWarps = NFK_TC_COMPUTE_WARPS;          // multiple of 4 (one warp per TMEM lane quarter)
 constexpr int kTcSets = kTcComputeWarps / 4;                   // tile sets working in parallel
 constexpr int kTcComputeThreads = 32 * kTcComputeWarps;
-constexpr int kTcThreads = kTcComputeThreads + 32;             // + the MMA warp (the last one)
+#ifndef NFK_TC_ISSUERS
+#define NFK_TC_ISSUERS 1
+#endif
+// MMA-issuing warps (the last ones; one elected thread each, M tiles dealt round robin).  Measured at the BASELINE
+// geometry (B = 16384, 64 x 64, K = 10): 1 issuer 2.834 ms, 2 issuers 2.884 ms, 3 issuers 3.64 ms (register cap):
+// this kernel is bound by the shared-memory data pipe (MMA operand reads + TMEM / LDS / STS traffic, 79 % busy),
+// not by the issuing thread -- unlike the N-D kernels (nfk_convnd_tc.cu), whose single issuer was the bottleneck.
+constexpr int kTcIssuers = NFK_TC_ISSUERS;
+constexpr int kTcThreads = kTcComputeThreads + 32 * kTcIssuers;
 constexpr int kTcTmemCols = 256;            // per CTA: two CTAs share the SM's 512 columns
 constexpr int kTcGuard = 8;                 // 16-byte records of slack in front of every plane
 constexpr float kLoScale = 2048.f;          // weights' lo part is stored times 2^11
