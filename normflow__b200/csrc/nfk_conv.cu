@@ -431,6 +431,238 @@ __global__ void __launch_bounds__(256) conv_bwd_weight_kernel(ConvWArgs a) {
     }
 }
 
+// The same arithmetic with the tap blocks dealt to the WARPS of a CTA instead of to grid.y: every warp of a CTA
+// walks the same sites, so the d loss / d pre-activation and the input values of a site come from HBM / L2 once per
+// block of output channels (and are L1 hits for the other warps) instead of once per (output block, tap block) --
+// 63 passes over the data for a 3-D 8 -> 28 layer became 7 (the kernel was bound by those re-reads: 74 % of a 3-D
+// training step).  A warp owns its accumulators outright: warp reduction, then atomics.
+template <int CO_B, int CI_B, int T_B>
+__global__ void __launch_bounds__(32 * 14) conv_bwd_weight_warptap_kernel(ConvWArgs a, int tb_per_cta) {
+    constexpr int NACC = CO_B * CI_B * T_B;
+    int y = blockIdx.y;
+    const int tgroup = y % a.n_tb; y /= a.n_tb;               // here n_tb = tap-block groups per CTA row
+    const int cib = y % a.n_cib; y /= a.n_cib;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int tb = tgroup * tb_per_cta + wid;
+    const int co0 = y * CO_B, ci0 = cib * CI_B, t0 = tb * T_B;
+    if (t0 >= a.T) return;
+    const bool do_bias = a.gbias != nullptr && cib == 0 && tb == 0;
+
+    float acc[NACC];
+    float accb[CO_B];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < CO_B; ++i) accb[i] = 0.f;
+
+    for (int64_t g = (int64_t)blockIdx.x * 32 + lane; g < a.BV; g += (int64_t)gridDim.x * 32) {
+        const int64_t b = g / a.V;
+        const int s = (int)(g - b * a.V);
+        float gv[CO_B];
+#pragma unroll
+        for (int co = 0; co < CO_B; ++co)
+            gv[co] = (co0 + co < a.Co) ? __ldg(a.gpre + (b * a.Co + co0 + co) * (int64_t)a.V + s) : 0.f;
+        if (do_bias) {
+#pragma unroll
+            for (int co = 0; co < CO_B; ++co) accb[co] += gv[co];
+        }
+        int c[4];
+        site_coords(a.lat, s, c);
+        const float* in_b = a.in + b * a.Ci * (int64_t)a.V;
+#pragma unroll
+        for (int t = 0; t < T_B; ++t) {
+            if (t0 + t >= a.T) break;
+            const int n = tap_neighbor(a.lat, s, c, t0 + t, a.ksize);
+            const bool keep = !a.in_mask || __ldg(a.in_mask + n) == (uint8_t)a.in_keep;
+#pragma unroll
+            for (int ci = 0; ci < CI_B; ++ci) {
+                const float v = (keep && ci0 + ci < a.Ci) ? __ldg(in_b + (int64_t)(ci0 + ci) * a.V + n) : 0.f;
+#pragma unroll
+                for (int co = 0; co < CO_B; ++co)
+                    acc[(co * CI_B + ci) * T_B + t] = fmaf(gv[co], v, acc[(co * CI_B + ci) * T_B + t]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) {
+        const float v = warp_sum(acc[i]);
+        const int t = i % T_B, ci = (i / T_B) % CI_B, co = i / (T_B * CI_B);
+        if (lane == 0 && co0 + co < a.Co && ci0 + ci < a.Ci && t0 + t < a.T)
+            atomicAdd(a.gw + ((int64_t)(co0 + co) * a.Ci + ci0 + ci) * a.T + t0 + t, v);
+    }
+    if (do_bias) {
+#pragma unroll
+        for (int i = 0; i < CO_B; ++i) {
+            const float v = warp_sum(accb[i]);
+            if (lane == 0 && co0 + i < a.Co) atomicAdd(a.gbias + co0 + i, v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- weight gradient, 3-D / 4-D, 8 input channels
+// gw[co][ci][t] += sum_{b, s} gpre[b][co][s] in[b][ci][nbr(s, t)]  for the ConvNd / Conv4d layers (convNd.py:84-127,
+// adjoint) with 3^D taps.  The generic kernel above spends ~100 index instructions per (site, tap) on periodic
+// neighbours and re-reads the data once per (output block, tap block); it was 74 % of a 3-D training step.  Here a
+// persistent CTA stages a strip of one (y, x) plane of a sample -- the input with its one-site halo in every
+// direction (3^(D-2) planes x 8 channels, periodic wrap resolved while loading) and the strip of gpre for a block of
+// output channels -- in shared memory; THREAD (t, ci) owns tap t and input channel ci for good, so its input address
+// is a constant offset plus the site index, keeps CO_B accumulators per output block in registers across all the
+// units it walks, and issues one atomic per weight at the end.  Per four sites: 4 LDS (conflict-free: the channel
+// plane stride is 4 mod 32, taps of a warp differ by 1) + CO_B broadcast LDS.128 + 4 CO_B FMAs.
+__device__ __forceinline__ void wg_cp_async4(float* dst, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void wg_cp_async16(float* dst, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
+struct WgNdArgs {
+    const float* in;        // [B][8][V]
+    const float* gpre;      // [B][Co][V]
+    float* gw;              // [Co][8][T]
+    float* gbias;           // [Co] or NULL
+    int D, Co, T, nplanes;  // nplanes = 3^(D-2)
+    int O0, O1, Y, X;       // lattice extents, right-aligned (O0 = O1 = 1 in 2-D, O0 = 1 in 3-D)
+    int R;                  // rows of a strip (divides Y)
+    long long B;
+};
+
+template <int CO_B, int NCB>
+__global__ void __launch_bounds__(672) conv_wgrad_nd_tile_kernel(const WgNdArgs a) {
+    extern __shared__ __align__(16) float wsm[];
+    const int XS = a.X + 2, PSZ = (a.R + 2) * XS;            // padded row / channel-plane size of the input strip
+    float* in_s = wsm;                                        // [nplanes][8][R + 2][X + 2]
+    float* g_s = wsm + a.nplanes * 8 * PSZ;                   // [CO_B][R][X]
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = blockDim.x >> 5;
+    const int t = tid >> 3, ci = tid & 7;
+    const bool worker = t < a.T;
+    const int pt = t / 9, ky = (t / 3) % 3, kx = t % 3;
+    const int base = (pt * 8 + ci) * PSZ + ky * XS + kx;
+    const int V = a.O0 * a.O1 * a.Y * a.X, PL = a.Y * a.X;
+    const int strips = a.Y / a.R;
+    const long long units = a.B * a.O0 * a.O1 * strips;
+    float acc[NCB][CO_B];
+    float bsum[NCB][2];                  // bias sums of channels wid and wid + nwarps of a block (CO_B <= 2 nwarps)
+#pragma unroll
+    for (int cb = 0; cb < NCB; ++cb) {
+        bsum[cb][0] = bsum[cb][1] = 0.f;
+#pragma unroll
+        for (int c = 0; c < CO_B; ++c) acc[cb][c] = 0.f;
+    }
+    for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+        long long rem = u;
+        const int strip = (int)(rem % strips); rem /= strips;
+        const int o1 = (int)(rem % a.O1); rem /= a.O1;
+        const int o0 = (int)(rem % a.O0);
+        const long long b = rem / a.O0;
+        const int y0 = strip * a.R;
+        __syncthreads();                                      // the previous unit's readers are done
+        // ---- input strip with halo: in_s[p][c][j][i] = in[b][c][o + dp][y0 + j - 1][i - 1] (periodic)
+        const int total_in = a.nplanes * 8 * PSZ;
+        for (int e = tid; e < total_in; e += blockDim.x) {
+            const int i = e % XS;
+            int r = e / XS;
+            const int j = r % (a.R + 2); r /= (a.R + 2);
+            const int c = r & 7, p = r >> 3;
+            int q0 = o0, q1 = o1;
+            if (a.D == 4) { q0 += p / 3 - 1; q1 += p % 3 - 1; }
+            else if (a.D == 3) { q1 += p - 1; }
+            q0 += q0 < 0 ? a.O0 : 0; q0 -= q0 >= a.O0 ? a.O0 : 0;
+            q1 += q1 < 0 ? a.O1 : 0; q1 -= q1 >= a.O1 ? a.O1 : 0;
+            int yy = y0 + j - 1, xx = i - 1;
+            yy += yy < 0 ? a.Y : 0; yy -= yy >= a.Y ? a.Y : 0;
+            xx += xx < 0 ? a.X : 0; xx -= xx >= a.X ? a.X : 0;
+            // asynchronous 4-byte copies: with seven warps per SM a register-staged load would pay the memory latency
+            // once per element (the kernel was bound by exactly that: 200 k of its 560 k cycles per unit)
+            wg_cp_async4(in_s + e, a.in + (b * 8 + c) * (long long)V + ((long long)(q0 * a.O1 + q1) * a.Y + yy) * a.X + xx);
+        }
+        const long long plane0 = ((long long)(o0 * a.O1 + o1) * a.Y + y0) * a.X;       // first site of the strip
+#pragma unroll
+        for (int cb = 0; cb < NCB; ++cb) {
+            if (cb * CO_B >= a.Co) break;
+            if (cb > 0) __syncthreads();                      // g_s readers of the previous block are done
+            const int rowq = (a.R * a.X) >> 2, total_g4 = CO_B * rowq;      // 16-byte chunks
+            for (int e = tid; e < total_g4; e += blockDim.x) {
+                const int c = e / rowq, k = (e - c * rowq) << 2;
+                const int co = cb * CO_B + c;
+                float* dst = g_s + c * a.R * a.X + k;
+                if (co < a.Co) wg_cp_async16(dst, a.gpre + (b * a.Co + co) * (long long)V + plane0 + k);
+                else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncthreads();
+            if (a.gbias) {                                    // bias gradient: warp w sums channel w (+ nwarps, ...)
+#pragma unroll
+                for (int k2 = 0; k2 < 2; ++k2) {
+                    const int c = wid + k2 * nwarps;
+                    if (c < CO_B) {
+                        float v = 0.f;
+                        for (int k = lane; k < a.R * a.X; k += 32) v += g_s[c * a.R * a.X + k];
+                        bsum[cb][k2] += warp_sum(v);
+                    }
+                }
+            }
+            if (worker) {
+                const int RX = a.R * a.X;
+                for (int y = 0; y < a.R; ++y) {
+                    const float* ip = in_s + base + y * XS;
+                    const float* gp = g_s + y * a.X;
+#pragma unroll 2
+                    for (int x4 = 0; x4 < a.X; x4 += 4) {
+                        const float i0 = ip[x4], i1 = ip[x4 + 1], i2 = ip[x4 + 2], i3 = ip[x4 + 3];
+#pragma unroll
+                        for (int c = 0; c < CO_B; ++c) {
+                            const float4 gv = *reinterpret_cast<const float4*>(gp + c * RX + x4);
+                            acc[cb][c] = fmaf(gv.x, i0, fmaf(gv.y, i1, fmaf(gv.z, i2, fmaf(gv.w, i3, acc[cb][c]))));
+                        }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int cb = 0; cb < NCB; ++cb) {
+#pragma unroll
+        for (int c = 0; c < CO_B; ++c) {
+            const int co = cb * CO_B + c;
+            if (worker && co < a.Co) atomicAdd(a.gw + ((long long)co * 8 + ci) * a.T + t, acc[cb][c]);
+        }
+#pragma unroll
+        for (int k2 = 0; k2 < 2; ++k2) {
+            const int c = wid + k2 * nwarps;
+            if (a.gbias && lane == 0 && c < CO_B && cb * CO_B + c < a.Co) atomicAdd(a.gbias + cb * CO_B + c, bsum[cb][k2]);
+        }
+    }
+}
+
+template <int CO_B, int NCB>
+static int wgrad_nd_tile_launch(WgNdArgs a, cudaStream_t st) {
+    int dev = 0, sm = 148, max_smem = 227 * 1024;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    // the tallest strip that still lets two CTAs share an SM (seven warps alone cannot hide the shared-memory
+    // latency of the inner loop); the tallest that fits at all otherwise
+    int best = 0, best2 = 0;
+    for (int R = 1; R <= a.Y; ++R) {
+        if (a.Y % R) continue;
+        const size_t need = ((size_t)a.nplanes * 8 * (R + 2) * (a.X + 2) + (size_t)CO_B * R * a.X) * 4;
+        if (need <= (size_t)max_smem - 1024) best = R;
+        if (need <= ((size_t)max_smem + 1024) / 2 - 1024 && a.T * 8 <= 512) best2 = R;
+    }
+    if (best2 >= 4) best = best2;
+    if (best == 0) return NFK_EUNSUPPORTED;
+    a.R = best;
+    const size_t smem = ((size_t)a.nplanes * 8 * (best + 2) * (a.X + 2) + (size_t)CO_B * best * a.X) * 4;
+    if (ensure_dynamic_smem<conv_wgrad_nd_tile_kernel<CO_B, NCB>>(max_smem) != NFK_OK) return NFK_ECUDA;
+    const long long units = a.B * a.O0 * a.O1 * (a.Y / best);
+    const int threads = (a.T * 8 + 31) / 32 * 32;
+    const long long ctas = (long long)sm * (best == best2 ? 2 : 1);
+    const long long grid = units < ctas ? units : ctas;
+    conv_wgrad_nd_tile_kernel<CO_B, NCB><<<(unsigned)grid, threads, smem, st>>>(a);
+    return check_launch();
+}
+
 // ---------------------------------------------------------------- weight gradient, 2-D 3x3
 // The ConvAct layers of the BASELINE configs: 2-D lattice, 3x3 taps, Ci <= 8.  A persistent CTA
 // (blockIdx.y = block of CO_B output channels) walks samples in strips of R rows held in shared
@@ -958,6 +1190,31 @@ static int conv_bwd_weight_impl(const float* in, const uint8_t* in_mask, int in_
     constexpr int TB = 3;
     a.n_tb = (T + TB - 1) / TB;
     cudaStream_t st = NFK_STREAM(stream);
+    if ((lat.ndim == 3 || lat.ndim == 4) && ksize == 3 && Ci == 8 && Co <= 28 && !in_mask &&
+        lat.shape[lat.ndim - 1] % 4 == 0 && ((uintptr_t)gpre % 16) == 0) {
+        WgNdArgs t{};
+        t.in = in; t.gpre = gpre; t.gw = gw; t.gbias = gbias;
+        t.D = lat.ndim; t.Co = Co; t.T = T; t.nplanes = T / 9; t.B = B;
+        t.O0 = lat.ndim == 4 ? lat.shape[0] : 1;
+        t.O1 = lat.shape[lat.ndim - 3];
+        t.Y = lat.shape[lat.ndim - 2];
+        t.X = lat.shape[lat.ndim - 1];
+        const int rc = Co <= 8 ? wgrad_nd_tile_launch<8, 1>(t, st) : wgrad_nd_tile_launch<7, 4>(t, st);
+        if (rc != NFK_EUNSUPPORTED) return rc;
+    }
+    if (T >= 27 && Ci >= 8 && a.BV >= 32 * 148) {
+        // 3-D / 4-D layers with 8+ input channels: tap blocks dealt to the warps of a CTA (data read once per block
+        // of output channels).  9 tap blocks of 3 (27 taps) per CTA; 81 taps take three such rows of CTAs.
+        const int tb_per_cta = a.n_tb < 9 ? a.n_tb : 9;
+        const int tgroups = (a.n_tb + tb_per_cta - 1) / tb_per_cta;
+        a.n_tb = tgroups;
+        a.n_cib = (Ci + 7) / 8;
+        int64_t want32 = (a.BV + 31) / 32;
+        const int gx32 = (int)(want32 < 148 * 2 ? want32 : 148 * 2);
+        const dim3 grid(gx32, ((Co + 3) / 4) * a.n_cib * tgroups);
+        conv_bwd_weight_warptap_kernel<4, 8, TB><<<grid, 32 * tb_per_cta, 0, st>>>(a, tb_per_cta);
+        return check_launch();
+    }
     // enough CTAs to fill 148 SMs a few times over, never more than the work
     int64_t want = (a.BV + 255) / 256;
     const int gx = (int)(want < 148 * 4 ? want : 148 * 4);

@@ -250,6 +250,42 @@ def test_convact_golden(tag, shape, hidden, P, bias):
         close_grad(gr, g[f"{tag}_grad_{name}"], tol=2e-5)
 
 
+@pytest.mark.parametrize("shape,Co,B,bias", [((8, 8, 8), 28, 3, True), ((32, 32, 32), 8, 2, False), ((6, 4, 8), 8, 2, True),
+                                             ((4, 4, 4, 4), 28, 2, True), ((16, 16, 16, 16), 2, 1, False)])
+def test_nd_weight_gradient_tile_kernel(shape, Co, B, bias):
+    """Weight / bias gradient of a 3-D / 4-D circular convolution with 8 input channels (the tiled kernel
+    conv_wgrad_nd_tile_kernel behind nfk_conv_circ_bwd_weight) against float64 autograd of the same convolution
+    written with torch ops (circular padding by concatenation + conv3d / summed conv3d slices)."""
+    D = len(shape)
+    g = torch.Generator('cpu').manual_seed(31)
+    rnd = lambda *s: torch.randn(*s, generator=g, dtype=torch.float64, device='cpu')
+    x = rnd(B, 8, *shape)
+    w = (rnd(Co, 8, *(3,) * D) * 0.1).requires_grad_(True)
+    bvec = (rnd(Co) * 0.1).requires_grad_(True) if bias else None
+    gout = rnd(B, Co, *shape)
+    # float64 reference: out[b, o, s] = sum_{i, k} w[o, i, k] x[b, i, s + k - 1]  (periodic)
+    out = torch.zeros(B, Co, *shape, dtype=torch.float64, device='cpu')
+    import itertools
+    for k in itertools.product(range(3), repeat=D):
+        shifted = torch.roll(x, shifts=[1 - kk for kk in k], dims=list(range(2, 2 + D)))
+        out = out + torch.einsum('oi,bi...->bo...', w[(slice(None), slice(None)) + k], shifted)
+    if bias:
+        out = out + bvec.reshape(1, Co, *(1,) * D)
+    grads = torch.autograd.grad((out * gout).sum(), [w] + ([bvec] if bias else []))
+    from normflow__b200 import _ops
+    conv = _ops.conv_stack(x.float().to(DEV).requires_grad_(False), [w.detach().float().to(DEV).requires_grad_(True)],
+                           [bvec.detach().float().to(DEV).requires_grad_(True) if bias else None], [None], 3)
+    close(conv, out.detach(), tol=2e-5)
+    # gradient through the package's autograd node
+    wd = w.detach().float().to(DEV).requires_grad_(True)
+    bd = bvec.detach().float().to(DEV).requires_grad_(True) if bias else None
+    o2 = _ops.conv_stack(x.float().to(DEV), [wd], [bd], [None], 3)
+    got = torch.autograd.grad((o2 * gout.float().to(DEV)).sum(), [wd] + ([bd] if bias else []))
+    close_grad(got[0], grads[0].numpy(), tol=2e-5)
+    if bias:
+        close_grad(got[1], grads[1].numpy(), tol=2e-5)
+
+
 def test_convact_unfused_path_equals_fused():
     torch.manual_seed(3)
     fused = ConvAct(1, 2, 3, hidden_sizes=[4], acts=['tanh', None], bias=True).to(DEV)
