@@ -319,6 +319,16 @@ int nfk_fusednd_step(const float* x, const float* w1, const float* b1, const flo
                      const float* log_in, float* y, float* log_out, int64_t B,
                      void* workspace, int64_t workspace_bytes, void* stream);
 
+/* The N-D step as the forward pass of TRAINING (Fitter.step, _normflowcore.py:275-294): additionally stores the
+ * post-activation hidden layers h1, h2 [B][H][V] and the conditioner output out [B][P][V] (defined at the active
+ * sites only) in float32 channel-major layout for the gradient kernels.  Forward direction only.                */
+int nfk_fusednd_step_train(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                           const float* w3, const float* b3, int H, int kind, nfk_rqs_params prm,
+                           nfk_lattice lat, int mask_parity, int parity,
+                           const float* log_in, float* y, float* log_out,
+                           float* h1, float* h2, float* out, int64_t B,
+                           void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------- PSD block (spectral part) ---
  * PSDBlock_ / FFTNet_ (psd_.py:25-40, fftflow_.py:121-131,167-180): the real-to-complex
  * and complex-to-real transforms are cuFFT calls made by the host package; these entries

@@ -71,6 +71,8 @@ _SIGNATURES = {
                                c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_l, c_f],
     "nfk_fusednd_step": [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, RqsParams, Lattice, c_i, c_i, c_i,
                          c_f, c_f, c_f, c_l, c_f, c_l, c_f],
+    "nfk_fusednd_step_train": [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, RqsParams, Lattice, c_i, c_i,
+                               c_f, c_f, c_f, c_f, c_f, c_f, c_l, c_f, c_l, c_f],
     "nfk_psd_weights_fwd": [c_f, c_l, c_i, c_i, c_f, c_f, c_f],
     "nfk_psd_weights_bwd": [c_f, c_f, c_f, c_f, c_l, c_i, c_i, c_f, c_f],
     "nfk_psd_scale": [c_f, c_f, c_f, c_fl, c_f, c_l, c_l, c_f],

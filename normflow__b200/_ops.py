@@ -846,6 +846,73 @@ def fusednd_step(x, weights, biases, kind, prm, mask_parity, parity, log0=0, inv
     return y, log_out
 
 
+class _FusedNdStepTrain(torch.autograd.Function):
+    """Training forward of an atomic coupling step on a 2-D .. 4-D lattice through the N-D tensor-core kernels
+    (nfk_fusednd_step_train keeps the hidden layers and the conditioner output); backward through the transform's
+    VJP kernel and the convolution gradient kernels, as _FusedStepTrain does in 2-D."""
+
+    @staticmethod
+    @_native
+    def forward(ctx, x, log_in, mask, kind, prm, mask_parity, parity, n_bias, *params):
+        w, b = params[:3], params[3:]
+        B, shape = x.shape[0], tuple(x.shape[1:])
+        H, P = w[0].shape[0], w[2].shape[0]
+        lat = _C.lattice(shape)
+        need = int(lib().nfk_fusednd_workspace(lat, int(H), int(kind), prm.n_knots, B))
+        if need <= 0:
+            check(need if need < 0 else _C.EUNSUPPORTED, "fusednd_workspace")
+        y = torch.empty_like(x)
+        log_out = torch.empty((B,), dtype=torch.float32, device=x.device)
+        h1 = torch.empty((B, H) + shape, dtype=torch.float32, device=x.device)
+        h2 = torch.empty((B, H) + shape, dtype=torch.float32, device=x.device)
+        out = torch.empty((B, P) + shape, dtype=torch.float32, device=x.device)
+        workspace = torch.empty((need,), dtype=torch.uint8, device=x.device)
+        with _C.timed("fusednd_step_train"):
+            check(lib().nfk_fusednd_step_train(dev(x), dev(w[0]), dev(b[0]), dev(w[1]), dev(b[1]), dev(w[2]), dev(b[2]),
+                                               int(H), kind, prm, lat, mask_parity, parity, dev(log_in), dev(y),
+                                               dev(log_out), dev(h1), dev(h2), dev(out), B,
+                                               dev(workspace, torch.uint8), need, stream()), "fusednd_step_train")
+        ctx.save_for_backward(x, h1, h2, out, mask, *w)
+        ctx.cfg = (kind, prm, parity, log_in is not None, [t is not None for t in b])
+        return y, log_out
+
+    @staticmethod
+    @_native
+    def backward(ctx, gy, glog):
+        x, h1, h2, out, mask, *w = ctx.saved_tensors
+        kind, prm, parity, has_log, has_bias = ctx.cfg
+        B, shape = x.shape[0], tuple(x.shape[1:])
+        V = x[0].numel()
+        gy, glog = _f32c(gy, "gy"), _f32c(glog, "glog")
+        gx, gout = torch.empty_like(x), torch.empty_like(out)
+        if kind == 1:
+            check(lib().nfk_rqs_bwd(dev(x), dev(out), dev(mask, torch.uint8), parity, _C.FROZEN_COPY, prm, dev(gy),
+                                    dev(glog), dev(gx), dev(gout), B, V, stream()), "rqs_bwd")
+        else:
+            check(lib().nfk_affine_bwd(dev(x), dev(out), dev(mask, torch.uint8), parity, _C.FROZEN_COPY, dev(gy),
+                                       dev(glog), dev(gx), dev(gout), B, V, stream()), "affine_bwd")
+        frozen_keep = 0 if parity == 0 else 1          # the conditioner saw the frozen partition only
+        acts = (_C.ACT['tanh'], _C.ACT['tanh'], _C.ACT[None])
+        gws, gbs, gin = _conv_stack_backward([x.unsqueeze(1), h1, h2], w, has_bias, acts, 3, shape, mask,
+                                             frozen_keep, gout, ctx.needs_input_grad[0])
+        if gin is not None:
+            gx = gx + gin.reshape(x.shape)
+        return (gx, glog if has_log else None, None, None, None, None, None, None, *gws, *gbs)
+
+
+@_native
+def fusednd_step_train(x, weights, biases, kind, prm, mask, mask_parity, parity, log0=0):
+    """Differentiable atomic coupling step on a 2-D .. 4-D lattice: tensor-core forward, kernel-by-kernel backward."""
+    x = _f32c(x, "x")
+    log_in = as_log(log0, x)
+    w = [_f32c(t, "conv weight") for t in weights]
+    b = [None if t is None else _f32c(t, "conv bias") for t in biases]
+    if prm is None:
+        prm = _C.RqsParams(2, 0.0, 1.0, 0.0, 1.0, 0, 0)
+    return _FusedNdStepTrain.apply(x, log_in, _mask_u8(mask), int(kind), prm, int(mask_parity), int(parity),
+                                   sum(t is not None for t in b), *w, *b)
+
+
 class _FusedStepTrain(torch.autograd.Function):
     """Forward of a training step through the tensor-core fused kernel (which also stores the
     hidden layers and the conditioner output); backward through the transform's VJP kernel and

@@ -635,6 +635,122 @@ __global__ void __launch_bounds__(672) conv_wgrad_nd_tile_kernel(const WgNdArgs 
     }
 }
 
+// First layer of a conditioner (one input channel, optionally seen through the checkerboard mask; Co = 8 per block):
+// the same staging, THREAD (t, co) owns weight (co, t).  Per four sites: 4 LDS of the input (the eight lanes of a tap
+// read the same words) + one LDS.128 of gpre (channel stride padded by 4 floats: the eight channels of a tap sit on
+// different banks) + 4 FMAs.
+struct WgNd1Args {
+    const float* in;        // [B][1][V]
+    const uint8_t* in_mask; // [V] or NULL
+    int in_keep;
+    const float* gpre;      // [B][Co][V]
+    float* gw;              // [Co][1][T]
+    float* gbias;
+    int D, Co, T, nplanes;
+    int O0, O1, Y, X, R;
+    long long B;
+};
+
+__global__ void __launch_bounds__(672) conv_wgrad_nd_first_kernel(const WgNd1Args a) {
+    extern __shared__ __align__(16) float wsm[];
+    const int XS = a.X + 2, PSZ = (a.R + 2) * XS, RX = a.R * a.X, GS = RX + 4;
+    float* in_s = wsm;                                        // [nplanes][R + 2][X + 2]
+    float* g_s = wsm + ((a.nplanes * PSZ + 3) & ~3);          // [8][R X + 4]
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = blockDim.x >> 5;
+    const int t = tid >> 3, co = tid & 7;
+    const bool worker = t < a.T;
+    const int pt = t / 9, ky = (t / 3) % 3, kx = t % 3;
+    const int base = pt * PSZ + ky * XS + kx;
+    const int V = a.O0 * a.O1 * a.Y * a.X;
+    const int strips = a.Y / a.R;
+    const long long units = a.B * a.O0 * a.O1 * strips;
+    const int nblocks = (a.Co + 7) >> 3;
+    for (int cb = 0; cb < nblocks; ++cb) {                    // (wide first layers: one pass over the data per 8 channels)
+        float acc = 0.f, bsum = 0.f;
+        for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+            long long rem = u;
+            const int strip = (int)(rem % strips); rem /= strips;
+            const int o1 = (int)(rem % a.O1); rem /= a.O1;
+            const int o0 = (int)(rem % a.O0);
+            const long long b = rem / a.O0;
+            const int y0 = strip * a.R;
+            __syncthreads();
+            for (int e = tid; e < a.nplanes * PSZ; e += blockDim.x) {
+                const int i = e % XS;
+                int r = e / XS;
+                const int j = r % (a.R + 2), p = r / (a.R + 2);
+                int q0 = o0, q1 = o1;
+                if (a.D == 4) { q0 += p / 3 - 1; q1 += p % 3 - 1; }
+                else if (a.D == 3) { q1 += p - 1; }
+                q0 += q0 < 0 ? a.O0 : 0; q0 -= q0 >= a.O0 ? a.O0 : 0;
+                q1 += q1 < 0 ? a.O1 : 0; q1 -= q1 >= a.O1 ? a.O1 : 0;
+                int yy = y0 + j - 1, xx = i - 1;
+                yy += yy < 0 ? a.Y : 0; yy -= yy >= a.Y ? a.Y : 0;
+                xx += xx < 0 ? a.X : 0; xx -= xx >= a.X ? a.X : 0;
+                const int n = ((q0 * a.O1 + q1) * a.Y + yy) * a.X + xx;
+                const bool keep = !a.in_mask || __ldg(a.in_mask + n) == (uint8_t)a.in_keep;
+                if (keep) wg_cp_async4(in_s + e, a.in + b * (long long)V + n);
+                else in_s[e] = 0.f;
+            }
+            const long long plane0 = ((long long)(o0 * a.O1 + o1) * a.Y + y0) * a.X;
+            const int rowq = RX >> 2;
+            for (int e = tid; e < 8 * rowq; e += blockDim.x) {
+                const int c = e / rowq, k = (e - c * rowq) << 2;
+                const int cc = cb * 8 + c;
+                float* dst = g_s + c * GS + k;
+                if (cc < a.Co) wg_cp_async16(dst, a.gpre + (b * a.Co + cc) * (long long)V + plane0 + k);
+                else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncthreads();
+            if (a.gbias && wid < 8) {                         // nwarps >= 7: channel 7 falls to warp 0 as well
+                for (int c = wid; c < 8; c += nwarps) {
+                    float v = 0.f;
+                    for (int k = lane; k < RX; k += 32) v += g_s[c * GS + k];
+                    v = warp_sum(v);
+                    if (c == wid) bsum += v;
+                    else if (lane == 0 && cb * 8 + c < a.Co) atomicAdd(a.gbias + cb * 8 + c, v);
+                }
+            }
+            if (worker) {
+                for (int y = 0; y < a.R; ++y) {
+                    const float* ip = in_s + base + y * XS;
+                    const float* gp = g_s + co * GS + y * a.X;
+#pragma unroll 2
+                    for (int x4 = 0; x4 < a.X; x4 += 4) {
+                        const float4 gv = *reinterpret_cast<const float4*>(gp + x4);
+                        acc = fmaf(gv.x, ip[x4], fmaf(gv.y, ip[x4 + 1], fmaf(gv.z, ip[x4 + 2], fmaf(gv.w, ip[x4 + 3], acc))));
+                    }
+                }
+            }
+        }
+        if (worker && cb * 8 + co < a.Co) atomicAdd(a.gw + (long long)(cb * 8 + co) * a.T + t, acc);
+        if (a.gbias && lane == 0 && wid < 8 && cb * 8 + wid < a.Co) atomicAdd(a.gbias + cb * 8 + wid, bsum);
+    }
+}
+
+static int wgrad_nd_first_launch(WgNd1Args a, cudaStream_t st) {
+    int dev = 0, sm = 148, max_smem = 227 * 1024;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    auto need = [&](int R) {
+        return ((((size_t)a.nplanes * (R + 2) * (a.X + 2) + 3) & ~(size_t)3) + (size_t)8 * (R * a.X + 4)) * 4;
+    };
+    int best = 0;
+    for (int R = 1; R <= a.Y; ++R)
+        if (a.Y % R == 0 && need(R) <= ((size_t)max_smem + 1024) / 2 - 1024) best = R;
+    if (best == 0) return NFK_EUNSUPPORTED;
+    a.R = best;
+    if (ensure_dynamic_smem<conv_wgrad_nd_first_kernel>(max_smem) != NFK_OK) return NFK_ECUDA;
+    const long long units = a.B * a.O0 * a.O1 * (a.Y / best);
+    const int threads = (a.T * 8 + 31) / 32 * 32;
+    const long long ctas = (long long)sm * (threads <= 512 ? 2 : 1);
+    const long long grid = units < ctas ? units : ctas;
+    conv_wgrad_nd_first_kernel<<<(unsigned)grid, threads, need(best), st>>>(a);
+    return check_launch();
+}
+
 template <int CO_B, int NCB>
 static int wgrad_nd_tile_launch(WgNdArgs a, cudaStream_t st) {
     int dev = 0, sm = 148, max_smem = 227 * 1024;
@@ -1200,6 +1316,18 @@ static int conv_bwd_weight_impl(const float* in, const uint8_t* in_mask, int in_
         t.Y = lat.shape[lat.ndim - 2];
         t.X = lat.shape[lat.ndim - 1];
         const int rc = Co <= 8 ? wgrad_nd_tile_launch<8, 1>(t, st) : wgrad_nd_tile_launch<7, 4>(t, st);
+        if (rc != NFK_EUNSUPPORTED) return rc;
+    }
+    if ((lat.ndim == 3 || lat.ndim == 4) && ksize == 3 && Ci == 1 && lat.shape[lat.ndim - 1] % 4 == 0 &&
+        ((uintptr_t)gpre % 16) == 0) {
+        WgNd1Args t{};
+        t.in = in; t.in_mask = in_mask; t.in_keep = in_keep; t.gpre = gpre; t.gw = gw; t.gbias = gbias;
+        t.D = lat.ndim; t.Co = Co; t.T = T; t.nplanes = T / 9; t.B = B;
+        t.O0 = lat.ndim == 4 ? lat.shape[0] : 1;
+        t.O1 = lat.shape[lat.ndim - 3];
+        t.Y = lat.shape[lat.ndim - 2];
+        t.X = lat.shape[lat.ndim - 1];
+        const int rc = wgrad_nd_first_launch(t, st);
         if (rc != NFK_EUNSUPPORTED) return rc;
     }
     if (T >= 27 && Ci >= 8 && a.BV >= 32 * 148) {

@@ -75,6 +75,9 @@ struct NdArgs {
     const float* x;              // final layer: the field, its transform and the per-sample log-Jacobian
     float* y;
     float* log_out;
+    float* save;                 // training forward: this layer's output, float32 channel-major [B][save_ch][V] (or NULL):
+    int save_ch;                 // hidden layer: post-activation h (H channels); last layer: conditioner output (P channels,
+                                 // written at the active sites only)
     long long B;
     NdGeom g;
     RqsCfg cfg;
@@ -167,6 +170,7 @@ struct NdLat {
 template <int D>
 __global__ void __launch_bounds__(256) nd_layer1_kernel(const float* __restrict__ x, const float* __restrict__ w1,
                                                         const float* __restrict__ b1, uint4* __restrict__ out_rec,
+                                                        float* __restrict__ save_h1,
                                                         const NdLat lat, int mask_parity, int active_val, long long B) {
     constexpr int TAPS = D == 2 ? 9 : (D == 3 ? 27 : 81);
     __shared__ __align__(16) float ws[TAPS * 8];
@@ -269,6 +273,14 @@ __global__ void __launch_bounds__(256) nd_layer1_kernel(const float* __restrict_
     cA[D - 1] += f_first ? 1 : 0;
     nd_store_site<D>(ob, lat.Vp, cF, Ld, ps, hF, lF);
     nd_store_site<D>(ob, lat.Vp, cA, Ld, ps, hA, lA);
+    if (save_h1) {                                            // training forward: h1 as float32 [B][H][V] as well
+        float* sp = save_h1 + (b * G + gidx) * 8LL * lat.V + 2 * pi;
+#pragma unroll
+        for (int co = 0; co < 8; ++co) {
+            const float2 v = f_first ? make_float2(vF[co], vA[co]) : make_float2(vA[co], vF[co]);
+            *reinterpret_cast<float2*>(sp + (long long)co * lat.V) = v;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------- layers 2 and 3
@@ -531,6 +543,11 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                         nd_records(v, rh, rl);
                         nd_store_site<4>(a.out_rec + (b * Gout + pass * (NH / 8) + q8) * 2LL * g.Vp, g.Vp, cc, g.L,
                                          g.pstride, rh, rl);
+                        if (a.save) {
+                            float* sp = a.save + (b * a.save_ch + pass * NH + q8 * 8) * (long long)g.V + site;
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) sp[(long long)c * g.V] = v[c];
+                        }
                     }
                 } else {
                     const float xv = NFK_LDG(a.x + b * (long long)g.V + site);
@@ -539,6 +556,11 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                         float prm[NH];
 #pragma unroll
                         for (int c = 0; c < NH; ++c) prm[c] = fmaf(lo[c], 1.f / kLoScale, hi[c]) + bias_s[c];
+                        if (a.save) {
+                            float* sp = a.save + b * a.save_ch * (long long)g.V + site;
+#pragma unroll
+                            for (int c = 0; c < P; ++c) sp[(long long)c * g.V] = prm[c];
+                        }
                         float l;
                         if (KIND == 0) {
                             const float t = prm[0], sc = fabsf(prm[1]);
@@ -657,11 +679,7 @@ bool nd_plan(NdGeom& g, int N2, int G, int npass, int bdup, uint32_t budget) {
             }
             c.nslots = kNdTmemCols / (N2 * c.nchunk);
             if (c.nslots > kNdMaxSlots) c.nslots = kNdMaxSlots;
-            {   // a slot is owned by one issuer and one epilogue half (see the kernel): a multiple of both counts
-                const int mult = (kNdIssuers % 2) ? 2 * kNdIssuers : kNdIssuers;
-                c.nslots -= c.nslots % mult;
-                if (c.nslots < mult) continue;
-            }
+            if (c.nslots < 2) continue;      // (slot -> issuer and slot -> epilogue half are fixed maps: any count works)
             const float eff = (float)outputs / (c.nt * 128.f);
             const float cost = c.taps * G * nd_mma_cycles(N2) / (128.f * eff) + 0.15f * G * (float)c.nbox / outputs +
                                2500.f / outputs;
@@ -762,11 +780,12 @@ extern "C" int64_t nfk_fusednd_workspace(nfk_lattice lat, int H, int kind, int n
     return nd_workspace(g, H, kind, n_knots, B > 0 ? B : 1, bdup).total;
 }
 
-extern "C" int nfk_fusednd_step(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
-                                const float* w3, const float* b3, int H, int kind, nfk_rqs_params prm,
-                                nfk_lattice lat, int mask_parity, int parity, int inverse,
-                                const float* log_in, float* y, float* log_out, int64_t B,
-                                void* workspace, int64_t workspace_bytes, void* stream) {
+static int nd_step_impl(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                        const float* w3, const float* b3, int H, int kind, nfk_rqs_params prm,
+                        nfk_lattice lat, int mask_parity, int parity, int inverse,
+                        const float* log_in, float* y, float* log_out, int64_t B,
+                        void* workspace, int64_t workspace_bytes, void* stream,
+                        float* save_h1, float* save_h2, float* save_out) {
     if (!x || !w1 || !w2 || !w3 || !y || !log_out || !workspace || x == y) return NFK_EINVAL;
     if (!nd_width_ok(H) || (kind != 0 && kind != 1) || !nd_lattice_ok(lat)) return NFK_EUNSUPPORTED;
     if (!nd_knots_ok(kind, prm.n_knots)) return NFK_EUNSUPPORTED;
@@ -822,14 +841,15 @@ extern "C" int nfk_fusednd_step(const float* x, const float* w1, const float* b1
     if (blocks >= (1LL << 31)) return NFK_EUNSUPPORTED;
     const dim3 grid1((unsigned)blocks, (unsigned)G);
     switch (D) {
-        case 2: nd_layer1_kernel<2><<<grid1, 256, 0, st>>>(x, w1, b1, h1, nl, mask_parity, g.active_val, B); break;
-        case 3: nd_layer1_kernel<3><<<grid1, 256, 0, st>>>(x, w1, b1, h1, nl, mask_parity, g.active_val, B); break;
-        default: nd_layer1_kernel<4><<<grid1, 256, 0, st>>>(x, w1, b1, h1, nl, mask_parity, g.active_val, B); break;
+        case 2: nd_layer1_kernel<2><<<grid1, 256, 0, st>>>(x, w1, b1, h1, save_h1, nl, mask_parity, g.active_val, B); break;
+        case 3: nd_layer1_kernel<3><<<grid1, 256, 0, st>>>(x, w1, b1, h1, save_h1, nl, mask_parity, g.active_val, B); break;
+        default: nd_layer1_kernel<4><<<grid1, 256, 0, st>>>(x, w1, b1, h1, save_h1, nl, mask_parity, g.active_val, B); break;
     }
     if (int e = check_launch()) return e;
 
     NdArgs a2{};
     a2.in_rec = h1; a2.out_rec = h2; a2.bimg = img2; a2.bias = b2; a2.B = B; a2.g = g2;
+    a2.save = save_h2; a2.save_ch = H;
     a2.cfg = RqsCfg{0.f, 1.f, 0.f, 1.f, 0, 0};
     int e2;
     if (OC == 8) e2 = nd_launch<0, 0, 8, 0>(a2, st);
@@ -842,6 +862,7 @@ extern "C" int nfk_fusednd_step(const float* x, const float* w1, const float* b1
 
     NdArgs a3{};
     a3.in_rec = h2; a3.bimg = img3; a3.bias = b3; a3.x = x; a3.y = y; a3.log_out = log_out; a3.B = B; a3.g = g3;
+    a3.save = save_out; a3.save_ch = P;
     a3.cfg = RqsCfg{0.f, 1.f, 0.f, 1.f, 0, 0};
     if (kind == 0) return nd_launch_final<0, 2>(a3, inverse, st);
     a3.cfg = RqsCfg{prm.xlim0, prm.xlim1 - prm.xlim0, prm.ylim0, prm.ylim1 - prm.ylim0, prm.extrap_left,
@@ -854,4 +875,27 @@ extern "C" int nfk_fusednd_step(const float* x, const float* w1, const float* b1
         case 10: return nd_launch_final<1, 10>(a3, inverse, st);
         default: return NFK_EUNSUPPORTED;
     }
+}
+
+extern "C" int nfk_fusednd_step(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                                const float* w3, const float* b3, int H, int kind, nfk_rqs_params prm,
+                                nfk_lattice lat, int mask_parity, int parity, int inverse,
+                                const float* log_in, float* y, float* log_out, int64_t B,
+                                void* workspace, int64_t workspace_bytes, void* stream) {
+    return nd_step_impl(x, w1, b1, w2, b2, w3, b3, H, kind, prm, lat, mask_parity, parity, inverse, log_in, y, log_out, B,
+                        workspace, workspace_bytes, stream, nullptr, nullptr, nullptr);
+}
+
+/* The same step as the forward pass of TRAINING: additionally stores the post-activation hidden layers
+ * h1, h2 [B][H][V] and the conditioner output out [B][P][V] (defined at the active sites only) in float32 for the
+ * gradient kernels (nfk_rqs_bwd / nfk_affine_bwd, nfk_conv_circ_fwd with transposed weights, nfk_conv_circ_bwd_weight). */
+extern "C" int nfk_fusednd_step_train(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                                      const float* w3, const float* b3, int H, int kind, nfk_rqs_params prm,
+                                      nfk_lattice lat, int mask_parity, int parity,
+                                      const float* log_in, float* y, float* log_out,
+                                      float* h1, float* h2, float* out, int64_t B,
+                                      void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!h1 || !h2 || !out) return NFK_EINVAL;
+    return nd_step_impl(x, w1, b1, w2, b2, w3, b3, H, kind, prm, lat, mask_parity, parity, 0, log_in, y, log_out, B,
+                        workspace, workspace_bytes, stream, h1, h2, out);
 }

@@ -92,6 +92,13 @@ class Coupling_(Module_):
                                                   self._fused_kind, self._fused_params(convs[-1].out_channels),
                                                   self.mask._mask, self.mask.mask_kwargs.get('parity', 0), p, log0)
                 continue
+            if (not inverse and self._fused_kind is not None and torch.is_grad_enabled()
+                    and self._fusable_nd_train(net, x)):
+                convs = net._convs()
+                x, log0 = _ops.fusednd_step_train(x, [c.standard_weight() for c in convs], [c.bias for c in convs],
+                                                  self._fused_kind, self._fused_params(convs[-1].out_channels),
+                                                  self.mask._mask, self.mask.mask_kwargs.get('parity', 0), p, log0)
+                continue
             if self._fused_kind is not None and self._fusable(net, x):
                 # conditioner + transform in ONE kernel: the (B,P,*L) tensor is never formed
                 convs = net._convs()
@@ -139,6 +146,20 @@ class Coupling_(Module_):
         if not (isinstance(net, ConvAct) and net.fusednd_ok):
             return False
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in net.parameters())):
+            return False
+        if not (isinstance(self.mask, EvenOddMask) and self.mask.mask_kwargs.get('exclude_mu') is None):
+            return False
+        return (x.is_cuda and self.channels_axis == 1 and x.dim() == net.conv_kwargs['conv_dim'] + 1
+                and _ops.fusednd_supported(x.shape[1:], self._fused_knots(net), net.conv_kwargs['hidden_sizes'][0]))
+
+    def _fusable_nd_train(self, net, x):
+        """The same structural conditions with an autograd graph wanted: the N-D tensor-core forward that also keeps
+        what the gradient kernels need (nfk_fusednd_step_train).  NFK_FUSED_ND_TRAIN=0 keeps the layer-by-layer path."""
+        if os.environ.get('NFK_FUSED_ND_TRAIN') == '0' or os.environ.get('NFK_FUSED_ND') == '0':
+            return False
+        if not (isinstance(net, ConvAct) and net.fusednd_ok):
+            return False
+        if not (x.requires_grad or any(p.requires_grad for p in net.parameters())):
             return False
         if not (isinstance(self.mask, EvenOddMask) and self.mask.mask_kwargs.get('exclude_mu') is None):
             return False

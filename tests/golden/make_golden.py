@@ -827,6 +827,12 @@ if __name__ == "__main__":
         gen_coupling("cpl_rqs_2d_32", (32, 32), 2, [("rqs", 2)], seed=60, per_step=False)
     if wanted("cpl_mixed_2d_40x24"):
         gen_coupling("cpl_mixed_2d_40x24", (40, 24), 2, [("affine", 2), ("rqs", 2)], seed=70, per_step=False)
+    # 3-D / 4-D stacks with the [8, 8] conditioner: the N-D tensor-core training forward and the tiled N-D
+    # weight-gradient kernels against reference autograd
+    if wanted("cpl_mixed_3d_h8"):
+        gen_coupling("cpl_mixed_3d_h8", (4, 6, 8), 2, [("affine", 1), ("rqs", 2)], seed=80, per_step=False)
+    if wanted("cpl_mixed_4d_h8"):
+        gen_coupling("cpl_mixed_4d_h8", (4, 4, 4, 4), 2, [("affine", 1), ("rqs", 1)], seed=90, per_step=False)
     if wanted("psd"):
         gen_psd()
     if wanted("model_psd_affine"):

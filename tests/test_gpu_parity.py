@@ -250,36 +250,38 @@ def test_convact_golden(tag, shape, hidden, P, bias):
         close_grad(gr, g[f"{tag}_grad_{name}"], tol=2e-5)
 
 
-@pytest.mark.parametrize("shape,Co,B,bias", [((8, 8, 8), 28, 3, True), ((32, 32, 32), 8, 2, False), ((6, 4, 8), 8, 2, True),
-                                             ((4, 4, 4, 4), 28, 2, True), ((16, 16, 16, 16), 2, 1, False)])
-def test_nd_weight_gradient_tile_kernel(shape, Co, B, bias):
-    """Weight / bias gradient of a 3-D / 4-D circular convolution with 8 input channels (the tiled kernel
-    conv_wgrad_nd_tile_kernel behind nfk_conv_circ_bwd_weight) against float64 autograd of the same convolution
-    written with torch ops (circular padding by concatenation + conv3d / summed conv3d slices)."""
+@pytest.mark.parametrize("shape,Ci,Co,B,bias,masked", [
+    ((8, 8, 8), 8, 28, 3, True, False), ((32, 32, 32), 8, 8, 2, False, False), ((6, 4, 8), 8, 8, 2, True, False),
+    ((4, 4, 4, 4), 8, 28, 2, True, False), ((16, 16, 16, 16), 8, 2, 1, False, False),
+    ((8, 8, 8), 1, 8, 3, True, True), ((32, 32, 32), 1, 8, 2, False, True), ((4, 6, 4, 8), 1, 8, 2, True, False),
+    ((6, 4, 8), 1, 16, 2, True, True)])
+def test_nd_weight_gradient_tile_kernels(shape, Ci, Co, B, bias, masked):
+    """Weight / bias gradient of a 3-D / 4-D circular convolution with 8 input channels (conv_wgrad_nd_tile_kernel) or
+    one, optionally masked, input channel (conv_wgrad_nd_first_kernel) -- both behind nfk_conv_circ_bwd_weight --
+    against float64 autograd of the same convolution written with torch.roll and einsum."""
+    import itertools
+    from normflow__b200 import _ops
     D = len(shape)
     g = torch.Generator('cpu').manual_seed(31)
     rnd = lambda *s: torch.randn(*s, generator=g, dtype=torch.float64, device='cpu')
-    x = rnd(B, 8, *shape)
-    w = (rnd(Co, 8, *(3,) * D) * 0.1).requires_grad_(True)
+    x = rnd(B, Ci, *shape)
+    w = (rnd(Co, Ci, *(3,) * D) * 0.1).requires_grad_(True)
     bvec = (rnd(Co) * 0.1).requires_grad_(True) if bias else None
     gout = rnd(B, Co, *shape)
+    mask = EvenOddMask(shape=shape)._mask if masked else None
+    xin = x * mask.cpu().double() if masked else x            # in_keep = 1: the sites with mask == 1 are visible
     # float64 reference: out[b, o, s] = sum_{i, k} w[o, i, k] x[b, i, s + k - 1]  (periodic)
     out = torch.zeros(B, Co, *shape, dtype=torch.float64, device='cpu')
-    import itertools
     for k in itertools.product(range(3), repeat=D):
-        shifted = torch.roll(x, shifts=[1 - kk for kk in k], dims=list(range(2, 2 + D)))
+        shifted = torch.roll(xin, shifts=[1 - kk for kk in k], dims=list(range(2, 2 + D)))
         out = out + torch.einsum('oi,bi...->bo...', w[(slice(None), slice(None)) + k], shifted)
     if bias:
         out = out + bvec.reshape(1, Co, *(1,) * D)
     grads = torch.autograd.grad((out * gout).sum(), [w] + ([bvec] if bias else []))
-    from normflow__b200 import _ops
-    conv = _ops.conv_stack(x.float().to(DEV).requires_grad_(False), [w.detach().float().to(DEV).requires_grad_(True)],
-                           [bvec.detach().float().to(DEV).requires_grad_(True) if bias else None], [None], 3)
-    close(conv, out.detach(), tol=2e-5)
-    # gradient through the package's autograd node
     wd = w.detach().float().to(DEV).requires_grad_(True)
     bd = bvec.detach().float().to(DEV).requires_grad_(True) if bias else None
-    o2 = _ops.conv_stack(x.float().to(DEV), [wd], [bd], [None], 3)
+    o2 = _ops.conv_stack(x.float().to(DEV), [wd], [bd], [None], 3, in_mask=mask.to(DEV) if masked else None, in_keep=1)
+    close(o2, out.detach(), tol=2e-5)
     got = torch.autograd.grad((o2 * gout.float().to(DEV)).sum(), [wd] + ([bd] if bias else []))
     close_grad(got[0], grads[0].numpy(), tol=2e-5)
     if bias:
@@ -331,7 +333,10 @@ def _build_stack(g, bias):
                                        ("cpl_mixed_3d", False), ("cpl_mixed_4d", True),
                                        # multi-strip geometries: the fused training forward, the tensor-core weight
                                        # gradient and the checkerboard data gradient against REFERENCE autograd
-                                       ("cpl_rqs_2d_32", False), ("cpl_mixed_2d_40x24", False)])
+                                       ("cpl_rqs_2d_32", False), ("cpl_mixed_2d_40x24", False),
+                                       # 3-D / 4-D with the [8, 8] conditioner: N-D tensor-core training forward
+                                       # + tiled N-D weight gradients against reference autograd
+                                       ("cpl_mixed_3d_h8", False), ("cpl_mixed_4d_h8", False)])
 def test_coupling_stack_golden(name, bias):
     g = load_golden(name)
     net_, shape = _build_stack(g, bias)

@@ -210,7 +210,7 @@ def _run_stack(g, inverse=False):
 
 
 @pytest.mark.parametrize("name", ["cpl_affine_2d", "cpl_rqs_2d", "cpl_shift_1d", "cpl_mixed_3d", "cpl_mixed_4d",
-                                  "cpl_rqs_2d_32", "cpl_mixed_2d_40x24"])
+                                  "cpl_rqs_2d_32", "cpl_mixed_2d_40x24", "cpl_mixed_3d_h8", "cpl_mixed_4d_h8"])
 def test_coupling_stack_golden(name):
     g = load_golden(name)
     mask, flows = _run_stack(g)
