@@ -368,7 +368,7 @@ def run_extras(args, torch, dist, model, world, rank, barrier, pk):
     return out
 
 
-def train_graph_entry(torch, dist, world, rank, barrier, config, batch, base=23, extra=200):
+def train_graph_entry(torch, dist, world, rank, barrier, config, batch, base=23, extra=2000):
     import contextlib
     import io
 

@@ -1,18 +1,24 @@
 #!/bin/bash
-# Round-2 evidence run (one GPU): bench line, launch list of the same command, per-kernel rooflines,
-# ncu --set full of the fused 2-D kernel, the RQ-spline apply kernel and the N-D tensor-core kernels.
+# Round-2 evidence run (one GPU): bench line, launch list of the same command, per-kernel rooflines, step timings of
+# the N-D / wide-conditioner paths, GPU test log with the printed tolerances, and ncu --set full captures of the fused
+# 2-D kernel, the RQ-spline apply kernel, the N-D tensor-core kernels and the tiled N-D weight gradient.
 set -x
-python bench.py --steps 10 --warmup 3 > gpurun_out/r02_bench.json 2> gpurun_out/r02_bench.err
-tail -c 300 gpurun_out/r02_bench.err
+python -m pytest tests -m gpu -q -s > gpurun_out/r02_pytest_gpu.log 2>&1
+tail -3 gpurun_out/r02_pytest_gpu.log
+python bench.py --steps 10 --warmup 3 > gpurun_out/r02_bench_final.json 2> gpurun_out/r02_bench_final.err
+tail -c 300 gpurun_out/r02_bench_final.err
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02_bench_reference.json 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches_raw.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > gpurun_out/r02_ncu_bench.log 2>&1
 python scratch/kernel_roofline.py > gpurun_out/r02_kernel_roofline.log 2>&1
-cp profiles/r02_kernel_roofline.json gpurun_out/ 2>/dev/null
-ncu --set full --clock-control none --import-source on -k regex:fused2d_tc -s 4 -c 1 -o gpurun_out/r02_fused2d_tc \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > /dev/null 2>&1
+(python scratch/nd_time.py; python scratch/wide_time.py) > gpurun_out/r02_nd_step_times.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r02_nd_launches_raw.csv python scratch/nd_time.py > /dev/null 2>&1
 B4=256 B5=32 ncu --set full --clock-control none --import-source on -k regex:"nd_layer1|convnd" -s 9 -c 3 -o gpurun_out/r02_nd3d \
     python scratch/nd_time.py > /dev/null 2>&1
 B4=256 B5=32 ncu --set full --clock-control none --import-source on -k regex:"nd_layer1|convnd" -s 27 -c 3 -o gpurun_out/r02_nd4d \
     python scratch/nd_time.py > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"PairSites" -c 1 -o gpurun_out/r02_rqs_fwd \
+    python scratch/kernel_roofline.py > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"conv_wgrad_nd_tile" -s 4 -c 2 -o gpurun_out/r02_wgrad_nd \
+    python scratch/nd_train_prof.py 4 64 > /dev/null 2>&1
 ls -la gpurun_out/*.ncu-rep
