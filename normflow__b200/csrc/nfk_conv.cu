@@ -299,10 +299,6 @@ extern "C" int nfk_conv_circ_fwd_cb(const float* in, int in_parity, const float*
                          Ci, Co, B, in_parity, stream);
 }
 
-static int conv_nd_tile_try(const float* in, const float* w, int w_transposed, const float* bias, int act,
-                            const float* dact_from, int dact_kind, float* out, nfk_lattice lat, int Ci, int Co,
-                            int64_t B, cudaStream_t st);
-
 static int conv_fwd_impl(const float* in, const float* w, int w_transposed, const float* bias,
                          const uint8_t* in_mask, int in_keep, int act, const float* dact_from, int dact_kind,
                          float* out, nfk_lattice lat, int ksize, int Ci, int Co, int64_t B, int in_parity,
@@ -315,12 +311,6 @@ static int conv_fwd_impl(const float* in, const float* w, int w_transposed, cons
         (!in_mask || ((uintptr_t)in_mask % 4) == 0)) {
         const int rc = conv2d_tile_launch(in, w, w_transposed, bias, in_mask, in_keep, act, dact_from, dact_kind, out,
                                           lat.shape[0], lat.shape[1], Ci, Co, B, in_parity, NFK_STREAM(stream));
-        if (rc != NFK_EUNSUPPORTED) return rc;
-    }
-    if ((lat.ndim == 3 || lat.ndim == 4) && ksize == 3 && !in_mask && Ci >= 2 && Ci <= 32 && Co >= 2 &&
-        lat.shape[lat.ndim - 1] % 4 == 0 && ((uintptr_t)out % 16) == 0 && (!dact_from || ((uintptr_t)dact_from % 16) == 0)) {
-        const int rc = conv_nd_tile_try(in, w, w_transposed, bias, act, dact_from, dact_kind, out, lat, Ci, Co, B,
-                                        NFK_STREAM(stream));
         if (rc != NFK_EUNSUPPORTED) return rc;
     }
     ConvArgs a;
@@ -509,182 +499,6 @@ __global__ void __launch_bounds__(32 * 14) conv_bwd_weight_warptap_kernel(ConvWA
     }
 }
 
-__device__ __forceinline__ void wg_cp_async4(float* dst, const float* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void wg_cp_async16(float* dst, const float* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-}
-
-// ---------------------------------------------------------------- 3-D / 4-D layers, shared-memory tiled
-// The N-D sibling of conv2d_tile_kernel (forward and data-gradient form, 8 output channels per pass): a persistent
-// CTA stages a strip of one (y, x) plane with its one-site halo in every direction (3^(D-2) planes x Ci channels,
-// periodic wrap resolved while loading, cp.async) and the layer's weights ([tap][ci][8], transposed and tap-flipped for
-// the data gradient) in shared memory; a thread keeps 4 consecutive columns x 8 output channels in registers and, per
-// (plane, input channel, row tap), reads its 6-wide window once plus 3 x 8 weights as broadcasts for 96 FMAs.  The
-// generic kernel it replaces gathers every input through periodic-index arithmetic from global memory (89 cycles per
-// site for an 8 -> 8 layer at 32^3: a third of a 3-D / 4-D training step after the weight gradients were tiled).
-struct ConvNdArgs {
-    const float* in;        // [B][Ci][V]
-    const float* w;
-    int w_transposed;
-    const float* bias;
-    int act;
-    const float* dact_from; // [B][Co][V] or NULL
-    int dact_kind;
-    float* out;             // [B][Co][V]
-    int D, Ci, Co, T, nplanes;
-    int O0, O1, Y, X, R;
-    long long B;
-};
-
-__global__ void __launch_bounds__(256) conv_nd_tile_kernel(const ConvNdArgs a) {
-    extern __shared__ __align__(16) float csm[];
-    const int XS = a.X + 2, PSZ = (a.R + 2) * XS;
-    float* ws = csm;                                          // [T][Ci][8]
-    float* in_s = csm + a.T * a.Ci * 8;                       // [nplanes][Ci][R + 2][X + 2]
-    const int tid = threadIdx.x;
-    const int V = a.O0 * a.O1 * a.Y * a.X;
-    const int strips = a.Y / a.R;
-    const int xq = a.X >> 2;
-    const long long units = a.B * a.O0 * a.O1 * strips;
-    const int copass = (a.Co + 7) >> 3;
-    for (int cp = 0; cp < copass; ++cp) {
-        const int co0 = cp * 8;
-        __syncthreads();
-        for (int e = tid; e < a.T * a.Ci * 8; e += blockDim.x) {
-            const int co = e & 7, ci = (e >> 3) % a.Ci, t = (e >> 3) / a.Ci;
-            float v = 0.f;
-            if (co0 + co < a.Co)
-                v = a.w_transposed ? __ldg(a.w + ((long long)ci * a.Co + co0 + co) * a.T + (a.T - 1 - t))
-                                   : __ldg(a.w + ((long long)(co0 + co) * a.Ci + ci) * a.T + t);
-            ws[e] = v;
-        }
-        for (long long u = blockIdx.x; u < units; u += gridDim.x) {
-            long long rem = u;
-            const int strip = (int)(rem % strips); rem /= strips;
-            const int o1 = (int)(rem % a.O1); rem /= a.O1;
-            const int o0 = (int)(rem % a.O0);
-            const long long b = rem / a.O0;
-            const int y0 = strip * a.R;
-            __syncthreads();
-            const int total_in = a.nplanes * a.Ci * PSZ;
-            for (int e = tid; e < total_in; e += blockDim.x) {
-                const int i = e % XS;
-                int r = e / XS;
-                const int j = r % (a.R + 2); r /= (a.R + 2);
-                const int c = r % a.Ci, p = r / a.Ci;
-                int q0 = o0, q1 = o1;
-                if (a.D == 4) { q0 += p / 3 - 1; q1 += p % 3 - 1; }
-                else if (a.D == 3) { q1 += p - 1; }
-                q0 += q0 < 0 ? a.O0 : 0; q0 -= q0 >= a.O0 ? a.O0 : 0;
-                q1 += q1 < 0 ? a.O1 : 0; q1 -= q1 >= a.O1 ? a.O1 : 0;
-                int yy = y0 + j - 1, xx = i - 1;
-                yy += yy < 0 ? a.Y : 0; yy -= yy >= a.Y ? a.Y : 0;
-                xx += xx < 0 ? a.X : 0; xx -= xx >= a.X ? a.X : 0;
-                wg_cp_async4(in_s + e, a.in + (b * a.Ci + c) * (long long)V + ((long long)(q0 * a.O1 + q1) * a.Y + yy) * a.X + xx);
-            }
-            asm volatile("cp.async.wait_all;" ::: "memory");
-            __syncthreads();
-            for (int item = tid; item < a.R * xq; item += blockDim.x) {
-                const int y = item / xq, x4 = (item - y * xq) << 2;
-                float acc[4][8];
-#pragma unroll
-                for (int co = 0; co < 8; ++co) {
-                    const float bv = (a.bias && co0 + co < a.Co) ? __ldg(a.bias + co0 + co) : 0.f;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) acc[k][co] = bv;
-                }
-                for (int p = 0; p < a.nplanes; ++p) {
-                    for (int ci = 0; ci < a.Ci; ++ci) {
-                        const float* ip = in_s + (p * a.Ci + ci) * PSZ + y * XS + x4;
-                        const float* wp = ws + ((p * 9) * a.Ci + ci) * 8;
-#pragma unroll
-                        for (int ky = 0; ky < 3; ++ky) {
-                            float win[6];
-#pragma unroll
-                            for (int k = 0; k < 6; ++k) win[k] = ip[ky * XS + k];
-#pragma unroll
-                            for (int kx = 0; kx < 3; ++kx) {
-                                const float4 w0 = *reinterpret_cast<const float4*>(wp + (ky * 3 + kx) * a.Ci * 8);
-                                const float4 w1 = *reinterpret_cast<const float4*>(wp + (ky * 3 + kx) * a.Ci * 8 + 4);
-                                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-                                for (int k = 0; k < 4; ++k)
-#pragma unroll
-                                    for (int co = 0; co < 8; ++co) acc[k][co] = fmaf(win[k + kx], wv[co], acc[k][co]);
-                            }
-                        }
-                    }
-                }
-                const long long site = ((long long)(o0 * a.O1 + o1) * a.Y + y0 + y) * a.X + x4;
-#pragma unroll
-                for (int co = 0; co < 8; ++co) {
-                    if (co0 + co >= a.Co) break;
-                    const long long o = (b * a.Co + co0 + co) * (long long)V + site;
-                    float4 v = make_float4(act_apply(a.act, acc[0][co]), act_apply(a.act, acc[1][co]),
-                                           act_apply(a.act, acc[2][co]), act_apply(a.act, acc[3][co]));
-                    if (a.dact_from) {
-                        const float4 h = *reinterpret_cast<const float4*>(a.dact_from + o);
-                        v.x *= act_grad_from_post(a.dact_kind, h.x);
-                        v.y *= act_grad_from_post(a.dact_kind, h.y);
-                        v.z *= act_grad_from_post(a.dact_kind, h.z);
-                        v.w *= act_grad_from_post(a.dact_kind, h.w);
-                    }
-                    *reinterpret_cast<float4*>(a.out + o) = v;
-                }
-            }
-        }
-    }
-}
-
-static int conv_nd_tile_launch(ConvNdArgs a, cudaStream_t st) {
-    int dev = 0, sm = 148, max_smem = 227 * 1024;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
-    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    auto need = [&](int R) {
-        return ((size_t)a.T * a.Ci * 8 + (size_t)a.nplanes * a.Ci * (R + 2) * (a.X + 2)) * 4;
-    };
-    // strips of at least 64 items (256 sites) when the plane allows, at most a third of an SM's shared memory so
-    // that three CTAs overlap their staging and compute phases
-    const size_t budget = ((size_t)max_smem + 1024) / 3 - 1024;
-    int best = 0;
-    for (int R = 1; R <= a.Y; ++R)
-        if (a.Y % R == 0 && need(R) <= budget) best = R;
-    if (best == 0) {
-        for (int R = 1; R <= a.Y; ++R)
-            if (a.Y % R == 0 && need(R) <= (size_t)max_smem - 1024) { best = R; break; }
-        if (best == 0) return NFK_EUNSUPPORTED;
-    }
-    a.R = best;
-    if (ensure_dynamic_smem<conv_nd_tile_kernel>(max_smem) != NFK_OK) return NFK_ECUDA;
-    const long long units = a.B * a.O0 * a.O1 * (a.Y / best);
-    int items = best * (a.X >> 2);
-    int threads = items >= 256 ? 256 : (items + 31) / 32 * 32;
-    const long long per_sm = (long long)(max_smem / (need(best) + 1024));
-    const long long ctas = (long long)sm * (per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm));
-    const long long grid = units < ctas ? units : ctas;
-    conv_nd_tile_kernel<<<(unsigned)grid, threads, need(best), st>>>(a);
-    return check_launch();
-}
-
-static int conv_nd_tile_try(const float* in, const float* w, int w_transposed, const float* bias, int act,
-                            const float* dact_from, int dact_kind, float* out, nfk_lattice lat, int Ci, int Co,
-                            int64_t B, cudaStream_t st) {
-    ConvNdArgs t{};
-    t.in = in; t.w = w; t.w_transposed = w_transposed; t.bias = bias; t.act = act;
-    t.dact_from = dact_from; t.dact_kind = dact_kind; t.out = out;
-    t.D = lat.ndim; t.Ci = Ci; t.Co = Co; t.B = B;
-    t.T = lat.ndim == 3 ? 27 : 81;
-    t.nplanes = t.T / 9;
-    t.O0 = lat.ndim == 4 ? lat.shape[0] : 1;
-    t.O1 = lat.shape[lat.ndim - 3];
-    t.Y = lat.shape[lat.ndim - 2];
-    t.X = lat.shape[lat.ndim - 1];
-    return conv_nd_tile_launch(t, st);
-}
-
 // ---------------------------------------------------------------- weight gradient, 3-D / 4-D, 8 input channels
 // gw[co][ci][t] += sum_{b, s} gpre[b][co][s] in[b][ci][nbr(s, t)]  for the ConvNd / Conv4d layers (convNd.py:84-127,
 // adjoint) with 3^D taps.  The generic kernel above spends ~100 index instructions per (site, tap) on periodic
@@ -695,6 +509,13 @@ static int conv_nd_tile_try(const float* in, const float* w, int w_transposed, c
 // is a constant offset plus the site index, keeps CO_B accumulators per output block in registers across all the
 // units it walks, and issues one atomic per weight at the end.  Per four sites: 4 LDS (conflict-free: the channel
 // plane stride is 4 mod 32, taps of a warp differ by 1) + CO_B broadcast LDS.128 + 4 CO_B FMAs.
+__device__ __forceinline__ void wg_cp_async4(float* dst, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void wg_cp_async16(float* dst, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
 struct WgNdArgs {
     const float* in;        // [B][8][V]
     const float* gpre;      // [B][Co][V]
