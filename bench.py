@@ -291,12 +291,23 @@ def run_extras(args, torch, dist, model, world, rank, barrier, pk):
     out = {}
     B = args.batch
 
+    def guarded(fn):
+        """One failing section (e.g. out of memory on a shared box) must not take the others, or the line, with it.
+        Every rank runs the same code on the same shapes, so a failure is collective and the ranks stay in step."""
+        try:
+            return fn()
+        except Exception as err:
+            torch.cuda.empty_cache()
+            return {"error": f"{type(err).__name__}: {err}"[:300]}
+
     # ---- mcmc.sample at the headline configuration ------------------------------------------------------
-    np.random.seed(7 + rank)
-    ms = _timed_loop(torch, dist, world, barrier, lambda: model.mcmc.sample(B), steps=min(args.steps, 5), warmup=2)
-    out["mcmc"] = {"what": "model.mcmc.sample(B): flow + device Metropolis scan + row gather (independent chain per rank)",
-                   "config": BC.CONFIGS[3]['name'], "batch_per_gpu": B, "samples_per_s": world * B / (ms * 1e-3),
-                   "ms_per_step": ms, "accept_rate_last": float(model.mcmc.history.accept_rate[-1])}
+    def mcmc_entry():
+        np.random.seed(7 + rank)
+        ms = _timed_loop(torch, dist, world, barrier, lambda: model.mcmc.sample(B), steps=min(args.steps, 5), warmup=2)
+        return {"what": "model.mcmc.sample(B): flow + device Metropolis scan + row gather (independent chain per rank)",
+                "config": BC.CONFIGS[3]['name'], "batch_per_gpu": B, "samples_per_s": world * B / (ms * 1e-3),
+                "ms_per_step": ms, "accept_rate_last": float(model.mcmc.history.accept_rate[-1])}
+    out["mcmc"] = guarded(mcmc_entry)
     model.mcmc._reset_chain()
     torch.cuda.empty_cache()
 
@@ -331,7 +342,7 @@ def run_extras(args, torch, dist, model, world, rank, barrier, pk):
         return entry
 
     tb = args.train_batch or B
-    out["train_step"] = train_entry(3, model, tb, steps=min(args.steps, 4), warmup=2)
+    out["train_step"] = guarded(lambda: train_entry(3, model, tb, steps=min(args.steps, 4), warmup=2))
     model.fit.optimizer = None
     torch.cuda.empty_cache()
 
@@ -347,20 +358,24 @@ def run_extras(args, torch, dist, model, world, rank, barrier, pk):
         cfg = BC.CONFIGS[config]
         m = build_model(torch, config)
         torch.manual_seed(4321 + rank)
-        ms_s = _timed_loop(torch, dist, world, barrier, lambda: m.posterior.sample__(sb), steps=ss, warmup=2 if config < 4 else 1)
-        rate = world * sb / (ms_s * 1e-3)
-        fb = BC.fwd_bytes_per_sample(cfg)
-        entry = {"config": cfg['name'], "lattice": list(cfg['lattice']),
-                 "sample": {"batch_per_gpu": sb, "samples_per_s": rate, "ms_per_step": ms_s,
-                            "model_bytes_per_sample": fb, "hbm_model_frac": fb * rate / world / hbm}}
+
+        def sample_entry():
+            ms_s = _timed_loop(torch, dist, world, barrier, lambda: m.posterior.sample__(sb), steps=ss,
+                               warmup=2 if config < 4 else 1)
+            rate = world * sb / (ms_s * 1e-3)
+            fb = BC.fwd_bytes_per_sample(cfg)
+            return {"batch_per_gpu": sb, "samples_per_s": rate, "ms_per_step": ms_s,
+                    "model_bytes_per_sample": fb, "hbm_model_frac": fb * rate / world / hbm}
+        entry = {"config": cfg['name'], "lattice": list(cfg['lattice']), "sample": guarded(sample_entry)}
         torch.cuda.empty_cache()
-        entry["train"] = {k: v for k, v in train_entry(config, m, tbatch, steps=ts, warmup=2 if config < 4 else 1).items()
-                          if k not in ("what", "config")}
+        entry["train"] = guarded(lambda: {k: v for k, v in train_entry(config, m, tbatch, steps=ts,
+                                                                         warmup=2 if config < 4 else 1).items()
+                                          if k not in ("what", "config")})
         if config < 3:
             # launch-bound workloads: the whole optimisation step -- with several ranks including the NCCL all-reduce --
             # replayed as ONE captured CUDA graph (Fitter.cuda_graph).  Two Model.fit runs of different length through
             # the public API, wall clock around each; the difference is `extra` graph replays.
-            entry["train_graph"] = train_graph_entry(torch, dist, world, rank, barrier, config, tbatch)
+            entry["train_graph"] = guarded(lambda: train_graph_entry(torch, dist, world, rank, barrier, config, tbatch))
         table[str(config)] = entry
         del m
         torch.cuda.empty_cache()
@@ -409,10 +424,10 @@ def attach_cpu(extras, results):
         c, what = int(r["config"]), r["what"]
         if c == 3:
             key = {"train": "train_step", "mcmc": "mcmc"}.get(what)
-            if key and key in extras:
+            if key and isinstance(extras.get(key), dict):
                 extras[key]["cpu_reference"] = cpu
-        elif str(c) in extras.get("configs", {}):
-            extras["configs"][str(c)][what if what != "mcmc" else "mcmc"]["cpu_reference"] = cpu
+        elif str(c) in extras.get("configs", {}) and isinstance(extras["configs"][str(c)].get(what), dict):
+            extras["configs"][str(c)][what]["cpu_reference"] = cpu
 
 
 def run_b200(args):
@@ -600,7 +615,10 @@ def run_b200(args):
     if not args.no_extras:
         del y, logq, logp
         torch.cuda.empty_cache()
-        extras = run_extras(args, torch, dist, model, world, rank, barrier, pk)
+        try:
+            extras = run_extras(args, torch, dist, model, world, rank, barrier, pk)
+        except Exception as err:                  # the headline figures above must survive a failure down here
+            extras = {"extras_error": f"{type(err).__name__}: {err}"[:500]}
 
     if rank != 0:
         if world > 1:
