@@ -832,17 +832,26 @@ def fusednd_step(x, weights, biases, kind, prm, mask_parity, parity, log0=0, inv
     if prm is None:
         prm = _C.RqsParams(2, 0.0, 1.0, 0.0, 1.0, 0, 0)
     lat = _C.lattice(shape)
-    need = int(lib().nfk_fusednd_workspace(lat, int(w[0].shape[0]), int(kind), prm.n_knots, B))
-    if need <= 0:
-        check(need if need < 0 else _C.EUNSUPPORTED, "fusednd_workspace")
+    H = int(w[0].shape[0])
+    per_sample = int(lib().nfk_fusednd_workspace(lat, H, int(kind), prm.n_knots, 1))
+    if per_sample <= 0:
+        check(per_sample if per_sample < 0 else _C.EUNSUPPORTED, "fusednd_workspace")
     y = torch.empty_like(x)
     log_out = torch.empty((B,), dtype=torch.float32, device=x.device)
+    # the two hidden layers live in the workspace as padded record arrays (about 8 H bytes per site and layer): walk the
+    # batch in slices that keep it under NFK_ND_WORKSPACE_GB (default 24 GB) -- samples are independent
+    cap = int(float(os.environ.get("NFK_ND_WORKSPACE_GB", "24")) * 2 ** 30)
+    chunk = max(1, min(B, cap // max(per_sample, 1)))
+    need = int(lib().nfk_fusednd_workspace(lat, H, int(kind), prm.n_knots, chunk))
     workspace = torch.empty((need,), dtype=torch.uint8, device=x.device)     # torch allocations are 512-byte aligned
     with _C.timed("fusednd_step"):
-        check(lib().nfk_fusednd_step(dev(x), dev(w[0]), dev(b[0]), dev(w[1]), dev(b[1]), dev(w[2]), dev(b[2]),
-                                     int(w[0].shape[0]), int(kind), prm, lat, int(mask_parity), int(parity),
-                                     int(bool(inverse)), dev(log_in), dev(y), dev(log_out), B,
-                                     dev(workspace, torch.uint8), need, stream()), "fusednd_step")
+        for lo in range(0, B, chunk):
+            hi = min(B, lo + chunk)
+            check(lib().nfk_fusednd_step(dev(x[lo:hi]), dev(w[0]), dev(b[0]), dev(w[1]), dev(b[1]), dev(w[2]), dev(b[2]),
+                                         H, int(kind), prm, lat, int(mask_parity), int(parity), int(bool(inverse)),
+                                         None if log_in is None else dev(log_in[lo:hi]), dev(y[lo:hi]),
+                                         dev(log_out[lo:hi]), hi - lo, dev(workspace, torch.uint8), need, stream()),
+                  "fusednd_step")
     return y, log_out
 
 

@@ -980,6 +980,22 @@ def test_wide_conditioner_takes_the_tensor_core_path(monkeypatch):
     close(out['1'][1], lr)
 
 
+def test_nd_step_batch_slices_give_the_same_result(monkeypatch):
+    """The N-D step walks the batch in slices when its workspace would pass NFK_ND_WORKSPACE_GB: same numbers,
+    including a carried log-Jacobian."""
+    from normflow__b200 import _ops
+    g = torch.Generator('cpu').manual_seed(5)
+    rnd = lambda *s, scale=1.0: (torch.randn(*s, generator=g, device='cpu') * scale).to(DEV)
+    w = [rnd(8, 1, 3, 3, 3, scale=0.2), rnd(8, 8, 3, 3, 3, scale=0.05), rnd(28, 8, 3, 3, 3, scale=0.05)]
+    x, log0 = rnd(7, 8, 8, 8), rnd(7)
+    prm = _C.RqsParams(10, -5.0, 5.0, -5.0, 5.0, 1, 1)
+    with torch.no_grad():
+        y0, l0 = _ops.fusednd_step(x, w, [None] * 3, 1, prm, 0, 1, log0, False)
+        monkeypatch.setenv('NFK_ND_WORKSPACE_GB', '0.0002')          # room for three samples at a time
+        y1, l1 = _ops.fusednd_step(x, w, [None] * 3, 1, prm, 0, 1, log0, False)
+    assert torch.equal(y0, y1) and torch.allclose(l0, l1, rtol=0, atol=1e-5)
+
+
 def test_nd_step_is_the_path_taken_in_3d_and_4d(monkeypatch):
     """Evaluation of a 3-D / 4-D coupling must go through nfk_fusednd_step (same numbers as the layer-by-layer
     kernels up to float32 rounding, but not bit-identical)."""
