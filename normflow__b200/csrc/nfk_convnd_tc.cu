@@ -63,6 +63,15 @@ struct NdGeom {
     int npass;                   // hidden layer: passes over the output channels (32 per pass at most)
     uint32_t comp_bytes;         // hi plane -> lo plane of the box in shared memory (planes: [group][hi | lo])
     uint32_t b_bytes;            // B operand image of one pass
+    // Second hidden layer, stored for a COMPACT last layer: padded to the odd extent L + 3 on every axis (all strides odd:
+    // the parity of a linear position is the parity of its coordinate sum) and split by that parity into two arrays,
+    // so that the last layer's M tiles enumerate the ACTIVE sites only, as the 2-D kernel does (nfk_fused_tc.cuh)
+    int estride[4];              // strides of that padded array
+    int Ep, Eh;                  // positions per sample and plane pair; records per parity plane (Ep / 2 + 1)
+    int out_split;               // hidden layer (MODE 0): write the records in that form
+    int compact;                 // last layer (MODE 1): read them in that form
+    int last;                    // compact: linear box index of the last interior position (first: the first)
+    uint32_t pb_bytes;           // compact: bytes of one parity plane of the box in shared memory
     uint32_t off_a, off_b, off_tab, off_bar, smem_bytes;
     int mask_parity, active_val;
 };
@@ -155,6 +164,32 @@ __device__ __forceinline__ void nd_store_site(uint4* hi_plane, int Vp, const int
     }
 }
 
+// The same for the parity-split layout (extent L + 3 per axis, strides es): position P goes to parity plane P & 1 at
+// index P >> 1; planes of one (sample, channel group): [hi even][hi odd][lo even][lo odd], Eh records each.
+template <int ND>
+__device__ __forceinline__ void nd_store_site_split(uint4* base, int Eh, const int (&c)[ND], const int (&L)[ND],
+                                                    const int (&es)[ND], const uint4& hi, const uint4& lo) {
+    int diff[ND];
+    int hasmask = 0, P = 0;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        const int m = (c[d] + 1) * es[d];
+        const bool has = es[d] != 0 && (c[d] == 0 || c[d] == L[d] - 1);
+        diff[d] = (c[d] == 0 ? (L[d] + 1) * es[d] : 0) - m;
+        hasmask |= has ? 1 << d : 0;
+        P += m;
+    }
+    base[(P & 1) * Eh + (P >> 1)] = hi;
+    base[(2 + (P & 1)) * Eh + (P >> 1)] = lo;
+    for (int mask = hasmask; mask; mask = (mask - 1) & hasmask) {
+        int o = P;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) o += (mask >> d) & 1 ? diff[d] : 0;
+        base[(o & 1) * Eh + (o >> 1)] = hi;
+        base[(2 + (o & 1)) * Eh + (o >> 1)] = lo;
+    }
+}
+
 // ------------------------------------------------------------------------------------------- layer 1
 struct NdLat {
     int L[4];                    // the D lattice extents first (unlike NdGeom), the rest 1
@@ -170,7 +205,7 @@ struct NdLat {
 template <int D>
 __global__ void __launch_bounds__(256) nd_layer1_kernel(const float* __restrict__ x, const float* __restrict__ w1,
                                                         const float* __restrict__ b1, uint4* __restrict__ out_rec,
-                                                        float* __restrict__ save_h1,
+                                                        float* __restrict__ save_h1, float* __restrict__ y_frozen,
                                                         const NdLat lat, int mask_parity, int active_val, long long B) {
     constexpr int TAPS = D == 2 ? 9 : (D == 3 ? 27 : 81);
     __shared__ __align__(16) float ws[TAPS * 8];
@@ -255,6 +290,11 @@ __global__ void __launch_bounds__(256) nd_layer1_kernel(const float* __restrict_
                 }
             }
         }
+    }
+    if (y_frozen && gidx == 0) {
+        // a compact last layer visits the active sites only: the frozen site of the pair is passed through here
+        const int s = (D >= 4 ? idx[0][1] : 0) + (D >= 3 ? idx[1][1] : 0) + idx[2][1] + xF[1];
+        y_frozen[b * (long long)lat.V + s] = NFK_LDG(xb + s);
     }
     float vF[8], vA[8];
 #pragma unroll
@@ -356,13 +396,21 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
         }
     };
 
+    // compact last layer: parity of the linear box position of the unit's ACTIVE sites (all box strides are odd, so it is
+    // the parity of the box-coordinate sum; lattice coordinate = origin + box coordinate - 1 on each of the D axes)
+    auto unit_parity = [&](const int (&org)[4]) {
+        return (g.active_val ^ (1 - g.mask_parity) ^ (org[0] + org[1] + org[2] + org[3]) ^ g.D) & 1;
+    };
+
     if (warp >= kNdEpiWarps) {
         // =============================== loads + MMA issue (one elected thread per issuer warp) ===========
         const int iw = warp - kNdEpiWarps;                            // issuer 0 also fetches the boxes
         if (tc::elect_one()) {
             const uint32_t a_base = tc::smem_u32(A);
             const uint32_t b_base = tc::smem_u32(Bs);
-            const uint64_t a_desc = tc::make_desc(a_base, g.comp_bytes, 128);
+            // (compact: the hi -> lo distance is two parity planes; plane 1 follows plane 0)
+            const uint64_t a_desc = tc::make_desc(a_base, g.compact ? 2u * g.pb_bytes : g.comp_bytes, 128);
+            const int pbrec = (int)(g.pb_bytes >> 4);
             const uint64_t b_desc = tc::make_desc(b_base, g.bdup == 2 ? N2 * 16 : 0, 128);
             const uint32_t idesc = tc::make_idesc(0, 128, N2);
             const uint32_t loaded_bar = tc::smem_u32(loaded);
@@ -370,7 +418,7 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
             // steps (nine taps of one channel group) per accumulation chain
             const int chain_len = (g.ngroups * G + g.nchunk - 1) / g.nchunk;
             const int bstep = g.bdup * N2;                           // B rows per (tap, channel group)
-            const int gstep = (int)(2 * g.comp_bytes >> 4);          // records between the planes of two channel groups
+            const int gstep = (int)((g.compact ? 4 * g.pb_bytes : 2 * g.comp_bytes) >> 4);   // records between two channel groups' planes
             int slot = 0;
             uint32_t ring_phase = 0, load_phase = 0;
             int last_slot[kNdIssuers], cur_pass = -1;                // last tile of every issuer in the previous unit
@@ -381,13 +429,15 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                 long long b;
                 int org[4], pass;
                 unit_origin(unit, pass, b, org);
+                const int pib = unit_parity(org);
+                const int cfirst = (g.first + ((pib ^ g.first) & 1)) >> 1;
                 if (iw == 0) {
                     // box (and weights) may be overwritten once every MMA of the previous unit has completed
 #pragma unroll
                     for (int w = 0; w < kNdIssuers; ++w)
                         if (last_slot[w] >= 0) tc::mbar_wait(tc::smem_u32(full + last_slot[w]), last_phase[w]);
                     const uint32_t run_bytes = (uint32_t)g.run_rec * 16;
-                    uint32_t tx = 2u * G * g.nruns * run_bytes;
+                    uint32_t tx = g.compact ? 2u * G * (uint32_t)g.nbox * 16u : 2u * G * g.nruns * run_bytes;
                     if (pass != cur_pass) tx += g.b_bytes;
                     nd_expect_tx(loaded_bar, tx);
                     if (pass != cur_pass) {
@@ -399,19 +449,38 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                         int rem = k, so = 0;
 #pragma unroll
                         for (int d = 3; d >= 0; --d) {
+                            const int st = g.compact ? g.estride[d] : g.pstride[d];
                             if (d < g.split) {
                                 const int q = nd_div(rem, g.box[d], g.magic_box[d]);
-                                so += (org[d] + rem - q * g.box[d]) * g.pstride[d];
+                                so += (org[d] + rem - q * g.box[d]) * st;
                                 rem = q;
-                            } else if (d == g.split) {
-                                so += org[d] * g.pstride[d];
+                            } else {
+                                so += org[d] * st;         // (d == split; the axes behind it are whole: origin 0)
                             }
                         }
-                        for (int gi = 0; gi < G; ++gi) {
-                            const uint4* src = a.in_rec + (b * G + gi) * 2LL * g.Vp + so;
-                            const uint32_t dst = a_base + (uint32_t)gi * 2u * g.comp_bytes + k * run_bytes;
-                            nd_bulk_load(dst, src, run_bytes, loaded_bar);
-                            nd_bulk_load(dst + g.comp_bytes, src + g.Vp, run_bytes, loaded_bar);
+                        if (!g.compact) {
+                            for (int gi = 0; gi < G; ++gi) {
+                                const uint4* src = a.in_rec + (b * G + gi) * 2LL * g.Vp + so;
+                                const uint32_t dst = a_base + (uint32_t)gi * 2u * g.comp_bytes + k * run_bytes;
+                                nd_bulk_load(dst, src, run_bytes, loaded_bar);
+                                nd_bulk_load(dst + g.comp_bytes, src + g.Vp, run_bytes, loaded_bar);
+                            }
+                        } else {
+                            // parity-split box: the run's positions of box parity q sit in source plane (so + ...) & 1
+                            const int a0 = k * g.run_rec;
+#pragma unroll
+                            for (int q = 0; q < 2; ++q) {
+                                const int pq = a0 + ((q ^ a0) & 1);
+                                if (pq >= a0 + g.run_rec) continue;
+                                const int n = (a0 + g.run_rec - pq + 1) >> 1;
+                                const int Pq = so + (pq - a0);
+                                for (int gi = 0; gi < G; ++gi) {
+                                    const uint4* src = a.in_rec + (b * G + gi) * 4LL * g.Eh + (Pq & 1) * g.Eh + (Pq >> 1);
+                                    const uint32_t dst = a_base + (uint32_t)gi * 4u * g.pb_bytes + q * g.pb_bytes + (pq >> 1) * 16;
+                                    nd_bulk_load(dst, src, n * 16, loaded_bar);
+                                    nd_bulk_load(dst + 2u * g.pb_bytes, src + 2LL * g.Eh, n * 16, loaded_bar);
+                                }
+                            }
                         }
                     }
                 }
@@ -434,7 +503,9 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                     // accumulation chain grows linearly with its length: the taps x channel groups MMAs of a tile
                     // are cut into `nchunk` chains, each in its own TMEM columns, which the epilogue adds up with
                     // round-to-nearest
-                    const uint64_t ad0 = tc::desc_advance(a_desc, g.first + m * 128);
+                    // compact: tile rows are the active positions c (box position 2 c + pib); a tap with linear offset
+                    // d reads parity plane (pib + d) & 1 at row c + ((pib + d) >> 1) -- the same shift for every row
+                    const uint64_t ad0 = tc::desc_advance(a_desc, (g.compact ? cfirst : g.first) + m * 128);
                     uint64_t bd = b_desc;
                     uint32_t acc = tmem + slot * cols_per_slot;
                     int cnt = 0;
@@ -444,7 +515,7 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                         if (g.ngroups == 9) od = (o / 3 - 1) * g.bstride[0] + (o % 3 - 1) * g.bstride[1];
                         else if (g.ngroups == 3) od = (o - 1) * g.bstride[1];
                         else od = 0;
-                        uint64_t ad = tc::desc_advance(ad0, od);
+                        uint64_t ad = tc::desc_advance(ad0, od);          // (compact: od is taken out again per tap, see below)
                         uint64_t bdg = bd;
                         // one compact copy of the nine unrolled taps, looped over the channel groups; a chain is a
                         // whole number of such steps
@@ -452,7 +523,11 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                         for (int gi = 0; gi < G; ++gi) {
 #pragma unroll
                             for (int i = 0; i < 9; ++i) {
-                                const int dl = (i / 3 - 1) * s2 + (i % 3 - 1);
+                                int dl = (i / 3 - 1) * s2 + (i % 3 - 1);
+                                if (g.compact) {
+                                    const int sft = pib + od + dl;
+                                    dl = (sft >> 1) + (sft & 1) * pbrec - od;       // (`ad` already carries od)
+                                }
                                 tc::mma_f16(acc, tc::desc_advance(ad, dl), tc::desc_advance(bdg, i * G * bstep), idesc,
                                             (cnt | i) != 0);
                             }
@@ -478,6 +553,8 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
             long long b;
             int org[4], pass;
             unit_origin(unit, pass, b, org);
+            const int pib = unit_parity(org);
+            const int cfirst = (g.first + ((pib ^ g.first) & 1)) >> 1;
             float lsum = 0.f;
             for (int m = 0; m < g.nt; ++m) {
                 if ((slot & 1) != half) {                          // the other warp of my quarter owns this slot
@@ -515,8 +592,15 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                 if (++slot == nslots) { slot = 0; ring_phase ^= 1u; }
                 // which site is this row?
                 const int r = m * 128 + quarter * 32 + lane;
-                if (r >= g.span) continue;
-                int rem = g.first + r, site = 0, csum = 0;
+                int rem;
+                if (g.compact) {
+                    rem = 2 * (cfirst + r) + pib;
+                    if (rem > g.last) continue;
+                } else {
+                    if (r >= g.span) continue;
+                    rem = g.first + r;
+                }
+                int site = 0, csum = 0;
                 int cc[4];
                 bool interior = true;
 #pragma unroll
@@ -541,8 +625,12 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                                                          fmaf(hi[q8 * 8 + c], kTwoLog2e, bias_s[pass * NH + q8 * 8 + c])));
                         uint4 rh, rl;
                         nd_records(v, rh, rl);
-                        nd_store_site<4>(a.out_rec + (b * Gout + pass * (NH / 8) + q8) * 2LL * g.Vp, g.Vp, cc, g.L,
-                                         g.pstride, rh, rl);
+                        if (g.out_split)
+                            nd_store_site_split<4>(a.out_rec + (b * Gout + pass * (NH / 8) + q8) * 4LL * g.Eh, g.Eh, cc,
+                                                   g.L, g.estride, rh, rl);
+                        else
+                            nd_store_site<4>(a.out_rec + (b * Gout + pass * (NH / 8) + q8) * 2LL * g.Vp, g.Vp, cc, g.L,
+                                             g.pstride, rh, rl);
                         if (a.save) {
                             float* sp = a.save + (b * a.save_ch + pass * NH + q8 * 8) * (long long)g.V + site;
 #pragma unroll
@@ -609,12 +697,21 @@ void nd_lattice(NdGeom& g, const nfk_lattice& lat) {
     }
     g.V = gs;
     g.Vp = ps;
+    int es = 1;
+    for (int j = 3; j >= 0; --j) {
+        const bool real = j >= r0;
+        g.estride[j] = real ? es : 0;
+        if (real) es *= g.L[j] + 3;
+    }
+    g.Ep = es;
+    g.Eh = es / 2 + 2;
 }
 
 // Chooses the tile of a (sample, tile) unit: trailing axes whole, one axis cut into divisors, leading axes one
 // site thick; minimises modelled cycles per output site subject to the shared-memory budget.
-bool nd_plan(NdGeom& g, int N2, int G, int npass, int bdup, uint32_t budget) {
+bool nd_plan(NdGeom& g, int N2, int G, int npass, int bdup, uint32_t budget, bool compact = false) {
     const int r0 = 4 - g.D;
+    g.compact = compact ? 1 : 0;
     g.bdup = bdup;
     g.G = G;
     g.npass = npass;
@@ -632,7 +729,8 @@ bool nd_plan(NdGeom& g, int N2, int G, int npass, int bdup, uint32_t budget) {
                 const bool real = j >= r0;
                 c.T[j] = !real ? 1 : (j < split ? 1 : (j == split ? t : g.L[j]));
                 c.ntile[j] = g.L[j] / c.T[j];
-                c.box[j] = real ? c.T[j] + 2 : 1;
+                // compact: every box extent odd (T + 2 for odd T, T + 3 for even T), so that every box stride is odd
+                c.box[j] = real ? c.T[j] + 2 + ((compact && c.T[j] % 2 == 0) ? 1 : 0) : 1;
                 c.lo[j] = real ? 1 : 0;
                 c.hi[j] = real ? c.T[j] : 0;
                 outputs *= c.T[j];
@@ -652,14 +750,17 @@ bool nd_plan(NdGeom& g, int N2, int G, int npass, int bdup, uint32_t budget) {
                 c.magic_box[j] = nd_magic(c.box[j]);
                 c.magic_ntile[j] = nd_magic(c.ntile[j]);
             }
-            c.nt = (c.span + 127) / 128;
+            c.last = c.first + c.span - 1;
+            c.nt = compact ? ((c.last - c.first) / 2 + 1 + 127) / 128 : (c.span + 127) / 128;
             c.split = split;
             c.run_rec = c.bstride[split] * c.box[split];
             c.nruns = c.nbox / c.run_rec;
             c.comp_bytes = align((uint32_t)(c.nbox + 128) * 16);
+            c.pb_bytes = align((uint32_t)((c.nbox + 1) / 2 + 136) * 16);
+            const uint32_t a_bytes = compact ? 4 * G * c.pb_bytes : 2 * G * c.comp_bytes;
             uint32_t off = 0;
-            if ((long long)2 * G * c.comp_bytes + c.b_bytes > (long long)budget) continue;
-            c.off_a = off; off += 2 * G * c.comp_bytes;
+            if ((long long)a_bytes + c.b_bytes > (long long)budget) continue;
+            c.off_a = off; off += a_bytes;
             c.off_b = off; off = align(off + c.b_bytes);
             c.off_tab = off; off = align(off + 64 * 4);
             c.off_bar = off; off = align(off + (2 * kNdMaxSlots + 1) * 8 + 64);
@@ -680,7 +781,7 @@ bool nd_plan(NdGeom& g, int N2, int G, int npass, int bdup, uint32_t budget) {
             c.nslots = kNdTmemCols / (N2 * c.nchunk);
             if (c.nslots > kNdMaxSlots) c.nslots = kNdMaxSlots;
             if (c.nslots < 2) continue;      // (slot -> issuer and slot -> epilogue half are fixed maps: any count works)
-            const float eff = (float)outputs / (c.nt * 128.f);
+            const float eff = (float)outputs / (c.nt * 128.f) * (compact ? 0.5f : 1.f);
             const float cost = c.taps * G * nd_mma_cycles(N2) / (128.f * eff) + 0.15f * G * (float)c.nbox / outputs +
                                2500.f / outputs;
             if (cost < best) { best = cost; bg = c; found = true; }
@@ -703,6 +804,11 @@ const NdProps& nd_props() {
         return p;
     }();
     return props;
+}
+
+bool nd_compact() {
+    const char* e = getenv("NFK_ND_COMPACT");          // 0: the last layer evaluates every site (A/B)
+    return !(e && e[0] == '0');
 }
 
 int nd_bdup() {
@@ -749,16 +855,17 @@ bool nd_knots_ok(int kind, int n_knots) {
 int nd_oc(int H) { return H < 32 ? H : 32; }
 
 struct NdWorkspace {
-    long long rec_bytes, img2_bytes, img3_bytes, total;
+    long long rec_bytes, rec2_bytes, img2_bytes, img3_bytes, total;
 };
-NdWorkspace nd_workspace(const NdGeom& g, int H, int kind, int n_knots, long long B, int bdup) {
+NdWorkspace nd_workspace(const NdGeom& g, int H, int kind, int n_knots, long long B, int bdup, bool compact) {
     auto al = [](long long v) { return (v + 255) / 256 * 256; };
     const int G = H / 8;
     NdWorkspace w;
     w.rec_bytes = al(B * G * g.Vp * 32LL);
+    w.rec2_bytes = compact ? al(B * G * 4LL * g.Eh * 16LL) : w.rec_bytes;
     w.img2_bytes = al((long long)(H / nd_oc(H)) * g.taps * G * bdup * 2 * nd_oc(H) * 16);
     w.img3_bytes = al((long long)g.taps * G * bdup * 2 * nd_hi_cols(kind, n_knots) * 16);
-    w.total = 2 * w.rec_bytes + w.img2_bytes + w.img3_bytes;
+    w.total = w.rec_bytes + w.rec2_bytes + w.img2_bytes + w.img3_bytes;
     return w;
 }
 
@@ -775,9 +882,11 @@ extern "C" int64_t nfk_fusednd_workspace(nfk_lattice lat, int H, int kind, int n
     const int bdup = nd_bdup();
     const uint32_t budget = (uint32_t)nd_props().max_smem;
     NdGeom g2 = g, g3 = g;
-    if (!nd_plan(g2, 2 * nd_oc(H), H / 8, H / nd_oc(H), bdup, budget) ||
-        !nd_plan(g3, 2 * nd_hi_cols(kind, n_knots), H / 8, 1, bdup, budget)) return NFK_EUNSUPPORTED;
-    return nd_workspace(g, H, kind, n_knots, B > 0 ? B : 1, bdup).total;
+    bool compact = nd_compact();
+    if (!nd_plan(g2, 2 * nd_oc(H), H / 8, H / nd_oc(H), bdup, budget)) return NFK_EUNSUPPORTED;
+    if (compact && !nd_plan(g3, 2 * nd_hi_cols(kind, n_knots), H / 8, 1, bdup, budget, true)) compact = false;
+    if (!compact && !nd_plan(g3, 2 * nd_hi_cols(kind, n_knots), H / 8, 1, bdup, budget)) return NFK_EUNSUPPORTED;
+    return nd_workspace(g, H, kind, n_knots, B > 0 ? B : 1, bdup, compact).total;
 }
 
 static int nd_step_impl(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
@@ -805,20 +914,24 @@ static int nd_step_impl(const float* x, const float* w1, const float* b1, const 
     g.active_val = parity == 0 ? 1 : 0;
     NdGeom g2 = g, g3 = g;
     const int NH3 = nd_hi_cols(kind, prm.n_knots);
-    if (!nd_plan(g2, 2 * OC, G, npass, bdup, budget) || !nd_plan(g3, 2 * NH3, G, 1, bdup, budget)) return NFK_EUNSUPPORTED;
+    bool compact = nd_compact();
+    if (!nd_plan(g2, 2 * OC, G, npass, bdup, budget)) return NFK_EUNSUPPORTED;
+    if (compact && !nd_plan(g3, 2 * NH3, G, 1, bdup, budget, true)) compact = false;
+    if (!compact && !nd_plan(g3, 2 * NH3, G, 1, bdup, budget)) return NFK_EUNSUPPORTED;
+    g2.out_split = compact ? 1 : 0;
     if (getenv("NFK_ND_DEBUG")) {                      // tile plan of the two tensor-core layers (tuning aid)
         for (const NdGeom* q : {&g2, &g3})
             fprintf(stderr, "nfk_fusednd: T = %d %d %d %d  box %d  tiles/unit %d (span %d)  runs %d x %d rec  G %d  passes %d  "
-                    "chains %d  slots %d  smem %u B\n", q->T[0], q->T[1], q->T[2], q->T[3], q->nbox, q->nt, q->span, q->nruns,
-                    q->run_rec, q->G, q->npass, q->nchunk, q->nslots, q->smem_bytes);
+                    "chains %d  slots %d  smem %u B%s\n", q->T[0], q->T[1], q->T[2], q->T[3], q->nbox, q->nt, q->span, q->nruns,
+                    q->run_rec, q->G, q->npass, q->nchunk, q->nslots, q->smem_bytes, q->compact ? "  (active sites only)" : "");
     }
-    const NdWorkspace ws = nd_workspace(g, H, kind, prm.n_knots, B, bdup);
+    const NdWorkspace ws = nd_workspace(g, H, kind, prm.n_knots, B, bdup, compact);
     if (workspace_bytes < ws.total || ((uintptr_t)workspace % 256) != 0) return NFK_EINVAL;
     uint8_t* wsp = static_cast<uint8_t*>(workspace);
     uint4* h1 = reinterpret_cast<uint4*>(wsp);
     uint4* h2 = reinterpret_cast<uint4*>(wsp + ws.rec_bytes);
-    __half* img2 = reinterpret_cast<__half*>(wsp + 2 * ws.rec_bytes);
-    __half* img3 = reinterpret_cast<__half*>(wsp + 2 * ws.rec_bytes + ws.img2_bytes);
+    __half* img2 = reinterpret_cast<__half*>(wsp + ws.rec_bytes + ws.rec2_bytes);
+    __half* img3 = reinterpret_cast<__half*>(wsp + ws.rec_bytes + ws.rec2_bytes + ws.img2_bytes);
     const int P = kind == 0 ? 2 : 3 * prm.n_knots - 2;
 
     nd_prep_weights_kernel<<<64, 256, 0, st>>>(w2, H, H, g.taps, OC, npass, bdup, img2);
@@ -840,10 +953,11 @@ static int nd_step_impl(const float* x, const float* w1, const float* b1, const 
     const long long blocks = B * ((pairs + 255) / 256);
     if (blocks >= (1LL << 31)) return NFK_EUNSUPPORTED;
     const dim3 grid1((unsigned)blocks, (unsigned)G);
+    float* yf = compact ? y : nullptr;            // (the full last layer writes every site itself)
     switch (D) {
-        case 2: nd_layer1_kernel<2><<<grid1, 256, 0, st>>>(x, w1, b1, h1, save_h1, nl, mask_parity, g.active_val, B); break;
-        case 3: nd_layer1_kernel<3><<<grid1, 256, 0, st>>>(x, w1, b1, h1, save_h1, nl, mask_parity, g.active_val, B); break;
-        default: nd_layer1_kernel<4><<<grid1, 256, 0, st>>>(x, w1, b1, h1, save_h1, nl, mask_parity, g.active_val, B); break;
+        case 2: nd_layer1_kernel<2><<<grid1, 256, 0, st>>>(x, w1, b1, h1, save_h1, yf, nl, mask_parity, g.active_val, B); break;
+        case 3: nd_layer1_kernel<3><<<grid1, 256, 0, st>>>(x, w1, b1, h1, save_h1, yf, nl, mask_parity, g.active_val, B); break;
+        default: nd_layer1_kernel<4><<<grid1, 256, 0, st>>>(x, w1, b1, h1, save_h1, yf, nl, mask_parity, g.active_val, B); break;
     }
     if (int e = check_launch()) return e;
 
