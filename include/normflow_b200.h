@@ -329,6 +329,18 @@ int nfk_fusednd_step_train(const float* x, const float* w1, const float* b1, con
                            float* h1, float* h2, float* out, int64_t B,
                            void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Data gradient of one circular 3^D convolution layer of a ConvAct stack on the tensor cores -- what autograd runs
+ * for modules.py:131-145 in Fitter.step (_normflowcore.py:288):
+ *     gin[b][ci][s] = act'(h[b][ci][s]) * sum_{co, t} w[co][ci][t] * gpre[b][co][s - t]
+ * with act' = 1 - h^2 (h = post-activation output of the tanh layer below, [B][Ci][V]) or 1 when h is NULL.
+ * gpre [B][Co][V] = d loss / d (this layer's pre-activation output), w [Co][Ci][3^D], gin [B][Ci][V].
+ * Ci in {8, 16, 32, 64}, 1 <= Co <= 64, 2-D .. 4-D lattices with even extents; NFK_EUNSUPPORTED otherwise (the
+ * caller then uses nfk_conv_circ_fwd with transposed weights).  Operands are fp16 pairs scaled by a power of two
+ * found from max |gpre| on the device.  `workspace`: nfk_convnd_dgrad_workspace bytes, 256-byte aligned.        */
+int64_t nfk_convnd_dgrad_workspace(nfk_lattice lat, int Co, int Ci, int64_t B);
+int nfk_convnd_dgrad(const float* gpre, const float* w, const float* h, float* gin, int Co, int Ci,
+                     nfk_lattice lat, int64_t B, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------- PSD block (spectral part) ---
  * PSDBlock_ / FFTNet_ (psd_.py:25-40, fftflow_.py:121-131,167-180): the real-to-complex
  * and complex-to-real transforms are cuFFT calls made by the host package; these entries

@@ -656,6 +656,36 @@ def _conv_call(inp, w, transposed, bias, in_mask, in_keep, act, dact_from, dact_
     return out
 
 
+def _conv_dgrad_tc(gpre, w, h, dact_kind, shape, ksize):
+    """Data gradient of a layer on the tensor cores (nfk_convnd_dgrad): d loss / d pre-activation of the layer below
+    from `gpre` = d loss / d this layer's output, `w` (Co, Ci, 3, ..) and the post-activation `h` of the layer below
+    (tanh) or None.  Returns None where the kernel does not apply (the caller then runs the CUDA-core convolution
+    with transposed weights); NFK_DGRAD_TC=0 switches it off."""
+    Co, Ci = int(w.shape[0]), int(w.shape[1])
+    if (os.environ.get('NFK_DGRAD_TC') == '0' or int(ksize) != 3 or not 2 <= len(shape) <= 4
+            or Ci not in (8, 16, 32, 64) or Co > 64 or dact_kind not in (0, _C.ACT['tanh'])):
+        return None
+    lat = _C.lattice(shape)
+    B = gpre.shape[0]
+    per_sample = int(lib().nfk_convnd_dgrad_workspace(lat, Co, Ci, 1))
+    if per_sample <= 0:
+        return None
+    cap = int(float(os.environ.get("NFK_ND_WORKSPACE_GB", "24")) * 2 ** 30)
+    chunk = max(1, min(B, cap // max(per_sample, 1)))
+    need = int(lib().nfk_convnd_dgrad_workspace(lat, Co, Ci, chunk))
+    workspace = torch.empty((need,), dtype=torch.uint8, device=gpre.device)
+    gin = torch.empty((B, Ci) + tuple(shape), dtype=torch.float32, device=gpre.device)
+    if dact_kind == 0:
+        h = None
+    with _C.timed(f"convnd_dgrad[{Co}->{Ci}]"):
+        for lo in range(0, B, chunk):
+            hi = min(B, lo + chunk)
+            check(lib().nfk_convnd_dgrad(dev(gpre[lo:hi]), dev(w), None if h is None else dev(h[lo:hi]), dev(gin[lo:hi]),
+                                         Co, Ci, lat, hi - lo, dev(workspace, torch.uint8), need, stream()),
+                  "convnd_dgrad")
+    return gin
+
+
 def _conv_weight_grad(inp, in_mask, in_keep, gpre, w_shape, want_bias, shape, ksize, g_parity=None):
     Co, Ci = w_shape[0], w_shape[1]
     gw = torch.zeros(w_shape, dtype=torch.float32, device=inp.device)
@@ -752,6 +782,11 @@ def _conv_stack_backward(hs, weights, has_bias, acts, ksize, shape, in_mask, in_
             gpre = None
             break
         # d/d(input of layer i): conv of gpre with w^T (taps flipped); multiply by act'(h_{i})
+        if not first:
+            g_tc = _conv_dgrad_tc(gpre, w.contiguous(), hs[i], acts[i - 1], shape, ksize)
+            if g_tc is not None:
+                gpre = g_tc
+                continue
         gpre = _conv_call(gpre, w.contiguous(), 1, None, None, 0, 0, hs[i] if not first else None,
                           acts[i - 1] if not first else 0, shape, ksize, Co, Ci,
                           in_parity=gpre_parity if i == n - 1 else None)

@@ -87,10 +87,23 @@ struct NdArgs {
     float* save;                 // training forward: this layer's output, float32 channel-major [B][save_ch][V] (or NULL):
     int save_ch;                 // hidden layer: post-activation h (H channels); last layer: conditioner output (P channels,
                                  // written at the active sites only)
+    const float* act;            // data gradient (MODE 2): post-activation output h of the layer below, [B][save_ch][V]
+                                 // (multiplies by tanh' = 1 - h^2), or NULL
+    const float* amax;           // data gradient: max |input| on the device; the records carry input * nd_grad_scale(amax)
     long long B;
     NdGeom g;
     RqsCfg cfg;
 };
+
+// Power of two that brings the largest magnitude of a gradient tensor to [4096, 8192): fp16 pairs have float16's
+// exponent range, gradients of a mean over the batch sit far below it.
+__host__ __device__ __forceinline__ float nd_grad_scale(float amax) {
+    if (!(amax > 0.f) || amax > 3.0e38f) return 1.f;
+    int e;
+    frexpf(amax, &e);                                   // amax = m 2^e, m in [0.5, 1)
+    e = 13 - e;
+    return ldexpf(1.f, e > 100 ? 100 : e);
+}
 
 // n / d by the precomputed magic ceil(2^32 / d) (exact for n d < 2^32); d == 1 has no 32-bit magic
 __device__ __forceinline__ int nd_div(int n, int d, uint32_t magic) { return d == 1 ? n : tc_div(n, magic); }
@@ -187,6 +200,52 @@ __device__ __forceinline__ void nd_store_site_split(uint4* base, int Eh, const i
         for (int d = 0; d < ND; ++d) o += (mask >> d) & 1 ? diff[d] : 0;
         base[(o & 1) * Eh + (o >> 1)] = hi;
         base[(2 + (o & 1)) * Eh + (o >> 1)] = lo;
+    }
+}
+
+// Data gradient: the same image for the TRANSPOSED layer with mirrored taps -- output rows are the layer's Ci input
+// channels, the K groups its Co output channels (zero beyond Co): d/d in[ci](s) = sum_{co, t} w[co][ci][t] g[co](s - t).
+__global__ void nd_prep_weights_t_kernel(const float* w, int Co, int Ci, int taps, int NH, int npass, int bdup, __half* img) {
+    const int N2 = 2 * NH, G = (Co + 7) / 8;
+    const long long total = (long long)npass * taps * G * N2 * 8;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int k8 = (int)(e & 7);
+        long long r = e >> 3;
+        const int n = (int)(r % N2); r /= N2;
+        const int gi = (int)(r % G); r /= G;
+        const int t = (int)(r % taps);
+        const int pass = (int)(r / taps);
+        const int ci = pass * NH + (n < NH ? n : n - NH), co = gi * 8 + k8;
+        __half val = __float2half_rn(0.f);
+        if (ci < Ci && co < Co) {
+            const float v = w[((long long)co * Ci + ci) * taps + (taps - 1 - t)];
+            const __half hi = __float2half_rn(v);
+            val = n < NH ? hi : __float2half_rn((v - __half2float(hi)) * kLoScale);
+        }
+        for (int kg = 0; kg < bdup; ++kg)
+            img[((((long long)pass * taps + t) * G + gi) * bdup + kg) * N2 * 8 + n * 8 + k8] = val;
+    }
+}
+
+// max |v| of a float32 array -> *amax (bit pattern of a non-negative float: unsigned order = float order)
+__global__ void __launch_bounds__(256) nd_amax_kernel(const float* __restrict__ v, long long n, unsigned* amax) {
+    float m = 0.f;
+    const long long n4 = n >> 2;
+    const float4* v4 = reinterpret_cast<const float4*>(v);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 q = NFK_LDG(v4 + i);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(q.x), fabsf(q.y))), fmaxf(fabsf(q.z), fabsf(q.w)));
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) m = fmaxf(m, fabsf(NFK_LDG(v + (n4 << 2) + threadIdx.x)));
+    if (!(m == m)) m = __int_as_float(0x7f800000);      // NaN -> inf: the scale falls back to 1, the NaN propagates
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ float sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) m = fmaxf(m, sm[i]);
+        atomicMax(amax, __float_as_uint(m));
     }
 }
 
@@ -323,6 +382,38 @@ __global__ void __launch_bounds__(256) nd_layer1_kernel(const float* __restrict_
     }
 }
 
+// Data gradient input: float32 channel-major g [B][C][V] -> scaled fp16-pair records with their periodic images
+// ([B][ceil(C/8)][2][Vp], zero channels beyond C).  A thread owns one site of one channel group.
+template <int D>
+__global__ void __launch_bounds__(256) nd_pack_records_kernel(const float* __restrict__ gsrc, int C, const float* __restrict__ amax,
+                                                              uint4* __restrict__ out_rec, const NdLat lat, long long B) {
+    const int gidx = blockIdx.y, G = gridDim.y;
+    const int bps = (lat.V + 255) >> 8;
+    const long long b = blockIdx.x / bps;
+    const int site = (int)(blockIdx.x - b * bps) * 256 + threadIdx.x;
+    if (b >= B || site >= lat.V) return;
+    const float scale = nd_grad_scale(NFK_LDG(amax));
+    int Ld[D], ps[D], c[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) { Ld[d] = lat.L[d]; ps[d] = lat.pstride[d]; }
+    int rem = site;
+#pragma unroll
+    for (int d = D - 1; d >= 0; --d) {
+        const int q = nd_div(rem, Ld[d], lat.magic_L[d]);
+        c[d] = rem - q * Ld[d];
+        rem = q;
+    }
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int ch = gidx * 8 + k;
+        v[k] = ch < C ? scale * NFK_LDG(gsrc + (b * C + ch) * (long long)lat.V + site) : 0.f;
+    }
+    uint4 hi, lo;
+    nd_records(v, hi, lo);
+    nd_store_site<D>(out_rec + (b * G + gidx) * 2LL * lat.Vp, lat.Vp, c, Ld, ps, hi, lo);
+}
+
 // ------------------------------------------------------------------------------------------- layers 2 and 3
 __device__ __forceinline__ void nd_bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -333,14 +424,15 @@ __device__ __forceinline__ void nd_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 
 // MODE 0: hidden layer (H -> OC of the H output channels per pass, tanh) -> records; the template argument K
-// carries OC (8, 16 or 32).  MODE 1: last layer (H -> P) + transform of the field.
+// carries OC (8, 16 or 32).  MODE 1: last layer (H -> P) + transform of the field.  MODE 2: data gradient of a layer
+// (records of d loss / d pre-activation, transposed mirrored weights) -> float32 [B][Ci][V], times 1 - h^2.
 // No CTA-wide barrier inside the unit loop: one thread of the last warp fetches the box of a unit with bulk
 // copies (the tile and its halo are contiguous runs of the padded record arrays, one pair of planes per group of
 // 8 input channels), issues the MMAs of its M tiles -- taps x channel groups, K = 16 = 8 channels hi | lo each --
 // into a ring of TMEM accumulator slots and commits each tile to an mbarrier; the epilogue warps drain the ring.
 template <int MODE, int KIND, int K, int INV>
 __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a) {
-    constexpr int P = MODE == 0 ? K : (KIND == 0 ? 2 : 3 * K - 2);
+    constexpr int P = MODE != 1 ? K : (KIND == 0 ? 2 : 3 * K - 2);
     constexpr int NH = (P + 7) / 8 * 8, N2 = 2 * NH;
     extern __shared__ __align__(128) uint8_t smem[];
     const NdGeom& g = a.g;
@@ -356,9 +448,9 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
 
     // ---- one-time set-up ---------------------------------------------------------------------------
     {
-        const int nbias = MODE == 0 ? g.npass * NH : NH;
+        const int nbias = MODE != 1 ? g.npass * NH : NH;
         for (int c = tid; c < nbias; c += kNdThreads) {
-            const float v = (a.bias && (MODE == 0 || c < P)) ? NFK_LDG(a.bias + c) : 0.f;
+            const float v = (a.bias && (MODE != 1 || c < P)) ? NFK_LDG(a.bias + c) : 0.f;
             bias_s[c] = MODE == 0 ? kTwoLog2e * v : v;
         }
         if (tid == 0) {
@@ -546,6 +638,7 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
     } else {
         // =============================== epilogue =======================================================
         const int quarter = warp & 3, half = warp >> 2;            // TMEM lanes 32 quarter .. +31; tiles of my parity
+        const float inv_scale = MODE == 2 ? 1.f / nd_grad_scale(NFK_LDG(a.amax)) : 1.f;
         const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
         int slot = 0;
         uint32_t ring_phase = 0;
@@ -636,6 +729,18 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
 #pragma unroll
                             for (int c = 0; c < 8; ++c) sp[(long long)c * g.V] = v[c];
                         }
+                    }
+                } else if (MODE == 2) {
+                    // data gradient: undo the input scale, multiply by tanh'(pre-activation) = 1 - h^2 of the layer below
+#pragma unroll
+                    for (int c = 0; c < NH; ++c) {
+                        const long long o = (b * a.save_ch + pass * NH + c) * (long long)g.V + site;
+                        float v = fmaf(lo[c], 1.f / kLoScale, hi[c]) * inv_scale;
+                        if (a.act) {
+                            const float h = NFK_LDG(a.act + o);
+                            v *= fmaf(-h, h, 1.f);
+                        }
+                        a.save[o] = v;
                     }
                 } else {
                     const float xv = NFK_LDG(a.x + b * (long long)g.V + site);
@@ -1012,4 +1117,101 @@ extern "C" int nfk_fusednd_step_train(const float* x, const float* w1, const flo
     if (!h1 || !h2 || !out) return NFK_EINVAL;
     return nd_step_impl(x, w1, b1, w2, b2, w3, b3, H, kind, prm, lat, mask_parity, parity, 0, log_in, y, log_out, B,
                         workspace, workspace_bytes, stream, h1, h2, out);
+}
+
+// ------------------------------------------------------------------------------------------- data gradient
+namespace {
+
+struct NdDgradPlan {
+    NdGeom g;
+    int OC, npass, G, bdup;
+    long long img_bytes, rec_bytes, total;
+};
+
+int nd_dgrad_plan(NdDgradPlan& p, nfk_lattice lat, int Co, int Ci, long long B) {
+    if (!nd_width_ok(Ci) || Co < 1 || Co > 64 || !nd_lattice_ok(lat)) return NFK_EUNSUPPORTED;
+    auto al = [](long long v) { return (v + 255) / 256 * 256; };
+    p.OC = nd_oc(Ci);
+    p.npass = Ci / p.OC;
+    p.G = (Co + 7) / 8;
+    p.bdup = nd_bdup();
+    p.g = NdGeom{};
+    nd_lattice(p.g, lat);
+    if (!nd_plan(p.g, 2 * p.OC, p.G, p.npass, p.bdup, (uint32_t)nd_props().max_smem)) return NFK_EUNSUPPORTED;
+    p.img_bytes = al((long long)p.npass * p.g.taps * p.G * p.bdup * 2 * p.OC * 16);
+    p.rec_bytes = al((B > 0 ? B : 1) * p.G * p.g.Vp * 32LL);
+    p.total = 256 + p.img_bytes + p.rec_bytes;
+    return NFK_OK;
+}
+
+}  // namespace
+
+extern "C" int64_t nfk_convnd_dgrad_workspace(nfk_lattice lat, int Co, int Ci, int64_t B) {
+    NdDgradPlan p;
+    if (int e = nd_dgrad_plan(p, lat, Co, Ci, B)) return e;
+    return p.total;
+}
+
+/* Data gradient of one circular 3^D convolution layer of a ConvAct stack on the tensor cores
+ * (autograd of modules.py:131-145): gin[b][ci][s] = act'(h[b][ci][s]) * sum_{co, t} w[co][ci][t] gpre[b][co][s - t],
+ * act' = 1 - h^2 for the tanh layer below (h = its post-activation output) or 1 when `h` is NULL.
+ * gpre [B][Co][V], w [Co][Ci][3^D], h / gin [B][Ci][V]; Ci in {8, 16, 32, 64}, Co <= 64, even extents, 2-D .. 4-D.
+ * The input is packed into fp16-pair records scaled by a power of two taken from its largest magnitude (found on the
+ * device), so the result has float32-level accuracy at any gradient magnitude. */
+extern "C" int nfk_convnd_dgrad(const float* gpre, const float* w, const float* h, float* gin, int Co, int Ci,
+                                nfk_lattice lat, int64_t B, void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!gpre || !w || !gin || !workspace) return NFK_EINVAL;
+    NdDgradPlan p;
+    if (int e = nd_dgrad_plan(p, lat, Co, Ci, B)) return e;
+    if (B <= 0) return NFK_OK;
+    if (workspace_bytes < p.total || ((uintptr_t)workspace % 256) != 0) return NFK_EINVAL;
+    cudaStream_t st = NFK_STREAM(stream);
+    const NdGeom& g = p.g;
+    if (getenv("NFK_ND_DEBUG"))
+        fprintf(stderr, "nfk_convnd_dgrad: T = %d %d %d %d  box %d  tiles/unit %d  G %d  passes %d  chains %d  slots %d  smem %u B\n",
+                g.T[0], g.T[1], g.T[2], g.T[3], g.nbox, g.nt, g.G, g.npass, g.nchunk, g.nslots, g.smem_bytes);
+    uint8_t* wsp = static_cast<uint8_t*>(workspace);
+    unsigned* amax = reinterpret_cast<unsigned*>(wsp);
+    __half* img = reinterpret_cast<__half*>(wsp + 256);
+    uint4* rec = reinterpret_cast<uint4*>(wsp + 256 + p.img_bytes);
+    const int D = lat.ndim;
+
+    if (cudaMemsetAsync(amax, 0, 4, st) != cudaSuccess) return NFK_ECUDA;
+    const long long n = (long long)B * Co * g.V;
+    long long ablocks = (n / 4 + 255) / 256;
+    if (ablocks > 148 * 16) ablocks = 148 * 16;
+    if (ablocks < 1) ablocks = 1;
+    nd_amax_kernel<<<(unsigned)ablocks, 256, 0, st>>>(gpre, n, amax);
+    if (int e = check_launch()) return e;
+    nd_prep_weights_t_kernel<<<64, 256, 0, st>>>(w, Co, Ci, g.taps, p.OC, p.npass, p.bdup, img);
+    if (int e = check_launch()) return e;
+
+    NdLat nl{};
+    for (int d = 0; d < 4; ++d) {
+        const int j = d + 4 - D;
+        nl.L[d] = d < D ? g.L[j] : 1;
+        nl.gstride[d] = d < D ? g.gstride[j] : 0;
+        nl.pstride[d] = d < D ? g.pstride[j] : 0;
+        nl.magic_L[d] = nd_magic(nl.L[d]);
+    }
+    nl.V = g.V;
+    nl.Vp = g.Vp;
+    const long long blocks = B * ((nl.V + 255) / 256);
+    if (blocks >= (1LL << 31)) return NFK_EUNSUPPORTED;
+    const dim3 gridp((unsigned)blocks, (unsigned)p.G);
+    const float* am = reinterpret_cast<const float*>(amax);
+    switch (D) {
+        case 2: nd_pack_records_kernel<2><<<gridp, 256, 0, st>>>(gpre, Co, am, rec, nl, B); break;
+        case 3: nd_pack_records_kernel<3><<<gridp, 256, 0, st>>>(gpre, Co, am, rec, nl, B); break;
+        default: nd_pack_records_kernel<4><<<gridp, 256, 0, st>>>(gpre, Co, am, rec, nl, B); break;
+    }
+    if (int e = check_launch()) return e;
+
+    NdArgs a{};
+    a.in_rec = rec; a.bimg = img; a.B = B; a.g = g;
+    a.save = gin; a.save_ch = Ci; a.act = h; a.amax = am;
+    a.cfg = RqsCfg{0.f, 1.f, 0.f, 1.f, 0, 0};
+    if (p.OC == 8) return nd_launch<2, 0, 8, 0>(a, st);
+    if (p.OC == 16) return nd_launch<2, 0, 16, 0>(a, st);
+    return nd_launch<2, 0, 32, 0>(a, st);
 }

@@ -996,6 +996,83 @@ def test_nd_step_batch_slices_give_the_same_result(monkeypatch):
     assert torch.equal(y0, y1) and torch.allclose(l0, l1, rtol=0, atol=1e-5)
 
 
+@pytest.mark.parametrize("shape,kind", [((4, 6, 8), 0), ((6, 8, 10), 1), ((4, 4, 4, 4), 1), ((12, 20), 1)])
+def test_nd_active_only_last_layer_matches_the_full_one(shape, kind, monkeypatch):
+    """The last layer over the active sites only (parity-split hidden records, frozen sites passed through by the
+    layer-1 kernel) against the same kernel over every site (NFK_ND_COMPACT=0).  The output buffer is poisoned
+    first: the caching allocator hands the NaN block back to the step's torch.empty."""
+    from normflow__b200 import _ops
+    D, K, B = len(shape), 8, 3
+    g = torch.Generator('cpu').manual_seed(31)
+    P = 2 if kind == 0 else 3 * K - 2
+    k3 = (3,) * D
+    rnd = lambda *s, scale=1.0: (torch.randn(*s, generator=g, device='cpu') * scale).to(DEV)
+    fan = 8 * 3 ** D
+    w = [rnd(8, 1, *k3, scale=0.9 / 3 ** (D / 2)), rnd(8, 8, *k3, scale=0.5 / fan ** 0.5), rnd(P, 8, *k3, scale=0.5 / fan ** 0.5)]
+    b = [rnd(8, scale=0.1), rnd(8, scale=0.1), rnd(P, scale=0.1)]
+    x = rnd(B, *shape, scale=1.3)
+    prm = _C.RqsParams(K, -5.0, 5.0, -5.0, 5.0, 1, 1) if kind == 1 else None
+    for parity in (0, 1):
+        res = {}
+        for flag in ('1', '0'):
+            monkeypatch.setenv('NFK_ND_COMPACT', flag)
+            poison = torch.full_like(x, float('nan'))
+            del poison
+            with torch.no_grad():
+                res[flag] = _ops.fusednd_step(x, w, b, kind, prm, 0, parity, 0, False)
+        frozen = torch.from_numpy(O.evenodd_mask(shape, parity=0) != (1 if parity == 0 else 0)).to(DEV)
+        for y, _ in res.values():
+            assert torch.equal(y[:, frozen], x[:, frozen])
+        assert torch.allclose(res['1'][0], res['0'][0], atol=2e-6, rtol=2e-6)
+        assert torch.allclose(res['1'][1], res['0'][1], atol=1e-4, rtol=1e-6)
+
+
+@pytest.mark.parametrize("shape,Co,Ci,B,tanh,gscale,sparse", [
+    ((16, 24), 28, 8, 3, True, 1.0, True),            # last layer of the RQ-spline conditioner (K = 10), checkerboard-sparse gradient
+    ((64, 64), 8, 8, 2, True, 1e-9, False),           # gradients of a mean over a large batch: far below float16's range
+    ((8, 8, 8), 28, 8, 2, True, 3e4, True),
+    ((8, 8, 8), 2, 8, 2, False, 1.0, False),          # affine conditioner, no activation below
+    ((4, 6, 8), 8, 16, 3, True, 1.0, False),
+    ((4, 4, 4, 4), 28, 8, 2, True, 1e-5, True),
+    ((6, 4, 4, 8), 8, 8, 2, True, 1.0, False),
+    ((16, 16), 64, 64, 2, True, 1.0, False),          # two passes of 32 output channels, eight input groups
+    ((12, 20), 13, 32, 2, True, 1.0, False),          # Co not a multiple of 8
+])
+def test_tensor_core_data_gradient(shape, Co, Ci, B, tanh, gscale, sparse):
+    """nfk_convnd_dgrad (fp16-pair implicit GEMM on transposed, mirrored weights; input scaled by a power of two from
+    its largest magnitude) against float64 autograd of the circular convolution (torch, 2-D / 3-D) and against the
+    float32 CUDA-core kernel that conv.npz pins to the reference (all dimensions)."""
+    from normflow__b200 import _ops
+    D = len(shape)
+    g = torch.Generator('cpu').manual_seed(41)
+    rnd = lambda *s, scale=1.0: (torch.randn(*s, generator=g, device='cpu') * scale).to(DEV)
+    w = rnd(Co, Ci, *(3,) * D, scale=0.7 / (Ci * 3 ** D) ** 0.5)
+    pre = rnd(B, Ci, *shape)
+    h = torch.tanh(pre) if tanh else None
+    gpre = rnd(B, Co, *shape) * gscale
+    if sparse:
+        gpre = gpre * torch.from_numpy(O.evenodd_mask(shape, parity=0)).to(DEV)
+    act = _C.ACT['tanh'] if tanh else 0
+    got = _ops._conv_dgrad_tc(gpre, w, h, act, shape, 3)
+    assert got is not None
+    ref32 = _ops._conv_call(gpre, w, 1, None, None, 0, 0, h, act, shape, 3, Co, Ci)
+    scale = float(ref32.abs().max())
+    assert torch.isfinite(got).all()
+    assert float((got - ref32).abs().max()) <= 3e-6 * scale
+    if D <= 3:
+        conv = torch.nn.functional.conv2d if D == 2 else torch.nn.functional.conv3d
+        xin = pre.double().requires_grad_(True)
+        act_in = torch.tanh(xin) if tanh else xin
+        pad = torch.nn.functional.pad(act_in, (1, 1) * D, mode='circular')
+        out = conv(pad, w.double())
+        ref64, = torch.autograd.grad(out, xin, gpre.double())
+        err = float((got.double() - ref64).abs().max())
+        err32 = float((ref32.double() - ref64).abs().max())
+        scale64 = float(ref64.abs().max())
+        print(f"dgrad {shape} {Co}->{Ci}: tensor-core err {err / scale64:.2e}, float32 CUDA-core err {err32 / scale64:.2e} (of max |g|)")
+        assert err <= 2e-6 * scale64
+
+
 def test_nd_step_is_the_path_taken_in_3d_and_4d(monkeypatch):
     """Evaluation of a 3-D / 4-D coupling must go through nfk_fusednd_step (same numbers as the layer-by-layer
     kernels up to float32 rounding, but not bit-identical)."""
