@@ -341,6 +341,17 @@ int64_t nfk_convnd_dgrad_workspace(nfk_lattice lat, int Co, int Ci, int64_t B);
 int nfk_convnd_dgrad(const float* gpre, const float* w, const float* h, float* gin, int Co, int Ci,
                      nfk_lattice lat, int64_t B, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Weight and bias gradient of one circular 3^D convolution layer with 8 input channels on the tensor cores (autograd
+ * of convNd.py:84-127 / modules.py:131-145 in Fitter.step):
+ *     gw[co][ci][t] += sum_{b, s} gpre[b][co][s] * h[b][ci][s + t - 1],     gb[co] += sum_{b, s} gpre[b][co][s]
+ * h [B][8][V] the layer's input, gpre [B][Co][V], Co <= 32; gw [Co][8][3^D] and gb [Co] (or NULL) are ACCUMULATED into.
+ * The sites are the GEMM's K dimension, read from site-major fp16-pair records as MN-major operands (no im2col).
+ * 2-D .. 4-D, even extents, innermost extent a multiple of 16; NFK_EUNSUPPORTED otherwise (use
+ * nfk_conv_circ_bwd_weight).  `workspace`: nfk_convnd_wgrad_workspace bytes, 256-byte aligned.                    */
+int64_t nfk_convnd_wgrad_workspace(nfk_lattice lat, int Co, int Ci, int64_t B);
+int nfk_convnd_wgrad(const float* h, const float* gpre, float* gw, float* gb, int Co, int Ci,
+                     nfk_lattice lat, int64_t B, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------- PSD block (spectral part) ---
  * PSDBlock_ / FFTNet_ (psd_.py:25-40, fftflow_.py:121-131,167-180): the real-to-complex
  * and complex-to-real transforms are cuFFT calls made by the host package; these entries

@@ -704,6 +704,24 @@ def _conv_weight_grad(inp, in_mask, in_keep, gpre, w_shape, want_bias, shape, ks
         if rc != _C.EUNSUPPORTED:
             check(rc, "conv2d_wgrad_tc")
             return gw, gb
+    nd_mode = os.environ.get('NFK_WGRAD_ND_TC')
+    if (in_mask is None and Ci == 8 and Co <= 32 and int(ksize) == 3 and 2 <= len(shape) <= 4 and shape[-1] % 16 == 0
+            and (nd_mode == '1' or (nd_mode != '0' and len(shape) >= 3))):
+        # sites as the K dimension of tensor-core GEMMs on the site-major records (nfk_convnd_wgrad)
+        lat = _C.lattice(shape)
+        B = inp.shape[0]
+        per_sample = int(lib().nfk_convnd_wgrad_workspace(lat, Co, Ci, 1))
+        if per_sample > 0:
+            cap = int(float(os.environ.get("NFK_ND_WORKSPACE_GB", "24")) * 2 ** 30)
+            chunk = max(1, min(B, cap // max(per_sample, 1)))
+            need = int(lib().nfk_convnd_wgrad_workspace(lat, Co, Ci, chunk))
+            workspace = torch.empty((need,), dtype=torch.uint8, device=inp.device)
+            with _C.timed(f"convnd_wgrad[{Ci}->{Co}]"):
+                for lo in range(0, B, chunk):
+                    hi = min(B, lo + chunk)
+                    check(lib().nfk_convnd_wgrad(dev(inp[lo:hi]), dev(gpre[lo:hi]), dev(gw), dev(gb), Co, Ci, lat, hi - lo,
+                                                 dev(workspace, torch.uint8), need, stream()), "convnd_wgrad")
+            return gw, gb
     if in_mask is not None and Ci == 1 and len(shape) == 2 and int(ksize) == 3:
         # first layer: apply Mask.split once (one cheap pass) so that the streamed weight-gradient kernel can be used
         inp, in_mask = mask_select(inp, in_mask, in_keep), None

@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(256) nd_pack_records_kernel(const float* __res
     const long long b = blockIdx.x / bps;
     const int site = (int)(blockIdx.x - b * bps) * 256 + threadIdx.x;
     if (b >= B || site >= lat.V) return;
-    const float scale = nd_grad_scale(NFK_LDG(amax));
+    const float scale = amax ? nd_grad_scale(NFK_LDG(amax)) : 1.f;
     int Ld[D], ps[D], c[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) { Ld[d] = lat.L[d]; ps[d] = lat.pstride[d]; }
@@ -1214,4 +1214,452 @@ extern "C" int nfk_convnd_dgrad(const float* gpre, const float* w, const float* 
     if (p.OC == 8) return nd_launch<2, 0, 8, 0>(a, st);
     if (p.OC == 16) return nd_launch<2, 0, 16, 0>(a, st);
     return nd_launch<2, 0, 32, 0>(a, st);
+}
+
+// ------------------------------------------------------------------------------------------- weight gradient
+// gw[co][ci][t] = sum_{b, s} gpre[b][co][s] h[b][ci][s + t - 1]  (adjoint of convNd.py:84-127) as tensor-core GEMMs with
+// the SITES as the K dimension, read straight from the site-major records without an im2col: eight consecutive records
+// (8 sites x 8 channels x fp16) are one core matrix of an MN-MAJOR no-swizzle operand (checked on hardware,
+// scratch/mn_probe.cu: SBO = stride between MN blocks, LBO = stride between K blocks of 8 sites; an M = 64 accumulator
+// keeps row i in TMEM lane 32 (i / 16) + i % 16).
+//   A (M = 64): the planes [channel group of gpre][hi | lo] of a tile, block stride = plane stride
+//   B (N = 24): the three taps of the innermost axis = the SAME records of h started one record apart (block stride =
+//               16 bytes, overlapping core matrices); the taps of the outer axes move the start by box strides
+//   D (64 x 24 per (outer tap group, hi | lo of h)): TMEM columns, accumulated over the K steps (16 sites each) of a
+//               chain of units, then added into float32 accumulators in shared memory by the epilogue warps (the tensor
+//               core truncates when it accumulates: chains stay at ~32 steps), atomics into gw once per CTA and pass.
+// The bias gradient is one more MMA per K step against a record of ones.
+namespace {
+
+constexpr int kWgIssuers = 4;            // MMA-issuing warps: the outer tap groups are dealt among them (one thread's issue
+                                         // loop, ~50 cycles per MMA, is slower than an M64 x N24 x K16 MMA)
+constexpr int kWgThreads = 32 * (4 + kWgIssuers);   // + 4 epilogue warps (TMEM lane quarters = gpre channel groups)
+constexpr int kWgGroupCols = 48;         // accumulator columns of one outer tap group: [dx][ci] for h hi, then for h lo
+constexpr int kWgMaxGroups = 9;          // outer tap groups per pass (432 columns + 8 for the bias)
+constexpr int kWgChainSteps = 64;        // K steps accumulated in TMEM before the float32 flush
+
+struct WgGeom {
+    int D, taps, ngroups, npass, gpp;
+    int L[4], T[4], ntile[4], box[4], bstride[4], pstride[4];     // dummy axes: extent 1, strides 0
+    uint32_t magic_ntile[4], magic_box[4];
+    int nbox, tiles_per_sample, V, Vp, split, nruns, run_rec;
+    int rows, row_len, tile_sites;
+    int Gg, Co;
+    int chain_units;
+    int acc_stride;                      // floats per row of the shared accumulators (odd: the 16 rows of a warp on different banks)
+    int nsets;                           // 2: two accumulator column sets in TMEM (the flush of a chain overlaps the next chain)
+    int toff[27];                        // box offset of an outer tap group
+    uint32_t hplane_bytes, gplane_bytes, buf_bytes, off_acc, off_ones, off_bar, smem_bytes;
+};
+
+struct WgArgs {
+    const uint4* h_rec;                  // [B][1][2][Vp] padded records of the layer's input (8 channels)
+    const uint4* g_rec;                  // [B][Gg][2][Vp] padded records of d loss / d pre-activation, scaled
+    const float* amax;
+    float* gw;                           // [Co][8][taps], accumulated into
+    float* gbias;                        // [Co] or NULL
+    long long B;
+    WgGeom g;
+};
+
+#ifndef NFK_WG_M
+#define NFK_WG_M 64
+#endif
+constexpr int kWgM = NFK_WG_M;           // 128: rows 64 .. 127 are junk (the planes that follow in shared memory); A/B of the MMA cost
+__device__ __forceinline__ uint32_t wg_idesc(int N) {      // f16 x f16 -> f32, A and B MN-major
+    return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kWgM >> 4) << 24);
+}
+
+// Use n (0, 1, ..) of a barrier is waited for with parity n & 1; every waiter sees the completions of its barrier in
+// order and never falls two behind (an issuer cannot start a chain in an accumulator set before that set is flushed).
+__global__ void __launch_bounds__(kWgThreads, 1) convnd_wgrad_tc_kernel(const WgArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const WgGeom& g = a.g;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float* acc_s = reinterpret_cast<float*>(smem + g.off_acc);
+    uint64_t* loaded = reinterpret_cast<uint64_t*>(smem + g.off_bar);       // [2] box of a unit has arrived
+    uint64_t* mma_done = loaded + 2;                                        // [2] the MMAs reading a buffer have completed
+    uint64_t* chain_done = mma_done + 2;                                    // [2] the MMAs of a chain (accumulator set) have completed
+    uint64_t* flushed = chain_done + 2;                                     // [2] the epilogue has drained an accumulator set
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(flushed + 2);
+    const int AS = g.acc_stride;
+
+    for (int i = tid; i < 64 * AS; i += kWgThreads) acc_s[i] = 0.f;
+    if (tid < 64) reinterpret_cast<__half*>(smem + g.off_ones)[tid] = __float2half_rn(1.f);     // 8 sites x 8 "channels" of ones
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(tc::smem_u32(loaded + i), 1);
+            tc::mbar_init(tc::smem_u32(mma_done + i), kWgIssuers);
+            tc::mbar_init(tc::smem_u32(chain_done + i), kWgIssuers);
+            tc::mbar_init(tc::smem_u32(flushed + i), 4);
+        }
+        tc::fence_mbar_init();
+    }
+    if (warp == 4) tc::tmem_alloc(tc::smem_u32(tmem_slot), 512);
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const long long nunits = a.B * g.tiles_per_sample;
+    const long long mine = nunits > blockIdx.x ? (nunits - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long chains = (mine + g.chain_units - 1) / g.chain_units;
+    const float inv_scale = 1.f / nd_grad_scale(NFK_LDG(a.amax));
+    const int set_cols = g.nsets == 2 ? 256 : 0;
+
+    for (int pass = 0; pass < g.npass; ++pass) {
+        const int g0 = pass * g.gpp;
+        const int ng = g.ngroups - g0 < g.gpp ? g.ngroups - g0 : g.gpp;
+        const bool with_bias = pass == 0 && a.gbias != nullptr;
+        const int ncols = ng * kWgGroupCols + (with_bias ? 8 : 0);
+        if (warp >= 4) {
+            const int iw = warp - 4;
+            if (tc::elect_one()) {
+                const uint32_t base = tc::smem_u32(smem);
+                const uint32_t id24 = wg_idesc(24), id8 = wg_idesc(8);
+                const uint64_t o_desc = tc::make_desc(tc::smem_u32(smem + g.off_ones), 0, 0);
+                const bool bias_here = with_bias && iw == kWgIssuers - 1;
+                // this issuer's outer tap groups (at most three of the nine of a pass), their box offsets and accumulator columns
+                int n_mine = 0;
+                uint32_t off_mine[3] = {0, 0, 0}, col_mine[3] = {0, 0, 0};
+                for (int tg = iw; tg < ng && n_mine < 3; tg += kWgIssuers) {
+                    off_mine[n_mine] = (uint32_t)g.toff[g0 + tg];
+                    col_mine[n_mine] = (uint32_t)(tg * kWgGroupCols);
+                    ++n_mine;
+                }
+                auto load_unit = [&](long long k, int buf) {
+                    const long long unit = blockIdx.x + k * gridDim.x;
+                    const long long b = unit / g.tiles_per_sample;
+                    int trem = (int)(unit - b * g.tiles_per_sample);
+                    int org[4];
+#pragma unroll
+                    for (int d = 3; d >= 0; --d) {
+                        const int q = nd_div(trem, g.ntile[d], g.magic_ntile[d]);
+                        org[d] = (trem - q * g.ntile[d]) * g.T[d];
+                        trem = q;
+                    }
+                    const uint32_t bar = tc::smem_u32(loaded + buf);
+                    const uint32_t hdst = base + buf * g.buf_bytes, gdst = hdst + 2 * g.hplane_bytes;
+                    nd_expect_tx(bar, 2u * (uint32_t)g.nbox * 16u + 2u * g.Gg * (uint32_t)g.tile_sites * 16u);
+                    // the input's tile + halo: contiguous runs of the padded array
+                    const uint32_t run_bytes = (uint32_t)g.run_rec * 16;
+                    for (int k2 = 0; k2 < g.nruns; ++k2) {
+                        int rem = k2, so = 0;
+#pragma unroll
+                        for (int d = 3; d >= 0; --d) {
+                            if (d < g.split) {
+                                const int q = nd_div(rem, g.box[d], g.magic_box[d]);
+                                so += (org[d] + rem - q * g.box[d]) * g.pstride[d];
+                                rem = q;
+                            } else {
+                                so += org[d] * g.pstride[d];
+                            }
+                        }
+                        const uint4* src = a.h_rec + b * 2LL * g.Vp + so;
+                        nd_bulk_load(hdst + k2 * run_bytes, src, run_bytes, bar);
+                        nd_bulk_load(hdst + g.hplane_bytes + k2 * run_bytes, src + g.Vp, run_bytes, bar);
+                    }
+                    // the gradient's interior rows, compact
+                    const uint32_t row_bytes = (uint32_t)g.row_len * 16;
+                    uint32_t dst = gdst;
+                    for (int c0 = 0; c0 < g.T[0]; ++c0)
+                        for (int c1 = 0; c1 < g.T[1]; ++c1)
+                            for (int c2 = 0; c2 < g.T[2]; ++c2) {
+                                const int so = (org[0] + c0 + 1) * g.pstride[0] + (org[1] + c1 + 1) * g.pstride[1] +
+                                               (org[2] + c2 + 1) * g.pstride[2] + g.pstride[3];
+                                const uint4* src = a.g_rec + b * 2LL * g.Gg * g.Vp + so;
+                                for (int p = 0; p < 2 * g.Gg; ++p)
+                                    nd_bulk_load(dst + p * g.gplane_bytes, src + (long long)p * g.Vp, row_bytes, bar);
+                                dst += row_bytes;
+                            }
+                };
+                const long long ku0 = pass * mine;                 // units walked before this pass
+                if (iw == 0 && mine > 0) load_unit(0, (int)(ku0 & 1));
+                for (long long k = 0; k < mine; ++k) {
+                    const long long ku = ku0 + k;
+                    const int buf = (int)(ku & 1);
+                    if (iw == 0 && k + 1 < mine) {
+                        // the other buffer was read by unit ku - 1
+                        if (ku >= 1) tc::mbar_wait(tc::smem_u32(mma_done + (buf ^ 1)), (uint32_t)(((ku - 1) >> 1) & 1));
+                        load_unit(k + 1, buf ^ 1);
+                    }
+                    tc::mbar_wait(tc::smem_u32(loaded + buf), (uint32_t)((ku >> 1) & 1));
+                    const bool chain_start = (k % g.chain_units) == 0;
+                    const long long cn = pass * chains + k / g.chain_units;
+                    const int set = (int)(cn % g.nsets);
+                    if (chain_start && cn >= g.nsets)
+                        tc::mbar_wait(tc::smem_u32(flushed + set), (uint32_t)((cn / g.nsets - 1) & 1));
+                    tc::fence_after_sync();
+                    const uint32_t hbase = base + buf * g.buf_bytes, gbase = hbase + 2 * g.hplane_bytes;
+                    // descriptors as (constant high word, running low word): every start address stays inside shared
+                    // memory, so the 14-bit address field never carries into the stride fields
+                    const uint64_t a_desc = tc::make_desc(gbase, 128, g.gplane_bytes);
+                    const uint64_t bh_desc = tc::make_desc(hbase, 128, 16);
+                    const uint64_t a_hi = a_desc & 0xFFFFFFFF00000000ULL, b_hi = bh_desc & 0xFFFFFFFF00000000ULL;
+                    const uint32_t lo_plane = g.hplane_bytes >> 4;
+                    const uint32_t acc0 = tmem + set * set_cols;
+                    uint32_t accf = chain_start ? 0u : 1u;
+                    uint32_t a_lo = (uint32_t)a_desc;
+                    const int nsteps = g.row_len >> 4;
+                    for (int c0 = 0; c0 < g.T[0]; ++c0)
+                        for (int c1 = 0; c1 < g.T[1]; ++c1)
+                            for (int c2 = 0; c2 < g.T[2]; ++c2) {
+                                const uint32_t b_row = (uint32_t)bh_desc + (c0 + 1) * g.bstride[0] + (c1 + 1) * g.bstride[1] +
+                                                       (c2 + 1) * g.bstride[2];
+                                uint32_t b0 = b_row + off_mine[0], b1 = b_row + off_mine[1], b2 = b_row + off_mine[2];
+#pragma unroll 1
+                                for (int i = 0; i < nsteps; ++i) {
+                                    const uint64_t ad = a_hi | a_lo;
+                                    if (n_mine > 0) {
+                                        tc::mma_f16(acc0 + col_mine[0], ad, b_hi | b0, id24, accf);
+                                        tc::mma_f16(acc0 + col_mine[0] + 24, ad, b_hi | (b0 + lo_plane), id24, accf);
+                                    }
+                                    if (n_mine > 1) {
+                                        tc::mma_f16(acc0 + col_mine[1], ad, b_hi | b1, id24, accf);
+                                        tc::mma_f16(acc0 + col_mine[1] + 24, ad, b_hi | (b1 + lo_plane), id24, accf);
+                                    }
+                                    if (n_mine > 2) {
+                                        tc::mma_f16(acc0 + col_mine[2], ad, b_hi | b2, id24, accf);
+                                        tc::mma_f16(acc0 + col_mine[2] + 24, ad, b_hi | (b2 + lo_plane), id24, accf);
+                                    }
+                                    if (bias_here) tc::mma_f16(acc0 + ng * kWgGroupCols, ad, o_desc, id8, accf);
+                                    accf = 1u;
+                                    a_lo += 16; b0 += 16; b1 += 16; b2 += 16;
+                                }
+                            }
+                    tc::mma_commit(tc::smem_u32(mma_done + buf));
+                    if ((k + 1) % g.chain_units == 0 || k + 1 == mine) tc::mma_commit(tc::smem_u32(chain_done + set));
+                }
+            }
+            __syncwarp();
+        } else {
+            // epilogue: warp w owns TMEM lanes 32 w .. 32 w + 15 = rows 16 w .. 16 w + 15 (channel group w: 8 hi rows, 8 lo rows)
+            const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+            // M = 64: row i of D lives in lane 32 (i / 16) + i % 16; M = 128: in lane i (rows 64 .. 127 are not ours)
+            const bool valid = kWgM == 64 ? lane < 16 : warp < 2;
+            float* row = acc_s + (kWgM == 64 ? warp * 16 + (lane & 15) : (warp & 1) * 32 + lane) * AS;
+            for (long long c = 0; c < chains; ++c) {
+                const long long cn = pass * chains + c;
+                const int set = (int)(cn % g.nsets);
+                tc::mbar_wait(tc::smem_u32(chain_done + set), (uint32_t)((cn / g.nsets) & 1));
+                tc::fence_after_sync();
+                const uint32_t col0 = lane_addr + set * set_cols;
+                for (int c32 = 0; c32 < ncols; c32 += 32) {
+                    float v[4][8];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (c32 + q * 8 < ncols) tc::tmem_ld8(col0 + c32 + q * 8, v[q]);
+                    tc::tmem_ld_wait();
+                    if (valid) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (c32 + q * 8 < ncols) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) row[c32 + q * 8 + j] += v[q][j];
+                            }
+                    }
+                }
+                tc::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(tc::smem_u32(flushed + set));
+            }
+        }
+        // ---- end of the pass: shared accumulators -> gw (all four hi / lo products), cleared for the next pass
+        __syncthreads();
+        const int per_co = ng * 24;
+        for (int e = tid; e < g.Co * per_co; e += kWgThreads) {
+            const int co = e / per_co, rest = e - co * per_co;
+            const int tg = rest / 24, dc = rest - tg * 24;                      // dc = dx * 8 + ci
+            const float* rh = acc_s + ((co >> 3) * 16 + (co & 7)) * AS + tg * kWgGroupCols;
+            const float* rl = rh + 8 * AS;
+            const float v = (rh[dc] + (rh[24 + dc] + rl[dc])) + rl[24 + dc];
+            const int t = (g0 + tg) * 3 + (dc >> 3);
+            atomicAdd(a.gw + ((long long)co * 8 + (dc & 7)) * g.taps + t, v * inv_scale);
+        }
+        if (with_bias)
+            for (int co = tid; co < g.Co; co += kWgThreads) {
+                const float* rh = acc_s + ((co >> 3) * 16 + (co & 7)) * AS + ng * kWgGroupCols;
+                atomicAdd(a.gbias + co, (rh[0] + rh[8 * AS]) * inv_scale);
+            }
+        __syncthreads();
+        if (pass + 1 < g.npass) {
+            for (int i = tid; i < 64 * AS; i += kWgThreads) acc_s[i] = 0.f;
+            __syncthreads();
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 4) tc::tmem_dealloc(tmem, 512);
+}
+
+// Tile of a unit: innermost axis whole (a multiple of 16 sites: K steps do not straddle rows), the axes before it as
+// in nd_plan; the largest tile whose two buffers fit next to the accumulators.
+bool wg_plan(WgGeom& g, const nfk_lattice& lat, int Co, uint32_t budget) {
+    const int D = lat.ndim, r0 = 4 - D;
+    g = WgGeom{};
+    g.D = D;
+    g.Co = Co;
+    g.Gg = (Co + 7) / 8;
+    g.taps = 1;
+    for (int d = 0; d < D; ++d) g.taps *= 3;
+    g.ngroups = g.taps / 3;
+    g.gpp = g.ngroups < kWgMaxGroups ? g.ngroups : kWgMaxGroups;
+    g.npass = (g.ngroups + g.gpp - 1) / g.gpp;
+    int ps = 1;
+    g.V = 1;
+    for (int j = 3; j >= 0; --j) {
+        const bool real = j >= r0;
+        g.L[j] = real ? lat.shape[j - r0] : 1;
+        g.pstride[j] = real ? ps : 0;
+        if (real) { ps *= g.L[j] + 2; g.V *= g.L[j]; }
+    }
+    g.Vp = ps;
+    if (g.L[3] % 16 != 0 || g.Gg > 4) return false;
+    auto align = [](uint32_t v) { return (v + 127u) & ~127u; };
+    bool found = false;
+    WgGeom best{};
+    for (int split = r0; split <= 2; ++split) {
+        for (int t = 1; t <= g.L[split]; ++t) {
+            if (g.L[split] % t) continue;
+            WgGeom c = g;
+            int bs = 1;
+            c.tiles_per_sample = 1;
+            c.rows = 1;
+            for (int j = 3; j >= 0; --j) {
+                const bool real = j >= r0;
+                c.T[j] = !real ? 1 : (j < split ? 1 : (j == split ? t : g.L[j]));
+                c.ntile[j] = g.L[j] / c.T[j];
+                c.box[j] = real ? c.T[j] + 2 : 1;
+                c.bstride[j] = real ? bs : 0;
+                bs *= c.box[j];
+                c.tiles_per_sample *= c.ntile[j];
+                if (j < 3) c.rows *= c.T[j];
+                c.magic_ntile[j] = nd_magic(c.ntile[j]);
+                c.magic_box[j] = nd_magic(c.box[j]);
+            }
+            c.nbox = bs;
+            c.split = split;
+            c.run_rec = c.bstride[split] * c.box[split];
+            c.nruns = c.nbox / c.run_rec;
+            c.row_len = g.L[3];
+            c.tile_sites = c.rows * c.row_len;
+            c.hplane_bytes = align((uint32_t)(c.nbox + 8) * 16);
+            c.gplane_bytes = align((uint32_t)c.tile_sites * 16);
+            if (c.gplane_bytes / 16 > 0x3FFF || c.nbox > 0x3FFF) continue;
+            c.buf_bytes = 2 * c.hplane_bytes + 2 * c.Gg * c.gplane_bytes;
+            uint32_t off = 2 * c.buf_bytes;
+            const int ncols_max = c.gpp * kWgGroupCols + 8;
+            c.acc_stride = ncols_max + 1;
+            c.nsets = 2 * ncols_max <= 512 && ncols_max <= 256 ? 2 : 1;
+            c.off_acc = off; off = align(off + 64 * c.acc_stride * 4);
+            c.off_ones = off; off += 128;
+            c.off_bar = off; off = align(off + 8 * 8 + 16);
+            c.smem_bytes = off < kNdMinSmem ? kNdMinSmem : off;
+            if (c.smem_bytes > budget) continue;
+            // the M = 64 operand always spans eight planes: the ones beyond 2 Gg must still lie inside the allocation
+            if (c.buf_bytes + 2 * c.hplane_bytes + (kWgM / 8) * c.gplane_bytes > c.smem_bytes) continue;
+            const int ksteps = c.tile_sites / 16;
+            c.chain_units = ksteps >= kWgChainSteps ? 1 : kWgChainSteps / ksteps;
+            for (int tg = 0; tg < c.ngroups; ++tg) {
+                int rem = tg, o = 0;
+                for (int j = 2; j >= r0; --j) { o += (rem % 3 - 1) * c.bstride[j]; rem /= 3; }
+                c.toff[tg] = o;
+            }
+            if (!found || c.tile_sites > best.tile_sites) { best = c; found = true; }
+        }
+    }
+    if (found) g = best;
+    return found;
+}
+
+struct NdWgradPlan {
+    WgGeom g;
+    long long hrec_bytes, grec_bytes, total;
+};
+
+int nd_wgrad_plan(NdWgradPlan& p, nfk_lattice lat, int Co, int Ci, long long B) {
+    if (Ci != 8 || Co < 1 || Co > 32 || !nd_lattice_ok(lat)) return NFK_EUNSUPPORTED;
+    if (!wg_plan(p.g, lat, Co, (uint32_t)nd_props().max_smem)) return NFK_EUNSUPPORTED;
+    auto al = [](long long v) { return (v + 255) / 256 * 256; };
+    const long long b = B > 0 ? B : 1;
+    p.hrec_bytes = al(b * p.g.Vp * 32LL);
+    p.grec_bytes = al(b * p.g.Gg * p.g.Vp * 32LL);
+    p.total = 256 + p.hrec_bytes + p.grec_bytes;
+    return NFK_OK;
+}
+
+}  // namespace
+
+extern "C" int64_t nfk_convnd_wgrad_workspace(nfk_lattice lat, int Co, int Ci, int64_t B) {
+    NdWgradPlan p;
+    if (int e = nd_wgrad_plan(p, lat, Co, Ci, B)) return e;
+    return p.total;
+}
+
+/* Weight (and bias) gradient of one circular 3^D convolution layer with 8 input channels on the tensor cores:
+ *     gw[co][ci][t] += sum_{b, s} gpre[b][co][s] * h[b][ci][s + t - 1],   gb[co] += sum_{b, s} gpre[b][co][s]
+ * h [B][8][V] the layer's input, gpre [B][Co][V] d loss / d (its pre-activation output), Co <= 32; gw [Co][8][3^D] and gb
+ * [Co] (or NULL) are ACCUMULATED into (zero them first).  2-D .. 4-D lattices with even extents and an innermost extent
+ * that is a multiple of 16; NFK_EUNSUPPORTED otherwise (the caller then uses nfk_conv_circ_bwd_weight).            */
+extern "C" int nfk_convnd_wgrad(const float* h, const float* gpre, float* gw, float* gb, int Co, int Ci,
+                                nfk_lattice lat, int64_t B, void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!h || !gpre || !gw || !workspace) return NFK_EINVAL;
+    NdWgradPlan p;
+    if (int e = nd_wgrad_plan(p, lat, Co, Ci, B)) return e;
+    if (B <= 0) return NFK_OK;
+    if (workspace_bytes < p.total || ((uintptr_t)workspace % 256) != 0) return NFK_EINVAL;
+    cudaStream_t st = NFK_STREAM(stream);
+    const WgGeom& g = p.g;
+    if (getenv("NFK_ND_DEBUG"))
+        fprintf(stderr, "nfk_convnd_wgrad: T = %d %d %d %d  box %d  rows %d x %d  runs %d x %d rec  groups %d in %d passes  chain %d units  smem %u B\n",
+                g.T[0], g.T[1], g.T[2], g.T[3], g.nbox, g.rows, g.row_len, g.nruns, g.run_rec, g.ngroups, g.npass, g.chain_units, g.smem_bytes);
+    uint8_t* wsp = static_cast<uint8_t*>(workspace);
+    unsigned* amax = reinterpret_cast<unsigned*>(wsp);
+    uint4* hrec = reinterpret_cast<uint4*>(wsp + 256);
+    uint4* grec = reinterpret_cast<uint4*>(wsp + 256 + p.hrec_bytes);
+    const int D = lat.ndim;
+
+    if (cudaMemsetAsync(amax, 0, 4, st) != cudaSuccess) return NFK_ECUDA;
+    const long long n = (long long)B * Co * g.V;
+    long long ablocks = (n / 4 + 255) / 256;
+    if (ablocks > 148 * 16) ablocks = 148 * 16;
+    if (ablocks < 1) ablocks = 1;
+    nd_amax_kernel<<<(unsigned)ablocks, 256, 0, st>>>(gpre, n, amax);
+    if (int e = check_launch()) return e;
+
+    NdLat nl{};
+    for (int d = 0; d < 4; ++d) {
+        const int j = d + 4 - D;
+        nl.L[d] = d < D ? g.L[j] : 1;
+        nl.pstride[d] = d < D ? g.pstride[j] : 0;
+        nl.magic_L[d] = nd_magic(nl.L[d]);
+    }
+    nl.V = g.V;
+    nl.Vp = g.Vp;
+    const long long blocks = B * ((nl.V + 255) / 256);
+    if (blocks >= (1LL << 31)) return NFK_EUNSUPPORTED;
+    const float* am = reinterpret_cast<const float*>(amax);
+    for (int which = 0; which < 2; ++which) {
+        const dim3 gridp((unsigned)blocks, (unsigned)(which == 0 ? 1 : g.Gg));
+        const float* src = which == 0 ? h : gpre;
+        const int C = which == 0 ? 8 : Co;
+        const float* sc = which == 0 ? nullptr : am;
+        uint4* dst = which == 0 ? hrec : grec;
+        switch (D) {
+            case 2: nd_pack_records_kernel<2><<<gridp, 256, 0, st>>>(src, C, sc, dst, nl, B); break;
+            case 3: nd_pack_records_kernel<3><<<gridp, 256, 0, st>>>(src, C, sc, dst, nl, B); break;
+            default: nd_pack_records_kernel<4><<<gridp, 256, 0, st>>>(src, C, sc, dst, nl, B); break;
+        }
+        if (int e = check_launch()) return e;
+    }
+
+    WgArgs a{};
+    a.h_rec = hrec; a.g_rec = grec; a.amax = am; a.gw = gw; a.gbias = gb; a.B = B; a.g = g;
+    const NdProps& pr = nd_props();
+    if (ensure_dynamic_smem<convnd_wgrad_tc_kernel>(pr.max_smem) != NFK_OK) return NFK_ECUDA;
+    long long grid = pr.sm_count;
+    const long long nunits = B * g.tiles_per_sample;
+    if (grid > nunits) grid = nunits;
+    convnd_wgrad_tc_kernel<<<(unsigned)grid, kWgThreads, g.smem_bytes, st>>>(a);
+    return check_launch();
 }

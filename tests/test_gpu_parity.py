@@ -288,6 +288,42 @@ def test_nd_weight_gradient_tile_kernels(shape, Ci, Co, B, bias, masked):
         close_grad(got[1], grads[1].numpy(), tol=2e-5)
 
 
+@pytest.mark.parametrize("shape,Co,B,bias,gscale", [
+    ((16, 16), 8, 3, True, 1.0), ((64, 64), 28, 5, True, 1e-7), ((8, 32), 2, 2, False, 1.0),
+    ((4, 4, 16), 28, 3, True, 1.0), ((32, 32, 32), 28, 2, True, 1e3), ((6, 8, 32), 8, 150, True, 1.0),
+    ((2, 4, 4, 16), 28, 2, True, 1.0), ((16, 16, 16, 16), 8, 2, True, 1e-4),
+])
+def test_nd_tensor_core_weight_gradient(shape, Co, B, bias, gscale, monkeypatch):
+    """nfk_convnd_wgrad (sites as the K dimension of MN-major fp16-pair operands read from the records, float32
+    accumulators flushed from TMEM every ~32 K steps) against float64 autograd of the circular convolution."""
+    import itertools
+    from normflow__b200 import _ops
+    monkeypatch.setenv('NFK_WGRAD_ND_TC', '1')
+    monkeypatch.setenv('NFK_WGRAD_TC', '0')
+    D = len(shape)
+    g = torch.Generator('cpu').manual_seed(43)
+    rnd = lambda *s: torch.randn(*s, generator=g, dtype=torch.float64, device='cpu')
+    h = torch.tanh(rnd(B, 8, *shape))
+    gpre = rnd(B, Co, *shape) * gscale
+    gw_ref = torch.zeros(Co, 8, *(3,) * D, dtype=torch.float64, device='cpu')
+    for k in itertools.product(range(3), repeat=D):
+        shifted = torch.roll(h, shifts=[1 - kk for kk in k], dims=list(range(2, 2 + D)))
+        gw_ref[(slice(None), slice(None)) + k] = torch.einsum('bo...,bi...->oi', gpre, shifted)
+    gb_ref = gpre.sum(dim=[0] + list(range(2, 2 + D)))
+    timer = _C.KernelTimer(); _C.kernel_timer = timer
+    try:
+        gw, gb = _ops._conv_weight_grad(h.float().to(DEV), None, 0, gpre.float().to(DEV), (Co, 8) + (3,) * D, bias, shape, 3)
+    finally:
+        _C.kernel_timer = None
+    assert any(k.startswith('convnd_wgrad') for k in timer.summary()), timer.summary().keys()
+    err = float((gw.double().cpu() - gw_ref).abs().max() / gw_ref.abs().max())
+    print(f"wgrad {shape} 8->{Co} B={B}: tensor-core err {err:.2e} of max |gw|")
+    assert err <= 5e-6
+    if bias:
+        # (a bias gradient is a sum of B V signed terms: its error is measured against sum |terms|)
+        assert float((gb.double().cpu() - gb_ref).abs().max()) <= 2e-6 * float(gpre.abs().sum(dim=[0] + list(range(2, 2 + D))).max())
+
+
 def test_convact_unfused_path_equals_fused():
     torch.manual_seed(3)
     fused = ConvAct(1, 2, 3, hidden_sizes=[4], acts=['tanh', None], bias=True).to(DEV)
