@@ -660,10 +660,15 @@ def _conv_dgrad_tc(gpre, w, h, dact_kind, shape, ksize):
     """Data gradient of a layer on the tensor cores (nfk_convnd_dgrad): d loss / d pre-activation of the layer below
     from `gpre` = d loss / d this layer's output, `w` (Co, Ci, 3, ..) and the post-activation `h` of the layer below
     (tanh) or None.  Returns None where the kernel does not apply (the caller then runs the CUDA-core convolution
-    with transposed weights); NFK_DGRAD_TC=0 switches it off."""
+    with transposed weights); NFK_DGRAD_TC=0 switches it off, =1 also takes 2-D layers with 8 inputs."""
     Co, Ci = int(w.shape[0]), int(w.shape[1])
-    if (os.environ.get('NFK_DGRAD_TC') == '0' or int(ksize) != 3 or not 2 <= len(shape) <= 4
+    mode = os.environ.get('NFK_DGRAD_TC')
+    if (mode == '0' or int(ksize) != 3 or not 2 <= len(shape) <= 4
             or Ci not in (8, 16, 32, 64) or Co > 64 or dact_kind not in (0, _C.ACT['tanh'])):
+        return None
+    if len(shape) == 2 and Ci == 8 and mode != '1':
+        # 2-D, [8, 8] conditioner: break-even with the shared-memory CUDA-core kernels at 64 x 64 (whose checkerboard form
+        # skips the known zeros of the last layer's gradient) and five launches instead of one on small lattices
         return None
     lat = _C.lattice(shape)
     B = gpre.shape[0]

@@ -1074,11 +1074,12 @@ def test_nd_active_only_last_layer_matches_the_full_one(shape, kind, monkeypatch
     ((16, 16), 64, 64, 2, True, 1.0, False),          # two passes of 32 output channels, eight input groups
     ((12, 20), 13, 32, 2, True, 1.0, False),          # Co not a multiple of 8
 ])
-def test_tensor_core_data_gradient(shape, Co, Ci, B, tanh, gscale, sparse):
+def test_tensor_core_data_gradient(shape, Co, Ci, B, tanh, gscale, sparse, monkeypatch):
     """nfk_convnd_dgrad (fp16-pair implicit GEMM on transposed, mirrored weights; input scaled by a power of two from
     its largest magnitude) against float64 autograd of the circular convolution (torch, 2-D / 3-D) and against the
     float32 CUDA-core kernel that conv.npz pins to the reference (all dimensions)."""
     from normflow__b200 import _ops
+    monkeypatch.setenv('NFK_DGRAD_TC', '1')          # (2-D layers with 8 inputs keep the CUDA-core kernels by default)
     D = len(shape)
     g = torch.Generator('cpu').manual_seed(41)
     rnd = lambda *s, scale=1.0: (torch.randn(*s, generator=g, device='cpu') * scale).to(DEV)
