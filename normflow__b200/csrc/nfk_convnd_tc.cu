@@ -70,6 +70,7 @@ struct NdGeom {
     int Ep, Eh;                  // positions per sample and plane pair; records per parity plane (Ep / 2 + 1)
     int out_split;               // hidden layer (MODE 0): write the records in that form
     int compact;                 // last layer (MODE 1): read them in that form
+    int prefetch;                // pull the next unit's box into L2 while this one is computed (NFK_ND_PREFETCH=0: off)
     int last;                    // compact: linear box index of the last interior position (first: the first)
     uint32_t pb_bytes;           // compact: bytes of one parity plane of the box in shared memory
     uint32_t off_a, off_b, off_tab, off_bar, smem_bytes;
@@ -419,6 +420,9 @@ __device__ __forceinline__ void nd_bulk_load(uint32_t dst_smem, const void* src,
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void nd_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void nd_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
 }
@@ -572,6 +576,38 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                                     nd_bulk_load(dst, src, n * 16, loaded_bar);
                                     nd_bulk_load(dst + 2u * g.pb_bytes, src + 2LL * g.Eh, n * 16, loaded_bar);
                                 }
+                            }
+                        }
+                    }
+                }
+                if (iw == kNdIssuers - 1 && g.prefetch && unit + gridDim.x < nunits) {
+                    // the single box buffer leaves the load of a unit exposed: pull the NEXT unit's runs into L2 meanwhile
+                    long long nb;
+                    int norg[4], npass;
+                    unit_origin(unit + gridDim.x, npass, nb, norg);
+                    for (int k = 0; k < g.nruns; ++k) {
+                        int rem = k, so = 0;
+#pragma unroll
+                        for (int d = 3; d >= 0; --d) {
+                            const int st = g.compact ? g.estride[d] : g.pstride[d];
+                            if (d < g.split) {
+                                const int q = nd_div(rem, g.box[d], g.magic_box[d]);
+                                so += (norg[d] + rem - q * g.box[d]) * st;
+                                rem = q;
+                            } else {
+                                so += norg[d] * st;
+                            }
+                        }
+                        for (int gi = 0; gi < G; ++gi) {
+                            if (!g.compact) {
+                                const uint4* src = a.in_rec + (nb * G + gi) * 2LL * g.Vp + so;
+                                nd_prefetch_l2(src, (uint32_t)g.run_rec * 16);
+                                nd_prefetch_l2(src + g.Vp, (uint32_t)g.run_rec * 16);
+                            } else {
+                                const uint4* src = a.in_rec + (nb * G + gi) * 4LL * g.Eh + (so >> 1);
+                                const uint32_t n16 = (uint32_t)((g.run_rec + 1) >> 1) * 16;
+#pragma unroll
+                                for (int pl = 0; pl < 4; ++pl) nd_prefetch_l2(src + (long long)pl * g.Eh, n16);
                             }
                         }
                     }
@@ -817,6 +853,7 @@ void nd_lattice(NdGeom& g, const nfk_lattice& lat) {
 bool nd_plan(NdGeom& g, int N2, int G, int npass, int bdup, uint32_t budget, bool compact = false) {
     const int r0 = 4 - g.D;
     g.compact = compact ? 1 : 0;
+    { const char* e = getenv("NFK_ND_PREFETCH"); g.prefetch = !(e && e[0] == '0'); }
     g.bdup = bdup;
     g.G = G;
     g.npass = npass;

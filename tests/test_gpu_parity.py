@@ -1277,6 +1277,32 @@ def test_cuda_graph_training_follows_the_eager_step():
     assert hist[True][-5:].mean() < hist[True][:5].mean()
 
 
+def test_cuda_graph_training_3d_with_the_tensor_core_backward():
+    """The same on a 3-D lattice whose innermost extent is a multiple of 16: the captured step contains the N-D
+    tensor-core forward, nfk_convnd_dgrad (device-side scale, memset + amax + pack inside the graph) and
+    nfk_convnd_wgrad; graph replay must follow the eager loop."""
+    hist = {}
+    for graph in (False, True):
+        torch.manual_seed(78)
+        np.random.seed(78)
+        model = _config_model((4, 4, 16), [('affine', 2), ('rqs', 2)], seed=33)
+        model.fit.cuda_graph = graph
+        timer = _C.KernelTimer() if not graph else None
+        _C.kernel_timer = timer
+        try:
+            model.fit(n_epochs=12, batch_size=64, hyperparam=dict(lr=1e-3, weight_decay=0.0),
+                      checkpoint_dict=dict(print_stride=20, print_batch_size=32))
+        finally:
+            _C.kernel_timer = None
+        if timer is not None:
+            names = set(timer.summary())
+            assert any(k.startswith('convnd_dgrad') for k in names) and any(k.startswith('convnd_wgrad') for k in names), names
+        hist[graph] = np.array(model.fit.train_history['loss'])
+        assert len(hist[graph]) == 12 and np.isfinite(hist[graph]).all()
+    np.testing.assert_allclose(hist[True][:4], hist[False][:4], rtol=2e-4, atol=2e-3)
+    np.testing.assert_allclose(hist[True], hist[False], rtol=5e-2, atol=0.5)
+
+
 def test_cuda_graph_training_zero_dim_converges_to_logz():
     """The reference's published run (0-dim phi^4, DistConvertor_(10, symmetric)) in graph mode:
     the loss converges to -log Z = -1.112773 and a divergent loss skips the update."""
