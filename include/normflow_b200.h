@@ -352,6 +352,16 @@ int64_t nfk_convnd_wgrad_workspace(nfk_lattice lat, int Co, int Ci, int64_t B);
 int nfk_convnd_wgrad(const float* h, const float* gpre, float* gw, float* gb, int Co, int Ci,
                      nfk_lattice lat, int64_t B, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Both gradients of ONE layer in one call (the per-layer step of autograd through modules.py:131-145): what
+ * nfk_convnd_wgrad and nfk_convnd_dgrad compute, with d loss / d pre-activation reduced (max |g|) and packed into records
+ * once for both kernels.  h_in [B][8][V] is the layer's input -- and, when act_below != 0, the tanh output whose derivative
+ * multiplies the data gradient; gw / gb are accumulated into, gin [B][8][V] is written.  Applies where both kernels do
+ * (8 input channels, Co <= 32, innermost extent a multiple of 16); NFK_EUNSUPPORTED otherwise.                          */
+int64_t nfk_convnd_layer_bwd_workspace(nfk_lattice lat, int Co, int Ci, int64_t B);
+int nfk_convnd_layer_bwd(const float* h_in, const float* gpre, const float* w, int act_below, float* gin,
+                         float* gw, float* gb, int Co, int Ci, nfk_lattice lat, int64_t B,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------- PSD block (spectral part) ---
  * PSDBlock_ / FFTNet_ (psd_.py:25-40, fftflow_.py:121-131,167-180): the real-to-complex
  * and complex-to-real transforms are cuFFT calls made by the host package; these entries

@@ -75,6 +75,7 @@ _SIGNATURES = {
                                c_f, c_f, c_f, c_f, c_f, c_f, c_l, c_f, c_l, c_f],
     "nfk_convnd_dgrad": [c_f, c_f, c_f, c_f, c_i, c_i, Lattice, c_l, c_f, c_l, c_f],
     "nfk_convnd_wgrad": [c_f, c_f, c_f, c_f, c_i, c_i, Lattice, c_l, c_f, c_l, c_f],
+    "nfk_convnd_layer_bwd": [c_f, c_f, c_f, c_i, c_f, c_f, c_f, c_i, c_i, Lattice, c_l, c_f, c_l, c_f],
     "nfk_psd_weights_fwd": [c_f, c_l, c_i, c_i, c_f, c_f, c_f],
     "nfk_psd_weights_bwd": [c_f, c_f, c_f, c_f, c_l, c_i, c_i, c_f, c_f],
     "nfk_psd_scale": [c_f, c_f, c_f, c_fl, c_f, c_l, c_l, c_f],
@@ -92,7 +93,8 @@ _lib = None
 def declared_symbols():
     """Every entry point of include/normflow_b200.h (checked by the CPU test-suite)."""
     return sorted(list(_SIGNATURES) + ["nfk_strerror", "nfk_version", "nfk_launch_count", "nfk_fusednd_workspace",
-                                            "nfk_convnd_dgrad_workspace", "nfk_convnd_wgrad_workspace"])
+                                            "nfk_convnd_dgrad_workspace", "nfk_convnd_wgrad_workspace",
+                                            "nfk_convnd_layer_bwd_workspace"])
 
 
 def lib():
@@ -115,6 +117,8 @@ def lib():
     handle.nfk_convnd_dgrad_workspace.restype = c_l
     handle.nfk_convnd_wgrad_workspace.argtypes = [Lattice, c_i, c_i, c_l]
     handle.nfk_convnd_wgrad_workspace.restype = c_l
+    handle.nfk_convnd_layer_bwd_workspace.argtypes = [Lattice, c_i, c_i, c_l]
+    handle.nfk_convnd_layer_bwd_workspace.restype = c_l
     handle.nfk_strerror.argtypes = [c_i]
     handle.nfk_strerror.restype = ctypes.c_char_p
     handle.nfk_version.restype = c_i

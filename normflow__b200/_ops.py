@@ -691,6 +691,37 @@ def _conv_dgrad_tc(gpre, w, h, dact_kind, shape, ksize):
     return gin
 
 
+def _conv_layer_bwd_tc(h_in, gpre, w, dact_kind, want_bias, shape, ksize):
+    """Weight, bias and data gradient of one layer with 8 input channels in one call (nfk_convnd_layer_bwd: the gradient
+    is reduced and packed into records once for both tensor-core kernels).  Returns (gw, gb, gin) or None where the pair
+    does not apply or is not the default (2-D lattices, see _conv_dgrad_tc / _conv_weight_grad)."""
+    Co, Ci = int(w.shape[0]), int(w.shape[1])
+    if (Ci != 8 or Co > 32 or int(ksize) != 3 or not 3 <= len(shape) <= 4 or shape[-1] % 16 != 0
+            or dact_kind not in (0, _C.ACT['tanh'])
+            or os.environ.get('NFK_DGRAD_TC') == '0' or os.environ.get('NFK_WGRAD_ND_TC') == '0'
+            or os.environ.get('NFK_LAYER_BWD') == '0'):
+        return None
+    lat = _C.lattice(shape)
+    B = gpre.shape[0]
+    per_sample = int(lib().nfk_convnd_layer_bwd_workspace(lat, Co, Ci, 1))
+    if per_sample <= 0:
+        return None
+    cap = int(float(os.environ.get("NFK_ND_WORKSPACE_GB", "24")) * 2 ** 30)
+    chunk = max(1, min(B, cap // max(per_sample, 1)))
+    need = int(lib().nfk_convnd_layer_bwd_workspace(lat, Co, Ci, chunk))
+    workspace = torch.empty((need,), dtype=torch.uint8, device=gpre.device)
+    gin = torch.empty((B, Ci) + tuple(shape), dtype=torch.float32, device=gpre.device)
+    gw = torch.zeros(tuple(w.shape), dtype=torch.float32, device=gpre.device)
+    gb = torch.zeros((Co,), dtype=torch.float32, device=gpre.device) if want_bias else None
+    with _C.timed(f"convnd_layer_bwd[{Ci}->{Co}]"):
+        for lo in range(0, B, chunk):
+            hi = min(B, lo + chunk)
+            check(lib().nfk_convnd_layer_bwd(dev(h_in[lo:hi]), dev(gpre[lo:hi]), dev(w), int(dact_kind != 0), dev(gin[lo:hi]),
+                                             dev(gw), dev(gb), Co, Ci, lat, hi - lo, dev(workspace, torch.uint8), need,
+                                             stream()), "convnd_layer_bwd")
+    return gw, gb, gin
+
+
 def _conv_weight_grad(inp, in_mask, in_keep, gpre, w_shape, want_bias, shape, ksize, g_parity=None):
     Co, Ci = w_shape[0], w_shape[1]
     gw = torch.zeros(w_shape, dtype=torch.float32, device=inp.device)
@@ -798,6 +829,11 @@ def _conv_stack_backward(hs, weights, has_bias, acts, ksize, shape, in_mask, in_
         w = weights[i]
         Co, Ci = w.shape[0], w.shape[1]
         first = (i == 0)
+        if not first:
+            both = _conv_layer_bwd_tc(hs[i], gpre, w.contiguous(), acts[i - 1], has_bias[i], shape, ksize)
+            if both is not None:
+                gws[i], gbs[i], gpre = both
+                continue
         gws[i], gbs[i] = _conv_weight_grad(hs[i], in_mask if first else None, in_keep, gpre,
                                            tuple(w.shape), has_bias[i], shape, ksize,
                                            g_parity=gpre_parity if i == n - 1 and n > 1 else None)

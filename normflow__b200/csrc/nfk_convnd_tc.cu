@@ -415,6 +415,30 @@ __global__ void __launch_bounds__(256) nd_pack_records_kernel(const float* __res
     nd_store_site<D>(out_rec + (b * G + gidx) * 2LL * lat.Vp, lat.Vp, c, Ld, ps, hi, lo);
 }
 
+uint32_t nd_magic(int d);
+// host side of nd_pack_records_kernel (L / pstride in NdGeom's right-aligned slots)
+int nd_pack(const float* src, int C, const float* amax, uint4* rec, int D, const int (&L)[4], const int (&pstride)[4], int V, int Vp,
+            int64_t B, cudaStream_t st) {
+    NdLat nl{};
+    for (int d = 0; d < 4; ++d) {
+        const int j = d + 4 - D;
+        nl.L[d] = d < D ? L[j] : 1;
+        nl.pstride[d] = d < D ? pstride[j] : 0;
+        nl.magic_L[d] = nd_magic(nl.L[d]);
+    }
+    nl.V = V;
+    nl.Vp = Vp;
+    const long long blocks = B * ((V + 255) / 256);
+    if (blocks >= (1LL << 31)) return NFK_EUNSUPPORTED;
+    const dim3 gridp((unsigned)blocks, (unsigned)((C + 7) / 8));
+    switch (D) {
+        case 2: nd_pack_records_kernel<2><<<gridp, 256, 0, st>>>(src, C, amax, rec, nl, B); break;
+        case 3: nd_pack_records_kernel<3><<<gridp, 256, 0, st>>>(src, C, amax, rec, nl, B); break;
+        default: nd_pack_records_kernel<4><<<gridp, 256, 0, st>>>(src, C, amax, rec, nl, B); break;
+    }
+    return check_launch();
+}
+
 // ------------------------------------------------------------------------------------------- layers 2 and 3
 __device__ __forceinline__ void nd_bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -1195,6 +1219,42 @@ extern "C" int64_t nfk_convnd_dgrad_workspace(nfk_lattice lat, int Co, int Ci, i
  * gpre [B][Co][V], w [Co][Ci][3^D], h / gin [B][Ci][V]; Ci in {8, 16, 32, 64}, Co <= 64, even extents, 2-D .. 4-D.
  * The input is packed into fp16-pair records scaled by a power of two taken from its largest magnitude (found on the
  * device), so the result has float32-level accuracy at any gradient magnitude. */
+namespace {
+
+// max |g| -> *amax (device), then g -> padded fp16-pair records scaled by nd_grad_scale(*amax); shared by the data and the
+// weight gradient of a layer
+int nd_pack_gradient(const float* gpre, int Co, const nfk_lattice& lat, const int (&L)[4], const int (&pstride)[4], int V, int Vp,
+                     int64_t B, unsigned* amax, uint4* rec, cudaStream_t st) {
+    const int D = lat.ndim;
+    if (cudaMemsetAsync(amax, 0, 4, st) != cudaSuccess) return NFK_ECUDA;
+    const long long n = (long long)B * Co * V;
+    long long ablocks = (n / 4 + 255) / 256;
+    if (ablocks > 148 * 16) ablocks = 148 * 16;
+    if (ablocks < 1) ablocks = 1;
+    nd_amax_kernel<<<(unsigned)ablocks, 256, 0, st>>>(gpre, n, amax);
+    if (int e = check_launch()) return e;
+    return nd_pack(gpre, Co, reinterpret_cast<const float*>(amax), rec, D, L, pstride, V, Vp, B, st);
+}
+
+int nd_dgrad_run(const NdDgradPlan& p, const uint4* rec, const float* amax, const float* w, const float* h, float* gin,
+                 int Co, int Ci, int64_t B, __half* img, cudaStream_t st) {
+    const NdGeom& g = p.g;
+    if (getenv("NFK_ND_DEBUG"))
+        fprintf(stderr, "nfk_convnd_dgrad: T = %d %d %d %d  box %d  tiles/unit %d  G %d  passes %d  chains %d  slots %d  smem %u B\n",
+                g.T[0], g.T[1], g.T[2], g.T[3], g.nbox, g.nt, g.G, g.npass, g.nchunk, g.nslots, g.smem_bytes);
+    nd_prep_weights_t_kernel<<<64, 256, 0, st>>>(w, Co, Ci, g.taps, p.OC, p.npass, p.bdup, img);
+    if (int e = check_launch()) return e;
+    NdArgs a{};
+    a.in_rec = rec; a.bimg = img; a.B = B; a.g = g;
+    a.save = gin; a.save_ch = Ci; a.act = h; a.amax = amax;
+    a.cfg = RqsCfg{0.f, 1.f, 0.f, 1.f, 0, 0};
+    if (p.OC == 8) return nd_launch<2, 0, 8, 0>(a, st);
+    if (p.OC == 16) return nd_launch<2, 0, 16, 0>(a, st);
+    return nd_launch<2, 0, 32, 0>(a, st);
+}
+
+}  // namespace
+
 extern "C" int nfk_convnd_dgrad(const float* gpre, const float* w, const float* h, float* gin, int Co, int Ci,
                                 nfk_lattice lat, int64_t B, void* workspace, int64_t workspace_bytes, void* stream) {
     if (!gpre || !w || !gin || !workspace) return NFK_EINVAL;
@@ -1203,54 +1263,12 @@ extern "C" int nfk_convnd_dgrad(const float* gpre, const float* w, const float* 
     if (B <= 0) return NFK_OK;
     if (workspace_bytes < p.total || ((uintptr_t)workspace % 256) != 0) return NFK_EINVAL;
     cudaStream_t st = NFK_STREAM(stream);
-    const NdGeom& g = p.g;
-    if (getenv("NFK_ND_DEBUG"))
-        fprintf(stderr, "nfk_convnd_dgrad: T = %d %d %d %d  box %d  tiles/unit %d  G %d  passes %d  chains %d  slots %d  smem %u B\n",
-                g.T[0], g.T[1], g.T[2], g.T[3], g.nbox, g.nt, g.G, g.npass, g.nchunk, g.nslots, g.smem_bytes);
     uint8_t* wsp = static_cast<uint8_t*>(workspace);
     unsigned* amax = reinterpret_cast<unsigned*>(wsp);
     __half* img = reinterpret_cast<__half*>(wsp + 256);
     uint4* rec = reinterpret_cast<uint4*>(wsp + 256 + p.img_bytes);
-    const int D = lat.ndim;
-
-    if (cudaMemsetAsync(amax, 0, 4, st) != cudaSuccess) return NFK_ECUDA;
-    const long long n = (long long)B * Co * g.V;
-    long long ablocks = (n / 4 + 255) / 256;
-    if (ablocks > 148 * 16) ablocks = 148 * 16;
-    if (ablocks < 1) ablocks = 1;
-    nd_amax_kernel<<<(unsigned)ablocks, 256, 0, st>>>(gpre, n, amax);
-    if (int e = check_launch()) return e;
-    nd_prep_weights_t_kernel<<<64, 256, 0, st>>>(w, Co, Ci, g.taps, p.OC, p.npass, p.bdup, img);
-    if (int e = check_launch()) return e;
-
-    NdLat nl{};
-    for (int d = 0; d < 4; ++d) {
-        const int j = d + 4 - D;
-        nl.L[d] = d < D ? g.L[j] : 1;
-        nl.gstride[d] = d < D ? g.gstride[j] : 0;
-        nl.pstride[d] = d < D ? g.pstride[j] : 0;
-        nl.magic_L[d] = nd_magic(nl.L[d]);
-    }
-    nl.V = g.V;
-    nl.Vp = g.Vp;
-    const long long blocks = B * ((nl.V + 255) / 256);
-    if (blocks >= (1LL << 31)) return NFK_EUNSUPPORTED;
-    const dim3 gridp((unsigned)blocks, (unsigned)p.G);
-    const float* am = reinterpret_cast<const float*>(amax);
-    switch (D) {
-        case 2: nd_pack_records_kernel<2><<<gridp, 256, 0, st>>>(gpre, Co, am, rec, nl, B); break;
-        case 3: nd_pack_records_kernel<3><<<gridp, 256, 0, st>>>(gpre, Co, am, rec, nl, B); break;
-        default: nd_pack_records_kernel<4><<<gridp, 256, 0, st>>>(gpre, Co, am, rec, nl, B); break;
-    }
-    if (int e = check_launch()) return e;
-
-    NdArgs a{};
-    a.in_rec = rec; a.bimg = img; a.B = B; a.g = g;
-    a.save = gin; a.save_ch = Ci; a.act = h; a.amax = am;
-    a.cfg = RqsCfg{0.f, 1.f, 0.f, 1.f, 0, 0};
-    if (p.OC == 8) return nd_launch<2, 0, 8, 0>(a, st);
-    if (p.OC == 16) return nd_launch<2, 0, 16, 0>(a, st);
-    return nd_launch<2, 0, 32, 0>(a, st);
+    if (int e = nd_pack_gradient(gpre, Co, lat, p.g.L, p.g.pstride, p.g.V, p.g.Vp, B, amax, rec, st)) return e;
+    return nd_dgrad_run(p, rec, reinterpret_cast<const float*>(amax), w, h, gin, Co, Ci, B, img, st);
 }
 
 // ------------------------------------------------------------------------------------------- weight gradient
@@ -1638,6 +1656,27 @@ extern "C" int64_t nfk_convnd_wgrad_workspace(nfk_lattice lat, int Co, int Ci, i
  * h [B][8][V] the layer's input, gpre [B][Co][V] d loss / d (its pre-activation output), Co <= 32; gw [Co][8][3^D] and gb
  * [Co] (or NULL) are ACCUMULATED into (zero them first).  2-D .. 4-D lattices with even extents and an innermost extent
  * that is a multiple of 16; NFK_EUNSUPPORTED otherwise (the caller then uses nfk_conv_circ_bwd_weight).            */
+namespace {
+
+int nd_wgrad_run(const NdWgradPlan& p, const uint4* hrec, const uint4* grec, const float* amax, float* gw, float* gb,
+                 int64_t B, cudaStream_t st) {
+    const WgGeom& g = p.g;
+    if (getenv("NFK_ND_DEBUG"))
+        fprintf(stderr, "nfk_convnd_wgrad: T = %d %d %d %d  box %d  rows %d x %d  runs %d x %d rec  groups %d in %d passes  chain %d units  smem %u B\n",
+                g.T[0], g.T[1], g.T[2], g.T[3], g.nbox, g.rows, g.row_len, g.nruns, g.run_rec, g.ngroups, g.npass, g.chain_units, g.smem_bytes);
+    WgArgs a{};
+    a.h_rec = hrec; a.g_rec = grec; a.amax = amax; a.gw = gw; a.gbias = gb; a.B = B; a.g = g;
+    const NdProps& pr = nd_props();
+    if (ensure_dynamic_smem<convnd_wgrad_tc_kernel>(pr.max_smem) != NFK_OK) return NFK_ECUDA;
+    long long grid = pr.sm_count;
+    const long long nunits = B * g.tiles_per_sample;
+    if (grid > nunits) grid = nunits;
+    convnd_wgrad_tc_kernel<<<(unsigned)grid, kWgThreads, g.smem_bytes, st>>>(a);
+    return check_launch();
+}
+
+}  // namespace
+
 extern "C" int nfk_convnd_wgrad(const float* h, const float* gpre, float* gw, float* gb, int Co, int Ci,
                                 nfk_lattice lat, int64_t B, void* workspace, int64_t workspace_bytes, void* stream) {
     if (!h || !gpre || !gw || !workspace) return NFK_EINVAL;
@@ -1647,56 +1686,58 @@ extern "C" int nfk_convnd_wgrad(const float* h, const float* gpre, float* gw, fl
     if (workspace_bytes < p.total || ((uintptr_t)workspace % 256) != 0) return NFK_EINVAL;
     cudaStream_t st = NFK_STREAM(stream);
     const WgGeom& g = p.g;
-    if (getenv("NFK_ND_DEBUG"))
-        fprintf(stderr, "nfk_convnd_wgrad: T = %d %d %d %d  box %d  rows %d x %d  runs %d x %d rec  groups %d in %d passes  chain %d units  smem %u B\n",
-                g.T[0], g.T[1], g.T[2], g.T[3], g.nbox, g.rows, g.row_len, g.nruns, g.run_rec, g.ngroups, g.npass, g.chain_units, g.smem_bytes);
     uint8_t* wsp = static_cast<uint8_t*>(workspace);
     unsigned* amax = reinterpret_cast<unsigned*>(wsp);
     uint4* hrec = reinterpret_cast<uint4*>(wsp + 256);
     uint4* grec = reinterpret_cast<uint4*>(wsp + 256 + p.hrec_bytes);
-    const int D = lat.ndim;
+    if (int e = nd_pack_gradient(gpre, Co, lat, g.L, g.pstride, g.V, g.Vp, B, amax, grec, st)) return e;
+    if (int e = nd_pack(h, 8, nullptr, hrec, lat.ndim, g.L, g.pstride, g.V, g.Vp, B, st)) return e;
+    return nd_wgrad_run(p, hrec, grec, reinterpret_cast<const float*>(amax), gw, gb, B, st);
+}
 
-    if (cudaMemsetAsync(amax, 0, 4, st) != cudaSuccess) return NFK_ECUDA;
-    const long long n = (long long)B * Co * g.V;
-    long long ablocks = (n / 4 + 255) / 256;
-    if (ablocks > 148 * 16) ablocks = 148 * 16;
-    if (ablocks < 1) ablocks = 1;
-    nd_amax_kernel<<<(unsigned)ablocks, 256, 0, st>>>(gpre, n, amax);
-    if (int e = check_launch()) return e;
+// ------------------------------------------------------------------------------------------- one layer, both gradients
+namespace {
+struct NdLayerBwdPlan {
+    NdDgradPlan d;
+    NdWgradPlan w;
+    long long total;
+};
+int nd_layer_bwd_plan(NdLayerBwdPlan& p, nfk_lattice lat, int Co, int Ci, long long B) {
+    if (int e = nd_dgrad_plan(p.d, lat, Co, Ci, B)) return e;
+    if (int e = nd_wgrad_plan(p.w, lat, Co, Ci, B)) return e;
+    p.total = 256 + p.d.img_bytes + p.w.hrec_bytes + p.w.grec_bytes;       // (the gradient's records: same layout for both)
+    return NFK_OK;
+}
+}  // namespace
 
-    NdLat nl{};
-    for (int d = 0; d < 4; ++d) {
-        const int j = d + 4 - D;
-        nl.L[d] = d < D ? g.L[j] : 1;
-        nl.pstride[d] = d < D ? g.pstride[j] : 0;
-        nl.magic_L[d] = nd_magic(nl.L[d]);
-    }
-    nl.V = g.V;
-    nl.Vp = g.Vp;
-    const long long blocks = B * ((nl.V + 255) / 256);
-    if (blocks >= (1LL << 31)) return NFK_EUNSUPPORTED;
+extern "C" int64_t nfk_convnd_layer_bwd_workspace(nfk_lattice lat, int Co, int Ci, int64_t B) {
+    NdLayerBwdPlan p;
+    if (int e = nd_layer_bwd_plan(p, lat, Co, Ci, B)) return e;
+    return p.total;
+}
+
+/* nfk_convnd_wgrad and nfk_convnd_dgrad of ONE layer in one call: d loss / d pre-activation is reduced (max |g|) and packed
+ * into records once for both kernels.  h_in [B][8][V] the layer's input (also the tensor whose tanh' the data gradient is
+ * multiplied by when `act_below` != 0), gpre [B][Co][V]; gw / gb accumulated into, gin [B][8][V] written.  Applies where
+ * both kernels do (8 input channels, Co <= 32, innermost extent a multiple of 16); NFK_EUNSUPPORTED otherwise.          */
+extern "C" int nfk_convnd_layer_bwd(const float* h_in, const float* gpre, const float* w, int act_below, float* gin,
+                                    float* gw, float* gb, int Co, int Ci, nfk_lattice lat, int64_t B,
+                                    void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!h_in || !gpre || !w || !gin || !gw || !workspace) return NFK_EINVAL;
+    NdLayerBwdPlan p;
+    if (int e = nd_layer_bwd_plan(p, lat, Co, Ci, B)) return e;
+    if (B <= 0) return NFK_OK;
+    if (workspace_bytes < p.total || ((uintptr_t)workspace % 256) != 0) return NFK_EINVAL;
+    cudaStream_t st = NFK_STREAM(stream);
+    const WgGeom& g = p.w.g;
+    uint8_t* wsp = static_cast<uint8_t*>(workspace);
+    unsigned* amax = reinterpret_cast<unsigned*>(wsp);
+    __half* img = reinterpret_cast<__half*>(wsp + 256);
+    uint4* hrec = reinterpret_cast<uint4*>(wsp + 256 + p.d.img_bytes);
+    uint4* grec = reinterpret_cast<uint4*>(wsp + 256 + p.d.img_bytes + p.w.hrec_bytes);
     const float* am = reinterpret_cast<const float*>(amax);
-    for (int which = 0; which < 2; ++which) {
-        const dim3 gridp((unsigned)blocks, (unsigned)(which == 0 ? 1 : g.Gg));
-        const float* src = which == 0 ? h : gpre;
-        const int C = which == 0 ? 8 : Co;
-        const float* sc = which == 0 ? nullptr : am;
-        uint4* dst = which == 0 ? hrec : grec;
-        switch (D) {
-            case 2: nd_pack_records_kernel<2><<<gridp, 256, 0, st>>>(src, C, sc, dst, nl, B); break;
-            case 3: nd_pack_records_kernel<3><<<gridp, 256, 0, st>>>(src, C, sc, dst, nl, B); break;
-            default: nd_pack_records_kernel<4><<<gridp, 256, 0, st>>>(src, C, sc, dst, nl, B); break;
-        }
-        if (int e = check_launch()) return e;
-    }
-
-    WgArgs a{};
-    a.h_rec = hrec; a.g_rec = grec; a.amax = am; a.gw = gw; a.gbias = gb; a.B = B; a.g = g;
-    const NdProps& pr = nd_props();
-    if (ensure_dynamic_smem<convnd_wgrad_tc_kernel>(pr.max_smem) != NFK_OK) return NFK_ECUDA;
-    long long grid = pr.sm_count;
-    const long long nunits = B * g.tiles_per_sample;
-    if (grid > nunits) grid = nunits;
-    convnd_wgrad_tc_kernel<<<(unsigned)grid, kWgThreads, g.smem_bytes, st>>>(a);
-    return check_launch();
+    if (int e = nd_pack_gradient(gpre, Co, lat, g.L, g.pstride, g.V, g.Vp, B, amax, grec, st)) return e;
+    if (int e = nd_pack(h_in, 8, nullptr, hrec, lat.ndim, g.L, g.pstride, g.V, g.Vp, B, st)) return e;
+    if (int e = nd_wgrad_run(p.w, hrec, grec, am, gw, gb, B, st)) return e;
+    return nd_dgrad_run(p.d, grec, am, w, act_below ? h_in : nullptr, gin, Co, Ci, B, img, st);
 }

@@ -324,6 +324,27 @@ def test_nd_tensor_core_weight_gradient(shape, Co, B, bias, gscale, monkeypatch)
         assert float((gb.double().cpu() - gb_ref).abs().max()) <= 2e-6 * float(gpre.abs().sum(dim=[0] + list(range(2, 2 + D))).max())
 
 
+@pytest.mark.parametrize("shape,Co,tanh", [((4, 6, 16), 28, True), ((2, 4, 4, 16), 8, True), ((8, 8, 32), 2, False)])
+def test_layer_backward_in_one_call_equals_the_two_kernels(shape, Co, tanh, monkeypatch):
+    """nfk_convnd_layer_bwd (the gradient reduced and packed once) against nfk_convnd_wgrad + nfk_convnd_dgrad."""
+    from normflow__b200 import _ops
+    D, B = len(shape), 3
+    g = torch.Generator('cpu').manual_seed(47)
+    rnd = lambda *s, scale=1.0: (torch.randn(*s, generator=g, device='cpu') * scale).to(DEV)
+    h = torch.tanh(rnd(B, 8, *shape))
+    gpre = rnd(B, Co, *shape, scale=1e-4)
+    w = rnd(Co, 8, *(3,) * D, scale=0.1)
+    act = _C.ACT['tanh'] if tanh else 0
+    both = _ops._conv_layer_bwd_tc(h, gpre, w, act, True, shape, 3)
+    assert both is not None
+    gw, gb, gin = both
+    gw2, gb2 = _ops._conv_weight_grad(h, None, 0, gpre, tuple(w.shape), True, shape, 3)
+    gin2 = _ops._conv_dgrad_tc(gpre, w, h, act, shape, 3)
+    assert torch.equal(gin, gin2)
+    assert torch.allclose(gw, gw2, rtol=1e-5, atol=1e-6 * float(gw2.abs().max()))       # (atomics: summation order differs)
+    assert torch.allclose(gb, gb2, rtol=1e-5, atol=1e-6 * float(gb2.abs().max()))
+
+
 def test_convact_unfused_path_equals_fused():
     torch.manual_seed(3)
     fused = ConvAct(1, 2, 3, hidden_sizes=[4], acts=['tanh', None], bias=True).to(DEV)
@@ -1279,8 +1300,8 @@ def test_cuda_graph_training_follows_the_eager_step():
 
 def test_cuda_graph_training_3d_with_the_tensor_core_backward():
     """The same on a 3-D lattice whose innermost extent is a multiple of 16: the captured step contains the N-D
-    tensor-core forward, nfk_convnd_dgrad (device-side scale, memset + amax + pack inside the graph) and
-    nfk_convnd_wgrad; graph replay must follow the eager loop."""
+    tensor-core forward and nfk_convnd_layer_bwd (device-side scale: memset + amax + pack inside the graph, then the
+    weight- and the data-gradient kernels); graph replay must follow the eager loop."""
     hist = {}
     for graph in (False, True):
         torch.manual_seed(78)
@@ -1296,7 +1317,7 @@ def test_cuda_graph_training_3d_with_the_tensor_core_backward():
             _C.kernel_timer = None
         if timer is not None:
             names = set(timer.summary())
-            assert any(k.startswith('convnd_dgrad') for k in names) and any(k.startswith('convnd_wgrad') for k in names), names
+            assert any(k.startswith('convnd_layer_bwd') for k in names), names
         hist[graph] = np.array(model.fit.train_history['loss'])
         assert len(hist[graph]) == 12 and np.isfinite(hist[graph]).all()
     np.testing.assert_allclose(hist[True][:4], hist[False][:4], rtol=2e-4, atol=2e-3)
