@@ -933,16 +933,22 @@ bool nd_plan(NdGeom& g, int N2, int G, int npass, int bdup, uint32_t budget, boo
             c.smem_bytes = off < kNdMinSmem ? kNdMinSmem : off;      // > half an SM: one CTA per SM owns all of TMEM
             if (c.smem_bytes > budget) continue;
             // Accumulation chains, in steps of nine MMAs (the taps of the two innermost axes for one channel group):
-            // one step where the extra TMEM columns are cheap (narrow accumulators), at most three otherwise (measured:
-            // 27 MMAs are within the parity contract, 81 are not), as far as TMEM still holds two tiles in flight.
+            // as many chains as still leave six accumulator slots in TMEM, and never more than three steps per chain
+            // (measured: 27 MMAs are within the parity contract, 81 are not; 16^4 with nine chains and three slots ran
+            // 10 % slower than with fewer chains and more slots).
             {
                 const int steps = c.ngroups * G;
-                c.nchunk = steps * N2 <= 170 ? steps : (steps + 2) / 3;
+                const int by_slots = kNdTmemCols / (6 * N2), by_len = (steps + 2) / 3;
+                c.nchunk = by_slots > by_len ? by_slots : by_len;
+                if (c.nchunk > steps) c.nchunk = steps;
                 if (c.nchunk * N2 > 256) c.nchunk = 256 / N2 > 0 ? 256 / N2 : 1;
                 if (const char* e = getenv("NFK_ND_CHUNKS")) {
                     const int v = atoi(e);
                     if (v >= 1 && v * N2 <= kNdTmemCols && v <= steps) c.nchunk = v;
                 }
+                // (the kernel starts a chain every ceil(steps / nchunk) steps: make nchunk the number of chains that gives)
+                const int len = (steps + c.nchunk - 1) / c.nchunk;
+                c.nchunk = (steps + len - 1) / len;
             }
             c.nslots = kNdTmemCols / (N2 * c.nchunk);
             if (c.nslots > kNdMaxSlots) c.nslots = kNdMaxSlots;
