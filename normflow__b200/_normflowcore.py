@@ -143,6 +143,7 @@ class Fitter:
         # captured CUDA graph.  For small lattices the step is pure launch latency (tens of kernels of
         # a few microseconds each); see _train_graph.  Also switched on by NFK_CUDA_GRAPH=1.
         self.cuda_graph = os.environ.get('NFK_CUDA_GRAPH') == '1'
+        self.graph_timing = None          # {'replays', 'ms'} of the last graph-mode fit (device time of the replays)
         self._pending_losses = []     # device scalars of the epochs since the last flush
         self._guard = None
 
@@ -339,6 +340,8 @@ class Fitter:
 
         print_stride = self.checkpoint_dict['print_stride']
         snapshot_path = self.checkpoint_dict['snapshot_path']
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
         for epoch in range(first_epoch, n_epochs + 1):
             graph.replay()
             diag = epoch == 1 or epoch == 10 or epoch % print_stride == 0
@@ -346,7 +349,11 @@ class Fitter:
             if diag or save:
                 flush(epoch - first_epoch + 1)
                 self._checkpoint_tail(epoch, save_every)
+        t1.record()
         flush(n_graph)
+        t1.synchronize()
+        # device time of the replayed epochs, capture excluded (diagnostics: bench.py reads it)
+        self.graph_timing = {'replays': n_graph, 'ms': t0.elapsed_time(t1)}
         return static_loss.detach()
 
     def step(self):
