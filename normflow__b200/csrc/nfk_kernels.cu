@@ -50,10 +50,74 @@ extern "C" int nfk_mask_select(const float* x, const uint8_t* mask, int keep, fl
 }
 
 // ============================================================== prior
+// Standard normal (no loc / scale), 1024 <= V <= 65536, V % 4 == 0: one CTA per sample, a thread draws quads of
+// sites.  The SAME numbers as PriorSampleOp up to the last bits of sqrt (same Philox counters, same uniforms, same
+// Box-Muller), with the generic kernel's per-call overheads removed: it executed 58 thread instructions per value
+// (ncu: issue slots 80 % busy, profiles/r02_prior_ncu_full.txt) where the draw itself needs about 25.
+__global__ void __launch_bounds__(256) prior_normal_fast_kernel(float* __restrict__ x, float* __restrict__ logr, int quads,
+                                                                uint64_t seed, uint64_t offset,
+                                                                const uint64_t* __restrict__ state) {
+    const uint64_t sd = state ? NFK_LDG(state) : seed, of = state ? NFK_LDG(state + 1) : offset;
+    const int64_t b = blockIdx.x;
+    const uint64_t c_base = (uint64_t)b * (uint64_t)quads;
+    float4* xb = reinterpret_cast<float4*>(x) + b * (int64_t)quads;
+    float acc = 0.f;
+    // the ten round keys depend on the seed only: out of the loop (philox4x32_10 re-derives them per call)
+    uint32_t rk0[10], rk1[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        rk0[i] = (uint32_t)sd + (uint32_t)i * 0x9E3779B9u;
+        rk1[i] = (uint32_t)(sd >> 32) + (uint32_t)i * 0xBB67AE85u;
+    }
+#pragma unroll 2
+    for (int q = threadIdx.x; q < quads; q += 256) {
+        Philox r;
+        {
+            const uint64_t ctr = c_base + (uint64_t)q;
+            uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = (uint32_t)of, c3 = (uint32_t)(of >> 32);
+#pragma unroll
+            for (int i = 0; i < 10; ++i) {
+                uint32_t h0, l0, h1, l1;
+                mulhilo(0xD2511F53u, c0, h0, l0);
+                mulhilo(0xCD9E8D57u, c2, h1, l1);
+                const uint32_t n0 = h1 ^ c1 ^ rk0[i], n2 = h0 ^ c3 ^ rk1[i];
+                c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+            }
+            r.c[0] = c0; r.c[1] = c1; r.c[2] = c2; r.c[3] = c3;
+        }
+        float z[4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float u1 = (float)r.c[2 * h] * 2.3283064365386963e-10f + 1.1641532182693481e-10f;
+            const float u2 = (float)r.c[2 * h + 1] * 2.3283064365386963e-10f + 1.1641532182693481e-10f;
+            float rad;
+            const float t = -1.3862943611198906f * __log2f(u1);             // -2 ln u1 >= 0 (u1 may round to 1)
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(t));
+            float sn, cs;
+            __sincosf(6.283185307179586f * (u2 - 0.5f), &sn, &cs);
+            z[2 * h] = rad * cs;
+            z[2 * h + 1] = rad * sn;
+        }
+        xb[q] = make_float4(z[0], z[1], z[2], z[3]);
+        acc = fmaf(z[0], z[0], fmaf(z[1], z[1], fmaf(z[2], z[2], fmaf(z[3], z[3], acc))));
+    }
+    if (logr == nullptr) return;
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) logr[b] = -0.5f * acc - 4.f * (float)quads * kLogSqrt2Pi;
+}
+static bool prior_fast_ok(const float* x, int64_t B, int64_t V, const float* loc, const float* scale) {
+    return !loc && !scale && V >= 1024 && V <= 65536 && (V & 3) == 0 && B < (1LL << 31) &&
+           (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+}
+
 extern "C" int nfk_prior_normal_sample(float* x, float* logr, int64_t B, int64_t V,
                                        const float* loc, const float* scale,
                                        uint64_t seed, uint64_t offset, void* stream) {
     if (!x) return NFK_EINVAL;
+    if (B > 0 && prior_fast_ok(x, B, V, loc, scale)) {
+        prior_normal_fast_kernel<<<(unsigned)B, 256, 0, NFK_STREAM(stream)>>>(x, logr, (int)(V >> 2), seed, offset, nullptr);
+        return check_launch();
+    }
     return launch_sites_vec<PriorSampleOp, 4>(PriorSampleOp{x, loc, scale, V, seed, offset, nullptr}, B, V,
                                               nullptr, logr, NFK_STREAM(stream));
 }
@@ -66,8 +130,14 @@ extern "C" int nfk_prior_normal_sample_dev(float* x, float* logr, int64_t B, int
                                            const float* loc, const float* scale,
                                            uint64_t* state, void* stream) {
     if (!x || !state) return NFK_EINVAL;
-    const int rc = launch_sites_vec<PriorSampleOp, 4>(PriorSampleOp{x, loc, scale, V, 0, 0, state}, B, V,
-                                                      nullptr, logr, NFK_STREAM(stream));
+    int rc;
+    if (B > 0 && prior_fast_ok(x, B, V, loc, scale)) {
+        prior_normal_fast_kernel<<<(unsigned)B, 256, 0, NFK_STREAM(stream)>>>(x, logr, (int)(V >> 2), 0, 0, state);
+        rc = check_launch();
+    } else {
+        rc = launch_sites_vec<PriorSampleOp, 4>(PriorSampleOp{x, loc, scale, V, 0, 0, state}, B, V,
+                                                nullptr, logr, NFK_STREAM(stream));
+    }
     if (rc != NFK_OK) return rc;
     advance_offset_kernel<<<1, 1, 0, NFK_STREAM(stream)>>>(state);
     return check_launch();
