@@ -21,6 +21,13 @@
 // tile of 128 box positions, fp32 accumulation in TMEM.  Rows that fall on the box's halo are computed and
 // dropped.  A persistent CTA per SM walks (sample, tile) units: cp.async box load -> MMAs of every M tile, each
 // committed to its own mbarrier -> epilogue warps drain the TMEM accumulator ring behind the MMA stream.
+//
+// The same file holds the BACKWARD of those conditioner layers on the tensor cores (autograd of modules.py:131-145):
+//   data gradient    (nfk_convnd_dgrad)   the hidden-layer kernel on transposed, mirrored weights (MODE 2), its input
+//                                         d loss / d pre-activation packed into records scaled by a power of two from its
+//                                         device-side max (fp16 pairs have float16's exponent range)
+//   weight gradient  (nfk_convnd_wgrad)   a GEMM over the SITES whose operands are the records read as MN-major matrices
+//   nfk_convnd_layer_bwd                  both, behind one reduction + packing of the gradient
 
 #include <stdio.h>
 #include <stdlib.h>
