@@ -17,9 +17,9 @@ B4=256 B5=32 ncu --set full --clock-control none --import-source on -k regex:"nd
     python scratch/nd_time.py > /dev/null 2>&1
 B4=256 B5=32 ncu --set full --clock-control none --import-source on -k regex:"nd_layer1|convnd" -s 27 -c 3 -o gpurun_out/r02_nd4d \
     python scratch/nd_time.py > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"PairSites.*RqsOp<10, 0>" -c 1 -o gpurun_out/r02_rqs_fwd \
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"PairSites<nfk::RqsOp" -c 1 -o gpurun_out/r02_rqs_fwd \
     python scratch/kernel_roofline.py > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"PriorSampleOp" -c 1 -o gpurun_out/r02_prior \
+ncu --set full --clock-control none --import-source on -k regex:"prior_normal_fast" -c 1 -o gpurun_out/r02_prior \
     python scratch/kernel_roofline.py > /dev/null 2>&1
 # tensor-core backward: weight gradient (MN-major operands) and data gradient of the 8 -> 28 layer at config-4 geometry
 ncu --set full --clock-control none --import-source on -k regex:"convnd_wgrad_tc|convnd_tc_kernel" -s 2 -c 2 -o gpurun_out/r02_bwd3d \
