@@ -440,7 +440,7 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     numa = None
-    if world > 1:
+    if world > 1 and os.environ.get("NFK_BENCH_AFFINITY", "1") != "0":
         # several ranks share one host: run this rank's threads on the CPUs next to its GPU, so that the pinned host
         # buffers of the end-to-end figure are first touched on the GPU-local NUMA node (8 ranks x 268 MB per step
         # through one memory controller cost 5.6 % at N = 8 in round 1)
@@ -451,6 +451,7 @@ def run_b200(args):
             numa = len(os.sched_getaffinity(0))
         except Exception:
             numa = None
+    if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from normflow__b200 import _C
     model = build_model(torch)
