@@ -336,9 +336,12 @@ int nfk_fusednd_step_train(const float* x, const float* w1, const float* b1, con
  * gpre [B][Co][V] = d loss / d (this layer's pre-activation output), w [Co][Ci][3^D], gin [B][Ci][V].
  * Ci in {8, 16, 32, 64}, 1 <= Co <= 64, 2-D .. 4-D lattices with even extents; NFK_EUNSUPPORTED otherwise (the
  * caller then uses nfk_conv_circ_fwd with transposed weights).  Operands are fp16 pairs scaled by a power of two
- * found from max |gpre| on the device.  `workspace`: nfk_convnd_dgrad_workspace bytes, 256-byte aligned.        */
+ * found from max |gpre| on the device.  g_parity >= 0 (as in nfk_conv_circ_fwd_cb): gpre vanishes on the sites whose
+ * coordinate sum % 2 != g_parity -- the gradient of a checkerboard coupling's conditioner output -- and only the MMAs
+ * that land on populated sites are issued (half of them); -1: dense.
+ * `workspace`: nfk_convnd_dgrad_workspace bytes (covers either form), 256-byte aligned.                          */
 int64_t nfk_convnd_dgrad_workspace(nfk_lattice lat, int Co, int Ci, int64_t B);
-int nfk_convnd_dgrad(const float* gpre, const float* w, const float* h, float* gin, int Co, int Ci,
+int nfk_convnd_dgrad(const float* gpre, int g_parity, const float* w, const float* h, float* gin, int Co, int Ci,
                      nfk_lattice lat, int64_t B, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Weight and bias gradient of one circular 3^D convolution layer with 8 input channels on the tensor cores (autograd
@@ -356,10 +359,11 @@ int nfk_convnd_wgrad(const float* h, const float* gpre, float* gw, float* gb, in
  * nfk_convnd_wgrad and nfk_convnd_dgrad compute, with d loss / d pre-activation reduced (max |g|) and packed into records
  * once for both kernels.  h_in [B][8][V] is the layer's input -- and, when act_below != 0, the tanh output whose derivative
  * multiplies the data gradient; gw / gb are accumulated into, gin [B][8][V] is written.  Applies where both kernels do
- * (8 input channels, Co <= 32, innermost extent a multiple of 16); NFK_EUNSUPPORTED otherwise.                          */
+ * (8 input channels, Co <= 32, innermost extent a multiple of 16); NFK_EUNSUPPORTED otherwise.  g_parity as in
+ * nfk_convnd_dgrad (the weight gradient reads the dense records either way).                                        */
 int64_t nfk_convnd_layer_bwd_workspace(nfk_lattice lat, int Co, int Ci, int64_t B);
-int nfk_convnd_layer_bwd(const float* h_in, const float* gpre, const float* w, int act_below, float* gin,
-                         float* gw, float* gb, int Co, int Ci, nfk_lattice lat, int64_t B,
+int nfk_convnd_layer_bwd(const float* h_in, const float* gpre, int g_parity, const float* w, int act_below,
+                         float* gin, float* gw, float* gb, int Co, int Ci, nfk_lattice lat, int64_t B,
                          void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------- PSD block (spectral part) ---

@@ -73,9 +73,9 @@ _SIGNATURES = {
                          c_f, c_f, c_f, c_l, c_f, c_l, c_f],
     "nfk_fusednd_step_train": [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, RqsParams, Lattice, c_i, c_i,
                                c_f, c_f, c_f, c_f, c_f, c_f, c_l, c_f, c_l, c_f],
-    "nfk_convnd_dgrad": [c_f, c_f, c_f, c_f, c_i, c_i, Lattice, c_l, c_f, c_l, c_f],
+    "nfk_convnd_dgrad": [c_f, c_i, c_f, c_f, c_f, c_i, c_i, Lattice, c_l, c_f, c_l, c_f],
     "nfk_convnd_wgrad": [c_f, c_f, c_f, c_f, c_i, c_i, Lattice, c_l, c_f, c_l, c_f],
-    "nfk_convnd_layer_bwd": [c_f, c_f, c_f, c_i, c_f, c_f, c_f, c_i, c_i, Lattice, c_l, c_f, c_l, c_f],
+    "nfk_convnd_layer_bwd": [c_f, c_f, c_i, c_f, c_i, c_f, c_f, c_f, c_i, c_i, Lattice, c_l, c_f, c_l, c_f],
     "nfk_psd_weights_fwd": [c_f, c_l, c_i, c_i, c_f, c_f, c_f],
     "nfk_psd_weights_bwd": [c_f, c_f, c_f, c_f, c_l, c_i, c_i, c_f, c_f],
     "nfk_psd_scale": [c_f, c_f, c_f, c_fl, c_f, c_l, c_l, c_f],

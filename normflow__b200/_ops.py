@@ -656,7 +656,7 @@ def _conv_call(inp, w, transposed, bias, in_mask, in_keep, act, dact_from, dact_
     return out
 
 
-def _conv_dgrad_tc(gpre, w, h, dact_kind, shape, ksize):
+def _conv_dgrad_tc(gpre, w, h, dact_kind, shape, ksize, g_parity=None):
     """Data gradient of a layer on the tensor cores (nfk_convnd_dgrad): d loss / d pre-activation of the layer below
     from `gpre` = d loss / d this layer's output, `w` (Co, Ci, 3, ..) and the post-activation `h` of the layer below
     (tanh) or None.  Returns None where the kernel does not apply (the caller then runs the CUDA-core convolution
@@ -667,9 +667,11 @@ def _conv_dgrad_tc(gpre, w, h, dact_kind, shape, ksize):
             or Ci not in (8, 16, 32, 64) or Co > 64 or dact_kind not in (0, _C.ACT['tanh'])):
         return None
     if len(shape) == 2 and Ci == 8 and mode != '1':
-        # 2-D, [8, 8] conditioner: break-even with the shared-memory CUDA-core kernels at 64 x 64 (whose checkerboard form
-        # skips the known zeros of the last layer's gradient) and five launches instead of one on small lattices
-        return None
+        # 2-D, [8, 8] conditioner: the dense 8 -> 8 gradient is break-even with the shared-memory CUDA-core kernel at
+        # 64 x 64 and five launches instead of one on small lattices; the checkerboard-sparse gradient of the last layer
+        # is faster here (half the MMAs: 1.7 vs 2.05 ms at 64 x 64, B = 4096) once the batch is large enough to fill it
+        if g_parity is None or gpre.shape[0] * int(np.prod(shape)) < (1 << 22):
+            return None
     lat = _C.lattice(shape)
     B = gpre.shape[0]
     per_sample = int(lib().nfk_convnd_dgrad_workspace(lat, Co, Ci, 1))
@@ -685,13 +687,14 @@ def _conv_dgrad_tc(gpre, w, h, dact_kind, shape, ksize):
     with _C.timed(f"convnd_dgrad[{Co}->{Ci}]"):
         for lo in range(0, B, chunk):
             hi = min(B, lo + chunk)
-            check(lib().nfk_convnd_dgrad(dev(gpre[lo:hi]), dev(w), None if h is None else dev(h[lo:hi]), dev(gin[lo:hi]),
+            check(lib().nfk_convnd_dgrad(dev(gpre[lo:hi]), -1 if g_parity is None else int(g_parity), dev(w),
+                                         None if h is None else dev(h[lo:hi]), dev(gin[lo:hi]),
                                          Co, Ci, lat, hi - lo, dev(workspace, torch.uint8), need, stream()),
                   "convnd_dgrad")
     return gin
 
 
-def _conv_layer_bwd_tc(h_in, gpre, w, dact_kind, want_bias, shape, ksize):
+def _conv_layer_bwd_tc(h_in, gpre, w, dact_kind, want_bias, shape, ksize, g_parity=None):
     """Weight, bias and data gradient of one layer with 8 input channels in one call (nfk_convnd_layer_bwd: the gradient
     is reduced and packed into records once for both tensor-core kernels).  Returns (gw, gb, gin) or None where the pair
     does not apply or is not the default (2-D lattices, see _conv_dgrad_tc / _conv_weight_grad)."""
@@ -716,7 +719,8 @@ def _conv_layer_bwd_tc(h_in, gpre, w, dact_kind, want_bias, shape, ksize):
     with _C.timed(f"convnd_layer_bwd[{Ci}->{Co}]"):
         for lo in range(0, B, chunk):
             hi = min(B, lo + chunk)
-            check(lib().nfk_convnd_layer_bwd(dev(h_in[lo:hi]), dev(gpre[lo:hi]), dev(w), int(dact_kind != 0), dev(gin[lo:hi]),
+            check(lib().nfk_convnd_layer_bwd(dev(h_in[lo:hi]), dev(gpre[lo:hi]), -1 if g_parity is None else int(g_parity),
+                                             dev(w), int(dact_kind != 0), dev(gin[lo:hi]),
                                              dev(gw), dev(gb), Co, Ci, lat, hi - lo, dev(workspace, torch.uint8), need,
                                              stream()), "convnd_layer_bwd")
     return gw, gb, gin
@@ -815,12 +819,14 @@ class _ConvStack(torch.autograd.Function):
 
 
 def _conv_stack_backward(hs, weights, has_bias, acts, ksize, shape, in_mask, in_keep, gpre, need_input_grad,
-                         gpre_parity=None):
+                         gpre_parity=None, tc_parity=None):
     """Gradients of a ConvAct stack.  hs[i] = input of layer i (hs[0] the stack's input, hs[i] the
     post-activation output of layer i-1), gpre = d loss / d (output of the last layer, which has
     no activation).  Walks the layers in reverse: one weight-gradient kernel plus one
     data-gradient kernel (the same circular conv on transposed/flipped weights with act' fused in
-    its epilogue) per layer.  Returns (weight grads, bias grads, input grad or None)."""
+    its epilogue) per layer.  Returns (weight grads, bias grads, input grad or None).
+    gpre_parity: gpre vanishes on the sites with coordinate sum % 2 != gpre_parity (2-D checkerboard kernels and the
+    tensor-core data gradient skip the known zeros); tc_parity: the same, for the tensor-core data gradient only."""
     n = len(weights)
     if acts[n - 1] != 0:
         raise NotImplementedError("ConvAct with an activation on the output layer: use the unfused path")
@@ -830,7 +836,8 @@ def _conv_stack_backward(hs, weights, has_bias, acts, ksize, shape, in_mask, in_
         Co, Ci = w.shape[0], w.shape[1]
         first = (i == 0)
         if not first:
-            both = _conv_layer_bwd_tc(hs[i], gpre, w.contiguous(), acts[i - 1], has_bias[i], shape, ksize)
+            sp = (tc_parity if tc_parity is not None else gpre_parity) if i == n - 1 else None
+            both = _conv_layer_bwd_tc(hs[i], gpre, w.contiguous(), acts[i - 1], has_bias[i], shape, ksize, g_parity=sp)
             if both is not None:
                 gws[i], gbs[i], gpre = both
                 continue
@@ -842,7 +849,8 @@ def _conv_stack_backward(hs, weights, has_bias, acts, ksize, shape, in_mask, in_
             break
         # d/d(input of layer i): conv of gpre with w^T (taps flipped); multiply by act'(h_{i})
         if not first:
-            g_tc = _conv_dgrad_tc(gpre, w.contiguous(), hs[i], acts[i - 1], shape, ksize)
+            sp = (tc_parity if tc_parity is not None else gpre_parity) if i == n - 1 else None
+            g_tc = _conv_dgrad_tc(gpre, w.contiguous(), hs[i], acts[i - 1], shape, ksize, g_parity=sp)
             if g_tc is not None:
                 gpre = g_tc
                 continue
@@ -976,14 +984,14 @@ class _FusedNdStepTrain(torch.autograd.Function):
                                                dev(log_out), dev(h1), dev(h2), dev(out), B,
                                                dev(workspace, torch.uint8), need, stream()), "fusednd_step_train")
         ctx.save_for_backward(x, h1, h2, out, mask, *w)
-        ctx.cfg = (kind, prm, parity, log_in is not None, [t is not None for t in b])
+        ctx.cfg = (kind, prm, parity, mask_parity, log_in is not None, [t is not None for t in b])
         return y, log_out
 
     @staticmethod
     @_native
     def backward(ctx, gy, glog):
         x, h1, h2, out, mask, *w = ctx.saved_tensors
-        kind, prm, parity, has_log, has_bias = ctx.cfg
+        kind, prm, parity, mask_parity, has_log, has_bias = ctx.cfg
         B, shape = x.shape[0], tuple(x.shape[1:])
         V = x[0].numel()
         gy, glog = _f32c(gy, "gy"), _f32c(glog, "glog")
@@ -996,8 +1004,12 @@ class _FusedNdStepTrain(torch.autograd.Function):
                                        dev(glog), dev(gx), dev(gout), B, V, stream()), "affine_bwd")
         frozen_keep = 0 if parity == 0 else 1          # the conditioner saw the frozen partition only
         acts = (_C.ACT['tanh'], _C.ACT['tanh'], _C.ACT[None])
+        # gout is non-zero on the active partition only: sites with (sum of coordinates) % 2 == g_parity
+        # (mask bit = (1 - mask_parity + sum) % 2, active <=> bit == (parity == 0))
+        g_parity = ((1 if parity == 0 else 0) - 1 + mask_parity) % 2
         gws, gbs, gin = _conv_stack_backward([x.unsqueeze(1), h1, h2], w, has_bias, acts, 3, shape, mask,
-                                             frozen_keep, gout, ctx.needs_input_grad[0])
+                                             frozen_keep, gout, ctx.needs_input_grad[0],
+                                             gpre_parity=g_parity if len(shape) == 2 else None, tc_parity=g_parity)
         if gin is not None:
             gx = gx + gin.reshape(x.shape)
         return (gx, glog if has_log else None, None, None, None, None, None, None, *gws, *gbs)

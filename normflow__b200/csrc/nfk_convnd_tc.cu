@@ -78,6 +78,10 @@ struct NdGeom {
     int out_split;               // hidden layer (MODE 0): write the records in that form
     int compact;                 // last layer (MODE 1): read them in that form
     int prefetch;                // pull the next unit's box into L2 while this one is computed (NFK_ND_PREFETCH=0: off)
+    // Data gradient of a checkerboard-sparse input (MODE 2): the records exist on ONE parity plane of the odd-extent array
+    // only (sites with coordinate sum % 2 == gpar); M tiles enumerate the output positions of one box parity at a time
+    // (nt = 2 x tiles of one parity), and a tap is issued only where it lands on the populated plane -- half the MMAs
+    int sparse, gpar;
     int last;                    // compact: linear box index of the last interior position (first: the first)
     uint32_t pb_bytes;           // compact: bytes of one parity plane of the box in shared memory
     uint32_t off_a, off_b, off_tab, off_bar, smem_bytes;
@@ -254,6 +258,31 @@ __global__ void __launch_bounds__(256) nd_amax_kernel(const float* __restrict__ 
     if (threadIdx.x == 0) {
         for (int i = 1; i < 8; ++i) m = fmaxf(m, sm[i]);
         atomicMax(amax, __float_as_uint(m));
+    }
+}
+
+// The same for records that exist on ONE parity plane only (checkerboard-sparse gradients): planes [hi][lo], Eh records each.
+template <int ND>
+__device__ __forceinline__ void nd_store_site_plane(uint4* base, int Eh, const int (&c)[ND], const int (&L)[ND],
+                                                    const int (&es)[ND], const uint4& hi, const uint4& lo) {
+    int diff[ND];
+    int hasmask = 0, P = 0;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        const int m = (c[d] + 1) * es[d];
+        const bool has = es[d] != 0 && (c[d] == 0 || c[d] == L[d] - 1);
+        diff[d] = (c[d] == 0 ? (L[d] + 1) * es[d] : 0) - m;
+        hasmask |= has ? 1 << d : 0;
+        P += m;
+    }
+    base[P >> 1] = hi;
+    base[Eh + (P >> 1)] = lo;
+    for (int mask = hasmask; mask; mask = (mask - 1) & hasmask) {      // (images differ by even amounts: same plane)
+        int o = P;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) o += (mask >> d) & 1 ? diff[d] : 0;
+        base[o >> 1] = hi;
+        base[Eh + (o >> 1)] = lo;
     }
 }
 
@@ -446,6 +475,65 @@ int nd_pack(const float* src, int C, const float* amax, uint4* rec, int D, const
     return check_launch();
 }
 
+// Checkerboard-sparse gradient (non-zero on the sites whose coordinate sum % 2 == gpar only): records of those sites
+// on one parity plane of the odd-extent array ([B][ceil(C/8)][2][Eh]).  A thread owns a pair of sites of the innermost axis.
+template <int D>
+__global__ void __launch_bounds__(256) nd_pack_active_kernel(const float* __restrict__ gsrc, int C, const float* __restrict__ amax,
+                                                             uint4* __restrict__ out_rec, const NdLat lat, int Eh, int gpar,
+                                                             long long B) {
+    const int gidx = blockIdx.y, G = gridDim.y;
+    const int pairs = lat.V >> 1;
+    const int bps = (pairs + 255) >> 8;
+    const long long b = blockIdx.x / bps;
+    const int pi = (int)(blockIdx.x - b * bps) * 256 + threadIdx.x;
+    if (b >= B || pi >= pairs) return;
+    const float scale = amax ? nd_grad_scale(NFK_LDG(amax)) : 1.f;
+    int Ld[D], es[D], c[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) { Ld[d] = lat.L[d]; es[d] = lat.pstride[d]; }       // (pstride carries the odd-extent strides here)
+    int rem = 2 * pi, csum = 0;
+#pragma unroll
+    for (int d = D - 1; d >= 0; --d) {
+        const int q = nd_div(rem, Ld[d], lat.magic_L[d]);
+        c[d] = rem - q * Ld[d];
+        rem = q;
+        csum += c[d];
+    }
+    const int add = (csum ^ gpar) & 1;                  // the pair's populated site
+    c[D - 1] += add;
+    const int site = 2 * pi + add;
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int ch = gidx * 8 + k;
+        v[k] = ch < C ? scale * NFK_LDG(gsrc + (b * C + ch) * (long long)lat.V + site) : 0.f;
+    }
+    uint4 hi, lo;
+    nd_records(v, hi, lo);
+    nd_store_site_plane<D>(out_rec + (b * G + gidx) * 2LL * Eh, Eh, c, Ld, es, hi, lo);
+}
+
+int nd_pack_active(const float* src, int C, const float* amax, uint4* rec, int D, const int (&L)[4], const int (&estride)[4], int V,
+                   int Eh, int gpar, int64_t B, cudaStream_t st) {
+    NdLat nl{};
+    for (int d = 0; d < 4; ++d) {
+        const int j = d + 4 - D;
+        nl.L[d] = d < D ? L[j] : 1;
+        nl.pstride[d] = d < D ? estride[j] : 0;
+        nl.magic_L[d] = nd_magic(nl.L[d]);
+    }
+    nl.V = V;
+    const long long blocks = B * ((V / 2 + 255) / 256);
+    if (blocks >= (1LL << 31)) return NFK_EUNSUPPORTED;
+    const dim3 gridp((unsigned)blocks, (unsigned)((C + 7) / 8));
+    switch (D) {
+        case 2: nd_pack_active_kernel<2><<<gridp, 256, 0, st>>>(src, C, amax, rec, nl, Eh, gpar, B); break;
+        case 3: nd_pack_active_kernel<3><<<gridp, 256, 0, st>>>(src, C, amax, rec, nl, Eh, gpar, B); break;
+        default: nd_pack_active_kernel<4><<<gridp, 256, 0, st>>>(src, C, amax, rec, nl, Eh, gpar, B); break;
+    }
+    return check_launch();
+}
+
 // ------------------------------------------------------------------------------------------- layers 2 and 3
 __device__ __forceinline__ void nd_bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -536,7 +624,8 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
             const uint32_t a_base = tc::smem_u32(A);
             const uint32_t b_base = tc::smem_u32(Bs);
             // (compact: the hi -> lo distance is two parity planes; plane 1 follows plane 0)
-            const uint64_t a_desc = tc::make_desc(a_base, g.compact ? 2u * g.pb_bytes : g.comp_bytes, 128);
+            const bool sparse = MODE == 2 && g.sparse;
+            const uint64_t a_desc = tc::make_desc(a_base, sparse ? g.pb_bytes : (g.compact ? 2u * g.pb_bytes : g.comp_bytes), 128);
             const int pbrec = (int)(g.pb_bytes >> 4);
             const uint64_t b_desc = tc::make_desc(b_base, g.bdup == 2 ? N2 * 16 : 0, 128);
             const uint32_t idesc = tc::make_idesc(0, 128, N2);
@@ -545,7 +634,7 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
             // steps (nine taps of one channel group) per accumulation chain
             const int chain_len = (g.ngroups * G + g.nchunk - 1) / g.nchunk;
             const int bstep = g.bdup * N2;                           // B rows per (tap, channel group)
-            const int gstep = (int)((g.compact ? 4 * g.pb_bytes : 2 * g.comp_bytes) >> 4);   // records between two channel groups' planes
+            const int gstep = (int)((sparse ? 2 * g.pb_bytes : (g.compact ? 4 * g.pb_bytes : 2 * g.comp_bytes)) >> 4);   // records between two channel groups' planes
             int slot = 0;
             uint32_t ring_phase = 0, load_phase = 0;
             int last_slot[kNdIssuers], cur_pass = -1;                // last tile of every issuer in the previous unit
@@ -558,13 +647,16 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                 unit_origin(unit, pass, b, org);
                 const int pib = unit_parity(org);
                 const int cfirst = (g.first + ((pib ^ g.first) & 1)) >> 1;
+                // sparse: box parity of the populated (non-zero) positions of this unit
+                const int abox = (g.gpar ^ org[0] ^ org[1] ^ org[2] ^ org[3] ^ g.D) & 1;
                 if (iw == 0) {
                     // box (and weights) may be overwritten once every MMA of the previous unit has completed
 #pragma unroll
                     for (int w = 0; w < kNdIssuers; ++w)
                         if (last_slot[w] >= 0) tc::mbar_wait(tc::smem_u32(full + last_slot[w]), last_phase[w]);
                     const uint32_t run_bytes = (uint32_t)g.run_rec * 16;
-                    uint32_t tx = g.compact ? 2u * G * (uint32_t)g.nbox * 16u : 2u * G * g.nruns * run_bytes;
+                    uint32_t tx = sparse ? 2u * G * (uint32_t)((g.nbox + 1 - abox) >> 1) * 16u
+                                         : (g.compact ? 2u * G * (uint32_t)g.nbox * 16u : 2u * G * g.nruns * run_bytes);
                     if (pass != cur_pass) tx += g.b_bytes;
                     nd_expect_tx(loaded_bar, tx);
                     if (pass != cur_pass) {
@@ -576,7 +668,7 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                         int rem = k, so = 0;
 #pragma unroll
                         for (int d = 3; d >= 0; --d) {
-                            const int st = g.compact ? g.estride[d] : g.pstride[d];
+                            const int st = (g.compact || sparse) ? g.estride[d] : g.pstride[d];
                             if (d < g.split) {
                                 const int q = nd_div(rem, g.box[d], g.magic_box[d]);
                                 so += (org[d] + rem - q * g.box[d]) * st;
@@ -585,7 +677,21 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                                 so += org[d] * st;         // (d == split; the axes behind it are whole: origin 0)
                             }
                         }
-                        if (!g.compact) {
+                        if (sparse) {
+                            // the run's positions of box parity abox, from the one populated plane of the source
+                            const int a0 = k * g.run_rec;
+                            const int pq = a0 + ((abox ^ a0) & 1);
+                            if (pq < a0 + g.run_rec) {
+                                const int n = (a0 + g.run_rec - pq + 1) >> 1;
+                                const int Pq = so + (pq - a0);
+                                for (int gi = 0; gi < G; ++gi) {
+                                    const uint4* src = a.in_rec + (b * G + gi) * 2LL * g.Eh + (Pq >> 1);
+                                    const uint32_t dst = a_base + (uint32_t)gi * 2u * g.pb_bytes + (pq >> 1) * 16;
+                                    nd_bulk_load(dst, src, n * 16, loaded_bar);
+                                    nd_bulk_load(dst + g.pb_bytes, src + g.Eh, n * 16, loaded_bar);
+                                }
+                            }
+                        } else if (!g.compact) {
                             for (int gi = 0; gi < G; ++gi) {
                                 const uint4* src = a.in_rec + (b * G + gi) * 2LL * g.Vp + so;
                                 const uint32_t dst = a_base + (uint32_t)gi * 2u * g.comp_bytes + k * run_bytes;
@@ -620,7 +726,7 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                         int rem = k, so = 0;
 #pragma unroll
                         for (int d = 3; d >= 0; --d) {
-                            const int st = g.compact ? g.estride[d] : g.pstride[d];
+                            const int st = (g.compact || sparse) ? g.estride[d] : g.pstride[d];
                             if (d < g.split) {
                                 const int q = nd_div(rem, g.box[d], g.magic_box[d]);
                                 so += (norg[d] + rem - q * g.box[d]) * st;
@@ -630,7 +736,12 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                             }
                         }
                         for (int gi = 0; gi < G; ++gi) {
-                            if (!g.compact) {
+                            if (sparse) {
+                                const uint4* src = a.in_rec + (nb * G + gi) * 2LL * g.Eh + (so >> 1);
+                                const uint32_t n16 = (uint32_t)((g.run_rec + 1) >> 1) * 16;
+                                nd_prefetch_l2(src, n16);
+                                nd_prefetch_l2(src + g.Eh, n16);
+                            } else if (!g.compact) {
                                 const uint4* src = a.in_rec + (nb * G + gi) * 2LL * g.Vp + so;
                                 nd_prefetch_l2(src, (uint32_t)g.run_rec * 16);
                                 nd_prefetch_l2(src + g.Vp, (uint32_t)g.run_rec * 16);
@@ -664,10 +775,15 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                     // round-to-nearest
                     // compact: tile rows are the active positions c (box position 2 c + pib); a tap with linear offset
                     // d reads parity plane (pib + d) & 1 at row c + ((pib + d) >> 1) -- the same shift for every row
-                    const uint64_t ad0 = tc::desc_advance(a_desc, (g.compact ? cfirst : g.first) + m * 128);
+                    // sparse: tiles 0 .. nt/2 - 1 are the output positions of box parity 0, the rest those of parity 1
+                    const int rp = sparse ? (m >= (g.nt >> 1) ? 1 : 0) : 0;
+                    const int ms = sparse ? m - rp * (g.nt >> 1) : m;
+                    const int cfs = (g.first + ((rp ^ g.first) & 1)) >> 1;
+                    const uint64_t ad0 = tc::desc_advance(a_desc, (sparse ? cfs : (g.compact ? cfirst : g.first)) + ms * 128);
                     uint64_t bd = b_desc;
                     uint32_t acc = tmem + slot * cols_per_slot;
                     int cnt = 0;
+                    uint32_t accf = 0;                                 // sparse: 0 for the first MMA of a chain
                     for (int o = 0; o < g.ngroups; ++o) {
                         // offset of the outer taps of this group: o enumerates (k0, k1) of the two outer axes
                         int od;
@@ -683,6 +799,16 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
 #pragma unroll
                             for (int i = 0; i < 9; ++i) {
                                 int dl = (i / 3 - 1) * s2 + (i % 3 - 1);
+                                if (MODE == 2 && sparse) {
+                                    // (all box strides odd: the parity of a tap's offset is that of its number of unit steps)
+                                    const int sft = rp + od + dl;
+                                    if (((sft ^ abox) & 1) == 0) {
+                                        tc::mma_f16(acc, tc::desc_advance(ad, (sft >> 1) - od), tc::desc_advance(bdg, i * G * bstep),
+                                                    idesc, accf);
+                                        accf = 1u;
+                                    }
+                                    continue;
+                                }
                                 if (g.compact) {
                                     const int sft = pib + od + dl;
                                     dl = (sft >> 1) + (sft & 1) * pbrec - od;       // (`ad` already carries od)
@@ -690,7 +816,7 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                                 tc::mma_f16(acc, tc::desc_advance(ad, dl), tc::desc_advance(bdg, i * G * bstep), idesc,
                                             (cnt | i) != 0);
                             }
-                            if (++cnt == chain_len) { cnt = 0; acc += N2; }
+                            if (++cnt == chain_len) { cnt = 0; acc += N2; accf = 0; }
                             ad = tc::desc_advance(ad, gstep);
                             bdg = tc::desc_advance(bdg, bstep);
                         }
@@ -721,6 +847,35 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                     if (++slot == nslots) { slot = 0; ring_phase ^= 1u; }
                     continue;
                 }
+                // data gradient: the tanh outputs this row's result is multiplied by are fetched BEFORE waiting for the
+                // tile's MMAs (eight dependent global loads per row were a fifth of the kernel's stall samples)
+                float hv[MODE == 2 ? NH : 1];
+                if (MODE == 2 && a.act) {
+                    const int r0 = m * 128 + quarter * 32 + lane;
+                    int rem0;
+                    bool ok0 = true;
+                    if (g.sparse) {
+                        const int rp = m >= (g.nt >> 1) ? 1 : 0;
+                        const int cfs = (g.first + ((rp ^ g.first) & 1)) >> 1;
+                        rem0 = 2 * (cfs + (r0 - rp * (g.nt >> 1) * 128)) + rp;
+                        ok0 = rem0 <= g.last;
+                    } else {
+                        ok0 = r0 < g.span;
+                        rem0 = g.first + r0;
+                    }
+                    int site0 = 0;
+#pragma unroll
+                    for (int d = 3; d >= 0; --d) {
+                        const int q = nd_div(rem0, g.box[d], g.magic_box[d]);
+                        const int i = rem0 - q * g.box[d];
+                        rem0 = q;
+                        ok0 = ok0 && i >= g.lo[d] && i <= g.hi[d];
+                        site0 += (org[d] + i - g.off[d]) * g.gstride[d];
+                    }
+#pragma unroll
+                    for (int c = 0; c < NH; ++c)
+                        hv[c] = ok0 ? NFK_LDG(a.act + (b * a.save_ch + pass * NH + c) * (long long)g.V + site0) : 0.f;
+                }
                 tc::mbar_wait(tc::smem_u32(full + slot), ring_phase);
                 tc::fence_after_sync();
                 float hi[NH], lo[NH];
@@ -729,11 +884,20 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                 for (int ch = 0; ch < g.nchunk; ++ch) {
                     const uint32_t col = lane_addr + slot * cols_per_slot + ch * N2;
                     if (NH == 8) {
-                        float acc[16];
+                        // two chains per round trip to TMEM (a load + wait is ~150 cycles; the narrow layers' tiles are
+                        // a few hundred cycles of MMAs, so the epilogue paced them)
+                        float acc[16], acc2[16];
+                        const bool two = ch + 1 < g.nchunk;
                         tc::tmem_ld16(col, acc);
+                        if (two) tc::tmem_ld16(col + N2, acc2);
                         tc::tmem_ld_wait();
 #pragma unroll
                         for (int c = 0; c < 8; ++c) { hi[c] += acc[c]; lo[c] += acc[8 + c]; }
+                        if (two) {
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) { hi[c] += acc2[c]; lo[c] += acc2[8 + c]; }
+                            ++ch;
+                        }
                     } else {
 #pragma unroll
                         for (int q8 = 0; q8 < NH / 8; ++q8) {
@@ -753,7 +917,12 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                 // which site is this row?
                 const int r = m * 128 + quarter * 32 + lane;
                 int rem;
-                if (g.compact) {
+                if (MODE == 2 && g.sparse) {
+                    const int rp = m >= (g.nt >> 1) ? 1 : 0;
+                    const int cfs = (g.first + ((rp ^ g.first) & 1)) >> 1;
+                    rem = 2 * (cfs + (r - rp * (g.nt >> 1) * 128)) + rp;
+                    if (rem > g.last) continue;
+                } else if (g.compact) {
                     rem = 2 * (cfirst + r) + pib;
                     if (rem > g.last) continue;
                 } else {
@@ -803,10 +972,7 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                     for (int c = 0; c < NH; ++c) {
                         const long long o = (b * a.save_ch + pass * NH + c) * (long long)g.V + site;
                         float v = fmaf(lo[c], 1.f / kLoScale, hi[c]) * inv_scale;
-                        if (a.act) {
-                            const float h = NFK_LDG(a.act + o);
-                            v *= fmaf(-h, h, 1.f);
-                        }
+                        if (a.act) v *= fmaf(-hv[c], hv[c], 1.f);
                         a.save[o] = v;
                     }
                 } else {
@@ -881,9 +1047,11 @@ void nd_lattice(NdGeom& g, const nfk_lattice& lat) {
 
 // Chooses the tile of a (sample, tile) unit: trailing axes whole, one axis cut into divisors, leading axes one
 // site thick; minimises modelled cycles per output site subject to the shared-memory budget.
-bool nd_plan(NdGeom& g, int N2, int G, int npass, int bdup, uint32_t budget, bool compact = false) {
+bool nd_plan(NdGeom& g, int N2, int G, int npass, int bdup, uint32_t budget, bool compact = false, bool sparse = false) {
     const int r0 = 4 - g.D;
     g.compact = compact ? 1 : 0;
+    g.sparse = sparse ? 1 : 0;
+    const bool odd = compact || sparse;
     { const char* e = getenv("NFK_ND_PREFETCH"); g.prefetch = !(e && e[0] == '0'); }
     g.bdup = bdup;
     g.G = G;
@@ -903,7 +1071,7 @@ bool nd_plan(NdGeom& g, int N2, int G, int npass, int bdup, uint32_t budget, boo
                 c.T[j] = !real ? 1 : (j < split ? 1 : (j == split ? t : g.L[j]));
                 c.ntile[j] = g.L[j] / c.T[j];
                 // compact: every box extent odd (T + 2 for odd T, T + 3 for even T), so that every box stride is odd
-                c.box[j] = real ? c.T[j] + 2 + ((compact && c.T[j] % 2 == 0) ? 1 : 0) : 1;
+                c.box[j] = real ? c.T[j] + 2 + ((odd && c.T[j] % 2 == 0) ? 1 : 0) : 1;
                 c.lo[j] = real ? 1 : 0;
                 c.hi[j] = real ? c.T[j] : 0;
                 outputs *= c.T[j];
@@ -924,13 +1092,14 @@ bool nd_plan(NdGeom& g, int N2, int G, int npass, int bdup, uint32_t budget, boo
                 c.magic_ntile[j] = nd_magic(c.ntile[j]);
             }
             c.last = c.first + c.span - 1;
-            c.nt = compact ? ((c.last - c.first) / 2 + 1 + 127) / 128 : (c.span + 127) / 128;
+            c.nt = odd ? ((c.last - c.first) / 2 + 1 + 127) / 128 : (c.span + 127) / 128;
+            if (sparse) c.nt *= 2;                               // the output positions of box parity 0, then those of parity 1
             c.split = split;
             c.run_rec = c.bstride[split] * c.box[split];
             c.nruns = c.nbox / c.run_rec;
             c.comp_bytes = align((uint32_t)(c.nbox + 128) * 16);
             c.pb_bytes = align((uint32_t)((c.nbox + 1) / 2 + 136) * 16);
-            const uint32_t a_bytes = compact ? 4 * G * c.pb_bytes : 2 * G * c.comp_bytes;
+            const uint32_t a_bytes = sparse ? 2 * G * c.pb_bytes : (compact ? 4 * G * c.pb_bytes : 2 * G * c.comp_bytes);
             uint32_t off = 0;
             if ((long long)a_bytes + c.b_bytes > (long long)budget) continue;
             c.off_a = off; off += a_bytes;
@@ -961,7 +1130,7 @@ bool nd_plan(NdGeom& g, int N2, int G, int npass, int bdup, uint32_t budget, boo
             if (c.nslots > kNdMaxSlots) c.nslots = kNdMaxSlots;
             if (c.nslots < 2) continue;      // (slot -> issuer and slot -> epilogue half are fixed maps: any count works)
             const float eff = (float)outputs / (c.nt * 128.f) * (compact ? 0.5f : 1.f);
-            const float cost = c.taps * G * nd_mma_cycles(N2) / (128.f * eff) + 0.15f * G * (float)c.nbox / outputs +
+            const float cost = (sparse ? 0.5f : 1.f) * c.taps * G * nd_mma_cycles(N2) / (128.f * eff) + 0.15f * G * (float)c.nbox / outputs +
                                2500.f / outputs;
             if (cost < best) { best = cost; bg = c; found = true; }
         }
@@ -1202,7 +1371,7 @@ struct NdDgradPlan {
     long long img_bytes, rec_bytes, total;
 };
 
-int nd_dgrad_plan(NdDgradPlan& p, nfk_lattice lat, int Co, int Ci, long long B) {
+int nd_dgrad_plan(NdDgradPlan& p, nfk_lattice lat, int Co, int Ci, long long B, bool sparse = false) {
     if (!nd_width_ok(Ci) || Co < 1 || Co > 64 || !nd_lattice_ok(lat)) return NFK_EUNSUPPORTED;
     auto al = [](long long v) { return (v + 255) / 256 * 256; };
     p.OC = nd_oc(Ci);
@@ -1211,18 +1380,29 @@ int nd_dgrad_plan(NdDgradPlan& p, nfk_lattice lat, int Co, int Ci, long long B) 
     p.bdup = nd_bdup();
     p.g = NdGeom{};
     nd_lattice(p.g, lat);
-    if (!nd_plan(p.g, 2 * p.OC, p.G, p.npass, p.bdup, (uint32_t)nd_props().max_smem)) return NFK_EUNSUPPORTED;
+    if (!nd_plan(p.g, 2 * p.OC, p.G, p.npass, p.bdup, (uint32_t)nd_props().max_smem, false, sparse)) return NFK_EUNSUPPORTED;
     p.img_bytes = al((long long)p.npass * p.g.taps * p.G * p.bdup * 2 * p.OC * 16);
-    p.rec_bytes = al((B > 0 ? B : 1) * p.G * p.g.Vp * 32LL);
+    p.rec_bytes = sparse ? al((B > 0 ? B : 1) * p.G * 2LL * p.g.Eh * 16LL) : al((B > 0 ? B : 1) * p.G * p.g.Vp * 32LL);
     p.total = 256 + p.img_bytes + p.rec_bytes;
     return NFK_OK;
+}
+
+// the checkerboard-sparse form where it can be planned (NFK_DGRAD_SPARSE=0: never), the dense one otherwise
+int nd_dgrad_plan_for(NdDgradPlan& p, nfk_lattice lat, int Co, int Ci, long long B, int g_parity) {
+    const char* e = getenv("NFK_DGRAD_SPARSE");
+    if (g_parity >= 0 && !(e && e[0] == '0') && nd_dgrad_plan(p, lat, Co, Ci, B, true) == NFK_OK) {
+        p.g.gpar = g_parity & 1;
+        return NFK_OK;
+    }
+    return nd_dgrad_plan(p, lat, Co, Ci, B, false);
 }
 
 }  // namespace
 
 extern "C" int64_t nfk_convnd_dgrad_workspace(nfk_lattice lat, int Co, int Ci, int64_t B) {
-    NdDgradPlan p;
+    NdDgradPlan p, q;
     if (int e = nd_dgrad_plan(p, lat, Co, Ci, B)) return e;
+    if (nd_dgrad_plan(q, lat, Co, Ci, B, true) == NFK_OK && q.total > p.total) return q.total;      // (either form fits)
     return p.total;
 }
 
@@ -1236,25 +1416,27 @@ namespace {
 
 // max |g| -> *amax (device), then g -> padded fp16-pair records scaled by nd_grad_scale(*amax); shared by the data and the
 // weight gradient of a layer
-int nd_pack_gradient(const float* gpre, int Co, const nfk_lattice& lat, const int (&L)[4], const int (&pstride)[4], int V, int Vp,
-                     int64_t B, unsigned* amax, uint4* rec, cudaStream_t st) {
-    const int D = lat.ndim;
+int nd_amax(const float* gpre, long long n, unsigned* amax, cudaStream_t st) {
     if (cudaMemsetAsync(amax, 0, 4, st) != cudaSuccess) return NFK_ECUDA;
-    const long long n = (long long)B * Co * V;
     long long ablocks = (n / 4 + 255) / 256;
     if (ablocks > 148 * 16) ablocks = 148 * 16;
     if (ablocks < 1) ablocks = 1;
     nd_amax_kernel<<<(unsigned)ablocks, 256, 0, st>>>(gpre, n, amax);
-    if (int e = check_launch()) return e;
-    return nd_pack(gpre, Co, reinterpret_cast<const float*>(amax), rec, D, L, pstride, V, Vp, B, st);
+    return check_launch();
+}
+int nd_pack_gradient(const float* gpre, int Co, const nfk_lattice& lat, const int (&L)[4], const int (&pstride)[4], int V, int Vp,
+                     int64_t B, unsigned* amax, uint4* rec, cudaStream_t st) {
+    if (int e = nd_amax(gpre, (long long)B * Co * V, amax, st)) return e;
+    return nd_pack(gpre, Co, reinterpret_cast<const float*>(amax), rec, lat.ndim, L, pstride, V, Vp, B, st);
 }
 
 int nd_dgrad_run(const NdDgradPlan& p, const uint4* rec, const float* amax, const float* w, const float* h, float* gin,
                  int Co, int Ci, int64_t B, __half* img, cudaStream_t st) {
     const NdGeom& g = p.g;
     if (getenv("NFK_ND_DEBUG"))
-        fprintf(stderr, "nfk_convnd_dgrad: T = %d %d %d %d  box %d  tiles/unit %d  G %d  passes %d  chains %d  slots %d  smem %u B\n",
-                g.T[0], g.T[1], g.T[2], g.T[3], g.nbox, g.nt, g.G, g.npass, g.nchunk, g.nslots, g.smem_bytes);
+        fprintf(stderr, "nfk_convnd_dgrad: T = %d %d %d %d  box %d  tiles/unit %d  G %d  passes %d  chains %d  slots %d  smem %u B%s\n",
+                g.T[0], g.T[1], g.T[2], g.T[3], g.nbox, g.nt, g.G, g.npass, g.nchunk, g.nslots, g.smem_bytes,
+                g.sparse ? "  (checkerboard-sparse input)" : "");
     nd_prep_weights_t_kernel<<<64, 256, 0, st>>>(w, Co, Ci, g.taps, p.OC, p.npass, p.bdup, img);
     if (int e = check_launch()) return e;
     NdArgs a{};
@@ -1268,11 +1450,11 @@ int nd_dgrad_run(const NdDgradPlan& p, const uint4* rec, const float* amax, cons
 
 }  // namespace
 
-extern "C" int nfk_convnd_dgrad(const float* gpre, const float* w, const float* h, float* gin, int Co, int Ci,
+extern "C" int nfk_convnd_dgrad(const float* gpre, int g_parity, const float* w, const float* h, float* gin, int Co, int Ci,
                                 nfk_lattice lat, int64_t B, void* workspace, int64_t workspace_bytes, void* stream) {
     if (!gpre || !w || !gin || !workspace) return NFK_EINVAL;
     NdDgradPlan p;
-    if (int e = nd_dgrad_plan(p, lat, Co, Ci, B)) return e;
+    if (int e = nd_dgrad_plan_for(p, lat, Co, Ci, B, g_parity)) return e;
     if (B <= 0) return NFK_OK;
     if (workspace_bytes < p.total || ((uintptr_t)workspace % 256) != 0) return NFK_EINVAL;
     cudaStream_t st = NFK_STREAM(stream);
@@ -1280,8 +1462,14 @@ extern "C" int nfk_convnd_dgrad(const float* gpre, const float* w, const float* 
     unsigned* amax = reinterpret_cast<unsigned*>(wsp);
     __half* img = reinterpret_cast<__half*>(wsp + 256);
     uint4* rec = reinterpret_cast<uint4*>(wsp + 256 + p.img_bytes);
-    if (int e = nd_pack_gradient(gpre, Co, lat, p.g.L, p.g.pstride, p.g.V, p.g.Vp, B, amax, rec, st)) return e;
-    return nd_dgrad_run(p, rec, reinterpret_cast<const float*>(amax), w, h, gin, Co, Ci, B, img, st);
+    const float* am = reinterpret_cast<const float*>(amax);
+    if (p.g.sparse) {
+        if (int e = nd_amax(gpre, (long long)B * Co * p.g.V, amax, st)) return e;
+        if (int e = nd_pack_active(gpre, Co, am, rec, lat.ndim, p.g.L, p.g.estride, p.g.V, p.g.Eh, p.g.gpar, B, st)) return e;
+    } else {
+        if (int e = nd_pack_gradient(gpre, Co, lat, p.g.L, p.g.pstride, p.g.V, p.g.Vp, B, amax, rec, st)) return e;
+    }
+    return nd_dgrad_run(p, rec, am, w, h, gin, Co, Ci, B, img, st);
 }
 
 // ------------------------------------------------------------------------------------------- weight gradient
@@ -1715,17 +1903,23 @@ struct NdLayerBwdPlan {
     NdWgradPlan w;
     long long total;
 };
-int nd_layer_bwd_plan(NdLayerBwdPlan& p, nfk_lattice lat, int Co, int Ci, long long B) {
-    if (int e = nd_dgrad_plan(p.d, lat, Co, Ci, B)) return e;
+// g_parity >= 0: the data gradient takes the checkerboard-sparse form (its own, smaller records); -2: size for either
+int nd_layer_bwd_plan(NdLayerBwdPlan& p, nfk_lattice lat, int Co, int Ci, long long B, int g_parity) {
+    if (int e = nd_dgrad_plan_for(p.d, lat, Co, Ci, B, g_parity == -2 ? -1 : g_parity)) return e;
     if (int e = nd_wgrad_plan(p.w, lat, Co, Ci, B)) return e;
-    p.total = 256 + p.d.img_bytes + p.w.hrec_bytes + p.w.grec_bytes;       // (the gradient's records: same layout for both)
+    // dense gradient records are shared by both kernels; a sparse data gradient reads its own
+    p.total = 256 + p.d.img_bytes + p.w.hrec_bytes + p.w.grec_bytes + (p.d.g.sparse ? p.d.rec_bytes : 0);
+    if (g_parity == -2) {
+        NdDgradPlan q;
+        if (nd_dgrad_plan(q, lat, Co, Ci, B, true) == NFK_OK) p.total += q.rec_bytes;
+    }
     return NFK_OK;
 }
 }  // namespace
 
 extern "C" int64_t nfk_convnd_layer_bwd_workspace(nfk_lattice lat, int Co, int Ci, int64_t B) {
     NdLayerBwdPlan p;
-    if (int e = nd_layer_bwd_plan(p, lat, Co, Ci, B)) return e;
+    if (int e = nd_layer_bwd_plan(p, lat, Co, Ci, B, -2)) return e;
     return p.total;
 }
 
@@ -1733,12 +1927,12 @@ extern "C" int64_t nfk_convnd_layer_bwd_workspace(nfk_lattice lat, int Co, int C
  * into records once for both kernels.  h_in [B][8][V] the layer's input (also the tensor whose tanh' the data gradient is
  * multiplied by when `act_below` != 0), gpre [B][Co][V]; gw / gb accumulated into, gin [B][8][V] written.  Applies where
  * both kernels do (8 input channels, Co <= 32, innermost extent a multiple of 16); NFK_EUNSUPPORTED otherwise.          */
-extern "C" int nfk_convnd_layer_bwd(const float* h_in, const float* gpre, const float* w, int act_below, float* gin,
-                                    float* gw, float* gb, int Co, int Ci, nfk_lattice lat, int64_t B,
+extern "C" int nfk_convnd_layer_bwd(const float* h_in, const float* gpre, int g_parity, const float* w, int act_below,
+                                    float* gin, float* gw, float* gb, int Co, int Ci, nfk_lattice lat, int64_t B,
                                     void* workspace, int64_t workspace_bytes, void* stream) {
     if (!h_in || !gpre || !w || !gin || !gw || !workspace) return NFK_EINVAL;
     NdLayerBwdPlan p;
-    if (int e = nd_layer_bwd_plan(p, lat, Co, Ci, B)) return e;
+    if (int e = nd_layer_bwd_plan(p, lat, Co, Ci, B, g_parity < 0 ? -1 : g_parity)) return e;
     if (B <= 0) return NFK_OK;
     if (workspace_bytes < p.total || ((uintptr_t)workspace % 256) != 0) return NFK_EINVAL;
     cudaStream_t st = NFK_STREAM(stream);
@@ -1752,5 +1946,11 @@ extern "C" int nfk_convnd_layer_bwd(const float* h_in, const float* gpre, const 
     if (int e = nd_pack_gradient(gpre, Co, lat, g.L, g.pstride, g.V, g.Vp, B, amax, grec, st)) return e;
     if (int e = nd_pack(h_in, 8, nullptr, hrec, lat.ndim, g.L, g.pstride, g.V, g.Vp, B, st)) return e;
     if (int e = nd_wgrad_run(p.w, hrec, grec, am, gw, gb, B, st)) return e;
-    return nd_dgrad_run(p.d, grec, am, w, act_below ? h_in : nullptr, gin, Co, Ci, B, img, st);
+    const uint4* drec = grec;
+    if (p.d.g.sparse) {
+        uint4* srec = reinterpret_cast<uint4*>(wsp + 256 + p.d.img_bytes + p.w.hrec_bytes + p.w.grec_bytes);
+        if (int e = nd_pack_active(gpre, Co, am, srec, lat.ndim, p.d.g.L, p.d.g.estride, p.d.g.V, p.d.g.Eh, p.d.g.gpar, B, st)) return e;
+        drec = srec;
+    }
+    return nd_dgrad_run(p.d, drec, am, w, act_below ? h_in : nullptr, gin, Co, Ci, B, img, st);
 }

@@ -335,11 +335,15 @@ def test_layer_backward_in_one_call_equals_the_two_kernels(shape, Co, tanh, monk
     gpre = rnd(B, Co, *shape, scale=1e-4)
     w = rnd(Co, 8, *(3,) * D, scale=0.1)
     act = _C.ACT['tanh'] if tanh else 0
-    both = _ops._conv_layer_bwd_tc(h, gpre, w, act, True, shape, 3)
+    gp = None
+    if Co != 8:                                         # the last layer of a coupling: gradient on one partition
+        gp = Co % 3 % 2
+        gpre = gpre * torch.from_numpy(O.evenodd_mask(shape, parity=gp)).to(DEV)
+    both = _ops._conv_layer_bwd_tc(h, gpre, w, act, True, shape, 3, g_parity=gp)
     assert both is not None
     gw, gb, gin = both
     gw2, gb2 = _ops._conv_weight_grad(h, None, 0, gpre, tuple(w.shape), True, shape, 3)
-    gin2 = _ops._conv_dgrad_tc(gpre, w, h, act, shape, 3)
+    gin2 = _ops._conv_dgrad_tc(gpre, w, h, act, shape, 3, g_parity=gp)
     assert torch.equal(gin, gin2)
     assert torch.allclose(gw, gw2, rtol=1e-5, atol=1e-6 * float(gw2.abs().max()))       # (atomics: summation order differs)
     assert torch.allclose(gb, gb2, rtol=1e-5, atol=1e-6 * float(gb2.abs().max()))
@@ -1094,6 +1098,11 @@ def test_nd_active_only_last_layer_matches_the_full_one(shape, kind, monkeypatch
     ((6, 4, 4, 8), 8, 8, 2, True, 1.0, False),
     ((16, 16), 64, 64, 2, True, 1.0, False),          # two passes of 32 output channels, eight input groups
     ((12, 20), 13, 32, 2, True, 1.0, False),          # Co not a multiple of 8
+    ((64, 64), 28, 8, 3, True, 1e-6, True),           # config-3 geometry, the last layer's gradient
+    ((32, 32, 32), 28, 8, 2, True, 1.0, True),        # config 4
+    ((16, 16, 16, 16), 2, 8, 1, True, 1.0, True),     # config 5, affine
+    ((4, 6, 8), 28, 16, 3, True, 1.0, True),
+    ((2, 2, 2), 4, 8, 3, True, 1.0, True),            # every neighbour is a wrap
 ])
 def test_tensor_core_data_gradient(shape, Co, Ci, B, tanh, gscale, sparse, monkeypatch):
     """nfk_convnd_dgrad (fp16-pair implicit GEMM on transposed, mirrored weights; input scaled by a power of two from
@@ -1108,11 +1117,17 @@ def test_tensor_core_data_gradient(shape, Co, Ci, B, tanh, gscale, sparse, monke
     pre = rnd(B, Ci, *shape)
     h = torch.tanh(pre) if tanh else None
     gpre = rnd(B, Co, *shape) * gscale
+    gp = None
     if sparse:
-        gpre = gpre * torch.from_numpy(O.evenodd_mask(shape, parity=0)).to(DEV)
+        gp = (B + Co) % 2                               # non-zero where the coordinate sum % 2 == gp
+        gpre = gpre * torch.from_numpy(O.evenodd_mask(shape, parity=gp)).to(DEV)
     act = _C.ACT['tanh'] if tanh else 0
-    got = _ops._conv_dgrad_tc(gpre, w, h, act, shape, 3)
+    got = _ops._conv_dgrad_tc(gpre, w, h, act, shape, 3, g_parity=gp)
     assert got is not None
+    if sparse:
+        # the checkerboard-sparse form (half the MMAs, records on one parity plane) against the dense one
+        dense = _ops._conv_dgrad_tc(gpre, w, h, act, shape, 3)
+        assert float((got - dense).abs().max()) <= 2e-6 * float(dense.abs().max())
     ref32 = _ops._conv_call(gpre, w, 1, None, None, 0, 0, h, act, shape, 3, Co, Ci)
     scale = float(ref32.abs().max())
     assert torch.isfinite(got).all()
