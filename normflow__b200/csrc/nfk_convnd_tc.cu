@@ -784,43 +784,63 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                     uint32_t acc = tmem + slot * cols_per_slot;
                     int cnt = 0;
                     uint32_t accf = 0;                                 // sparse: 0 for the first MMA of a chain
-                    for (int o = 0; o < g.ngroups; ++o) {
-                        // offset of the outer taps of this group: o enumerates (k0, k1) of the two outer axes
-                        int od;
-                        if (g.ngroups == 9) od = (o / 3 - 1) * g.bstride[0] + (o % 3 - 1) * g.bstride[1];
-                        else if (g.ngroups == 3) od = (o - 1) * g.bstride[1];
-                        else od = 0;
-                        uint64_t ad = tc::desc_advance(ad0, od);          // (compact: od is taken out again per tap, see below)
-                        uint64_t bdg = bd;
-                        // one compact copy of the nine unrolled taps, looped over the channel groups; a chain is a
-                        // whole number of such steps
+                    if (MODE == 2 && sparse) {
+                        for (int o = 0; o < g.ngroups; ++o) {
+                            int od;
+                            if (g.ngroups == 9) od = (o / 3 - 1) * g.bstride[0] + (o % 3 - 1) * g.bstride[1];
+                            else if (g.ngroups == 3) od = (o - 1) * g.bstride[1];
+                            else od = 0;
+                            uint64_t ad = ad0;
+                            uint64_t bdg = bd;
+                            // (all box strides odd: the parity of a tap's offset is that of its number of unit steps, so the taps
+                            // that land on the populated plane are the five "even" or the four "odd" ones of each group of nine)
+                            const int want = (abox ^ rp ^ od) & 1;
 #pragma unroll 1
-                        for (int gi = 0; gi < G; ++gi) {
+                            for (int gi = 0; gi < G; ++gi) {
 #pragma unroll
-                            for (int i = 0; i < 9; ++i) {
-                                int dl = (i / 3 - 1) * s2 + (i % 3 - 1);
-                                if (MODE == 2 && sparse) {
-                                    // (all box strides odd: the parity of a tap's offset is that of its number of unit steps)
-                                    const int sft = rp + od + dl;
-                                    if (((sft ^ abox) & 1) == 0) {
-                                        tc::mma_f16(acc, tc::desc_advance(ad, (sft >> 1) - od), tc::desc_advance(bdg, i * G * bstep),
+                                for (int i = 0; i < 9; ++i) {
+                                    const int dl = (i / 3 - 1) * s2 + (i % 3 - 1);
+                                    if ((((i / 3) + (i % 3)) & 1) == want) {
+                                        tc::mma_f16(acc, tc::desc_advance(ad, (rp + od + dl) >> 1), tc::desc_advance(bdg, i * G * bstep),
                                                     idesc, accf);
                                         accf = 1u;
                                     }
-                                    continue;
                                 }
-                                if (g.compact) {
-                                    const int sft = pib + od + dl;
-                                    dl = (sft >> 1) + (sft & 1) * pbrec - od;       // (`ad` already carries od)
-                                }
-                                tc::mma_f16(acc, tc::desc_advance(ad, dl), tc::desc_advance(bdg, i * G * bstep), idesc,
-                                            (cnt | i) != 0);
+                                if (++cnt == chain_len) { cnt = 0; acc += N2; accf = 0; }
+                                ad = tc::desc_advance(ad, gstep);
+                                bdg = tc::desc_advance(bdg, bstep);
                             }
-                            if (++cnt == chain_len) { cnt = 0; acc += N2; accf = 0; }
-                            ad = tc::desc_advance(ad, gstep);
-                            bdg = tc::desc_advance(bdg, bstep);
+                            bd = tc::desc_advance(bd, 9 * G * bstep);
                         }
-                        bd = tc::desc_advance(bd, 9 * G * bstep);
+                    } else {
+                        for (int o = 0; o < g.ngroups; ++o) {
+                            // offset of the outer taps of this group: o enumerates (k0, k1) of the two outer axes
+                            int od;
+                            if (g.ngroups == 9) od = (o / 3 - 1) * g.bstride[0] + (o % 3 - 1) * g.bstride[1];
+                            else if (g.ngroups == 3) od = (o - 1) * g.bstride[1];
+                            else od = 0;
+                            uint64_t ad = tc::desc_advance(ad0, od);          // (compact: od is taken out again per tap, see below)
+                            uint64_t bdg = bd;
+                            // one compact copy of the nine unrolled taps, looped over the channel groups; a chain is a
+                            // whole number of such steps
+#pragma unroll 1
+                            for (int gi = 0; gi < G; ++gi) {
+#pragma unroll
+                                for (int i = 0; i < 9; ++i) {
+                                    int dl = (i / 3 - 1) * s2 + (i % 3 - 1);
+                                    if (g.compact) {
+                                        const int sft = pib + od + dl;
+                                        dl = (sft >> 1) + (sft & 1) * pbrec - od;       // (`ad` already carries od)
+                                    }
+                                    tc::mma_f16(acc, tc::desc_advance(ad, dl), tc::desc_advance(bdg, i * G * bstep), idesc,
+                                                (cnt | i) != 0);
+                                }
+                                if (++cnt == chain_len) { cnt = 0; acc += N2; }
+                                ad = tc::desc_advance(ad, gstep);
+                                bdg = tc::desc_advance(bdg, bstep);
+                            }
+                            bd = tc::desc_advance(bd, 9 * G * bstep);
+                        }
                     }
                     tc::mma_commit(tc::smem_u32(full + slot));
                     if (++slot == nslots) { slot = 0; ring_phase ^= 1u; }

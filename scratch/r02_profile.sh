@@ -26,4 +26,9 @@ ncu --set full --clock-control none --import-source on -k regex:"convnd_wgrad_tc
     python scratch/bwd_ops.py 32x32x32 64 28 > /dev/null 2>&1
 (python scratch/nd_train_time.py 4 64; python scratch/nd_train_time.py 5 16; NFK_DGRAD_TC=0 NFK_WGRAD_ND_TC=0 python scratch/nd_train_time.py 4 64; \
  NFK_DGRAD_TC=0 NFK_WGRAD_ND_TC=0 python scratch/nd_train_time.py 5 16) > gpurun_out/r02_nd_train_times.log 2>&1
-ls -la gpurun_out/*.ncu-rep
+# summaries stay, the reports (80 MB) do not: gpurun copies at most 64 MiB back
+for n in nd3d nd4d rqs_fwd prior bwd3d; do
+    python scratch/ncu_brief.py gpurun_out/r02_$n.ncu-rep > gpurun_out/r02_${n}_ncu_full.txt 2>/dev/null
+    rm -f gpurun_out/r02_$n.ncu-rep
+done
+ls -la gpurun_out/
