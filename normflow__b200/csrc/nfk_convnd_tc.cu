@@ -546,6 +546,23 @@ __device__ __forceinline__ void nd_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
 }
 
+// The nine taps of one (outer tap group, channel group) step of the ACTIVE-SITES-ONLY last layer; WANT = parity of the
+// step's base offset.  `ad` already points at row shift bh of plane 0.
+template <int WANT>
+__device__ __forceinline__ void nd_issue9_compact(uint32_t acc, uint64_t ad, uint64_t bdg, int h2, int pbrec, int tap_step,
+                                                  uint32_t idesc, int cnt) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        constexpr int kNone = 0;
+        const int dy = i / 3 - 1, dx = i % 3 - 1;
+        const int e = WANT + dy + dx;                         // in [-2, 3]
+        const int sh = (e + 4) / 2 - 2 + kNone;               // floor(e / 2)
+        const int pl = (e + 4) & 1;
+        const int dl = dy * h2 + sh + pl * pbrec;
+        tc::mma_f16(acc, tc::desc_advance(ad, dl), tc::desc_advance(bdg, i * tap_step), idesc, (cnt | i) != 0);
+    }
+}
+
 // MODE 0: hidden layer (H -> OC of the H output channels per pass, tanh) -> records; the template argument K
 // carries OC (8, 16 or 32).  MODE 1: last layer (H -> P) + transform of the field.  MODE 2: data gradient of a layer
 // (records of d loss / d pre-activation, transposed mirrored weights) -> float32 [B][Ci][V], times 1 - h^2.
@@ -560,6 +577,9 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
     extern __shared__ __align__(128) uint8_t smem[];
     const NdGeom& g = a.g;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // only the last layer reads parity-split records: for the other modes the per-tap test in the MMA issue loop compiles
+    // away (a predicated branch per MMA on the issuing thread is measurable: see the sparse data gradient)
+    const bool kcompact = MODE == 1 && g.compact;
 
     uint8_t* A = smem + g.off_a;
     uint8_t* Bs = smem + g.off_b;
@@ -625,7 +645,7 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
             const uint32_t b_base = tc::smem_u32(Bs);
             // (compact: the hi -> lo distance is two parity planes; plane 1 follows plane 0)
             const bool sparse = MODE == 2 && g.sparse;
-            const uint64_t a_desc = tc::make_desc(a_base, sparse ? g.pb_bytes : (g.compact ? 2u * g.pb_bytes : g.comp_bytes), 128);
+            const uint64_t a_desc = tc::make_desc(a_base, sparse ? g.pb_bytes : (kcompact ? 2u * g.pb_bytes : g.comp_bytes), 128);
             const int pbrec = (int)(g.pb_bytes >> 4);
             const uint64_t b_desc = tc::make_desc(b_base, g.bdup == 2 ? N2 * 16 : 0, 128);
             const uint32_t idesc = tc::make_idesc(0, 128, N2);
@@ -634,7 +654,7 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
             // steps (nine taps of one channel group) per accumulation chain
             const int chain_len = (g.ngroups * G + g.nchunk - 1) / g.nchunk;
             const int bstep = g.bdup * N2;                           // B rows per (tap, channel group)
-            const int gstep = (int)((sparse ? 2 * g.pb_bytes : (g.compact ? 4 * g.pb_bytes : 2 * g.comp_bytes)) >> 4);   // records between two channel groups' planes
+            const int gstep = (int)((sparse ? 2 * g.pb_bytes : (kcompact ? 4 * g.pb_bytes : 2 * g.comp_bytes)) >> 4);   // records between two channel groups' planes
             int slot = 0;
             uint32_t ring_phase = 0, load_phase = 0;
             int last_slot[kNdIssuers], cur_pass = -1;                // last tile of every issuer in the previous unit
@@ -656,7 +676,7 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                         if (last_slot[w] >= 0) tc::mbar_wait(tc::smem_u32(full + last_slot[w]), last_phase[w]);
                     const uint32_t run_bytes = (uint32_t)g.run_rec * 16;
                     uint32_t tx = sparse ? 2u * G * (uint32_t)((g.nbox + 1 - abox) >> 1) * 16u
-                                         : (g.compact ? 2u * G * (uint32_t)g.nbox * 16u : 2u * G * g.nruns * run_bytes);
+                                         : (kcompact ? 2u * G * (uint32_t)g.nbox * 16u : 2u * G * g.nruns * run_bytes);
                     if (pass != cur_pass) tx += g.b_bytes;
                     nd_expect_tx(loaded_bar, tx);
                     if (pass != cur_pass) {
@@ -668,7 +688,7 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                         int rem = k, so = 0;
 #pragma unroll
                         for (int d = 3; d >= 0; --d) {
-                            const int st = (g.compact || sparse) ? g.estride[d] : g.pstride[d];
+                            const int st = (kcompact || sparse) ? g.estride[d] : g.pstride[d];
                             if (d < g.split) {
                                 const int q = nd_div(rem, g.box[d], g.magic_box[d]);
                                 so += (org[d] + rem - q * g.box[d]) * st;
@@ -691,7 +711,7 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                                     nd_bulk_load(dst + g.pb_bytes, src + g.Eh, n * 16, loaded_bar);
                                 }
                             }
-                        } else if (!g.compact) {
+                        } else if (!kcompact) {
                             for (int gi = 0; gi < G; ++gi) {
                                 const uint4* src = a.in_rec + (b * G + gi) * 2LL * g.Vp + so;
                                 const uint32_t dst = a_base + (uint32_t)gi * 2u * g.comp_bytes + k * run_bytes;
@@ -726,7 +746,7 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                         int rem = k, so = 0;
 #pragma unroll
                         for (int d = 3; d >= 0; --d) {
-                            const int st = (g.compact || sparse) ? g.estride[d] : g.pstride[d];
+                            const int st = (kcompact || sparse) ? g.estride[d] : g.pstride[d];
                             if (d < g.split) {
                                 const int q = nd_div(rem, g.box[d], g.magic_box[d]);
                                 so += (norg[d] + rem - q * g.box[d]) * st;
@@ -741,7 +761,7 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                                 const uint32_t n16 = (uint32_t)((g.run_rec + 1) >> 1) * 16;
                                 nd_prefetch_l2(src, n16);
                                 nd_prefetch_l2(src + g.Eh, n16);
-                            } else if (!g.compact) {
+                            } else if (!kcompact) {
                                 const uint4* src = a.in_rec + (nb * G + gi) * 2LL * g.Vp + so;
                                 nd_prefetch_l2(src, (uint32_t)g.run_rec * 16);
                                 nd_prefetch_l2(src + g.Vp, (uint32_t)g.run_rec * 16);
@@ -779,7 +799,7 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                     const int rp = sparse ? (m >= (g.nt >> 1) ? 1 : 0) : 0;
                     const int ms = sparse ? m - rp * (g.nt >> 1) : m;
                     const int cfs = (g.first + ((rp ^ g.first) & 1)) >> 1;
-                    const uint64_t ad0 = tc::desc_advance(a_desc, (sparse ? cfs : (g.compact ? cfirst : g.first)) + ms * 128);
+                    const uint64_t ad0 = tc::desc_advance(a_desc, (sparse ? cfs : (kcompact ? cfirst : g.first)) + ms * 128);
                     uint64_t bd = b_desc;
                     uint32_t acc = tmem + slot * cols_per_slot;
                     int cnt = 0;
@@ -819,25 +839,40 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                             if (g.ngroups == 9) od = (o / 3 - 1) * g.bstride[0] + (o % 3 - 1) * g.bstride[1];
                             else if (g.ngroups == 3) od = (o - 1) * g.bstride[1];
                             else od = 0;
-                            uint64_t ad = tc::desc_advance(ad0, od);          // (compact: od is taken out again per tap, see below)
+                            uint64_t ad = tc::desc_advance(ad0, od);
                             uint64_t bdg = bd;
                             // one compact copy of the nine unrolled taps, looped over the channel groups; a chain is a
                             // whole number of such steps
+                            if (kcompact) {
+                                // Active rows only: tap (dy, dx) of this group reads parity plane (base + dy s2 + dx) & 1 at row
+                                // shift (base + dy s2 + dx) >> 1, base = pib + od.  s2 is odd (= 2 h2 + 1), so with base =
+                                // 2 bh + want the shift is bh + dy h2 + ((want + dy + dx) >> 1) and the plane (want + dy + dx) & 1:
+                                // compile-time constants per tap once `want` is known -- nothing per MMA on the issuing thread
+                                // but the descriptor add.
+                                const int base = pib + od, want = base & 1, bh = base >> 1, h2 = s2 >> 1;
+                                const uint64_t adc = tc::desc_advance(ad0, bh);
+                                uint64_t adg = adc;
 #pragma unroll 1
-                            for (int gi = 0; gi < G; ++gi) {
-#pragma unroll
-                                for (int i = 0; i < 9; ++i) {
-                                    int dl = (i / 3 - 1) * s2 + (i % 3 - 1);
-                                    if (g.compact) {
-                                        const int sft = pib + od + dl;
-                                        dl = (sft >> 1) + (sft & 1) * pbrec - od;       // (`ad` already carries od)
-                                    }
-                                    tc::mma_f16(acc, tc::desc_advance(ad, dl), tc::desc_advance(bdg, i * G * bstep), idesc,
-                                                (cnt | i) != 0);
+                                for (int gi = 0; gi < G; ++gi) {
+                                    if (want) nd_issue9_compact<1>(acc, adg, bdg, h2, pbrec, G * bstep, idesc, cnt);
+                                    else nd_issue9_compact<0>(acc, adg, bdg, h2, pbrec, G * bstep, idesc, cnt);
+                                    if (++cnt == chain_len) { cnt = 0; acc += N2; }
+                                    adg = tc::desc_advance(adg, gstep);
+                                    bdg = tc::desc_advance(bdg, bstep);
                                 }
-                                if (++cnt == chain_len) { cnt = 0; acc += N2; }
-                                ad = tc::desc_advance(ad, gstep);
-                                bdg = tc::desc_advance(bdg, bstep);
+                            } else {
+#pragma unroll 1
+                                for (int gi = 0; gi < G; ++gi) {
+#pragma unroll
+                                    for (int i = 0; i < 9; ++i) {
+                                        const int dl = (i / 3 - 1) * s2 + (i % 3 - 1);
+                                        tc::mma_f16(acc, tc::desc_advance(ad, dl), tc::desc_advance(bdg, i * G * bstep), idesc,
+                                                    (cnt | i) != 0);
+                                    }
+                                    if (++cnt == chain_len) { cnt = 0; acc += N2; }
+                                    ad = tc::desc_advance(ad, gstep);
+                                    bdg = tc::desc_advance(bdg, bstep);
+                                }
                             }
                             bd = tc::desc_advance(bd, 9 * G * bstep);
                         }
@@ -942,7 +977,7 @@ __global__ void __launch_bounds__(kNdThreads, 1) convnd_tc_kernel(const NdArgs a
                     const int cfs = (g.first + ((rp ^ g.first) & 1)) >> 1;
                     rem = 2 * (cfs + (r - rp * (g.nt >> 1) * 128)) + rp;
                     if (rem > g.last) continue;
-                } else if (g.compact) {
+                } else if (kcompact) {
                     rem = 2 * (cfirst + r) + pib;
                     if (rem > g.last) continue;
                 } else {
