@@ -49,6 +49,24 @@ def test_library_exports_every_declared_symbol():
     assert handle.nfk_strerror(0) == b"ok" and b"unsupported" in handle.nfk_strerror(-2)
 
 
+def test_ctypes_signatures_have_the_header_arity():
+    """Every prototype of include/normflow_b200.h against the argtypes the Python side binds: a drifted argument list
+    would corrupt the call frame silently (the GPU tests would only show it as wrong numbers or a fault)."""
+    text = open(os.path.join(ROOT, "include", "normflow_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = re.findall(r"\b(?:int|int64_t|uint64_t|void|const char\*)\s+\*?(nfk_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S)
+    assert len(protos) == len(_header_symbols())
+    checked = 0
+    for name, args in protos:
+        args = args.strip()
+        n = 0 if args in ("", "void") else args.count(",") + 1
+        sig = _C._SIGNATURES.get(name)
+        if sig is not None:
+            assert len(sig) == n, f"{name}: header has {n} parameters, _C._SIGNATURES {len(sig)}"
+            checked += 1
+    assert checked == len(_C._SIGNATURES)
+
+
 def test_library_is_sm100a_only():
     out = subprocess.run(["cuobjdump", "--list-elf", _C.LIB_PATH], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_\d+a?", out))
